@@ -1,0 +1,259 @@
+/*
+ * gpx.h — C ABI of the B200 physics-tick / ray-query backend (libgpx.so).
+ *
+ * This is the boundary the engine's physics wrapper binds instead of joltc.  Plain C: opaque handle,
+ * POD structs, pointers + sizes, int error codes; no C++ or torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree).
+ *
+ * One `gpx_world` is an ENSEMBLE of `worlds` independent world instances that share one static map
+ * (collision triangles + LBVH).  The engine uses worlds == 1; parameter sweeps use thousands.
+ * There is no CPU path: every call that computes launches sm_100a kernels and fails with
+ * GPX_ERR_CUDA if the device is unusable.
+ */
+#ifndef GPX_H
+#define GPX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPX_ABI_VERSION 1
+
+/* ---- error codes.  0..4 mirror JPH_PhysicsUpdateError as consumed at engine/src/physics/MapPhysics.c:105-113
+ *      (non-zero is fatal in the engine). */
+enum gpx_error
+{
+	GPX_OK = 0,
+	GPX_ERR_MANIFOLD_CACHE_FULL = 1,
+	GPX_ERR_BODY_PAIR_CACHE_FULL = 2,
+	GPX_ERR_CONTACT_CONSTRAINTS_FULL = 4,
+	GPX_ERR_INVALID_ARG = 16,
+	GPX_ERR_CAPACITY = 17,
+	GPX_ERR_CUDA = 32,
+};
+
+/* ---- enums with the reference's values */
+enum gpx_motion_type /* JPH_MotionType */
+{
+	GPX_MOTION_STATIC = 0,
+	GPX_MOTION_KINEMATIC = 1,
+	GPX_MOTION_DYNAMIC = 2,
+};
+
+enum gpx_object_layer /* engine/include/engine/physics/Physics.h:36-42 */
+{
+	GPX_LAYER_STATIC = 0,
+	GPX_LAYER_DYNAMIC = 1,
+	GPX_LAYER_PLAYER = 2,
+	GPX_LAYER_SENSOR = 3,
+};
+
+enum gpx_shape_type /* shape vocabulary of SURVEY §8 row a12 */
+{
+	GPX_SHAPE_EMPTY = 0,  /* JPH_EmptyShapeSettings_Create  (Actor.c:153, Laser.c:114) */
+	GPX_SHAPE_BOX = 1,    /* JPH_BoxShape_Create            (ModelLoader.c:152, Trigger.c:37, Coin.c:43) */
+	GPX_SHAPE_SPHERE = 2, /* hull recognised as a sphere    (orb.gmdl, ModelLoader.c:330) */
+};
+
+enum gpx_allowed_dofs /* JPH_AllowedDOFs (TestActor.c:42-46) */
+{
+	GPX_DOF_TX = 1, GPX_DOF_TY = 2, GPX_DOF_TZ = 4,
+	GPX_DOF_RX = 8, GPX_DOF_RY = 16, GPX_DOF_RZ = 32,
+	GPX_DOF_ALL = 63,
+};
+
+/* Ray layer masks: bit i = object layer i accepted.  Replaces the BroadPhaseLayerFilter/ObjectLayerFilter callback
+ * pairs, which in the reference are pure functions of the layer (PlayerPhysics.c:55-77, Laser.c:40-72). */
+#define GPX_RAYMASK_STATIC (1u << GPX_LAYER_STATIC)
+#define GPX_RAYMASK_STATIC_DYNAMIC ((1u << GPX_LAYER_STATIC) | (1u << GPX_LAYER_DYNAMIC))
+/* Extra ray flag: only hit bodies whose `ray_flags` has GPX_BODY_BLOCKS_LASERS (the laser BodyFilter, Laser.c:74-85). */
+#define GPX_RAYMASK_REQUIRE_BLOCKS_LASERS (1u << 8)
+
+#define GPX_BODY_BLOCKS_LASERS 1u /* "no actor, or actor->flags has ACTOR_FLAG_CAN_BLOCK_LASERS" evaluated at create time */
+
+#define GPX_INVALID_BODY 0xFFFFFFFFu /* JPH_BodyId_InvalidBodyID */
+#define GPX_INVALID_FACE 0xFFFFFFFFu
+
+typedef struct gpx_world gpx_world;
+
+/* JPH_PhysicsSystemSettings (engine/src/physics/Physics.c:89-100) + the Jolt defaults the tick uses */
+typedef struct gpx_world_config
+{
+	uint32_t worlds;                  /* number of independent world instances sharing the static map */
+	uint32_t max_bodies_per_world;    /* non-static-mesh body slots per world (<= 64) */
+	uint32_t max_manifolds_per_world; /* contact manifolds per world and sub-step; 0 = default */
+	uint32_t max_static_triangles;    /* capacity of the shared static triangle soup */
+	float gravity[3];                 /* JPH_PhysicsSystem_SetGravity (Physics.c:99) */
+	int32_t device;                   /* CUDA device ordinal */
+	uint32_t velocity_steps;          /* 0 = 10 */
+	uint32_t position_steps;          /* 0 = 2  */
+	uint32_t flags;                   /* reserved, 0 */
+} gpx_world_config;
+
+/* JPH_BodyCreationSettings as the reference fills it (Create2_GAME + setters) */
+typedef struct gpx_body_desc
+{
+	uint32_t shape;          /* gpx_shape_type */
+	float half_extents[3];   /* box half extents; sphere: x = radius */
+	float convex_radius;     /* carried for parity with JPH_BoxShape_Create(.., r); contacts use the full extents */
+	float position[3];
+	float rotation[4];       /* x y z w */
+	float linear_velocity[3];
+	float angular_velocity[3];
+	uint32_t motion_type;    /* gpx_motion_type */
+	uint32_t layer;          /* gpx_object_layer */
+	float mass;              /* > 0: SetMassPropertiesOverride + CalculateInertia (Physbox.c:27-32); 0: density 1000 */
+	float friction;          /* Jolt default 0.2; map geometry 4.25 (MapLoader.c:263) */
+	float restitution;       /* Jolt default 0 */
+	float linear_damping;    /* Jolt default 0.05 */
+	float angular_damping;   /* Jolt default 0.05 */
+	float gravity_factor;    /* Jolt default 1 */
+	uint32_t is_sensor;      /* JPH_BodyCreationSettings_SetIsSensor (Trigger.c:44) */
+	uint32_t allowed_dofs;   /* gpx_allowed_dofs; 0 = all */
+	uint32_t allow_sleeping; /* Jolt default 1 */
+	uint32_t ray_flags;      /* GPX_BODY_* */
+	uint64_t user_data;      /* Actor* */
+} gpx_body_desc;
+
+/* Transform (joltc/Math/Transform.h as used at PlayerPhysics.c:305, Actor.c:32) */
+typedef struct gpx_transform
+{
+	float position[3];
+	float rotation[4];
+} gpx_transform;
+
+typedef struct gpx_ray /* 32 B */
+{
+	float origin[3];
+	float tmax;      /* maxDistance: 10 (PlayerPhysics.c:24,305) or 50 (Laser.c:110) */
+	float dir[3];    /* unit direction */
+	uint32_t mask;   /* GPX_RAYMASK_*; high 16 bits = world index */
+} gpx_ray;
+
+typedef struct gpx_hit /* 16 B — JPH_RayCastResult {bodyID, fraction, subShapeID2} */
+{
+	float fraction;  /* t / tmax in [0,1]; 2.0f on miss */
+	uint32_t body;   /* body id, GPX_INVALID_BODY on miss */
+	uint32_t face;   /* canonical face id: index of the triangle in upload order; box face 0..5; sphere 0 */
+	uint32_t world;  /* world index the ray ran in */
+} gpx_hit;
+
+typedef struct gpx_world_stats /* 32 B, gathered across GPUs at the end of a run */
+{
+	float kinetic_energy;
+	float max_speed;
+	uint32_t awake_bodies;
+	uint32_t manifolds;
+	uint64_t position_checksum;
+	uint32_t ticks;
+	uint32_t error;
+} gpx_world_stats;
+
+typedef struct gpx_contact_event /* body<->sensor / body<->body begin/persist/end (PlayerPhysics.c:89-152 analogue) */
+{
+	uint32_t world;
+	uint32_t body_a;
+	uint32_t body_b;
+	uint32_t kind; /* 0 added, 1 persisted, 2 removed */
+} gpx_contact_event;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+
+/* JPH_Init (Physics.c:75).  Returns GPX_ABI_VERSION on success, negative gpx_error otherwise. */
+int gpx_init(int device);
+/* JPH_Shutdown (Physics.c:86) */
+void gpx_shutdown(void);
+/* Last CUDA/driver error string for this thread ("" if none). */
+const char *gpx_last_error(void);
+
+/* JPH_PhysicsSystem_Create + SetGravity (Physics.c:89-100) */
+gpx_world *gpx_world_create(const gpx_world_config *cfg);
+/* JPH_PhysicsSystem_Destroy (Physics.c:105) */
+void gpx_world_destroy(gpx_world *w);
+
+/* ---- static map geometry ------------------------------------------------------------------------------------ */
+
+/* One collision mesh = one static body: MeshShape -> StaticCompound -> CreateAndAddBody(Static, LAYER_STATIC)
+ * (MapLoader.c:206-271; static model actors StaticModel.c:21-72).  `tris` = ntris*9 floats relative to `xfm`.
+ * Shared by every world of the ensemble.  Returns the static body id in *out_body. */
+int gpx_static_add_mesh(gpx_world *w, const gpx_transform *xfm, const float *tris, uint64_t ntris, float friction,
+						uint64_t user_data, uint32_t *out_body);
+/* JPH_PhysicsSystem_OptimizeBroadPhase (MapLoader.c:273): uploads the soup and (re)builds the LBVH on device. */
+int gpx_static_commit(gpx_world *w);
+/* Parse a decompressed .gmap collision section straight into the static soup (MapLoader.c:200-273).
+ * `body` points at the whole decompressed map; returns number of static bodies added or negative error. */
+int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size);
+
+/* ---- bodies --------------------------------------------------------------------------------------------------- */
+
+/* JPH_BodyInterface_CreateAndAddBody (17 call sites).  Returns body id or GPX_INVALID_BODY. */
+uint32_t gpx_body_create(gpx_world *w, uint32_t world, const gpx_body_desc *desc);
+/* Same body list instantiated in every world; per-world initial velocities optional
+ * (`linvel`/`angvel` = worlds*count*3 floats or NULL).  `out_ids` (count) receives the ids, equal in all worlds. */
+int gpx_body_create_all(gpx_world *w, const gpx_body_desc *descs, uint32_t count, const float *linvel,
+						const float *angvel, uint32_t *out_ids);
+/* JPH_BodyInterface_RemoveAndDestroyBody (Actor.c:68, Map.c:113, Door.c:207) */
+int gpx_body_destroy(gpx_world *w, uint32_t world, uint32_t body);
+
+/* Setters, applied at the start of the next step (Door.c:59-96, PlayerPhysics.c:377-384, ActorWall.c:70) */
+int gpx_body_set_linear_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3]);
+int gpx_body_set_linear_and_angular_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3],
+											 const float av[3]);
+int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int activate);
+int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int activate);
+
+/* Getters served from the host mirror refreshed by gpx_sync_transforms (rows a9: GetPosition/Rotation/
+ * PositionAndRotation/WorldTransform/UserData) */
+int gpx_body_get_transform(const gpx_world *w, uint32_t world, uint32_t body, gpx_transform *out);
+int gpx_body_get_world_matrix(const gpx_world *w, uint32_t world, uint32_t body, float out_mat4[16]);
+int gpx_body_get_velocity(const gpx_world *w, uint32_t world, uint32_t body, float v[3], float av[3]);
+uint64_t gpx_body_get_user_data(const gpx_world *w, uint32_t world, uint32_t body);
+int gpx_body_is_active(const gpx_world *w, uint32_t world, uint32_t body);
+
+/* ---- the tick ---------------------------------------------------------------------------------------------------- */
+
+/* JPH_PhysicsSystem_Update(system, dt, collisionSteps, jobSystem) (MapPhysics.c:105-108).
+ * Asynchronous on the world's stream; returns the error of the PREVIOUS completed step merged with launch errors.
+ * gpx_sync_* waits. */
+int gpx_step(gpx_world *w, float dt, int collision_steps);
+/* Wait for the stream; D2H the transform mirror (pinned) so getters are wait-free.  Returns the tick's error code. */
+int gpx_sync_transforms(gpx_world *w);
+/* Bulk readback: worlds*max_bodies transforms (28 B each) / velocities (24 B each) into caller memory. */
+int gpx_read_transforms(gpx_world *w, gpx_transform *out, uint64_t capacity);
+int gpx_read_velocities(gpx_world *w, float *out_lin_ang6, uint64_t capacity);
+/* Per-world stats computed on device, `out` has `worlds` entries (host). */
+int gpx_read_stats(gpx_world *w, gpx_world_stats *out);
+/* Contact events of the last step (sensor overlaps and body pairs that touch). Returns count or negative error. */
+int64_t gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity);
+
+/* ---- ray queries -------------------------------------------------------------------------------------------------- */
+
+/* Batched closest-hit rays (JPH_NarrowPhaseQuery_CastRay_GAME / CastRay2_GAME; PlayerPhysics.c:305, Laser.c:142).
+ * Host buffers; copies are part of the call. */
+int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits);
+/* Same with device-resident buffers (cudaMalloc'd by the caller or by gpx_device_alloc), async on the world's stream. */
+int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
+/* Engine-style single ray: origin transform, direction = transform's local -Z. */
+int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *origin, float max_distance, uint32_t mask,
+						  gpx_hit *out);
+
+/* ---- device helpers for harnesses --------------------------------------------------------------------------------- */
+void *gpx_device_alloc(uint64_t bytes);
+void gpx_device_free(void *p);
+int gpx_memcpy_h2d(void *dst, const void *src, uint64_t bytes);
+int gpx_memcpy_d2h(void *dst, const void *src, uint64_t bytes);
+int gpx_device_sync(gpx_world *w);
+/* cudaEvent timing on the world's stream: begin/end bracket, returns elapsed ms of the last bracket. */
+int gpx_timer_begin(gpx_world *w);
+float gpx_timer_end(gpx_world *w);
+/* Number of kernels this library launched since gpx_init (for bench.py's gpu_launches). */
+uint64_t gpx_launch_count(void);
+/* Static LBVH introspection for tests: node count and triangle count after commit. */
+int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *n_bodies);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPX_H */

@@ -1,0 +1,1415 @@
+/* orc.c — CPU oracle (TEST INFRASTRUCTURE ONLY; header comment in orc.h states scope, sources and "parity unpinned").
+ *
+ * Structure of one sub-step (restating Jolt's published PhysicsSystem::Update step as the reference invokes it with
+ * collisionSteps = 2, engine/src/physics/MapPhysics.c:105-108):
+ *   1 apply gravity + damping, clamp velocities            (dynamic bodies)
+ *   2 find contacts: all-pairs AABB + brute-force triangle loop, SAT + supporting-face clipping, <=4 points
+ *   3 carry impulses from the previous sub-step's manifolds (warm start)
+ *   4 colour manifolds greedily in canonical order; solve in (colour, index) order
+ *   5 velocity_steps x (friction, then non-penetration)    sequential impulses
+ *   6 integrate positions / rotations
+ *   7 position_steps x Baumgarte position correction
+ */
+#include "orc.h"
+#include "orc_math.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* ---- constants (Jolt PhysicsSettings defaults, SURVEY §8c "upstream, unverified") */
+#define SPECULATIVE_DISTANCE 0.02f
+#define PENETRATION_SLOP 0.02f
+#define BAUMGARTE 0.2f
+#define MAX_PENETRATION_DISTANCE 0.2f
+#define MAX_LINEAR_VELOCITY 500.0f
+#define MAX_ANGULAR_VELOCITY 47.1238898f /* 0.25 * pi * 60 */
+#define MIN_VELOCITY_FOR_RESTITUTION 1.0f
+#define NORMAL_COS_MAX_DELTA 0.99619470f /* cos 5 deg: manifolds of one body pair merge below this angle */
+#define PRESERVE_LAMBDA_MAX_DIST_SQ 1.0e-4f
+#define FACE_AXIS_TOL 1.0e-4f
+#define EDGE_AXIS_TOL 2.0e-3f
+#define RAY_MISS_FRACTION 2.0f
+#define MAX_POLY 16
+#define MAX_SLOTS 4 /* manifolds per (body, static body) pair */
+
+typedef struct
+{
+	int alive;
+	uint32_t shape;
+	v3 he;
+	v3 x;
+	q4 q;
+	v3 v, w;
+	uint32_t motion, layer;
+	float inv_mass;
+	v3 inv_inertia; /* local diagonal */
+	float friction, restitution, lin_damp, ang_damp, grav_factor;
+	uint32_t sensor, dofs, allow_sleep, ray_flags;
+	uint64_t user_data;
+} body_t;
+
+typedef struct
+{
+	uint32_t a, b; /* a: slot body (dynamic side); b: slot body or ORC_STATIC_BODY_BASE + k */
+	v3 n;          /* world normal, a -> b */
+	float depth;   /* deepest penetration seen when merging */
+	int np;
+	v3 p1l[4], p2l[4]; /* contact points in the local frames of a and b (static: world) */
+	float ln[4], lt1[4], lt2[4];
+	/* solver scratch */
+	float friction, restitution;
+	v3 t1, t2;
+	float bias[4];
+	/* per point, per axis (0 normal, 1 tangent1, 2 tangent2): lever arm cross axis, I^-1 applied, effective mass */
+	v3 r1xa[4][3], r2xa[4][3], i1[4][3], i2[4][3];
+	float em[4][3];
+	int colour;
+} manifold_t;
+
+typedef struct
+{
+	v3 v0, e1, e2; /* world space */
+	v3 n;          /* unit normal */
+	v3 lo, hi;
+	uint32_t body; /* static body index k */
+} tri_t;
+
+typedef struct
+{
+	float friction;
+	uint32_t ray_flags;
+	uint32_t first, count;
+} sbody_t;
+
+struct orc_world
+{
+	uint32_t max_bodies, max_manifolds, vel_steps, pos_steps;
+	v3 gravity;
+	body_t *bodies;
+	tri_t *tris;
+	uint32_t ntris, cap_tris;
+	sbody_t *sbodies;
+	uint32_t nsbodies, cap_sbodies;
+	manifold_t *man, *prev;
+	uint32_t nman, nprev;
+	uint32_t *order;
+};
+
+/* ------------------------------------------------------------------------------------------ world management */
+
+orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const float gravity[3], uint32_t vs,
+							uint32_t ps)
+{
+	orc_world *w = (orc_world *)calloc(1, sizeof(orc_world));
+	w->max_bodies = max_bodies;
+	w->max_manifolds = max_manifolds ? max_manifolds : max_bodies * 8u;
+	w->vel_steps = vs ? vs : 10u;
+	w->pos_steps = ps ? ps : 2u;
+	w->gravity = V(gravity[0], gravity[1], gravity[2]);
+	w->bodies = (body_t *)calloc(max_bodies, sizeof(body_t));
+	w->man = (manifold_t *)calloc(w->max_manifolds, sizeof(manifold_t));
+	w->prev = (manifold_t *)calloc(w->max_manifolds, sizeof(manifold_t));
+	w->order = (uint32_t *)calloc(w->max_manifolds, sizeof(uint32_t));
+	return w;
+}
+
+void orc_world_destroy(orc_world *w)
+{
+	if (!w) return;
+	free(w->bodies);
+	free(w->tris);
+	free(w->sbodies);
+	free(w->man);
+	free(w->prev);
+	free(w->order);
+	free(w);
+}
+
+uint32_t orc_static_add_mesh(orc_world *w, const float pos[3], const float rot[4], const float *tris, uint64_t ntris,
+							 float friction)
+{
+	if (w->nsbodies == w->cap_sbodies)
+	{
+		w->cap_sbodies = w->cap_sbodies ? w->cap_sbodies * 2 : 16;
+		w->sbodies = (sbody_t *)realloc(w->sbodies, w->cap_sbodies * sizeof(sbody_t));
+	}
+	if (w->ntris + ntris > w->cap_tris)
+	{
+		w->cap_tris = (uint32_t)(w->ntris + ntris) * 2;
+		w->tris = (tri_t *)realloc(w->tris, w->cap_tris * sizeof(tri_t));
+	}
+	const uint32_t k = w->nsbodies++;
+	sbody_t *sb = &w->sbodies[k];
+	sb->friction = friction;
+	sb->ray_flags = 1;
+	sb->first = w->ntris;
+	sb->count = (uint32_t)ntris;
+	const q4 q = {rot[0], rot[1], rot[2], rot[3]};
+	const v3 p = V(pos[0], pos[1], pos[2]);
+	for (uint64_t i = 0; i < ntris; i++)
+	{
+		const float *t = tris + i * 9;
+		v3 a = vadd(qrot(q, V(t[0], t[1], t[2])), p);
+		v3 b = vadd(qrot(q, V(t[3], t[4], t[5])), p);
+		v3 c = vadd(qrot(q, V(t[6], t[7], t[8])), p);
+		tri_t *T = &w->tris[w->ntris++];
+		T->v0 = a;
+		T->e1 = vsub(b, a);
+		T->e2 = vsub(c, a);
+		v3 n = vcross(T->e1, T->e2);
+		float l = vlen(n);
+		T->n = l > 0.0f ? vscale(n, 1.0f / l) : V(0, 1, 0);
+		T->lo = V(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+		T->hi = V(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+		T->body = k;
+	}
+	return ORC_STATIC_BODY_BASE + k;
+}
+
+void orc_static_commit(orc_world *w) { (void)w; }
+
+uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_body, uint32_t cap)
+{
+	for (uint32_t i = 0; i < w->ntris && i < cap; i++)
+	{
+		const tri_t *T = &w->tris[i];
+		v3 b = vadd(T->v0, T->e1), c = vadd(T->v0, T->e2);
+		float *o = out9 + 9 * i;
+		o[0] = T->v0.x; o[1] = T->v0.y; o[2] = T->v0.z;
+		o[3] = b.x; o[4] = b.y; o[5] = b.z;
+		o[6] = c.x; o[7] = c.y; o[8] = c.z;
+		if (out_body) out_body[i] = ORC_STATIC_BODY_BASE + T->body;
+	}
+	return w->ntris;
+}
+
+uint32_t orc_body_create(orc_world *w, const orc_body_desc *d)
+{
+	uint32_t id = ORC_INVALID;
+	for (uint32_t i = 0; i < w->max_bodies; i++)
+		if (!w->bodies[i].alive)
+		{
+			id = i;
+			break;
+		}
+	if (id == ORC_INVALID) return id;
+	body_t *b = &w->bodies[id];
+	memset(b, 0, sizeof(*b));
+	b->alive = 1;
+	b->shape = d->shape;
+	b->he = V(d->half_extents[0], d->half_extents[1], d->half_extents[2]);
+	b->x = V(d->position[0], d->position[1], d->position[2]);
+	q4 q = {d->rotation[0], d->rotation[1], d->rotation[2], d->rotation[3]};
+	b->q = qnormalize(q);
+	b->v = V(d->linear_velocity[0], d->linear_velocity[1], d->linear_velocity[2]);
+	b->w = V(d->angular_velocity[0], d->angular_velocity[1], d->angular_velocity[2]);
+	b->motion = d->motion_type;
+	b->layer = d->layer;
+	b->friction = d->friction;
+	b->restitution = d->restitution;
+	b->lin_damp = d->linear_damping;
+	b->ang_damp = d->angular_damping;
+	b->grav_factor = d->gravity_factor;
+	b->sensor = d->is_sensor;
+	b->dofs = d->allowed_dofs ? d->allowed_dofs : 63u;
+	b->allow_sleep = d->allow_sleeping;
+	b->ray_flags = d->ray_flags;
+	b->user_data = d->user_data;
+	if (b->motion == ORC_MOTION_DYNAMIC && b->shape != ORC_SHAPE_EMPTY)
+	{
+		/* mass override + CalculateInertia (Physbox.c:27-32): inertia of the shape at density 1000 scaled to the mass */
+		float m, ix, iy, iz;
+		if (b->shape == ORC_SHAPE_BOX)
+		{
+			float sx = 2.0f * b->he.x, sy = 2.0f * b->he.y, sz = 2.0f * b->he.z;
+			float vol = (sx * sy) * sz;
+			m = d->mass > 0.0f ? d->mass : 1000.0f * vol;
+			float k = m / 12.0f;
+			ix = k * ((sy * sy) + (sz * sz));
+			iy = k * ((sx * sx) + (sz * sz));
+			iz = k * ((sx * sx) + (sy * sy));
+		}
+		else
+		{
+			float r = b->he.x;
+			float vol = (4.18879020f * r) * (r * r);
+			m = d->mass > 0.0f ? d->mass : 1000.0f * vol;
+			ix = iy = iz = (0.4f * m) * (r * r);
+		}
+		b->inv_mass = 1.0f / m;
+		b->inv_inertia = V(1.0f / ix, 1.0f / iy, 1.0f / iz);
+	}
+	return id;
+}
+
+void orc_body_destroy(orc_world *w, uint32_t id)
+{
+	if (id < w->max_bodies) w->bodies[id].alive = 0;
+}
+
+void orc_body_set_velocity(orc_world *w, uint32_t id, const float v[3], const float av[3])
+{
+	if (id >= w->max_bodies) return;
+	if (v) w->bodies[id].v = V(v[0], v[1], v[2]);
+	if (av) w->bodies[id].w = V(av[0], av[1], av[2]);
+}
+
+void orc_body_get(const orc_world *w, uint32_t id, float *xf7, float *vel6)
+{
+	const body_t *b = &w->bodies[id];
+	if (xf7)
+	{
+		xf7[0] = b->x.x; xf7[1] = b->x.y; xf7[2] = b->x.z;
+		xf7[3] = b->q.x; xf7[4] = b->q.y; xf7[5] = b->q.z; xf7[6] = b->q.w;
+	}
+	if (vel6)
+	{
+		vel6[0] = b->v.x; vel6[1] = b->v.y; vel6[2] = b->v.z;
+		vel6[3] = b->w.x; vel6[4] = b->w.y; vel6[5] = b->w.z;
+	}
+}
+
+uint32_t orc_body_active(const orc_world *w, uint32_t id) { return id < w->max_bodies && w->bodies[id].alive; }
+uint32_t orc_manifold_count(const orc_world *w) { return w->nprev; }
+uint32_t orc_events(const orc_world *w, uint32_t *out, uint32_t cap)
+{
+	(void)w; (void)out; (void)cap;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ rays */
+
+/* Two-sided Moller-Trumbore; accepts t in [0, tmax]. */
+static int ray_tri(v3 o, v3 d, float tmax, const tri_t *T, float *tout)
+{
+	v3 p = vcross(d, T->e2);
+	float det = vdot(T->e1, p);
+	if (fabsf(det) < 1.0e-12f) return 0;
+	float inv = 1.0f / det;
+	v3 tv = vsub(o, T->v0);
+	float u = vdot(tv, p) * inv;
+	if (u < 0.0f || u > 1.0f) return 0;
+	v3 q = vcross(tv, T->e1);
+	float v = vdot(d, q) * inv;
+	if (v < 0.0f || (u + v) > 1.0f) return 0;
+	float t = vdot(T->e2, q) * inv;
+	if (t < 0.0f || t > tmax) return 0;
+	*tout = t;
+	return 1;
+}
+
+static int ray_box(v3 o, v3 d, float tmax, const body_t *b, float *tout, uint32_t *face)
+{
+	m33 R = qmat(b->q);
+	v3 lo = mtmul(&R, vsub(o, b->x));
+	v3 ld = mtmul(&R, d);
+	float tn = -3.0e38f, tf = 3.0e38f;
+	uint32_t fn = 0;
+	for (int k = 0; k < 3; k++)
+	{
+		float ok = vget(lo, k), dk = vget(ld, k), hk = vget(b->he, k);
+		if (dk == 0.0f)
+		{
+			if (ok < -hk || ok > hk) return 0;
+			continue;
+		}
+		float inv = 1.0f / dk;
+		float t1 = (-hk - ok) * inv, t2 = (hk - ok) * inv;
+		uint32_t f1 = (uint32_t)(2 * k), f2 = (uint32_t)(2 * k + 1); /* face 2k = -axis, 2k+1 = +axis */
+		if (t1 > t2)
+		{
+			float tt = t1; t1 = t2; t2 = tt;
+			f1 = f2;
+		}
+		if (t1 > tn) { tn = t1; fn = f1; }
+		if (t2 < tf) tf = t2;
+	}
+	if (tn > tf || tf < 0.0f) return 0;
+	float t = tn < 0.0f ? 0.0f : tn;
+	if (t > tmax) return 0;
+	*tout = t;
+	*face = fn;
+	return 1;
+}
+
+static int ray_sphere(v3 o, v3 d, float tmax, const body_t *b, float *tout)
+{
+	v3 m = vsub(o, b->x);
+	float r = b->he.x;
+	float bq = vdot(m, d);
+	float c = vdot(m, m) - (r * r);
+	if (c > 0.0f && bq > 0.0f) return 0;
+	float disc = (bq * bq) - c;
+	if (disc < 0.0f) return 0;
+	float t = -bq - sqrtf(disc);
+	if (t < 0.0f) t = 0.0f;
+	if (t > tmax) return 0;
+	*tout = t;
+	return 1;
+}
+
+static void raycast_one(const orc_world *w, const orc_ray *r, orc_hit *h)
+{
+	const v3 o = V(r->origin[0], r->origin[1], r->origin[2]);
+	const v3 d = V(r->dir[0], r->dir[1], r->dir[2]);
+	const uint32_t layers = r->mask & 0xFu;
+	const int need_flag = (r->mask & (1u << 8)) != 0;
+	float best = 3.0e38f;
+	uint32_t bbody = ORC_INVALID, bface = ORC_INVALID;
+	if (layers & 1u)
+		for (uint32_t i = 0; i < w->ntris; i++)
+		{
+			const tri_t *T = &w->tris[i];
+			if (need_flag && !(w->sbodies[T->body].ray_flags & 1u)) continue;
+			float t;
+			if (ray_tri(o, d, r->tmax, T, &t) && t < best)
+			{
+				best = t;
+				bbody = ORC_STATIC_BODY_BASE + T->body;
+				bface = i;
+			}
+		}
+	for (uint32_t i = 0; i < w->max_bodies; i++)
+	{
+		const body_t *b = &w->bodies[i];
+		if (!b->alive || b->shape == ORC_SHAPE_EMPTY) continue;
+		if (!((layers >> b->layer) & 1u)) continue;
+		if (need_flag && !(b->ray_flags & 1u)) continue;
+		float t;
+		uint32_t f = 0;
+		int hit = b->shape == ORC_SHAPE_BOX ? ray_box(o, d, r->tmax, b, &t, &f) : ray_sphere(o, d, r->tmax, b, &t);
+		if (hit && t < best)
+		{
+			best = t;
+			bbody = i;
+			bface = f;
+		}
+	}
+	h->world = r->mask >> 16;
+	if (bbody == ORC_INVALID)
+	{
+		h->fraction = RAY_MISS_FRACTION;
+		h->body = ORC_INVALID;
+		h->face = ORC_INVALID;
+	}
+	else
+	{
+		h->fraction = best / r->tmax;
+		h->body = bbody;
+		h->face = bface;
+	}
+}
+
+void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits)
+{
+	for (uint64_t i = 0; i < n; i++) raycast_one(w, &rays[i], &hits[i]);
+}
+
+/* ---- host-thread fan-out for the timed CPU baseline (plain pthreads, static partition) */
+typedef struct
+{
+	void (*fn)(void *ctx, int64_t lo, int64_t hi);
+	void *ctx;
+	int64_t lo, hi;
+} job_t;
+
+static void *job_main(void *arg)
+{
+	job_t *j = (job_t *)arg;
+	j->fn(j->ctx, j->lo, j->hi);
+	return NULL;
+}
+
+int orc_max_threads(void)
+{
+	long n = sysconf(_SC_NPROCESSORS_ONLN);
+	return n < 1 ? 1 : (n > 256 ? 256 : (int)n);
+}
+
+static void parallel_for(int64_t n, void (*fn)(void *, int64_t, int64_t), void *ctx)
+{
+	int nt = orc_max_threads();
+	if ((int64_t)nt > n) nt = n > 0 ? (int)n : 1;
+	pthread_t th[256];
+	job_t jobs[256];
+	for (int t = 0; t < nt; t++)
+	{
+		jobs[t].fn = fn;
+		jobs[t].ctx = ctx;
+		jobs[t].lo = n * t / nt;
+		jobs[t].hi = n * (t + 1) / nt;
+		if (t > 0) pthread_create(&th[t], NULL, job_main, &jobs[t]);
+	}
+	job_main(&jobs[0]);
+	for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+}
+
+typedef struct { const orc_world *w; const orc_ray *rays; orc_hit *hits; } rayjob_t;
+static void ray_range(void *ctx, int64_t lo, int64_t hi)
+{
+	rayjob_t *r = (rayjob_t *)ctx;
+	for (int64_t i = lo; i < hi; i++) raycast_one(r->w, &r->rays[i], &r->hits[i]);
+}
+
+void orc_raycast_mt(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits)
+{
+	rayjob_t r = {w, rays, hits};
+	parallel_for((int64_t)n, ray_range, &r);
+}
+
+/* ------------------------------------------------------------------------------------------ narrowphase */
+
+typedef struct
+{
+	v3 n;        /* a -> b */
+	float depth; /* -separation along n */
+	int np;
+	v3 p1[MAX_POLY], p2[MAX_POLY]; /* world points on a and on b */
+} hit_t;
+
+static void body_aabb(const body_t *b, v3 *lo, v3 *hi)
+{
+	v3 e;
+	if (b->shape == ORC_SHAPE_BOX)
+	{
+		m33 R = qmat(b->q);
+		e.x = ((fabsf(R.c0.x) * b->he.x) + (fabsf(R.c1.x) * b->he.y)) + (fabsf(R.c2.x) * b->he.z);
+		e.y = ((fabsf(R.c0.y) * b->he.x) + (fabsf(R.c1.y) * b->he.y)) + (fabsf(R.c2.y) * b->he.z);
+		e.z = ((fabsf(R.c0.z) * b->he.x) + (fabsf(R.c1.z) * b->he.y)) + (fabsf(R.c2.z) * b->he.z);
+	}
+	else
+		e = V(b->he.x, b->he.x, b->he.x);
+	*lo = vsub(b->x, e);
+	*hi = vadd(b->x, e);
+}
+
+static int aabb_overlap(v3 alo, v3 ahi, v3 blo, v3 bhi, float m)
+{
+	return (alo.x - m) <= bhi.x && blo.x <= (ahi.x + m) && (alo.y - m) <= bhi.y && blo.y <= (ahi.y + m) &&
+		   (alo.z - m) <= bhi.z && blo.z <= (ahi.z + m);
+}
+
+/* Sutherland-Hodgman: keep the side where (p - origin).normal >= 0 */
+static int clip_plane(const v3 *in, int n, v3 origin, v3 normal, v3 *out)
+{
+	int m = 0;
+	if (n == 0) return 0;
+	v3 e1 = in[n - 1];
+	float prev = vdot(vsub(origin, e1), normal);
+	int prev_in = prev < 0.0f;
+	for (int i = 0; i < n; i++)
+	{
+		v3 e2 = in[i];
+		float num = vdot(vsub(origin, e2), normal);
+		int cur_in = num < 0.0f;
+		if (cur_in != prev_in)
+		{
+			v3 e12 = vsub(e2, e1);
+			float den = vdot(e12, normal);
+			if (den != 0.0f)
+			{
+				if (m < MAX_POLY) out[m++] = vadd(e1, vscale(e12, prev / den));
+			}
+			else
+				cur_in = prev_in;
+		}
+		if (cur_in && m < MAX_POLY) out[m++] = e2;
+		prev = num;
+		prev_in = cur_in;
+		e1 = e2;
+	}
+	return m;
+}
+
+/* Clip face2 against the side planes of face1 (planes through face1's edges, parallel to `axis`), then keep the
+ * points within max_sep of face1's plane (outward unit normal n1) and project them onto it. */
+static void manifold_between_faces(const v3 *f1, int n1v, v3 n1, const v3 *f2, int n2v, v3 axis, float max_sep,
+								   hit_t *h)
+{
+	v3 bufa[MAX_POLY], bufb[MAX_POLY];
+	v3 *src = bufa, *dst = bufb;
+	int n = n2v;
+	for (int i = 0; i < n2v; i++) src[i] = f2[i];
+	v3 cen = f1[0];
+	for (int i = 1; i < n1v; i++) cen = vadd(cen, f1[i]);
+	cen = vscale(cen, 1.0f / (float)n1v);
+	for (int i = 0; i < n1v && n > 0; i++)
+	{
+		v3 a = f1[i], b = f1[(i + 1) % n1v];
+		v3 pn = vcross(axis, vsub(b, a));
+		if (vdot(vsub(cen, a), pn) < 0.0f) pn = vneg(pn);
+		n = clip_plane(src, n, a, pn, dst);
+		v3 *t = src; src = dst; dst = t;
+	}
+	h->np = 0;
+	for (int i = 0; i < n; i++)
+	{
+		float dist = vdot(vsub(src[i], f1[0]), n1);
+		if (dist <= max_sep)
+		{
+			h->p2[h->np] = src[i];
+			h->p1[h->np] = vsub(src[i], vscale(n1, dist));
+			h->np++;
+		}
+	}
+}
+
+/* supporting face of a box in world direction dir; also returns its outward unit normal */
+static void box_face(const body_t *b, const m33 *R, v3 dir, v3 *out4, v3 *nout)
+{
+	v3 l = mtmul(R, dir);
+	float ax = fabsf(l.x), ay = fabsf(l.y), az = fabsf(l.z);
+	int k = 0;
+	if (ay > ax) k = 1;
+	if (az > (k == 0 ? ax : ay)) k = 2;
+	float s = vget(l, k) < 0.0f ? -1.0f : 1.0f;
+	int u = (k + 1) % 3, v = (k + 2) % 3;
+	const v3 *cols = &R->c0;
+	v3 ck = vscale(cols[k], s * vget(b->he, k));
+	v3 cu = vscale(cols[u], vget(b->he, u));
+	v3 cv = vscale(cols[v], vget(b->he, v));
+	v3 c = vadd(b->x, ck);
+	out4[0] = vadd(vadd(c, cu), cv);
+	out4[1] = vadd(vsub(c, cu), cv);
+	out4[2] = vsub(vsub(c, cu), cv);
+	out4[3] = vsub(vadd(c, cu), cv);
+	*nout = vscale(cols[k], s);
+}
+
+static float box_radius(const body_t *b, const m33 *R, v3 L)
+{
+	return ((b->he.x * fabsf(vdot(R->c0, L))) + (b->he.y * fabsf(vdot(R->c1, L)))) + (b->he.z * fabsf(vdot(R->c2, L)));
+}
+
+/* support vertex of a box in direction dir */
+static v3 box_support(const body_t *b, const m33 *R, v3 dir)
+{
+	v3 l = mtmul(R, dir);
+	v3 s = V(l.x < 0.0f ? -b->he.x : b->he.x, l.y < 0.0f ? -b->he.y : b->he.y, l.z < 0.0f ? -b->he.z : b->he.z);
+	return vadd(b->x, mmul(R, s));
+}
+
+/* closest points between segments p1+s*d1 (s in [-h1,h1]) and p2+t*d2 (t in [-h2,h2]); d1,d2 unit */
+static void closest_on_edges(v3 p1, v3 d1, float h1, v3 p2, v3 d2, float h2, v3 *c1, v3 *c2)
+{
+	v3 r = vsub(p1, p2);
+	float b = vdot(d1, d2);
+	float c = vdot(d1, r);
+	float f = vdot(d2, r);
+	float den = 1.0f - (b * b);
+	float s = 0.0f;
+	if (den > 1.0e-6f) s = ((b * f) - c) / den;
+	if (s < -h1) s = -h1;
+	if (s > h1) s = h1;
+	float t = (b * s) + f;
+	if (t < -h2) t = -h2;
+	if (t > h2) t = h2;
+	s = (b * t) - c;
+	if (s < -h1) s = -h1;
+	if (s > h1) s = h1;
+	*c1 = vadd(p1, vscale(d1, s));
+	*c2 = vadd(p2, vscale(d2, t));
+}
+
+static int collide_box_box(const body_t *A, const body_t *B, float max_sep, hit_t *h)
+{
+	m33 RA = qmat(A->q), RB = qmat(B->q);
+	const v3 *ca = &RA.c0, *cb = &RB.c0;
+	v3 d = vsub(B->x, A->x);
+	float best = -3.0e38f;
+	v3 bn = V(0, 1, 0);
+	int kind = 0, ei = 0, ej = 0; /* kind 0: A face, 1: B face, 2: edge */
+	for (int i = 0; i < 3; i++)
+	{
+		v3 L = ca[i];
+		float dl = vdot(d, L);
+		float sep = fabsf(dl) - (vget(A->he, i) + box_radius(B, &RB, L));
+		if (sep > max_sep) return 0;
+		if (i == 0 || sep > best + FACE_AXIS_TOL)
+		{
+			best = sep;
+			bn = dl < 0.0f ? vneg(L) : L;
+			kind = 0;
+		}
+	}
+	for (int i = 0; i < 3; i++)
+	{
+		v3 L = cb[i];
+		float dl = vdot(d, L);
+		float sep = fabsf(dl) - (box_radius(A, &RA, L) + vget(B->he, i));
+		if (sep > max_sep) return 0;
+		if (sep > best + FACE_AXIS_TOL)
+		{
+			best = sep;
+			bn = dl < 0.0f ? vneg(L) : L;
+			kind = 1;
+		}
+	}
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++)
+		{
+			v3 L = vcross(ca[i], cb[j]);
+			float l2 = vlen2(L);
+			if (l2 < 1.0e-6f) continue;
+			L = vscale(L, 1.0f / sqrtf(l2));
+			float dl = vdot(d, L);
+			float sep = fabsf(dl) - (box_radius(A, &RA, L) + box_radius(B, &RB, L));
+			if (sep > max_sep) return 0;
+			if (sep > best + EDGE_AXIS_TOL)
+			{
+				best = sep;
+				bn = dl < 0.0f ? vneg(L) : L;
+				kind = 2;
+				ei = i;
+				ej = j;
+			}
+		}
+	h->n = bn;
+	h->depth = -best;
+	v3 fa[4], fb[4], na, nb;
+	box_face(A, &RA, bn, fa, &na);
+	box_face(B, &RB, vneg(bn), fb, &nb);
+	manifold_between_faces(fa, 4, na, fb, 4, bn, max_sep, h);
+	if (h->np == 0)
+	{
+		if (kind == 2)
+		{
+			v3 pa = A->x, pb = B->x;
+			for (int k = 0; k < 3; k++)
+			{
+				if (k != ei) pa = vadd(pa, vscale(ca[k], vdot(bn, ca[k]) < 0.0f ? -vget(A->he, k) : vget(A->he, k)));
+				if (k != ej) pb = vsub(pb, vscale(cb[k], vdot(bn, cb[k]) < 0.0f ? -vget(B->he, k) : vget(B->he, k)));
+			}
+			closest_on_edges(pa, ca[ei], vget(A->he, ei), pb, cb[ej], vget(B->he, ej), &h->p1[0], &h->p2[0]);
+		}
+		else if (kind == 0)
+		{
+			h->p2[0] = box_support(B, &RB, vneg(bn));
+			h->p1[0] = vadd(h->p2[0], vscale(bn, -best));
+		}
+		else
+		{
+			h->p1[0] = box_support(A, &RA, bn);
+			h->p2[0] = vadd(h->p1[0], vscale(bn, best));
+		}
+		h->np = 1;
+	}
+	return 1;
+}
+
+static int collide_box_tri(const body_t *A, const tri_t *T, float max_sep, hit_t *h)
+{
+	m33 R = qmat(A->q);
+	const v3 *ca = &R.c0;
+	v3 tv[3];
+	tv[0] = T->v0;
+	tv[1] = vadd(T->v0, T->e1);
+	tv[2] = vadd(T->v0, T->e2);
+	float best;
+	v3 bn;
+	int kind = 0, ei = 0, ej = 0;
+	{
+		/* triangle plane */
+		float r = box_radius(A, &R, T->n);
+		float cp = vdot(A->x, T->n), tp = vdot(T->v0, T->n);
+		float sp = tp - (cp + r), sm = (cp - r) - tp;
+		if (sp > sm) { best = sp; bn = T->n; }
+		else { best = sm; bn = vneg(T->n); }
+		if (best > max_sep) return 0;
+	}
+	for (int i = 0; i < 3; i++)
+	{
+		v3 L = ca[i];
+		float p0 = vdot(tv[0], L), p1 = vdot(tv[1], L), p2 = vdot(tv[2], L);
+		float tmin = fminf(p0, fminf(p1, p2)), tmax = fmaxf(p0, fmaxf(p1, p2));
+		float cp = vdot(A->x, L), r = vget(A->he, i);
+		float sp = tmin - (cp + r), sm = (cp - r) - tmax;
+		float sep = sp > sm ? sp : sm;
+		if (sep > max_sep) return 0;
+		if (sep > best + FACE_AXIS_TOL)
+		{
+			best = sep;
+			bn = sp > sm ? L : vneg(L);
+			kind = 1;
+		}
+	}
+	v3 te[3];
+	te[0] = T->e1;
+	te[1] = vsub(tv[2], tv[1]);
+	te[2] = vsub(tv[0], tv[2]);
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++)
+		{
+			v3 L = vcross(ca[i], te[j]);
+			float l2 = vlen2(L);
+			if (l2 < 1.0e-8f * vlen2(te[j])) continue;
+			L = vscale(L, 1.0f / sqrtf(l2));
+			float p0 = vdot(tv[0], L), p1 = vdot(tv[1], L), p2 = vdot(tv[2], L);
+			float tmin = fminf(p0, fminf(p1, p2)), tmax = fmaxf(p0, fmaxf(p1, p2));
+			float cp = vdot(A->x, L), r = box_radius(A, &R, L);
+			float sp = tmin - (cp + r), sm = (cp - r) - tmax;
+			float sep = sp > sm ? sp : sm;
+			if (sep > max_sep) return 0;
+			if (sep > best + EDGE_AXIS_TOL)
+			{
+				best = sep;
+				bn = sp > sm ? L : vneg(L);
+				kind = 2;
+				ei = i;
+				ej = j;
+			}
+		}
+	h->n = bn;
+	h->depth = -best;
+	v3 fa[4], na;
+	box_face(A, &R, bn, fa, &na);
+	manifold_between_faces(fa, 4, na, tv, 3, bn, max_sep, h);
+	if (h->np == 0)
+	{
+		if (kind == 2)
+		{
+			v3 pa = A->x;
+			for (int k = 0; k < 3; k++)
+				if (k != ei) pa = vadd(pa, vscale(ca[k], vdot(bn, ca[k]) < 0.0f ? -vget(A->he, k) : vget(A->he, k)));
+			float el = vlen(te[ej]);
+			v3 ed = vscale(te[ej], 1.0f / el);
+			v3 mid = vadd(tv[ej], vscale(te[ej], 0.5f));
+			closest_on_edges(pa, ca[ei], vget(A->he, ei), mid, ed, 0.5f * el, &h->p1[0], &h->p2[0]);
+		}
+		else
+		{
+			h->p1[0] = box_support(A, &R, bn);
+			h->p2[0] = vadd(h->p1[0], vscale(bn, best));
+		}
+		h->np = 1;
+	}
+	return 1;
+}
+
+/* closest point on triangle (Ericson 5.1.5) */
+static v3 closest_on_tri(v3 p, v3 a, v3 b, v3 c)
+{
+	v3 ab = vsub(b, a), ac = vsub(c, a), ap = vsub(p, a);
+	float d1 = vdot(ab, ap), d2 = vdot(ac, ap);
+	if (d1 <= 0.0f && d2 <= 0.0f) return a;
+	v3 bp = vsub(p, b);
+	float d3 = vdot(ab, bp), d4 = vdot(ac, bp);
+	if (d3 >= 0.0f && d4 <= d3) return b;
+	float vc = (d1 * d4) - (d3 * d2);
+	if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) return vadd(a, vscale(ab, d1 / (d1 - d3)));
+	v3 cp = vsub(p, c);
+	float d5 = vdot(ab, cp), d6 = vdot(ac, cp);
+	if (d6 >= 0.0f && d5 <= d6) return c;
+	float vb = (d5 * d2) - (d1 * d6);
+	if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) return vadd(a, vscale(ac, d2 / (d2 - d6)));
+	float va = (d3 * d6) - (d5 * d4);
+	if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f)
+		return vadd(b, vscale(vsub(c, b), (d4 - d3) / ((d4 - d3) + (d5 - d6))));
+	float den = 1.0f / ((va + vb) + vc);
+	float v = vb * den, w = vc * den;
+	return vadd(vadd(a, vscale(ab, v)), vscale(ac, w));
+}
+
+static int collide_sphere_tri(const body_t *A, const tri_t *T, float max_sep, hit_t *h)
+{
+	v3 c = closest_on_tri(A->x, T->v0, vadd(T->v0, T->e1), vadd(T->v0, T->e2));
+	v3 d = vsub(c, A->x);
+	float dist = vlen(d);
+	float r = A->he.x;
+	if ((dist - r) > max_sep) return 0;
+	h->n = dist > 1.0e-9f ? vscale(d, 1.0f / dist) : vneg(T->n);
+	h->depth = r - dist;
+	h->np = 1;
+	h->p1[0] = vadd(A->x, vscale(h->n, r));
+	h->p2[0] = c;
+	return 1;
+}
+
+static int collide_sphere_sphere(const body_t *A, const body_t *B, float max_sep, hit_t *h)
+{
+	v3 d = vsub(B->x, A->x);
+	float dist = vlen(d);
+	float ra = A->he.x, rb = B->he.x;
+	if ((dist - (ra + rb)) > max_sep) return 0;
+	h->n = dist > 1.0e-9f ? vscale(d, 1.0f / dist) : V(0, 1, 0);
+	h->depth = (ra + rb) - dist;
+	h->np = 1;
+	h->p1[0] = vadd(A->x, vscale(h->n, ra));
+	h->p2[0] = vsub(B->x, vscale(h->n, rb));
+	return 1;
+}
+
+/* sphere S vs box X.  Normal returned points from the sphere to the box. */
+static int collide_sphere_box(const body_t *S, const body_t *X, float max_sep, hit_t *h)
+{
+	m33 R = qmat(X->q);
+	v3 l = mtmul(&R, vsub(S->x, X->x));
+	v3 cl = V(fminf(fmaxf(l.x, -X->he.x), X->he.x), fminf(fmaxf(l.y, -X->he.y), X->he.y),
+			  fminf(fmaxf(l.z, -X->he.z), X->he.z));
+	v3 dl = vsub(cl, l);
+	float dist = vlen(dl);
+	float r = S->he.x;
+	v3 nl;
+	v3 pb;
+	float depth;
+	if (dist > 1.0e-9f)
+	{
+		if ((dist - r) > max_sep) return 0;
+		nl = vscale(dl, 1.0f / dist);
+		pb = cl;
+		depth = r - dist;
+	}
+	else
+	{
+		/* centre inside the box: push out through the nearest face */
+		float dx = X->he.x - fabsf(l.x), dy = X->he.y - fabsf(l.y), dz = X->he.z - fabsf(l.z);
+		int k = 0;
+		float dm = dx;
+		if (dy < dm) { dm = dy; k = 1; }
+		if (dz < dm) { dm = dz; k = 2; }
+		float s = vget(l, k) < 0.0f ? -1.0f : 1.0f;
+		nl = V(k == 0 ? -s : 0.0f, k == 1 ? -s : 0.0f, k == 2 ? -s : 0.0f);
+		pb = l;
+		if (k == 0) pb.x = s * X->he.x;
+		if (k == 1) pb.y = s * X->he.y;
+		if (k == 2) pb.z = s * X->he.z;
+		depth = r + dm;
+	}
+	h->n = mmul(&R, nl);
+	h->depth = depth;
+	h->np = 1;
+	h->p1[0] = vadd(S->x, vscale(h->n, r));
+	h->p2[0] = vadd(X->x, mmul(&R, pb));
+	return 1;
+}
+
+/* Reduce to <= 4 points keeping the largest, deepest spread (restating Jolt's PruneContactPoints). */
+static void prune_points(v3 xa, v3 axis, int *np, v3 *p1, v3 *p2)
+{
+	int n = *np;
+	if (n <= 4) return;
+	v3 proj[2 * MAX_POLY];
+	float dsq[2 * MAX_POLY];
+	for (int i = 0; i < n; i++)
+	{
+		v3 v1 = vsub(p1[i], xa);
+		proj[i] = vsub(v1, vscale(axis, vdot(v1, axis)));
+		dsq[i] = fmaxf(1.0e-6f, vlen2(vsub(p2[i], p1[i])));
+	}
+	int i1 = 0;
+	float best = -1.0f;
+	for (int i = 0; i < n; i++)
+	{
+		float v = fmaxf(1.0e-6f, vlen2(proj[i])) * dsq[i];
+		if (v > best) { best = v; i1 = i; }
+	}
+	int i2 = -1;
+	best = -1.0f;
+	for (int i = 0; i < n; i++)
+		if (i != i1)
+		{
+			float v = fmaxf(1.0e-6f, vlen2(vsub(proj[i], proj[i1]))) * dsq[i];
+			if (v > best) { best = v; i2 = i; }
+		}
+	int i3 = -1, i4 = -1;
+	float mn = 0.0f, mx = 0.0f;
+	v3 perp = vcross(vsub(proj[i2], proj[i1]), axis);
+	for (int i = 0; i < n; i++)
+		if (i != i1 && i != i2)
+		{
+			float v = vdot(perp, vsub(proj[i], proj[i1]));
+			if (v < mn) { mn = v; i3 = i; }
+			else if (v > mx) { mx = v; i4 = i; }
+		}
+	v3 o1[4], o2[4];
+	int m = 0;
+	o1[m] = p1[i1]; o2[m++] = p2[i1];
+	if (i3 >= 0) { o1[m] = p1[i3]; o2[m++] = p2[i3]; }
+	o1[m] = p1[i2]; o2[m++] = p2[i2];
+	if (i4 >= 0) { o1[m] = p1[i4]; o2[m++] = p2[i4]; }
+	for (int i = 0; i < m; i++) { p1[i] = o1[i]; p2[i] = o2[i]; }
+	*np = m;
+}
+
+/* ------------------------------------------------------------------------------------------ contact generation */
+
+static int layers_collide(const body_t *a, const body_t *b)
+{
+	/* ObjectLayerShouldCollide, both orders (engine/src/physics/Physics.c:35-52): DYNAMIC/PLAYER vs STATIC/DYNAMIC/SENSOR */
+	int a_init = a->layer == 1 || a->layer == 2, b_init = b->layer == 1 || b->layer == 2;
+	int a_tgt = a->layer == 0 || a->layer == 1 || a->layer == 3, b_tgt = b->layer == 0 || b->layer == 1 || b->layer == 3;
+	return (a_init && b_tgt) || (b_init && a_tgt);
+}
+
+static manifold_t *push_manifold(orc_world *w, int *err)
+{
+	if (w->nman >= w->max_manifolds)
+	{
+		*err = 4;
+		return NULL;
+	}
+	manifold_t *m = &w->man[w->nman++];
+	memset(m, 0, sizeof(*m));
+	return m;
+}
+
+static void store_points(manifold_t *m, const body_t *A, const body_t *B, int np, const v3 *p1, const v3 *p2)
+{
+	m33 RA = qmat(A->q);
+	m->np = np;
+	for (int i = 0; i < np; i++)
+	{
+		m->p1l[i] = mtmul(&RA, vsub(p1[i], A->x));
+		if (B)
+		{
+			m33 RB = qmat(B->q);
+			m->p2l[i] = mtmul(&RB, vsub(p2[i], B->x));
+		}
+		else
+			m->p2l[i] = p2[i];
+	}
+}
+
+static void find_contacts(orc_world *w, int *err)
+{
+	w->nman = 0;
+	for (uint32_t i = 0; i < w->max_bodies; i++)
+	{
+		body_t *A = &w->bodies[i];
+		if (!A->alive || A->shape == ORC_SHAPE_EMPTY) continue;
+		v3 alo, ahi;
+		body_aabb(A, &alo, &ahi);
+		/* (a) against the static triangle soup: dynamic bodies of layers that collide with STATIC */
+		if (A->motion == ORC_MOTION_DYNAMIC && !A->sensor && (A->layer == 1 || A->layer == 2))
+		{
+			/* per static body: up to MAX_SLOTS manifolds grouped by normal */
+			uint32_t cur_body = ORC_INVALID;
+			v3 sp1[MAX_SLOTS][8], sp2[MAX_SLOTS][8];
+			int snp[MAX_SLOTS];
+			manifold_t *slots[MAX_SLOTS];
+			int nslots = 0;
+			for (uint32_t t = 0; t <= w->ntris; t++)
+			{
+				const tri_t *T = t < w->ntris ? &w->tris[t] : NULL;
+				if (!T || T->body != cur_body)
+				{
+					/* flush slots of the previous static body */
+					for (int s = 0; s < nslots; s++) store_points(slots[s], A, NULL, snp[s], sp1[s], sp2[s]);
+					nslots = 0;
+					if (!T) break;
+					cur_body = T->body;
+				}
+				if (!aabb_overlap(alo, ahi, T->lo, T->hi, SPECULATIVE_DISTANCE)) continue;
+				hit_t h;
+				int hit = A->shape == ORC_SHAPE_BOX ? collide_box_tri(A, T, SPECULATIVE_DISTANCE, &h)
+													: collide_sphere_tri(A, T, SPECULATIVE_DISTANCE, &h);
+				if (!hit) continue;
+				prune_points(A->x, h.n, &h.np, h.p1, h.p2);
+				int s = -1;
+				for (int k = 0; k < nslots; k++)
+					if (vdot(slots[k]->n, h.n) >= NORMAL_COS_MAX_DELTA)
+					{
+						s = k;
+						break;
+					}
+				if (s < 0)
+				{
+					if (nslots == MAX_SLOTS) continue;
+					manifold_t *m = push_manifold(w, err);
+					if (!m) return;
+					m->a = i;
+					m->b = ORC_STATIC_BODY_BASE + T->body;
+					m->n = h.n;
+					m->depth = h.depth;
+					m->friction = sqrtf(A->friction * w->sbodies[T->body].friction);
+					m->restitution = A->restitution;
+					s = nslots++;
+					slots[s] = m;
+					snp[s] = 0;
+				}
+				else if (h.depth > slots[s]->depth)
+				{
+					slots[s]->depth = h.depth;
+					slots[s]->n = h.n;
+				}
+				for (int k = 0; k < h.np; k++)
+				{
+					sp1[s][snp[s]] = h.p1[k];
+					sp2[s][snp[s]] = h.p2[k];
+					snp[s]++;
+				}
+				prune_points(A->x, slots[s]->n, &snp[s], sp1[s], sp2[s]);
+			}
+		}
+		/* (b) against higher-numbered slot bodies */
+		for (uint32_t j = i + 1; j < w->max_bodies; j++)
+		{
+			body_t *B = &w->bodies[j];
+			if (!B->alive || B->shape == ORC_SHAPE_EMPTY) continue;
+			if (A->motion != ORC_MOTION_DYNAMIC && B->motion != ORC_MOTION_DYNAMIC) continue;
+			if (!layers_collide(A, B)) continue;
+			if (A->sensor || B->sensor) continue; /* sensors produce events only (not part of the solve) */
+			v3 blo, bhi;
+			body_aabb(B, &blo, &bhi);
+			if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) continue;
+			hit_t h;
+			int hit;
+			if (A->shape == ORC_SHAPE_BOX && B->shape == ORC_SHAPE_BOX)
+				hit = collide_box_box(A, B, SPECULATIVE_DISTANCE, &h);
+			else if (A->shape == ORC_SHAPE_SPHERE && B->shape == ORC_SHAPE_SPHERE)
+				hit = collide_sphere_sphere(A, B, SPECULATIVE_DISTANCE, &h);
+			else if (A->shape == ORC_SHAPE_SPHERE)
+				hit = collide_sphere_box(A, B, SPECULATIVE_DISTANCE, &h);
+			else
+			{
+				hit = collide_sphere_box(B, A, SPECULATIVE_DISTANCE, &h);
+				if (hit)
+				{
+					h.n = vneg(h.n);
+					v3 t = h.p1[0];
+					h.p1[0] = h.p2[0];
+					h.p2[0] = t;
+				}
+			}
+			if (!hit) continue;
+			prune_points(A->x, h.n, &h.np, h.p1, h.p2);
+			manifold_t *m = push_manifold(w, err);
+			if (!m) return;
+			m->a = i;
+			m->b = j;
+			m->n = h.n;
+			m->depth = h.depth;
+			m->friction = sqrtf(A->friction * B->friction);
+			m->restitution = fmaxf(A->restitution, B->restitution);
+			store_points(m, A, B, h.np, h.p1, h.p2);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ solver */
+
+static void warm_start_match(orc_world *w)
+{
+	for (uint32_t i = 0; i < w->nman; i++)
+	{
+		manifold_t *m = &w->man[i];
+		for (uint32_t j = 0; j < w->nprev; j++)
+		{
+			const manifold_t *o = &w->prev[j];
+			if (o->a != m->a || o->b != m->b) continue;
+			for (int p = 0; p < m->np; p++)
+			{
+				if (m->ln[p] != 0.0f || m->lt1[p] != 0.0f || m->lt2[p] != 0.0f) continue;
+				for (int k = 0; k < o->np; k++)
+					if (vlen2(vsub(m->p1l[p], o->p1l[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
+						vlen2(vsub(m->p2l[p], o->p2l[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ)
+					{
+						m->ln[p] = o->ln[k];
+						m->lt1[p] = o->lt1[k];
+						m->lt2[p] = o->lt2[k];
+						break;
+					}
+			}
+		}
+	}
+}
+
+static int colour_manifolds(orc_world *w)
+{
+	/* greedy first-fit in canonical order; only dynamic bodies constrain the colour */
+	uint64_t used[4096];
+	uint32_t nb = w->max_bodies < 4096 ? w->max_bodies : 4096;
+	memset(used, 0, nb * sizeof(uint64_t));
+	int ncol = 0;
+	for (uint32_t i = 0; i < w->nman; i++)
+	{
+		manifold_t *m = &w->man[i];
+		uint64_t u = 0;
+		int a_dyn = w->bodies[m->a].motion == ORC_MOTION_DYNAMIC;
+		int b_dyn = m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC;
+		if (a_dyn) u |= used[m->a];
+		if (b_dyn) u |= used[m->b];
+		int c = 0;
+		while (c < 63 && ((u >> c) & 1u)) c++;
+		m->colour = c;
+		if (a_dyn) used[m->a] |= 1ull << c;
+		if (b_dyn) used[m->b] |= 1ull << c;
+		if (c + 1 > ncol) ncol = c + 1;
+	}
+	uint32_t k = 0;
+	for (int c = 0; c < ncol; c++)
+		for (uint32_t i = 0; i < w->nman; i++)
+			if (w->man[i].colour == c) w->order[k++] = i;
+	return ncol;
+}
+
+typedef struct
+{
+	v3 x;
+	q4 q;
+	v3 v, w;
+	float inv_mass;
+	v3 inv_inertia;
+	uint32_t dofs;
+	int dynamic;
+} sb_t; /* solver view of a body; static geometry = zeros */
+
+static v3 apply_inv_inertia(const m33 *R, v3 inv_i, uint32_t dofs, v3 a)
+{
+	/* world inverse inertia R diag(inv_i) R^T, with locked rotation axes masked in world space */
+	if (!(dofs & 8u)) a.x = 0.0f;
+	if (!(dofs & 16u)) a.y = 0.0f;
+	if (!(dofs & 32u)) a.z = 0.0f;
+	v3 l = mtmul(R, a);
+	l = vmulc(l, inv_i);
+	v3 r = mmul(R, l);
+	if (!(dofs & 8u)) r.x = 0.0f;
+	if (!(dofs & 16u)) r.y = 0.0f;
+	if (!(dofs & 32u)) r.z = 0.0f;
+	return r;
+}
+
+static v3 mask_lin(uint32_t dofs, v3 a)
+{
+	if (!(dofs & 1u)) a.x = 0.0f;
+	if (!(dofs & 2u)) a.y = 0.0f;
+	if (!(dofs & 4u)) a.z = 0.0f;
+	return a;
+}
+
+typedef struct
+{
+	body_t *A, *B; /* B == NULL for static geometry */
+	m33 RA, RB;
+	float ima, imb;
+} pair_t;
+
+static void pair_init(orc_world *w, manifold_t *m, pair_t *p)
+{
+	p->A = &w->bodies[m->a];
+	p->B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
+	p->RA = qmat(p->A->q);
+	p->ima = p->A->motion == ORC_MOTION_DYNAMIC ? p->A->inv_mass : 0.0f;
+	if (p->B)
+	{
+		p->RB = qmat(p->B->q);
+		p->imb = p->B->motion == ORC_MOTION_DYNAMIC ? p->B->inv_mass : 0.0f;
+	}
+	else
+		p->imb = 0.0f;
+}
+
+static v3 inv_i_a(const pair_t *p, v3 a)
+{
+	if (p->A->motion != ORC_MOTION_DYNAMIC) return V(0, 0, 0);
+	return apply_inv_inertia(&p->RA, p->A->inv_inertia, p->A->dofs, a);
+}
+static v3 inv_i_b(const pair_t *p, v3 a)
+{
+	if (!p->B || p->B->motion != ORC_MOTION_DYNAMIC) return V(0, 0, 0);
+	return apply_inv_inertia(&p->RB, p->B->inv_inertia, p->B->dofs, a);
+}
+
+static float eff_mass(const pair_t *p, v3 r1, v3 r2, v3 axis, v3 *r1xa, v3 *r2xa, v3 *i1, v3 *i2)
+{
+	*r1xa = vcross(r1, axis);
+	*r2xa = vcross(r2, axis);
+	*i1 = inv_i_a(p, *r1xa);
+	*i2 = inv_i_b(p, *r2xa);
+	v3 la = mask_lin(p->A->dofs, axis);
+	v3 lb = p->B ? mask_lin(p->B->dofs, axis) : axis;
+	float k = (((p->ima * vdot(la, axis)) + (p->imb * vdot(lb, axis))) + vdot(*i1, *r1xa)) + vdot(*i2, *r2xa);
+	return k > 0.0f ? 1.0f / k : 0.0f;
+}
+
+static float axis_jv(const pair_t *p, v3 axis, v3 r1xa, v3 r2xa)
+{
+	v3 vb = p->B ? p->B->v : V(0, 0, 0), wb = p->B ? p->B->w : V(0, 0, 0);
+	return (vdot(axis, vsub(p->A->v, vb)) + vdot(r1xa, p->A->w)) - vdot(r2xa, wb);
+}
+
+static void axis_apply(const pair_t *p, v3 axis, v3 i1, v3 i2, float lambda)
+{
+	if (p->A->motion == ORC_MOTION_DYNAMIC)
+	{
+		p->A->v = vsub(p->A->v, mask_lin(p->A->dofs, vscale(axis, lambda * p->ima)));
+		p->A->w = vsub(p->A->w, vscale(i1, lambda));
+	}
+	if (p->B && p->B->motion == ORC_MOTION_DYNAMIC)
+	{
+		p->B->v = vadd(p->B->v, mask_lin(p->B->dofs, vscale(axis, lambda * p->imb)));
+		p->B->w = vadd(p->B->w, vscale(i2, lambda));
+	}
+}
+
+/* per sub-step set-up: lever arms, tangents, effective masses, speculative / restitution bias; then warm start */
+static void setup_and_warm_start(orc_world *w, manifold_t *m, float h)
+{
+	pair_t p;
+	pair_init(w, m, &p);
+	m->t1 = vperp(m->n);
+	m->t2 = vcross(m->n, m->t1);
+	const v3 axes[3] = {m->n, m->t1, m->t2};
+	for (int k = 0; k < m->np; k++)
+	{
+		v3 p1 = vadd(p.A->x, mmul(&p.RA, m->p1l[k]));
+		v3 p2 = p.B ? vadd(p.B->x, mmul(&p.RB, m->p2l[k])) : m->p2l[k];
+		v3 mid = vscale(vadd(p1, p2), 0.5f);
+		v3 r1 = vsub(mid, p.A->x);
+		v3 r2 = p.B ? vsub(mid, p.B->x) : V(0, 0, 0);
+		for (int c = 0; c < 3; c++)
+			m->em[k][c] = eff_mass(&p, r1, r2, axes[c], &m->r1xa[k][c], &m->r2xa[k][c], &m->i1[k][c], &m->i2[k][c]);
+		float pen = vdot(vsub(p1, p2), m->n);
+		float bias = fmaxf(0.0f, -pen / h);
+		if (m->restitution > 0.0f)
+		{
+			float nv = -axis_jv(&p, m->n, m->r1xa[k][0], m->r2xa[k][0]); /* separating speed of b relative to a */
+			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m->restitution * nv;
+		}
+		m->bias[k] = bias;
+	}
+	for (int k = 0; k < m->np; k++)
+	{
+		if (m->lt1[k] != 0.0f || m->lt2[k] != 0.0f)
+		{
+			axis_apply(&p, m->t1, m->i1[k][1], m->i2[k][1], m->lt1[k]);
+			axis_apply(&p, m->t2, m->i1[k][2], m->i2[k][2], m->lt2[k]);
+		}
+		if (m->ln[k] != 0.0f) axis_apply(&p, m->n, m->i1[k][0], m->i2[k][0], m->ln[k]);
+	}
+}
+
+static void solve_velocity(orc_world *w, manifold_t *m)
+{
+	pair_t p;
+	p.A = &w->bodies[m->a];
+	p.B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
+	p.ima = p.A->motion == ORC_MOTION_DYNAMIC ? p.A->inv_mass : 0.0f;
+	p.imb = (p.B && p.B->motion == ORC_MOTION_DYNAMIC) ? p.B->inv_mass : 0.0f;
+	/* friction first (non-penetration is more important, so it goes last) */
+	for (int k = 0; k < m->np; k++)
+	{
+		float l1 = m->lt1[k] + (m->em[k][1] * axis_jv(&p, m->t1, m->r1xa[k][1], m->r2xa[k][1]));
+		float l2 = m->lt2[k] + (m->em[k][2] * axis_jv(&p, m->t2, m->r1xa[k][2], m->r2xa[k][2]));
+		float maxf = m->friction * m->ln[k];
+		float sq = (l1 * l1) + (l2 * l2);
+		if (sq > (maxf * maxf))
+		{
+			float s = maxf / sqrtf(sq);
+			l1 = l1 * s;
+			l2 = l2 * s;
+		}
+		axis_apply(&p, m->t1, m->i1[k][1], m->i2[k][1], l1 - m->lt1[k]);
+		axis_apply(&p, m->t2, m->i1[k][2], m->i2[k][2], l2 - m->lt2[k]);
+		m->lt1[k] = l1;
+		m->lt2[k] = l2;
+	}
+	for (int k = 0; k < m->np; k++)
+	{
+		float jv = axis_jv(&p, m->n, m->r1xa[k][0], m->r2xa[k][0]);
+		float lambda = m->em[k][0] * (jv - m->bias[k]);
+		float nt = fmaxf(0.0f, m->ln[k] + lambda);
+		lambda = nt - m->ln[k];
+		m->ln[k] = nt;
+		axis_apply(&p, m->n, m->i1[k][0], m->i2[k][0], lambda);
+	}
+}
+
+static void solve_position(orc_world *w, manifold_t *m)
+{
+	for (int k = 0; k < m->np; k++)
+	{
+		pair_t p;
+		pair_init(w, m, &p); /* rotations change inside the loop */
+		v3 p1 = vadd(p.A->x, mmul(&p.RA, m->p1l[k]));
+		v3 p2 = p.B ? vadd(p.B->x, mmul(&p.RB, m->p2l[k])) : m->p2l[k];
+		float sep = vdot(vsub(p2, p1), m->n) + PENETRATION_SLOP;
+		if (sep >= 0.0f) continue;
+		v3 mid = vscale(vadd(p1, p2), 0.5f);
+		v3 r1 = vsub(mid, p.A->x), r2 = p.B ? vsub(mid, p.B->x) : V(0, 0, 0);
+		v3 rx1, rx2, i1, i2;
+		float e = eff_mass(&p, r1, r2, m->n, &rx1, &rx2, &i1, &i2);
+		float c = fmaxf(sep, -MAX_PENETRATION_DISTANCE);
+		float lambda = (-e * BAUMGARTE) * c;
+		if (p.A->motion == ORC_MOTION_DYNAMIC)
+		{
+			p.A->x = vsub(p.A->x, mask_lin(p.A->dofs, vscale(m->n, lambda * p.ima)));
+			p.A->q = qstep(p.A->q, vscale(i1, -lambda));
+		}
+		if (p.B && p.B->motion == ORC_MOTION_DYNAMIC)
+		{
+			p.B->x = vadd(p.B->x, mask_lin(p.B->dofs, vscale(m->n, lambda * p.imb)));
+			p.B->q = qstep(p.B->q, vscale(i2, lambda));
+		}
+	}
+}
+
+static v3 clamp_len(v3 v, float maxl)
+{
+	float l2 = vlen2(v);
+	if (l2 > (maxl * maxl)) return vscale(v, maxl / sqrtf(l2));
+	return v;
+}
+
+int orc_step(orc_world *w, float dt, int collision_steps)
+{
+	int err = 0;
+	if (collision_steps < 1) collision_steps = 1;
+	const float h = dt / (float)collision_steps;
+	for (int s = 0; s < collision_steps; s++)
+	{
+		for (uint32_t i = 0; i < w->max_bodies; i++)
+		{
+			body_t *b = &w->bodies[i];
+			if (!b->alive || b->motion != ORC_MOTION_DYNAMIC) continue;
+			b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
+			b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
+			b->w = vscale(b->w, fmaxf(0.0f, 1.0f - (b->ang_damp * h)));
+			b->v = clamp_len(mask_lin(b->dofs, b->v), MAX_LINEAR_VELOCITY);
+			v3 ww = b->w;
+			if (!(b->dofs & 8u)) ww.x = 0.0f;
+			if (!(b->dofs & 16u)) ww.y = 0.0f;
+			if (!(b->dofs & 32u)) ww.z = 0.0f;
+			b->w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+		}
+		find_contacts(w, &err);
+		warm_start_match(w);
+		colour_manifolds(w);
+		for (uint32_t k = 0; k < w->nman; k++) setup_and_warm_start(w, &w->man[w->order[k]], h);
+		for (uint32_t it = 0; it < w->vel_steps; it++)
+			for (uint32_t k = 0; k < w->nman; k++) solve_velocity(w, &w->man[w->order[k]]);
+		for (uint32_t i = 0; i < w->max_bodies; i++)
+		{
+			body_t *b = &w->bodies[i];
+			if (!b->alive || b->motion == ORC_MOTION_STATIC) continue;
+			b->x = vadd(b->x, vscale(b->v, h));
+			b->q = qstep(b->q, vscale(b->w, h));
+		}
+		for (uint32_t it = 0; it < w->pos_steps; it++)
+			for (uint32_t k = 0; k < w->nman; k++) solve_position(w, &w->man[w->order[k]]);
+		manifold_t *t = w->prev;
+		w->prev = w->man;
+		w->man = t;
+		w->nprev = w->nman;
+	}
+	return err;
+}
+
+typedef struct { orc_world **ws; float dt; int steps, ticks; int err; } stepjob_t;
+static void step_range(void *ctx, int64_t lo, int64_t hi)
+{
+	stepjob_t *j = (stepjob_t *)ctx;
+	int err = 0;
+	for (int64_t i = lo; i < hi; i++)
+		for (int t = 0; t < j->ticks; t++) err |= orc_step(j->ws[i], j->dt, j->steps);
+	if (err) __atomic_fetch_or(&j->err, err, __ATOMIC_RELAXED);
+}
+
+int orc_step_many(orc_world **ws, uint32_t n, float dt, int collision_steps, int ticks)
+{
+	stepjob_t j = {ws, dt, collision_steps, ticks, 0};
+	parallel_for((int64_t)n, step_range, &j);
+	return j.err;
+}

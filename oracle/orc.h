@@ -1,0 +1,98 @@
+/*
+ * orc.h — CPU oracle for the physics tick and ray queries.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or
+ * call this.  The product (libgpx.so) never links it and has no CPU path.
+ *
+ * PARITY UNPINNED: the reference delegates this path to joltc @226bd1e0afa8552917ffd56bca03ccb5c14ecd27 ->
+ * JoltPhysics, which is not vendored in the reference tree and cannot be fetched or built here; the
+ * reference has no tests or golden vectors.  This file therefore restates Jolt's PUBLISHED tick structure
+ * (sub-steps; gravity+damping; speculative contacts; manifold clipping between supporting faces; 4-point
+ * manifold reduction; warm-started sequential impulses, friction before non-penetration; integrate; Baumgarte
+ * position pass) with Jolt's documented default constants, anchored on the reference's call sites:
+ *   tick order / dt / 2 collision steps ..... engine/src/physics/MapPhysics.c:58-119
+ *   world, layers, gravity ................... engine/src/physics/Physics.c:20-100, Physics.h:12-51
+ *   static map upload, friction 4.25 ......... engine/src/assets/MapLoader.c:200-273
+ *   body parameters .......................... game/src/actor/prop/Physbox.c:19-38, engine/src/actor/Trigger.c:33-50 ...
+ *   rays and their filters ................... engine/src/physics/PlayerPhysics.c:55-86,297-315, game/src/actor/prop/Laser.c:40-158
+ * It is pinned instead by analytic known answers (tests/test_oracle_*.py): free fall with damping, resting
+ * contact height, Moller-Trumbore known hits, momentum/energy properties.
+ *
+ * Plain C, single precision, compiled with -ffp-contract=off so that every expression rounds exactly like the
+ * CUDA build (-fmad=false).  Algorithms here are deliberately the naive ones (all-pairs broadphase, brute-force
+ * triangle loops, sequential constraint order) — the GPU path must reproduce their results, not their structure.
+ */
+#ifndef ORC_H
+#define ORC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_STATIC_BODY_BASE 0x400000u
+#define ORC_INVALID 0xFFFFFFFFu
+
+enum { ORC_SHAPE_EMPTY = 0, ORC_SHAPE_BOX = 1, ORC_SHAPE_SPHERE = 2 };
+enum { ORC_MOTION_STATIC = 0, ORC_MOTION_KINEMATIC = 1, ORC_MOTION_DYNAMIC = 2 };
+
+typedef struct orc_ray { float origin[3]; float tmax; float dir[3]; uint32_t mask; } orc_ray;
+typedef struct orc_hit { float fraction; uint32_t body; uint32_t face; uint32_t world; } orc_hit;
+
+typedef struct orc_body_desc
+{
+	uint32_t shape;
+	float half_extents[3];
+	float convex_radius;
+	float position[3];
+	float rotation[4];
+	float linear_velocity[3];
+	float angular_velocity[3];
+	uint32_t motion_type;
+	uint32_t layer;
+	float mass;
+	float friction;
+	float restitution;
+	float linear_damping;
+	float angular_damping;
+	float gravity_factor;
+	uint32_t is_sensor;
+	uint32_t allowed_dofs;
+	uint32_t allow_sleeping;
+	uint32_t ray_flags;
+	uint64_t user_data;
+} orc_body_desc;
+
+typedef struct orc_world orc_world;
+
+orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const float gravity[3],
+							uint32_t velocity_steps, uint32_t position_steps);
+void orc_world_destroy(orc_world *w);
+/* static collision mesh = one static body; tris relative to (pos, rot) */
+uint32_t orc_static_add_mesh(orc_world *w, const float pos[3], const float rot[4], const float *tris, uint64_t ntris,
+							 float friction);
+void orc_static_commit(orc_world *w);
+uint32_t orc_body_create(orc_world *w, const orc_body_desc *d);
+void orc_body_destroy(orc_world *w, uint32_t id);
+void orc_body_set_velocity(orc_world *w, uint32_t id, const float v[3], const float av[3]);
+/* one tick = collision_steps sub-steps of dt/collision_steps; returns 0 or an error code (4 = contact constraints full) */
+int orc_step(orc_world *w, float dt, int collision_steps);
+/* state access: out = 7 floats pos+quat, 6 floats lin+ang */
+void orc_body_get(const orc_world *w, uint32_t id, float *xf7, float *vel6);
+uint32_t orc_body_active(const orc_world *w, uint32_t id);
+uint32_t orc_manifold_count(const orc_world *w);
+/* contact events of the last step: triples (a, b, kind) */
+uint32_t orc_events(const orc_world *w, uint32_t *out, uint32_t cap);
+/* closest-hit rays, brute force over every static triangle and every body */
+void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);
+uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_body, uint32_t cap);
+/* threads used by the *_mt helpers below (OpenMP) */
+int orc_max_threads(void);
+void orc_raycast_mt(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);
+/* step many independent worlds (array of handles) in parallel over host threads */
+int orc_step_many(orc_world **ws, uint32_t n, float dt, int collision_steps, int ticks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
