@@ -1,0 +1,731 @@
+// gpx_api.cu — the C ABI of include/gpx.h: world/body management, host mirror, command queue.
+// Host logic only; every compute entry point ends in a kernel launch from the other translation units.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gpx_internal.h"
+#include "gpx_math.cuh"
+
+namespace gpx {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+static int g_device = -1;
+
+void set_error(const char *what, cudaError_t e)
+{
+	g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+}
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static uint32_t pack_flags(const gpx_body_desc &d)
+{
+	uint32_t f = BF_ALIVE;
+	f |= (d.shape & 7u) << BF_SHAPE_SHIFT;
+	f |= (d.motion_type & 3u) << BF_MOTION_SHIFT;
+	f |= (d.layer & 3u) << BF_LAYER_SHIFT;
+	if (d.is_sensor) f |= BF_SENSOR;
+	f |= ((d.allowed_dofs ? d.allowed_dofs : 63u) & 63u) << BF_DOF_SHIFT;
+	if (d.allow_sleeping) f |= BF_ALLOW_SLEEP;
+	f |= (d.ray_flags & 0xFFu) << BF_RAYFLAG_SHIFT;
+	return f;
+}
+
+// JPH_MassProperties override + CalculateInertia (game/src/actor/prop/Physbox.c:27-32): the shape's inertia scaled
+// to the requested mass; density 1000 when no mass is given.
+static void mass_properties(const gpx_body_desc &d, float &inv_mass, float inv_i[3])
+{
+	inv_mass = 0.0f;
+	inv_i[0] = inv_i[1] = inv_i[2] = 0.0f;
+	if (d.motion_type != GPX_MOTION_DYNAMIC || d.shape == GPX_SHAPE_EMPTY) return;
+	float m, ix, iy, iz;
+	if (d.shape == GPX_SHAPE_BOX)
+	{
+		float sx = 2.0f * d.half_extents[0], sy = 2.0f * d.half_extents[1], sz = 2.0f * d.half_extents[2];
+		float vol = (sx * sy) * sz;
+		m = d.mass > 0.0f ? d.mass : 1000.0f * vol;
+		float k = m / 12.0f;
+		ix = k * ((sy * sy) + (sz * sz));
+		iy = k * ((sx * sx) + (sz * sz));
+		iz = k * ((sx * sx) + (sy * sy));
+	}
+	else
+	{
+		float r = d.half_extents[0];
+		float vol = (4.18879020f * r) * (r * r);
+		m = d.mass > 0.0f ? d.mass : 1000.0f * vol;
+		ix = iy = iz = (0.4f * m) * (r * r);
+	}
+	inv_mass = 1.0f / m;
+	inv_i[0] = 1.0f / ix;
+	inv_i[1] = 1.0f / iy;
+	inv_i[2] = 1.0f / iz;
+}
+
+static BodyCommand command_from_desc(uint32_t index, const gpx_body_desc &d)
+{
+	BodyCommand c;
+	memset(&c, 0, sizeof(c));
+	c.index = index;
+	c.mask = 31u;
+	c.flags = pack_flags(d);
+	c.pos = make_float4(d.position[0], d.position[1], d.position[2], 0.0f);
+	q4 q;
+	q.x = d.rotation[0]; q.y = d.rotation[1]; q.z = d.rotation[2]; q.w = d.rotation[3];
+	q = qnormalize(q);
+	c.quat = make_float4(q.x, q.y, q.z, q.w);
+	c.lin = make_float4(d.linear_velocity[0], d.linear_velocity[1], d.linear_velocity[2], 0.0f);
+	c.ang = make_float4(d.angular_velocity[0], d.angular_velocity[1], d.angular_velocity[2], 0.0f);
+	float im, ii[3];
+	mass_properties(d, im, ii);
+	c.prop0 = make_float4(im, ii[0], ii[1], ii[2]);
+	c.prop1 = make_float4(d.half_extents[0], d.half_extents[1], d.half_extents[2], d.friction);
+	c.prop2 = make_float4(d.linear_damping, d.angular_damping, d.gravity_factor, d.restitution);
+	return c;
+}
+
+// Push queued host writes to the device (one H2D + one scatter kernel).  Caller holds w->mu.
+static int flush_commands(gpx_world *w)
+{
+	const size_t n = w->pending.size();
+	if (n == 0) return GPX_OK;
+	if (n > w->d_cmd_cap)
+	{
+		if (w->d_cmd) cudaFree(w->d_cmd);
+		w->d_cmd_cap = n * 2;
+		GPX_CUDA(cudaMalloc(&w->d_cmd, sizeof(BodyCommand) * w->d_cmd_cap));
+	}
+	GPX_CUDA(cudaMemcpyAsync(w->d_cmd, w->pending.data(), sizeof(BodyCommand) * n, cudaMemcpyHostToDevice, w->stream));
+	int rc = launch_apply_commands(w, w->d_cmd, (uint32_t)n);
+	// the staging vector is pageable: wait so it can be reused
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	w->pending.clear();
+	return rc;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t n)
+{
+	GPX_CUDA(cudaMalloc(p, sizeof(T) * n));
+	GPX_CUDA(cudaMemset(*p, 0, sizeof(T) * n));
+	return GPX_OK;
+}
+
+}  // namespace gpx
+
+namespace {
+struct Cursor
+{
+	const uint8_t *d;
+	uint64_t n, o = 0;
+	bool bad = false;
+	template <typename T>
+	T get()
+	{
+		T v{};
+		if (o + sizeof(T) > n) { bad = true; return v; }
+		memcpy(&v, d + o, sizeof(T));
+		o += sizeof(T);
+		return v;
+	}
+	void skip(uint64_t k)
+	{
+		if (o + k > n || o + k < o) bad = true;
+		else o += k;
+	}
+	void skip_string() { uint64_t l = get<uint64_t>(); if (!bad) skip(l); }
+	void skip_param();
+	void skip_kvlist()
+	{
+		uint64_t k = get<uint64_t>();
+		for (uint64_t i = 0; i < k && !bad; i++) { skip_string(); skip_param(); }
+	}
+};
+void Cursor::skip_param()
+{
+	uint8_t t = get<uint8_t>();
+	switch (t)
+	{
+		case 0: case 3: skip(1); break;            /* byte, bool */
+		case 1: case 2: skip(4); break;            /* int, float */
+		case 4: skip_string(); break;
+		case 6: skip(16); break;                   /* colour */
+		case 7: skip_kvlist(); break;
+		case 8: { uint64_t k = get<uint64_t>(); for (uint64_t i = 0; i < k && !bad; i++) skip_param(); break; }
+		case 9: skip(8); break;
+		case 10: skip(8); break;
+		case 11: skip(12); break;
+		default: break;
+	}
+}
+}  // namespace
+
+using namespace gpx;
+
+extern "C" {
+
+int gpx_init(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+	{
+		set_error("gpx_init: no CUDA device (this library has no CPU path)", e == cudaSuccess ? cudaErrorNoDevice : e);
+		return -GPX_ERR_CUDA;
+	}
+	if (device < 0 || device >= n) return -GPX_ERR_INVALID_ARG;
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess)
+	{
+		set_error("cudaSetDevice", e);
+		return -GPX_ERR_CUDA;
+	}
+	g_device = device;
+	return GPX_ABI_VERSION;
+}
+
+void gpx_shutdown(void) { g_device = -1; }
+
+const char *gpx_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t gpx_launch_count(void) { return g_launches.load(); }
+
+gpx_world *gpx_world_create(const gpx_world_config *cfg)
+{
+	if (!cfg || cfg->worlds == 0 || cfg->max_bodies_per_world == 0 || cfg->max_bodies_per_world > 64) return nullptr;
+	if (cudaSetDevice(cfg->device) != cudaSuccess) return nullptr;
+	gpx_world *w = new gpx_world();
+	w->cfg = *cfg;
+	w->device = cfg->device;
+	w->W = cfg->worlds;
+	w->cap = cfg->max_bodies_per_world;
+	w->cap_m = cfg->max_manifolds_per_world ? cfg->max_manifolds_per_world : w->cap * 4u;
+	if (w->cap_m & 1u) w->cap_m++;
+	const size_t nb = (size_t)w->W * w->cap, nm = (size_t)w->W * w->cap_m;
+	bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess;
+	ok = ok && dalloc(&w->bs.pos, nb) == GPX_OK && dalloc(&w->bs.quat, nb) == GPX_OK && dalloc(&w->bs.lin, nb) == GPX_OK &&
+		 dalloc(&w->bs.ang, nb) == GPX_OK && dalloc(&w->bs.prop0, nb) == GPX_OK && dalloc(&w->bs.prop1, nb) == GPX_OK &&
+		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK;
+	ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
+		 dalloc(&w->mc.lt2, nm) == GPX_OK && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
+	ok = ok && dalloc(&w->d_err, (size_t)w->W + 1) == GPX_OK && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
+	ok = ok && cudaMallocHost(&w->m_pos, sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->m_quat, sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->m_lin, sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->m_ang, sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->m_err, sizeof(uint32_t) * 4) == cudaSuccess;
+	if (!ok)
+	{
+		set_error("gpx_world_create", cudaGetLastError());
+		gpx_world_destroy(w);
+		return nullptr;
+	}
+	memset(w->m_pos, 0, sizeof(float4) * nb);
+	memset(w->m_quat, 0, sizeof(float4) * nb);
+	memset(w->m_lin, 0, sizeof(float4) * nb);
+	memset(w->m_ang, 0, sizeof(float4) * nb);
+	w->m_err[0] = 0;
+	w->h_flags.assign(nb, 0u);
+	w->h_user_data.assign(nb, 0ull);
+	return w;
+}
+
+void gpx_world_destroy(gpx_world *w)
+{
+	if (!w) return;
+	cudaSetDevice(w->device);
+	if (w->stream) cudaStreamSynchronize(w->stream);
+	cudaFree(w->bs.pos); cudaFree(w->bs.quat); cudaFree(w->bs.lin); cudaFree(w->bs.ang);
+	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
+	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
+	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
+	cudaFree(w->d_rays); cudaFree(w->d_hits);
+	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
+	if (w->ev0) cudaEventDestroy(w->ev0);
+	if (w->ev1) cudaEventDestroy(w->ev1);
+	if (w->stream) cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+/* ---- static geometry */
+
+int gpx_static_add_mesh(gpx_world *w, const gpx_transform *xfm, const float *tris, uint64_t ntris, float friction,
+						uint64_t user_data, uint32_t *out_body)
+{
+	if (!w || !xfm || (!tris && ntris)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	if (w->cfg.max_static_triangles && w->h_tri_body.size() + ntris > w->cfg.max_static_triangles) return GPX_ERR_CAPACITY;
+	StaticBodyHost sb;
+	sb.xfm = *xfm;
+	sb.friction = friction;
+	sb.ray_flags = GPX_BODY_BLOCKS_LASERS;  // map geometry has no actor: lasers stop on it (Laser.c:74-85)
+	sb.user_data = user_data;
+	sb.first = (uint32_t)w->h_tri_body.size();
+	sb.count = (uint32_t)ntris;
+	const uint32_t k = (uint32_t)w->sbodies.size();
+	w->sbodies.push_back(sb);
+	q4 q;
+	q.x = xfm->rotation[0]; q.y = xfm->rotation[1]; q.z = xfm->rotation[2]; q.w = xfm->rotation[3];
+	const v3 p = V(xfm->position[0], xfm->position[1], xfm->position[2]);
+	for (uint64_t i = 0; i < ntris; i++)
+		for (int v = 0; v < 3; v++)
+		{
+			const float *t = tris + i * 9 + v * 3;
+			v3 pw = qrot(q, V(t[0], t[1], t[2])) + p;
+			w->h_tris.push_back(pw.x);
+			w->h_tris.push_back(pw.y);
+			w->h_tris.push_back(pw.z);
+		}
+	w->h_tri_body.insert(w->h_tri_body.end(), ntris, k);
+	w->static_dirty = true;
+	if (out_body) *out_body = STATIC_BODY_BASE + k;
+	return GPX_OK;
+}
+
+int gpx_static_commit(gpx_world *w)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	return build_static(w);
+}
+
+int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *n_bodies)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	if (n_tris) *n_tris = w->sd.n_tris;
+	if (n_nodes) *n_nodes = w->sd.n_nodes;
+	if (n_bodies) *n_bodies = (uint32_t)w->sbodies.size();
+	return GPX_OK;
+}
+
+/* Collision section of a decompressed .gmap (engine/src/assets/MapLoader.c:54-273): skip sky/strings/actors/models,
+ * then numCollisionMeshes x { pos, subShapeCount x { numTris x 9 f32 } }; each mesh becomes one static body with
+ * friction 4.25 (MapLoader.c:263). */
+
+int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size)
+{
+	if (!w || !body) return -GPX_ERR_INVALID_ARG;
+	Cursor c{body, size};
+	if (c.get<uint8_t>()) c.skip_string();
+	c.skip_string();
+	c.skip_string();
+	const uint64_t n_actors = c.get<uint64_t>();
+	for (uint64_t i = 0; i < n_actors && !c.bad; i++)
+	{
+		c.skip_string();
+		c.skip(24);
+		const uint64_t n_conn = c.get<uint64_t>();
+		for (uint64_t j = 0; j < n_conn && !c.bad; j++)
+		{
+			c.skip_string(); c.skip_string(); c.skip_string();
+			if (c.get<uint8_t>()) c.skip_param();
+			c.skip(8);
+		}
+		c.skip_kvlist();
+	}
+	const uint64_t n_models = c.get<uint64_t>();
+	for (uint64_t i = 0; i < n_models && !c.bad; i++)
+	{
+		c.skip_string();
+		c.skip((uint64_t)c.get<uint32_t>() * 28u);
+		c.skip((uint64_t)c.get<uint32_t>() * 4u);
+	}
+	const uint64_t n_meshes = c.get<uint64_t>();
+	int added = 0;
+	std::vector<float> tris;
+	for (uint64_t i = 0; i < n_meshes && !c.bad; i++)
+	{
+		gpx_transform xfm;
+		memset(&xfm, 0, sizeof(xfm));
+		xfm.rotation[3] = 1.0f;
+		xfm.position[0] = c.get<float>();
+		xfm.position[1] = c.get<float>();
+		xfm.position[2] = c.get<float>();
+		const uint64_t n_sub = c.get<uint64_t>();
+		if (n_sub == 0) continue;  // MapLoader.c:213-216
+		tris.clear();
+		for (uint64_t j = 0; j < n_sub && !c.bad; j++)
+		{
+			const uint64_t nt = c.get<uint64_t>();
+			if (c.bad || c.o + nt * 36u > c.n) { c.bad = true; break; }
+			const size_t at = tris.size();
+			tris.resize(at + nt * 9u);
+			memcpy(tris.data() + at, c.d + c.o, nt * 36u);
+			c.skip(nt * 36u);
+		}
+		if (c.bad) break;
+		int rc = gpx_static_add_mesh(w, &xfm, tris.data(), tris.size() / 9u, 4.25f, 0, nullptr);
+		if (rc != GPX_OK) return -rc;
+		added++;
+	}
+	if (c.bad) return -GPX_ERR_INVALID_ARG;
+	return added;
+}
+
+/* ---- bodies */
+
+static inline bool valid_slot(const gpx_world *w, uint32_t world, uint32_t body)
+{
+	return w && world < w->W && body < w->cap;
+}
+
+uint32_t gpx_body_create(gpx_world *w, uint32_t world, const gpx_body_desc *desc)
+{
+	if (!w || !desc || world >= w->W) return GPX_INVALID_BODY;
+	std::lock_guard<std::mutex> lk(w->mu);
+	const size_t base = (size_t)world * w->cap;
+	for (uint32_t i = 0; i < w->cap; i++)
+		if (!(w->h_flags[base + i] & BF_ALIVE))
+		{
+			BodyCommand c = command_from_desc((uint32_t)(base + i), *desc);
+			w->h_flags[base + i] = c.flags;
+			w->h_user_data[base + i] = desc->user_data;
+			w->m_pos[base + i] = c.pos;
+			w->m_quat[base + i] = c.quat;
+			w->m_lin[base + i] = c.lin;
+			w->m_ang[base + i] = c.ang;
+			w->pending.push_back(c);
+			return i;
+		}
+	return GPX_INVALID_BODY;
+}
+
+int gpx_body_create_all(gpx_world *w, const gpx_body_desc *descs, uint32_t count, const float *linvel, const float *angvel,
+						uint32_t *out_ids)
+{
+	if (!w || !descs) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	// same free slots in every world: take them from world 0 and require the same layout everywhere
+	std::vector<uint32_t> ids;
+	for (uint32_t i = 0; i < w->cap && ids.size() < count; i++)
+		if (!(w->h_flags[i] & BF_ALIVE)) ids.push_back(i);
+	if (ids.size() < count) return GPX_ERR_CAPACITY;
+	w->pending.reserve(w->pending.size() + (size_t)w->W * count);
+	for (uint32_t k = 0; k < count; k++)
+	{
+		BodyCommand proto = command_from_desc(0, descs[k]);
+		for (uint32_t wi = 0; wi < w->W; wi++)
+		{
+			const size_t g = (size_t)wi * w->cap + ids[k];
+			if (w->h_flags[g] & BF_ALIVE) return GPX_ERR_CAPACITY;
+			BodyCommand c = proto;
+			c.index = (uint32_t)g;
+			if (linvel)
+			{
+				const float *v = linvel + ((size_t)wi * count + k) * 3;
+				c.lin = make_float4(v[0], v[1], v[2], 0.0f);
+			}
+			if (angvel)
+			{
+				const float *v = angvel + ((size_t)wi * count + k) * 3;
+				c.ang = make_float4(v[0], v[1], v[2], 0.0f);
+			}
+			w->h_flags[g] = c.flags;
+			w->h_user_data[g] = descs[k].user_data;
+			w->m_pos[g] = c.pos;
+			w->m_quat[g] = c.quat;
+			w->m_lin[g] = c.lin;
+			w->m_ang[g] = c.ang;
+			w->pending.push_back(c);
+		}
+		if (out_ids) out_ids[k] = ids[k];
+	}
+	return GPX_OK;
+}
+
+int gpx_body_destroy(gpx_world *w, uint32_t world, uint32_t body)
+{
+	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	const size_t g = (size_t)world * w->cap + body;
+	if (!(w->h_flags[g] & BF_ALIVE)) return GPX_ERR_INVALID_ARG;
+	w->h_flags[g] = 0;
+	w->h_user_data[g] = 0;
+	BodyCommand c;
+	memset(&c, 0, sizeof(c));
+	c.index = (uint32_t)g;
+	c.mask = 31u;
+	c.quat = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+	w->pending.push_back(c);
+	return GPX_OK;
+}
+
+static int queue_write(gpx_world *w, uint32_t world, uint32_t body, uint32_t mask, const float *a, const float *b)
+{
+	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	const size_t g = (size_t)world * w->cap + body;
+	if (!(w->h_flags[g] & BF_ALIVE)) return GPX_ERR_INVALID_ARG;
+	BodyCommand c;
+	memset(&c, 0, sizeof(c));
+	c.index = (uint32_t)g;
+	c.mask = mask;
+	if (mask & 1u) w->m_pos[g] = c.pos = make_float4(a[0], a[1], a[2], 0.0f);
+	if (mask & 2u)
+	{
+		q4 q;
+		q.x = a[0]; q.y = a[1]; q.z = a[2]; q.w = a[3];
+		q = qnormalize(q);
+		w->m_quat[g] = c.quat = make_float4(q.x, q.y, q.z, q.w);
+	}
+	if (mask & 4u) w->m_lin[g] = c.lin = make_float4(a[0], a[1], a[2], 0.0f);
+	if (mask & 8u)
+	{
+		const float *s = (mask & 4u) ? b : a;
+		w->m_ang[g] = c.ang = make_float4(s[0], s[1], s[2], 0.0f);
+	}
+	w->pending.push_back(c);
+	return GPX_OK;
+}
+
+int gpx_body_set_linear_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3])
+{
+	return v ? queue_write(w, world, body, 4u, v, nullptr) : GPX_ERR_INVALID_ARG;
+}
+int gpx_body_set_linear_and_angular_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3], const float av[3])
+{
+	return (v && av) ? queue_write(w, world, body, 12u, v, av) : GPX_ERR_INVALID_ARG;
+}
+int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int /*activate*/)
+{
+	return p ? queue_write(w, world, body, 1u, p, nullptr) : GPX_ERR_INVALID_ARG;
+}
+int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int /*activate*/)
+{
+	return q ? queue_write(w, world, body, 2u, q, nullptr) : GPX_ERR_INVALID_ARG;
+}
+
+int gpx_body_get_transform(const gpx_world *w, uint32_t world, uint32_t body, gpx_transform *out)
+{
+	if (!out) return GPX_ERR_INVALID_ARG;
+	if (w && world < w->W && body >= STATIC_BODY_BASE && body - STATIC_BODY_BASE < w->sbodies.size())
+	{
+		*out = w->sbodies[body - STATIC_BODY_BASE].xfm;
+		return GPX_OK;
+	}
+	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
+	const size_t g = (size_t)world * w->cap + body;
+	const float4 p = w->m_pos[g], q = w->m_quat[g];
+	out->position[0] = p.x; out->position[1] = p.y; out->position[2] = p.z;
+	out->rotation[0] = q.x; out->rotation[1] = q.y; out->rotation[2] = q.z; out->rotation[3] = q.w;
+	return GPX_OK;
+}
+
+int gpx_body_get_world_matrix(const gpx_world *w, uint32_t world, uint32_t body, float m[16])
+{
+	gpx_transform t;
+	int rc = gpx_body_get_transform(w, world, body, &t);
+	if (rc != GPX_OK) return rc;
+	q4 q;
+	q.x = t.rotation[0]; q.y = t.rotation[1]; q.z = t.rotation[2]; q.w = t.rotation[3];
+	m33 R = qmat(q);
+	/* column-major 4x4, as cglm/Jolt Mat44 (engine/src/graphics/RenderingHelpers.c:101-126) */
+	m[0] = R.c0.x; m[1] = R.c0.y; m[2] = R.c0.z; m[3] = 0.0f;
+	m[4] = R.c1.x; m[5] = R.c1.y; m[6] = R.c1.z; m[7] = 0.0f;
+	m[8] = R.c2.x; m[9] = R.c2.y; m[10] = R.c2.z; m[11] = 0.0f;
+	m[12] = t.position[0]; m[13] = t.position[1]; m[14] = t.position[2]; m[15] = 1.0f;
+	return GPX_OK;
+}
+
+int gpx_body_get_velocity(const gpx_world *w, uint32_t world, uint32_t body, float v[3], float av[3])
+{
+	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
+	const size_t g = (size_t)world * w->cap + body;
+	if (v) { v[0] = w->m_lin[g].x; v[1] = w->m_lin[g].y; v[2] = w->m_lin[g].z; }
+	if (av) { av[0] = w->m_ang[g].x; av[1] = w->m_ang[g].y; av[2] = w->m_ang[g].z; }
+	return GPX_OK;
+}
+
+uint64_t gpx_body_get_user_data(const gpx_world *w, uint32_t world, uint32_t body)
+{
+	if (w && body >= STATIC_BODY_BASE && body - STATIC_BODY_BASE < w->sbodies.size())
+		return w->sbodies[body - STATIC_BODY_BASE].user_data;
+	if (!valid_slot(w, world, body)) return 0;
+	return w->h_user_data[(size_t)world * w->cap + body];
+}
+
+int gpx_body_is_active(const gpx_world *w, uint32_t world, uint32_t body)
+{
+	if (!valid_slot(w, world, body)) return 0;
+	return (w->h_flags[(size_t)world * w->cap + body] & BF_ALIVE) ? 1 : 0;
+}
+
+/* ---- tick */
+
+int gpx_step(gpx_world *w, float dt, int collision_steps)
+{
+	if (!w || !(dt > 0.0f)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	if ((rc = launch_tick(w, dt, collision_steps)) != GPX_OK) return rc;
+	w->ticks++;
+	return (int)w->m_err[0];
+}
+
+int gpx_sync_transforms(gpx_world *w)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	const size_t nb = (size_t)w->W * w->cap;
+	GPX_CUDA(cudaMemcpyAsync(w->m_pos, w->bs.pos, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(w->m_quat, w->bs.quat, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(w->m_err, w->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return (int)w->m_err[0];
+}
+
+int gpx_read_transforms(gpx_world *w, gpx_transform *out, uint64_t capacity)
+{
+	if (!w || !out) return GPX_ERR_INVALID_ARG;
+	const size_t nb = (size_t)w->W * w->cap;
+	if (capacity < nb) return GPX_ERR_CAPACITY;
+	int rc = gpx_sync_transforms(w);
+	for (size_t g = 0; g < nb; g++)
+	{
+		const float4 p = w->m_pos[g], q = w->m_quat[g];
+		out[g].position[0] = p.x; out[g].position[1] = p.y; out[g].position[2] = p.z;
+		out[g].rotation[0] = q.x; out[g].rotation[1] = q.y; out[g].rotation[2] = q.z; out[g].rotation[3] = q.w;
+	}
+	return rc;
+}
+
+int gpx_read_velocities(gpx_world *w, float *out, uint64_t capacity)
+{
+	if (!w || !out) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	const size_t nb = (size_t)w->W * w->cap;
+	if (capacity < nb) return GPX_ERR_CAPACITY;
+	int rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	GPX_CUDA(cudaMemcpyAsync(w->m_lin, w->bs.lin, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(w->m_ang, w->bs.ang, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	for (size_t g = 0; g < nb; g++)
+	{
+		out[6 * g + 0] = w->m_lin[g].x; out[6 * g + 1] = w->m_lin[g].y; out[6 * g + 2] = w->m_lin[g].z;
+		out[6 * g + 3] = w->m_ang[g].x; out[6 * g + 4] = w->m_ang[g].y; out[6 * g + 5] = w->m_ang[g].z;
+	}
+	return GPX_OK;
+}
+
+int gpx_read_stats(gpx_world *w, gpx_world_stats *out)
+{
+	if (!w || !out) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	if ((rc = launch_stats(w)) != GPX_OK) return rc;
+	GPX_CUDA(cudaMemcpyAsync(out, w->d_stats, sizeof(gpx_world_stats) * w->W, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+
+/* ---- rays */
+
+int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
+{
+	if (!w || (n && (!d_rays || !d_hits))) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	return launch_raycast(w, d_rays, n, d_hits);
+}
+
+int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
+{
+	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
+	if (n == 0) return GPX_OK;
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		cudaSetDevice(w->device);
+		if (n > w->ray_cap)
+		{
+			cudaFree(w->d_rays);
+			cudaFree(w->d_hits);
+			w->d_rays = w->d_hits = nullptr;
+			w->ray_cap = 0;
+			GPX_CUDA(cudaMalloc(&w->d_rays, sizeof(gpx_ray) * n));
+			GPX_CUDA(cudaMalloc(&w->d_hits, sizeof(gpx_hit) * n));
+			w->ray_cap = n;
+		}
+		GPX_CUDA(cudaMemcpyAsync(w->d_rays, rays, sizeof(gpx_ray) * n, cudaMemcpyHostToDevice, w->stream));
+	}
+	int rc = gpx_raycast_batch_device(w, w->d_rays, n, w->d_hits);
+	if (rc != GPX_OK) return rc;
+	GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+
+int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *origin, float max_distance, uint32_t mask,
+						  gpx_hit *out)
+{
+	if (!w || !origin || !out || world >= w->W) return GPX_ERR_INVALID_ARG;
+	gpx_ray r;
+	q4 q;
+	q.x = origin->rotation[0]; q.y = origin->rotation[1]; q.z = origin->rotation[2]; q.w = origin->rotation[3];
+	const v3 d = qrot(q, V(0.0f, 0.0f, -1.0f));  // forward = local -Z (PlayerPhysics.c:360, LaserEmitter.c:105-110)
+	r.origin[0] = origin->position[0]; r.origin[1] = origin->position[1]; r.origin[2] = origin->position[2];
+	r.tmax = max_distance;
+	r.dir[0] = d.x; r.dir[1] = d.y; r.dir[2] = d.z;
+	r.mask = (mask & 0xFFFFu) | (world << 16);
+	return gpx_raycast_batch(w, &r, 1, out);
+}
+
+/* ---- harness helpers */
+
+void *gpx_device_alloc(uint64_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+	return p;
+}
+void gpx_device_free(void *p) { cudaFree(p); }
+int gpx_memcpy_h2d(void *dst, const void *src, uint64_t bytes)
+{
+	GPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+	return GPX_OK;
+}
+int gpx_memcpy_d2h(void *dst, const void *src, uint64_t bytes)
+{
+	GPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	return GPX_OK;
+}
+int gpx_device_sync(gpx_world *w)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+int gpx_timer_begin(gpx_world *w)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	GPX_CUDA(cudaEventRecord(w->ev0, w->stream));
+	return GPX_OK;
+}
+float gpx_timer_end(gpx_world *w)
+{
+	if (!w) return -1.0f;
+	if (cudaEventRecord(w->ev1, w->stream) != cudaSuccess) return -1.0f;
+	if (cudaEventSynchronize(w->ev1) != cudaSuccess) return -1.0f;
+	float ms = -1.0f;
+	cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+	return ms;
+}
+
+}  // extern "C"

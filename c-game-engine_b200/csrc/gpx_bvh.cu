@@ -1,0 +1,362 @@
+// gpx_bvh.cu — LBVH over the map's static collision triangles, built on the device.
+//
+// Replaces what JPH_PhysicsSystem_OptimizeBroadPhase + MeshShape tree construction do for the reference at map
+// load (engine/src/assets/MapLoader.c:200-273): the zlib-decompressed triangles are uploaded once, Morton-sorted,
+// linked into a binary radix tree (Karras 2012) and refitted bottom-up.  Output is two flat float4 arrays laid out
+// for the traversal kernels: 64-byte nodes that carry BOTH children's boxes, and 64-byte triangle records in leaf
+// order.  The whole tree of a shipped map (<= 2k triangles) is <= 250 KB and is read through shared memory / L2.
+#include <cfloat>
+
+#include "gpx_internal.h"
+#include "gpx_math.cuh"
+
+namespace gpx {
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+
+// key = 30-bit Morton code of the centroid (high word) | original triangle index (low word): unique, so the radix
+// tree never has to break ties.
+__global__ void k_morton_keys(const float *__restrict__ tris, uint32_t n, uint32_t n_pad, float3 lo, float3 inv_ext,
+							  unsigned long long *__restrict__ keys)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pad) return;
+	if (i >= n)
+	{
+		keys[i] = ~0ull;
+		return;
+	}
+	const float *t = tris + 9ull * i;
+	float cx = (t[0] + t[3] + t[6]) * (1.0f / 3.0f), cy = (t[1] + t[4] + t[7]) * (1.0f / 3.0f),
+		  cz = (t[2] + t[5] + t[8]) * (1.0f / 3.0f);
+	float fx = fminf(fmaxf((cx - lo.x) * inv_ext.x * 1024.0f, 0.0f), 1023.0f);
+	float fy = fminf(fmaxf((cy - lo.y) * inv_ext.y * 1024.0f, 0.0f), 1023.0f);
+	float fz = fminf(fmaxf((cz - lo.z) * inv_ext.z * 1024.0f, 0.0f), 1023.0f);
+	uint32_t m = (expand_bits10((uint32_t)fx) << 2) | (expand_bits10((uint32_t)fy) << 1) | expand_bits10((uint32_t)fz);
+	keys[i] = ((unsigned long long)m << 32) | i;
+}
+
+// One compare-exchange pass of a bitonic network over a power-of-two key array.
+__global__ void k_bitonic_pass(unsigned long long *keys, uint32_t n_pad, uint32_t j, uint32_t k)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pad) return;
+	uint32_t p = i ^ j;
+	if (p > i)
+	{
+		unsigned long long a = keys[i], b = keys[p];
+		bool up = (i & k) == 0;
+		if ((a > b) == up)
+		{
+			keys[i] = b;
+			keys[p] = a;
+		}
+	}
+}
+
+// All passes with stride < 1024 of one merge stage run inside a CTA's shared memory.
+__global__ void k_bitonic_smem(unsigned long long *keys, uint32_t n_pad, uint32_t k_first, uint32_t k_last,
+							   uint32_t j_start_for_first)
+{
+	__shared__ unsigned long long s[2048];
+	const uint32_t base = blockIdx.x * 2048u;
+	for (uint32_t t = threadIdx.x; t < 2048u; t += blockDim.x) s[t] = (base + t < n_pad) ? keys[base + t] : ~0ull;
+	__syncthreads();
+	for (uint32_t k = k_first; k <= k_last; k <<= 1)
+	{
+		uint32_t j0 = (k == k_first) ? j_start_for_first : (k >> 1);
+		for (uint32_t j = j0; j > 0; j >>= 1)
+		{
+			for (uint32_t t = threadIdx.x; t < 2048u; t += blockDim.x)
+			{
+				uint32_t i = t, p = t ^ j;
+				if (p > i)
+				{
+					unsigned long long a = s[i], b = s[p];
+					bool up = ((base + i) & k) == 0;
+					if ((a > b) == up)
+					{
+						s[i] = b;
+						s[p] = a;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	}
+	for (uint32_t t = threadIdx.x; t < 2048u; t += blockDim.x)
+		if (base + t < n_pad) keys[base + t] = s[t];
+}
+
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j)
+{
+	if (j < 0 || j >= n) return -1;
+	return __clzll(keys[i] ^ keys[j]);
+}
+
+// Karras 2012: internal node i covers a key range found by binary search on common-prefix length.
+// child >= 0: internal node; child < 0: leaf ~child.
+__global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, int2 *__restrict__ children,
+							int *__restrict__ parent_internal, int *__restrict__ parent_leaf)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n - 1) return;
+	int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	int dmin = delta(keys, n, i, i - d);
+	int lmax = 2;
+	while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+	int l = 0;
+	for (int t = lmax >> 1; t >= 1; t >>= 1)
+		if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+	int j = i + l * d;
+	int dnode = delta(keys, n, i, j);
+	int s = 0;
+	for (int t = (l + 1) >> 1;; t = (t + 1) >> 1)
+	{
+		if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+		if (t <= 1) break;
+	}
+	int gamma = i + s * d + min(d, 0);
+	int lo = min(i, j), hi = max(i, j);
+	int2 c;
+	if (lo == gamma)
+	{
+		c.x = ~gamma;
+		parent_leaf[gamma] = i;
+	}
+	else
+	{
+		c.x = gamma;
+		parent_internal[gamma] = i;
+	}
+	if (hi == gamma + 1)
+	{
+		c.y = ~(gamma + 1);
+		parent_leaf[gamma + 1] = i;
+	}
+	else
+	{
+		c.y = gamma + 1;
+		parent_internal[gamma + 1] = i;
+	}
+	children[i] = c;
+	if (i == 0) parent_internal[0] = -1;
+}
+
+__device__ __forceinline__ void tri_bounds(const float *t, float3 &lo, float3 &hi)
+{
+	lo.x = fminf(t[0], fminf(t[3], t[6]));
+	lo.y = fminf(t[1], fminf(t[4], t[7]));
+	lo.z = fminf(t[2], fminf(t[5], t[8]));
+	hi.x = fmaxf(t[0], fmaxf(t[3], t[6]));
+	hi.y = fmaxf(t[1], fmaxf(t[4], t[7]));
+	hi.z = fmaxf(t[2], fmaxf(t[5], t[8]));
+}
+
+// Bottom-up refit: the second thread to reach a node owns it (its sibling subtree is complete and fenced).
+__global__ void k_refit(const float *__restrict__ tris, const unsigned long long *__restrict__ keys, int n,
+						const int2 *__restrict__ children, const int *__restrict__ parent_internal,
+						const int *__restrict__ parent_leaf, float *lo_out, float *hi_out, int *visit)
+{
+	int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if (leaf >= n) return;
+	int node = parent_leaf[leaf];
+	while (node >= 0)
+	{
+		__threadfence();
+		if (atomicAdd(&visit[node], 1) == 0) return;
+		float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+		int2 c = children[node];
+		int cc[2] = {c.x, c.y};
+#pragma unroll
+		for (int k = 0; k < 2; k++)
+		{
+			float3 l, h;
+			if (cc[k] < 0)
+				tri_bounds(tris + 9ull * (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), l, h);
+			else
+			{
+				volatile float *vl = lo_out + 3 * cc[k], *vh = hi_out + 3 * cc[k];
+				l = make_float3(vl[0], vl[1], vl[2]);
+				h = make_float3(vh[0], vh[1], vh[2]);
+			}
+			lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+			hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
+		}
+		lo_out[3 * node + 0] = lo.x; lo_out[3 * node + 1] = lo.y; lo_out[3 * node + 2] = lo.z;
+		hi_out[3 * node + 0] = hi.x; hi_out[3 * node + 1] = hi.y; hi_out[3 * node + 2] = hi.z;
+		node = parent_internal[node];
+	}
+}
+
+// Emit traversal nodes (both children's padded boxes per node) and leaf-ordered triangle records.
+__global__ void k_pack(const float *__restrict__ tris, const uint32_t *__restrict__ tri_body,
+					   const float *__restrict__ body_friction, const uint32_t *__restrict__ body_rayflags,
+					   const unsigned long long *__restrict__ keys, int n, const int2 *__restrict__ children,
+					   const float *__restrict__ lo_in, const float *__restrict__ hi_in, float4 *__restrict__ nodes,
+					   float4 *__restrict__ tri_out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		uint32_t orig = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+		const float *t = tris + 9ull * orig;
+		v3 a = V(t[0], t[1], t[2]), b = V(t[3], t[4], t[5]), c = V(t[6], t[7], t[8]);
+		v3 nn = cross(b - a, c - a);
+		float l = len(nn);
+		v3 nu = l > 0.0f ? nn * (1.0f / l) : V(0.0f, 1.0f, 0.0f);
+		uint32_t body = tri_body[orig];
+		tri_out[4 * i + 0] = F4(a, __uint_as_float(orig));
+		tri_out[4 * i + 1] = F4(b, __uint_as_float(body));
+		tri_out[4 * i + 2] = F4(c, body_friction[body]);
+		tri_out[4 * i + 3] = F4(nu, __uint_as_float(body_rayflags[body]));
+	}
+	int n_nodes = n > 1 ? n - 1 : 1;
+	if (i < n_nodes)
+	{
+		int2 c = n > 1 ? children[i] : make_int2(~0, ~0);
+		int cc[2] = {c.x, c.y};
+		float3 lo[2], hi[2];
+#pragma unroll
+		for (int k = 0; k < 2; k++)
+		{
+			if (n == 1 && k == 1)
+			{
+				// single-triangle map: the second child is an empty box that no query can enter
+				lo[k] = make_float3(FLT_MAX, FLT_MAX, FLT_MAX);
+				hi[k] = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+				continue;
+			}
+			if (cc[k] < 0)
+				tri_bounds(tris + 9ull * (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), lo[k], hi[k]);
+			else
+			{
+				lo[k] = make_float3(lo_in[3 * cc[k]], lo_in[3 * cc[k] + 1], lo_in[3 * cc[k] + 2]);
+				hi[k] = make_float3(hi_in[3 * cc[k]], hi_in[3 * cc[k] + 1], hi_in[3 * cc[k] + 2]);
+			}
+			lo[k].x -= BVH_PAD; lo[k].y -= BVH_PAD; lo[k].z -= BVH_PAD;
+			hi[k].x += BVH_PAD; hi[k].y += BVH_PAD; hi[k].z += BVH_PAD;
+		}
+		nodes[4 * i + 0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+		nodes[4 * i + 1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+		nodes[4 * i + 2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+		nodes[4 * i + 3] = make_float4(__int_as_float(cc[0]), __int_as_float(cc[1]), 0.0f, 0.0f);
+	}
+}
+
+static uint32_t next_pow2(uint32_t v)
+{
+	uint32_t p = 1;
+	while (p < v) p <<= 1;
+	return p;
+}
+
+int build_static(gpx_world *w)
+{
+	StaticDevice &sd = w->sd;
+	if (sd.tri) cudaFree(sd.tri);
+	if (sd.nodes) cudaFree(sd.nodes);
+	sd.tri = sd.nodes = nullptr;
+	const uint32_t n = (uint32_t)w->h_tri_body.size();
+	sd.n_tris = n;
+	sd.n_nodes = n == 0 ? 0 : (n > 1 ? n - 1 : 1);
+	w->static_dirty = false;
+	if (n == 0) return GPX_OK;
+
+	// scene bounds on the host (it already walks every vertex while appending)
+	float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	for (size_t i = 0; i < w->h_tris.size(); i++)
+	{
+		float v = w->h_tris[i];
+		int a = (int)(i % 3);
+		lo[a] = v < lo[a] ? v : lo[a];
+		hi[a] = v > hi[a] ? v : hi[a];
+	}
+	float3 flo = make_float3(lo[0], lo[1], lo[2]);
+	float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.0f,
+							 hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.0f);
+
+	std::vector<float> fr(w->sbodies.size());
+	std::vector<uint32_t> rf(w->sbodies.size());
+	for (size_t i = 0; i < w->sbodies.size(); i++)
+	{
+		fr[i] = w->sbodies[i].friction;
+		rf[i] = w->sbodies[i].ray_flags;
+	}
+
+	const uint32_t n_pad = next_pow2(n);
+	float *d_tris = nullptr, *d_fr = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+	uint32_t *d_body = nullptr, *d_rf = nullptr;
+	unsigned long long *d_keys = nullptr;
+	int2 *d_children = nullptr;
+	int *d_pi = nullptr, *d_pl = nullptr, *d_visit = nullptr;
+	cudaStream_t st = w->stream;
+	GPX_CUDA(cudaMalloc(&d_tris, sizeof(float) * 9ull * n));
+	GPX_CUDA(cudaMalloc(&d_body, sizeof(uint32_t) * n));
+	GPX_CUDA(cudaMalloc(&d_fr, sizeof(float) * fr.size()));
+	GPX_CUDA(cudaMalloc(&d_rf, sizeof(uint32_t) * rf.size()));
+	GPX_CUDA(cudaMalloc(&d_keys, sizeof(unsigned long long) * n_pad));
+	GPX_CUDA(cudaMalloc(&d_children, sizeof(int2) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_pi, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_pl, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_visit, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_lo, sizeof(float) * 3ull * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_hi, sizeof(float) * 3ull * (n + 1)));
+	GPX_CUDA(cudaMalloc(&sd.tri, sizeof(float4) * 4ull * n));
+	GPX_CUDA(cudaMalloc(&sd.nodes, sizeof(float4) * 4ull * sd.n_nodes));
+	GPX_CUDA(cudaMemcpyAsync(d_tris, w->h_tris.data(), sizeof(float) * 9ull * n, cudaMemcpyHostToDevice, st));
+	GPX_CUDA(cudaMemcpyAsync(d_body, w->h_tri_body.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+	GPX_CUDA(cudaMemcpyAsync(d_fr, fr.data(), sizeof(float) * fr.size(), cudaMemcpyHostToDevice, st));
+	GPX_CUDA(cudaMemcpyAsync(d_rf, rf.data(), sizeof(uint32_t) * rf.size(), cudaMemcpyHostToDevice, st));
+	GPX_CUDA(cudaMemsetAsync(d_visit, 0, sizeof(int) * (n + 1), st));
+	GPX_CUDA(cudaMemsetAsync(d_pl, 0xFF, sizeof(int) * (n + 1), st));
+
+	const uint32_t tb = 256;
+	k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, n, n_pad, flo, inv, d_keys);
+	count_launch();
+	// bitonic sort: strides >= 2048 go through global memory, the rest of each stage runs in shared memory
+	if (n_pad <= 2048)
+	{
+		k_bitonic_smem<<<1, 1024, 0, st>>>(d_keys, n_pad, 2, n_pad, 1);
+		count_launch();
+	}
+	else
+	{
+		k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, 2, 2048, 1);
+		count_launch();
+		for (uint32_t k = 4096; k <= n_pad; k <<= 1)
+		{
+			for (uint32_t j = k >> 1; j >= 2048; j >>= 1)
+			{
+				k_bitonic_pass<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_keys, n_pad, j, k);
+				count_launch();
+			}
+			k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, k, k, 1024);
+			count_launch();
+		}
+	}
+	if (n > 1)
+	{
+		k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);
+		count_launch();
+		k_refit<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_keys, (int)n, d_children, d_pi, d_pl, d_lo, d_hi, d_visit);
+		count_launch();
+	}
+	k_pack<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_body, d_fr, d_rf, d_keys, (int)n, d_children, d_lo, d_hi, sd.nodes,
+											 sd.tri);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	GPX_CUDA(cudaStreamSynchronize(st));
+	cudaFree(d_tris); cudaFree(d_body); cudaFree(d_fr); cudaFree(d_rf); cudaFree(d_keys); cudaFree(d_children);
+	cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_visit); cudaFree(d_lo); cudaFree(d_hi);
+	return GPX_OK;
+}
+
+}  // namespace gpx

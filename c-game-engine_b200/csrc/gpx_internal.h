@@ -1,0 +1,146 @@
+// gpx_internal.h — host-side world object and kernel entry points shared by the libgpx translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/gpx.h"
+
+namespace gpx {
+
+constexpr uint32_t STATIC_BODY_BASE = 0x400000u;  // ids >= this name static collision meshes (shared by all worlds)
+constexpr float RAY_MISS_FRACTION = 2.0f;
+constexpr float BVH_PAD = 1.0e-3f;  // node boxes are padded; leaves are re-tested exactly
+
+// body flag word
+constexpr uint32_t BF_ALIVE = 1u;
+constexpr uint32_t BF_SHAPE_SHIFT = 1;   // 3 bits
+constexpr uint32_t BF_MOTION_SHIFT = 4;  // 2 bits
+constexpr uint32_t BF_LAYER_SHIFT = 6;   // 2 bits
+constexpr uint32_t BF_SENSOR = 1u << 8;
+constexpr uint32_t BF_DOF_SHIFT = 9;     // 6 bits
+constexpr uint32_t BF_ALLOW_SLEEP = 1u << 15;
+constexpr uint32_t BF_RAYFLAG_SHIFT = 16;  // 8 bits
+
+// Structure-of-arrays body store in HBM; index = world * cap + slot.  Every array is 16-byte vectorised.
+struct BodyStore
+{
+	float4 *pos;    // xyz, w unused
+	float4 *quat;   // xyzw
+	float4 *lin;    // linear velocity xyz
+	float4 *ang;    // angular velocity xyz
+	float4 *prop0;  // inv mass, local inverse inertia diagonal xyz
+	float4 *prop1;  // half extents xyz (sphere: radius in x), friction
+	float4 *prop2;  // linear damping, angular damping, gravity factor, restitution
+	uint32_t *flags;
+};
+
+// Contact cache carried between sub-steps and ticks (warm starting); index = world * cap_m + m
+struct ManifoldCache
+{
+	uint4 *key;       // a, b, np, 0
+	float4 *p1;       // 4 per manifold: local point on a, w = normal lambda
+	float4 *p2;       // 4 per manifold: local point on b (static: world), w = tangent-1 lambda
+	float4 *lt2;      // tangent-2 lambdas of the 4 points
+	uint32_t *count;  // per world
+};
+
+struct StaticDevice
+{
+	uint32_t n_tris = 0, n_nodes = 0;
+	float4 *tri = nullptr;    // 4 float4 per triangle in LBVH order: (a, orig index) (b, static body) (c, friction) (n, ray flags)
+	float4 *nodes = nullptr;  // 4 float4 per internal node: c0 xy bounds, c1 xy bounds, both z bounds, child indices
+};
+
+struct BodyCommand  // host -> device write, applied by k_apply_commands before the next step
+{
+	uint32_t index;
+	uint32_t mask;  // 1 pos, 2 quat, 4 lin, 8 ang, 16 props+flags
+	uint32_t flags;
+	uint32_t pad;
+	float4 pos, quat, lin, ang, prop0, prop1, prop2;
+};
+
+struct StaticBodyHost
+{
+	gpx_transform xfm;
+	float friction;
+	uint32_t ray_flags;
+	uint64_t user_data;
+	uint32_t first, count;
+};
+
+struct TickParams
+{
+	uint32_t worlds, cap, cap_m;
+	uint32_t vel_steps, pos_steps;
+	float gx, gy, gz;
+	float h;  // sub-step
+	int substeps;
+};
+
+}  // namespace gpx
+
+struct gpx_world
+{
+	gpx_world_config cfg{};
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	uint32_t W = 0, cap = 0, cap_m = 0;
+
+	// static soup (host staging, world space) + device LBVH
+	std::vector<float> h_tris;
+	std::vector<uint32_t> h_tri_body;
+	std::vector<gpx::StaticBodyHost> sbodies;
+	bool static_dirty = false;
+	gpx::StaticDevice sd;
+
+	// bodies
+	gpx::BodyStore bs{};
+	gpx::ManifoldCache mc{};
+	std::vector<uint32_t> h_flags;      // host shadow of the flag word (slot allocation, getters)
+	std::vector<uint64_t> h_user_data;  // Actor* per body
+	std::vector<gpx::BodyCommand> pending;
+	gpx::BodyCommand *d_cmd = nullptr;
+	size_t d_cmd_cap = 0;
+	std::mutex mu;  // guards pending/h_flags: create/destroy/set arrive from several engine threads
+
+	// host mirror (pinned) served to getters
+	float4 *m_pos = nullptr, *m_quat = nullptr, *m_lin = nullptr, *m_ang = nullptr;
+	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors
+	uint32_t *m_err = nullptr;  // pinned
+	gpx_world_stats *d_stats = nullptr;
+	uint32_t ticks = 0;
+
+	// ray staging
+	void *d_rays = nullptr, *d_hits = nullptr;
+	size_t ray_cap = 0;
+};
+
+namespace gpx {
+// gpx_bvh.cu
+int build_static(gpx_world *w);
+// gpx_rays.cu
+int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
+// gpx_tick.cu
+int launch_tick(gpx_world *w, float dt, int substeps);
+int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n);
+int launch_stats(gpx_world *w);
+// gpx_api.cu
+void set_error(const char *what, cudaError_t e);
+void count_launch(uint64_t n = 1);
+}  // namespace gpx
+
+#define GPX_CUDA(call)                                         \
+	do                                                         \
+	{                                                          \
+		cudaError_t e_ = (call);                               \
+		if (e_ != cudaSuccess)                                 \
+		{                                                      \
+			gpx::set_error(#call, e_);                         \
+			return GPX_ERR_CUDA;                               \
+		}                                                      \
+	} while (0)

@@ -1,0 +1,975 @@
+// gpx_tick.cu — the fixed-timestep physics tick, one fused kernel per tick for an ensemble of small worlds.
+//
+// Replaces JPH_PhysicsSystem_Update(system, dt, collisionSteps = 2, jobSystem) as the reference calls it from
+// MapFixedUpdate (engine/src/physics/MapPhysics.c:105-108).  One TILE of lanes owns one world; the world's bodies,
+// contact manifolds and warm-start cache live in shared memory for the whole tick, so HBM sees each body exactly
+// once in and once out per tick (the structure-of-arrays body store, float4 loads/stores, lane = body).
+//
+// Phases of a sub-step (barriers are tile-wide; a tile never spans warps):
+//   1 lane/body     gravity, damping, velocity clamp, world inverse inertia, AABB          ("integrate velocities")
+//   2 lane/body     LBVH box query -> candidate triangles; box/sphere vs triangle SAT + face clipping;
+//                   manifolds grouped by normal per static body                           ("narrowphase vs map")
+//   3 lane/body     all-pairs AABB sweep over the world's <= 64 bodies -> ordered pair list ("broadphase")
+//   4 lane/pair     box-box / sphere contact manifolds, one thread per pair               ("narrowphase")
+//   5 lane/manifold match against the previous sub-step's cache, carry impulses           ("warm start")
+//   6 lane 0        greedy graph colouring in canonical manifold order
+//   7 lane/manifold constraint set-up; then per colour: warm start, 10 x velocity solve   ("coloured Gauss-Seidel")
+//   8 lane/body     integrate positions and rotations                                      ("integrate")
+//   9 lane/manifold per colour: 2 x Baumgarte position solve
+// The solve order (colour, manifold index) and every arithmetic expression are fixed, so results are reproducible
+// and identical for any TILE width.
+#include <cooperative_groups.h>
+
+#include "gpx_internal.h"
+#include "gpx_narrow.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gpx {
+
+struct SBody  // 39 words: odd stride, conflict-free when lane = body
+{
+	v3 x;
+	q4 q;
+	v3 v, w;
+	float im;    // inverse mass as seen by the solver (0 unless dynamic)
+	float M[6];  // world inverse inertia xx xy xz yy yz zz
+	v3 he;
+	float friction, restitution, lin_damp, ang_damp, grav;
+	uint32_t flags;
+	v3 inv_i;
+	v3 lo, hi;
+	float inv_mass;  // as stored in the body store
+};
+
+struct SMan  // 91 words
+{
+	uint32_t a, b;
+	v3 n;
+	int np;      // 0 = empty slot (pair that did not touch)
+	int colour;
+	float friction, restitution;
+	v3 t1, t2;
+	v3 p1l[4], p2l[4];
+	float ln[4], lt1[4], lt2[4];
+	float bias[4];
+	v3 r1[4], r2[4];
+	float em[4][3];
+};
+
+struct SPrev  // 39 words
+{
+	uint32_t a, b, np;
+	v3 p1l[4], p2l[4];
+	float ln[4], lt1[4], lt2[4];
+};
+
+struct TickArgs
+{
+	BodyStore bs;
+	ManifoldCache mc;
+	const float4 *nodes;
+	const float4 *tris;
+	uint32_t n_nodes;
+	uint32_t *err;  // [0] OR of all worlds' errors, [1 + world] per world
+	TickParams p;
+};
+
+__host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
+{
+	size_t b = 0;
+	b += sizeof(unsigned long long) * cap;            // per-body pair masks / colour sets (first: 8-byte aligned)
+	b += sizeof(SBody) * cap;
+	b += sizeof(SMan) * cap_m;
+	b += sizeof(SPrev) * cap_m;
+	b += sizeof(uint32_t) * 2 * cap_m;                // pair list (a, b)
+	b += sizeof(uint32_t) * 2 * cap;                  // per-body counts, bases
+	b += sizeof(uint32_t) * 8;                        // header
+	return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ bool is_dynamic(uint32_t f) { return ((f >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_DYNAMIC; }
+__device__ __forceinline__ uint32_t shape_of(uint32_t f) { return (f >> BF_SHAPE_SHIFT) & 7u; }
+__device__ __forceinline__ uint32_t layer_of(uint32_t f) { return (f >> BF_LAYER_SHIFT) & 3u; }
+__device__ __forceinline__ uint32_t dofs_of(uint32_t f) { return (f >> BF_DOF_SHIFT) & 63u; }
+
+__device__ __forceinline__ v3 mask_lin(uint32_t dofs, v3 a)
+{
+	if (!(dofs & 1u)) a.x = 0.0f;
+	if (!(dofs & 2u)) a.y = 0.0f;
+	if (!(dofs & 4u)) a.z = 0.0f;
+	return a;
+}
+__device__ __forceinline__ v3 clamp_len(v3 v, float maxl)
+{
+	float l2 = len2(v);
+	if (l2 > (maxl * maxl)) return v * (maxl / sqrtf(l2));
+	return v;
+}
+
+// world inverse inertia R diag(inv_i) R^T, locked rotation axes zeroed; im = inverse mass (dynamic only)
+__device__ __forceinline__ void body_world_inertia(SBody &b)
+{
+	if (!is_dynamic(b.flags))
+	{
+#pragma unroll
+		for (int k = 0; k < 6; k++) b.M[k] = 0.0f;
+		b.im = 0.0f;
+		return;
+	}
+	m33 R = qmat(b.q);
+	v3 s0 = R.c0 * b.inv_i.x, s1 = R.c1 * b.inv_i.y, s2 = R.c2 * b.inv_i.z;
+	float xx = ((s0.x * R.c0.x) + (s1.x * R.c1.x)) + (s2.x * R.c2.x);
+	float xy = ((s0.x * R.c0.y) + (s1.x * R.c1.y)) + (s2.x * R.c2.y);
+	float xz = ((s0.x * R.c0.z) + (s1.x * R.c1.z)) + (s2.x * R.c2.z);
+	float yy = ((s0.y * R.c0.y) + (s1.y * R.c1.y)) + (s2.y * R.c2.y);
+	float yz = ((s0.y * R.c0.z) + (s1.y * R.c1.z)) + (s2.y * R.c2.z);
+	float zz = ((s0.z * R.c0.z) + (s1.z * R.c1.z)) + (s2.z * R.c2.z);
+	const uint32_t dofs = dofs_of(b.flags);
+	const bool lx = !(dofs & 8u), ly = !(dofs & 16u), lz = !(dofs & 32u);
+	b.M[0] = lx ? 0.0f : xx;
+	b.M[1] = (lx || ly) ? 0.0f : xy;
+	b.M[2] = (lx || lz) ? 0.0f : xz;
+	b.M[3] = ly ? 0.0f : yy;
+	b.M[4] = (ly || lz) ? 0.0f : yz;
+	b.M[5] = lz ? 0.0f : zz;
+	b.im = b.inv_mass;
+}
+
+__device__ __forceinline__ void body_aabb(SBody &b)
+{
+	v3 e;
+	if (shape_of(b.flags) == GPX_SHAPE_BOX)
+	{
+		m33 R = qmat(b.q);
+		e.x = ((fabsf(R.c0.x) * b.he.x) + (fabsf(R.c1.x) * b.he.y)) + (fabsf(R.c2.x) * b.he.z);
+		e.y = ((fabsf(R.c0.y) * b.he.x) + (fabsf(R.c1.y) * b.he.y)) + (fabsf(R.c2.y) * b.he.z);
+		e.z = ((fabsf(R.c0.z) * b.he.x) + (fabsf(R.c1.z) * b.he.y)) + (fabsf(R.c2.z) * b.he.z);
+	}
+	else
+		e = V(b.he.x, b.he.x, b.he.x);
+	b.lo = b.x - e;
+	b.hi = b.x + e;
+}
+
+__device__ __forceinline__ bool aabb_overlap(v3 alo, v3 ahi, v3 blo, v3 bhi, float m)
+{
+	return (alo.x - m) <= bhi.x && blo.x <= (ahi.x + m) && (alo.y - m) <= bhi.y && blo.y <= (ahi.y + m) &&
+		   (alo.z - m) <= bhi.z && blo.z <= (ahi.z + m);
+}
+
+__device__ __forceinline__ bool layers_collide(uint32_t la, uint32_t lb)
+{
+	// ObjectLayerShouldCollide in both orders (engine/src/physics/Physics.c:35-52)
+	bool a_init = la == 1 || la == 2, b_init = lb == 1 || lb == 2;
+	bool a_tgt = la == 0 || la == 1 || la == 3, b_tgt = lb == 0 || lb == 1 || lb == 3;
+	return (a_init && b_tgt) || (b_init && a_tgt);
+}
+
+// Box query of the static LBVH: leaves whose exact triangle box overlaps [lo-m, hi+m], sorted by triangle index.
+__device__ __forceinline__ int query_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris,
+											uint32_t n_nodes, v3 lo, v3 hi, float m, int *cand_orig, int *cand_leaf,
+											bool &overflow)
+{
+	int nc = 0;
+	if (n_nodes == 0) return 0;
+	int stack[64];
+	int sp = 0, node = 0;
+	const float qlx = lo.x - m, qly = lo.y - m, qlz = lo.z - m, qhx = hi.x + m, qhy = hi.y + m, qhz = hi.z + m;
+	while (true)
+	{
+		if (node >= 0)
+		{
+			const float4 n0 = __ldg(&nodes[4 * node + 0]), n1 = __ldg(&nodes[4 * node + 1]),
+						 n2 = __ldg(&nodes[4 * node + 2]), n3 = __ldg(&nodes[4 * node + 3]);
+			bool h0 = qlx <= n0.y && n0.x <= qhx && qly <= n0.w && n0.z <= qhy && qlz <= n2.y && n2.x <= qhz;
+			bool h1 = qlx <= n1.y && n1.x <= qhx && qly <= n1.w && n1.z <= qhy && qlz <= n2.w && n2.z <= qhz;
+			int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+			if (h0 && h1)
+			{
+				stack[sp++] = c1;
+				node = c0;
+				continue;
+			}
+			if (h0) { node = c0; continue; }
+			if (h1) { node = c1; continue; }
+		}
+		else
+		{
+			const int leaf = ~node;
+			const float4 A = __ldg(&tris[4 * leaf + 0]), B = __ldg(&tris[4 * leaf + 1]), C = __ldg(&tris[4 * leaf + 2]);
+			v3 tlo = V(fminf(A.x, fminf(B.x, C.x)), fminf(A.y, fminf(B.y, C.y)), fminf(A.z, fminf(B.z, C.z)));
+			v3 thi = V(fmaxf(A.x, fmaxf(B.x, C.x)), fmaxf(A.y, fmaxf(B.y, C.y)), fmaxf(A.z, fmaxf(B.z, C.z)));
+			if (aabb_overlap(lo, hi, tlo, thi, m))
+			{
+				if (nc < MAX_TRI_CANDIDATES)
+				{
+					int orig = (int)__float_as_uint(A.w);
+					int k = nc++;
+					while (k > 0 && cand_orig[k - 1] > orig)
+					{
+						cand_orig[k] = cand_orig[k - 1];
+						cand_leaf[k] = cand_leaf[k - 1];
+						k--;
+					}
+					cand_orig[k] = orig;
+					cand_leaf[k] = leaf;
+				}
+				else
+					overflow = true;
+			}
+		}
+		if (sp == 0) break;
+		node = stack[--sp];
+	}
+	return nc;
+}
+
+// ---- solver pieces (same formulas for every manifold; b == static geometry has zero mass and velocity)
+
+__device__ __forceinline__ float eff_mass(float ima, const float *MA, float imb, const float *MB, v3 r1, v3 r2, v3 axis)
+{
+	v3 r1xa = cross(r1, axis), r2xa = cross(r2, axis);
+	float k = ((ima + imb) + dot(r1xa, sym_mul(MA, r1xa))) + dot(r2xa, sym_mul(MB, r2xa));
+	return k > 0.0f ? 1.0f / k : 0.0f;
+}
+
+__device__ __forceinline__ v3 rel_vel(const SBody &A, const SBody *B, v3 r1, v3 r2)
+{
+	v3 ua = A.v + cross(A.w, r1);
+	if (!B) return ua;
+	return ua - (B->v + cross(B->w, r2));
+}
+
+__device__ __forceinline__ void apply_impulse(SBody &A, SBody *B, v3 r1, v3 r2, v3 P)
+{
+	if (is_dynamic(A.flags))
+	{
+		A.v = A.v - mask_lin(dofs_of(A.flags), P * A.im);
+		A.w = A.w - sym_mul(A.M, cross(r1, P));
+	}
+	if (B && is_dynamic(B->flags))
+	{
+		B->v = B->v + mask_lin(dofs_of(B->flags), P * B->im);
+		B->w = B->w + sym_mul(B->M, cross(r2, P));
+	}
+}
+
+__device__ __forceinline__ void setup_manifold(SMan &m, SBody *bodies, float h)
+{
+	SBody &A = bodies[m.a];
+	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
+	const float zero_m[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+	const float imb = B ? B->im : 0.0f;
+	const float *MB = B ? B->M : zero_m;
+	m.t1 = vperp(m.n);
+	m.t2 = cross(m.n, m.t1);
+	for (int k = 0; k < m.np; k++)
+	{
+		v3 p1 = A.x + qrot(A.q, m.p1l[k]);
+		v3 p2 = B ? B->x + qrot(B->q, m.p2l[k]) : m.p2l[k];
+		v3 mid = (p1 + p2) * 0.5f;
+		v3 r1 = mid - A.x;
+		v3 r2 = B ? mid - B->x : V(0.0f, 0.0f, 0.0f);
+		m.r1[k] = r1;
+		m.r2[k] = r2;
+		m.em[k][0] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.n);
+		m.em[k][1] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.t1);
+		m.em[k][2] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.t2);
+		float pen = dot(p1 - p2, m.n);
+		float bias = fmaxf(0.0f, -pen / h);
+		if (m.restitution > 0.0f)
+		{
+			float nv = -dot(m.n, rel_vel(A, B, r1, r2));
+			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
+		}
+		m.bias[k] = bias;
+	}
+}
+
+__device__ __forceinline__ void warm_start(SMan &m, SBody *bodies)
+{
+	SBody &A = bodies[m.a];
+	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
+	for (int k = 0; k < m.np; k++)
+	{
+		if (m.ln[k] == 0.0f && m.lt1[k] == 0.0f && m.lt2[k] == 0.0f) continue;
+		v3 P = ((m.n * m.ln[k]) + (m.t1 * m.lt1[k])) + (m.t2 * m.lt2[k]);
+		apply_impulse(A, B, m.r1[k], m.r2[k], P);
+	}
+}
+
+__device__ __forceinline__ void solve_velocity(SMan &m, SBody *bodies)
+{
+	SBody &A = bodies[m.a];
+	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
+	// friction first: non-penetration is more important, so it goes last
+	for (int k = 0; k < m.np; k++)
+	{
+		v3 u = rel_vel(A, B, m.r1[k], m.r2[k]);
+		float l1 = m.lt1[k] + (m.em[k][1] * dot(m.t1, u));
+		float l2 = m.lt2[k] + (m.em[k][2] * dot(m.t2, u));
+		float maxf = m.friction * m.ln[k];
+		float sq = (l1 * l1) + (l2 * l2);
+		if (sq > (maxf * maxf))
+		{
+			float s = maxf / sqrtf(sq);
+			l1 = l1 * s;
+			l2 = l2 * s;
+		}
+		v3 P = (m.t1 * (l1 - m.lt1[k])) + (m.t2 * (l2 - m.lt2[k]));
+		m.lt1[k] = l1;
+		m.lt2[k] = l2;
+		apply_impulse(A, B, m.r1[k], m.r2[k], P);
+	}
+	for (int k = 0; k < m.np; k++)
+	{
+		v3 u = rel_vel(A, B, m.r1[k], m.r2[k]);
+		float lambda = m.em[k][0] * (dot(m.n, u) - m.bias[k]);
+		float nt = fmaxf(0.0f, m.ln[k] + lambda);
+		lambda = nt - m.ln[k];
+		m.ln[k] = nt;
+		apply_impulse(A, B, m.r1[k], m.r2[k], m.n * lambda);
+	}
+}
+
+__device__ __forceinline__ void solve_position(SMan &m, SBody *bodies)
+{
+	SBody &A = bodies[m.a];
+	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
+	const float zero_m[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+	body_world_inertia(A);
+	if (B) body_world_inertia(*B);
+	const float imb = B ? B->im : 0.0f;
+	const float *MB = B ? B->M : zero_m;
+	for (int k = 0; k < m.np; k++)
+	{
+		v3 p1 = A.x + qrot(A.q, m.p1l[k]);
+		v3 p2 = B ? B->x + qrot(B->q, m.p2l[k]) : m.p2l[k];
+		float sep = dot(p2 - p1, m.n) + PENETRATION_SLOP;
+		if (sep >= 0.0f) continue;
+		v3 mid = (p1 + p2) * 0.5f;
+		v3 r1 = mid - A.x, r2 = B ? mid - B->x : V(0.0f, 0.0f, 0.0f);
+		float e = eff_mass(A.im, A.M, imb, MB, r1, r2, m.n);
+		float c = fmaxf(sep, -MAX_PENETRATION_DISTANCE);
+		float lambda = (-e * BAUMGARTE) * c;
+		v3 P = m.n * lambda;
+		if (is_dynamic(A.flags))
+		{
+			A.x = A.x - mask_lin(dofs_of(A.flags), P * A.im);
+			A.q = qstep(A.q, -sym_mul(A.M, cross(r1, P)));
+		}
+		if (B && is_dynamic(B->flags))
+		{
+			B->x = B->x + mask_lin(dofs_of(B->flags), P * B->im);
+			B->q = qstep(B->q, sym_mul(B->M, cross(r2, P)));
+		}
+	}
+}
+
+// manifold points: world -> local frames (b static: world)
+__device__ __forceinline__ void store_points(SMan &m, const SBody &A, const SBody *B, int np, const v3 *p1, const v3 *p2)
+{
+	m33 RA = qmat(A.q);
+	m.np = np;
+	m33 RB;
+	if (B) RB = qmat(B->q);
+	for (int i = 0; i < np; i++)
+	{
+		m.p1l[i] = mtmul(RA, p1[i] - A.x);
+		m.p2l[i] = B ? mtmul(RB, p2[i] - B->x) : p2[i];
+	}
+	for (int i = 0; i < 4; i++) m.ln[i] = m.lt1[i] = m.lt2[i] = 0.0f;
+}
+
+struct StaticSlot
+{
+	v3 n;
+	float depth, friction;
+	uint32_t sbody;
+	int np;
+	v3 p1[8], p2[8];
+};
+
+template <int TILE>
+__global__ void __launch_bounds__(128) k_tick(TickArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	auto tile = cg::tiled_partition<TILE>(cg::this_thread_block());
+	const int lane = tile.thread_rank();
+	const uint32_t tiles_per_block = blockDim.x / TILE;
+	const uint32_t world = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
+	const uint32_t cap = a.p.cap, cap_m = a.p.cap_m;
+	if (world >= a.p.worlds) return;  // whole tile exits together
+
+	unsigned char *base = smem_raw + world_smem_bytes(cap, cap_m) * (threadIdx.x / TILE);
+	unsigned long long *pmask = reinterpret_cast<unsigned long long *>(base);
+	SBody *bodies = reinterpret_cast<SBody *>(pmask + cap);
+	SMan *man = reinterpret_cast<SMan *>(bodies + cap);
+	SPrev *prev = reinterpret_cast<SPrev *>(man + cap_m);
+	uint32_t *pair_a = reinterpret_cast<uint32_t *>(prev + cap_m);
+	uint32_t *pair_b = pair_a + cap_m;
+	uint32_t *cnt_static = pair_b + cap_m;
+	uint32_t *slot_base = cnt_static + cap;
+	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs
+
+	const uint32_t g0 = world * cap;
+	// ---- load: HBM -> shared, lane = body, 16-byte vector loads
+	for (uint32_t i = lane; i < cap; i += TILE)
+	{
+		SBody &b = bodies[i];
+		const float4 p = a.bs.pos[g0 + i], q = a.bs.quat[g0 + i], l = a.bs.lin[g0 + i], w = a.bs.ang[g0 + i];
+		const float4 p0 = a.bs.prop0[g0 + i], p1 = a.bs.prop1[g0 + i], p2 = a.bs.prop2[g0 + i];
+		b.x = V(p);
+		b.q = Q(q);
+		b.v = V(l);
+		b.w = V(w);
+		b.inv_mass = p0.x;
+		b.inv_i = V(p0.y, p0.z, p0.w);
+		b.he = V(p1);
+		b.friction = p1.w;
+		b.lin_damp = p2.x;
+		b.ang_damp = p2.y;
+		b.grav = p2.z;
+		b.restitution = p2.w;
+		b.flags = a.bs.flags[g0 + i];
+	}
+	const uint32_t m0 = world * cap_m;
+	if (lane == 0)
+	{
+		hdr[1] = min(a.mc.count[world], cap_m);
+		hdr[3] = 0;
+	}
+	tile.sync();
+	for (uint32_t i = lane; i < hdr[1]; i += TILE)
+	{
+		SPrev &o = prev[i];
+		const uint4 k = a.mc.key[m0 + i];
+		o.a = k.x; o.b = k.y; o.np = k.z;
+		const float4 l2 = a.mc.lt2[m0 + i];
+		const float l2a[4] = {l2.x, l2.y, l2.z, l2.w};
+#pragma unroll
+		for (int k4 = 0; k4 < 4; k4++)
+		{
+			const float4 c1 = a.mc.p1[4 * (m0 + i) + k4], c2 = a.mc.p2[4 * (m0 + i) + k4];
+			o.p1l[k4] = V(c1);
+			o.ln[k4] = c1.w;
+			o.p2l[k4] = V(c2);
+			o.lt1[k4] = c2.w;
+			o.lt2[k4] = l2a[k4];
+		}
+	}
+	tile.sync();
+
+	const float h = a.p.h;
+	const v3 gravity = V(a.p.gx, a.p.gy, a.p.gz);
+
+	for (int sub = 0; sub < a.p.substeps; sub++)
+	{
+		// ---- 1: forces, inertia, bounds
+		for (uint32_t i = lane; i < cap; i += TILE)
+		{
+			SBody &b = bodies[i];
+			if (!(b.flags & BF_ALIVE)) continue;
+			if (is_dynamic(b.flags))
+			{
+				const uint32_t dofs = dofs_of(b.flags);
+				b.v = b.v + (gravity * (h * b.grav));
+				b.v = b.v * fmaxf(0.0f, 1.0f - (b.lin_damp * h));
+				b.w = b.w * fmaxf(0.0f, 1.0f - (b.ang_damp * h));
+				b.v = clamp_len(mask_lin(dofs, b.v), MAX_LINEAR_VELOCITY);
+				v3 ww = b.w;
+				if (!(dofs & 8u)) ww.x = 0.0f;
+				if (!(dofs & 16u)) ww.y = 0.0f;
+				if (!(dofs & 32u)) ww.z = 0.0f;
+				b.w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+			}
+			body_world_inertia(b);
+			body_aabb(b);
+		}
+		tile.sync();
+
+		// ---- 2 + 3: per body: contacts with the static map (kept in registers/local until slots are known) and the
+		// mask of higher-numbered bodies whose boxes overlap
+		for (uint32_t i0 = 0; i0 < cap; i0 += TILE)
+		{
+			const uint32_t i = i0 + lane;
+			StaticSlot slots[MAX_STATIC_PER_BODY];
+			int nslots = 0;
+			unsigned long long mask = 0ull;
+			uint32_t err = 0;
+			if (i < cap && (bodies[i].flags & BF_ALIVE) && shape_of(bodies[i].flags) != GPX_SHAPE_EMPTY)
+			{
+				const SBody &A = bodies[i];
+				const uint32_t fa = A.flags;
+				const uint32_t la = layer_of(fa);
+				if (is_dynamic(fa) && !(fa & BF_SENSOR) && (la == 1 || la == 2))
+				{
+					int cand_orig[MAX_TRI_CANDIDATES], cand_leaf[MAX_TRI_CANDIDATES];
+					bool overflow = false;
+					const int nc = query_static(a.nodes, a.tris, a.n_nodes, A.lo, A.hi, SPECULATIVE_DISTANCE, cand_orig,
+												cand_leaf, overflow);
+					if (overflow) err |= GPX_ERR_BODY_PAIR_CACHE_FULL;
+					Box bx;
+					bx.x = A.x;
+					bx.R = qmat(A.q);
+					bx.he = A.he;
+					int group_start = 0;
+					uint32_t cur_body = 0xFFFFFFFFu;
+					for (int c = 0; c < nc; c++)
+					{
+						const int leaf = cand_leaf[c];
+						const float4 TA = __ldg(&a.tris[4 * leaf + 0]), TB = __ldg(&a.tris[4 * leaf + 1]),
+									 TC = __ldg(&a.tris[4 * leaf + 2]), TN = __ldg(&a.tris[4 * leaf + 3]);
+						const uint32_t sbody = __float_as_uint(TB.w);
+						if (sbody != cur_body)
+						{
+							cur_body = sbody;
+							group_start = nslots;
+						}
+						Tri T;
+						T.a = V(TA); T.b = V(TB); T.c = V(TC); T.n = V(TN);
+						Hit hit;
+						bool ok = shape_of(fa) == GPX_SHAPE_BOX ? collide_box_tri(bx, T, SPECULATIVE_DISTANCE, hit)
+																: collide_sphere_tri(A.x, A.he.x, T, SPECULATIVE_DISTANCE, hit);
+						if (!ok) continue;
+						prune_points(A.x, hit.n, hit.np, hit.p1, hit.p2);
+						int s = -1;
+						for (int k = group_start; k < nslots; k++)
+							if (dot(slots[k].n, hit.n) >= NORMAL_COS_MAX_DELTA)
+							{
+								s = k;
+								break;
+							}
+						if (s < 0)
+						{
+							if (nslots - group_start == MAX_SLOTS) continue;
+							if (nslots == MAX_STATIC_PER_BODY)
+							{
+								err |= GPX_ERR_MANIFOLD_CACHE_FULL;
+								continue;
+							}
+							s = nslots++;
+							slots[s].n = hit.n;
+							slots[s].depth = hit.depth;
+							slots[s].friction = sqrtf(A.friction * TC.w);
+							slots[s].sbody = sbody;
+							slots[s].np = 0;
+						}
+						else if (hit.depth > slots[s].depth)
+						{
+							slots[s].depth = hit.depth;
+							slots[s].n = hit.n;
+						}
+						for (int k = 0; k < hit.np; k++)
+						{
+							slots[s].p1[slots[s].np] = hit.p1[k];
+							slots[s].p2[slots[s].np] = hit.p2[k];
+							slots[s].np++;
+						}
+						prune_points(A.x, slots[s].n, slots[s].np, slots[s].p1, slots[s].p2);
+					}
+				}
+				for (uint32_t j = i + 1; j < cap; j++)
+				{
+					const SBody &B = bodies[j];
+					const uint32_t fb = B.flags;
+					if (!(fb & BF_ALIVE) || shape_of(fb) == GPX_SHAPE_EMPTY) continue;
+					if (!is_dynamic(fa) && !is_dynamic(fb)) continue;
+					if (!layers_collide(la, layer_of(fb))) continue;
+					if ((fa & BF_SENSOR) || (fb & BF_SENSOR)) continue;
+					if (!aabb_overlap(A.lo, A.hi, B.lo, B.hi, SPECULATIVE_DISTANCE)) continue;
+					mask |= 1ull << j;
+				}
+			}
+			if (i < cap)
+			{
+				cnt_static[i] = (uint32_t)nslots;
+				pmask[i] = mask;
+			}
+			if (err) atomicOr(&hdr[3], err);
+			tile.sync();
+			// slots for this chunk of bodies: serial prefix on lane 0 (a handful of bodies)
+			if (lane == 0)
+			{
+				uint32_t n = i0 == 0 ? 0 : hdr[0];
+				uint32_t np = i0 == 0 ? 0 : hdr[4];
+				for (uint32_t k = i0; k < min(i0 + TILE, cap); k++)
+				{
+					slot_base[k] = n;
+					n += cnt_static[k];
+					unsigned long long pm = pmask[k];
+					while (pm)
+					{
+						int j = __ffsll((long long)pm) - 1;
+						pm &= pm - 1;
+						if (n < cap_m && np < cap_m)
+						{
+							pair_a[np] = k | (n << 16);
+							pair_b[np] = (uint32_t)j;
+							np++;
+						}
+						n++;
+					}
+				}
+				if (n > cap_m) hdr[3] |= GPX_ERR_CONTACT_CONSTRAINTS_FULL;
+				hdr[0] = min(n, cap_m);
+				hdr[4] = np;
+			}
+			tile.sync();
+			if (i < cap)
+			{
+				const SBody &A = bodies[i];
+				for (int s = 0; s < nslots; s++)
+				{
+					const uint32_t slot = slot_base[i] + s;
+					if (slot >= cap_m) break;
+					SMan &m = man[slot];
+					m.a = i;
+					m.b = STATIC_BODY_BASE + slots[s].sbody;
+					m.n = slots[s].n;
+					m.friction = slots[s].friction;
+					m.restitution = A.restitution;
+					store_points(m, A, nullptr, slots[s].np, slots[s].p1, slots[s].p2);
+				}
+			}
+		}
+		tile.sync();
+
+		// ---- 4: body-body contact manifolds, one lane per candidate pair
+		const uint32_t npairs = hdr[4];
+		for (uint32_t pi = lane; pi < npairs; pi += TILE)
+		{
+			const uint32_t ia = pair_a[pi] & 0xFFFFu, slot = pair_a[pi] >> 16, ib = pair_b[pi];
+			const SBody &A = bodies[ia];
+			const SBody &B = bodies[ib];
+			SMan &m = man[slot];
+			m.a = ia;
+			m.b = ib;
+			m.np = 0;
+			Hit hit;
+			bool ok;
+			const uint32_t sa = shape_of(A.flags), sb = shape_of(B.flags);
+			if (sa == GPX_SHAPE_BOX && sb == GPX_SHAPE_BOX)
+			{
+				Box ba, bb;
+				ba.x = A.x; ba.R = qmat(A.q); ba.he = A.he;
+				bb.x = B.x; bb.R = qmat(B.q); bb.he = B.he;
+				ok = collide_box_box(ba, bb, SPECULATIVE_DISTANCE, hit);
+			}
+			else if (sa == GPX_SHAPE_SPHERE && sb == GPX_SHAPE_SPHERE)
+				ok = collide_sphere_sphere(A.x, A.he.x, B.x, B.he.x, SPECULATIVE_DISTANCE, hit);
+			else if (sa == GPX_SHAPE_SPHERE)
+			{
+				Box bb;
+				bb.x = B.x; bb.R = qmat(B.q); bb.he = B.he;
+				ok = collide_sphere_box(A.x, A.he.x, bb, SPECULATIVE_DISTANCE, hit);
+			}
+			else
+			{
+				Box ba;
+				ba.x = A.x; ba.R = qmat(A.q); ba.he = A.he;
+				ok = collide_sphere_box(B.x, B.he.x, ba, SPECULATIVE_DISTANCE, hit);
+				if (ok)
+				{
+					hit.n = -hit.n;
+					v3 t = hit.p1[0];
+					hit.p1[0] = hit.p2[0];
+					hit.p2[0] = t;
+				}
+			}
+			if (!ok) continue;
+			prune_points(A.x, hit.n, hit.np, hit.p1, hit.p2);
+			m.n = hit.n;
+			m.friction = sqrtf(A.friction * B.friction);
+			m.restitution = fmaxf(A.restitution, B.restitution);
+			store_points(m, A, &B, hit.np, hit.p1, hit.p2);
+		}
+		tile.sync();
+
+		// ---- 5: carry impulses from the previous sub-step's manifolds
+		const uint32_t nman = hdr[0], nprev = hdr[1];
+		for (uint32_t mi = lane; mi < nman; mi += TILE)
+		{
+			SMan &m = man[mi];
+			if (m.np == 0) continue;
+			for (uint32_t j = 0; j < nprev; j++)
+			{
+				const SPrev &o = prev[j];
+				if (o.a != m.a || o.b != m.b) continue;
+				for (int p = 0; p < m.np; p++)
+				{
+					if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
+					for (uint32_t k = 0; k < o.np; k++)
+						if (len2(m.p1l[p] - o.p1l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
+							len2(m.p2l[p] - o.p2l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ)
+						{
+							m.ln[p] = o.ln[k];
+							m.lt1[p] = o.lt1[k];
+							m.lt2[p] = o.lt2[k];
+							break;
+						}
+				}
+			}
+			setup_manifold(m, bodies, h);  // ---- 7a: reads body state only
+		}
+		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour)
+		if (lane == 0)
+		{
+			unsigned long long *used = pmask;  // reuse: per-body colour sets
+			for (uint32_t k = 0; k < cap; k++) used[k] = 0ull;
+			int ncol = 0;
+			for (uint32_t mi = 0; mi < nman; mi++)
+			{
+				SMan &m = man[mi];
+				if (m.np == 0)
+				{
+					m.colour = -1;
+					continue;
+				}
+				const bool a_dyn = is_dynamic(bodies[m.a].flags);
+				const bool b_dyn = m.b < STATIC_BODY_BASE && is_dynamic(bodies[m.b].flags);
+				unsigned long long u = 0ull;
+				if (a_dyn) u |= used[m.a];
+				if (b_dyn) u |= used[m.b];
+				int c = 0;
+				while (c < 63 && ((u >> c) & 1ull)) c++;
+				m.colour = c;
+				if (a_dyn) used[m.a] |= 1ull << c;
+				if (b_dyn) used[m.b] |= 1ull << c;
+				if (c + 1 > ncol) ncol = c + 1;
+			}
+			hdr[2] = (uint32_t)ncol;
+		}
+		tile.sync();
+		const int ncol = (int)hdr[2];
+
+		// ---- 7b: warm start, then velocity iterations; within a colour no two manifolds share a dynamic body
+		for (int c = 0; c < ncol; c++)
+		{
+			for (uint32_t mi = lane; mi < nman; mi += TILE)
+				if (man[mi].colour == c) warm_start(man[mi], bodies);
+			tile.sync();
+		}
+		for (uint32_t it = 0; it < a.p.vel_steps; it++)
+			for (int c = 0; c < ncol; c++)
+			{
+				for (uint32_t mi = lane; mi < nman; mi += TILE)
+					if (man[mi].colour == c) solve_velocity(man[mi], bodies);
+				tile.sync();
+			}
+
+		// ---- 8: integrate
+		for (uint32_t i = lane; i < cap; i += TILE)
+		{
+			SBody &b = bodies[i];
+			if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC) continue;
+			b.x = b.x + (b.v * h);
+			b.q = qstep(b.q, b.w * h);
+		}
+		tile.sync();
+
+		// ---- 9: position iterations
+		for (uint32_t it = 0; it < a.p.pos_steps; it++)
+			for (int c = 0; c < ncol; c++)
+			{
+				for (uint32_t mi = lane; mi < nman; mi += TILE)
+					if (man[mi].colour == c) solve_position(man[mi], bodies);
+				tile.sync();
+			}
+
+		// ---- this sub-step's manifolds become the warm-start cache (compacted, canonical order kept)
+		if (lane == 0)
+		{
+			uint32_t k = 0;
+			for (uint32_t mi = 0; mi < nman; mi++)
+				if (man[mi].np > 0) man[mi].colour = (int)k++;
+			hdr[1] = k;
+		}
+		tile.sync();
+		for (uint32_t mi = lane; mi < nman; mi += TILE)
+		{
+			const SMan &m = man[mi];
+			if (m.np == 0) continue;
+			SPrev &o = prev[m.colour];
+			o.a = m.a; o.b = m.b; o.np = (uint32_t)m.np;
+			for (int k = 0; k < 4; k++)
+			{
+				o.p1l[k] = m.p1l[k];
+				o.p2l[k] = m.p2l[k];
+				o.ln[k] = m.ln[k];
+				o.lt1[k] = m.lt1[k];
+				o.lt2[k] = m.lt2[k];
+			}
+		}
+		tile.sync();
+	}
+
+	// ---- store: shared -> HBM
+	for (uint32_t i = lane; i < cap; i += TILE)
+	{
+		const SBody &b = bodies[i];
+		if (!(b.flags & BF_ALIVE)) continue;
+		a.bs.pos[g0 + i] = F4(b.x, 0.0f);
+		a.bs.quat[g0 + i] = make_float4(b.q.x, b.q.y, b.q.z, b.q.w);
+		a.bs.lin[g0 + i] = F4(b.v, 0.0f);
+		a.bs.ang[g0 + i] = F4(b.w, 0.0f);
+	}
+	const uint32_t nprev = hdr[1];
+	for (uint32_t i = lane; i < nprev; i += TILE)
+	{
+		const SPrev &o = prev[i];
+		a.mc.key[m0 + i] = make_uint4(o.a, o.b, o.np, 0u);
+		a.mc.lt2[m0 + i] = make_float4(o.lt2[0], o.lt2[1], o.lt2[2], o.lt2[3]);
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			a.mc.p1[4 * (m0 + i) + k] = F4(o.p1l[k], o.ln[k]);
+			a.mc.p2[4 * (m0 + i) + k] = F4(o.p2l[k], o.lt1[k]);
+		}
+	}
+	if (lane == 0)
+	{
+		a.mc.count[world] = nprev;
+		if (hdr[3])
+		{
+			a.err[1 + world] |= hdr[3];
+			atomicOr(&a.err[0], hdr[3]);
+		}
+	}
+}
+
+__global__ void k_apply_commands(BodyStore bs, const BodyCommand *__restrict__ cmd, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const BodyCommand c = cmd[i];
+	if (c.mask & 1u) bs.pos[c.index] = c.pos;
+	if (c.mask & 2u) bs.quat[c.index] = c.quat;
+	if (c.mask & 4u) bs.lin[c.index] = c.lin;
+	if (c.mask & 8u) bs.ang[c.index] = c.ang;
+	if (c.mask & 16u)
+	{
+		bs.prop0[c.index] = c.prop0;
+		bs.prop1[c.index] = c.prop1;
+		bs.prop2[c.index] = c.prop2;
+		bs.flags[c.index] = c.flags;
+	}
+}
+
+// per-world summary for the end-of-run gather: one warp per world
+__global__ void k_stats(BodyStore bs, ManifoldCache mc, const uint32_t *err, uint32_t worlds, uint32_t cap, uint32_t ticks,
+						gpx_world_stats *out)
+{
+	const uint32_t world = (blockIdx.x * blockDim.x + threadIdx.x) / 32u;
+	const uint32_t lane = threadIdx.x & 31u;
+	if (world >= worlds) return;
+	float ke = 0.0f, vmax = 0.0f;
+	uint32_t awake = 0;
+	unsigned long long sum = 0ull;
+	for (uint32_t i = lane; i < cap; i += 32)
+	{
+		const uint32_t g = world * cap + i;
+		const uint32_t f = bs.flags[g];
+		if (!(f & BF_ALIVE)) continue;
+		const float4 p = bs.pos[g], q = bs.quat[g], l = bs.lin[g], p0 = bs.prop0[g];
+		// order-independent checksum of the exact position/rotation bits
+		unsigned long long hsh = 1469598103934665603ull * (i + 1);
+		const uint32_t w[7] = {__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(q.x),
+							   __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(q.w)};
+#pragma unroll
+		for (int k = 0; k < 7; k++) hsh = (hsh ^ w[k]) * 1099511628211ull;
+		sum += hsh;
+		if (is_dynamic(f))
+		{
+			awake++;
+			const float v2 = ((l.x * l.x) + (l.y * l.y)) + (l.z * l.z);
+			if (p0.x > 0.0f) ke += (0.5f / p0.x) * v2;
+			vmax = fmaxf(vmax, sqrtf(v2));
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		ke += __shfl_xor_sync(0xFFFFFFFFu, ke, o);
+		vmax = fmaxf(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, o));
+		awake += __shfl_xor_sync(0xFFFFFFFFu, awake, o);
+		sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+	}
+	if (lane == 0)
+	{
+		gpx_world_stats s;
+		s.kinetic_energy = ke;
+		s.max_speed = vmax;
+		s.awake_bodies = awake;
+		s.manifolds = mc.count[world];
+		s.position_checksum = sum;
+		s.ticks = ticks;
+		s.error = err[1 + world];
+		out[world] = s;
+	}
+}
+
+template <int TILE>
+static int launch_tick_t(gpx_world *w, const TickArgs &a)
+{
+	const uint32_t threads = 128;
+	const uint32_t wpb = threads / TILE;
+	const size_t smem = world_smem_bytes(w->cap, w->cap_m) * wpb;
+	static size_t configured = 0;
+	if (smem > configured)
+	{
+		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = smem;
+	}
+	const uint32_t grid = (w->W + wpb - 1) / wpb;
+	k_tick<TILE><<<grid, threads, smem, w->stream>>>(a);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
+int launch_tick(gpx_world *w, float dt, int substeps)
+{
+	TickArgs a;
+	a.bs = w->bs;
+	a.mc = w->mc;
+	a.nodes = w->sd.nodes;
+	a.tris = w->sd.tri;
+	a.n_nodes = w->sd.n_nodes;
+	a.err = w->d_err;
+	a.p.worlds = w->W;
+	a.p.cap = w->cap;
+	a.p.cap_m = w->cap_m;
+	a.p.vel_steps = w->cfg.velocity_steps ? w->cfg.velocity_steps : 10u;
+	a.p.pos_steps = w->cfg.position_steps ? w->cfg.position_steps : 2u;
+	a.p.gx = w->cfg.gravity[0];
+	a.p.gy = w->cfg.gravity[1];
+	a.p.gz = w->cfg.gravity[2];
+	if (substeps < 1) substeps = 1;
+	a.p.substeps = substeps;
+	a.p.h = dt / (float)substeps;
+	if (w->cap <= 8) return launch_tick_t<8>(w, a);
+	if (w->cap <= 16) return launch_tick_t<16>(w, a);
+	return launch_tick_t<32>(w, a);
+}
+
+int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n)
+{
+	if (n == 0) return GPX_OK;
+	k_apply_commands<<<(n + 127) / 128, 128, 0, w->stream>>>(w->bs, d_cmd, n);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
+int launch_stats(gpx_world *w)
+{
+	const uint32_t threads = 128;
+	const uint32_t grid = (w->W * 32u + threads - 1) / threads;
+	k_stats<<<grid, threads, 0, w->stream>>>(w->bs, w->mc, w->d_err, w->W, w->cap, w->ticks, w->d_stats);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
+}  // namespace gpx

@@ -151,14 +151,6 @@ typedef struct gpx_world_stats /* 32 B, gathered across GPUs at the end of a run
 	uint32_t error;
 } gpx_world_stats;
 
-typedef struct gpx_contact_event /* body<->sensor / body<->body begin/persist/end (PlayerPhysics.c:89-152 analogue) */
-{
-	uint32_t world;
-	uint32_t body_a;
-	uint32_t body_b;
-	uint32_t kind; /* 0 added, 1 persisted, 2 removed */
-} gpx_contact_event;
-
 /* ---- lifecycle ------------------------------------------------------------------------------------------- */
 
 /* JPH_Init (Physics.c:75).  Returns GPX_ABI_VERSION on success, negative gpx_error otherwise. */
@@ -225,8 +217,6 @@ int gpx_read_transforms(gpx_world *w, gpx_transform *out, uint64_t capacity);
 int gpx_read_velocities(gpx_world *w, float *out_lin_ang6, uint64_t capacity);
 /* Per-world stats computed on device, `out` has `worlds` entries (host). */
 int gpx_read_stats(gpx_world *w, gpx_world_stats *out);
-/* Contact events of the last step (sensor overlaps and body pairs that touch). Returns count or negative error. */
-int64_t gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity);
 
 /* ---- ray queries -------------------------------------------------------------------------------------------------- */
 

@@ -48,6 +48,9 @@ typedef struct
 	float friction, restitution, lin_damp, ang_damp, grav_factor;
 	uint32_t sensor, dofs, allow_sleep, ray_flags;
 	uint64_t user_data;
+	/* per sub-step solver view */
+	float im;   /* inverse mass, 0 unless dynamic */
+	float M[6]; /* world inverse inertia xx xy xz yy yz zz */
 } body_t;
 
 typedef struct
@@ -62,15 +65,15 @@ typedef struct
 	float friction, restitution;
 	v3 t1, t2;
 	float bias[4];
-	/* per point, per axis (0 normal, 1 tangent1, 2 tangent2): lever arm cross axis, I^-1 applied, effective mass */
-	v3 r1xa[4][3], r2xa[4][3], i1[4][3], i2[4][3];
-	float em[4][3];
+	v3 r1[4], r2[4];  /* lever arms from the centres of mass to the contact midpoint */
+	float em[4][3];   /* effective mass along normal, tangent1, tangent2 */
 	int colour;
 } manifold_t;
 
 typedef struct
 {
-	v3 v0, e1, e2; /* world space */
+	v3 v0, e1, e2; /* world space: first vertex and the two edges from it */
+	v3 vb, vc;     /* the other two vertices as uploaded */
 	v3 n;          /* unit normal */
 	v3 lo, hi;
 	uint32_t body; /* static body index k */
@@ -156,6 +159,8 @@ uint32_t orc_static_add_mesh(orc_world *w, const float pos[3], const float rot[4
 		v3 c = vadd(qrot(q, V(t[6], t[7], t[8])), p);
 		tri_t *T = &w->tris[w->ntris++];
 		T->v0 = a;
+		T->vb = b;
+		T->vc = c;
 		T->e1 = vsub(b, a);
 		T->e2 = vsub(c, a);
 		v3 n = vcross(T->e1, T->e2);
@@ -175,7 +180,7 @@ uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_bod
 	for (uint32_t i = 0; i < w->ntris && i < cap; i++)
 	{
 		const tri_t *T = &w->tris[i];
-		v3 b = vadd(T->v0, T->e1), c = vadd(T->v0, T->e2);
+		v3 b = T->vb, c = T->vc;
 		float *o = out9 + 9 * i;
 		o[0] = T->v0.x; o[1] = T->v0.y; o[2] = T->v0.z;
 		o[3] = b.x; o[4] = b.y; o[5] = b.z;
@@ -705,8 +710,8 @@ static int collide_box_tri(const body_t *A, const tri_t *T, float max_sep, hit_t
 	const v3 *ca = &R.c0;
 	v3 tv[3];
 	tv[0] = T->v0;
-	tv[1] = vadd(T->v0, T->e1);
-	tv[2] = vadd(T->v0, T->e2);
+	tv[1] = T->vb;
+	tv[2] = T->vc;
 	float best;
 	v3 bn;
 	int kind = 0, ei = 0, ej = 0;
@@ -814,7 +819,7 @@ static v3 closest_on_tri(v3 p, v3 a, v3 b, v3 c)
 
 static int collide_sphere_tri(const body_t *A, const tri_t *T, float max_sep, hit_t *h)
 {
-	v3 c = closest_on_tri(A->x, T->v0, vadd(T->v0, T->e1), vadd(T->v0, T->e2));
+	v3 c = closest_on_tri(A->x, T->v0, T->vb, T->vc);
 	v3 d = vsub(c, A->x);
 	float dist = vlen(d);
 	float r = A->he.x;
@@ -1145,30 +1150,38 @@ static int colour_manifolds(orc_world *w)
 	return ncol;
 }
 
-typedef struct
+/* World-space inverse inertia R diag(inv_i) R^T as 6 unique entries (mirrored), locked rotation axes zeroed.
+ * Refreshed once per sub-step (after forces) and at the start of each manifold's position pass. */
+static void body_world_inertia(body_t *b)
 {
-	v3 x;
-	q4 q;
-	v3 v, w;
-	float inv_mass;
-	v3 inv_inertia;
-	uint32_t dofs;
-	int dynamic;
-} sb_t; /* solver view of a body; static geometry = zeros */
+	if (b->motion != ORC_MOTION_DYNAMIC)
+	{
+		memset(b->M, 0, sizeof(b->M));
+		b->im = 0.0f;
+		return;
+	}
+	m33 R = qmat(b->q);
+	v3 s0 = vscale(R.c0, b->inv_inertia.x), s1 = vscale(R.c1, b->inv_inertia.y), s2 = vscale(R.c2, b->inv_inertia.z);
+	float xx = ((s0.x * R.c0.x) + (s1.x * R.c1.x)) + (s2.x * R.c2.x);
+	float xy = ((s0.x * R.c0.y) + (s1.x * R.c1.y)) + (s2.x * R.c2.y);
+	float xz = ((s0.x * R.c0.z) + (s1.x * R.c1.z)) + (s2.x * R.c2.z);
+	float yy = ((s0.y * R.c0.y) + (s1.y * R.c1.y)) + (s2.y * R.c2.y);
+	float yz = ((s0.y * R.c0.z) + (s1.y * R.c1.z)) + (s2.y * R.c2.z);
+	float zz = ((s0.z * R.c0.z) + (s1.z * R.c1.z)) + (s2.z * R.c2.z);
+	const int lx = !(b->dofs & 8u), ly = !(b->dofs & 16u), lz = !(b->dofs & 32u);
+	b->M[0] = lx ? 0.0f : xx;
+	b->M[1] = (lx || ly) ? 0.0f : xy;
+	b->M[2] = (lx || lz) ? 0.0f : xz;
+	b->M[3] = ly ? 0.0f : yy;
+	b->M[4] = (ly || lz) ? 0.0f : yz;
+	b->M[5] = lz ? 0.0f : zz;
+	b->im = b->inv_mass;
+}
 
-static v3 apply_inv_inertia(const m33 *R, v3 inv_i, uint32_t dofs, v3 a)
+static v3 sym_mul(const float *M, v3 v)
 {
-	/* world inverse inertia R diag(inv_i) R^T, with locked rotation axes masked in world space */
-	if (!(dofs & 8u)) a.x = 0.0f;
-	if (!(dofs & 16u)) a.y = 0.0f;
-	if (!(dofs & 32u)) a.z = 0.0f;
-	v3 l = mtmul(R, a);
-	l = vmulc(l, inv_i);
-	v3 r = mmul(R, l);
-	if (!(dofs & 8u)) r.x = 0.0f;
-	if (!(dofs & 16u)) r.y = 0.0f;
-	if (!(dofs & 32u)) r.z = 0.0f;
-	return r;
+	return V(((M[0] * v.x) + (M[1] * v.y)) + (M[2] * v.z), ((M[1] * v.x) + (M[3] * v.y)) + (M[4] * v.z),
+			 ((M[2] * v.x) + (M[4] * v.y)) + (M[5] * v.z));
 }
 
 static v3 mask_lin(uint32_t dofs, v3 a)
@@ -1179,120 +1192,92 @@ static v3 mask_lin(uint32_t dofs, v3 a)
 	return a;
 }
 
-typedef struct
-{
-	body_t *A, *B; /* B == NULL for static geometry */
-	m33 RA, RB;
-	float ima, imb;
-} pair_t;
+static const float ZERO_M[6] = {0, 0, 0, 0, 0, 0};
 
-static void pair_init(orc_world *w, manifold_t *m, pair_t *p)
+/* 1 / (J M^-1 J^T) for a contact axis */
+static float eff_mass(float ima, const float *MA, float imb, const float *MB, v3 r1, v3 r2, v3 axis)
 {
-	p->A = &w->bodies[m->a];
-	p->B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
-	p->RA = qmat(p->A->q);
-	p->ima = p->A->motion == ORC_MOTION_DYNAMIC ? p->A->inv_mass : 0.0f;
-	if (p->B)
-	{
-		p->RB = qmat(p->B->q);
-		p->imb = p->B->motion == ORC_MOTION_DYNAMIC ? p->B->inv_mass : 0.0f;
-	}
-	else
-		p->imb = 0.0f;
-}
-
-static v3 inv_i_a(const pair_t *p, v3 a)
-{
-	if (p->A->motion != ORC_MOTION_DYNAMIC) return V(0, 0, 0);
-	return apply_inv_inertia(&p->RA, p->A->inv_inertia, p->A->dofs, a);
-}
-static v3 inv_i_b(const pair_t *p, v3 a)
-{
-	if (!p->B || p->B->motion != ORC_MOTION_DYNAMIC) return V(0, 0, 0);
-	return apply_inv_inertia(&p->RB, p->B->inv_inertia, p->B->dofs, a);
-}
-
-static float eff_mass(const pair_t *p, v3 r1, v3 r2, v3 axis, v3 *r1xa, v3 *r2xa, v3 *i1, v3 *i2)
-{
-	*r1xa = vcross(r1, axis);
-	*r2xa = vcross(r2, axis);
-	*i1 = inv_i_a(p, *r1xa);
-	*i2 = inv_i_b(p, *r2xa);
-	v3 la = mask_lin(p->A->dofs, axis);
-	v3 lb = p->B ? mask_lin(p->B->dofs, axis) : axis;
-	float k = (((p->ima * vdot(la, axis)) + (p->imb * vdot(lb, axis))) + vdot(*i1, *r1xa)) + vdot(*i2, *r2xa);
+	v3 r1xa = vcross(r1, axis), r2xa = vcross(r2, axis);
+	float k = ((ima + imb) + vdot(r1xa, sym_mul(MA, r1xa))) + vdot(r2xa, sym_mul(MB, r2xa));
 	return k > 0.0f ? 1.0f / k : 0.0f;
 }
 
-static float axis_jv(const pair_t *p, v3 axis, v3 r1xa, v3 r2xa)
+/* velocity of a's contact point relative to b's */
+static v3 rel_vel(const body_t *A, const body_t *B, v3 r1, v3 r2)
 {
-	v3 vb = p->B ? p->B->v : V(0, 0, 0), wb = p->B ? p->B->w : V(0, 0, 0);
-	return (vdot(axis, vsub(p->A->v, vb)) + vdot(r1xa, p->A->w)) - vdot(r2xa, wb);
+	v3 ua = vadd(A->v, vcross(A->w, r1));
+	if (!B) return ua;
+	return vsub(ua, vadd(B->v, vcross(B->w, r2)));
 }
 
-static void axis_apply(const pair_t *p, v3 axis, v3 i1, v3 i2, float lambda)
+/* impulse P pushes b along +P and a along -P */
+static void apply_impulse(body_t *A, body_t *B, v3 r1, v3 r2, v3 P)
 {
-	if (p->A->motion == ORC_MOTION_DYNAMIC)
+	if (A->motion == ORC_MOTION_DYNAMIC)
 	{
-		p->A->v = vsub(p->A->v, mask_lin(p->A->dofs, vscale(axis, lambda * p->ima)));
-		p->A->w = vsub(p->A->w, vscale(i1, lambda));
+		A->v = vsub(A->v, mask_lin(A->dofs, vscale(P, A->im)));
+		A->w = vsub(A->w, sym_mul(A->M, vcross(r1, P)));
 	}
-	if (p->B && p->B->motion == ORC_MOTION_DYNAMIC)
+	if (B && B->motion == ORC_MOTION_DYNAMIC)
 	{
-		p->B->v = vadd(p->B->v, mask_lin(p->B->dofs, vscale(axis, lambda * p->imb)));
-		p->B->w = vadd(p->B->w, vscale(i2, lambda));
+		B->v = vadd(B->v, mask_lin(B->dofs, vscale(P, B->im)));
+		B->w = vadd(B->w, sym_mul(B->M, vcross(r2, P)));
 	}
 }
 
-/* per sub-step set-up: lever arms, tangents, effective masses, speculative / restitution bias; then warm start */
-static void setup_and_warm_start(orc_world *w, manifold_t *m, float h)
+/* per sub-step set-up (reads body state only): lever arms, tangents, effective masses, speculative / restitution bias */
+static void setup_manifold(orc_world *w, manifold_t *m, float h)
 {
-	pair_t p;
-	pair_init(w, m, &p);
+	body_t *A = &w->bodies[m->a];
+	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
+	const float imb = B ? B->im : 0.0f;
+	const float *MB = B ? B->M : ZERO_M;
 	m->t1 = vperp(m->n);
 	m->t2 = vcross(m->n, m->t1);
-	const v3 axes[3] = {m->n, m->t1, m->t2};
 	for (int k = 0; k < m->np; k++)
 	{
-		v3 p1 = vadd(p.A->x, mmul(&p.RA, m->p1l[k]));
-		v3 p2 = p.B ? vadd(p.B->x, mmul(&p.RB, m->p2l[k])) : m->p2l[k];
+		v3 p1 = vadd(A->x, qrot(A->q, m->p1l[k]));
+		v3 p2 = B ? vadd(B->x, qrot(B->q, m->p2l[k])) : m->p2l[k];
 		v3 mid = vscale(vadd(p1, p2), 0.5f);
-		v3 r1 = vsub(mid, p.A->x);
-		v3 r2 = p.B ? vsub(mid, p.B->x) : V(0, 0, 0);
-		for (int c = 0; c < 3; c++)
-			m->em[k][c] = eff_mass(&p, r1, r2, axes[c], &m->r1xa[k][c], &m->r2xa[k][c], &m->i1[k][c], &m->i2[k][c]);
+		m->r1[k] = vsub(mid, A->x);
+		m->r2[k] = B ? vsub(mid, B->x) : V(0, 0, 0);
+		m->em[k][0] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->n);
+		m->em[k][1] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->t1);
+		m->em[k][2] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->t2);
 		float pen = vdot(vsub(p1, p2), m->n);
 		float bias = fmaxf(0.0f, -pen / h);
 		if (m->restitution > 0.0f)
 		{
-			float nv = -axis_jv(&p, m->n, m->r1xa[k][0], m->r2xa[k][0]); /* separating speed of b relative to a */
+			float nv = -vdot(m->n, rel_vel(A, B, m->r1[k], m->r2[k])); /* separating speed of b relative to a */
 			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m->restitution * nv;
 		}
 		m->bias[k] = bias;
 	}
+}
+
+/* re-apply the impulses carried over from the previous sub-step */
+static void warm_start(orc_world *w, manifold_t *m)
+{
+	body_t *A = &w->bodies[m->a];
+	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
 	for (int k = 0; k < m->np; k++)
 	{
-		if (m->lt1[k] != 0.0f || m->lt2[k] != 0.0f)
-		{
-			axis_apply(&p, m->t1, m->i1[k][1], m->i2[k][1], m->lt1[k]);
-			axis_apply(&p, m->t2, m->i1[k][2], m->i2[k][2], m->lt2[k]);
-		}
-		if (m->ln[k] != 0.0f) axis_apply(&p, m->n, m->i1[k][0], m->i2[k][0], m->ln[k]);
+		if (m->ln[k] == 0.0f && m->lt1[k] == 0.0f && m->lt2[k] == 0.0f) continue;
+		v3 P = vadd(vadd(vscale(m->n, m->ln[k]), vscale(m->t1, m->lt1[k])), vscale(m->t2, m->lt2[k]));
+		apply_impulse(A, B, m->r1[k], m->r2[k], P);
 	}
 }
 
 static void solve_velocity(orc_world *w, manifold_t *m)
 {
-	pair_t p;
-	p.A = &w->bodies[m->a];
-	p.B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
-	p.ima = p.A->motion == ORC_MOTION_DYNAMIC ? p.A->inv_mass : 0.0f;
-	p.imb = (p.B && p.B->motion == ORC_MOTION_DYNAMIC) ? p.B->inv_mass : 0.0f;
+	body_t *A = &w->bodies[m->a];
+	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
 	/* friction first (non-penetration is more important, so it goes last) */
 	for (int k = 0; k < m->np; k++)
 	{
-		float l1 = m->lt1[k] + (m->em[k][1] * axis_jv(&p, m->t1, m->r1xa[k][1], m->r2xa[k][1]));
-		float l2 = m->lt2[k] + (m->em[k][2] * axis_jv(&p, m->t2, m->r1xa[k][2], m->r2xa[k][2]));
+		v3 u = rel_vel(A, B, m->r1[k], m->r2[k]);
+		float l1 = m->lt1[k] + (m->em[k][1] * vdot(m->t1, u));
+		float l2 = m->lt2[k] + (m->em[k][2] * vdot(m->t2, u));
 		float maxf = m->friction * m->ln[k];
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
@@ -1301,47 +1286,51 @@ static void solve_velocity(orc_world *w, manifold_t *m)
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
-		axis_apply(&p, m->t1, m->i1[k][1], m->i2[k][1], l1 - m->lt1[k]);
-		axis_apply(&p, m->t2, m->i1[k][2], m->i2[k][2], l2 - m->lt2[k]);
+		v3 P = vadd(vscale(m->t1, l1 - m->lt1[k]), vscale(m->t2, l2 - m->lt2[k]));
 		m->lt1[k] = l1;
 		m->lt2[k] = l2;
+		apply_impulse(A, B, m->r1[k], m->r2[k], P);
 	}
 	for (int k = 0; k < m->np; k++)
 	{
-		float jv = axis_jv(&p, m->n, m->r1xa[k][0], m->r2xa[k][0]);
-		float lambda = m->em[k][0] * (jv - m->bias[k]);
+		v3 u = rel_vel(A, B, m->r1[k], m->r2[k]);
+		float lambda = m->em[k][0] * (vdot(m->n, u) - m->bias[k]);
 		float nt = fmaxf(0.0f, m->ln[k] + lambda);
 		lambda = nt - m->ln[k];
 		m->ln[k] = nt;
-		axis_apply(&p, m->n, m->i1[k][0], m->i2[k][0], lambda);
+		apply_impulse(A, B, m->r1[k], m->r2[k], vscale(m->n, lambda));
 	}
 }
 
 static void solve_position(orc_world *w, manifold_t *m)
 {
+	body_t *A = &w->bodies[m->a];
+	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
+	body_world_inertia(A);
+	if (B) body_world_inertia(B);
+	const float imb = B ? B->im : 0.0f;
+	const float *MB = B ? B->M : ZERO_M;
 	for (int k = 0; k < m->np; k++)
 	{
-		pair_t p;
-		pair_init(w, m, &p); /* rotations change inside the loop */
-		v3 p1 = vadd(p.A->x, mmul(&p.RA, m->p1l[k]));
-		v3 p2 = p.B ? vadd(p.B->x, mmul(&p.RB, m->p2l[k])) : m->p2l[k];
+		v3 p1 = vadd(A->x, qrot(A->q, m->p1l[k]));
+		v3 p2 = B ? vadd(B->x, qrot(B->q, m->p2l[k])) : m->p2l[k];
 		float sep = vdot(vsub(p2, p1), m->n) + PENETRATION_SLOP;
 		if (sep >= 0.0f) continue;
 		v3 mid = vscale(vadd(p1, p2), 0.5f);
-		v3 r1 = vsub(mid, p.A->x), r2 = p.B ? vsub(mid, p.B->x) : V(0, 0, 0);
-		v3 rx1, rx2, i1, i2;
-		float e = eff_mass(&p, r1, r2, m->n, &rx1, &rx2, &i1, &i2);
+		v3 r1 = vsub(mid, A->x), r2 = B ? vsub(mid, B->x) : V(0, 0, 0);
+		float e = eff_mass(A->im, A->M, imb, MB, r1, r2, m->n);
 		float c = fmaxf(sep, -MAX_PENETRATION_DISTANCE);
 		float lambda = (-e * BAUMGARTE) * c;
-		if (p.A->motion == ORC_MOTION_DYNAMIC)
+		v3 P = vscale(m->n, lambda);
+		if (A->motion == ORC_MOTION_DYNAMIC)
 		{
-			p.A->x = vsub(p.A->x, mask_lin(p.A->dofs, vscale(m->n, lambda * p.ima)));
-			p.A->q = qstep(p.A->q, vscale(i1, -lambda));
+			A->x = vsub(A->x, mask_lin(A->dofs, vscale(P, A->im)));
+			A->q = qstep(A->q, vneg(sym_mul(A->M, vcross(r1, P))));
 		}
-		if (p.B && p.B->motion == ORC_MOTION_DYNAMIC)
+		if (B && B->motion == ORC_MOTION_DYNAMIC)
 		{
-			p.B->x = vadd(p.B->x, mask_lin(p.B->dofs, vscale(m->n, lambda * p.imb)));
-			p.B->q = qstep(p.B->q, vscale(i2, lambda));
+			B->x = vadd(B->x, mask_lin(B->dofs, vscale(P, B->im)));
+			B->q = qstep(B->q, sym_mul(B->M, vcross(r2, P)));
 		}
 	}
 }
@@ -1363,21 +1352,26 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t i = 0; i < w->max_bodies; i++)
 		{
 			body_t *b = &w->bodies[i];
-			if (!b->alive || b->motion != ORC_MOTION_DYNAMIC) continue;
-			b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
-			b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
-			b->w = vscale(b->w, fmaxf(0.0f, 1.0f - (b->ang_damp * h)));
-			b->v = clamp_len(mask_lin(b->dofs, b->v), MAX_LINEAR_VELOCITY);
-			v3 ww = b->w;
-			if (!(b->dofs & 8u)) ww.x = 0.0f;
-			if (!(b->dofs & 16u)) ww.y = 0.0f;
-			if (!(b->dofs & 32u)) ww.z = 0.0f;
-			b->w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+			if (!b->alive) continue;
+			if (b->motion == ORC_MOTION_DYNAMIC)
+			{
+				b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
+				b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
+				b->w = vscale(b->w, fmaxf(0.0f, 1.0f - (b->ang_damp * h)));
+				b->v = clamp_len(mask_lin(b->dofs, b->v), MAX_LINEAR_VELOCITY);
+				v3 ww = b->w;
+				if (!(b->dofs & 8u)) ww.x = 0.0f;
+				if (!(b->dofs & 16u)) ww.y = 0.0f;
+				if (!(b->dofs & 32u)) ww.z = 0.0f;
+				b->w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+			}
+			body_world_inertia(b);
 		}
 		find_contacts(w, &err);
 		warm_start_match(w);
 		colour_manifolds(w);
-		for (uint32_t k = 0; k < w->nman; k++) setup_and_warm_start(w, &w->man[w->order[k]], h);
+		for (uint32_t k = 0; k < w->nman; k++) setup_manifold(w, &w->man[k], h);
+		for (uint32_t k = 0; k < w->nman; k++) warm_start(w, &w->man[w->order[k]]);
 		for (uint32_t it = 0; it < w->vel_steps; it++)
 			for (uint32_t k = 0; k < w->nman; k++) solve_velocity(w, &w->man[w->order[k]]);
 		for (uint32_t i = 0; i < w->max_bodies; i++)

@@ -1,0 +1,139 @@
+"""GPU parity: batched closest-hit rays through the C ABI vs the brute-force oracle.
+
+Bar (north_star): hit/miss and body/face ids bit-exact; distances within 1e-5 relative.  Both sides evaluate the
+same Moller-Trumbore expression without FMA contraction, so the distances are in fact required to be bit-identical
+here; the 1e-5 bound is asserted as well so a future kernel change reports which bar it broke.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worlds(gpx, orc, scenes, name, max_bodies=8):
+    meshes = scenes.load_static(name)
+    g = gpx.World(worlds=1, max_bodies=max_bodies)
+    o = orc.World(max_bodies)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    return g, o, meshes
+
+
+def _assert_hits_equal(h_gpu, h_ref):
+    assert np.array_equal(h_gpu["body"], h_ref["body"]), "hit/miss or body ids differ"
+    assert np.array_equal(h_gpu["face"], h_ref["face"]), "face ids differ"
+    hit = h_ref["body"] != 0xFFFFFFFF
+    rel = np.abs(h_gpu["fraction"][hit] - h_ref["fraction"][hit]) / np.maximum(h_ref["fraction"][hit], 1e-12)
+    assert rel.size == 0 or rel.max() <= 1e-5, f"hit distance off by {rel.max()} relative (bar 1e-5)"
+    assert np.array_equal(h_gpu["fraction"].view(np.uint32), h_ref["fraction"].view(np.uint32)), "fractions not bit-identical"
+
+
+@pytest.mark.parametrize("name", ["shapes", "stacked", "test", "orb"])
+def test_static_rays_match_oracle(gpx, orc, scenes, name):
+    g, o, meshes = _worlds(gpx, orc, scenes, name)
+    nt, nn, nb = g.static_info()
+    assert nt == sum(len(t) for _, t in meshes) and nb == len(meshes) and nn == max(nt - 1, 1)
+    rays = scenes.shapes_rays(20000, np.array([p for p, _ in meshes]))
+    _assert_hits_equal(g.raycast(rays), o.raycast(rays, mt=True))
+
+
+def test_shapes_rays_match_committed_golden(gpx, orc, scenes):
+    g, o, meshes = _worlds(gpx, orc, scenes, "shapes")
+    rays = scenes.shapes_rays(8192, np.array([p for p, _ in meshes]))
+    gold = np.load(scenes.GOLDEN + "/oracle_rays_shapes.npz")["hits"]
+    _assert_hits_equal(g.raycast(rays), gold)
+
+
+def test_empty_batch_empty_map_and_single_triangle(gpx, orc):
+    g = gpx.World(worlds=1, max_bodies=8)
+    g.commit()
+    rays = np.zeros(4, gpx.RAY_DTYPE)
+    rays["dir"] = (0, 0, -1)
+    rays["tmax"] = 10
+    rays["mask"] = gpx.RAYMASK_STATIC
+    h = g.raycast(rays)
+    assert (h["body"] == gpx.INVALID_BODY).all() and (h["fraction"] == 2.0).all()
+    assert len(g.raycast(rays[:0])) == 0
+    tri = np.array([[[-1, -1, -5], [1, -1, -5], [0, 1, -5]]], np.float32)
+    g.add_mesh((0, 0, 0), tri)
+    g.commit()
+    o = orc.World(8)
+    o.add_mesh((0, 0, 0), tri)
+    rays["origin"][1] = (5, 0, 0)        # misses
+    rays["dir"][2] = (0, 0, 1)           # points away
+    rays["tmax"][3] = 4.0                # too short
+    hg, ho = g.raycast(rays), o.raycast(rays)
+    _assert_hits_equal(hg, ho)
+    assert hg["body"][0] == gpx.STATIC_BODY_BASE and hg["face"][0] == 0 and hg["fraction"][0] == np.float32(0.5)
+    assert (hg["body"][1:] == gpx.INVALID_BODY).all()
+
+
+def test_axis_aligned_and_degenerate_directions(gpx, orc, scenes):
+    """Zero direction components exercise the reciprocal-direction handling of the slab test."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "shapes")
+    pos = np.array([p for p, _ in meshes])
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1],
+                     [1, 1, 0], [0, -1, 1], [1, 0, -1]], np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    rays = np.zeros(len(pos) * len(dirs), gpx.RAY_DTYPE)
+    rays["origin"] = np.repeat(pos, len(dirs), axis=0)
+    rays["dir"] = np.tile(dirs, (len(pos), 1))
+    rays["tmax"] = 50
+    rays["mask"] = gpx.RAYMASK_STATIC
+    _assert_hits_equal(g.raycast(rays), o.raycast(rays))
+
+
+def test_rays_hit_dynamic_bodies_and_respect_masks(gpx, orc, scenes):
+    """Crosshair ray sees STATIC+DYNAMIC layers; the 'triple' laser sees STATIC only; the body filter needs
+    GPX_BODY_BLOCKS_LASERS (engine/src/physics/PlayerPhysics.c:55-77, game/src/actor/prop/Laser.c:40-85)."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "stacked")
+    descs = [gpx.body_desc(position=(0.0, -1.0, -1.5), rotation=(0, 0.3826834, 0, 0.9238795)),
+             gpx.body_desc(position=(1.0, -1.0, -1.5), ray_flags=0),
+             gpx.body_desc(shape=gpx.SHAPE_SPHERE, half_extents=(0.4, 0, 0), position=(-1.0, -1.0, -1.5)),
+             gpx.body_desc(position=(0.0, -0.2, -1.5), layer=gpx.LAYER_SENSOR, motion_type=gpx.MOTION_STATIC, is_sensor=1)]
+    for d in descs:
+        assert g.create(d) == o.create(d)
+    rng = np.random.default_rng(7)
+    n = 6000
+    rays = np.zeros(n, gpx.RAY_DTYPE)
+    rays["origin"] = np.array([0, -0.5, -1.5], np.float32) + rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmax"] = 10
+    for mask in (gpx.RAYMASK_STATIC_DYNAMIC, gpx.RAYMASK_STATIC, 2,
+                 gpx.RAYMASK_STATIC_DYNAMIC | gpx.RAYMASK_REQUIRE_BLOCKS_LASERS):
+        rays["mask"] = mask
+        hg, ho = g.raycast(rays), o.raycast(rays)
+        _assert_hits_equal(hg, ho)
+        if mask == gpx.RAYMASK_STATIC_DYNAMIC:
+            assert set(np.unique(hg["body"][hg["body"] < 8])) == {0, 1, 2}  # boxes + sphere hit, sensor never
+        if mask & gpx.RAYMASK_REQUIRE_BLOCKS_LASERS:
+            assert 1 not in hg["body"]
+
+
+def test_full_size_batch_properties(gpx, orc, scenes):
+    """BASELINE config 3 at full size (2^20 rays): checked by sampling against the oracle and by invariants."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "shapes")
+    n = 1 << 20
+    rays = scenes.shapes_rays(n, np.array([p for p, _ in meshes]))
+    h = g.raycast(rays)
+    hit = h["body"] != gpx.INVALID_BODY
+    assert hit.mean() > 0.99                      # closed rooms: almost every ray hits
+    assert (h["fraction"][hit] >= 0).all() and (h["fraction"][hit] <= 1).all()
+    assert (h["fraction"][~hit] == 2.0).all()
+    assert (h["face"][hit] < 512).all() and ((h["body"][hit] - gpx.STATIC_BODY_BASE) < 24).all()
+    sel = np.random.default_rng(3).choice(n, 30000, replace=False)
+    _assert_hits_equal(h[sel], o.raycast(rays[sel], mt=True))
+    # determinism: same batch again, identical bytes
+    assert np.array_equal(g.raycast(rays).view(np.uint8), h.view(np.uint8))
+
+
+def test_engine_style_single_ray(gpx, orc, scenes):
+    """CastRay_GAME: origin transform, direction = local -Z, fraction * maxDistance = metres (PlayerPhysics.c:305,404)."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "stacked")
+    h = g.raycast_transform((0, 0, 0), (0, 0, 0, 1), 10.0)
+    assert h["body"] == gpx.STATIC_BODY_BASE + 0 and abs(h["fraction"] * 10.0 - 4.0) < 1e-5  # wall z = -4
+    h = g.raycast_transform((0, 0, 0), (0, 0, 0, 1), 3.0)
+    assert h["body"] == gpx.INVALID_BODY
