@@ -912,9 +912,14 @@ __global__ void k_stats(BodyStore bs, ManifoldCache mc, const uint32_t *err, uin
 template <int TILE>
 static int launch_tick_t(gpx_world *w, const TickArgs &a)
 {
-	const uint32_t threads = 128;
-	const uint32_t wpb = threads / TILE;
-	const size_t smem = world_smem_bytes(w->cap, w->cap_m) * wpb;
+	// worlds per block: as many tiles as fit in 128 threads and in the shared-memory budget
+	const size_t per_world = world_smem_bytes(w->cap, w->cap_m);
+	const size_t budget = 200u * 1024u;
+	if (per_world > budget) return GPX_ERR_CAPACITY;
+	uint32_t wpb = 128 / TILE;
+	while (wpb > 1 && per_world * wpb > budget / 2) wpb >>= 1;  // leave room for two blocks per SM
+	const uint32_t threads = wpb * TILE;
+	const size_t smem = per_world * wpb;
 	static size_t configured = 0;
 	if (smem > configured)
 	{

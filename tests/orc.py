@@ -104,7 +104,7 @@ def lib():
                                       C.c_uint64, C.c_float]
     L.orc_static_commit.argtypes = [C.c_void_p]
     L.orc_body_create.restype = C.c_uint32
-    L.orc_body_create.argtypes = [C.c_void_p, C.POINTER(BodyDesc)]
+    L.orc_body_create.argtypes = [C.c_void_p, C.c_void_p]  # same layout as gpx_body_desc
     L.orc_body_destroy.argtypes = [C.c_void_p, C.c_uint32]
     L.orc_body_set_velocity.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.orc_step.restype = C.c_int

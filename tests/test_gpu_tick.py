@@ -13,15 +13,19 @@ POS_TOL, ROT_TOL, REST_TOL = 1e-4, 1e-4, 1e-3
 
 
 def _quat_angle(qa, qb):
-    d = np.abs(np.sum(qa * qb, axis=-1)).clip(0, 1)
-    return 2 * np.arccos(d)
+    """Rotation angle between two orientations (atan2 form: exact near zero, unlike acos of a float32 dot)."""
+    qa, qb = qa.astype(np.float64), qb.astype(np.float64)
+    va, wa, vb, wb = qa[..., :3], qa[..., 3:], qb[..., :3], qb[..., 3:]
+    vec = wa * vb - wb * va - np.cross(va, vb)
+    dot = np.abs(np.sum(qa * qb, axis=-1))
+    return 2 * np.arctan2(np.linalg.norm(vec, axis=-1), dot)
 
 
 def _assert_state(xg, xo, what, exact=True):
     dp = np.abs(xg[..., :3] - xo[..., :3]).max()
     da = _quat_angle(xg[..., 3:], xo[..., 3:]).max()
     assert dp <= POS_TOL, f"{what}: position differs by {dp} m (bar {POS_TOL})"
-    assert da <= ROT_TOL + 1e-3 * 0, f"{what}: orientation differs by {da} rad (bar {ROT_TOL})"
+    assert da <= ROT_TOL, f"{what}: orientation differs by {da} rad (bar {ROT_TOL})"
     if exact:
         assert np.array_equal(xg.view(np.uint32), xo.view(np.uint32)), f"{what}: not bit-identical (max dp {dp})"
 
@@ -106,7 +110,7 @@ def test_ensemble_worlds_match_independent_oracles(gpx, orc, scenes):
 def test_tile_widths_give_identical_results(gpx, orc, scenes, cap, tile_case):
     """The same scene run with every lane-per-world width must produce the same bits (fixed solve order)."""
     g, (o,) = _pair(gpx, orc, scenes, max_bodies=cap, max_manifolds=96)
-    pos = scenes.block_positions(2, 3, 2, 0.42)
+    pos = scenes.block_positions(2, 2, 2, 0.42)
     rng = np.random.default_rng(5)
     for p in pos:
         d = gpx.body_desc(position=tuple(p), linear_velocity=tuple(rng.uniform(-0.5, 0.5, 3)),
