@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the physics tick (and the batched ray query) on B200, next to the CPU restatement.
+
+Workload (BASELINE.json configs[4], the one `metric` is quoted on): an ensemble of independent worlds, each the
+8-box column over sector 0 of stacked.gmap with Philox-randomised initial velocities.  One STEP is
+one fixed tick (dt = 1/60 s, two collision sub-steps; engine/src/physics/MapPhysics.c:72,105-108) of every world a
+rank owns.  Worlds are independent, so ranks shard the ensemble with no data-path collective: 4096 worlds per GPU
+("weak"); NCCL is used only for the timing reduction and the end-of-run stats gather.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA through the C ABI, libgpx.so)
+  python bench.py --impl reference ...                            the CPU arm: the oracle restatement on all host
+                                                                  threads (Jolt/joltc is not buildable here)
+
+JSON keys: see the contract in the task statement; `value` = body-steps/s with state resident in HBM, `e2e` = the
+same metric through the engine-facing per-tick sequence with HOST buffers (ray batch H2D -> rays -> hits D2H -> step
+-> transform mirror D2H), `rays` = the secondary metric (2^20 hitscan rays against shapes.gmap).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BYTES_PER_BODY_STEP = 136   # state R+W 104 B + read-only properties 32 B
+BYTES_PER_RAY = 48          # ray in 32 B + hit out 16 B
+BOXES = 8
+RAYS_PER_WORLD_TICK = 5     # crosshair ray + 4 lasers, as in test.gmap (PlayerPhysics.c:305, Laser.c:142)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines: list[str] = []
+        self.th = None
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._pump, daemon=True)
+        self.th.start()
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- scene set-up
+
+def make_gpu_ensemble(gpx, scenes, worlds: int, first_world: int, device: int):
+    g = gpx.World(worlds=worlds, max_bodies=BOXES, device=device)
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+    g.commit()
+    vel = scenes.ensemble_velocities(worlds, BOXES, first_world=first_world)
+    descs = [gpx.body_desc(position=tuple(p)) for p in scenes.stack_positions(BOXES)]
+    g.create_all(descs, linvel=vel)
+    return g
+
+
+def make_cpu_ensemble(orc, scenes, worlds: int, first_world: int = 0):
+    import ctypes as C
+    meshes = scenes.load_static("stacked")
+    vel = scenes.ensemble_velocities(worlds, BOXES, first_world=first_world)
+    pos = scenes.stack_positions(BOXES)
+    ws = []
+    for wi in range(worlds):
+        o = orc.World(BOXES)
+        for p, t in meshes:
+            o.add_mesh(p, t)
+        for k in range(BOXES):
+            o.create(orc.body_desc(position=tuple(pos[k]), linear_velocity=tuple(vel[wi, k])))
+        ws.append(o)
+    arr = (C.c_void_p * worlds)(*[o.h for o in ws])
+    return ws, arr
+
+
+def tick_rays(gpx, worlds: int, tick: int, out: np.ndarray):
+    """Per-tick engine-style rays for every world: 5 rays from around the column, STATIC|DYNAMIC layers."""
+    n = worlds * RAYS_PER_WORLD_TICK
+    rng = np.random.default_rng(1000 + tick)
+    out["origin"][:n] = np.array([0.0, -0.5, -1.5], np.float32) + rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    out["dir"][:n] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    out["tmax"][:n] = 50.0
+    out["mask"][:n] = gpx.RAYMASK_STATIC_DYNAMIC | (np.repeat(np.arange(worlds, dtype=np.uint32), RAYS_PER_WORLD_TICK) << 16)
+    return n
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_tick_rate(orc, scenes, target_s: float, worlds: int, warm_ticks: int):
+    """body-steps/s of the oracle on all host threads over `worlds` sample worlds; ticks scaled to ~target_s."""
+    ws, arr = make_cpu_ensemble(orc, scenes, worlds)
+    L = orc.lib()
+    threads = min(L.orc_max_threads(), worlds)
+    L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, warm_ticks)
+    t0 = time.perf_counter()
+    L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 10)
+    per_tick = (time.perf_counter() - t0) / 10
+    ticks = int(max(10, min(600, target_s / max(per_tick, 1e-6))))
+    t0 = time.perf_counter()
+    err = L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, ticks)
+    dt = time.perf_counter() - t0
+    assert err == 0
+    return worlds * BOXES * ticks / dt, threads, ticks
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the same tick on all host threads, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import orc
+    scenes = importlib.import_module("c-game-engine_b200.scenes")
+    L = orc.lib()
+    worlds = args.ref_worlds
+    ws, arr = make_cpu_ensemble(orc, scenes, worlds)
+    threads = min(L.orc_max_threads(), worlds)
+    for _ in range(args.warmup):
+        L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        err = L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 1)
+        assert err == 0
+    dt = time.perf_counter() - t0
+    value = worlds * BOXES * args.steps / dt
+    sample = f"{worlds} of the {args.worlds} worlds per step (first {worlds} world indices), {args.steps} ticks"
+    line = {
+        "impl": "reference", "metric": "body_steps_per_s", "value": value, "unit": "body-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "CPU restatement (oracle/orc.c); Jolt/joltc is not vendored and cannot be built here"},
+        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C5 ensemble: {args.worlds} independent stacked.gmap worlds per GPU x {BOXES}-box column, "
+                        "Philox initial velocities (key 0x5EED0005), dt=1/60, 2 sub-steps, 10 velocity + 2 position iterations",
+            "worlds_per_gpu": args.worlds, "bodies_per_world": BOXES, "static_triangles": 396,
+            "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
+            "parallelism": f"worlds sharded, {args.gpus} rank(s), no data-path collective"}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gpx = importlib.import_module("c-game-engine_b200")
+    scenes = importlib.import_module("c-game-engine_b200.scenes")
+    L = gpx.lib()
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = args.worlds
+    first = rank * W
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    # ---------------- value: ticks with state resident in HBM
+    g = make_gpu_ensemble(gpx, scenes, W, first, local_rank)
+    for _ in range(args.warmup):
+        assert g.step() == 0
+    assert g.sync() == 0
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.gpx_launch_count()
+    dev_ms = 0.0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        g.timer_begin()
+        rc = g.step()
+        dev_ms += g.timer_end()
+        assert rc == 0, f"gpx_step error {rc}"
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = L.gpx_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    assert g.sync() == 0
+    dev_ms = max_over_ranks(dev_ms)
+    ms_per_step = dev_ms / args.steps
+    bodies_per_rank = W * BOXES
+    value = world_size * bodies_per_rank / (ms_per_step * 1e-3)
+    achieved = bodies_per_rank * BYTES_PER_BODY_STEP / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- e2e: the engine-facing per-tick sequence with host buffers
+    n_rays = W * RAYS_PER_WORLD_TICK
+    h_rays = gpx.pinned_array(n_rays, gpx.RAY_DTYPE)
+    h_hits = gpx.pinned_array(n_rays, gpx.HIT_DTYPE)
+    tick_rays(gpx, W, 0, h_rays)
+    for _ in range(3):
+        g.raycast_into(h_rays, h_hits)
+        g.step()
+        g.sync()
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.raycast_into(h_rays, h_hits)     # H2D rays, k_raycast, D2H hits (PlayerPhysics.c:305, Laser.c:142)
+        rc = g.step()                      # JPH_PhysicsSystem_Update (MapPhysics.c:105)
+        rc |= g.sync()                     # transform mirror D2H, served to the getters (rows a9)
+        assert rc == 0
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world_size * bodies_per_rank * e2e_steps / e2e_s
+    h2d = n_rays * 32
+    d2h = n_rays * 16 + 2 * 16 * bodies_per_rank + 4
+    stats = g.stats()
+    assert (stats["error"] == 0).all()
+
+    # ---------------- secondary metric: 2^20 hitscan rays against shapes.gmap (C3)
+    rays_res = bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
+
+    # ---------------- end-of-run stats gather over NCCL (the only collective)
+    gathered_worlds = W
+    if dist is not None:
+        t = torch.from_numpy(stats.view(np.uint8).reshape(-1).copy()).cuda()
+        out = [torch.empty_like(t) for _ in range(world_size)]
+        dist.all_gather(out, t)
+        gathered_worlds = sum(o.numel() for o in out) // 32
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            import orc
+            v, threads, ticks = cpu_tick_rate(orc, scenes, args.cpu_seconds, args.ref_worlds, 5)
+            cpu = {"value": v, "unit": "body-steps/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.ref_worlds} worlds of the same ensemble x {ticks} ticks on {threads} host threads "
+                             "(oracle/orc.c via orc_step_many; Jolt unavailable in this environment)"}
+        line = {
+            "metric": "body_steps_per_s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": f"per tick: gpx_raycast_batch({n_rays} host rays, pinned) + gpx_step + gpx_sync_transforms; wall clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_tick", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": args.traffic, "peak_source": peak_src,
+                         "bytes_per_unit": BYTES_PER_BODY_STEP, "units_per_launch": bodies_per_rank},
+            "cpu_baseline": cpu,
+            "rays": rays_res,
+            "wall_ms_timed_region": wall_ms,
+            "stats_gathered_worlds": gathered_worlds,
+            "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ranks, flush, hbm_peak):
+    import torch
+    meshes = scenes.load_static("shapes")
+    g = gpx.World(worlds=1, max_bodies=8, device=device)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+    g.commit()
+    n = args.rays
+    rays = scenes.shapes_rays(n, np.array([p for p, _ in meshes]), first=rank * n)
+    L = gpx.lib()
+    d_rays = L.gpx_device_alloc(n * 32)
+    d_hits = L.gpx_device_alloc(n * 16)
+    assert d_rays and d_hits
+    L.gpx_memcpy_h2d(d_rays, rays.ctypes.data, n * 32)
+    for _ in range(3):
+        g.raycast_device(d_rays, n, d_hits)
+    g.device_sync()
+    barrier()
+    reps = args.ray_reps
+    ms = 0.0
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        g.timer_begin()
+        g.raycast_device(d_rays, n, d_hits)
+        ms += g.timer_end()
+    ms = max_over_ranks(ms) / reps
+    # e2e with pinned host buffers
+    h_rays = gpx.pinned_array(n, gpx.RAY_DTYPE)
+    h_hits = gpx.pinned_array(n, gpx.HIT_DTYPE)
+    h_rays[:] = rays
+    g.raycast_into(h_rays, h_hits)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        g.raycast_into(h_rays, h_hits)
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / reps
+    hit_frac = float((h_hits["body"] != gpx.INVALID_BODY).mean())
+    L.gpx_device_free(d_rays)
+    L.gpx_device_free(d_hits)
+    res = {"metric": "rays_per_s", "value": world_size * n / (ms * 1e-3), "unit": "rays/s", "rays_per_gpu": n,
+           "ms_per_batch": ms, "workload": "C3: 2^20 closest-hit rays vs shapes.gmap (512 tris), STATIC mask, Philox key 0x5EED0003",
+           "e2e": {"value": world_size * n / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16},
+           "roofline": {"bound": "hbm", "kernel": "k_raycast", "achieved": n * BYTES_PER_RAY / (ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": args.ray_traffic},
+           "hit_fraction": hit_frac}
+    if rank == 0 and world_size == 1 and not args.no_cpu:
+        import orc
+        o = orc.World(8)
+        for pos, tris in meshes:
+            o.add_mesh(pos, tris)
+        m = min(n, args.cpu_rays)
+        t0 = time.perf_counter()
+        ho = o.raycast(rays[:m], mt=True)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": m / dt, "unit": "rays/s", "cores": orc.lib().orc_max_threads(), "kind": "port",
+                               "sample": f"first {m} rays of the batch, brute force over 512 triangles (oracle/orc.c)"}
+        res["sample_matches_oracle"] = bool(np.array_equal(ho.view(np.uint8), np.asarray(h_hits[:m]).view(np.uint8)))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--rays", type=int, default=1 << 20, help="rays per GPU for the secondary metric")
+    ap.add_argument("--ray-reps", type=int, default=20)
+    ap.add_argument("--ref-worlds", type=int, default=256, help="worlds per step in the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-rays", type=int, default=1 << 17)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiling runs)")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per k_tick launch (profiles/), if known")
+    ap.add_argument("--ray-traffic", type=float, default=None)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,8 @@ def lib() -> C.CDLL:
         "gpx_raycast_transform": (i32, [vp, u32, C.POINTER(Transform), f32, u32, vp]),
         "gpx_device_alloc": (vp, [u64]),
         "gpx_device_free": (None, [vp]),
+        "gpx_host_alloc": (vp, [u64]),
+        "gpx_host_free": (None, [vp]),
         "gpx_memcpy_h2d": (i32, [vp, vp, u64]),
         "gpx_memcpy_d2h": (i32, [vp, vp, u64]),
         "gpx_device_sync": (i32, [vp]),
@@ -333,6 +335,28 @@ class World:
         _check(self.L.gpx_raycast_batch(self.h, rays.ctypes.data, len(rays), hits.ctypes.data), "gpx_raycast_batch")
         return hits
 
+    def raycast_into(self, rays: np.ndarray, hits: np.ndarray) -> None:
+        """gpx_raycast_batch on caller-owned host arrays (e.g. pinned ones from pinned_array): no allocation."""
+        assert rays.dtype == RAY_DTYPE and hits.dtype == HIT_DTYPE and len(hits) >= len(rays)
+        _check(self.L.gpx_raycast_batch(self.h, rays.ctypes.data, len(rays), hits.ctypes.data), "gpx_raycast_batch")
+
+    def raycast_device(self, d_rays: int, n: int, d_hits: int) -> None:
+        """gpx_raycast_batch_device: buffers already resident in HBM; asynchronous on the world's stream."""
+        _check(self.L.gpx_raycast_batch_device(self.h, C.c_void_p(d_rays), n, C.c_void_p(d_hits)),
+               "gpx_raycast_batch_device")
+
+    def timer_begin(self):
+        _check(self.L.gpx_timer_begin(self.h), "gpx_timer_begin")
+
+    def timer_end(self) -> float:
+        ms = self.L.gpx_timer_end(self.h)
+        if ms < 0:
+            raise GpxError(f"gpx_timer_end failed: {self.L.gpx_last_error().decode()}")
+        return ms
+
+    def device_sync(self):
+        _check(self.L.gpx_device_sync(self.h), "gpx_device_sync")
+
     def raycast_transform(self, pos, rot, max_distance, mask=RAYMASK_STATIC_DYNAMIC, world=0):
         t = Transform()
         t.position[:] = pos
@@ -341,3 +365,32 @@ class World:
         _check(self.L.gpx_raycast_transform(self.h, world, C.byref(t), max_distance, mask, hit.ctypes.data),
                "gpx_raycast_transform")
         return hit[0]
+
+
+def pinned_array(n: int, dtype) -> np.ndarray:
+    """numpy view of page-locked host memory from gpx_host_alloc (kept alive by the returned array's base)."""
+    dtype = np.dtype(dtype)
+    L = lib()
+    nbytes = max(int(n) * dtype.itemsize, 1)
+    p = L.gpx_host_alloc(nbytes)
+    if not p:
+        raise GpxError("gpx_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+            self.buf = (C.c_uint8 * nbytes).from_address(ptr)
+
+        def __del__(self):
+            try:
+                L.gpx_host_free(C.c_void_p(self.ptr))
+            except Exception:
+                pass
+
+    o = _Owner(p)
+    a = np.frombuffer(o.buf, dtype=dtype, count=int(n))
+    _PINNED.append(o)  # freed at interpreter exit; harness buffers live for the whole run
+    return a
+
+
+_PINNED: list = []

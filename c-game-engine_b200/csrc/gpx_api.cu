@@ -696,6 +696,13 @@ void *gpx_device_alloc(uint64_t bytes)
 	return p;
 }
 void gpx_device_free(void *p) { cudaFree(p); }
+void *gpx_host_alloc(uint64_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+	return p;
+}
+void gpx_host_free(void *p) { cudaFreeHost(p); }
 int gpx_memcpy_h2d(void *dst, const void *src, uint64_t bytes)
 {
 	GPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));

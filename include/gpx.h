@@ -232,6 +232,9 @@ int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *ori
 /* ---- device helpers for harnesses --------------------------------------------------------------------------------- */
 void *gpx_device_alloc(uint64_t bytes);
 void gpx_device_free(void *p);
+/* Page-locked host memory for ray/hit staging buffers (so the copies inside gpx_raycast_batch run at PCIe rate). */
+void *gpx_host_alloc(uint64_t bytes);
+void gpx_host_free(void *p);
 int gpx_memcpy_h2d(void *dst, const void *src, uint64_t bytes);
 int gpx_memcpy_d2h(void *dst, const void *src, uint64_t bytes);
 int gpx_device_sync(gpx_world *w);
