@@ -202,7 +202,7 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	w->device = cfg->device;
 	w->W = cfg->worlds;
 	w->cap = cfg->max_bodies_per_world;
-	w->cap_m = cfg->max_manifolds_per_world ? cfg->max_manifolds_per_world : w->cap * 4u;
+	w->cap_m = cfg->max_manifolds_per_world ? cfg->max_manifolds_per_world : (w->cap * 3u < 16u ? 16u : w->cap * 3u);
 	if (w->cap_m & 1u) w->cap_m++;
 	const size_t nb = (size_t)w->W * w->cap, nm = (size_t)w->W * w->cap_m;
 	bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;

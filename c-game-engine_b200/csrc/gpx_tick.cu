@@ -1,9 +1,11 @@
 // gpx_tick.cu — the fixed-timestep physics tick, one fused kernel per tick for an ensemble of small worlds.
 //
 // Replaces JPH_PhysicsSystem_Update(system, dt, collisionSteps = 2, jobSystem) as the reference calls it from
-// MapFixedUpdate (engine/src/physics/MapPhysics.c:105-108).  One TILE of lanes owns one world; the world's bodies,
-// contact manifolds and warm-start cache live in shared memory for the whole tick, so HBM sees each body exactly
-// once in and once out per tick (the structure-of-arrays body store, float4 loads/stores, lane = body).
+// MapFixedUpdate (engine/src/physics/MapPhysics.c:105-108).  One TILE of lanes owns one world; the world's bodies and
+// contact manifolds live in shared memory for the whole tick, so HBM sees each body exactly once in and once out per
+// tick (structure-of-arrays body store, float4 loads/stores, lane = body).  The warm-start cache of the previous
+// sub-step lives in global memory (L2-resident) so that the shared-memory footprint of a world stays under 8 KB and
+// every world of a 4096-world ensemble is resident at once (one wave, ~28 worlds per SM).
 //
 // Phases of a sub-step (barriers are tile-wide; a tile never spans warps):
 //   1 lane/body     gravity, damping, velocity clamp, world inverse inertia, AABB          ("integrate velocities")
@@ -13,7 +15,8 @@
 //   4 lane/pair     box-box / sphere contact manifolds, one thread per pair               ("narrowphase")
 //   5 lane/manifold match against the previous sub-step's cache, carry impulses           ("warm start")
 //   6 lane 0        greedy graph colouring in canonical manifold order
-//   7 lane/manifold constraint set-up; then per colour: warm start, 10 x velocity solve   ("coloured Gauss-Seidel")
+//   7 lane/manifold constraint rows held in REGISTERS for the whole velocity solve; per colour the lane pulls its two
+//                   bodies' velocities from shared memory, runs its rows, pushes them back  ("coloured Gauss-Seidel")
 //   8 lane/body     integrate positions and rotations                                      ("integrate")
 //   9 lane/manifold per colour: 2 x Baumgarte position solve
 // The solve order (colour, manifold index) and every arithmetic expression are fixed, so results are reproducible
@@ -42,25 +45,32 @@ struct SBody  // 39 words: odd stride, conflict-free when lane = body
 	float inv_mass;  // as stored in the body store
 };
 
-struct SMan  // 91 words
+struct SMan  // 49 words (odd stride): what outlives one manifold's register-resident solve
 {
 	uint32_t a, b;
-	v3 n;
 	int np;      // 0 = empty slot (pair that did not touch)
 	int colour;
+	v3 n;
 	float friction, restitution;
-	v3 t1, t2;
 	v3 p1l[4], p2l[4];
 	float ln[4], lt1[4], lt2[4];
 	float bias[4];
-	v3 r1[4], r2[4];
-	float em[4][3];
 };
 
-struct SPrev  // 39 words
+// One manifold's constraint rows, register-resident while its lane iterates (phase 7).
+struct Con
 {
-	uint32_t a, b, np;
-	v3 p1l[4], p2l[4];
+	uint32_t ia, ib;
+	bool has_b, a_dyn, b_dyn;
+	uint32_t a_dofs, b_dofs;
+	float ima, imb;
+	float MA[6], MB[6];
+	int np;
+	float friction;
+	v3 n, t1, t2;
+	v3 r1[4], r2[4];
+	float em[4][3];
+	float bias[4];
 	float ln[4], lt1[4], lt2[4];
 };
 
@@ -78,13 +88,14 @@ struct TickArgs
 __host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
 {
 	size_t b = 0;
-	b += sizeof(unsigned long long) * cap;            // per-body pair masks / colour sets (first: 8-byte aligned)
+	b += sizeof(unsigned long long) * cap;  // per-body pair masks / colour sets (first: 8-byte aligned)
 	b += sizeof(SBody) * cap;
 	b += sizeof(SMan) * cap_m;
-	b += sizeof(SPrev) * cap_m;
-	b += sizeof(uint32_t) * 2 * cap_m;                // pair list (a, b)
-	b += sizeof(uint32_t) * 2 * cap;                  // per-body counts, bases
-	b += sizeof(uint32_t) * 8;                        // header
+	b += sizeof(uint32_t) * 2 * cap_m;      // pair list (a | slot << 16, b)
+	b += sizeof(uint32_t) * 3 * cap_m;      // keys of the previous sub-step's manifolds (a, b, np)
+	b += sizeof(uint32_t) * cap_m;          // active manifolds in canonical order
+	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
+	b += sizeof(uint32_t) * 8;              // header
 	return (b + 15) & ~(size_t)15;
 }
 
@@ -167,9 +178,9 @@ __device__ __forceinline__ bool layers_collide(uint32_t la, uint32_t lb)
 }
 
 // Box query of the static LBVH: leaves whose exact triangle box overlaps [lo-m, hi+m], sorted by triangle index.
-__device__ __forceinline__ int query_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris,
-											uint32_t n_nodes, v3 lo, v3 hi, float m, int *cand_orig, int *cand_leaf,
-											bool &overflow)
+__device__ __noinline__ int query_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris,
+										 uint32_t n_nodes, v3 lo, v3 hi, float m, int *cand_orig, int *cand_leaf,
+										 bool &overflow)
 {
 	int nc = 0;
 	if (n_nodes == 0) return 0;
@@ -234,82 +245,166 @@ __device__ __forceinline__ float eff_mass(float ima, const float *MA, float imb,
 	return k > 0.0f ? 1.0f / k : 0.0f;
 }
 
-__device__ __forceinline__ v3 rel_vel(const SBody &A, const SBody *B, v3 r1, v3 r2)
+// The two bodies' velocities of one manifold, in registers for the duration of one colour phase.
+struct Vel
 {
-	v3 ua = A.v + cross(A.w, r1);
-	if (!B) return ua;
-	return ua - (B->v + cross(B->w, r2));
+	v3 va, wa, vb, wb;
+};
+
+__device__ __forceinline__ v3 rel_vel(const Con &c, const Vel &u, int k)
+{
+	v3 ua = u.va + cross(u.wa, c.r1[k]);
+	if (!c.has_b) return ua;
+	return ua - (u.vb + cross(u.wb, c.r2[k]));
 }
 
-__device__ __forceinline__ void apply_impulse(SBody &A, SBody *B, v3 r1, v3 r2, v3 P)
+__device__ __forceinline__ void apply_impulse(const Con &c, Vel &u, int k, v3 P)
 {
-	if (is_dynamic(A.flags))
+	if (c.a_dyn)
 	{
-		A.v = A.v - mask_lin(dofs_of(A.flags), P * A.im);
-		A.w = A.w - sym_mul(A.M, cross(r1, P));
+		u.va = u.va - mask_lin(c.a_dofs, P * c.ima);
+		u.wa = u.wa - sym_mul(c.MA, cross(c.r1[k], P));
 	}
-	if (B && is_dynamic(B->flags))
+	if (c.has_b && c.b_dyn)
 	{
-		B->v = B->v + mask_lin(dofs_of(B->flags), P * B->im);
-		B->w = B->w + sym_mul(B->M, cross(r2, P));
+		u.vb = u.vb + mask_lin(c.b_dofs, P * c.imb);
+		u.wb = u.wb + sym_mul(c.MB, cross(c.r2[k], P));
 	}
 }
 
-__device__ __forceinline__ void setup_manifold(SMan &m, SBody *bodies, float h)
+__device__ __forceinline__ void load_vel(const Con &c, const SBody *bodies, Vel &u)
 {
-	SBody &A = bodies[m.a];
-	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
-	const float zero_m[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-	const float imb = B ? B->im : 0.0f;
-	const float *MB = B ? B->M : zero_m;
-	m.t1 = vperp(m.n);
-	m.t2 = cross(m.n, m.t1);
-	for (int k = 0; k < m.np; k++)
+	u.va = bodies[c.ia].v;
+	u.wa = bodies[c.ia].w;
+	if (c.has_b)
 	{
-		v3 p1 = A.x + qrot(A.q, m.p1l[k]);
-		v3 p2 = B ? B->x + qrot(B->q, m.p2l[k]) : m.p2l[k];
-		v3 mid = (p1 + p2) * 0.5f;
-		v3 r1 = mid - A.x;
-		v3 r2 = B ? mid - B->x : V(0.0f, 0.0f, 0.0f);
-		m.r1[k] = r1;
-		m.r2[k] = r2;
-		m.em[k][0] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.n);
-		m.em[k][1] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.t1);
-		m.em[k][2] = eff_mass(A.im, A.M, imb, MB, r1, r2, m.t2);
-		float pen = dot(p1 - p2, m.n);
-		float bias = fmaxf(0.0f, -pen / h);
-		if (m.restitution > 0.0f)
+		u.vb = bodies[c.ib].v;
+		u.wb = bodies[c.ib].w;
+	}
+	else
+		u.vb = u.wb = V(0.0f, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ void store_vel(const Con &c, SBody *bodies, const Vel &u)
+{
+	if (c.a_dyn)
+	{
+		bodies[c.ia].v = u.va;
+		bodies[c.ia].w = u.wa;
+	}
+	if (c.has_b && c.b_dyn)
+	{
+		bodies[c.ib].v = u.vb;
+		bodies[c.ib].w = u.wb;
+	}
+}
+
+// Constraint set-up of one manifold (reads body state only).  FIRST: also derives the speculative / restitution bias
+// and parks it in the shared record; later rebuilds (worlds with more manifolds than lanes) read it back.
+template <bool FIRST>
+__device__ __forceinline__ void build_con(Con &c, SMan &m, const SBody *bodies, float h)
+{
+	const SBody &A = bodies[m.a];
+	c.ia = m.a;
+	c.has_b = m.b < STATIC_BODY_BASE;
+	c.ib = c.has_b ? m.b : m.a;
+	const SBody &B = bodies[c.ib];
+	c.a_dyn = is_dynamic(A.flags);
+	c.b_dyn = c.has_b && is_dynamic(B.flags);
+	c.a_dofs = dofs_of(A.flags);
+	c.b_dofs = dofs_of(B.flags);
+	c.ima = A.im;
+	c.imb = c.has_b ? B.im : 0.0f;
+#pragma unroll
+	for (int k = 0; k < 6; k++)
+	{
+		c.MA[k] = A.M[k];
+		c.MB[k] = c.has_b ? B.M[k] : 0.0f;
+	}
+	c.np = m.np;
+	c.friction = m.friction;
+	c.n = m.n;
+	c.t1 = vperp(c.n);
+	c.t2 = cross(c.n, c.t1);
+	const v3 ax = A.x, bx = B.x;
+	const q4 aq = A.q, bq = B.q;
+	Vel u;
+	if (FIRST) load_vel(c, bodies, u);
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		if (k < c.np)
 		{
-			float nv = -dot(m.n, rel_vel(A, B, r1, r2));
-			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
+			v3 p1 = ax + qrot(aq, m.p1l[k]);
+			v3 p2 = c.has_b ? bx + qrot(bq, m.p2l[k]) : m.p2l[k];
+			v3 mid = (p1 + p2) * 0.5f;
+			c.r1[k] = mid - ax;
+			c.r2[k] = c.has_b ? mid - bx : V(0.0f, 0.0f, 0.0f);
+			c.em[k][0] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.n);
+			c.em[k][1] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.t1);
+			c.em[k][2] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.t2);
+			if (FIRST)
+			{
+				float pen = dot(p1 - p2, c.n);
+				float bias = fmaxf(0.0f, -pen / h);
+				if (m.restitution > 0.0f)
+				{
+					float nv = -dot(c.n, rel_vel(c, u, k));
+					if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
+				}
+				c.bias[k] = bias;
+				m.bias[k] = bias;
+			}
+			else
+				c.bias[k] = m.bias[k];
+			c.ln[k] = m.ln[k];
+			c.lt1[k] = m.lt1[k];
+			c.lt2[k] = m.lt2[k];
 		}
-		m.bias[k] = bias;
+		else
+		{
+			c.r1[k] = c.r2[k] = V(0.0f, 0.0f, 0.0f);
+			c.em[k][0] = c.em[k][1] = c.em[k][2] = 0.0f;
+			c.bias[k] = c.ln[k] = c.lt1[k] = c.lt2[k] = 0.0f;
+		}
 	}
 }
 
-__device__ __forceinline__ void warm_start(SMan &m, SBody *bodies)
+__device__ __forceinline__ void store_lambdas(const Con &c, SMan &m)
 {
-	SBody &A = bodies[m.a];
-	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
-	for (int k = 0; k < m.np; k++)
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (k < c.np)
+		{
+			m.ln[k] = c.ln[k];
+			m.lt1[k] = c.lt1[k];
+			m.lt2[k] = c.lt2[k];
+		}
+}
+
+__device__ __forceinline__ void warm_start(const Con &c, Vel &u)
+{
+#pragma unroll
+	for (int k = 0; k < 4; k++)
 	{
-		if (m.ln[k] == 0.0f && m.lt1[k] == 0.0f && m.lt2[k] == 0.0f) continue;
-		v3 P = ((m.n * m.ln[k]) + (m.t1 * m.lt1[k])) + (m.t2 * m.lt2[k]);
-		apply_impulse(A, B, m.r1[k], m.r2[k], P);
+		if (k >= c.np) continue;
+		if (c.ln[k] == 0.0f && c.lt1[k] == 0.0f && c.lt2[k] == 0.0f) continue;
+		v3 P = ((c.n * c.ln[k]) + (c.t1 * c.lt1[k])) + (c.t2 * c.lt2[k]);
+		apply_impulse(c, u, k, P);
 	}
 }
 
-__device__ __forceinline__ void solve_velocity(SMan &m, SBody *bodies)
+__device__ __forceinline__ void solve_velocity(Con &c, Vel &u)
 {
-	SBody &A = bodies[m.a];
-	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
 	// friction first: non-penetration is more important, so it goes last
-	for (int k = 0; k < m.np; k++)
+#pragma unroll
+	for (int k = 0; k < 4; k++)
 	{
-		v3 u = rel_vel(A, B, m.r1[k], m.r2[k]);
-		float l1 = m.lt1[k] + (m.em[k][1] * dot(m.t1, u));
-		float l2 = m.lt2[k] + (m.em[k][2] * dot(m.t2, u));
-		float maxf = m.friction * m.ln[k];
+		if (k >= c.np) continue;
+		v3 rv = rel_vel(c, u, k);
+		float l1 = c.lt1[k] + (c.em[k][1] * dot(c.t1, rv));
+		float l2 = c.lt2[k] + (c.em[k][2] * dot(c.t2, rv));
+		float maxf = c.friction * c.ln[k];
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
@@ -317,23 +412,25 @@ __device__ __forceinline__ void solve_velocity(SMan &m, SBody *bodies)
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
-		v3 P = (m.t1 * (l1 - m.lt1[k])) + (m.t2 * (l2 - m.lt2[k]));
-		m.lt1[k] = l1;
-		m.lt2[k] = l2;
-		apply_impulse(A, B, m.r1[k], m.r2[k], P);
+		v3 P = (c.t1 * (l1 - c.lt1[k])) + (c.t2 * (l2 - c.lt2[k]));
+		c.lt1[k] = l1;
+		c.lt2[k] = l2;
+		apply_impulse(c, u, k, P);
 	}
-	for (int k = 0; k < m.np; k++)
+#pragma unroll
+	for (int k = 0; k < 4; k++)
 	{
-		v3 u = rel_vel(A, B, m.r1[k], m.r2[k]);
-		float lambda = m.em[k][0] * (dot(m.n, u) - m.bias[k]);
-		float nt = fmaxf(0.0f, m.ln[k] + lambda);
-		lambda = nt - m.ln[k];
-		m.ln[k] = nt;
-		apply_impulse(A, B, m.r1[k], m.r2[k], m.n * lambda);
+		if (k >= c.np) continue;
+		v3 rv = rel_vel(c, u, k);
+		float lambda = c.em[k][0] * (dot(c.n, rv) - c.bias[k]);
+		float nt = fmaxf(0.0f, c.ln[k] + lambda);
+		lambda = nt - c.ln[k];
+		c.ln[k] = nt;
+		apply_impulse(c, u, k, c.n * lambda);
 	}
 }
 
-__device__ __forceinline__ void solve_position(SMan &m, SBody *bodies)
+__device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
 {
 	SBody &A = bodies[m.a];
 	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
@@ -406,12 +503,15 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	unsigned long long *pmask = reinterpret_cast<unsigned long long *>(base);
 	SBody *bodies = reinterpret_cast<SBody *>(pmask + cap);
 	SMan *man = reinterpret_cast<SMan *>(bodies + cap);
-	SPrev *prev = reinterpret_cast<SPrev *>(man + cap_m);
-	uint32_t *pair_a = reinterpret_cast<uint32_t *>(prev + cap_m);
+	uint32_t *pair_a = reinterpret_cast<uint32_t *>(man + cap_m);
 	uint32_t *pair_b = pair_a + cap_m;
-	uint32_t *cnt_static = pair_b + cap_m;
+	uint32_t *pkey_a = pair_b + cap_m;
+	uint32_t *pkey_b = pkey_a + cap_m;
+	uint32_t *pkey_np = pkey_b + cap_m;
+	uint32_t *act = pkey_np + cap_m;
+	uint32_t *cnt_static = act + cap_m;
 	uint32_t *slot_base = cnt_static + cap;
-	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs
+	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
 
 	const uint32_t g0 = world * cap;
 	// ---- load: HBM -> shared, lane = body, 16-byte vector loads
@@ -441,31 +541,23 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		hdr[3] = 0;
 	}
 	tile.sync();
-	for (uint32_t i = lane; i < hdr[1]; i += TILE)
-	{
-		SPrev &o = prev[i];
-		const uint4 k = a.mc.key[m0 + i];
-		o.a = k.x; o.b = k.y; o.np = k.z;
-		const float4 l2 = a.mc.lt2[m0 + i];
-		const float l2a[4] = {l2.x, l2.y, l2.z, l2.w};
-#pragma unroll
-		for (int k4 = 0; k4 < 4; k4++)
-		{
-			const float4 c1 = a.mc.p1[4 * (m0 + i) + k4], c2 = a.mc.p2[4 * (m0 + i) + k4];
-			o.p1l[k4] = V(c1);
-			o.ln[k4] = c1.w;
-			o.p2l[k4] = V(c2);
-			o.lt1[k4] = c2.w;
-			o.lt2[k4] = l2a[k4];
-		}
-	}
-	tile.sync();
 
 	const float h = a.p.h;
 	const v3 gravity = V(a.p.gx, a.p.gy, a.p.gz);
 
 	for (int sub = 0; sub < a.p.substeps; sub++)
 	{
+		// ---- 0: keys of the cached manifolds (global -> shared; the records themselves stay in L2)
+		{
+			const uint32_t nprev = hdr[1];
+			for (uint32_t i = lane; i < nprev; i += TILE)
+			{
+				const uint4 k = __ldcg(&a.mc.key[m0 + i]);
+				pkey_a[i] = k.x;
+				pkey_b[i] = k.y;
+				pkey_np[i] = k.z;
+			}
+		}
 		// ---- 1: forces, inertia, bounds
 		for (uint32_t i = lane; i < cap; i += TILE)
 		{
@@ -687,7 +779,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		}
 		tile.sync();
 
-		// ---- 5: carry impulses from the previous sub-step's manifolds
+		// ---- 5: carry impulses from the previous sub-step's manifolds (keys in shared memory, records in L2)
 		const uint32_t nman = hdr[0], nprev = hdr[1];
 		for (uint32_t mi = lane; mi < nman; mi += TILE)
 		{
@@ -695,30 +787,40 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			if (m.np == 0) continue;
 			for (uint32_t j = 0; j < nprev; j++)
 			{
-				const SPrev &o = prev[j];
-				if (o.a != m.a || o.b != m.b) continue;
+				if (pkey_a[j] != m.a || pkey_b[j] != m.b) continue;
+				const uint32_t onp = pkey_np[j];
+				const float4 l2 = __ldcg(&a.mc.lt2[m0 + j]);
+				const float ol2[4] = {l2.x, l2.y, l2.z, l2.w};
+				float4 c1[4], c2[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					c1[k] = __ldcg(&a.mc.p1[4 * (m0 + j) + k]);
+					c2[k] = __ldcg(&a.mc.p2[4 * (m0 + j) + k]);
+				}
 				for (int p = 0; p < m.np; p++)
 				{
 					if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
-					for (uint32_t k = 0; k < o.np; k++)
-						if (len2(m.p1l[p] - o.p1l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
-							len2(m.p2l[p] - o.p2l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ)
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						if ((uint32_t)k < onp && len2(m.p1l[p] - V(c1[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
+							len2(m.p2l[p] - V(c2[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ)
 						{
-							m.ln[p] = o.ln[k];
-							m.lt1[p] = o.lt1[k];
-							m.lt2[p] = o.lt2[k];
+							m.ln[p] = c1[k].w;
+							m.lt1[p] = c2[k].w;
+							m.lt2[p] = ol2[k];
 							break;
 						}
 				}
 			}
-			setup_manifold(m, bodies, h);  // ---- 7a: reads body state only
 		}
-		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour)
+		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour); active list
 		if (lane == 0)
 		{
 			unsigned long long *used = pmask;  // reuse: per-body colour sets
 			for (uint32_t k = 0; k < cap; k++) used[k] = 0ull;
 			int ncol = 0;
+			uint32_t nact = 0;
 			for (uint32_t mi = 0; mi < nman; mi++)
 			{
 				SMan &m = man[mi];
@@ -738,26 +840,84 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				if (a_dyn) used[m.a] |= 1ull << c;
 				if (b_dyn) used[m.b] |= 1ull << c;
 				if (c + 1 > ncol) ncol = c + 1;
+				act[nact++] = mi;
 			}
 			hdr[2] = (uint32_t)ncol;
+			hdr[5] = nact;
 		}
 		tile.sync();
 		const int ncol = (int)hdr[2];
+		const uint32_t nact = hdr[5];
 
-		// ---- 7b: warm start, then velocity iterations; within a colour no two manifolds share a dynamic body
-		for (int c = 0; c < ncol; c++)
+		// ---- 7: set-up, warm start, velocity iterations; within a colour no two manifolds share a dynamic body
+		if (nact <= (uint32_t)TILE)
 		{
-			for (uint32_t mi = lane; mi < nman; mi += TILE)
-				if (man[mi].colour == c) warm_start(man[mi], bodies);
-			tile.sync();
-		}
-		for (uint32_t it = 0; it < a.p.vel_steps; it++)
-			for (int c = 0; c < ncol; c++)
+			// every active manifold has its own lane: rows stay in registers across all iterations
+			const bool mine = (uint32_t)lane < nact;
+			SMan &m = man[mine ? act[lane] : 0];
+			Con c;
+			int colour = -1;
+			if (mine)
 			{
-				for (uint32_t mi = lane; mi < nman; mi += TILE)
-					if (man[mi].colour == c) solve_velocity(man[mi], bodies);
+				build_con<true>(c, m, bodies, h);
+				colour = m.colour;
+			}
+			for (int col = 0; col < ncol; col++)
+			{
+				if (colour == col)
+				{
+					Vel u;
+					load_vel(c, bodies, u);
+					warm_start(c, u);
+					store_vel(c, bodies, u);
+				}
 				tile.sync();
 			}
+			for (uint32_t it = 0; it < a.p.vel_steps; it++)
+				for (int col = 0; col < ncol; col++)
+				{
+					if (colour == col)
+					{
+						Vel u;
+						load_vel(c, bodies, u);
+						solve_velocity(c, u);
+						store_vel(c, bodies, u);
+					}
+					tile.sync();
+				}
+			if (mine) store_lambdas(c, m);
+		}
+		else
+		{
+			// more manifolds than lanes: rows are rebuilt from the shared records each time a lane revisits one
+			for (uint32_t k = lane; k < nact; k += TILE)
+			{
+				Con c;
+				build_con<true>(c, man[act[k]], bodies, h);
+			}
+			tile.sync();
+			for (uint32_t it = 0; it <= a.p.vel_steps; it++)
+				for (int col = 0; col < ncol; col++)
+				{
+					for (uint32_t k = lane; k < nact; k += TILE)
+					{
+						SMan &m = man[act[k]];
+						if (m.colour != col) continue;
+						Con c;
+						build_con<false>(c, m, bodies, h);
+						Vel u;
+						load_vel(c, bodies, u);
+						if (it == 0)
+							warm_start(c, u);
+						else
+							solve_velocity(c, u);
+						store_vel(c, bodies, u);
+						store_lambdas(c, m);
+					}
+					tile.sync();
+				}
+		}
+		tile.sync();
 
 		// ---- 8: integrate
 		for (uint32_t i = lane; i < cap; i += TILE)
@@ -773,35 +933,26 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		for (uint32_t it = 0; it < a.p.pos_steps; it++)
 			for (int c = 0; c < ncol; c++)
 			{
-				for (uint32_t mi = lane; mi < nman; mi += TILE)
-					if (man[mi].colour == c) solve_position(man[mi], bodies);
+				for (uint32_t k = lane; k < nact; k += TILE)
+					if (man[act[k]].colour == c) solve_position(man[act[k]], bodies);
 				tile.sync();
 			}
 
 		// ---- this sub-step's manifolds become the warm-start cache (compacted, canonical order kept)
-		if (lane == 0)
+		for (uint32_t k = lane; k < nact; k += TILE)
 		{
-			uint32_t k = 0;
-			for (uint32_t mi = 0; mi < nman; mi++)
-				if (man[mi].np > 0) man[mi].colour = (int)k++;
-			hdr[1] = k;
-		}
-		tile.sync();
-		for (uint32_t mi = lane; mi < nman; mi += TILE)
-		{
-			const SMan &m = man[mi];
-			if (m.np == 0) continue;
-			SPrev &o = prev[m.colour];
-			o.a = m.a; o.b = m.b; o.np = (uint32_t)m.np;
-			for (int k = 0; k < 4; k++)
+			const SMan &m = man[act[k]];
+			__stcg(&a.mc.key[m0 + k], make_uint4(m.a, m.b, (uint32_t)m.np, 0u));
+			__stcg(&a.mc.lt2[m0 + k], make_float4(m.lt2[0], m.lt2[1], m.lt2[2], m.lt2[3]));
+#pragma unroll
+			for (int p = 0; p < 4; p++)
 			{
-				o.p1l[k] = m.p1l[k];
-				o.p2l[k] = m.p2l[k];
-				o.ln[k] = m.ln[k];
-				o.lt1[k] = m.lt1[k];
-				o.lt2[k] = m.lt2[k];
+				__stcg(&a.mc.p1[4 * (m0 + k) + p], F4(m.p1l[p], m.ln[p]));
+				__stcg(&a.mc.p2[4 * (m0 + k) + p], F4(m.p2l[p], m.lt1[p]));
 			}
 		}
+		if (lane == 0) hdr[1] = nact;
+		__threadfence_block();
 		tile.sync();
 	}
 
@@ -815,22 +966,9 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		a.bs.lin[g0 + i] = F4(b.v, 0.0f);
 		a.bs.ang[g0 + i] = F4(b.w, 0.0f);
 	}
-	const uint32_t nprev = hdr[1];
-	for (uint32_t i = lane; i < nprev; i += TILE)
-	{
-		const SPrev &o = prev[i];
-		a.mc.key[m0 + i] = make_uint4(o.a, o.b, o.np, 0u);
-		a.mc.lt2[m0 + i] = make_float4(o.lt2[0], o.lt2[1], o.lt2[2], o.lt2[3]);
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-		{
-			a.mc.p1[4 * (m0 + i) + k] = F4(o.p1l[k], o.ln[k]);
-			a.mc.p2[4 * (m0 + i) + k] = F4(o.p2l[k], o.lt1[k]);
-		}
-	}
 	if (lane == 0)
 	{
-		a.mc.count[world] = nprev;
+		a.mc.count[world] = hdr[1];
 		if (hdr[3])
 		{
 			a.err[1 + world] |= hdr[3];
@@ -912,18 +1050,19 @@ __global__ void k_stats(BodyStore bs, ManifoldCache mc, const uint32_t *err, uin
 template <int TILE>
 static int launch_tick_t(gpx_world *w, const TickArgs &a)
 {
-	// worlds per block: as many tiles as fit in 128 threads and in the shared-memory budget
+	// one warp per block (32 / TILE worlds): the finest granularity for spreading 4096 worlds over 148 SMs in ONE wave
 	const size_t per_world = world_smem_bytes(w->cap, w->cap_m);
 	const size_t budget = 200u * 1024u;
 	if (per_world > budget) return GPX_ERR_CAPACITY;
-	uint32_t wpb = 128 / TILE;
-	while (wpb > 1 && per_world * wpb > budget / 2) wpb >>= 1;  // leave room for two blocks per SM
+	uint32_t wpb = 32 / TILE;
+	while (wpb > 1 && per_world * wpb > budget) wpb >>= 1;
 	const uint32_t threads = wpb * TILE;
 	const size_t smem = per_world * wpb;
 	static size_t configured = 0;
 	if (smem > configured)
 	{
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 		configured = smem;
 	}
 	const uint32_t grid = (w->W + wpb - 1) / wpb;
