@@ -177,6 +177,7 @@ def lib() -> C.CDLL:
         "gpx_timer_begin": (i32, [vp]),
         "gpx_timer_end": (f32, [vp]),
         "gpx_launch_count": (u64, []),
+        "gpx_debug_phase_cycles": (i32, [vp, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -353,6 +354,15 @@ class World:
         if ms < 0:
             raise GpxError(f"gpx_timer_end failed: {self.L.gpx_last_error().decode()}")
         return ms
+
+    PHASES = ("load", "forces", "static_narrow", "pair_narrow", "match", "colour", "setup", "warm_start", "velocity",
+              "integrate", "position", "cache", "store")
+
+    def phase_cycles(self, enable=True) -> dict:
+        """Read (and re-arm) the per-phase SM cycle counters of the tick kernel (profiling aid)."""
+        out = np.zeros(16, np.uint64)
+        _check(self.L.gpx_debug_phase_cycles(self.h, 1 if enable else 0, out.ctypes.data), "gpx_debug_phase_cycles")
+        return {k: int(v) for k, v in zip(self.PHASES, out)}
 
     def device_sync(self):
         _check(self.L.gpx_device_sync(self.h), "gpx_device_sync")

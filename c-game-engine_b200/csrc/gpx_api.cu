@@ -243,7 +243,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
 	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
-	cudaFree(w->d_rays); cudaFree(w->d_hits);
+	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase);
 	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
@@ -717,6 +717,22 @@ int gpx_device_sync(gpx_world *w)
 {
 	if (!w) return GPX_ERR_INVALID_ARG;
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+int gpx_debug_phase_cycles(gpx_world *w, int enable, uint64_t *out16)
+{
+	if (!w) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	if (w->d_phase && out16) GPX_CUDA(cudaMemcpy(out16, w->d_phase, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	if (enable && !w->d_phase) GPX_CUDA(cudaMalloc(&w->d_phase, 16 * sizeof(uint64_t)));
+	if (w->d_phase) GPX_CUDA(cudaMemset(w->d_phase, 0, 16 * sizeof(uint64_t)));
+	if (!enable && w->d_phase)
+	{
+		cudaFree(w->d_phase);
+		w->d_phase = nullptr;
+	}
 	return GPX_OK;
 }
 int gpx_timer_begin(gpx_world *w)

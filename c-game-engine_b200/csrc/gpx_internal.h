@@ -113,6 +113,7 @@ struct gpx_world
 	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors
 	uint32_t *m_err = nullptr;  // pinned
 	gpx_world_stats *d_stats = nullptr;
+	unsigned long long *d_phase = nullptr;  // 16 counters, allocated by gpx_debug_phase_cycles(enable)
 	uint32_t ticks = 0;
 
 	// ray staging

@@ -82,7 +82,31 @@ struct TickArgs
 	const float4 *tris;
 	uint32_t n_nodes;
 	uint32_t *err;  // [0] OR of all worlds' errors, [1 + world] per world
+	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
+};
+
+enum Phase { PH_LOAD, PH_FORCES, PH_STATIC, PH_PAIRS, PH_MATCH, PH_COLOUR, PH_SETUP, PH_WARM, PH_VELOCITY, PH_INTEGRATE,
+			 PH_POSITION, PH_CACHE, PH_STORE, PH_COUNT };
+
+struct PhaseClock
+{
+	unsigned long long *out;
+	long long t;
+	__device__ __forceinline__ void start(unsigned long long *o, int lane)
+	{
+		out = lane == 0 ? o : nullptr;
+		if (out) t = clock64();
+	}
+	__device__ __forceinline__ void mark(int phase)
+	{
+		if (out)
+		{
+			long long n = clock64();
+			atomicAdd(&out[phase], (unsigned long long)(n - t));
+			t = n;
+		}
+	}
 };
 
 __host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
@@ -513,6 +537,8 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	uint32_t *slot_base = cnt_static + cap;
 	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
 
+	PhaseClock pc;
+	pc.start(a.phase_cycles, lane);
 	const uint32_t g0 = world * cap;
 	// ---- load: HBM -> shared, lane = body, 16-byte vector loads
 	for (uint32_t i = lane; i < cap; i += TILE)
@@ -541,6 +567,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		hdr[3] = 0;
 	}
 	tile.sync();
+	pc.mark(PH_LOAD);
 
 	const float h = a.p.h;
 	const v3 gravity = V(a.p.gx, a.p.gy, a.p.gz);
@@ -580,6 +607,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			body_aabb(b);
 		}
 		tile.sync();
+		pc.mark(PH_FORCES);
 
 		// ---- 2 + 3: per body: contacts with the static map (kept in registers/local until slots are known) and the
 		// mask of higher-numbered bodies whose boxes overlap
@@ -727,6 +755,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			}
 		}
 		tile.sync();
+		pc.mark(PH_STATIC);
 
 		// ---- 4: body-body contact manifolds, one lane per candidate pair
 		const uint32_t npairs = hdr[4];
@@ -778,6 +807,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			store_points(m, A, &B, hit.np, hit.p1, hit.p2);
 		}
 		tile.sync();
+		pc.mark(PH_PAIRS);
 
 		// ---- 5: carry impulses from the previous sub-step's manifolds (keys in shared memory, records in L2)
 		const uint32_t nman = hdr[0], nprev = hdr[1];
@@ -814,6 +844,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				}
 			}
 		}
+		pc.mark(PH_MATCH);
 		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour); active list
 		if (lane == 0)
 		{
@@ -848,6 +879,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		tile.sync();
 		const int ncol = (int)hdr[2];
 		const uint32_t nact = hdr[5];
+		pc.mark(PH_COLOUR);
 
 		// ---- 7: set-up, warm start, velocity iterations; within a colour no two manifolds share a dynamic body
 		if (nact <= (uint32_t)TILE)
@@ -862,6 +894,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				build_con<true>(c, m, bodies, h);
 				colour = m.colour;
 			}
+			pc.mark(PH_SETUP);
 			for (int col = 0; col < ncol; col++)
 			{
 				if (colour == col)
@@ -873,6 +906,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				}
 				tile.sync();
 			}
+			pc.mark(PH_WARM);
 			for (uint32_t it = 0; it < a.p.vel_steps; it++)
 				for (int col = 0; col < ncol; col++)
 				{
@@ -918,6 +952,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				}
 		}
 		tile.sync();
+		pc.mark(PH_VELOCITY);
 
 		// ---- 8: integrate
 		for (uint32_t i = lane; i < cap; i += TILE)
@@ -928,6 +963,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			b.q = qstep(b.q, b.w * h);
 		}
 		tile.sync();
+		pc.mark(PH_INTEGRATE);
 
 		// ---- 9: position iterations
 		for (uint32_t it = 0; it < a.p.pos_steps; it++)
@@ -938,6 +974,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				tile.sync();
 			}
 
+		pc.mark(PH_POSITION);
 		// ---- this sub-step's manifolds become the warm-start cache (compacted, canonical order kept)
 		for (uint32_t k = lane; k < nact; k += TILE)
 		{
@@ -954,6 +991,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		if (lane == 0) hdr[1] = nact;
 		__threadfence_block();
 		tile.sync();
+		pc.mark(PH_CACHE);
 	}
 
 	// ---- store: shared -> HBM
@@ -975,6 +1013,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			atomicOr(&a.err[0], hdr[3]);
 		}
 	}
+	pc.mark(PH_STORE);
 }
 
 __global__ void k_apply_commands(BodyStore bs, const BodyCommand *__restrict__ cmd, uint32_t n)
@@ -1081,6 +1120,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.tris = w->sd.tri;
 	a.n_nodes = w->sd.n_nodes;
 	a.err = w->d_err;
+	a.phase_cycles = w->d_phase;
 	a.p.worlds = w->W;
 	a.p.cap = w->cap;
 	a.p.cap_m = w->cap_m;

@@ -243,6 +243,11 @@ int gpx_timer_begin(gpx_world *w);
 float gpx_timer_end(gpx_world *w);
 /* Number of kernels this library launched since gpx_init (for bench.py's gpu_launches). */
 uint64_t gpx_launch_count(void);
+/* Profiling aid: SM cycles spent per tick phase, summed over every world's lane 0 since the last call
+ * (enable != 0 arms the counters; out16 may be NULL).  Order: load, forces, static narrowphase, pair narrowphase,
+ * warm-start match, colouring, constraint set-up, warm start, velocity iterations, integrate, position iterations,
+ * cache write, store. */
+int gpx_debug_phase_cycles(gpx_world *w, int enable, uint64_t *out16);
 /* Static LBVH introspection for tests: node count and triangle count after commit. */
 int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *n_bodies);
 
