@@ -212,6 +212,9 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK;
 	ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
 		 dalloc(&w->mc.lt2, nm) == GPX_OK && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
+	ok = ok && dalloc(&w->d_park, nm * 9) == GPX_OK;
+	ok = ok && cudaMalloc(&w->d_cand, sizeof(uint4) * 8 * nb) == cudaSuccess &&
+		 cudaMemset(w->d_cand, 0xFF, sizeof(uint4) * 8 * nb) == cudaSuccess;
 	ok = ok && dalloc(&w->d_err, (size_t)w->W + 1) == GPX_OK && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
 	ok = ok && cudaMallocHost(&w->m_pos, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_quat, sizeof(float4) * nb) == cudaSuccess &&
@@ -243,7 +246,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
 	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
-	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase);
+	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);

@@ -268,6 +268,8 @@ int build_static(gpx_world *w)
 	sd.n_tris = n;
 	sd.n_nodes = n == 0 ? 0 : (n > 1 ? n - 1 : 1);
 	w->static_dirty = false;
+	// leaf indices change with every rebuild: forget the per-body candidate lists
+	if (w->d_cand) GPX_CUDA(cudaMemsetAsync(w->d_cand, 0xFF, sizeof(uint4) * 8 * (size_t)w->W * w->cap, w->stream));
 	if (n == 0) return GPX_OK;
 
 	// scene bounds on the host (it already walks every vertex while appending)

@@ -113,6 +113,8 @@ struct gpx_world
 	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors
 	uint32_t *m_err = nullptr;  // pinned
 	gpx_world_stats *d_stats = nullptr;
+	float4 *d_park = nullptr;  // 9 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
+	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)
 	unsigned long long *d_phase = nullptr;  // 16 counters, allocated by gpx_debug_phase_cycles(enable)
 	uint32_t ticks = 0;
 

@@ -20,18 +20,32 @@ constexpr float NORMAL_COS_MAX_DELTA = 0.99619470f;  // cos 5 deg
 constexpr float PRESERVE_LAMBDA_MAX_DIST_SQ = 1.0e-4f;
 constexpr float FACE_AXIS_TOL = 1.0e-4f;
 constexpr float EDGE_AXIS_TOL = 2.0e-3f;
-constexpr int MAX_POLY = 16;
+constexpr int MAX_POLY = 8;   // a quad or triangle clipped by four planes has at most 8 vertices
 constexpr int MAX_SLOTS = 4;                 // manifolds per (body, static body) pair
 constexpr int MAX_STATIC_PER_BODY = 8;       // manifolds per body against all static geometry
 constexpr int MAX_TRI_CANDIDATES = 24;       // triangles whose box overlaps one body's box
+
+// Per-lane polygon scratch (shared memory in the tick kernel): two ping-pong buffers for face clipping; afterwards
+// they hold the contact points on a (buf[0]) and on b (buf[1]).  Thread-local arrays would live in local memory and
+// every clip step would pay an L1/L2 round trip.
+struct Scratch
+{
+	v3 buf[2][MAX_POLY];
+};
 
 struct Hit
 {
 	v3 n;         // from a to b
 	float depth;  // -separation along n
 	int np;
-	v3 p1[MAX_POLY], p2[MAX_POLY];  // world points on a and on b
+	v3 *p1, *p2;  // world points on a and on b (in the caller's Scratch)
 };
+
+__device__ __forceinline__ void hit_bind(Hit &h, Scratch &s)
+{
+	h.p1 = s.buf[0];
+	h.p2 = s.buf[1];
+}
 
 struct Box
 {
@@ -106,36 +120,48 @@ __device__ __forceinline__ int clip_plane(const v3 *in, int n, v3 origin, v3 nor
 }
 
 // Clip face2 by the side planes of face1 (through face1's edges, parallel to axis); keep points within max_sep of
-// face1's plane and project them onto it.
-__device__ __forceinline__ void manifold_between_faces(const v3 *f1, int n1v, v3 n1, const v3 *f2, int n2v, v3 axis,
-													   float max_sep, Hit &h)
+// face1's plane and project them onto it.  N1, N2: vertex counts (compile time, so the faces stay in registers).
+template <int N1, int N2>
+__device__ __forceinline__ void manifold_between_faces(const v3 *f1, v3 n1, const v3 *f2, v3 axis, float max_sep,
+														   Scratch &sc, Hit &h)
 {
-	v3 bufa[MAX_POLY], bufb[MAX_POLY];
-	v3 *src = bufa, *dst = bufb;
-	int n = n2v;
-	for (int i = 0; i < n2v; i++) src[i] = f2[i];
+	v3 *src = sc.buf[0], *dst = sc.buf[1];
+	int n = N2;
+#pragma unroll
+	for (int i = 0; i < N2; i++) src[i] = f2[i];
 	v3 cen = f1[0];
-	for (int i = 1; i < n1v; i++) cen = cen + f1[i];
-	cen = cen * (1.0f / (float)n1v);
-	for (int i = 0; i < n1v && n > 0; i++)
+#pragma unroll
+	for (int i = 1; i < N1; i++) cen = cen + f1[i];
+	cen = cen * (1.0f / (float)N1);
+#pragma unroll
+	for (int i = 0; i < N1; i++)
 	{
-		v3 a = f1[i], b = f1[(i + 1) % n1v];
-		v3 pn = cross(axis, b - a);
-		if (dot(cen - a, pn) < 0.0f) pn = -pn;
-		n = clip_plane(src, n, a, pn, dst);
-		v3 *t = src; src = dst; dst = t;
-	}
-	h.np = 0;
-	for (int i = 0; i < n; i++)
-	{
-		float dist = dot(src[i] - f1[0], n1);
-		if (dist <= max_sep)
+		if (n > 0)
 		{
-			h.p2[h.np] = src[i];
-			h.p1[h.np] = src[i] - (n1 * dist);
-			h.np++;
+			v3 a = f1[i], b = f1[(i + 1) % N1];
+			v3 pn = cross(axis, b - a);
+			if (dot(cen - a, pn) < 0.0f) pn = -pn;
+			n = clip_plane(src, n, a, pn, dst);
+			v3 *t = src; src = dst; dst = t;
 		}
 	}
+	// contact points: on b = the clipped vertex, on a = its projection onto face1's plane.  Points on b are compacted
+	// in place; points on a go to the other buffer, which clipping no longer needs.
+	int np = 0;
+	for (int i = 0; i < n; i++)
+	{
+		v3 p = src[i];
+		float dist = dot(p - f1[0], n1);
+		if (dist <= max_sep)
+		{
+			src[np] = p;
+			dst[np] = p - (n1 * dist);
+			np++;
+		}
+	}
+	h.np = np;
+	h.p2 = src;
+	h.p1 = dst;
 }
 
 // closest points of segments p1 + s d1 (|s| <= h1) and p2 + t d2 (|t| <= h2); unit directions
@@ -160,7 +186,7 @@ __device__ __forceinline__ void closest_on_edges(v3 p1, v3 d1, float h1, v3 p2, 
 	c2 = p2 + (d2 * t);
 }
 
-__device__ __noinline__ bool collide_box_box(const Box &A, const Box &B, float max_sep, Hit &h)
+__device__ __noinline__ bool collide_box_box(const Box &A, const Box &B, float max_sep, Scratch &sc, Hit &h)
 {
 	v3 d = B.x - A.x;
 	float best = -3.0e38f;
@@ -216,7 +242,7 @@ __device__ __noinline__ bool collide_box_box(const Box &A, const Box &B, float m
 	v3 fa[4], fb[4], na, nb;
 	box_face(A, bn, fa, na);
 	box_face(B, -bn, fb, nb);
-	manifold_between_faces(fa, 4, na, fb, 4, bn, max_sep, h);
+	manifold_between_faces<4, 4>(fa, na, fb, bn, max_sep, sc, h);
 	if (h.np == 0)
 	{
 		if (kind == 2)
@@ -249,7 +275,7 @@ struct Tri
 	v3 a, b, c, n;
 };
 
-__device__ __noinline__ bool collide_box_tri(const Box &A, const Tri &T, float max_sep, Hit &h)
+__device__ __noinline__ bool collide_box_tri(const Box &A, const Tri &T, float max_sep, Scratch &sc, Hit &h)
 {
 	v3 tv[3] = {T.a, T.b, T.c};
 	float best;
@@ -309,7 +335,7 @@ __device__ __noinline__ bool collide_box_tri(const Box &A, const Tri &T, float m
 	h.depth = -best;
 	v3 fa[4], na;
 	box_face(A, bn, fa, na);
-	manifold_between_faces(fa, 4, na, tv, 3, bn, max_sep, h);
+	manifold_between_faces<4, 3>(fa, na, tv, bn, max_sep, sc, h);
 	if (h.np == 0)
 	{
 		if (kind == 2)
@@ -422,51 +448,56 @@ __device__ __forceinline__ bool collide_sphere_box(v3 sx, float r, const Box &X,
 }
 
 // Keep <= 4 points: the one with most leverage x depth, the farthest from it, and the extremes on both sides of
-// that segment (the reduction Jolt documents for PruneContactPoints).
+// that segment (the reduction Jolt documents for PruneContactPoints).  Projections are re-derived per pass instead of
+// being parked in thread-local arrays; p1/p2 may point at shared or local memory.
+__device__ __forceinline__ v3 prune_proj(v3 xa, v3 axis, v3 p1)
+{
+	v3 v1 = p1 - xa;
+	return v1 - (axis * dot(v1, axis));
+}
+__device__ __forceinline__ float prune_dsq(v3 p1, v3 p2) { return fmaxf(1.0e-6f, len2(p2 - p1)); }
+
 __device__ __forceinline__ void prune_points(v3 xa, v3 axis, int &np, v3 *p1, v3 *p2)
 {
-	int n = np;
+	const int n = np;
 	if (n <= 4) return;
-	v3 proj[MAX_POLY];
-	float dsq[MAX_POLY];
-	for (int i = 0; i < n; i++)
-	{
-		v3 v1 = p1[i] - xa;
-		proj[i] = v1 - (axis * dot(v1, axis));
-		dsq[i] = fmaxf(1.0e-6f, len2(p2[i] - p1[i]));
-	}
 	int i1 = 0;
 	float best = -1.0f;
 	for (int i = 0; i < n; i++)
 	{
-		float v = fmaxf(1.0e-6f, len2(proj[i])) * dsq[i];
+		v3 a = p1[i];
+		float v = fmaxf(1.0e-6f, len2(prune_proj(xa, axis, a))) * prune_dsq(a, p2[i]);
 		if (v > best) { best = v; i1 = i; }
 	}
+	const v3 proj1 = prune_proj(xa, axis, p1[i1]);
 	int i2 = -1;
 	best = -1.0f;
 	for (int i = 0; i < n; i++)
 		if (i != i1)
 		{
-			float v = fmaxf(1.0e-6f, len2(proj[i] - proj[i1])) * dsq[i];
+			v3 a = p1[i];
+			float v = fmaxf(1.0e-6f, len2(prune_proj(xa, axis, a) - proj1)) * prune_dsq(a, p2[i]);
 			if (v > best) { best = v; i2 = i; }
 		}
 	int i3 = -1, i4 = -1;
 	float mn = 0.0f, mx = 0.0f;
-	v3 perp = cross(proj[i2] - proj[i1], axis);
+	v3 perp = cross(prune_proj(xa, axis, p1[i2]) - proj1, axis);
 	for (int i = 0; i < n; i++)
 		if (i != i1 && i != i2)
 		{
-			float v = dot(perp, proj[i] - proj[i1]);
+			float v = dot(perp, prune_proj(xa, axis, p1[i]) - proj1);
 			if (v < mn) { mn = v; i3 = i; }
 			else if (v > mx) { mx = v; i4 = i; }
 		}
-	v3 o1[4], o2[4];
-	int m = 0;
-	o1[m] = p1[i1]; o2[m++] = p2[i1];
-	if (i3 >= 0) { o1[m] = p1[i3]; o2[m++] = p2[i3]; }
-	o1[m] = p1[i2]; o2[m++] = p2[i2];
-	if (i4 >= 0) { o1[m] = p1[i4]; o2[m++] = p2[i4]; }
-	for (int i = 0; i < m; i++) { p1[i] = o1[i]; p2[i] = o2[i]; }
+	// output order: i1, (i3), i2, (i4)
+	const int e0 = i1, e1 = i3 >= 0 ? i3 : i2, e2 = i3 >= 0 ? i2 : i4, e3 = i3 >= 0 ? i4 : -1;
+	const int m = (i3 >= 0 ? 3 : 2) + (i4 >= 0 ? 1 : 0);
+	const v3 a0 = p1[e0], b0 = p2[e0], a1 = p1[e1], b1 = p2[e1];
+	const v3 a2 = p1[e2 >= 0 ? e2 : 0], b2 = p2[e2 >= 0 ? e2 : 0], a3 = p1[e3 >= 0 ? e3 : 0], b3 = p2[e3 >= 0 ? e3 : 0];
+	p1[0] = a0; p2[0] = b0;
+	p1[1] = a1; p2[1] = b1;
+	if (m > 2) { p1[2] = a2; p2[2] = b2; }
+	if (m > 3) { p1[3] = a3; p2[3] = b3; }
 	np = m;
 }
 

@@ -23,6 +23,8 @@
 // and identical for any TILE width.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "gpx_internal.h"
 #include "gpx_narrow.cuh"
 
@@ -82,6 +84,8 @@ struct TickArgs
 	const float4 *tris;
 	uint32_t n_nodes;
 	uint32_t *err;  // [0] OR of all worlds' errors, [1 + world] per world
+	float4 *con_park;  // 9 float4 per manifold slot: parked solver constants of worlds with more manifolds than lanes
+	uint4 *cand;  // per body 8 x uint4: {count, -, -, -}, {fat lo xyz, -}, {fat hi xyz, -}... see cand_* below
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
 };
@@ -109,6 +113,15 @@ struct PhaseClock
 	}
 };
 
+// One Scratch per lane while contacts are generated; once they are, the same bytes hold the keys of the previous
+// sub-step's manifolds (a, b, np) and the list of active manifolds.
+__host__ __device__ inline uint32_t tile_width(uint32_t cap) { return cap <= 8 ? 8u : (cap <= 16 ? 16u : 32u); }
+__host__ __device__ inline size_t world_scratch_bytes(uint32_t cap, uint32_t cap_m)
+{
+	size_t a = sizeof(Scratch) * tile_width(cap), b = sizeof(uint32_t) * 4 * cap_m;
+	return a > b ? a : b;
+}
+
 __host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
 {
 	size_t b = 0;
@@ -116,8 +129,7 @@ __host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
 	b += sizeof(SBody) * cap;
 	b += sizeof(SMan) * cap_m;
 	b += sizeof(uint32_t) * 2 * cap_m;      // pair list (a | slot << 16, b)
-	b += sizeof(uint32_t) * 3 * cap_m;      // keys of the previous sub-step's manifolds (a, b, np)
-	b += sizeof(uint32_t) * cap_m;          // active manifolds in canonical order
+	b += world_scratch_bytes(cap, cap_m);   // narrowphase polygon scratch, later the cached keys + the active list
 	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
 	b += sizeof(uint32_t) * 8;              // header
 	return (b + 15) & ~(size_t)15;
@@ -256,6 +268,82 @@ __device__ __noinline__ int query_static(const float4 *__restrict__ nodes, const
 		}
 		if (sp == 0) break;
 		node = stack[--sp];
+	}
+	return nc;
+}
+
+// Candidate triangles of one body.  A box query of the LBVH costs a chain of dependent L2 round trips, and a body
+// that rests or creeps asks the same question every sub-step, so the answer is cached per body in global memory: the
+// leaves whose boxes touch a FAT box around the body.  While the body's query box stays inside the fat box the
+// candidates are re-derived from that list with the same exact leaf test the traversal applies, so the result (set
+// and order) is identical to a fresh query.  Layout per body: 8 x uint4 = {count | 0xFFFFFFFF, fat lo.xyz},
+// {fat hi.xyz, 0}, 6 x 4 leaf indices.
+constexpr float CAND_FAT = 0.05f;
+constexpr uint32_t CAND_INVALID = 0xFFFFFFFFu;
+
+__device__ __noinline__ int static_candidates(const TickArgs &a, uint32_t gbody, v3 lo, v3 hi, int *cand_orig, int *cand_leaf,
+											  bool &overflow)
+{
+	const float m = SPECULATIVE_DISTANCE;
+	if (a.n_nodes == 0) return 0;
+	uint4 *rec = a.cand + 8ull * gbody;
+	const uint4 h0 = __ldcg(&rec[0]), h1 = __ldcg(&rec[1]);
+	const v3 flo = V(__uint_as_float(h0.y), __uint_as_float(h0.z), __uint_as_float(h0.w));
+	const v3 fhi = V(__uint_as_float(h1.x), __uint_as_float(h1.y), __uint_as_float(h1.z));
+	const bool inside = h0.x != CAND_INVALID && (lo.x - m) >= flo.x && (lo.y - m) >= flo.y && (lo.z - m) >= flo.z &&
+						(hi.x + m) <= fhi.x && (hi.y + m) <= fhi.y && (hi.z + m) <= fhi.z;
+	if (!inside)
+	{
+		// refill: query the fat box; more leaves than the record holds -> leave it invalid and query exactly each time
+		const v3 qlo = V((lo.x - m) - CAND_FAT, (lo.y - m) - CAND_FAT, (lo.z - m) - CAND_FAT);
+		const v3 qhi = V((hi.x + m) + CAND_FAT, (hi.y + m) + CAND_FAT, (hi.z + m) + CAND_FAT);
+		bool fat_overflow = false;
+		const int nf = query_static(a.nodes, a.tris, a.n_nodes, qlo, qhi, 0.0f, cand_orig, cand_leaf, fat_overflow);
+		if (fat_overflow)
+		{
+			__stcg(&rec[0], make_uint4(CAND_INVALID, 0u, 0u, 0u));
+			return query_static(a.nodes, a.tris, a.n_nodes, lo, hi, m, cand_orig, cand_leaf, overflow);
+		}
+		__stcg(&rec[0], make_uint4((uint32_t)nf, __float_as_uint(qlo.x), __float_as_uint(qlo.y), __float_as_uint(qlo.z)));
+		__stcg(&rec[1], make_uint4(__float_as_uint(qhi.x), __float_as_uint(qhi.y), __float_as_uint(qhi.z), 0u));
+		for (int c = 0; c < nf; c += 4)
+			__stcg(&rec[2 + c / 4], make_uint4((uint32_t)cand_leaf[c], c + 1 < nf ? (uint32_t)cand_leaf[c + 1] : 0u,
+											   c + 2 < nf ? (uint32_t)cand_leaf[c + 2] : 0u,
+											   c + 3 < nf ? (uint32_t)cand_leaf[c + 3] : 0u));
+		// fall through: filter the fresh list exactly like a cached one (it is already in registers/local)
+		int nc = 0;
+		for (int c = 0; c < nf; c++)
+		{
+			const int leaf = cand_leaf[c];
+			const float4 A = __ldg(&a.tris[4 * leaf + 0]), B = __ldg(&a.tris[4 * leaf + 1]), C = __ldg(&a.tris[4 * leaf + 2]);
+			v3 tlo = V(fminf(A.x, fminf(B.x, C.x)), fminf(A.y, fminf(B.y, C.y)), fminf(A.z, fminf(B.z, C.z)));
+			v3 thi = V(fmaxf(A.x, fmaxf(B.x, C.x)), fmaxf(A.y, fmaxf(B.y, C.y)), fmaxf(A.z, fmaxf(B.z, C.z)));
+			if (!aabb_overlap(lo, hi, tlo, thi, m)) continue;
+			cand_orig[nc] = cand_orig[c];
+			cand_leaf[nc] = leaf;
+			nc++;
+		}
+		return nc;
+	}
+	const int nf = (int)h0.x;
+	int nc = 0;
+	for (int c0 = 0; c0 < nf; c0 += 4)
+	{
+		const uint4 ids = __ldcg(&rec[2 + c0 / 4]);
+		const uint32_t id4[4] = {ids.x, ids.y, ids.z, ids.w};
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			if (c0 + k >= nf) break;
+			const int leaf = (int)id4[k];
+			const float4 A = __ldg(&a.tris[4 * leaf + 0]), B = __ldg(&a.tris[4 * leaf + 1]), C = __ldg(&a.tris[4 * leaf + 2]);
+			v3 tlo = V(fminf(A.x, fminf(B.x, C.x)), fminf(A.y, fminf(B.y, C.y)), fminf(A.z, fminf(B.z, C.z)));
+			v3 thi = V(fmaxf(A.x, fmaxf(B.x, C.x)), fmaxf(A.y, fmaxf(B.y, C.y)), fmaxf(A.z, fmaxf(B.z, C.z)));
+			if (!aabb_overlap(lo, hi, tlo, thi, m)) continue;
+			cand_orig[nc] = (int)__float_as_uint(A.w);
+			cand_leaf[nc] = leaf;
+			nc++;
+		}
 	}
 	return nc;
 }
@@ -406,6 +494,65 @@ __device__ __forceinline__ void store_lambdas(const Con &c, SMan &m)
 		}
 }
 
+// r1, r2, em of the four points <-> 9 float4 in global memory (worlds with more manifolds than lanes)
+__device__ __forceinline__ void park_con(const Con &c, float4 *g)
+{
+	float f[36];
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		f[9 * k + 0] = c.r1[k].x; f[9 * k + 1] = c.r1[k].y; f[9 * k + 2] = c.r1[k].z;
+		f[9 * k + 3] = c.r2[k].x; f[9 * k + 4] = c.r2[k].y; f[9 * k + 5] = c.r2[k].z;
+		f[9 * k + 6] = c.em[k][0]; f[9 * k + 7] = c.em[k][1]; f[9 * k + 8] = c.em[k][2];
+	}
+#pragma unroll
+	for (int i = 0; i < 9; i++) __stcg(&g[i], make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
+}
+
+__device__ __forceinline__ void unpark_con(Con &c, const SMan &m, const SBody *bodies, const float4 *g)
+{
+	float f[36];
+#pragma unroll
+	for (int i = 0; i < 9; i++)
+	{
+		const float4 v = __ldcg(&g[i]);
+		f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+	}
+	const SBody &A = bodies[m.a];
+	c.ia = m.a;
+	c.has_b = m.b < STATIC_BODY_BASE;
+	c.ib = c.has_b ? m.b : m.a;
+	const SBody &B = bodies[c.ib];
+	c.a_dyn = is_dynamic(A.flags);
+	c.b_dyn = c.has_b && is_dynamic(B.flags);
+	c.a_dofs = dofs_of(A.flags);
+	c.b_dofs = dofs_of(B.flags);
+	c.ima = A.im;
+	c.imb = c.has_b ? B.im : 0.0f;
+#pragma unroll
+	for (int k = 0; k < 6; k++)
+	{
+		c.MA[k] = A.M[k];
+		c.MB[k] = c.has_b ? B.M[k] : 0.0f;
+	}
+	c.np = m.np;
+	c.friction = m.friction;
+	c.n = m.n;
+	c.t1 = vperp(c.n);
+	c.t2 = cross(c.n, c.t1);
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		c.r1[k] = V(f[9 * k + 0], f[9 * k + 1], f[9 * k + 2]);
+		c.r2[k] = V(f[9 * k + 3], f[9 * k + 4], f[9 * k + 5]);
+		c.em[k][0] = f[9 * k + 6]; c.em[k][1] = f[9 * k + 7]; c.em[k][2] = f[9 * k + 8];
+		c.bias[k] = m.bias[k];
+		c.ln[k] = m.ln[k];
+		c.lt1[k] = m.lt1[k];
+		c.lt2[k] = m.lt2[k];
+	}
+}
+
 __device__ __forceinline__ void warm_start(const Con &c, Vel &u)
 {
 #pragma unroll
@@ -503,6 +650,63 @@ __device__ __forceinline__ void store_points(SMan &m, const SBody &A, const SBod
 	for (int i = 0; i < 4; i++) m.ln[i] = m.lt1[i] = m.lt2[i] = 0.0f;
 }
 
+// Velocity solve with every active manifold of the world in a register slot of some lane (K per lane): set-up once,
+// warm start, then the iterations; per colour a lane pulls its bodies' velocities from shared memory, runs its rows and
+// pushes them back.
+template <int TILE, int K, typename Tile>
+__device__ __forceinline__ void solve_in_registers(Tile &tile, int lane, SMan *man, const uint32_t *act, uint32_t nact,
+												   SBody *bodies, int ncol, uint32_t vel_steps, float h, PhaseClock &pc)
+{
+	Con c[K];
+	int colour[K];
+	uint32_t slot[K];
+#pragma unroll
+	for (int s = 0; s < K; s++)
+	{
+		const uint32_t k = (uint32_t)s * TILE + lane;
+		colour[s] = -1;
+		slot[s] = 0;
+		if (k < nact)
+		{
+			slot[s] = act[k];
+			build_con<true>(c[s], man[slot[s]], bodies, h);
+			colour[s] = man[slot[s]].colour;
+		}
+	}
+	pc.mark(PH_SETUP);
+	for (int col = 0; col < ncol; col++)
+	{
+#pragma unroll
+		for (int s = 0; s < K; s++)
+			if (colour[s] == col)
+			{
+				Vel u;
+				load_vel(c[s], bodies, u);
+				warm_start(c[s], u);
+				store_vel(c[s], bodies, u);
+			}
+		tile.sync();
+	}
+	pc.mark(PH_WARM);
+	for (uint32_t it = 0; it < vel_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+#pragma unroll
+			for (int s = 0; s < K; s++)
+				if (colour[s] == col)
+				{
+					Vel u;
+					load_vel(c[s], bodies, u);
+					solve_velocity(c[s], u);
+					store_vel(c[s], bodies, u);
+				}
+			tile.sync();
+		}
+#pragma unroll
+	for (int s = 0; s < K; s++)
+		if (colour[s] >= 0) store_lambdas(c[s], man[slot[s]]);
+}
+
 struct StaticSlot
 {
 	v3 n;
@@ -529,11 +733,13 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	SMan *man = reinterpret_cast<SMan *>(bodies + cap);
 	uint32_t *pair_a = reinterpret_cast<uint32_t *>(man + cap_m);
 	uint32_t *pair_b = pair_a + cap_m;
-	uint32_t *pkey_a = pair_b + cap_m;
+	unsigned char *scratch_raw = reinterpret_cast<unsigned char *>(pair_b + cap_m);
+	Scratch &scratch = reinterpret_cast<Scratch *>(scratch_raw)[lane];
+	uint32_t *pkey_a = reinterpret_cast<uint32_t *>(scratch_raw);  // aliases the scratch: live from phase 5 on
 	uint32_t *pkey_b = pkey_a + cap_m;
 	uint32_t *pkey_np = pkey_b + cap_m;
 	uint32_t *act = pkey_np + cap_m;
-	uint32_t *cnt_static = act + cap_m;
+	uint32_t *cnt_static = reinterpret_cast<uint32_t *>(scratch_raw + world_scratch_bytes(cap, cap_m));
 	uint32_t *slot_base = cnt_static + cap;
 	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
 
@@ -574,17 +780,6 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 	for (int sub = 0; sub < a.p.substeps; sub++)
 	{
-		// ---- 0: keys of the cached manifolds (global -> shared; the records themselves stay in L2)
-		{
-			const uint32_t nprev = hdr[1];
-			for (uint32_t i = lane; i < nprev; i += TILE)
-			{
-				const uint4 k = __ldcg(&a.mc.key[m0 + i]);
-				pkey_a[i] = k.x;
-				pkey_b[i] = k.y;
-				pkey_np[i] = k.z;
-			}
-		}
 		// ---- 1: forces, inertia, bounds
 		for (uint32_t i = lane; i < cap; i += TILE)
 		{
@@ -627,8 +822,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				{
 					int cand_orig[MAX_TRI_CANDIDATES], cand_leaf[MAX_TRI_CANDIDATES];
 					bool overflow = false;
-					const int nc = query_static(a.nodes, a.tris, a.n_nodes, A.lo, A.hi, SPECULATIVE_DISTANCE, cand_orig,
-												cand_leaf, overflow);
+					const int nc = static_candidates(a, g0 + i, A.lo, A.hi, cand_orig, cand_leaf, overflow);
 					if (overflow) err |= GPX_ERR_BODY_PAIR_CACHE_FULL;
 					Box bx;
 					bx.x = A.x;
@@ -650,7 +844,8 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 						Tri T;
 						T.a = V(TA); T.b = V(TB); T.c = V(TC); T.n = V(TN);
 						Hit hit;
-						bool ok = shape_of(fa) == GPX_SHAPE_BOX ? collide_box_tri(bx, T, SPECULATIVE_DISTANCE, hit)
+						hit_bind(hit, scratch);
+						bool ok = shape_of(fa) == GPX_SHAPE_BOX ? collide_box_tri(bx, T, SPECULATIVE_DISTANCE, scratch, hit)
 																: collide_sphere_tri(A.x, A.he.x, T, SPECULATIVE_DISTANCE, hit);
 						if (!ok) continue;
 						prune_points(A.x, hit.n, hit.np, hit.p1, hit.p2);
@@ -769,6 +964,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			m.b = ib;
 			m.np = 0;
 			Hit hit;
+			hit_bind(hit, scratch);
 			bool ok;
 			const uint32_t sa = shape_of(A.flags), sb = shape_of(B.flags);
 			if (sa == GPX_SHAPE_BOX && sb == GPX_SHAPE_BOX)
@@ -776,7 +972,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				Box ba, bb;
 				ba.x = A.x; ba.R = qmat(A.q); ba.he = A.he;
 				bb.x = B.x; bb.R = qmat(B.q); bb.he = B.he;
-				ok = collide_box_box(ba, bb, SPECULATIVE_DISTANCE, hit);
+				ok = collide_box_box(ba, bb, SPECULATIVE_DISTANCE, scratch, hit);
 			}
 			else if (sa == GPX_SHAPE_SPHERE && sb == GPX_SHAPE_SPHERE)
 				ok = collide_sphere_sphere(A.x, A.he.x, B.x, B.he.x, SPECULATIVE_DISTANCE, hit);
@@ -811,13 +1007,30 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 		// ---- 5: carry impulses from the previous sub-step's manifolds (keys in shared memory, records in L2)
 		const uint32_t nman = hdr[0], nprev = hdr[1];
-		for (uint32_t mi = lane; mi < nman; mi += TILE)
+		for (uint32_t i = lane; i < nprev; i += TILE)
 		{
-			SMan &m = man[mi];
-			if (m.np == 0) continue;
+			const uint4 k = __ldcg(&a.mc.key[m0 + i]);
+			pkey_a[i] = k.x;
+			pkey_b[i] = k.y;
+			pkey_np[i] = k.z;
+		}
+		tile.sync();
+		for (uint32_t mi0 = 0; mi0 < nman; mi0 += TILE)
+		{
+			// stage 1 (shared memory only, no early exits): first cached record with this manifold's key, and how many
+			const uint32_t mi = mi0 + lane;
+			SMan &m = man[mi < nman ? mi : 0];
+			const bool live = mi < nman && m.np > 0;
+			int j0 = -1, nmatch = 0;
 			for (uint32_t j = 0; j < nprev; j++)
 			{
-				if (pkey_a[j] != m.a || pkey_b[j] != m.b) continue;
+				const bool hit = live && pkey_a[j] == m.a && pkey_b[j] == m.b;
+				if (hit && j0 < 0) j0 = (int)j;
+				nmatch += hit ? 1 : 0;
+			}
+			// stage 2: every lane with a match pulls its record at once (one overlapped batch of L2 reads per tile)
+			for (int j = j0; j >= 0 && nmatch > 0; )
+			{
 				const uint32_t onp = pkey_np[j];
 				const float4 l2 = __ldcg(&a.mc.lt2[m0 + j]);
 				const float ol2[4] = {l2.x, l2.y, l2.z, l2.w};
@@ -828,20 +1041,38 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 					c1[k] = __ldcg(&a.mc.p1[4 * (m0 + j) + k]);
 					c2[k] = __ldcg(&a.mc.p2[4 * (m0 + j) + k]);
 				}
-				for (int p = 0; p < m.np; p++)
+#pragma unroll
+				for (int p = 0; p < 4; p++)
 				{
+					if (p >= m.np) continue;
 					if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
+					const v3 a1 = m.p1l[p], a2 = m.p2l[p];
+					bool done = false;
 #pragma unroll
 					for (int k = 0; k < 4; k++)
-						if ((uint32_t)k < onp && len2(m.p1l[p] - V(c1[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
-							len2(m.p2l[p] - V(c2[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ)
+					{
+						const bool ok = !done && (uint32_t)k < onp && len2(a1 - V(c1[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
+										len2(a2 - V(c2[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ;
+						if (ok)
 						{
 							m.ln[p] = c1[k].w;
 							m.lt1[p] = c2[k].w;
 							m.lt2[p] = ol2[k];
+							done = true;
+						}
+					}
+				}
+				// further records with the same key (several manifolds of one body against one static body): rare
+				nmatch--;
+				int jn = -1;
+				if (nmatch > 0)
+					for (uint32_t jj = (uint32_t)j + 1; jj < nprev; jj++)
+						if (pkey_a[jj] == m.a && pkey_b[jj] == m.b)
+						{
+							jn = (int)jj;
 							break;
 						}
-				}
+				j = jn;
 			}
 		}
 		pc.mark(PH_MATCH);
@@ -883,52 +1114,19 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 		// ---- 7: set-up, warm start, velocity iterations; within a colour no two manifolds share a dynamic body
 		if (nact <= (uint32_t)TILE)
-		{
-			// every active manifold has its own lane: rows stay in registers across all iterations
-			const bool mine = (uint32_t)lane < nact;
-			SMan &m = man[mine ? act[lane] : 0];
-			Con c;
-			int colour = -1;
-			if (mine)
-			{
-				build_con<true>(c, m, bodies, h);
-				colour = m.colour;
-			}
-			pc.mark(PH_SETUP);
-			for (int col = 0; col < ncol; col++)
-			{
-				if (colour == col)
-				{
-					Vel u;
-					load_vel(c, bodies, u);
-					warm_start(c, u);
-					store_vel(c, bodies, u);
-				}
-				tile.sync();
-			}
-			pc.mark(PH_WARM);
-			for (uint32_t it = 0; it < a.p.vel_steps; it++)
-				for (int col = 0; col < ncol; col++)
-				{
-					if (colour == col)
-					{
-						Vel u;
-						load_vel(c, bodies, u);
-						solve_velocity(c, u);
-						store_vel(c, bodies, u);
-					}
-					tile.sync();
-				}
-			if (mine) store_lambdas(c, m);
-		}
+			solve_in_registers<TILE, 1>(tile, lane, man, act, nact, bodies, ncol, a.p.vel_steps, h, pc);
 		else
 		{
-			// more manifolds than lanes: rows are rebuilt from the shared records each time a lane revisits one
+			// more manifolds than lanes: a lane revisits several manifolds, so the per-point constants (lever arms,
+			// effective masses) are parked in an L2-resident scratch record and pulled back each visit
+			float4 *park = a.con_park + 9ull * m0;
 			for (uint32_t k = lane; k < nact; k += TILE)
 			{
 				Con c;
 				build_con<true>(c, man[act[k]], bodies, h);
+				park_con(c, park + 9ull * act[k]);
 			}
+			__threadfence_block();
 			tile.sync();
 			for (uint32_t it = 0; it <= a.p.vel_steps; it++)
 				for (int col = 0; col < ncol; col++)
@@ -938,7 +1136,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 						SMan &m = man[act[k]];
 						if (m.colour != col) continue;
 						Con c;
-						build_con<false>(c, m, bodies, h);
+						unpark_con(c, m, bodies, park + 9ull * act[k]);
 						Vel u;
 						load_vel(c, bodies, u);
 						if (it == 0)
@@ -1101,7 +1299,9 @@ static int launch_tick_t(gpx_world *w, const TickArgs &a)
 	if (smem > configured)
 	{
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		int carve = 100;
+		if (const char *e = getenv("GPX_CARVEOUT")) carve = atoi(e);  // tuning knob for profiling runs
+		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
 		configured = smem;
 	}
 	const uint32_t grid = (w->W + wpb - 1) / wpb;
@@ -1121,6 +1321,8 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.n_nodes = w->sd.n_nodes;
 	a.err = w->d_err;
 	a.phase_cycles = w->d_phase;
+	a.cand = w->d_cand;
+	a.con_park = w->d_park;
 	a.p.worlds = w->W;
 	a.p.cap = w->cap;
 	a.p.cap_m = w->cap_m;

@@ -8,7 +8,8 @@ gpx = importlib.import_module("c-game-engine_b200")
 scenes = importlib.import_module("c-game-engine_b200.scenes")
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 g = bench.make_gpu_ensemble(gpx, scenes, W, 0, 0)
-for _ in range(20):
+WARM = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+for _ in range(WARM):
     g.step()
 g.phase_cycles(True)
 N = 50
@@ -18,6 +19,8 @@ for _ in range(N):
 ms = g.timer_end()
 ph = g.phase_cycles(False)
 tot = sum(ph.values())
-print(f"{W} worlds: {ms / N * 1e3:.1f} us/tick (with counters armed); cycles per world-tick (lane 0): {tot / (N * W):.0f}")
+st = g.stats()
+print("manifolds per world: mean", st["manifolds"].mean(), "max", st["manifolds"].max(), "errors", (st["error"] != 0).sum())
+print(f"{W} worlds after {WARM} ticks: {ms / N * 1e3:.1f} us/tick (with counters armed); cycles per world-tick (lane 0): {tot / (N * W):.0f}")
 for k, v in ph.items():
     print(f"  {k:14s} {v / (N * W):10.0f} cyc/world-tick  {100 * v / tot:5.1f}%")
