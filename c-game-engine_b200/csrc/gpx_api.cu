@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
@@ -90,8 +91,39 @@ static BodyCommand command_from_desc(uint32_t index, const gpx_body_desc &d)
 // Push queued host writes to the device (one H2D + one scatter kernel).  Caller holds w->mu.
 static int flush_commands(gpx_world *w)
 {
+	if (w->pending.empty()) return GPX_OK;
+	// The scatter kernel applies commands in parallel, so several writes to one body (destroy + create of a reused slot,
+	// two setters) are folded into one command here, later fields winning, to keep the order the engine issued them in.
+	{
+		std::unordered_map<uint32_t, size_t> at;
+		std::vector<BodyCommand> merged;
+		merged.reserve(w->pending.size());
+		for (const BodyCommand &c : w->pending)
+		{
+			auto it = at.find(c.index);
+			if (it == at.end())
+			{
+				at.emplace(c.index, merged.size());
+				merged.push_back(c);
+				continue;
+			}
+			BodyCommand &e = merged[it->second];
+			if (c.mask & 1u) e.pos = c.pos;
+			if (c.mask & 2u) e.quat = c.quat;
+			if (c.mask & 4u) e.lin = c.lin;
+			if (c.mask & 8u) e.ang = c.ang;
+			if (c.mask & 16u)
+			{
+				e.prop0 = c.prop0;
+				e.prop1 = c.prop1;
+				e.prop2 = c.prop2;
+				e.flags = c.flags;
+			}
+			e.mask |= c.mask;
+		}
+		w->pending.swap(merged);
+	}
 	const size_t n = w->pending.size();
-	if (n == 0) return GPX_OK;
 	if (n > w->d_cmd_cap)
 	{
 		if (w->d_cmd) cudaFree(w->d_cmd);
@@ -195,14 +227,18 @@ uint64_t gpx_launch_count(void) { return g_launches.load(); }
 
 gpx_world *gpx_world_create(const gpx_world_config *cfg)
 {
-	if (!cfg || cfg->worlds == 0 || cfg->max_bodies_per_world == 0 || cfg->max_bodies_per_world > 64) return nullptr;
+	if (!cfg || cfg->worlds == 0 || cfg->max_bodies_per_world == 0) return nullptr;
+	// up to 64 bodies per world: ensembles (one tile of lanes per world, gpx_tick.cu).  More: ONE wide world (gpx_wide.cu)
+	const bool wide = cfg->max_bodies_per_world > 64;
+	if (wide && (cfg->worlds != 1 || cfg->max_bodies_per_world > (1u << 20))) return nullptr;
 	if (cudaSetDevice(cfg->device) != cudaSuccess) return nullptr;
 	gpx_world *w = new gpx_world();
 	w->cfg = *cfg;
 	w->device = cfg->device;
 	w->W = cfg->worlds;
 	w->cap = cfg->max_bodies_per_world;
-	w->cap_m = cfg->max_manifolds_per_world ? cfg->max_manifolds_per_world : (w->cap * 3u < 16u ? 16u : w->cap * 3u);
+	w->cap_m = cfg->max_manifolds_per_world ? cfg->max_manifolds_per_world
+										 : (wide ? w->cap * 8u : (w->cap * 3u < 16u ? 16u : w->cap * 3u));
 	if (w->cap_m & 1u) w->cap_m++;
 	const size_t nb = (size_t)w->W * w->cap, nm = (size_t)w->W * w->cap_m;
 	bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -210,9 +246,12 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	ok = ok && dalloc(&w->bs.pos, nb) == GPX_OK && dalloc(&w->bs.quat, nb) == GPX_OK && dalloc(&w->bs.lin, nb) == GPX_OK &&
 		 dalloc(&w->bs.ang, nb) == GPX_OK && dalloc(&w->bs.prop0, nb) == GPX_OK && dalloc(&w->bs.prop1, nb) == GPX_OK &&
 		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK;
-	ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
-		 dalloc(&w->mc.lt2, nm) == GPX_OK && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
-	ok = ok && dalloc(&w->d_park, nm * 9) == GPX_OK;
+	ok = ok && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
+	if (!wide)
+		ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
+			 dalloc(&w->mc.lt2, nm) == GPX_OK && dalloc(&w->d_park, nm * 9) == GPX_OK;
+	else
+		ok = ok && wide_create(w) == GPX_OK;
 	ok = ok && cudaMalloc(&w->d_cand, sizeof(uint4) * 8 * nb) == cudaSuccess &&
 		 cudaMemset(w->d_cand, 0xFF, sizeof(uint4) * 8 * nb) == cudaSuccess;
 	ok = ok && dalloc(&w->d_err, (size_t)w->W + 1) == GPX_OK && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
@@ -232,6 +271,7 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	memset(w->m_lin, 0, sizeof(float4) * nb);
 	memset(w->m_ang, 0, sizeof(float4) * nb);
 	w->m_err[0] = 0;
+	w->free_hint.assign(w->W, 0u);
 	w->h_flags.assign(nb, 0u);
 	w->h_user_data.assign(nb, 0ull);
 	return w;
@@ -242,6 +282,7 @@ void gpx_world_destroy(gpx_world *w)
 	if (!w) return;
 	cudaSetDevice(w->device);
 	if (w->stream) cudaStreamSynchronize(w->stream);
+	wide_destroy(w);
 	cudaFree(w->bs.pos); cudaFree(w->bs.quat); cudaFree(w->bs.lin); cudaFree(w->bs.ang);
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
@@ -382,9 +423,11 @@ uint32_t gpx_body_create(gpx_world *w, uint32_t world, const gpx_body_desc *desc
 	if (!w || !desc || world >= w->W) return GPX_INVALID_BODY;
 	std::lock_guard<std::mutex> lk(w->mu);
 	const size_t base = (size_t)world * w->cap;
-	for (uint32_t i = 0; i < w->cap; i++)
+	// lowest free slot; everything below the hint is known to be taken (destroy lowers it)
+	for (uint32_t i = w->free_hint[world]; i < w->cap; i++)
 		if (!(w->h_flags[base + i] & BF_ALIVE))
 		{
+			w->free_hint[world] = i + 1;
 			BodyCommand c = command_from_desc((uint32_t)(base + i), *desc);
 			w->h_flags[base + i] = c.flags;
 			w->h_user_data[base + i] = desc->user_data;
@@ -449,6 +492,7 @@ int gpx_body_destroy(gpx_world *w, uint32_t world, uint32_t body)
 	if (!(w->h_flags[g] & BF_ALIVE)) return GPX_ERR_INVALID_ARG;
 	w->h_flags[g] = 0;
 	w->h_user_data[g] = 0;
+	if (body < w->free_hint[world]) w->free_hint[world] = body;
 	BodyCommand c;
 	memset(&c, 0, sizeof(c));
 	c.index = (uint32_t)g;
@@ -568,7 +612,7 @@ int gpx_step(gpx_world *w, float dt, int collision_steps)
 	int rc;
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
-	if ((rc = launch_tick(w, dt, collision_steps)) != GPX_OK) return rc;
+	if ((rc = (w->wide ? launch_wide_tick(w, dt, collision_steps) : launch_tick(w, dt, collision_steps))) != GPX_OK) return rc;
 	w->ticks++;
 	return (int)w->m_err[0];
 }

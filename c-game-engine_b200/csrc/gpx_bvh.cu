@@ -95,6 +95,31 @@ __global__ void k_bitonic_smem(unsigned long long *keys, uint32_t n_pad, uint32_
 		if (base + t < n_pad) keys[base + t] = s[t];
 }
 
+// Ascending sort of a power-of-two array of 64-bit keys: strides >= 2048 go through global memory, the rest of each
+// merge stage runs inside one CTA's shared memory.
+void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t st)
+{
+	const uint32_t tb = 256;
+	if (n_pad <= 2048)
+	{
+		k_bitonic_smem<<<1, 1024, 0, st>>>(d_keys, n_pad, 2, n_pad, 1);
+		count_launch();
+		return;
+	}
+	k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, 2, 2048, 1);
+	count_launch();
+	for (uint32_t k = 4096; k <= n_pad; k <<= 1)
+	{
+		for (uint32_t j = k >> 1; j >= 2048; j >>= 1)
+		{
+			k_bitonic_pass<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_keys, n_pad, j, k);
+			count_launch();
+		}
+		k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, k, k, 1024);
+		count_launch();
+	}
+}
+
 __device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j)
 {
 	if (j < 0 || j >= n) return -1;
@@ -251,7 +276,7 @@ __global__ void k_pack(const float *__restrict__ tris, const uint32_t *__restric
 	}
 }
 
-static uint32_t next_pow2(uint32_t v)
+uint32_t next_pow2(uint32_t v)
 {
 	uint32_t p = 1;
 	while (p < v) p <<= 1;
@@ -323,27 +348,7 @@ int build_static(gpx_world *w)
 	const uint32_t tb = 256;
 	k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, n, n_pad, flo, inv, d_keys);
 	count_launch();
-	// bitonic sort: strides >= 2048 go through global memory, the rest of each stage runs in shared memory
-	if (n_pad <= 2048)
-	{
-		k_bitonic_smem<<<1, 1024, 0, st>>>(d_keys, n_pad, 2, n_pad, 1);
-		count_launch();
-	}
-	else
-	{
-		k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, 2, 2048, 1);
-		count_launch();
-		for (uint32_t k = 4096; k <= n_pad; k <<= 1)
-		{
-			for (uint32_t j = k >> 1; j >= 2048; j >>= 1)
-			{
-				k_bitonic_pass<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_keys, n_pad, j, k);
-				count_launch();
-			}
-			k_bitonic_smem<<<n_pad / 2048, 1024, 0, st>>>(d_keys, n_pad, k, k, 1024);
-			count_launch();
-		}
-	}
+	bitonic_sort_u64(d_keys, n_pad, st);
 	if (n > 1)
 	{
 		k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);

@@ -83,6 +83,8 @@ struct TickParams
 
 }  // namespace gpx
 
+namespace gpx { struct WideDevice; }
+
 struct gpx_world
 {
 	gpx_world_config cfg{};
@@ -101,6 +103,7 @@ struct gpx_world
 	// bodies
 	gpx::BodyStore bs{};
 	gpx::ManifoldCache mc{};
+	std::vector<uint32_t> free_hint;    // per world: no free slot below this index
 	std::vector<uint32_t> h_flags;      // host shadow of the flag word (slot allocation, getters)
 	std::vector<uint64_t> h_user_data;  // Actor* per body
 	std::vector<gpx::BodyCommand> pending;
@@ -114,6 +117,7 @@ struct gpx_world
 	uint32_t *m_err = nullptr;  // pinned
 	gpx_world_stats *d_stats = nullptr;
 	float4 *d_park = nullptr;  // 9 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
+	gpx::WideDevice *wide = nullptr;  // non-null: this world runs the wide-world kernels
 	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)
 	unsigned long long *d_phase = nullptr;  // 16 counters, allocated by gpx_debug_phase_cycles(enable)
 	uint32_t ticks = 0;
@@ -126,6 +130,13 @@ struct gpx_world
 namespace gpx {
 // gpx_bvh.cu
 int build_static(gpx_world *w);
+void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t st);
+uint32_t next_pow2(uint32_t v);
+// gpx_wide.cu: the tick of ONE large world (more than 64 bodies), state in global memory
+struct WideDevice;
+int wide_create(gpx_world *w);
+void wide_destroy(gpx_world *w);
+int launch_wide_tick(gpx_world *w, float dt, int substeps);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 // gpx_tick.cu

@@ -186,7 +186,7 @@ __device__ __forceinline__ void closest_on_edges(v3 p1, v3 d1, float h1, v3 p2, 
 	c2 = p2 + (d2 * t);
 }
 
-__device__ __noinline__ bool collide_box_box(const Box &A, const Box &B, float max_sep, Scratch &sc, Hit &h)
+static __device__ __noinline__ bool collide_box_box(const Box &A, const Box &B, float max_sep, Scratch &sc, Hit &h)
 {
 	v3 d = B.x - A.x;
 	float best = -3.0e38f;
@@ -275,7 +275,7 @@ struct Tri
 	v3 a, b, c, n;
 };
 
-__device__ __noinline__ bool collide_box_tri(const Box &A, const Tri &T, float max_sep, Scratch &sc, Hit &h)
+static __device__ __noinline__ bool collide_box_tri(const Box &A, const Tri &T, float max_sep, Scratch &sc, Hit &h)
 {
 	v3 tv[3] = {T.a, T.b, T.c};
 	float best;

@@ -133,7 +133,7 @@ __device__ __forceinline__ bool layers_collide(uint32_t la, uint32_t lb)
 }
 
 // Box query of the static LBVH: leaves whose exact triangle box overlaps [lo-m, hi+m], sorted by triangle index.
-__device__ __noinline__ int query_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris,
+static __device__ __noinline__ int query_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris,
 										 uint32_t n_nodes, v3 lo, v3 hi, float m, int *cand_orig, int *cand_leaf,
 										 bool &overflow)
 {
@@ -207,7 +207,7 @@ struct StaticView
 	uint32_t n_nodes;
 };
 
-__device__ __noinline__ int static_candidates(const StaticView &a, uint4 *rec, v3 lo, v3 hi, int *cand_orig, int *cand_leaf,
+static __device__ __noinline__ int static_candidates(const StaticView &a, uint4 *rec, v3 lo, v3 hi, int *cand_orig, int *cand_leaf,
 											  bool &overflow)
 {
 	const float m = SPECULATIVE_DISTANCE;
@@ -526,7 +526,7 @@ __device__ __forceinline__ void solve_velocity(Con &c, Vel &u)
 	}
 }
 
-__device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
+static __device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
 {
 	SBody &A = bodies[m.a];
 	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;

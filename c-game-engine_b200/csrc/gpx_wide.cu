@@ -1,0 +1,673 @@
+// gpx_wide.cu — the tick of ONE large world (hundreds to hundreds of thousands of bodies): BASELINE config 4.
+//
+// Same JPH_PhysicsSystem_Update(system, dt, 2, jobSystem) contract as gpx_tick.cu (engine/src/physics/MapPhysics.c:
+// 105-108), same device functions (gpx_solver.cuh) and therefore the same fp32 results per contact, but a different
+// decomposition: state lives in global memory (L2-resident at 100k bodies) and every stage is one thread per item.
+//
+//   kw_begin      thread/body      SoA -> work record (first sub-step), forces, inertia, AABB, sort key = min x
+//   bitonic sort  (gpx_bvh.cu)     bodies ordered by the lower x bound of their boxes
+//   kw_gather     thread/slot      sorted boxes packed into two float4 streams
+//   kw_sweep      thread/body      sort-and-sweep broadphase: walk forward while boxes can still overlap on x,
+//                                  exact box test, layer matrix -> pair list (atomic append)
+//   kw_pairs      thread/pair      box-box / sphere contact manifolds
+//   kw_static     thread/body      LBVH candidates (cached), box/sphere-vs-triangle manifolds grouped by normal
+//   kw_link       thread/manifold  warm-start lookup in a hash table of the previous sub-step's manifolds, incidence
+//                                  lists per dynamic body, colouring priority
+//   kw_colour     cooperative      Jones-Plassmann colouring with hashed priorities (result depends on the contact
+//                                  graph only, not on list order), then per-colour manifold lists
+//   kw_solve      cooperative      set-up; warm start; 10 x (colour by colour) velocity rows; integrate;
+//                                  2 x (colour by colour) position rows — grid-wide barriers between colours
+//   kw_finish     thread/manifold  hash table for the next sub-step; last sub-step: work records -> SoA
+//
+// No float atomics and no order-dependent reductions: within a colour no two manifolds share a dynamic body, so the
+// result is a pure function of the contact set.
+#include <cooperative_groups.h>
+
+#include "gpx_solver.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gpx {
+
+constexpr int WIDE_MAXADJ = 16;      // manifolds incident to one dynamic body
+constexpr int WIDE_MAXCOL = 64;
+constexpr uint32_t WT = 128;         // threads per block of the per-item kernels
+constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase kernels (shared polygon scratch)
+
+enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_COLCNT = 8,
+				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_COUNT = WC_COLCUR + WIDE_MAXCOL };
+
+struct WideDevice
+{
+	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0;
+	SBody *bodies = nullptr;
+	unsigned long long *keys = nullptr;
+	float4 *boxlo = nullptr, *boxhi = nullptr;
+	SMan *man[2] = {nullptr, nullptr};
+	uint32_t *ord[2] = {nullptr, nullptr};  // ordinal of a manifold among those with the same (a, b)
+	int cur = 0;
+	float4 *park = nullptr;
+	uint32_t *counters = nullptr;
+	unsigned long long *hkeys = nullptr;
+	uint32_t *hvals = nullptr;
+	uint32_t *adj = nullptr, *adj_n = nullptr;
+	uint32_t *prio = nullptr;
+	int *pending = nullptr;
+	uint32_t *col_list = nullptr;
+	int coop_grid_colour = 0, coop_grid_solve = 0;
+};
+
+struct WideArgs
+{
+	BodyStore bs;
+	SBody *bodies;
+	unsigned long long *keys;
+	float4 *boxlo, *boxhi;
+	SMan *man, *prev;
+	uint32_t *ord, *prev_ord;
+	float4 *park;
+	uint32_t *cnt;
+	unsigned long long *hkeys;
+	uint32_t *hvals;
+	uint32_t *adj, *adj_n;
+	uint32_t *prio;
+	int *pending;
+	uint32_t *col_list;
+	uint4 *cand;
+	StaticView sv;
+	uint32_t nb, n_pad, cap_m, hmask;
+	uint32_t vel_steps, pos_steps;
+	float gx, gy, gz, h;
+	int first, last;
+};
+
+__device__ __forceinline__ uint32_t sortable(float f)
+{
+	uint32_t b = __float_as_uint(f);
+	return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+__device__ __forceinline__ unsigned long long man_key(uint32_t a, uint32_t b, uint32_t ord)
+{
+	return ((unsigned long long)(a + 1u) << 40) | ((unsigned long long)b << 8) | (unsigned long long)(ord & 0xFFu);
+}
+__device__ __forceinline__ uint32_t key_slot(unsigned long long k, uint32_t mask)
+{
+	k ^= k >> 33;
+	k *= 0xFF51AFD7ED558CCDull;
+	k ^= k >> 33;
+	k *= 0xC4CEB9FE1A85EC53ull;
+	k ^= k >> 33;
+	return (uint32_t)k & mask;
+}
+// Colouring priority: a fixed hash of the manifold's identity (restated in the oracle, oracle/orc.c colour_manifolds_jp)
+__device__ __forceinline__ uint32_t man_prio(uint32_t a, uint32_t b, uint32_t ord)
+{
+	uint32_t h = (a * 0x9E3779B1u) ^ ((b + ord * 0x7F4A7C15u) * 0x85EBCA77u);
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	h ^= h >> 12;
+	h *= 0x297A2D39u;
+	h ^= h >> 15;
+	return h;
+}
+
+// ---------------------------------------------------------------------------------------------------- per body
+
+__global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= a.n_pad) return;
+	if (i >= a.nb)
+	{
+		a.keys[i] = ~0ull;
+		return;
+	}
+	SBody &b = a.bodies[i];
+	if (a.first)
+	{
+		const float4 p = a.bs.pos[i], q = a.bs.quat[i], l = a.bs.lin[i], w = a.bs.ang[i];
+		const float4 p0 = a.bs.prop0[i], p1 = a.bs.prop1[i], p2 = a.bs.prop2[i];
+		b.x = V(p);
+		b.q = Q(q);
+		b.v = V(l);
+		b.w = V(w);
+		b.inv_mass = p0.x;
+		b.inv_i = V(p0.y, p0.z, p0.w);
+		b.he = V(p1);
+		b.friction = p1.w;
+		b.lin_damp = p2.x;
+		b.ang_damp = p2.y;
+		b.grav = p2.z;
+		b.restitution = p2.w;
+		b.flags = a.bs.flags[i];
+	}
+	a.adj_n[i] = 0;
+	const uint32_t f = b.flags;
+	if (!(f & BF_ALIVE))
+	{
+		a.keys[i] = ~0ull;
+		return;
+	}
+	const float h = a.h;
+	if (is_dynamic(f))
+	{
+		const uint32_t dofs = dofs_of(f);
+		const v3 gravity = V(a.gx, a.gy, a.gz);
+		b.v = b.v + (gravity * (h * b.grav));
+		b.v = b.v * fmaxf(0.0f, 1.0f - (b.lin_damp * h));
+		b.w = b.w * fmaxf(0.0f, 1.0f - (b.ang_damp * h));
+		b.v = clamp_len(mask_lin(dofs, b.v), MAX_LINEAR_VELOCITY);
+		v3 ww = b.w;
+		if (!(dofs & 8u)) ww.x = 0.0f;
+		if (!(dofs & 16u)) ww.y = 0.0f;
+		if (!(dofs & 32u)) ww.z = 0.0f;
+		b.w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+	}
+	body_world_inertia(b);
+	body_aabb(b);
+	a.keys[i] = shape_of(f) == GPX_SHAPE_EMPTY ? ~0ull : (((unsigned long long)sortable(b.lo.x) << 32) | i);
+}
+
+__global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
+{
+	const uint32_t p = blockIdx.x * WT + threadIdx.x;
+	if (p >= a.n_pad) return;
+	const unsigned long long k = a.keys[p];
+	if (k == ~0ull)
+	{
+		a.boxlo[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+		return;
+	}
+	const uint32_t i = (uint32_t)(k & 0xFFFFFFFFull);
+	const SBody &b = a.bodies[i];
+	a.boxlo[p] = F4(b.lo, __uint_as_float(i));
+	a.boxhi[p] = F4(b.hi, __uint_as_float(b.flags));
+}
+
+// Sort-and-sweep: bodies are ordered by lo.x; body p only has to look at later bodies whose lo.x is still below its
+// hi.x (+ margin).  The exact test is the ensemble kernel's, evaluated with the lower-numbered body first.
+__global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
+{
+	const uint32_t p = blockIdx.x * WT + threadIdx.x;
+	if (p >= a.n_pad) return;
+	const float4 lo_p = a.boxlo[p];
+	const uint32_t ip = __float_as_uint(lo_p.w);
+	if (ip == 0xFFFFFFFFu) return;
+	const float4 hi_p = a.boxhi[p];
+	const uint32_t fp = __float_as_uint(hi_p.w);
+	const float reach = (hi_p.x + SPECULATIVE_DISTANCE) + SPECULATIVE_DISTANCE;  // a little beyond the exact test's reach
+	for (uint32_t q = p + 1; q < a.n_pad; q++)
+	{
+		const float4 lo_q = a.boxlo[q];
+		const uint32_t iq = __float_as_uint(lo_q.w);
+		if (iq == 0xFFFFFFFFu || lo_q.x > reach) break;
+		const float4 hi_q = a.boxhi[q];
+		const uint32_t fq = __float_as_uint(hi_q.w);
+		if (!is_dynamic(fp) && !is_dynamic(fq)) continue;
+		if (!layers_collide(layer_of(fp), layer_of(fq))) continue;
+		if ((fp & BF_SENSOR) || (fq & BF_SENSOR)) continue;
+		const bool p_first = ip < iq;
+		const v3 alo = p_first ? V(lo_p) : V(lo_q), ahi = p_first ? V(hi_p) : V(hi_q);
+		const v3 blo = p_first ? V(lo_q) : V(lo_p), bhi = p_first ? V(hi_q) : V(hi_p);
+		if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) continue;
+		const uint32_t k = atomicAdd(&a.cnt[WC_NMAN], 1u);
+		if (k >= a.cap_m)
+		{
+			atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+			break;
+		}
+		SMan &m = a.man[k];
+		m.a = p_first ? ip : iq;
+		m.b = p_first ? iq : ip;
+		m.np = 0;
+		m.colour = -2;
+		a.ord[k] = 0;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------- narrowphase
+
+__global__ void __launch_bounds__(NARROW_T) kw_pairs(WideArgs a)
+{
+	__shared__ Scratch scratch[NARROW_T];
+	const uint32_t k = blockIdx.x * NARROW_T + threadIdx.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);  // only pairs have been appended so far
+	if (k >= n) return;
+	SMan &m = a.man[k];
+	pair_contact(a.bodies[m.a], a.bodies[m.b], scratch[threadIdx.x], m);
+}
+
+__global__ void __launch_bounds__(NARROW_T) kw_static(WideArgs a)
+{
+	__shared__ Scratch scratch[NARROW_T];
+	const uint32_t i = blockIdx.x * NARROW_T + threadIdx.x;
+	if (i >= a.nb) return;
+	const SBody &A = a.bodies[i];
+	const uint32_t fa = A.flags;
+	if (!(fa & BF_ALIVE) || shape_of(fa) == GPX_SHAPE_EMPTY) return;
+	const uint32_t la = layer_of(fa);
+	if (!is_dynamic(fa) || (fa & BF_SENSOR) || !(la == 1 || la == 2)) return;
+	StaticSlot slots[MAX_STATIC_PER_BODY];
+	uint32_t err = 0;
+	const int nslots = body_static_contacts(a.sv, a.cand + 8ull * i, A, scratch[threadIdx.x], slots, err);
+	if (err) atomicOr(&a.cnt[WC_ERR], err);
+	if (nslots == 0) return;
+	const uint32_t base = atomicAdd(&a.cnt[WC_NMAN], (uint32_t)nslots);
+	for (int s = 0; s < nslots; s++)
+	{
+		const uint32_t k = base + s;
+		if (k >= a.cap_m)
+		{
+			atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+			break;
+		}
+		SMan &m = a.man[k];
+		m.a = i;
+		m.b = STATIC_BODY_BASE + slots[s].sbody;
+		m.colour = -2;
+		m.n = slots[s].n;
+		m.friction = slots[s].friction;
+		m.restitution = A.restitution;
+		store_points(m, A, nullptr, slots[s].np, slots[s].p1, slots[s].p2);
+		uint32_t o = 0;
+		for (int t = 0; t < s; t++) o += slots[t].sbody == slots[s].sbody ? 1u : 0u;
+		a.ord[k] = o;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------- linking
+
+__device__ __forceinline__ int hash_find(const WideArgs &a, unsigned long long key)
+{
+	uint32_t s = key_slot(key, a.hmask);
+	for (uint32_t probe = 0; probe <= a.hmask; probe++)
+	{
+		const unsigned long long k = a.hkeys[s];
+		if (k == key) return (int)a.hvals[s];
+		if (k == 0ull) return -1;
+		s = (s + 1u) & a.hmask;
+	}
+	return -1;
+}
+
+__global__ void __launch_bounds__(WT) kw_link(WideArgs a)
+{
+	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	if (mi >= n) return;
+	SMan &m = a.man[mi];
+	if (m.np == 0)
+	{
+		m.colour = -2;
+		return;
+	}
+	// warm start: previous manifolds of the same body pair, in creation order (ordinal 0, 1, ...)
+	for (uint32_t o = 0; o < (uint32_t)MAX_SLOTS; o++)
+	{
+		const int j = hash_find(a, man_key(m.a, m.b, o));
+		if (j < 0) break;
+		const SMan &old = a.prev[j];
+		for (int p = 0; p < m.np; p++)
+		{
+			if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
+			for (int k = 0; k < old.np; k++)
+				if (len2(m.p1l[p] - old.p1l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
+					len2(m.p2l[p] - old.p2l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ)
+				{
+					m.ln[p] = old.ln[k];
+					m.lt1[p] = old.lt1[k];
+					m.lt2[p] = old.lt2[k];
+					break;
+				}
+		}
+		if (m.b < STATIC_BODY_BASE) break;  // body pairs have exactly one manifold
+	}
+	// incidence lists of the dynamic bodies (what the colouring walks)
+	const bool a_dyn = is_dynamic(a.bodies[m.a].flags);
+	const bool b_dyn = m.b < STATIC_BODY_BASE && is_dynamic(a.bodies[m.b].flags);
+	if (a_dyn)
+	{
+		const uint32_t k = atomicAdd(&a.adj_n[m.a], 1u);
+		if (k < (uint32_t)WIDE_MAXADJ) a.adj[m.a * WIDE_MAXADJ + k] = mi;
+		else atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+	}
+	if (b_dyn)
+	{
+		const uint32_t k = atomicAdd(&a.adj_n[m.b], 1u);
+		if (k < (uint32_t)WIDE_MAXADJ) a.adj[m.b * WIDE_MAXADJ + k] = mi;
+		else atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+	}
+	a.prio[mi] = man_prio(m.a, m.b, a.ord[mi]);
+	m.colour = -1;
+	atomicAdd(&a.cnt[WC_UNCOLOURED], 1u);
+}
+
+// total order on manifolds for the colouring: priority, then identity
+__device__ __forceinline__ bool outranks(const WideArgs &a, uint32_t x, uint32_t y)
+{
+	const uint32_t px = a.prio[x], py = a.prio[y];
+	if (px != py) return px > py;
+	const SMan &mx = a.man[x], &my = a.man[y];
+	if (mx.a != my.a) return mx.a > my.a;
+	if (mx.b != my.b) return mx.b > my.b;
+	return a.ord[x] > a.ord[y];
+}
+
+// Jones-Plassmann: in each round every uncoloured manifold that outranks all its uncoloured neighbours takes the
+// smallest colour none of its coloured neighbours has.  Decisions of a round only read colours of earlier rounds.
+__global__ void __launch_bounds__(256) kw_colour(WideArgs a)
+{
+	cg::grid_group grid = cg::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	for (int round = 0; round < 4096; round++)
+	{
+		if (a.cnt[WC_UNCOLOURED] == 0) break;
+		grid.sync();
+		for (uint32_t mi = tid; mi < n; mi += stride)
+		{
+			const SMan &m = a.man[mi];
+			int decision = -1;
+			if (m.colour == -1)
+			{
+				bool top = true;
+				unsigned long long used = 0ull;
+				const uint32_t ends[2] = {m.a, m.b};
+				for (int e = 0; e < 2 && top; e++)
+				{
+					const uint32_t body = ends[e];
+					if (body >= STATIC_BODY_BASE || !is_dynamic(a.bodies[body].flags)) continue;
+					const uint32_t cntb = min(a.adj_n[body], (uint32_t)WIDE_MAXADJ);
+					for (uint32_t k = 0; k < cntb; k++)
+					{
+						const uint32_t other = a.adj[body * WIDE_MAXADJ + k];
+						if (other == mi) continue;
+						const int oc = a.man[other].colour;
+						if (oc == -1)
+						{
+							if (outranks(a, other, mi))
+							{
+								top = false;
+								break;
+							}
+						}
+						else if (oc >= 0)
+							used |= 1ull << oc;
+					}
+				}
+				if (top)
+				{
+					decision = __ffsll((long long)~used) - 1;
+					if (decision < 0 || decision >= WIDE_MAXCOL)
+					{
+						decision = WIDE_MAXCOL - 1;
+						atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+					}
+				}
+			}
+			a.pending[mi] = decision;
+		}
+		grid.sync();
+		uint32_t done = 0;
+		for (uint32_t mi = tid; mi < n; mi += stride)
+		{
+			const int d = a.pending[mi];
+			if (d >= 0)
+			{
+				a.man[mi].colour = d;
+				atomicAdd(&a.cnt[WC_COLCNT + d], 1u);
+				done++;
+			}
+		}
+		if (done) atomicSub(&a.cnt[WC_UNCOLOURED], done);
+		grid.sync();
+	}
+	grid.sync();
+	// per-colour lists
+	if (tid == 0)
+	{
+		uint32_t off = 0, ncol = 0;
+		for (int c = 0; c < WIDE_MAXCOL; c++)
+		{
+			a.cnt[WC_COLOFF + c] = off;
+			a.cnt[WC_COLCUR + c] = off;
+			off += a.cnt[WC_COLCNT + c];
+			if (a.cnt[WC_COLCNT + c]) ncol = (uint32_t)c + 1u;
+		}
+		a.cnt[WC_COLOFF + WIDE_MAXCOL] = off;
+		a.cnt[WC_NCOL] = ncol;
+		a.cnt[WC_NACTIVE] = off;
+	}
+	grid.sync();
+	for (uint32_t mi = tid; mi < n; mi += stride)
+	{
+		const int c = a.man[mi].colour;
+		if (c >= 0) a.col_list[atomicAdd(&a.cnt[WC_COLCUR + c], 1u)] = mi;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------- solve
+
+__global__ void __launch_bounds__(256) kw_solve(WideArgs a)
+{
+	cg::grid_group grid = cg::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	const uint32_t nact = a.cnt[WC_NACTIVE];
+	const int ncol = (int)a.cnt[WC_NCOL];
+	const float h = a.h;
+	// set-up: lever arms, effective masses, bias; parked next to the manifold
+	for (uint32_t k = tid; k < nact; k += stride)
+	{
+		const uint32_t mi = a.col_list[k];
+		Con c;
+		build_con<true>(c, a.man[mi], a.bodies, h);
+		park_con(c, a.park + 9ull * mi);
+	}
+	grid.sync();
+	// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
+	// dynamic body, so every body is written by at most one thread per phase.
+	for (uint32_t it = 0; it <= a.vel_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
+			for (uint32_t k = lo + tid; k < hi; k += stride)
+			{
+				const uint32_t mi = a.col_list[k];
+				SMan &m = a.man[mi];
+				Con c;
+				unpark_con(c, m, a.bodies, a.park + 9ull * mi);
+				Vel u;
+				load_vel(c, a.bodies, u);
+				if (it == 0)
+					warm_start(c, u);
+				else
+					solve_velocity(c, u);
+				store_vel(c, a.bodies, u);
+				store_lambdas(c, m);
+			}
+			grid.sync();
+		}
+	// integrate
+	for (uint32_t i = tid; i < a.nb; i += stride)
+	{
+		SBody &b = a.bodies[i];
+		if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC) continue;
+		b.x = b.x + (b.v * h);
+		b.q = qstep(b.q, b.w * h);
+	}
+	grid.sync();
+	// position iterations
+	for (uint32_t it = 0; it < a.pos_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
+			for (uint32_t k = lo + tid; k < hi; k += stride) solve_position(a.man[a.col_list[k]], a.bodies);
+			grid.sync();
+		}
+}
+
+__global__ void __launch_bounds__(WT) kw_finish(WideArgs a)
+{
+	const uint32_t t = blockIdx.x * WT + threadIdx.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	if (t < n)
+	{
+		const SMan &m = a.man[t];
+		if (m.np > 0)
+		{
+			const unsigned long long key = man_key(m.a, m.b, a.ord[t]);
+			uint32_t s = key_slot(key, a.hmask);
+			for (uint32_t probe = 0; probe <= a.hmask; probe++)
+			{
+				const unsigned long long old = atomicCAS(&a.hkeys[s], 0ull, key);
+				if (old == 0ull || old == key)
+				{
+					a.hvals[s] = t;
+					break;
+				}
+				s = (s + 1u) & a.hmask;
+			}
+		}
+	}
+	if (a.last && t < a.nb)
+	{
+		const SBody &b = a.bodies[t];
+		if (b.flags & BF_ALIVE)
+		{
+			a.bs.pos[t] = F4(b.x, 0.0f);
+			a.bs.quat[t] = make_float4(b.q.x, b.q.y, b.q.z, b.q.w);
+			a.bs.lin[t] = F4(b.v, 0.0f);
+			a.bs.ang[t] = F4(b.w, 0.0f);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------- host
+
+template <typename T>
+static bool walloc(T **p, size_t n)
+{
+	if (cudaMalloc(p, sizeof(T) * n) != cudaSuccess) return false;
+	return cudaMemset(*p, 0, sizeof(T) * n) == cudaSuccess;
+}
+
+int wide_create(gpx_world *w)
+{
+	WideDevice *d = new WideDevice();
+	w->wide = d;
+	d->nb = w->cap;
+	d->n_pad = next_pow2(d->nb);
+	d->cap_m = w->cap_m;
+	d->hsize = next_pow2(2u * d->cap_m);
+	bool ok = walloc(&d->bodies, d->nb) && walloc(&d->keys, d->n_pad) && walloc(&d->boxlo, d->n_pad) &&
+			  walloc(&d->boxhi, d->n_pad) && walloc(&d->man[0], d->cap_m) && walloc(&d->man[1], d->cap_m) &&
+			  walloc(&d->ord[0], d->cap_m) && walloc(&d->ord[1], d->cap_m) && walloc(&d->park, (size_t)d->cap_m * 9) &&
+			  walloc(&d->counters, (size_t)WC_COUNT) && walloc(&d->hkeys, d->hsize) && walloc(&d->hvals, d->hsize) &&
+			  walloc(&d->adj, (size_t)d->nb * WIDE_MAXADJ) && walloc(&d->adj_n, d->nb) && walloc(&d->prio, d->cap_m) &&
+			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m);
+	if (!ok)
+	{
+		set_error("wide_create", cudaGetLastError());
+		return GPX_ERR_CUDA;
+	}
+	int sms = 148, per_sm = 1;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_colour, 256, 0));
+	d->coop_grid_colour = sms * (per_sm > 0 ? per_sm : 1);
+	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_solve, 256, 0));
+	d->coop_grid_solve = sms * (per_sm > 0 ? per_sm : 1);
+	return GPX_OK;
+}
+
+void wide_destroy(gpx_world *w)
+{
+	WideDevice *d = w->wide;
+	if (!d) return;
+	cudaFree(d->bodies); cudaFree(d->keys); cudaFree(d->boxlo); cudaFree(d->boxhi); cudaFree(d->man[0]); cudaFree(d->man[1]);
+	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->park); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
+	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
+	delete d;
+	w->wide = nullptr;
+}
+
+static int coop_launch(const void *fn, int grid, WideArgs &a, cudaStream_t st)
+{
+	void *params[] = {&a};
+	GPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), params, 0, st));
+	count_launch();
+	return GPX_OK;
+}
+
+int launch_wide_tick(gpx_world *w, float dt, int substeps)
+{
+	WideDevice *d = w->wide;
+	cudaStream_t st = w->stream;
+	if (substeps < 1) substeps = 1;
+	WideArgs a;
+	a.bs = w->bs;
+	a.bodies = d->bodies;
+	a.keys = d->keys;
+	a.boxlo = d->boxlo;
+	a.boxhi = d->boxhi;
+	a.park = d->park;
+	a.cnt = d->counters;
+	a.hkeys = d->hkeys;
+	a.hvals = d->hvals;
+	a.adj = d->adj;
+	a.adj_n = d->adj_n;
+	a.prio = d->prio;
+	a.pending = d->pending;
+	a.col_list = d->col_list;
+	a.cand = w->d_cand;
+	a.sv.nodes = w->sd.nodes;
+	a.sv.tris = w->sd.tri;
+	a.sv.n_nodes = w->sd.n_nodes;
+	a.nb = d->nb;
+	a.n_pad = d->n_pad;
+	a.cap_m = d->cap_m;
+	a.hmask = d->hsize - 1u;
+	a.vel_steps = w->cfg.velocity_steps ? w->cfg.velocity_steps : 10u;
+	a.pos_steps = w->cfg.position_steps ? w->cfg.position_steps : 2u;
+	a.gx = w->cfg.gravity[0];
+	a.gy = w->cfg.gravity[1];
+	a.gz = w->cfg.gravity[2];
+	a.h = dt / (float)substeps;
+	const uint32_t gb = (d->n_pad + WT - 1) / WT, gm = (d->cap_m + WT - 1) / WT;
+	for (int sub = 0; sub < substeps; sub++)
+	{
+		a.first = sub == 0;
+		a.last = sub == substeps - 1;
+		a.man = d->man[d->cur];
+		a.prev = d->man[d->cur ^ 1];
+		a.ord = d->ord[d->cur];
+		a.prev_ord = d->ord[d->cur ^ 1];
+		// counters: everything but the error word and the previous count starts from zero
+		GPX_CUDA(cudaMemsetAsync(d->counters + WC_NMAN, 0, sizeof(uint32_t), st));
+		GPX_CUDA(cudaMemsetAsync(d->counters + WC_UNCOLOURED, 0, sizeof(uint32_t) * (WC_COUNT - WC_UNCOLOURED), st));
+		kw_begin<<<gb, WT, 0, st>>>(a);
+		count_launch();
+		bitonic_sort_u64(d->keys, d->n_pad, st);
+		kw_gather<<<gb, WT, 0, st>>>(a);
+		kw_sweep<<<gb, WT, 0, st>>>(a);
+		kw_pairs<<<(d->cap_m + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);
+		kw_static<<<(d->nb + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);
+		kw_link<<<gm, WT, 0, st>>>(a);
+		count_launch(5);
+		int rc;
+		if ((rc = coop_launch((const void *)kw_colour, d->coop_grid_colour, a, st)) != GPX_OK) return rc;
+		if ((rc = coop_launch((const void *)kw_solve, d->coop_grid_solve, a, st)) != GPX_OK) return rc;
+		// this sub-step's manifolds become the next one's warm-start table
+		GPX_CUDA(cudaMemsetAsync(d->hkeys, 0, sizeof(unsigned long long) * d->hsize, st));
+		kw_finish<<<max(gm, gb), WT, 0, st>>>(a);
+		count_launch();
+		d->cur ^= 1;
+	}
+	// merge the error word into the world's error slot (d_err[0], d_err[1])
+	GPX_CUDA(cudaMemcpyAsync(w->d_err, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+	GPX_CUDA(cudaMemcpyAsync(w->d_err + 1, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
+}  // namespace gpx

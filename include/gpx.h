@@ -82,7 +82,7 @@ typedef struct gpx_world gpx_world;
 typedef struct gpx_world_config
 {
 	uint32_t worlds;                  /* number of independent world instances sharing the static map */
-	uint32_t max_bodies_per_world;    /* non-static-mesh body slots per world (<= 64) */
+	uint32_t max_bodies_per_world;    /* body slots per world: <= 64 for ensembles; up to 2^20 when worlds == 1 (one wide world) */
 	uint32_t max_manifolds_per_world; /* contact manifolds per world and sub-step; 0 = default */
 	uint32_t max_static_triangles;    /* capacity of the shared static triangle soup */
 	float gravity[3];                 /* JPH_PhysicsSystem_SetGravity (Physics.c:99) */

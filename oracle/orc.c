@@ -68,6 +68,8 @@ typedef struct
 	v3 r1[4], r2[4];  /* lever arms from the centres of mass to the contact midpoint */
 	float em[4][3];   /* effective mass along normal, tangent1, tangent2 */
 	int colour;
+	uint32_t ord;  /* ordinal among the manifolds of the same (a, b): 0 for body pairs, slot index for static bodies */
+	uint32_t prio; /* colouring priority (mode 1) */
 } manifold_t;
 
 typedef struct
@@ -98,6 +100,7 @@ struct orc_world
 	manifold_t *man, *prev;
 	uint32_t nman, nprev;
 	uint32_t *order;
+	int mode; /* 0: greedy colouring in canonical order (ensembles); 1: hashed-priority rounds (wide worlds) */
 };
 
 /* ------------------------------------------------------------------------------------------ world management */
@@ -117,6 +120,8 @@ orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const f
 	w->order = (uint32_t *)calloc(w->max_manifolds, sizeof(uint32_t));
 	return w;
 }
+
+void orc_world_set_mode(orc_world *w, int mode) { w->mode = mode; }
 
 void orc_world_destroy(orc_world *w)
 {
@@ -1033,6 +1038,7 @@ static void find_contacts(orc_world *w, int *err)
 					s = nslots++;
 					slots[s] = m;
 					snp[s] = 0;
+					m->ord = (uint32_t)s;
 				}
 				else if (h.depth > slots[s]->depth)
 				{
@@ -1124,9 +1130,8 @@ static void warm_start_match(orc_world *w)
 static int colour_manifolds(orc_world *w)
 {
 	/* greedy first-fit in canonical order; only dynamic bodies constrain the colour */
-	uint64_t used[4096];
-	uint32_t nb = w->max_bodies < 4096 ? w->max_bodies : 4096;
-	memset(used, 0, nb * sizeof(uint64_t));
+	uint32_t nb = w->max_bodies;
+	uint64_t *used = (uint64_t *)calloc(nb, sizeof(uint64_t));
 	int ncol = 0;
 	for (uint32_t i = 0; i < w->nman; i++)
 	{
@@ -1143,9 +1148,116 @@ static int colour_manifolds(orc_world *w)
 		if (b_dyn) used[m->b] |= 1ull << c;
 		if (c + 1 > ncol) ncol = c + 1;
 	}
+	free(used);
 	uint32_t k = 0;
 	for (int c = 0; c < ncol; c++)
 		for (uint32_t i = 0; i < w->nman; i++)
+			if (w->man[i].colour == c) w->order[k++] = i;
+	return ncol;
+}
+
+/* Mode 1 (wide worlds): Jones-Plassmann colouring with hashed priorities.  In each round every uncoloured manifold
+ * that outranks all its uncoloured neighbours (manifolds sharing a dynamic body) takes the smallest colour none of
+ * its already-coloured neighbours has; decisions of a round only see colours of earlier rounds.  The result is a
+ * function of the contact graph alone, so a parallel evaluation gives the same colours. */
+static uint32_t man_prio(uint32_t a, uint32_t b, uint32_t ord)
+{
+	uint32_t h = (a * 0x9E3779B1u) ^ ((b + ord * 0x7F4A7C15u) * 0x85EBCA77u);
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	h ^= h >> 12;
+	h *= 0x297A2D39u;
+	h ^= h >> 15;
+	return h;
+}
+
+static int outranks(const manifold_t *x, const manifold_t *y)
+{
+	if (x->prio != y->prio) return x->prio > y->prio;
+	if (x->a != y->a) return x->a > y->a;
+	if (x->b != y->b) return x->b > y->b;
+	return x->ord > y->ord;
+}
+
+static int colour_manifolds_jp(orc_world *w)
+{
+	const uint32_t n = w->nman, nb = w->max_bodies;
+	/* incidence lists of the dynamic bodies */
+	uint32_t *cnt = (uint32_t *)calloc(nb + 1, sizeof(uint32_t));
+	for (uint32_t i = 0; i < n; i++)
+	{
+		manifold_t *m = &w->man[i];
+		m->prio = man_prio(m->a, m->b, m->ord);
+		m->colour = -1;
+		if (w->bodies[m->a].motion == ORC_MOTION_DYNAMIC) cnt[m->a + 1]++;
+		if (m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC) cnt[m->b + 1]++;
+	}
+	for (uint32_t i = 0; i < nb; i++) cnt[i + 1] += cnt[i];
+	uint32_t *adj = (uint32_t *)malloc((cnt[nb] + 1) * sizeof(uint32_t));
+	uint32_t *cur = (uint32_t *)malloc((nb + 1) * sizeof(uint32_t));
+	memcpy(cur, cnt, (nb + 1) * sizeof(uint32_t));
+	for (uint32_t i = 0; i < n; i++)
+	{
+		manifold_t *m = &w->man[i];
+		if (w->bodies[m->a].motion == ORC_MOTION_DYNAMIC) adj[cur[m->a]++] = i;
+		if (m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC) adj[cur[m->b]++] = i;
+	}
+	int *pending = (int *)malloc((n + 1) * sizeof(int));
+	uint32_t left = n;
+	int ncol = 0;
+	while (left)
+	{
+		for (uint32_t i = 0; i < n; i++)
+		{
+			const manifold_t *m = &w->man[i];
+			pending[i] = -1;
+			if (m->colour != -1) continue;
+			int top = 1;
+			uint64_t used = 0;
+			const uint32_t ends[2] = {m->a, m->b};
+			for (int e = 0; e < 2 && top; e++)
+			{
+				uint32_t body = ends[e];
+				if (body >= ORC_STATIC_BODY_BASE || w->bodies[body].motion != ORC_MOTION_DYNAMIC) continue;
+				for (uint32_t k = cnt[body]; k < cnt[body + 1]; k++)
+				{
+					uint32_t other = adj[k];
+					if (other == i) continue;
+					int oc = w->man[other].colour;
+					if (oc == -1)
+					{
+						if (outranks(&w->man[other], m))
+						{
+							top = 0;
+							break;
+						}
+					}
+					else
+						used |= 1ull << oc;
+				}
+			}
+			if (top)
+			{
+				int c = 0;
+				while (c < 63 && ((used >> c) & 1u)) c++;
+				pending[i] = c;
+			}
+		}
+		for (uint32_t i = 0; i < n; i++)
+			if (pending[i] >= 0)
+			{
+				w->man[i].colour = pending[i];
+				if (pending[i] + 1 > ncol) ncol = pending[i] + 1;
+				left--;
+			}
+	}
+	free(pending);
+	free(cur);
+	free(adj);
+	free(cnt);
+	uint32_t k = 0;
+	for (int c = 0; c < ncol; c++)
+		for (uint32_t i = 0; i < n; i++)
 			if (w->man[i].colour == c) w->order[k++] = i;
 	return ncol;
 }
@@ -1369,7 +1481,8 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		}
 		find_contacts(w, &err);
 		warm_start_match(w);
-		colour_manifolds(w);
+		if (w->mode == 1) colour_manifolds_jp(w);
+		else colour_manifolds(w);
 		for (uint32_t k = 0; k < w->nman; k++) setup_manifold(w, &w->man[k], h);
 		for (uint32_t k = 0; k < w->nman; k++) warm_start(w, &w->man[w->order[k]]);
 		for (uint32_t it = 0; it < w->vel_steps; it++)

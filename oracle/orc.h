@@ -68,6 +68,8 @@ typedef struct orc_world orc_world;
 orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const float gravity[3],
 							uint32_t velocity_steps, uint32_t position_steps);
 void orc_world_destroy(orc_world *w);
+/* 0 (default): greedy colouring in canonical order, as the ensemble kernel; 1: hashed-priority rounds, as the wide-world kernels */
+void orc_world_set_mode(orc_world *w, int mode);
 /* static collision mesh = one static body; tris relative to (pos, rot) */
 uint32_t orc_static_add_mesh(orc_world *w, const float pos[3], const float rot[4], const float *tris, uint64_t ntris,
 							 float friction);

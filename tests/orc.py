@@ -99,6 +99,7 @@ def lib():
     L.orc_world_create.restype = C.c_void_p
     L.orc_world_create.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32]
     L.orc_world_destroy.argtypes = [C.c_void_p]
+    L.orc_world_set_mode.argtypes = [C.c_void_p, C.c_int]
     L.orc_static_add_mesh.restype = C.c_uint32
     L.orc_static_add_mesh.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,
                                       C.c_uint64, C.c_float]
@@ -127,11 +128,14 @@ class World:
     """One oracle world."""
 
     def __init__(self, max_bodies=64, max_manifolds=0, gravity=(0.0, -9.81, 0.0), velocity_steps=0,
-                 position_steps=0):
+                 position_steps=0, wide=None):
         self.L = lib()
         g = (C.c_float * 3)(*gravity)
         self.h = C.c_void_p(self.L.orc_world_create(max_bodies, max_manifolds, g, velocity_steps, position_steps))
         self.max_bodies = max_bodies
+        # the product switches to its wide-world kernels (hashed-priority colouring) above 64 bodies per world
+        if wide if wide is not None else max_bodies > 64:
+            self.L.orc_world_set_mode(self.h, 1)
 
     def close(self):
         if self.h:

