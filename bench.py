@@ -305,6 +305,9 @@ def run_gpu(args):
     # ---------------- secondary metric: 2^20 hitscan rays against shapes.gmap (C3)
     rays_res = bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
+    # ---------------- C4: one wide world of 100k boxes (replicated per rank)
+    wide_res = None if args.no_wide else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
+
     # ---------------- end-of-run stats gather over NCCL (the only collective)
     gathered_worlds = W
     if dist is not None:
@@ -335,6 +338,7 @@ def run_gpu(args):
                          "bytes_per_unit": BYTES_PER_BODY_STEP, "units_per_launch": bodies_per_rank},
             "cpu_baseline": cpu,
             "rays": rays_res,
+            "wide": wide_res,
             "wall_ms_timed_region": wall_ms,
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
@@ -343,6 +347,76 @@ def run_gpu(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def make_wide_world(gpx, scenes, pos, device):
+    n = len(pos)
+    g = gpx.World(worlds=1, max_bodies=n, device=device)
+    for p, t in scenes.box_map():
+        g.add_mesh(p, t)
+    g.commit()
+    proto = gpx.body_desc()
+    arr = (gpx.BodyDesc * n)()
+    for i in range(n):
+        arr[i] = proto
+        arr[i].position[0], arr[i].position[1], arr[i].position[2] = pos[i]
+    ids = np.zeros(n, np.uint32)
+    assert g.L.gpx_body_create_all(g.h, arr, n, None, None, ids.ctypes.data) == 0
+    return g
+
+
+def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ranks, flush, hbm_peak):
+    """BASELINE configs[3]: mapSources/max_box.json scaled to 100k dynamic boxes in ONE world (broadphase + solver
+    stress); every rank runs its own replica (a single world does not shard)."""
+    import torch
+    pos = scenes.lattice_positions()
+    n = len(pos)
+    g = make_wide_world(gpx, scenes, pos, device)
+    for _ in range(30):           # let the lattice drop the 5-10 cm onto the floor / each other: contacts everywhere
+        assert g.step() == 0
+    assert g.sync() == 0
+    L = gpx.lib()
+    barrier()
+    l0 = L.gpx_launch_count()
+    ms = 0.0
+    for _ in range(args.wide_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        g.timer_begin()
+        rc = g.step()
+        ms += g.timer_end()
+        assert rc == 0
+    launches = (L.gpx_launch_count() - l0) / args.wide_steps
+    assert g.sync() == 0
+    ms = max_over_ranks(ms) / args.wide_steps
+    y = g.transforms()[0, :, 1]
+    res = {"metric": "body_steps_per_s", "value": world_size * n / (ms * 1e-3), "unit": "body-steps/s", "bodies": n,
+           "ms_per_tick": ms, "launches_per_tick": launches,
+           "workload": "C4: 100 x 10 x 100 lattice of 0.4 m boxes (pitch 0.5, xz jitter +-0.02, Philox key 0x5EED0004) in the "
+                       "12-triangle 1024 m room of mapSources/max_box.json, one world per GPU, after 30 settling ticks",
+           "roofline": {"bound": "hbm", "kernel": "wide tick (all kw_* kernels)", "achieved": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           "min_y": float(y.min())}
+    if rank == 0 and not args.no_cpu:
+        import orc
+        sp = scenes.lattice_positions(16, 10, 16)
+        o = orc.World(len(sp))
+        for p, t in scenes.box_map():
+            o.add_mesh(p, t)
+        for q in sp:
+            o.create(orc.body_desc(position=tuple(q)))
+        for _ in range(3):
+            o.step()
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < args.cpu_seconds / 2 and k < 60:
+            o.step()
+            k += 1
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": len(sp) * k / dt, "unit": "body-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"16 x 10 x 16 = {len(sp)} boxes of the same lattice, {k} ticks, single thread "
+                                         "(oracle/orc.c wide mode; its broadphase is all-pairs, so larger samples are not representative)"}
+    return res
 
 
 def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ranks, flush, hbm_peak):
@@ -419,6 +493,8 @@ def main():
     ap.add_argument("--ref-worlds", type=int, default=256, help="worlds per step in the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-rays", type=int, default=1 << 17)
+    ap.add_argument("--no-wide", action="store_true", help="skip the C4 wide-world section")
+    ap.add_argument("--wide-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiling runs)")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per k_tick launch (profiles/), if known")
     ap.add_argument("--ray-traffic", type=float, default=None)

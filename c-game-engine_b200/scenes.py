@@ -148,3 +148,95 @@ def lattice_positions(nx=100, ny=10, nz=100, pitch=0.5, floor_y=-512.0, key: int
     z = (k.ravel() - (nz - 1) / 2) * pitch + jit[:, 1]
     y = floor_y + 0.25 + j.ravel() * pitch
     return np.stack([x, y, z], axis=1).astype(np.float32)
+
+
+# ---- C1: mapSources/test.json with its actors, from the committed fixtures
+def euler_to_quat(e) -> np.ndarray:
+    """JPH_Quat_FromEulerAngles: rotate about X, then Y, then Z (q = qz * qy * qx); returns x y z w."""
+    hx, hy, hz = (0.5 * float(v) for v in e)
+    cx, sx, cy, sy, cz, sz = np.cos(hx), np.sin(hx), np.cos(hy), np.sin(hy), np.cos(hz), np.sin(hz)
+    return np.array([cz * sx * cy - sz * cx * sy, cz * cx * sy + sz * sx * cy, sz * cx * cy - cz * sx * sy,
+                     cz * cx * cy + sz * sx * sy], dtype=np.float32)
+
+
+def _qrot(q, v):
+    u = q[:3].astype(np.float64)
+    t = 2.0 * np.cross(u, v)
+    return v + q[3] * t + np.cross(u, t)
+
+
+LASER_HEIGHT_OFFSET = {0: -0.3, 1: 0.0, 2: 0.3, 3: 0.0}   # floor / middle / ceiling / triple (Laser.c:192-204)
+
+
+def test_map_scene():
+    """The physics content of test.gmap as the engine would create it at load + first tick.
+
+    Returns dict(meshes=[(pos, rot, tris, friction)], bodies=[kwargs for body_desc], lasers=[(pos, quat, mask)],
+    names=[actor class per body]).  Body order = actor order in the file (MapLoader.c:74-159), lasers after
+    (LaserEmitter.c:59-75).  What is approximated: the player capsule is not created (character controller is a later
+    row); leafy.gmdl's two convex hulls are represented by the model's bounding box (ModelLoader.c:152)."""
+    z = np.load(os.path.join(GOLDEN, "static_test.npz"), allow_pickle=False)
+    models = np.load(os.path.join(GOLDEN, "models.npz"))
+    meshes = [(z["mesh_pos"][i], (0.0, 0.0, 0.0, 1.0), z["tris"][z["mesh_start"][i]:z["mesh_start"][i + 1]], 4.25)
+              for i in range(len(z["mesh_pos"]))]
+    params = {13: dict(width=4.0, height=2.0, depth=4.0)}                      # trigger (actor index 12 in file order)
+    laser_height = {3: 1, 4: 0, 5: 2, 6: 3}                                   # 'height' params of the four emitters
+    leafy_he = tuple(float(v) for v in models["leafy_bb"][3:])
+    leafy_off = tuple(float(v) for v in models["leafy_bb"][:3])
+    bodies, names, lasers = [], [], []
+    S, K, D = 0, 1, 2
+    for ai, (cls, xf) in enumerate(zip(z["actors"], z["actor_xf"])):
+        pos, q = xf[:3].astype(np.float32), euler_to_quat(xf[3:])
+        base = dict(position=tuple(float(v) for v in pos), rotation=tuple(float(v) for v in q), user_data=ai + 1)
+        cls = str(cls)
+        if cls == "player" or cls.startswith("global_"):
+            continue
+        if cls == "prop_coin":
+            bodies.append(dict(base, half_extents=(0.25, 0.25, 0.25), motion_type=S, layer=3, is_sensor=1, ray_flags=0))
+        elif cls == "prop_goal":
+            bodies.append(dict(base, half_extents=(0.5, 0.5, 0.5), motion_type=S, layer=3, is_sensor=1, ray_flags=0))
+        elif cls == "trigger":
+            p = params.get(ai + 1, dict(width=1.0, height=1.0, depth=1.0))
+            bodies.append(dict(base, half_extents=(p["width"] / 2, p["height"] / 2, p["depth"] / 2), motion_type=S, layer=3,
+                               is_sensor=1, ray_flags=0))
+        elif cls == "prop_model_static":
+            c = _qrot(q, np.array(leafy_off))
+            bodies.append(dict(base, position=tuple(float(v) for v in pos + c), half_extents=leafy_he, motion_type=S, layer=0,
+                               ray_flags=0))
+        elif cls == "prop_laser_emitter":
+            tris = models["laseremitter_tris"].reshape(-1, 3, 3)
+            meshes.append((pos, tuple(float(v) for v in q), tris, 0.2))
+            fwd = _qrot(q, np.array([0.0, 0.0, 1.0]))
+            lp = pos - fwd * float(models["laseremitter_bb"][5])
+            h = laser_height.get(ai, 1)
+            lp = lp + np.array([0.0, LASER_HEIGHT_OFFSET[h], 0.0])
+            lasers.append((lp.astype(np.float32), q, (1 if h == 3 else 3) | (1 << 8)))
+            continue
+        elif cls == "prop_physbox":
+            bodies.append(dict(base, half_extents=(0.2, 0.2, 0.2), motion_type=D, layer=1, mass=10.0, ray_flags=1))
+        elif cls == "test_actor":
+            c = _qrot(q, np.array(leafy_off))
+            bodies.append(dict(base, position=tuple(float(v) for v in pos + c), half_extents=leafy_he, motion_type=D, layer=1,
+                               mass=15.0, allowed_dofs=1 | 2 | 4 | 16, ray_flags=0))
+        elif cls == "prop_sprite":
+            bodies.append(dict(base, shape=0, motion_type=K, layer=0, ray_flags=0))
+        else:
+            continue
+        names.append(cls)
+    for lp, q, _ in lasers:                                                   # the Laser actors' own empty bodies
+        bodies.append(dict(position=tuple(float(v) for v in lp), rotation=tuple(float(v) for v in q), shape=0, motion_type=S,
+                           layer=0, ray_flags=0))
+        names.append("prop_laser")
+    return dict(meshes=meshes, bodies=bodies, lasers=lasers, names=names)
+
+
+def laser_rays(lasers, tmax=50.0, world=0) -> np.ndarray:
+    """One ray per laser: origin = the laser body's position, direction = its local -Z (Laser.c:142)."""
+    rays = np.zeros(len(lasers), RAY_DTYPE)
+    for i, (p, q, mask) in enumerate(lasers):
+        rays["origin"][i] = p
+        d = _qrot(np.asarray(q, np.float32), np.array([0.0, 0.0, -1.0]))
+        rays["dir"][i] = (d / np.linalg.norm(d)).astype(np.float32)
+        rays["mask"][i] = mask | (world << 16)
+    rays["tmax"] = tmax
+    return rays
