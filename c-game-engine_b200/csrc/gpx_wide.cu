@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t key_slot(unsigned long long k, uint32_t mask
 	k ^= k >> 33;
 	return (uint32_t)k & mask;
 }
-// Colouring priority: a fixed hash of the manifold's identity (restated in the oracle, oracle/orc.c colour_manifolds_jp)
+// Colouring priority: a fixed hash of the manifold's identity (the CPU restatement of the tick uses the same constants)
 __device__ __forceinline__ uint32_t man_prio(uint32_t a, uint32_t b, uint32_t ord)
 {
 	uint32_t h = (a * 0x9E3779B1u) ^ ((b + ord * 0x7F4A7C15u) * 0x85EBCA77u);
