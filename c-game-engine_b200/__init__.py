@@ -32,6 +32,7 @@ ERR_CUDA = 32
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmax", "<f4"), ("dir", "<f4", 3), ("mask", "<u4")])
 HIT_DTYPE = np.dtype([("fraction", "<f4"), ("body", "<u4"), ("face", "<u4"), ("world", "<u4")])
 TRANSFORM_DTYPE = np.dtype([("position", "<f4", 3), ("rotation", "<f4", 4)])
+EVENT_DTYPE = np.dtype([("world", "<u4"), ("body_a", "<u4"), ("body_b", "<u4"), ("kind", "<u4")])
 STATS_DTYPE = np.dtype([("kinetic_energy", "<f4"), ("max_speed", "<f4"), ("awake_bodies", "<u4"),
                         ("manifolds", "<u4"), ("position_checksum", "<u8"), ("ticks", "<u4"), ("error", "<u4")])
 
@@ -178,6 +179,8 @@ def lib() -> C.CDLL:
         "gpx_timer_end": (f32, [vp]),
         "gpx_launch_count": (u64, []),
         "gpx_debug_phase_cycles": (i32, [vp, i32, vp]),
+        "gpx_events_enable": (i32, [vp, i32]),
+        "gpx_poll_events": (i32, [vp, vp, u64, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -363,6 +366,22 @@ class World:
         out = np.zeros(16, np.uint64)
         _check(self.L.gpx_debug_phase_cycles(self.h, 1 if enable else 0, out.ctypes.data), "gpx_debug_phase_cycles")
         return {k: int(v) for k, v in zip(self.PHASES, out)}
+
+    def enable_events(self, on=True):
+        _check(self.L.gpx_events_enable(self.h, 1 if on else 0), "gpx_events_enable")
+
+    def poll_events(self) -> np.ndarray:
+        """Contact events of the last completed tick: records (world, body_a, body_b, kind)."""
+        cap = self.worlds * 64
+        while True:
+            out = np.zeros(cap, EVENT_DTYPE)
+            n = C.c_uint64(0)
+            rc = self.L.gpx_poll_events(self.h, out.ctypes.data, cap, C.byref(n))
+            if rc == 0:
+                return out[:n.value]
+            if rc != 17:
+                raise GpxError(f"gpx_poll_events failed ({rc})")
+            cap = int(n.value)
 
     def device_sync(self):
         _check(self.L.gpx_device_sync(self.h), "gpx_device_sync")

@@ -288,6 +288,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
 	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
+	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
@@ -766,6 +767,58 @@ int gpx_device_sync(gpx_world *w)
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;
 }
+int gpx_events_enable(gpx_world *w, int enable)
+{
+	if (!w || w->wide) return GPX_ERR_INVALID_ARG;  // the wide-world path does not report contact events yet
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	if (enable && !w->d_ev_out)
+	{
+		const size_t nm = (size_t)w->W * w->cap_m;
+		int rc;
+		if ((rc = dalloc(&w->d_ev_prev, nm)) != GPX_OK || (rc = dalloc(&w->d_ev_nprev, (size_t)w->W)) != GPX_OK ||
+			(rc = dalloc(&w->d_ev_count, (size_t)w->W)) != GPX_OK || (rc = dalloc(&w->d_ev_out, 2 * nm)) != GPX_OK)
+			return rc;
+	}
+	else if (!enable && w->d_ev_out)
+	{
+		cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
+		w->d_ev_prev = nullptr;
+		w->d_ev_nprev = w->d_ev_count = nullptr;
+		w->d_ev_out = nullptr;
+	}
+	return GPX_OK;
+}
+
+int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uint64_t *count)
+{
+	if (!w || !count || (capacity && !out)) return GPX_ERR_INVALID_ARG;
+	*count = 0;
+	std::lock_guard<std::mutex> lk(w->mu);
+	if (!w->d_ev_out) return GPX_ERR_INVALID_ARG;
+	cudaSetDevice(w->device);
+	const size_t per = 2u * (size_t)w->cap_m;
+	w->h_ev_count.resize(w->W);
+	w->h_ev_out.resize((size_t)w->W * per);
+	GPX_CUDA(cudaMemcpyAsync(w->h_ev_count.data(), w->d_ev_count, sizeof(uint32_t) * w->W, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(w->h_ev_out.data(), w->d_ev_out, sizeof(uint4) * w->h_ev_out.size(), cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	uint64_t n = 0;
+	for (uint32_t wi = 0; wi < w->W; wi++)
+		for (uint32_t k = 0; k < w->h_ev_count[wi] && k < per; k++, n++)
+			if (n < capacity)
+			{
+				const uint4 e = w->h_ev_out[wi * per + k];
+				out[n].world = wi;
+				out[n].body_a = e.x;
+				out[n].body_b = e.y;
+				out[n].kind = e.z;
+			}
+	*count = n;
+	return n > capacity ? GPX_ERR_CAPACITY : GPX_OK;
+}
+
 int gpx_debug_phase_cycles(gpx_world *w, int enable, uint64_t *out16)
 {
 	if (!w) return GPX_ERR_INVALID_ARG;

@@ -116,6 +116,12 @@ struct gpx_world
 	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors
 	uint32_t *m_err = nullptr;  // pinned
 	gpx_world_stats *d_stats = nullptr;
+	// contact events (gpx_events_enable)
+	unsigned long long *d_ev_prev = nullptr;
+	uint32_t *d_ev_nprev = nullptr, *d_ev_count = nullptr;
+	uint4 *d_ev_out = nullptr;
+	std::vector<uint4> h_ev_out;
+	std::vector<uint32_t> h_ev_count;
 	float4 *d_park = nullptr;  // 9 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
 	gpx::WideDevice *wide = nullptr;  // non-null: this world runs the wide-world kernels
 	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)

@@ -41,6 +41,11 @@ struct TickArgs
 	uint32_t *err;  // [0] OR of all worlds' errors, [1 + world] per world
 	float4 *con_park;  // 9 float4 per manifold slot: parked solver constants of worlds with more manifolds than lanes
 	uint4 *cand;  // per body 8 x uint4: {count, -, -, -}, {fat lo xyz, -}, {fat hi xyz, -}... see cand_* below
+	// contact events (gpx_events_enable): per world the sorted touching pairs of the previous tick and this tick's events
+	unsigned long long *ev_prev;
+	uint32_t *ev_nprev;
+	uint4 *ev_out;
+	uint32_t *ev_count;
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
 };
@@ -88,6 +93,11 @@ __host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
 	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
 	b += sizeof(uint32_t) * 8;              // header
 	return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ bool sensor_pair(const SMan &m, const SBody *bodies)
+{
+	return m.b < STATIC_BODY_BASE && ((bodies[m.a].flags | bodies[m.b].flags) & BF_SENSOR) != 0;
 }
 
 template <int TILE, int K, typename Tile>
@@ -258,7 +268,6 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 					if (!(fb & BF_ALIVE) || shape_of(fb) == GPX_SHAPE_EMPTY) continue;
 					if (!is_dynamic(fa) && !is_dynamic(fb)) continue;
 					if (!layers_collide(la, layer_of(fb))) continue;
-					if ((fa & BF_SENSOR) || (fb & BF_SENSOR)) continue;
 					if (!aabb_overlap(A.lo, A.hi, B.lo, B.hi, SPECULATIVE_DISTANCE)) continue;
 					mask |= 1ull << j;
 				}
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			// stage 1 (shared memory only, no early exits): first cached record with this manifold's key, and how many
 			const uint32_t mi = mi0 + lane;
 			SMan &m = man[mi < nman ? mi : 0];
-			const bool live = mi < nman && m.np > 0;
+			const bool live = mi < nman && m.np > 0 && !sensor_pair(m, bodies);
 			int j0 = -1, nmatch = 0;
 			for (uint32_t j = 0; j < nprev; j++)
 			{
@@ -418,6 +427,11 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				if (m.np == 0)
 				{
 					m.colour = -1;
+					continue;
+				}
+				if (sensor_pair(m, bodies))
+				{
+					m.colour = -3;  // touching, reported as a contact event, never solved
 					continue;
 				}
 				const bool a_dyn = is_dynamic(bodies[m.a].flags);
@@ -520,6 +534,56 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		tile.sync();
 		pc.mark(PH_CACHE);
 	}
+
+	// ---- contact events: touching pairs after the last sub-step (solver manifolds + sensor overlaps) against the
+	// previous tick's; canonical order = added/persisted sorted by (a, b), then removed sorted by (a, b)
+	if (a.ev_out && lane == 0)
+	{
+		unsigned long long *keys = reinterpret_cast<unsigned long long *>(scratch_raw);  // free after the last sub-step
+		const uint32_t nman = hdr[0];
+		uint32_t n = 0;
+		for (uint32_t mi = 0; mi < nman; mi++)
+		{
+			if (man[mi].np == 0) continue;
+			const unsigned long long key = ((unsigned long long)man[mi].a << 32) | man[mi].b;
+			uint32_t k = n;
+			bool dup = false;
+			while (k > 0 && keys[k - 1] >= key)
+			{
+				if (keys[k - 1] == key)
+				{
+					dup = true;
+					break;
+				}
+				k--;
+			}
+			if (dup) continue;
+			for (uint32_t t = n; t > k; t--) keys[t] = keys[t - 1];
+			keys[k] = key;
+			n++;
+		}
+		unsigned long long *prev = a.ev_prev + (size_t)world * cap_m;
+		const uint32_t np = a.ev_nprev[world];
+		uint4 *out = a.ev_out + (size_t)world * 2u * cap_m;
+		uint32_t e = 0, j = 0;
+		for (uint32_t i = 0; i < n; i++)
+		{
+			while (j < np && prev[j] < keys[i]) j++;
+			const bool persisted = j < np && prev[j] == keys[i];
+			out[e++] = make_uint4((uint32_t)(keys[i] >> 32), (uint32_t)(keys[i] & 0xFFFFFFFFull), persisted ? 2u : 1u, world);
+		}
+		uint32_t i = 0;
+		for (j = 0; j < np; j++)
+		{
+			while (i < n && keys[i] < prev[j]) i++;
+			if (i < n && keys[i] == prev[j]) continue;
+			out[e++] = make_uint4((uint32_t)(prev[j] >> 32), (uint32_t)(prev[j] & 0xFFFFFFFFull), 3u, world);
+		}
+		for (uint32_t t = 0; t < n; t++) prev[t] = keys[t];
+		a.ev_nprev[world] = n;
+		a.ev_count[world] = e;
+	}
+	tile.sync();
 
 	// ---- store: shared -> HBM
 	for (uint32_t i = lane; i < cap; i += TILE)
@@ -651,6 +715,10 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.err = w->d_err;
 	a.phase_cycles = w->d_phase;
 	a.cand = w->d_cand;
+	a.ev_prev = w->d_ev_prev;
+	a.ev_nprev = w->d_ev_nprev;
+	a.ev_out = w->d_ev_out;
+	a.ev_count = w->d_ev_count;
 	a.con_park = w->d_park;
 	a.p.worlds = w->W;
 	a.p.cap = w->cap;

@@ -218,6 +218,26 @@ int gpx_read_velocities(gpx_world *w, float *out_lin_ang6, uint64_t capacity);
 /* Per-world stats computed on device, `out` has `worlds` entries (host). */
 int gpx_read_stats(gpx_world *w, gpx_world_stats *out);
 
+/* ---- contact events ------------------------------------------------------------------------------------------------ */
+
+/* The listener the engine registers (JPH_CharacterContactListener: OnContactAdded / Persisted / Removed ->
+ * ActorDefinition::OnPlayerContact*, engine/src/physics/PlayerPhysics.c:89-152) becomes a polled list: after a tick,
+ * every pair of bodies that touches (solver contacts and sensor overlaps alike; body_b >= 0x400000 names a static
+ * map mesh) is reported as added, persisted or removed relative to the previous tick.  Order per world: added and
+ * persisted pairs sorted by (body_a, body_b), then removed pairs sorted the same way. */
+enum gpx_event_kind { GPX_EVENT_ADDED = 1, GPX_EVENT_PERSISTED = 2, GPX_EVENT_REMOVED = 3 };
+typedef struct gpx_contact_event
+{
+	uint32_t world;
+	uint32_t body_a; /* lower body id */
+	uint32_t body_b;
+	uint32_t kind;   /* gpx_event_kind */
+} gpx_contact_event;
+/* Events cost one pass per tick on the device and are off by default (ensemble worlds only, <= 64 bodies per world). */
+int gpx_events_enable(gpx_world *w, int enable);
+/* Waits for the stream and returns the events of the last completed tick; *count is the number available. */
+int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uint64_t *count);
+
 /* ---- ray queries -------------------------------------------------------------------------------------------------- */
 
 /* Batched closest-hit rays (JPH_NarrowPhaseQuery_CastRay_GAME / CastRay2_GAME; PlayerPhysics.c:305, Laser.c:142).

@@ -100,6 +100,11 @@ struct orc_world
 	manifold_t *man, *prev;
 	uint32_t nman, nprev;
 	uint32_t *order;
+	/* touching pairs for contact events: keys (a << 32 | b), sorted; sensors are kept apart from the solver's manifolds */
+	uint64_t *sens, *ev_cur, *ev_prev;
+	uint32_t nsens, nev_cur, nev_prev;
+	uint32_t *events; /* triples a, b, kind (1 added, 2 persisted, 3 removed) of the last tick */
+	uint32_t nevents;
 	int mode; /* 0: greedy colouring in canonical order (ensembles); 1: hashed-priority rounds (wide worlds) */
 };
 
@@ -118,6 +123,10 @@ orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const f
 	w->man = (manifold_t *)calloc(w->max_manifolds, sizeof(manifold_t));
 	w->prev = (manifold_t *)calloc(w->max_manifolds, sizeof(manifold_t));
 	w->order = (uint32_t *)calloc(w->max_manifolds, sizeof(uint32_t));
+	w->sens = (uint64_t *)calloc(w->max_manifolds, sizeof(uint64_t));
+	w->ev_cur = (uint64_t *)calloc(2 * w->max_manifolds, sizeof(uint64_t));
+	w->ev_prev = (uint64_t *)calloc(2 * w->max_manifolds, sizeof(uint64_t));
+	w->events = (uint32_t *)calloc(12 * w->max_manifolds, sizeof(uint32_t));
 	return w;
 }
 
@@ -132,6 +141,10 @@ void orc_world_destroy(orc_world *w)
 	free(w->man);
 	free(w->prev);
 	free(w->order);
+	free(w->sens);
+	free(w->ev_cur);
+	free(w->ev_prev);
+	free(w->events);
 	free(w);
 }
 
@@ -285,8 +298,9 @@ uint32_t orc_body_active(const orc_world *w, uint32_t id) { return id < w->max_b
 uint32_t orc_manifold_count(const orc_world *w) { return w->nprev; }
 uint32_t orc_events(const orc_world *w, uint32_t *out, uint32_t cap)
 {
-	(void)w; (void)out; (void)cap;
-	return 0;
+	uint32_t n = w->nevents < cap ? w->nevents : cap;
+	if (out) memcpy(out, w->events, (size_t)n * 3 * sizeof(uint32_t));
+	return w->nevents;
 }
 
 /* ------------------------------------------------------------------------------------------ rays */
@@ -985,6 +999,7 @@ static void store_points(manifold_t *m, const body_t *A, const body_t *B, int np
 static void find_contacts(orc_world *w, int *err)
 {
 	w->nman = 0;
+	w->nsens = 0;
 	for (uint32_t i = 0; i < w->max_bodies; i++)
 	{
 		body_t *A = &w->bodies[i];
@@ -1061,7 +1076,6 @@ static void find_contacts(orc_world *w, int *err)
 			if (!B->alive || B->shape == ORC_SHAPE_EMPTY) continue;
 			if (A->motion != ORC_MOTION_DYNAMIC && B->motion != ORC_MOTION_DYNAMIC) continue;
 			if (!layers_collide(A, B)) continue;
-			if (A->sensor || B->sensor) continue; /* sensors produce events only (not part of the solve) */
 			v3 blo, bhi;
 			body_aabb(B, &blo, &bhi);
 			if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) continue;
@@ -1085,6 +1099,12 @@ static void find_contacts(orc_world *w, int *err)
 				}
 			}
 			if (!hit) continue;
+			if (A->sensor || B->sensor)
+			{
+				/* sensors produce events only (not part of the solve) */
+				if (w->nsens < w->max_manifolds) w->sens[w->nsens++] = ((uint64_t)i << 32) | j;
+				continue;
+			}
 			prune_points(A->x, h.n, &h.np, h.p1, h.p2);
 			manifold_t *m = push_manifold(w, err);
 			if (!m) return;
@@ -1447,6 +1467,54 @@ static void solve_position(orc_world *w, manifold_t *m)
 	}
 }
 
+/* Contact events of the tick (the ContactListener / CharacterContactListener analogue, PlayerPhysics.c:89-152): the set
+ * of touching pairs after the last sub-step — solver manifolds and sensor overlaps — against the set of the previous
+ * tick.  Canonical order: added/persisted pairs sorted by (a, b), then removed pairs sorted by (a, b). */
+static int cmp_u64(const void *x, const void *y)
+{
+	uint64_t a = *(const uint64_t *)x, b = *(const uint64_t *)y;
+	return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+static void make_events(orc_world *w)
+{
+	uint32_t n = 0;
+	for (uint32_t i = 0; i < w->nprev; i++) w->ev_cur[n++] = ((uint64_t)w->prev[i].a << 32) | w->prev[i].b;
+	for (uint32_t i = 0; i < w->nsens; i++) w->ev_cur[n++] = w->sens[i];
+	qsort(w->ev_cur, n, sizeof(uint64_t), cmp_u64);
+	uint32_t m = 0;
+	for (uint32_t i = 0; i < n; i++)
+		if (m == 0 || w->ev_cur[m - 1] != w->ev_cur[i]) w->ev_cur[m++] = w->ev_cur[i];
+	w->nev_cur = m;
+	uint32_t e = 0, i = 0, j = 0;
+	/* added / persisted */
+	for (i = 0; i < w->nev_cur; i++)
+	{
+		while (j < w->nev_prev && w->ev_prev[j] < w->ev_cur[i]) j++;
+		int persisted = j < w->nev_prev && w->ev_prev[j] == w->ev_cur[i];
+		w->events[3 * e + 0] = (uint32_t)(w->ev_cur[i] >> 32);
+		w->events[3 * e + 1] = (uint32_t)(w->ev_cur[i] & 0xFFFFFFFFu);
+		w->events[3 * e + 2] = persisted ? 2u : 1u;
+		e++;
+	}
+	/* removed */
+	i = 0;
+	for (j = 0; j < w->nev_prev; j++)
+	{
+		while (i < w->nev_cur && w->ev_cur[i] < w->ev_prev[j]) i++;
+		if (i < w->nev_cur && w->ev_cur[i] == w->ev_prev[j]) continue;
+		w->events[3 * e + 0] = (uint32_t)(w->ev_prev[j] >> 32);
+		w->events[3 * e + 1] = (uint32_t)(w->ev_prev[j] & 0xFFFFFFFFu);
+		w->events[3 * e + 2] = 3u;
+		e++;
+	}
+	w->nevents = e;
+	uint64_t *t = w->ev_prev;
+	w->ev_prev = w->ev_cur;
+	w->ev_cur = t;
+	w->nev_prev = w->nev_cur;
+}
+
 static v3 clamp_len(v3 v, float maxl)
 {
 	float l2 = vlen2(v);
@@ -1501,6 +1569,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		w->man = t;
 		w->nprev = w->nman;
 	}
+	make_events(w);
 	return err;
 }
 

@@ -111,6 +111,8 @@ def lib():
     L.orc_step.restype = C.c_int
     L.orc_step.argtypes = [C.c_void_p, C.c_float, C.c_int]
     L.orc_body_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_events.restype = C.c_uint32
+    L.orc_events.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.orc_manifold_count.restype = C.c_uint32
     L.orc_manifold_count.argtypes = [C.c_void_p]
     L.orc_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -178,6 +180,13 @@ class World:
         for i in range(n):
             self.L.orc_body_get(self.h, i, xf[i].ctypes.data, vel[i].ctypes.data)
         return xf, vel
+
+    def events(self) -> np.ndarray:
+        """(n, 3) triples a, b, kind of the last tick."""
+        n = self.L.orc_events(self.h, None, 0)
+        out = np.zeros((n, 3), np.uint32)
+        self.L.orc_events(self.h, out.ctypes.data, n)
+        return out
 
     def manifolds(self) -> int:
         return self.L.orc_manifold_count(self.h)

@@ -1,0 +1,79 @@
+"""GPU parity: contact events (added / persisted / removed) through gpx_poll_events vs the oracle.
+
+The engine consumes such events as actor callbacks (OnPlayerContactAdded/Persisted/Removed,
+engine/src/physics/PlayerPhysics.c:89-152; coins, goals and triggers are sensor bodies: Coin.c:41-55, Trigger.c:33-50).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_box_falls_through_a_sensor_onto_the_floor(gpx, orc, scenes):
+    g = gpx.World(worlds=1, max_bodies=8)
+    o = orc.World(8)
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    descs = [dict(position=(0.0, 0.2, -1.5)),                                                        # falling box
+             dict(half_extents=(0.5, 0.15, 0.5), position=(0.0, -0.2, -1.5), layer=3, motion_type=0, is_sensor=1),  # trigger
+             dict(position=(0.0, -1.29, -1.5)),                                                      # box resting on the floor
+             dict(shape=2, half_extents=(0.2, 0, 0), position=(0.9, -1.0, -1.5))]                    # sphere beside it
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    seen = {1: set(), 2: set(), 3: set()}
+    for tick in range(1, 121):
+        assert g.step() == 0 and o.step() == 0
+        eg = g.poll_events()
+        eo = o.events()
+        got = np.stack([eg["body_a"], eg["body_b"], eg["kind"]], axis=1) if len(eg) else np.zeros((0, 3), np.uint32)
+        assert np.array_equal(got, eo), f"tick {tick}: events differ\n{got}\n{eo}"
+        assert (eg["world"] == 0).all()
+        for a, b, k in got:
+            seen[int(k)].add((int(a), int(b)))
+    # the falling box entered the sensor, left it again, landed on the resting box
+    assert (0, 1) in seen[1] and (0, 1) in seen[2] and (0, 1) in seen[3]
+    assert (0, 2) in seen[1] and (0, 2) in seen[2]
+    # resting box and sphere touch the floor mesh of sector 0 from the first tick on
+    assert any(a == 2 and b >= gpx.STATIC_BODY_BASE for a, b in seen[1])
+    assert any(a == 3 and b >= gpx.STATIC_BODY_BASE for a, b in seen[1])
+    # state parity is unaffected by event generation
+    assert np.array_equal(g.transforms()[0, :4].view(np.uint32), o.state(4)[0].view(np.uint32))
+
+
+def test_events_per_world_in_an_ensemble(gpx, orc, scenes):
+    W = 6
+    g = gpx.World(worlds=W, max_bodies=8)
+    os_ = [orc.World(8) for _ in range(W)]
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+        for o in os_:
+            o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    vel = scenes.ensemble_velocities(W, 8)
+    pos = scenes.stack_positions(8)
+    g.create_all([gpx.body_desc(position=tuple(p)) for p in pos], linvel=vel)
+    for wi, o in enumerate(os_):
+        for k in range(8):
+            o.create(orc.body_desc(position=tuple(pos[k]), linear_velocity=tuple(vel[wi, k])))
+    for tick in range(1, 31):
+        assert g.step() == 0
+        eg = g.poll_events()
+        for wi, o in enumerate(os_):
+            assert o.step() == 0
+            mine = eg[eg["world"] == wi]
+            got = np.stack([mine["body_a"], mine["body_b"], mine["kind"]], axis=1) if len(mine) else np.zeros((0, 3), np.uint32)
+            assert np.array_equal(got, o.events()), f"tick {tick} world {wi}"
+    assert len(eg) == W * 8 and (eg["kind"] == 2).all()     # settled column: 8 persisted contacts per world
+
+
+def test_events_must_be_enabled_and_are_refused_for_wide_worlds(gpx):
+    g = gpx.World(worlds=1, max_bodies=8)
+    with pytest.raises(gpx.GpxError):
+        g.poll_events()
+    w = gpx.World(worlds=1, max_bodies=128)
+    with pytest.raises(gpx.GpxError):
+        w.enable_events()
