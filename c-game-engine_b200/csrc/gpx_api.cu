@@ -243,6 +243,11 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	const size_t nb = (size_t)w->W * w->cap, nm = (size_t)w->W * w->cap_m;
 	bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+		 cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+		 cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && dalloc(&w->d_busy, (size_t)cfg->worlds) == GPX_OK && dalloc(&w->d_busy_n, 1) == GPX_OK &&
+		 dalloc(&w->d_busy_flag, (size_t)cfg->worlds) == GPX_OK;
 	ok = ok && dalloc(&w->bs.pos, nb) == GPX_OK && dalloc(&w->bs.quat, nb) == GPX_OK && dalloc(&w->bs.lin, nb) == GPX_OK &&
 		 dalloc(&w->bs.ang, nb) == GPX_OK && dalloc(&w->bs.prop0, nb) == GPX_OK && dalloc(&w->bs.prop1, nb) == GPX_OK &&
 		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK;
@@ -292,6 +297,10 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
+	if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+	if (w->ev_join) cudaEventDestroy(w->ev_join);
+	if (w->stream2) cudaStreamDestroy(w->stream2);
+	cudaFree(w->d_busy); cudaFree(w->d_busy_n); cudaFree(w->d_busy_flag);
 	if (w->stream) cudaStreamDestroy(w->stream);
 	delete w;
 }

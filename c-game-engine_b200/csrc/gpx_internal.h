@@ -89,7 +89,10 @@ struct gpx_world
 {
 	gpx_world_config cfg{};
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the 32-lane launch for busy worlds (gpx_tick.cu)
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	uint32_t *d_busy = nullptr, *d_busy_n = nullptr;
+	uint8_t *d_busy_flag = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint32_t W = 0, cap = 0, cap_m = 0;
 

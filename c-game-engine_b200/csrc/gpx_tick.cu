@@ -31,6 +31,8 @@ namespace cg = cooperative_groups;
 
 namespace gpx {
 
+constexpr uint32_t MAX_BUSY_WORLDS = 512;  // grid of the 32-lane launch; further busy worlds stay with the narrow launch
+
 struct TickArgs
 {
 	BodyStore bs;
@@ -46,6 +48,8 @@ struct TickArgs
 	uint32_t *ev_nprev;
 	uint4 *ev_out;
 	uint32_t *ev_count;
+	const uint32_t *busy_list, *busy_count;  // worlds routed to the 32-lane launch (that launch only)
+	const uint8_t *busy_flag;                // narrow launch: skip these worlds
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
 };
@@ -75,21 +79,20 @@ struct PhaseClock
 
 // One Scratch per lane while contacts are generated; once they are, the same bytes hold the keys of the previous
 // sub-step's manifolds (a, b, np) and the list of active manifolds.
-__host__ __device__ inline uint32_t tile_width(uint32_t cap) { return cap <= 8 ? 8u : (cap <= 16 ? 16u : 32u); }
-__host__ __device__ inline size_t world_scratch_bytes(uint32_t cap, uint32_t cap_m)
+__host__ __device__ inline size_t world_scratch_bytes(uint32_t tile, uint32_t cap_m)
 {
-	size_t a = sizeof(Scratch) * tile_width(cap), b = sizeof(uint32_t) * 4 * cap_m;
+	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 4 * cap_m;
 	return a > b ? a : b;
 }
 
-__host__ __device__ inline size_t world_smem_bytes(uint32_t cap, uint32_t cap_m)
+__host__ __device__ inline size_t world_smem_bytes(uint32_t tile, uint32_t cap, uint32_t cap_m)
 {
 	size_t b = 0;
 	b += sizeof(unsigned long long) * cap;  // per-body pair masks / colour sets (first: 8-byte aligned)
 	b += sizeof(SBody) * cap;
 	b += sizeof(SMan) * cap_m;
 	b += sizeof(uint32_t) * 2 * cap_m;      // pair list (a | slot << 16, b)
-	b += world_scratch_bytes(cap, cap_m);   // narrowphase polygon scratch, later the cached keys + the active list
+	b += world_scratch_bytes(tile, cap_m);  // narrowphase polygon scratch, later the cached keys + the active list
 	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
 	b += sizeof(uint32_t) * 8;              // header
 	return (b + 15) & ~(size_t)15;
@@ -161,11 +164,24 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	auto tile = cg::tiled_partition<TILE>(cg::this_thread_block());
 	const int lane = tile.thread_rank();
 	const uint32_t tiles_per_block = blockDim.x / TILE;
-	const uint32_t world = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
+	const uint32_t slot = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
 	const uint32_t cap = a.p.cap, cap_m = a.p.cap_m;
-	if (world >= a.p.worlds) return;  // whole tile exits together
+	// Worlds whose last tick ended with more manifolds than a narrow tile has lanes (a toppled column) are handed to a
+	// second launch of this kernel with 32 lanes per world, so they do not hold up the wave: a.busy_list != nullptr
+	// selects that launch; a.split_above > 0 makes the narrow launch skip them.
+	uint32_t world = slot;
+	if (a.busy_list)
+	{
+		if (slot >= min(*a.busy_count, MAX_BUSY_WORLDS)) return;
+		world = a.busy_list[slot];
+	}
+	else
+	{
+		if (world >= a.p.worlds) return;  // whole tile exits together
+		if (a.busy_flag && a.busy_flag[world]) return;
+	}
 
-	unsigned char *base = smem_raw + world_smem_bytes(cap, cap_m) * (threadIdx.x / TILE);
+	unsigned char *base = smem_raw + world_smem_bytes(TILE, cap, cap_m) * (threadIdx.x / TILE);
 	unsigned long long *pmask = reinterpret_cast<unsigned long long *>(base);
 	SBody *bodies = reinterpret_cast<SBody *>(pmask + cap);
 	SMan *man = reinterpret_cast<SMan *>(bodies + cap);
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	uint32_t *pkey_b = pkey_a + cap_m;
 	uint32_t *pkey_np = pkey_b + cap_m;
 	uint32_t *act = pkey_np + cap_m;
-	uint32_t *cnt_static = reinterpret_cast<uint32_t *>(scratch_raw + world_scratch_bytes(cap, cap_m));
+	uint32_t *cnt_static = reinterpret_cast<uint32_t *>(scratch_raw + world_scratch_bytes(TILE, cap_m));
 	uint32_t *slot_base = cnt_static + cap;
 	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
 
@@ -677,18 +693,37 @@ __global__ void k_stats(BodyStore bs, ManifoldCache mc, const uint32_t *err, uin
 	}
 }
 
+// list[0 .. n) = worlds for the 32-lane launch, flag[world] = 1 for exactly those
+__global__ void k_classify(const uint32_t *__restrict__ count, uint32_t worlds, uint32_t above, uint32_t *list, uint32_t *n,
+						   uint8_t *flag)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= worlds) return;
+	uint8_t f = 0;
+	if (count[i] > above)
+	{
+		const uint32_t k = atomicAdd(n, 1u);
+		if (k < MAX_BUSY_WORLDS)
+		{
+			list[k] = i;
+			f = 1;
+		}
+	}
+	flag[i] = f;
+}
+
 template <int TILE>
-static int launch_tick_t(gpx_world *w, const TickArgs &a)
+static int launch_tick_t(gpx_world *w, const TickArgs &a, cudaStream_t stream, uint32_t grid_worlds)
 {
 	// one warp per block (32 / TILE worlds): the finest granularity for spreading 4096 worlds over 148 SMs in ONE wave
-	const size_t per_world = world_smem_bytes(w->cap, w->cap_m);
+	const size_t per_world = world_smem_bytes(TILE, w->cap, w->cap_m);
 	const size_t budget = 200u * 1024u;
 	if (per_world > budget) return GPX_ERR_CAPACITY;
 	uint32_t wpb = 32 / TILE;
 	while (wpb > 1 && per_world * wpb > budget) wpb >>= 1;
 	const uint32_t threads = wpb * TILE;
 	const size_t smem = per_world * wpb;
-	static size_t configured = 0;
+	static size_t configured = 0;  // per instantiation
 	if (smem > configured)
 	{
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -697,8 +732,8 @@ static int launch_tick_t(gpx_world *w, const TickArgs &a)
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
 		configured = smem;
 	}
-	const uint32_t grid = (w->W + wpb - 1) / wpb;
-	k_tick<TILE><<<grid, threads, smem, w->stream>>>(a);
+	const uint32_t grid = (grid_worlds + wpb - 1) / wpb;
+	k_tick<TILE><<<grid, threads, smem, stream>>>(a);
 	count_launch();
 	GPX_CUDA(cudaGetLastError());
 	return GPX_OK;
@@ -731,9 +766,27 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	if (substeps < 1) substeps = 1;
 	a.p.substeps = substeps;
 	a.p.h = dt / (float)substeps;
-	if (w->cap <= 8) return launch_tick_t<8>(w, a);
-	if (w->cap <= 16) return launch_tick_t<16>(w, a);
-	return launch_tick_t<32>(w, a);
+	a.busy_list = a.busy_count = nullptr;
+	a.busy_flag = nullptr;
+	if (w->cap > 16 || w->W < 64) return launch_tick_t<32>(w, a, w->stream, w->W);
+	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane
+	// launch on a second stream takes the rest; both read the same per-world counts, so each world runs exactly once.
+	const uint32_t tile = w->cap <= 8 ? 8u : 16u;
+	int rc;
+	GPX_CUDA(cudaMemsetAsync(w->d_busy_n, 0, sizeof(uint32_t), w->stream));
+	k_classify<<<(w->W + 255) / 256, 256, 0, w->stream>>>(w->mc.count, w->W, tile, w->d_busy, w->d_busy_n, w->d_busy_flag);
+	count_launch();
+	GPX_CUDA(cudaEventRecord(w->ev_fork, w->stream));
+	GPX_CUDA(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
+	TickArgs b = a;
+	b.busy_list = w->d_busy;
+	b.busy_count = w->d_busy_n;
+	if ((rc = launch_tick_t<32>(w, b, w->stream2, w->W < MAX_BUSY_WORLDS ? w->W : MAX_BUSY_WORLDS)) != GPX_OK) return rc;
+	GPX_CUDA(cudaEventRecord(w->ev_join, w->stream2));
+	a.busy_flag = w->d_busy_flag;
+	rc = tile == 8u ? launch_tick_t<8>(w, a, w->stream, w->W) : launch_tick_t<16>(w, a, w->stream, w->W);
+	GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+	return rc;
 }
 
 int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n)
