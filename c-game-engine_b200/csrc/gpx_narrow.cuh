@@ -31,6 +31,7 @@ constexpr int MAX_TRI_CANDIDATES = 24;       // triangles whose box overlaps one
 struct Scratch
 {
 	v3 buf[2][MAX_POLY];
+	float pad;  // 49 words: an odd stride keeps lanes (lane = record) on distinct shared-memory banks
 };
 
 struct Hit

@@ -36,7 +36,11 @@ struct SMan  // 49 words (odd stride): what outlives one manifold's register-res
 	float bias[4];
 };
 
-// One manifold's constraint rows, register-resident while its lane iterates (phase 7).
+// One manifold's constraint rows while its lane iterates (phase 7).  The per-manifold part lives in registers; the
+// per-point part (lever arms, effective masses) in a small per-lane record in shared memory so that the four points
+// run through ONE rolled loop body — fully unrolled, the velocity iteration alone was ~18 KB of SASS and the warps
+// spent a third of their time waiting for instruction fetch.  Accumulated impulses and biases are read and written
+// in place in the manifold record.
 struct Con
 {
 	uint32_t ia, ib;
@@ -47,10 +51,12 @@ struct Con
 	int np;
 	float friction;
 	v3 n, t1, t2;
+};
+
+struct ConPts  // 36 words
+{
 	v3 r1[4], r2[4];
 	float em[4][3];
-	float bias[4];
-	float ln[4], lt1[4], lt2[4];
 };
 
 
@@ -288,24 +294,24 @@ struct Vel
 	v3 va, wa, vb, wb;
 };
 
-__device__ __forceinline__ v3 rel_vel(const Con &c, const Vel &u, int k)
+__device__ __forceinline__ v3 rel_vel(const Con &c, const Vel &u, v3 r1, v3 r2)
 {
-	v3 ua = u.va + cross(u.wa, c.r1[k]);
+	v3 ua = u.va + cross(u.wa, r1);
 	if (!c.has_b) return ua;
-	return ua - (u.vb + cross(u.wb, c.r2[k]));
+	return ua - (u.vb + cross(u.wb, r2));
 }
 
-__device__ __forceinline__ void apply_impulse(const Con &c, Vel &u, int k, v3 P)
+__device__ __forceinline__ void apply_impulse(const Con &c, Vel &u, v3 r1, v3 r2, v3 P)
 {
 	if (c.a_dyn)
 	{
 		u.va = u.va - mask_lin(c.a_dofs, P * c.ima);
-		u.wa = u.wa - sym_mul(c.MA, cross(c.r1[k], P));
+		u.wa = u.wa - sym_mul(c.MA, cross(r1, P));
 	}
 	if (c.has_b && c.b_dyn)
 	{
 		u.vb = u.vb + mask_lin(c.b_dofs, P * c.imb);
-		u.wb = u.wb + sym_mul(c.MB, cross(c.r2[k], P));
+		u.wb = u.wb + sym_mul(c.MB, cross(r2, P));
 	}
 }
 
@@ -336,10 +342,8 @@ __device__ __forceinline__ void store_vel(const Con &c, SBody *bodies, const Vel
 	}
 }
 
-// Constraint set-up of one manifold (reads body state only).  FIRST: also derives the speculative / restitution bias
-// and parks it in the shared record; later rebuilds (worlds with more manifolds than lanes) read it back.
-template <bool FIRST>
-__device__ __forceinline__ void build_con(Con &c, SMan &m, const SBody *bodies, float h)
+// Per-manifold part of the constraint set-up (reads body state only)
+__device__ __forceinline__ void con_header(Con &c, const SMan &m, const SBody *bodies)
 {
 	const SBody &A = bodies[m.a];
 	c.ia = m.a;
@@ -363,144 +367,85 @@ __device__ __forceinline__ void build_con(Con &c, SMan &m, const SBody *bodies, 
 	c.n = m.n;
 	c.t1 = vperp(c.n);
 	c.t2 = cross(c.n, c.t1);
+}
+
+// Full set-up of one manifold: header + per-point lever arms / effective masses into `pt`, and the speculative /
+// restitution bias into the manifold record.
+__device__ __forceinline__ void build_con(Con &c, ConPts &pt, SMan &m, const SBody *bodies, float h)
+{
+	con_header(c, m, bodies);
+	const SBody &A = bodies[c.ia], &B = bodies[c.ib];
 	const v3 ax = A.x, bx = B.x;
 	const q4 aq = A.q, bq = B.q;
 	Vel u;
-	if (FIRST) load_vel(c, bodies, u);
-#pragma unroll
-	for (int k = 0; k < 4; k++)
+	load_vel(c, bodies, u);
+#pragma unroll 1
+	for (int k = 0; k < c.np; k++)
 	{
-		if (k < c.np)
+		v3 p1 = ax + qrot(aq, m.p1l[k]);
+		v3 p2 = c.has_b ? bx + qrot(bq, m.p2l[k]) : m.p2l[k];
+		v3 mid = (p1 + p2) * 0.5f;
+		const v3 r1 = mid - ax;
+		const v3 r2 = c.has_b ? mid - bx : V(0.0f, 0.0f, 0.0f);
+		pt.r1[k] = r1;
+		pt.r2[k] = r2;
+		pt.em[k][0] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.n);
+		pt.em[k][1] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.t1);
+		pt.em[k][2] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.t2);
+		float pen = dot(p1 - p2, c.n);
+		float bias = fmaxf(0.0f, -pen / h);
+		if (m.restitution > 0.0f)
 		{
-			v3 p1 = ax + qrot(aq, m.p1l[k]);
-			v3 p2 = c.has_b ? bx + qrot(bq, m.p2l[k]) : m.p2l[k];
-			v3 mid = (p1 + p2) * 0.5f;
-			c.r1[k] = mid - ax;
-			c.r2[k] = c.has_b ? mid - bx : V(0.0f, 0.0f, 0.0f);
-			c.em[k][0] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.n);
-			c.em[k][1] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.t1);
-			c.em[k][2] = eff_mass(c.ima, c.MA, c.imb, c.MB, c.r1[k], c.r2[k], c.t2);
-			if (FIRST)
-			{
-				float pen = dot(p1 - p2, c.n);
-				float bias = fmaxf(0.0f, -pen / h);
-				if (m.restitution > 0.0f)
-				{
-					float nv = -dot(c.n, rel_vel(c, u, k));
-					if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
-				}
-				c.bias[k] = bias;
-				m.bias[k] = bias;
-			}
-			else
-				c.bias[k] = m.bias[k];
-			c.ln[k] = m.ln[k];
-			c.lt1[k] = m.lt1[k];
-			c.lt2[k] = m.lt2[k];
+			float nv = -dot(c.n, rel_vel(c, u, r1, r2));
+			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
 		}
-		else
-		{
-			c.r1[k] = c.r2[k] = V(0.0f, 0.0f, 0.0f);
-			c.em[k][0] = c.em[k][1] = c.em[k][2] = 0.0f;
-			c.bias[k] = c.ln[k] = c.lt1[k] = c.lt2[k] = 0.0f;
-		}
+		m.bias[k] = bias;
 	}
 }
 
-__device__ __forceinline__ void store_lambdas(const Con &c, SMan &m)
+// ConPts <-> 9 float4 in global memory (worlds with more manifolds than lanes; the wide-world kernels)
+__device__ __forceinline__ void park_con(const ConPts &pt, float4 *g)
 {
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		if (k < c.np)
-		{
-			m.ln[k] = c.ln[k];
-			m.lt1[k] = c.lt1[k];
-			m.lt2[k] = c.lt2[k];
-		}
-}
-
-// r1, r2, em of the four points <-> 9 float4 in global memory (worlds with more manifolds than lanes)
-__device__ __forceinline__ void park_con(const Con &c, float4 *g)
-{
-	float f[36];
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-	{
-		f[9 * k + 0] = c.r1[k].x; f[9 * k + 1] = c.r1[k].y; f[9 * k + 2] = c.r1[k].z;
-		f[9 * k + 3] = c.r2[k].x; f[9 * k + 4] = c.r2[k].y; f[9 * k + 5] = c.r2[k].z;
-		f[9 * k + 6] = c.em[k][0]; f[9 * k + 7] = c.em[k][1]; f[9 * k + 8] = c.em[k][2];
-	}
+	const float *f = reinterpret_cast<const float *>(&pt);
 #pragma unroll
 	for (int i = 0; i < 9; i++) __stcg(&g[i], make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
 }
 
-__device__ __forceinline__ void unpark_con(Con &c, const SMan &m, const SBody *bodies, const float4 *g)
+__device__ __forceinline__ void unpark_con(ConPts &pt, const float4 *g)
 {
-	float f[36];
+	float *f = reinterpret_cast<float *>(&pt);
 #pragma unroll
 	for (int i = 0; i < 9; i++)
 	{
 		const float4 v = __ldcg(&g[i]);
 		f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
 	}
-	const SBody &A = bodies[m.a];
-	c.ia = m.a;
-	c.has_b = m.b < STATIC_BODY_BASE;
-	c.ib = c.has_b ? m.b : m.a;
-	const SBody &B = bodies[c.ib];
-	c.a_dyn = is_dynamic(A.flags);
-	c.b_dyn = c.has_b && is_dynamic(B.flags);
-	c.a_dofs = dofs_of(A.flags);
-	c.b_dofs = dofs_of(B.flags);
-	c.ima = A.im;
-	c.imb = c.has_b ? B.im : 0.0f;
-#pragma unroll
-	for (int k = 0; k < 6; k++)
-	{
-		c.MA[k] = A.M[k];
-		c.MB[k] = c.has_b ? B.M[k] : 0.0f;
-	}
-	c.np = m.np;
-	c.friction = m.friction;
-	c.n = m.n;
-	c.t1 = vperp(c.n);
-	c.t2 = cross(c.n, c.t1);
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-	{
-		c.r1[k] = V(f[9 * k + 0], f[9 * k + 1], f[9 * k + 2]);
-		c.r2[k] = V(f[9 * k + 3], f[9 * k + 4], f[9 * k + 5]);
-		c.em[k][0] = f[9 * k + 6]; c.em[k][1] = f[9 * k + 7]; c.em[k][2] = f[9 * k + 8];
-		c.bias[k] = m.bias[k];
-		c.ln[k] = m.ln[k];
-		c.lt1[k] = m.lt1[k];
-		c.lt2[k] = m.lt2[k];
-	}
 }
 
-__device__ __forceinline__ void warm_start(const Con &c, Vel &u)
+__device__ __forceinline__ void warm_start(const Con &c, const ConPts &pt, const SMan &m, Vel &u)
 {
-#pragma unroll
-	for (int k = 0; k < 4; k++)
+#pragma unroll 1
+	for (int k = 0; k < c.np; k++)
 	{
-		if (k >= c.np) continue;
-		if (c.ln[k] == 0.0f && c.lt1[k] == 0.0f && c.lt2[k] == 0.0f) continue;
-		v3 P = ((c.n * c.ln[k]) + (c.t1 * c.lt1[k])) + (c.t2 * c.lt2[k]);
-		apply_impulse(c, u, k, P);
+		const float ln = m.ln[k], lt1 = m.lt1[k], lt2 = m.lt2[k];
+		if (ln == 0.0f && lt1 == 0.0f && lt2 == 0.0f) continue;
+		v3 P = ((c.n * ln) + (c.t1 * lt1)) + (c.t2 * lt2);
+		apply_impulse(c, u, pt.r1[k], pt.r2[k], P);
 	}
 }
 
-__device__ __forceinline__ void solve_velocity(Con &c, Vel &u)
+__device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, SMan &m, Vel &u)
 {
 	// friction first: non-penetration is more important, so it goes last
-#pragma unroll
-	for (int k = 0; k < 4; k++)
+#pragma unroll 1
+	for (int k = 0; k < c.np; k++)
 	{
-		if (k >= c.np) continue;
-		v3 rv = rel_vel(c, u, k);
-		float l1 = c.lt1[k] + (c.em[k][1] * dot(c.t1, rv));
-		float l2 = c.lt2[k] + (c.em[k][2] * dot(c.t2, rv));
-		float maxf = c.friction * c.ln[k];
+		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
+		const float o1 = m.lt1[k], o2 = m.lt2[k];
+		v3 rv = rel_vel(c, u, r1, r2);
+		float l1 = o1 + (pt.em[k][1] * dot(c.t1, rv));
+		float l2 = o2 + (pt.em[k][2] * dot(c.t2, rv));
+		float maxf = c.friction * m.ln[k];
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
@@ -508,21 +453,22 @@ __device__ __forceinline__ void solve_velocity(Con &c, Vel &u)
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
-		v3 P = (c.t1 * (l1 - c.lt1[k])) + (c.t2 * (l2 - c.lt2[k]));
-		c.lt1[k] = l1;
-		c.lt2[k] = l2;
-		apply_impulse(c, u, k, P);
+		v3 P = (c.t1 * (l1 - o1)) + (c.t2 * (l2 - o2));
+		m.lt1[k] = l1;
+		m.lt2[k] = l2;
+		apply_impulse(c, u, r1, r2, P);
 	}
-#pragma unroll
-	for (int k = 0; k < 4; k++)
+#pragma unroll 1
+	for (int k = 0; k < c.np; k++)
 	{
-		if (k >= c.np) continue;
-		v3 rv = rel_vel(c, u, k);
-		float lambda = c.em[k][0] * (dot(c.n, rv) - c.bias[k]);
-		float nt = fmaxf(0.0f, c.ln[k] + lambda);
-		lambda = nt - c.ln[k];
-		c.ln[k] = nt;
-		apply_impulse(c, u, k, c.n * lambda);
+		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
+		const float old = m.ln[k];
+		v3 rv = rel_vel(c, u, r1, r2);
+		float lambda = pt.em[k][0] * (dot(c.n, rv) - m.bias[k]);
+		float nt = fmaxf(0.0f, old + lambda);
+		lambda = nt - old;
+		m.ln[k] = nt;
+		apply_impulse(c, u, r1, r2, c.n * lambda);
 	}
 }
 

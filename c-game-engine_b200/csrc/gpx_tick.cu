@@ -81,7 +81,7 @@ struct PhaseClock
 // sub-step's manifolds (a, b, np) and the list of active manifolds.
 __host__ __device__ inline size_t world_scratch_bytes(uint32_t tile, uint32_t cap_m)
 {
-	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 4 * cap_m;
+	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 3 * cap_m;
 	return a > b ? a : b;
 }
 
@@ -92,6 +92,7 @@ __host__ __device__ inline size_t world_smem_bytes(uint32_t tile, uint32_t cap, 
 	b += sizeof(SBody) * cap;
 	b += sizeof(SMan) * cap_m;
 	b += sizeof(uint32_t) * 2 * cap_m;      // pair list (a | slot << 16, b)
+	b += sizeof(uint32_t) * cap_m;          // active manifolds in canonical order
 	b += world_scratch_bytes(tile, cap_m);  // narrowphase polygon scratch, later the cached keys + the active list
 	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
 	b += sizeof(uint32_t) * 8;              // header
@@ -103,58 +104,48 @@ __device__ __forceinline__ bool sensor_pair(const SMan &m, const SBody *bodies)
 	return m.b < STATIC_BODY_BASE && ((bodies[m.a].flags | bodies[m.b].flags) & BF_SENSOR) != 0;
 }
 
-template <int TILE, int K, typename Tile>
-__device__ __forceinline__ void solve_in_registers(Tile &tile, int lane, SMan *man, const uint32_t *act, uint32_t nact,
-												   SBody *bodies, int ncol, uint32_t vel_steps, float h, PhaseClock &pc)
+// Velocity solve with one lane per active manifold: set-up once, warm start, then the iterations; per colour a lane
+// pulls its bodies' velocities from shared memory, runs its rows and pushes them back.
+template <int TILE, typename Tile>
+__device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *man, const uint32_t *act, uint32_t nact,
+												   SBody *bodies, ConPts &pt, int ncol, uint32_t vel_steps, float h,
+												   PhaseClock &pc)
 {
-	Con c[K];
-	int colour[K];
-	uint32_t slot[K];
-#pragma unroll
-	for (int s = 0; s < K; s++)
+	const bool mine = (uint32_t)lane < nact;
+	SMan &m = man[mine ? act[lane] : 0];
+	Con c;
+	int colour = -1;
+	tile.sync();  // the cached keys that share `pt`'s bytes are dead from here on
+	if (mine)
 	{
-		const uint32_t k = (uint32_t)s * TILE + lane;
-		colour[s] = -1;
-		slot[s] = 0;
-		if (k < nact)
-		{
-			slot[s] = act[k];
-			build_con<true>(c[s], man[slot[s]], bodies, h);
-			colour[s] = man[slot[s]].colour;
-		}
+		build_con(c, pt, m, bodies, h);
+		colour = m.colour;
 	}
 	pc.mark(PH_SETUP);
 	for (int col = 0; col < ncol; col++)
 	{
-#pragma unroll
-		for (int s = 0; s < K; s++)
-			if (colour[s] == col)
-			{
-				Vel u;
-				load_vel(c[s], bodies, u);
-				warm_start(c[s], u);
-				store_vel(c[s], bodies, u);
-			}
+		if (colour == col)
+		{
+			Vel u;
+			load_vel(c, bodies, u);
+			warm_start(c, pt, m, u);
+			store_vel(c, bodies, u);
+		}
 		tile.sync();
 	}
 	pc.mark(PH_WARM);
 	for (uint32_t it = 0; it < vel_steps; it++)
 		for (int col = 0; col < ncol; col++)
 		{
-#pragma unroll
-			for (int s = 0; s < K; s++)
-				if (colour[s] == col)
-				{
-					Vel u;
-					load_vel(c[s], bodies, u);
-					solve_velocity(c[s], u);
-					store_vel(c[s], bodies, u);
-				}
+			if (colour == col)
+			{
+				Vel u;
+				load_vel(c, bodies, u);
+				solve_velocity(c, pt, m, u);
+				store_vel(c, bodies, u);
+			}
 			tile.sync();
 		}
-#pragma unroll
-	for (int s = 0; s < K; s++)
-		if (colour[s] >= 0) store_lambdas(c[s], man[slot[s]]);
 }
 
 template <int TILE>
@@ -187,12 +178,15 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	SMan *man = reinterpret_cast<SMan *>(bodies + cap);
 	uint32_t *pair_a = reinterpret_cast<uint32_t *>(man + cap_m);
 	uint32_t *pair_b = pair_a + cap_m;
-	unsigned char *scratch_raw = reinterpret_cast<unsigned char *>(pair_b + cap_m);
+	uint32_t *act = pair_b + cap_m;
+	// One region, three lives per sub-step: a polygon Scratch per lane while contacts are generated; the cached keys
+	// during the warm-start match; a ConPts per lane during the velocity solve.
+	unsigned char *scratch_raw = reinterpret_cast<unsigned char *>(act + cap_m);
 	Scratch &scratch = reinterpret_cast<Scratch *>(scratch_raw)[lane];
-	uint32_t *pkey_a = reinterpret_cast<uint32_t *>(scratch_raw);  // aliases the scratch: live from phase 5 on
+	ConPts &conpts = *reinterpret_cast<ConPts *>(&scratch);
+	uint32_t *pkey_a = reinterpret_cast<uint32_t *>(scratch_raw);
 	uint32_t *pkey_b = pkey_a + cap_m;
 	uint32_t *pkey_np = pkey_b + cap_m;
-	uint32_t *act = pkey_np + cap_m;
 	uint32_t *cnt_static = reinterpret_cast<uint32_t *>(scratch_raw + world_scratch_bytes(TILE, cap_m));
 	uint32_t *slot_base = cnt_static + cap;
 	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
@@ -473,17 +467,18 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 		// ---- 7: set-up, warm start, velocity iterations; within a colour no two manifolds share a dynamic body
 		if (nact <= (uint32_t)TILE)
-			solve_in_registers<TILE, 1>(tile, lane, man, act, nact, bodies, ncol, a.p.vel_steps, h, pc);
+			solve_one_per_lane<TILE>(tile, lane, man, act, nact, bodies, conpts, ncol, a.p.vel_steps, h, pc);
 		else
 		{
 			// more manifolds than lanes: a lane revisits several manifolds, so the per-point constants (lever arms,
 			// effective masses) are parked in an L2-resident scratch record and pulled back each visit
 			float4 *park = a.con_park + 9ull * m0;
+			tile.sync();  // the cached keys that share `conpts`' bytes are dead from here on
 			for (uint32_t k = lane; k < nact; k += TILE)
 			{
 				Con c;
-				build_con<true>(c, man[act[k]], bodies, h);
-				park_con(c, park + 9ull * act[k]);
+				build_con(c, conpts, man[act[k]], bodies, h);
+				park_con(conpts, park + 9ull * act[k]);
 			}
 			__threadfence_block();
 			tile.sync();
@@ -495,15 +490,15 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 						SMan &m = man[act[k]];
 						if (m.colour != col) continue;
 						Con c;
-						unpark_con(c, m, bodies, park + 9ull * act[k]);
+						con_header(c, m, bodies);
+						unpark_con(conpts, park + 9ull * act[k]);
 						Vel u;
 						load_vel(c, bodies, u);
 						if (it == 0)
-							warm_start(c, u);
+							warm_start(c, conpts, m, u);
 						else
-							solve_velocity(c, u);
+							solve_velocity(c, conpts, m, u);
 						store_vel(c, bodies, u);
-						store_lambdas(c, m);
 					}
 					tile.sync();
 				}
@@ -556,6 +551,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	if (a.ev_out && lane == 0)
 	{
 		unsigned long long *keys = reinterpret_cast<unsigned long long *>(scratch_raw);  // free after the last sub-step
+		static_assert(sizeof(Scratch) >= sizeof(ConPts), "per-lane scratch must hold the solver's per-point record");
 		const uint32_t nman = hdr[0];
 		uint32_t n = 0;
 		for (uint32_t mi = 0; mi < nman; mi++)

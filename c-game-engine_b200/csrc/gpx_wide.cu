@@ -457,12 +457,14 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 	const int ncol = (int)a.cnt[WC_NCOL];
 	const float h = a.h;
 	// set-up: lever arms, effective masses, bias; parked next to the manifold
+	__shared__ ConPts pts[256];
+	ConPts &pt = pts[threadIdx.x];
 	for (uint32_t k = tid; k < nact; k += stride)
 	{
 		const uint32_t mi = a.col_list[k];
 		Con c;
-		build_con<true>(c, a.man[mi], a.bodies, h);
-		park_con(c, a.park + 9ull * mi);
+		build_con(c, pt, a.man[mi], a.bodies, h);
+		park_con(pt, a.park + 9ull * mi);
 	}
 	grid.sync();
 	// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
@@ -476,15 +478,15 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 				const uint32_t mi = a.col_list[k];
 				SMan &m = a.man[mi];
 				Con c;
-				unpark_con(c, m, a.bodies, a.park + 9ull * mi);
+				con_header(c, m, a.bodies);
+				unpark_con(pt, a.park + 9ull * mi);
 				Vel u;
 				load_vel(c, a.bodies, u);
 				if (it == 0)
-					warm_start(c, u);
+					warm_start(c, pt, m, u);
 				else
-					solve_velocity(c, u);
+					solve_velocity(c, pt, m, u);
 				store_vel(c, a.bodies, u);
-				store_lambdas(c, m);
 			}
 			grid.sync();
 		}
