@@ -1,6 +1,8 @@
 // gpx_math.cuh — fp32 vector helpers for the sm_100a kernels.
-// Compiled with -fmad=false: every expression is parenthesised so the rounding sequence is fixed and the kernels
-// are reproducible run to run and comparable bit-for-bit with a scalar evaluation of the same formulas.
+// Compiled with -fmad=false: the compiler never contracts on its own, every expression is parenthesised, and the
+// fused multiply-adds that matter (dot, cross, matrix-vector, quaternion products: about a third of the tick's fp32
+// instructions) are written out as fmaf().  The rounding sequence is therefore fixed and the kernels are reproducible
+// run to run and comparable bit-for-bit with a scalar evaluation of the same formulas.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,31 +20,33 @@ GPX_HD v3 operator+(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
 GPX_HD v3 operator-(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
 GPX_HD v3 operator-(v3 a) { return V(-a.x, -a.y, -a.z); }
 GPX_HD v3 operator*(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
-GPX_HD float dot(v3 a, v3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); }
+GPX_HD float dot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 GPX_HD v3 cross(v3 a, v3 b)
 {
-	return V((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+	return V(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 GPX_HD float len2(v3 a) { return dot(a, a); }
 GPX_HD float len(v3 a) { return sqrtf(dot(a, a)); }
 GPX_HD float get(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 GPX_HD v3 mulc(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+// v + t * s
+GPX_HD v3 madd(v3 v, v3 t, float s) { return V(fmaf(t.x, s, v.x), fmaf(t.y, s, v.y), fmaf(t.z, s, v.z)); }
 GPX_HD float4 F4(v3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
 
 GPX_HD v3 qrot(q4 q, v3 v)
 {
 	v3 u = V(q.x, q.y, q.z);
 	v3 t = cross(u, v) * 2.0f;
-	return (v + (t * q.w)) + cross(u, t);
+	return madd(v, t, q.w) + cross(u, t);
 }
 GPX_HD q4 Q(const float4 &f) { q4 q; q.x = f.x; q.y = f.y; q.z = f.z; q.w = f.w; return q; }
 GPX_HD q4 qmul(q4 a, q4 b)
 {
 	q4 r;
-	r.x = (((a.w * b.x) + (a.x * b.w)) + (a.y * b.z)) - (a.z * b.y);
-	r.y = (((a.w * b.y) - (a.x * b.z)) + (a.y * b.w)) + (a.z * b.x);
-	r.z = (((a.w * b.z) + (a.x * b.y)) - (a.y * b.x)) + (a.z * b.w);
-	r.w = (((a.w * b.w) - (a.x * b.x)) - (a.y * b.y)) - (a.z * b.z);
+	r.x = fmaf(-a.z, b.y, fmaf(a.y, b.z, fmaf(a.x, b.w, a.w * b.x)));
+	r.y = fmaf(a.z, b.x, fmaf(a.y, b.w, fmaf(-a.x, b.z, a.w * b.y)));
+	r.z = fmaf(a.z, b.w, fmaf(-a.y, b.x, fmaf(a.x, b.y, a.w * b.z)));
+	r.w = fmaf(-a.z, b.z, fmaf(-a.y, b.y, fmaf(-a.x, b.x, a.w * b.w)));
 	return r;
 }
 GPX_HD q4 qnormalize(q4 q)
@@ -60,7 +64,7 @@ GPX_HD m33 qmat(q4 q)
 	m.c2 = qrot(q, V(0.0f, 0.0f, 1.0f));
 	return m;
 }
-GPX_HD v3 mmul(const m33 &m, v3 v) { return ((m.c0 * v.x) + (m.c1 * v.y)) + (m.c2 * v.z); }
+GPX_HD v3 mmul(const m33 &m, v3 v) { return madd(madd(m.c0 * v.x, m.c1, v.y), m.c2, v.z); }
 GPX_HD v3 mtmul(const m33 &m, v3 v) { return V(dot(m.c0, v), dot(m.c1, v), dot(m.c2, v)); }
 GPX_HD v3 col(const m33 &m, int i) { return i == 0 ? m.c0 : (i == 1 ? m.c1 : m.c2); }
 
@@ -100,8 +104,8 @@ GPX_HD v3 vperp(v3 n)
 // symmetric 3x3 (xx xy xz yy yz zz) times vector
 GPX_HD v3 sym_mul(const float *M, v3 v)
 {
-	return V(((M[0] * v.x) + (M[1] * v.y)) + (M[2] * v.z), ((M[1] * v.x) + (M[3] * v.y)) + (M[4] * v.z),
-			 ((M[2] * v.x) + (M[4] * v.y)) + (M[5] * v.z));
+	return V(fmaf(M[2], v.z, fmaf(M[1], v.y, M[0] * v.x)), fmaf(M[4], v.z, fmaf(M[3], v.y, M[1] * v.x)),
+			 fmaf(M[5], v.z, fmaf(M[4], v.y, M[2] * v.x)));
 }
 
 }  // namespace gpx

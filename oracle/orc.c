@@ -1312,8 +1312,8 @@ static void body_world_inertia(body_t *b)
 
 static v3 sym_mul(const float *M, v3 v)
 {
-	return V(((M[0] * v.x) + (M[1] * v.y)) + (M[2] * v.z), ((M[1] * v.x) + (M[3] * v.y)) + (M[4] * v.z),
-			 ((M[2] * v.x) + (M[4] * v.y)) + (M[5] * v.z));
+	return V(fmaf(M[2], v.z, fmaf(M[1], v.y, M[0] * v.x)), fmaf(M[4], v.z, fmaf(M[3], v.y, M[1] * v.x)),
+			 fmaf(M[5], v.z, fmaf(M[4], v.y, M[2] * v.x)));
 }
 
 static v3 mask_lin(uint32_t dofs, v3 a)

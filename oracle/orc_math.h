@@ -1,5 +1,7 @@
 /* orc_math.h — scalar fp32 vector helpers for the CPU oracle (test infrastructure only; see orc.h).
- * Every expression is fully parenthesised: with -ffp-contract=off the rounding sequence is fixed. */
+ * Every expression is fully parenthesised: with -ffp-contract=off the compiler never contracts on its own, and the
+ * fused multiply-adds of dot / cross / matrix-vector / quaternion products are spelled fmaf(), so the rounding
+ * sequence is fixed (fmaf is exact-then-round on every conforming libm / FMA unit). */
 #ifndef ORC_MATH_H
 #define ORC_MATH_H
 #include <math.h>
@@ -13,30 +15,32 @@ static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
 static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
 static inline v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
-static inline float vdot(v3 a, v3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); }
+static inline float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 static inline v3 vcross(v3 a, v3 b)
 {
-	return V((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+	return V(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 static inline float vlen2(v3 a) { return vdot(a, a); }
 static inline float vlen(v3 a) { return sqrtf(vdot(a, a)); }
 static inline float vget(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+/* v + t * s */
+static inline v3 vmadd(v3 v, v3 t, float s) { return V(fmaf(t.x, s, v.x), fmaf(t.y, s, v.y), fmaf(t.z, s, v.z)); }
 static inline v3 vmulc(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 
 static inline v3 qrot(q4 q, v3 v)
 {
 	v3 u = V(q.x, q.y, q.z);
 	v3 t = vscale(vcross(u, v), 2.0f);
-	return vadd(vadd(v, vscale(t, q.w)), vcross(u, t));
+	return vadd(vmadd(v, t, q.w), vcross(u, t));
 }
 static inline q4 qconj(q4 q) { q4 r = {-q.x, -q.y, -q.z, q.w}; return r; }
 static inline q4 qmul(q4 a, q4 b)
 {
 	q4 r;
-	r.x = (((a.w * b.x) + (a.x * b.w)) + (a.y * b.z)) - (a.z * b.y);
-	r.y = (((a.w * b.y) - (a.x * b.z)) + (a.y * b.w)) + (a.z * b.x);
-	r.z = (((a.w * b.z) + (a.x * b.y)) - (a.y * b.x)) + (a.z * b.w);
-	r.w = (((a.w * b.w) - (a.x * b.x)) - (a.y * b.y)) - (a.z * b.z);
+	r.x = fmaf(-a.z, b.y, fmaf(a.y, b.z, fmaf(a.x, b.w, a.w * b.x)));
+	r.y = fmaf(a.z, b.x, fmaf(a.y, b.w, fmaf(-a.x, b.z, a.w * b.y)));
+	r.z = fmaf(a.z, b.w, fmaf(-a.y, b.x, fmaf(a.x, b.y, a.w * b.z)));
+	r.w = fmaf(-a.z, b.z, fmaf(-a.y, b.y, fmaf(-a.x, b.x, a.w * b.w)));
 	return r;
 }
 static inline q4 qnormalize(q4 q)
@@ -57,7 +61,7 @@ static inline m33 qmat(q4 q)
 /* world = M * local */
 static inline v3 mmul(const m33 *m, v3 v)
 {
-	return vadd(vadd(vscale(m->c0, v.x), vscale(m->c1, v.y)), vscale(m->c2, v.z));
+	return vmadd(vmadd(vscale(m->c0, v.x), m->c1, v.y), m->c2, v.z);
 }
 /* local = M^T * world */
 static inline v3 mtmul(const m33 *m, v3 v) { return V(vdot(m->c0, v), vdot(m->c1, v), vdot(m->c2, v)); }
