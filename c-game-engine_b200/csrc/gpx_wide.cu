@@ -4,11 +4,12 @@
 // 105-108), same device functions (gpx_solver.cuh) and therefore the same fp32 results per contact, but a different
 // decomposition: state lives in global memory (L2-resident at 100k bodies) and every stage is one thread per item.
 //
-//   kw_begin      thread/body      SoA -> work record (first sub-step), forces, inertia, AABB, sort key = min x
-//   bitonic sort  (gpx_bvh.cu)     bodies ordered by the lower x bound of their boxes
+//   kw_begin      thread/body      SoA -> work record (first sub-step), forces, inertia, AABB, largest extents
+//   kw_keys       thread/body      sort key = (row along z, lower x bound, body)
+//   bitonic sort  (gpx_bvh.cu)     bodies ordered by row, then by the lower x bound of their boxes
 //   kw_gather     thread/slot      sorted boxes packed into two float4 streams
-//   kw_sweep      thread/body      sort-and-sweep broadphase: walk forward while boxes can still overlap on x,
-//                                  exact box test, layer matrix -> pair list (atomic append)
+//   kw_sweep      thread/body      sort-and-sweep broadphase: walk forward in the own row and through the reachable
+//                                  part of the next row, exact box test, layer matrix -> pair list (atomic append)
 //   kw_pairs      thread/pair      box-box / sphere contact manifolds
 //   kw_static     thread/body      LBVH candidates (cached), box/sphere-vs-triangle manifolds grouped by normal
 //   kw_link       thread/manifold  warm-start lookup in a hash table of the previous sub-step's manifolds, incidence
@@ -34,7 +35,7 @@ constexpr int WIDE_MAXCOL = 64;
 constexpr uint32_t WT = 128;         // threads per block of the per-item kernels
 constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase kernels (shared polygon scratch)
 
-enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_COLCNT = 8,
+enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_MAXEXT_X, WC_MAXEXT_Z, WC_COLCNT = 8,
 				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_COUNT = WC_COLCUR + WIDE_MAXCOL };
 
 struct WideDevice
@@ -166,7 +167,40 @@ __global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
 	}
 	body_world_inertia(b);
 	body_aabb(b);
-	a.keys[i] = shape_of(f) == GPX_SHAPE_EMPTY ? ~0ull : (((unsigned long long)sortable(b.lo.x) << 32) | i);
+	if (shape_of(f) == GPX_SHAPE_EMPTY)
+	{
+		a.keys[i] = ~0ull;
+		return;
+	}
+	a.keys[i] = 0ull;  // filled by kw_keys once the largest extents are known
+	atomicMax(&a.cnt[WC_MAXEXT_X], __float_as_uint(fmaxf(b.hi.x - b.lo.x, 0.0f)));
+	atomicMax(&a.cnt[WC_MAXEXT_Z], __float_as_uint(fmaxf(b.hi.z - b.lo.z, 0.0f)));
+}
+
+// Sort key: [row: 12 bits][lower x bound, order-preserving: 32 bits][body: 20 bits].  Rows are slabs along z at least
+// as thick as the largest body (plus the contact margin), so two bodies that overlap in z sit in the same or in
+// adjacent rows; within a row the bodies are ordered by the lower x bound of their boxes.
+constexpr int WIDE_ROWS = 4096;
+__device__ __forceinline__ float row_thickness(const WideArgs &a)
+{
+	return (__uint_as_float(a.cnt[WC_MAXEXT_Z]) + (4.0f * SPECULATIVE_DISTANCE)) + 1.0e-3f;
+}
+__device__ __forceinline__ uint32_t row_of(float lo_z, float thickness)
+{
+	const float r = floorf(lo_z / thickness) + (float)(WIDE_ROWS / 2);
+	return (uint32_t)fminf(fmaxf(r, 0.0f), (float)(WIDE_ROWS - 1));
+}
+__device__ __forceinline__ unsigned long long sweep_key(uint32_t row, float lo_x, uint32_t body)
+{
+	return ((unsigned long long)row << 52) | ((unsigned long long)sortable(lo_x) << 20) | (unsigned long long)body;
+}
+
+__global__ void __launch_bounds__(WT) kw_keys(WideArgs a)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= a.nb || a.keys[i] == ~0ull) return;
+	const SBody &b = a.bodies[i];
+	a.keys[i] = sweep_key(row_of(b.lo.z, row_thickness(a)), b.lo.x, i);
 }
 
 __global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
@@ -179,50 +213,75 @@ __global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
 		a.boxlo[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
 		return;
 	}
-	const uint32_t i = (uint32_t)(k & 0xFFFFFFFFull);
+	const uint32_t i = (uint32_t)(k & 0xFFFFFull);
 	const SBody &b = a.bodies[i];
 	a.boxlo[p] = F4(b.lo, __uint_as_float(i));
 	a.boxhi[p] = F4(b.hi, __uint_as_float(b.flags));
 }
 
-// Sort-and-sweep: bodies are ordered by lo.x; body p only has to look at later bodies whose lo.x is still below its
-// hi.x (+ margin).  The exact test is the ensemble kernel's, evaluated with the lower-numbered body first.
+// Sort-and-sweep over rows: body p walks forward in its own row while boxes can still overlap on x, then through
+// the part of the next row that can overlap it (found by binary search on the sort keys).  The exact test is the
+// ensemble kernel's, evaluated with the lower-numbered body first, so the pair set equals an all-pairs test.
+__device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p, uint32_t ip, uint32_t fp, uint32_t q)
+{
+	const float4 lo_q = a.boxlo[q], hi_q = a.boxhi[q];
+	const uint32_t iq = __float_as_uint(lo_q.w), fq = __float_as_uint(hi_q.w);
+	if (!is_dynamic(fp) && !is_dynamic(fq)) return;
+	if (!layers_collide(layer_of(fp), layer_of(fq))) return;
+	if ((fp & BF_SENSOR) || (fq & BF_SENSOR)) return;  // sensor overlaps are events, not contacts (not reported by this path yet)
+	const bool p_first = ip < iq;
+	const v3 alo = p_first ? V(lo_p) : V(lo_q), ahi = p_first ? V(hi_p) : V(hi_q);
+	const v3 blo = p_first ? V(lo_q) : V(lo_p), bhi = p_first ? V(hi_q) : V(hi_p);
+	if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) return;
+	const uint32_t k = atomicAdd(&a.cnt[WC_NMAN], 1u);
+	if (k >= a.cap_m)
+	{
+		atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+		return;
+	}
+	SMan &m = a.man[k];
+	m.a = p_first ? ip : iq;
+	m.b = p_first ? iq : ip;
+	m.np = 0;
+	m.colour = -2;
+	a.ord[k] = 0;
+}
+
 __global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
 {
 	const uint32_t p = blockIdx.x * WT + threadIdx.x;
 	if (p >= a.n_pad) return;
-	const float4 lo_p = a.boxlo[p];
-	const uint32_t ip = __float_as_uint(lo_p.w);
-	if (ip == 0xFFFFFFFFu) return;
-	const float4 hi_p = a.boxhi[p];
-	const uint32_t fp = __float_as_uint(hi_p.w);
+	const unsigned long long key_p = a.keys[p];
+	if (key_p == ~0ull) return;
+	const float4 lo_p = a.boxlo[p], hi_p = a.boxhi[p];
+	const uint32_t ip = __float_as_uint(lo_p.w), fp = __float_as_uint(hi_p.w);
+	const uint32_t row = (uint32_t)(key_p >> 52);
 	const float reach = (hi_p.x + SPECULATIVE_DISTANCE) + SPECULATIVE_DISTANCE;  // a little beyond the exact test's reach
+	// own row: later bodies only (earlier ones find p themselves)
 	for (uint32_t q = p + 1; q < a.n_pad; q++)
 	{
-		const float4 lo_q = a.boxlo[q];
-		const uint32_t iq = __float_as_uint(lo_q.w);
-		if (iq == 0xFFFFFFFFu || lo_q.x > reach) break;
-		const float4 hi_q = a.boxhi[q];
-		const uint32_t fq = __float_as_uint(hi_q.w);
-		if (!is_dynamic(fp) && !is_dynamic(fq)) continue;
-		if (!layers_collide(layer_of(fp), layer_of(fq))) continue;
-		if ((fp & BF_SENSOR) || (fq & BF_SENSOR)) continue;
-		const bool p_first = ip < iq;
-		const v3 alo = p_first ? V(lo_p) : V(lo_q), ahi = p_first ? V(hi_p) : V(hi_q);
-		const v3 blo = p_first ? V(lo_q) : V(lo_p), bhi = p_first ? V(hi_q) : V(hi_p);
-		if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) continue;
-		const uint32_t k = atomicAdd(&a.cnt[WC_NMAN], 1u);
-		if (k >= a.cap_m)
-		{
-			atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
-			break;
-		}
-		SMan &m = a.man[k];
-		m.a = p_first ? ip : iq;
-		m.b = p_first ? iq : ip;
-		m.np = 0;
-		m.colour = -2;
-		a.ord[k] = 0;
+		const unsigned long long kq = a.keys[q];
+		if (kq == ~0ull || (uint32_t)(kq >> 52) != row) break;
+		if (a.boxlo[q].x > reach) break;
+		sweep_test(a, lo_p, hi_p, ip, fp, q);
+	}
+	// next row: everything whose box can reach back to lo_p.x
+	if (row + 1 >= (uint32_t)WIDE_ROWS) return;
+	const float back = (lo_p.x - __uint_as_float(a.cnt[WC_MAXEXT_X])) - (4.0f * SPECULATIVE_DISTANCE);
+	const unsigned long long want = sweep_key(row + 1, back, 0u);
+	uint32_t lo = p + 1, hi = a.n_pad;  // first q with keys[q] >= want (padding keys are ~0, so the array is sorted)
+	while (lo < hi)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (a.keys[mid] < want) lo = mid + 1;
+		else hi = mid;
+	}
+	for (uint32_t q = lo; q < a.n_pad; q++)
+	{
+		const unsigned long long kq = a.keys[q];
+		if (kq == ~0ull || (uint32_t)(kq >> 52) != row + 1) break;
+		if (a.boxlo[q].x > reach) break;
+		sweep_test(a, lo_p, hi_p, ip, fp, q);
 	}
 }
 
@@ -648,7 +707,8 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		GPX_CUDA(cudaMemsetAsync(d->counters + WC_NMAN, 0, sizeof(uint32_t), st));
 		GPX_CUDA(cudaMemsetAsync(d->counters + WC_UNCOLOURED, 0, sizeof(uint32_t) * (WC_COUNT - WC_UNCOLOURED), st));
 		kw_begin<<<gb, WT, 0, st>>>(a);
-		count_launch();
+		kw_keys<<<gb, WT, 0, st>>>(a);
+		count_launch(2);
 		bitonic_sort_u64(d->keys, d->n_pad, st);
 		kw_gather<<<gb, WT, 0, st>>>(a);
 		kw_sweep<<<gb, WT, 0, st>>>(a);
