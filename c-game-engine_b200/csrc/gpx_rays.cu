@@ -109,7 +109,9 @@ __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, c
 	float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
 	float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
 	float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-	float ox = o.x * idx, oy = o.y * idy, oz = o.z * idz;
+	// the slab arithmetic only decides which nodes are visited (boxes are padded by BVH_PAD, far more than its rounding),
+	// so it may use fused multiply-adds; the triangle test below is the exact one
+	const float ox = -(o.x * idx), oy = -(o.y * idy), oz = -(o.z * idz);
 	int stack[STACK_DEPTH];
 	int sp = 0;
 	int node = 0;
@@ -121,13 +123,13 @@ __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, c
 			const float4 n0 = NODES[4 * node + 0], n1 = NODES[4 * node + 1], n2 = NODES[4 * node + 2],
 						 n3 = NODES[4 * node + 3];
 			// child 0
-			float ax0 = n0.x * idx - ox, ax1 = n0.y * idx - ox, ay0 = n0.z * idy - oy, ay1 = n0.w * idy - oy;
-			float az0 = n2.x * idz - oz, az1 = n2.y * idz - oz;
+			float ax0 = fmaf(n0.x, idx, ox), ax1 = fmaf(n0.y, idx, ox), ay0 = fmaf(n0.z, idy, oy), ay1 = fmaf(n0.w, idy, oy);
+			float az0 = fmaf(n2.x, idz, oz), az1 = fmaf(n2.y, idz, oz);
 			float tn0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
 			float tf0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), limit));
 			// child 1
-			float bx0 = n1.x * idx - ox, bx1 = n1.y * idx - ox, by0 = n1.z * idy - oy, by1 = n1.w * idy - oy;
-			float bz0 = n2.z * idz - oz, bz1 = n2.w * idz - oz;
+			float bx0 = fmaf(n1.x, idx, ox), bx1 = fmaf(n1.y, idx, ox), by0 = fmaf(n1.z, idy, oy), by1 = fmaf(n1.w, idy, oy);
+			float bz0 = fmaf(n2.z, idz, oz), bz1 = fmaf(n2.w, idz, oz);
 			float tn1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
 			float tf1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), limit));
 			// the boxes are padded by BVH_PAD, far more than the rounding of these slabs
