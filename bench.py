@@ -41,6 +41,16 @@ RAYS_PER_WORLD_TICK = 5     # crosshair ray + 4 lasers, as in test.gmap (PlayerP
 L2_FLUSH_BYTES = 256 << 20
 
 
+def measured_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            v = json.load(f).get(kernel)
+        return float(v) if v is not None else None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -334,7 +344,7 @@ def run_gpu(args):
                     "what": f"per tick: gpx_raycast_batch({n_rays} host rays, pinned) + gpx_step + gpx_sync_transforms; wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_tick", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": args.traffic, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": args.traffic if args.traffic is not None else measured_traffic("k_tick"), "peak_source": peak_src,
                          "bytes_per_unit": BYTES_PER_BODY_STEP, "units_per_launch": bodies_per_rank},
             "cpu_baseline": cpu,
             "rays": rays_res,
@@ -464,7 +474,7 @@ def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
            "e2e": {"value": world_size * n / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16},
            "roofline": {"bound": "hbm", "kernel": "k_raycast", "achieved": n * BYTES_PER_RAY / (ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / hbm_peak,
-                        "traffic": args.ray_traffic},
+                        "traffic": args.ray_traffic if args.ray_traffic is not None else measured_traffic("k_raycast")},
            "hit_fraction": hit_frac}
     if rank == 0 and world_size == 1 and not args.no_cpu:
         import orc

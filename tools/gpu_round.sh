@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, the bench (both arms), then the ncu launch list and full captures of the two hot kernels.
+# One GPU-box visit: parity tests, the bench (both arms), then the ncu launch list and full captures of the hot kernels.
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
 tag=${1:-r1}
 out=gpurun_out
@@ -8,11 +8,13 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
 python bench.py --impl reference --steps 100 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err
-P="python bench.py --steps 12 --warmup 3 --ray-reps 3 --no-cpu"
+python tools/phase_profile.py 4096 20 > $out/${tag}_phases.txt 2>&1
+P="python bench.py --steps 12 --warmup 3 --ray-reps 3 --wide-steps 2 --no-cpu"
 $P > $out/${tag}_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $P > $out/${tag}_ncu1.log 2>&1
-$P > $out/${tag}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_tick -s 8 -c 2 -o $out/${tag}_tick $P > $out/${tag}_ncu2.log 2>&1
-$P > $out/${tag}_plain3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_raycast -s 20 -c 2 -o $out/${tag}_rays $P > $out/${tag}_ncu3.log 2>&1
-tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench.json; tail -2 $out/${tag}_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches.csv $P > $out/${tag}_ncu1.log 2>&1
+Q="python bench.py --steps 12 --warmup 3 --ray-reps 3 --no-wide --no-cpu"
+$Q > $out/${tag}_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_tick -s 20 -c 2 -o $out/${tag}_tick $Q > $out/${tag}_ncu2.log 2>&1
+$Q > $out/${tag}_plain3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_raycast -s 20 -c 1 -o $out/${tag}_rays $Q > $out/${tag}_ncu3.log 2>&1
+tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench.json | cut -c1-600; tail -2 $out/${tag}_bench.err
