@@ -76,6 +76,16 @@ class BodyDesc(C.Structure):
     ]
 
 
+class CharacterDesc(C.Structure):
+    _fields_ = [("half_height", C.c_float), ("radius", C.c_float), ("max_slope_deg", C.c_float), ("mass", C.c_float),
+                ("position", C.c_float * 3)]
+
+
+class CharacterState(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("linear_velocity", C.c_float * 3), ("ground_normal", C.c_float * 3),
+                ("ground_state", C.c_uint32), ("ground_body", C.c_uint32)]
+
+
 class Transform(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("rotation", C.c_float * 4)]
 
@@ -179,6 +189,12 @@ def lib() -> C.CDLL:
         "gpx_timer_end": (f32, [vp]),
         "gpx_launch_count": (u64, []),
         "gpx_debug_phase_cycles": (i32, [vp, i32, vp]),
+        "gpx_character_create": (i32, [vp, u32, C.POINTER(CharacterDesc)]),
+        "gpx_character_destroy": (i32, [vp, u32]),
+        "gpx_character_set_linear_velocity": (i32, [vp, u32, C.POINTER(f32)]),
+        "gpx_character_set_position": (i32, [vp, u32, C.POINTER(f32)]),
+        "gpx_character_update": (i32, [vp, f32]),
+        "gpx_character_get": (i32, [vp, u32, C.POINTER(CharacterState)]),
         "gpx_events_enable": (i32, [vp, i32]),
         "gpx_poll_events": (i32, [vp, vp, u64, C.POINTER(u64)]),
     }
@@ -366,6 +382,28 @@ class World:
         out = np.zeros(16, np.uint64)
         _check(self.L.gpx_debug_phase_cycles(self.h, 1 if enable else 0, out.ctypes.data), "gpx_debug_phase_cycles")
         return {k: int(v) for k, v in zip(self.PHASES, out)}
+
+    # ---- player character (JPH_CharacterVirtual as used by PlayerPhysics.c)
+    def character_create(self, pos, half_height=0.2, radius=0.25, max_slope_deg=50.0, world=0):
+        d = CharacterDesc()
+        d.half_height, d.radius, d.max_slope_deg, d.mass = half_height, radius, max_slope_deg, 10.0
+        d.position[:] = pos
+        _check(self.L.gpx_character_create(self.h, world, C.byref(d)), "gpx_character_create")
+
+    def character_set_velocity(self, v, world=0):
+        _check(self.L.gpx_character_set_linear_velocity(self.h, world, (C.c_float * 3)(*v)), "gpx_character_set_linear_velocity")
+
+    def character_set_position(self, p, world=0):
+        _check(self.L.gpx_character_set_position(self.h, world, (C.c_float * 3)(*p)), "gpx_character_set_position")
+
+    def character_update(self, dt=1.0 / 60.0):
+        _check(self.L.gpx_character_update(self.h, dt), "gpx_character_update")
+
+    def character_get(self, world=0):
+        s = CharacterState()
+        _check(self.L.gpx_character_get(self.h, world, C.byref(s)), "gpx_character_get")
+        return (np.array(list(s.position), np.float32), np.array(list(s.linear_velocity), np.float32), s.ground_state,
+                s.ground_body)
 
     def enable_events(self, on=True):
         _check(self.L.gpx_events_enable(self.h, 1 if on else 0), "gpx_events_enable")

@@ -294,6 +294,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
+	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);
 	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
@@ -776,6 +777,108 @@ int gpx_device_sync(gpx_world *w)
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;
 }
+/* ---- player character */
+
+static int char_upload(gpx_world *w, uint32_t world)
+{
+	GPX_CUDA(cudaMemcpyAsync(w->d_ch + world, &w->h_ch[world], sizeof(CharDev), cudaMemcpyHostToDevice, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));  // h_ch is pageable
+	return GPX_OK;
+}
+
+int gpx_character_create(gpx_world *w, uint32_t world, const gpx_character_desc *d)
+{
+	if (!w || !d || world >= w->W || w->wide) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	if (!w->d_ch)
+	{
+		int rc;
+		if ((rc = dalloc(&w->d_ch, (size_t)w->W)) != GPX_OK ||
+			(rc = dalloc(&w->d_ch_keys, (size_t)w->W * CHARACTER_MAX_CONTACTS)) != GPX_OK ||
+			(rc = dalloc(&w->d_ch_nkeys, (size_t)w->W)) != GPX_OK)
+			return rc;
+		w->h_ch.assign(w->W, CharDev{});
+	}
+	CharDev &c = w->h_ch[world];
+	memset(&c, 0, sizeof(c));
+	c.px = d->position[0]; c.py = d->position[1]; c.pz = d->position[2];
+	c.hh = d->half_height;
+	c.r = d->radius;
+	c.cos_slope = cosf(d->max_slope_deg * 0.0174532925f);
+	c.gny = 1.0f;
+	c.alive = 1;
+	c.ground = 3;  /* JPH_GroundState_InAir until the first update */
+	c.ground_body = GPX_INVALID_BODY;
+	return char_upload(w, world);
+}
+
+int gpx_character_destroy(gpx_world *w, uint32_t world)
+{
+	if (!w || world >= w->W || !w->d_ch) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	memset(&w->h_ch[world], 0, sizeof(CharDev));
+	GPX_CUDA(cudaMemsetAsync(w->d_ch_nkeys + world, 0, sizeof(uint32_t), w->stream));
+	return char_upload(w, world);
+}
+
+static int char_fetch(gpx_world *w, uint32_t world)
+{
+	GPX_CUDA(cudaMemcpyAsync(&w->h_ch[world], w->d_ch + world, sizeof(CharDev), cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+
+int gpx_character_set_linear_velocity(gpx_world *w, uint32_t world, const float v[3])
+{
+	if (!w || world >= w->W || !w->d_ch || !v) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc = char_fetch(w, world);
+	if (rc != GPX_OK) return rc;
+	w->h_ch[world].vx = v[0]; w->h_ch[world].vy = v[1]; w->h_ch[world].vz = v[2];
+	return char_upload(w, world);
+}
+
+int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3])
+{
+	if (!w || world >= w->W || !w->d_ch || !p) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc = char_fetch(w, world);
+	if (rc != GPX_OK) return rc;
+	w->h_ch[world].px = p[0]; w->h_ch[world].py = p[1]; w->h_ch[world].pz = p[2];
+	return char_upload(w, world);
+}
+
+int gpx_character_update(gpx_world *w, float dt)
+{
+	if (!w || !w->d_ch || !(dt > 0.0f)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	return launch_character(w, dt);
+}
+
+int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out)
+{
+	if (!w || world >= w->W || !w->d_ch || !out) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc = char_fetch(w, world);
+	if (rc != GPX_OK) return rc;
+	const CharDev &c = w->h_ch[world];
+	out->position[0] = c.px; out->position[1] = c.py; out->position[2] = c.pz;
+	out->linear_velocity[0] = c.vx; out->linear_velocity[1] = c.vy; out->linear_velocity[2] = c.vz;
+	out->ground_normal[0] = c.gnx; out->ground_normal[1] = c.gny; out->ground_normal[2] = c.gnz;
+	out->ground_state = c.ground;
+	out->ground_body = c.ground_body;
+	return c.alive ? GPX_OK : GPX_ERR_INVALID_ARG;
+}
+
 int gpx_events_enable(gpx_world *w, int enable)
 {
 	if (!w || w->wide) return GPX_ERR_INVALID_ARG;  // the wide-world path does not report contact events yet
@@ -784,7 +887,7 @@ int gpx_events_enable(gpx_world *w, int enable)
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	if (enable && !w->d_ev_out)
 	{
-		const size_t nm = (size_t)w->W * w->cap_m;
+		const size_t nm = (size_t)w->W * (w->cap_m + CHARACTER_MAX_CONTACTS);
 		int rc;
 		if ((rc = dalloc(&w->d_ev_prev, nm)) != GPX_OK || (rc = dalloc(&w->d_ev_nprev, (size_t)w->W)) != GPX_OK ||
 			(rc = dalloc(&w->d_ev_count, (size_t)w->W)) != GPX_OK || (rc = dalloc(&w->d_ev_out, 2 * nm)) != GPX_OK)
@@ -807,7 +910,7 @@ int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uin
 	std::lock_guard<std::mutex> lk(w->mu);
 	if (!w->d_ev_out) return GPX_ERR_INVALID_ARG;
 	cudaSetDevice(w->device);
-	const size_t per = 2u * (size_t)w->cap_m;
+	const size_t per = 2u * ((size_t)w->cap_m + CHARACTER_MAX_CONTACTS);
 	w->h_ev_count.resize(w->W);
 	w->h_ev_out.resize((size_t)w->W * per);
 	GPX_CUDA(cudaMemcpyAsync(w->h_ev_count.data(), w->d_ev_count, sizeof(uint32_t) * w->W, cudaMemcpyDeviceToHost, w->stream));

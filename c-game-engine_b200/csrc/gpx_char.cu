@@ -1,0 +1,456 @@
+// gpx_char.cu — the player character: a capsule moved by collide-and-slide against the map and the solid bodies.
+//
+// Replaces JPH_CharacterVirtual as the engine uses it (engine/src/physics/PlayerPhysics.c): created per map
+// (:173-194, capsule half height 0.2, radius 0.25, max slope 50 degrees), given a velocity by MovePlayer (:203-295),
+// advanced by JPH_CharacterVirtual_ExtendedUpdate BEFORE the physics update (:439-453, MapPhysics.c:66-77), read back
+// with GetPosition / GetLinearVelocity / GetGroundState, and its contacts forwarded to actor callbacks (:89-152).
+// One warp per world: the lanes share the candidate triangles (LBVH box query) and the world's bodies, each computes
+// segment-vs-shape closest points, and a shuffle reduction picks the deepest penetration (ties: lowest id) — up to
+// eight push-outs per update, then the ground probe / stick-to-floor step and the contact list that the tick's event
+// pass merges with the body contacts.
+#include "gpx_solver.cuh"
+
+namespace gpx {
+
+constexpr int CH_MAX_ITERS = 8;
+constexpr float CH_CONTACT_MARGIN = 0.02f;
+constexpr float CH_GROUND_PROBE = 0.05f;
+
+__device__ __forceinline__ float clamp01(float t) { return t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t); }
+
+// closest points of segments p1-q1 and p2-q2 (Ericson, Real-Time Collision Detection 5.1.9)
+__device__ __forceinline__ void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3 &c1, v3 &c2)
+{
+	v3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+	float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+	float s, t;
+	const float EPS = 1.0e-12f;
+	if (a <= EPS && e <= EPS)
+	{
+		s = t = 0.0f;
+	}
+	else if (a <= EPS)
+	{
+		s = 0.0f;
+		t = clamp01(f / e);
+	}
+	else
+	{
+		float c = dot(d1, r);
+		if (e <= EPS)
+		{
+			t = 0.0f;
+			s = clamp01(-c / a);
+		}
+		else
+		{
+			float b = dot(d1, d2);
+			float denom = (a * e) - (b * b);
+			s = denom != 0.0f ? clamp01(((b * f) - (c * e)) / denom) : 0.0f;
+			t = ((b * s) + f) / e;
+			if (t < 0.0f)
+			{
+				t = 0.0f;
+				s = clamp01(-c / a);
+			}
+			else if (t > 1.0f)
+			{
+				t = 1.0f;
+				s = clamp01((b - c) / a);
+			}
+		}
+	}
+	c1 = p1 + (d1 * s);
+	c2 = p2 + (d2 * t);
+}
+
+// closest points between segment p0-p1 and a triangle; returns squared distance (0 when the segment pierces it)
+static __device__ __noinline__ float seg_tri(v3 p0, v3 p1, v3 a, v3 b, v3 c, v3 &cs, v3 &ct)
+{
+	{
+		v3 d = p1 - p0, e1 = b - a, e2 = c - a;
+		v3 pv = cross(d, e2);
+		float det = dot(e1, pv);
+		if (fabsf(det) >= 1.0e-12f)
+		{
+			float inv = 1.0f / det;
+			v3 tv = p0 - a;
+			float u = dot(tv, pv) * inv;
+			if (u >= 0.0f && u <= 1.0f)
+			{
+				v3 q = cross(tv, e1);
+				float v = dot(d, q) * inv;
+				if (v >= 0.0f && (u + v) <= 1.0f)
+				{
+					float t = dot(e2, q) * inv;
+					if (t >= 0.0f && t <= 1.0f)
+					{
+						cs = ct = p0 + (d * t);
+						return 0.0f;
+					}
+				}
+			}
+		}
+	}
+	float best = 3.0e38f;
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+	{
+		const v3 ea = i == 0 ? a : (i == 1 ? b : c), eb = i == 0 ? b : (i == 1 ? c : a);
+		v3 x, y;
+		seg_seg(p0, p1, ea, eb, x, y);
+		float d2 = len2(x - y);
+		if (d2 < best) { best = d2; cs = x; ct = y; }
+	}
+#pragma unroll
+	for (int i = 0; i < 2; i++)
+	{
+		const v3 e = i == 0 ? p0 : p1;
+		v3 y = closest_on_tri(e, a, b, c);
+		float d2 = len2(e - y);
+		if (d2 < best) { best = d2; cs = e; ct = y; }
+	}
+	return best;
+}
+
+// closest points between segment p0-p1 and an oriented box; returns squared distance (0 when the segment enters it)
+static __device__ __noinline__ float seg_box(v3 p0, v3 p1, v3 bx, q4 bq, v3 he, v3 &cs, v3 &cb)
+{
+	m33 R = qmat(bq);
+	v3 l0 = mtmul(R, p0 - bx), l1 = mtmul(R, p1 - bx);
+	{
+		v3 d = l1 - l0;
+		float tn = 0.0f, tf = 1.0f;
+		bool hit = true;
+#pragma unroll
+		for (int k = 0; k < 3; k++)
+		{
+			if (!hit) continue;
+			float ok = get(l0, k), dk = get(d, k), hk = get(he, k);
+			if (dk == 0.0f)
+			{
+				if (ok < -hk || ok > hk) hit = false;
+				continue;
+			}
+			float inv = 1.0f / dk;
+			float t1 = (-hk - ok) * inv, t2 = (hk - ok) * inv;
+			if (t1 > t2) { float tt = t1; t1 = t2; t2 = tt; }
+			if (t1 > tn) tn = t1;
+			if (t2 < tf) tf = t2;
+			if (tn > tf) hit = false;
+		}
+		if (hit)
+		{
+			v3 lp = l0 + (d * tn);
+			cs = cb = bx + mmul(R, lp);
+			return 0.0f;
+		}
+	}
+	float best = 3.0e38f;
+	v3 bs = l0, bb = l0;
+#pragma unroll
+	for (int i = 0; i < 2; i++)
+	{
+		v3 l = i == 0 ? l0 : l1;
+		v3 q = V(fminf(fmaxf(l.x, -he.x), he.x), fminf(fmaxf(l.y, -he.y), he.y), fminf(fmaxf(l.z, -he.z), he.z));
+		float d2 = len2(l - q);
+		if (d2 < best) { best = d2; bs = l; bb = q; }
+	}
+	for (int k = 0; k < 3; k++)
+	{
+		const int u = (k + 1) % 3, v = (k + 2) % 3;
+		for (int sgn = 0; sgn < 4; sgn++)
+		{
+			const float su = (sgn & 1) ? 1.0f : -1.0f, sv = (sgn & 2) ? 1.0f : -1.0f;
+			float e0[3], e1[3];
+			e0[k] = -get(he, k); e1[k] = get(he, k);
+			e0[u] = e1[u] = su * get(he, u);
+			e0[v] = e1[v] = sv * get(he, v);
+			v3 x, y;
+			seg_seg(l0, l1, V(e0[0], e0[1], e0[2]), V(e1[0], e1[1], e1[2]), x, y);
+			float d2 = len2(x - y);
+			if (d2 < best) { best = d2; bs = x; bb = y; }
+		}
+	}
+	cs = bx + mmul(R, bs);
+	cb = bx + mmul(R, bb);
+	return best;
+}
+
+__device__ __forceinline__ float seg_point(v3 p0, v3 p1, v3 c, v3 &cs)
+{
+	v3 d = p1 - p0;
+	float a = dot(d, d);
+	float t = a > 1.0e-12f ? clamp01(dot(c - p0, d) / a) : 0.0f;
+	cs = p0 + (d * t);
+	return len2(cs - c);
+}
+
+struct CharArgs
+{
+	CharDev *ch;
+	unsigned long long *keys;  // 64 per world
+	uint32_t *nkeys;
+	BodyStore bs;
+	StaticView sv;
+	uint32_t worlds, cap;
+	uint32_t *err;
+	float dt;
+};
+
+struct Deepest
+{
+	float pen;
+	uint32_t id;
+	v3 n;
+	uint32_t body;
+};
+
+// Deepest penetration of the capsule centred at x (warp-cooperative; every lane returns the same result).
+__device__ __forceinline__ Deepest ch_deepest(const CharArgs &a, uint32_t world, v3 x, float hh, float r, int *cand_orig,
+											 int *cand_leaf, int *s_nc, uint32_t &err)
+{
+	const int lane = threadIdx.x & 31;
+	const v3 p0 = V(x.x, x.y - hh, x.z), p1 = V(x.x, x.y + hh, x.z);
+	if (lane == 0)
+	{
+		bool overflow = false;
+		*s_nc = query_static(a.sv.nodes, a.sv.tris, a.sv.n_nodes, V(p0.x - r, p0.y - r, p0.z - r), V(p1.x + r, p1.y + r, p1.z + r),
+							 0.0f, cand_orig, cand_leaf, overflow);
+		if (overflow) err |= GPX_ERR_BODY_PAIR_CACHE_FULL;
+	}
+	__syncwarp();
+	const int nc = *s_nc;
+	Deepest best;
+	best.pen = 0.0f;
+	best.id = 0xFFFFFFFFu;
+	best.n = V(0.0f, 1.0f, 0.0f);
+	best.body = GPX_INVALID_BODY;
+	for (int c = lane; c < nc; c += 32)
+	{
+		const int leaf = cand_leaf[c];
+		const float4 TA = __ldg(&a.sv.tris[4 * leaf + 0]), TB = __ldg(&a.sv.tris[4 * leaf + 1]),
+					 TC = __ldg(&a.sv.tris[4 * leaf + 2]), TN = __ldg(&a.sv.tris[4 * leaf + 3]);
+		v3 cs, ct;
+		const float d2 = seg_tri(p0, p1, V(TA), V(TB), V(TC), cs, ct);
+		const float dist = sqrtf(d2);
+		const float pen = r - dist;
+		const uint32_t id = (uint32_t)cand_orig[c];
+		if (pen > best.pen || (pen == best.pen && pen > 0.0f && id < best.id))
+		{
+			v3 n;
+			if (dist > 1.0e-6f) n = (cs - ct) * (1.0f / dist);
+			else n = dot(x - V(TA), V(TN)) >= 0.0f ? V(TN) : -V(TN);
+			best.pen = pen;
+			best.id = id;
+			best.n = n;
+			best.body = STATIC_BODY_BASE + __float_as_uint(TB.w);
+		}
+	}
+	const uint32_t g0 = world * a.cap;
+	for (uint32_t i = lane; i < a.cap; i += 32)
+	{
+		const uint32_t f = a.bs.flags[g0 + i];
+		const uint32_t shape = shape_of(f), layer = layer_of(f);
+		if (!(f & BF_ALIVE) || shape == GPX_SHAPE_EMPTY || (f & BF_SENSOR) || !(layer == 0 || layer == 1)) continue;
+		const v3 bx = V(a.bs.pos[g0 + i]);
+		const float4 p1h = a.bs.prop1[g0 + i];
+		v3 cs, cb;
+		float d2, rr = r;
+		if (shape == GPX_SHAPE_BOX) d2 = seg_box(p0, p1, bx, Q(a.bs.quat[g0 + i]), V(p1h), cs, cb);
+		else
+		{
+			d2 = seg_point(p0, p1, bx, cs);
+			cb = bx;
+			rr = r + p1h.x;
+		}
+		const float dist = sqrtf(d2);
+		const float pen = rr - dist;
+		const uint32_t id = 0x80000000u + i;
+		if (pen > best.pen || (pen == best.pen && pen > 0.0f && id < best.id))
+		{
+			v3 n;
+			if (dist > 1.0e-6f) n = (cs - cb) * (1.0f / dist);
+			else
+			{
+				v3 d = x - bx;
+				float l = len(d);
+				n = l > 1.0e-6f ? d * (1.0f / l) : V(0.0f, 1.0f, 0.0f);
+			}
+			best.pen = pen;
+			best.id = id;
+			best.n = n;
+			best.body = i;
+		}
+	}
+	// warp reduction: largest penetration, ties to the lowest id
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		const float open = __shfl_xor_sync(0xFFFFFFFFu, best.pen, o);
+		const uint32_t oid = __shfl_xor_sync(0xFFFFFFFFu, best.id, o);
+		const float onx = __shfl_xor_sync(0xFFFFFFFFu, best.n.x, o), ony = __shfl_xor_sync(0xFFFFFFFFu, best.n.y, o),
+					onz = __shfl_xor_sync(0xFFFFFFFFu, best.n.z, o);
+		const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, best.body, o);
+		if (open > best.pen || (open == best.pen && oid < best.id))
+		{
+			best.pen = open;
+			best.id = oid;
+			best.n = V(onx, ony, onz);
+			best.body = ob;
+		}
+	}
+	__syncwarp();
+	return best;
+}
+
+__global__ void __launch_bounds__(128) k_character(CharArgs a)
+{
+	__shared__ int s_orig[4][MAX_TRI_CANDIDATES], s_leaf[4][MAX_TRI_CANDIDATES], s_nc[4];
+	__shared__ unsigned char s_touch[4][MAX_TRI_CANDIDATES];
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t world = blockIdx.x * 4 + wib;
+	if (world >= a.worlds) return;
+	CharDev ch = a.ch[world];
+	if (!ch.alive) return;
+	uint32_t err = 0;
+	const float hh = ch.hh, r = ch.r;
+	v3 v = V(ch.vx, ch.vy, ch.vz);
+	v3 x = V(ch.px, ch.py, ch.pz) + (v * a.dt);
+	uint32_t ground = 3u, ground_body = GPX_INVALID_BODY;
+	v3 ground_n = V(0.0f, 1.0f, 0.0f);
+	for (int it = 0; it < CH_MAX_ITERS; it++)
+	{
+		const Deepest d = ch_deepest(a, world, x, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+		if (!(d.pen > 0.0f)) break;
+		x = x + (d.n * d.pen);
+		const float vn = dot(v, d.n);
+		if (vn < 0.0f) v = v - (d.n * vn);
+		if (d.n.y >= ch.cos_slope)
+		{
+			ground = 0u;
+			ground_body = d.body;
+			ground_n = d.n;
+		}
+		else if (d.n.y > 0.0f && ground != 0u)
+		{
+			ground = 1u;
+			ground_body = d.body;
+			ground_n = d.n;
+		}
+	}
+	if (ground == 3u)
+	{
+		const Deepest d = ch_deepest(a, world, V(x.x, x.y - CH_GROUND_PROBE, x.z), hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+		if (d.pen > 0.0f && d.n.y > 0.0f)
+		{
+			ground = d.n.y >= ch.cos_slope ? 0u : 1u;
+			ground_body = d.body;
+			ground_n = d.n;
+			// stick to the floor: close the gap over walkable ground when not moving up
+			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, CH_GROUND_PROBE - d.pen);
+		}
+	}
+	// ---- contacts for the callbacks: bodies (sensors included) and static meshes within the contact margin
+	const v3 p0 = V(x.x, x.y - hh, x.z), p1 = V(x.x, x.y + hh, x.z);
+	const float reach = r + CH_CONTACT_MARGIN;
+	unsigned long long *keys = a.keys + 64ull * world;
+	uint32_t nkeys = 0;
+	const uint32_t g0 = world * a.cap;
+	for (uint32_t i0 = 0; i0 < a.cap; i0 += 32)
+	{
+		const uint32_t i = i0 + lane;
+		bool touch = false;
+		if (i < a.cap)
+		{
+			const uint32_t f = a.bs.flags[g0 + i];
+			const uint32_t shape = shape_of(f), layer = layer_of(f);
+			if ((f & BF_ALIVE) && shape != GPX_SHAPE_EMPTY && (layer == 0 || layer == 1 || layer == 3))
+			{
+				const v3 bx = V(a.bs.pos[g0 + i]);
+				const float4 p1h = a.bs.prop1[g0 + i];
+				v3 cs, cb;
+				float d2, rr = reach;
+				if (shape == GPX_SHAPE_BOX) d2 = seg_box(p0, p1, bx, Q(a.bs.quat[g0 + i]), V(p1h), cs, cb);
+				else
+				{
+					d2 = seg_point(p0, p1, bx, cs);
+					rr = reach + p1h.x;
+				}
+				touch = d2 <= rr * rr;
+			}
+		}
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, touch);
+		if (touch)
+		{
+			const uint32_t k = nkeys + __popc(m & ((1u << lane) - 1u));
+			if (k < 64u) keys[k] = ((unsigned long long)i << 32) | (unsigned long long)CHARACTER_BODY_ID;
+		}
+		nkeys = min(nkeys + __popc(m), 64u);
+	}
+	if (lane == 0)
+	{
+		bool overflow = false;
+		s_nc[wib] = query_static(a.sv.nodes, a.sv.tris, a.sv.n_nodes, V(p0.x - reach, p0.y - reach, p0.z - reach),
+								 V(p1.x + reach, p1.y + reach, p1.z + reach), 0.0f, s_orig[wib], s_leaf[wib], overflow);
+		if (overflow) err |= GPX_ERR_BODY_PAIR_CACHE_FULL;
+	}
+	__syncwarp();
+	const int nc = s_nc[wib];
+	for (int c = lane; c < nc; c += 32)
+	{
+		const int leaf = s_leaf[wib][c];
+		const float4 TA = __ldg(&a.sv.tris[4 * leaf + 0]), TB = __ldg(&a.sv.tris[4 * leaf + 1]), TC = __ldg(&a.sv.tris[4 * leaf + 2]);
+		v3 cs, ct;
+		const float d2 = seg_tri(p0, p1, V(TA), V(TB), V(TC), cs, ct);
+		s_touch[wib][c] = d2 <= reach * reach ? 1 : 0;
+	}
+	__syncwarp();
+	if (lane == 0)
+	{
+		// candidates are in upload order and the triangles of one mesh are contiguous: one contact per static mesh
+		uint32_t last = 0xFFFFFFFFu;
+		for (int c = 0; c < nc && nkeys < 64u; c++)
+		{
+			if (!s_touch[wib][c]) continue;
+			const uint32_t sb = __float_as_uint(__ldg(&a.sv.tris[4 * s_leaf[wib][c] + 1]).w);
+			if (sb == last) continue;
+			keys[nkeys++] = ((unsigned long long)CHARACTER_BODY_ID << 32) | (unsigned long long)(STATIC_BODY_BASE + sb);
+			last = sb;
+		}
+		a.nkeys[world] = nkeys;
+		ch.px = x.x; ch.py = x.y; ch.pz = x.z;
+		ch.vx = v.x; ch.vy = v.y; ch.vz = v.z;
+		ch.gnx = ground_n.x; ch.gny = ground_n.y; ch.gnz = ground_n.z;
+		ch.ground = ground;
+		ch.ground_body = ground_body;
+		a.ch[world] = ch;
+		if (err)
+		{
+			atomicOr(&a.err[1 + world], err);
+			atomicOr(&a.err[0], err);
+		}
+	}
+}
+
+int launch_character(gpx_world *w, float dt)
+{
+	CharArgs a;
+	a.ch = w->d_ch;
+	a.keys = w->d_ch_keys;
+	a.nkeys = w->d_ch_nkeys;
+	a.bs = w->bs;
+	a.sv.nodes = w->sd.nodes;
+	a.sv.tris = w->sd.tri;
+	a.sv.n_nodes = w->sd.n_nodes;
+	a.worlds = w->W;
+	a.cap = w->cap;
+	a.err = w->d_err;
+	a.dt = dt;
+	k_character<<<(w->W + 3) / 4, 128, 0, w->stream>>>(a);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
+}  // namespace gpx

@@ -12,6 +12,8 @@ namespace gpx {
 
 constexpr uint32_t STATIC_BODY_BASE = 0x400000u;  // ids >= this name static collision meshes (shared by all worlds)
 constexpr float RAY_MISS_FRACTION = 2.0f;
+constexpr uint32_t CHARACTER_BODY_ID = 0x3FFFFFu;  // pseudo body id of a world's player character in contact events
+constexpr uint32_t CHARACTER_MAX_CONTACTS = 64;
 constexpr float BVH_PAD = 1.0e-3f;  // node boxes are padded; leaves are re-tested exactly
 
 // body flag word
@@ -52,6 +54,15 @@ struct StaticDevice
 	uint32_t n_tris = 0, n_nodes = 0;
 	float4 *tri = nullptr;    // 4 float4 per triangle in LBVH order: (a, orig index) (b, static body) (c, friction) (n, ray flags)
 	float4 *nodes = nullptr;  // 4 float4 per internal node: c0 xy bounds, c1 xy bounds, both z bounds, child indices
+};
+
+// player character of one world (gpx_char.cu)
+struct CharDev
+{
+	float px, py, pz, hh;
+	float vx, vy, vz, r;
+	float gnx, gny, gnz, cos_slope;
+	uint32_t alive, ground, ground_body, pad;
 };
 
 struct BodyCommand  // host -> device write, applied by k_apply_commands before the next step
@@ -125,6 +136,11 @@ struct gpx_world
 	uint4 *d_ev_out = nullptr;
 	std::vector<uint4> h_ev_out;
 	std::vector<uint32_t> h_ev_count;
+	// player characters (gpx_char.cu): one per world, contact keys for the event pass
+	gpx::CharDev *d_ch = nullptr;
+	unsigned long long *d_ch_keys = nullptr;
+	uint32_t *d_ch_nkeys = nullptr;
+	std::vector<gpx::CharDev> h_ch;
 	float4 *d_park = nullptr;  // 9 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
 	gpx::WideDevice *wide = nullptr;  // non-null: this world runs the wide-world kernels
 	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)
@@ -148,6 +164,8 @@ void wide_destroy(gpx_world *w);
 int launch_wide_tick(gpx_world *w, float dt, int substeps);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
+// gpx_char.cu
+int launch_character(gpx_world *w, float dt);
 // gpx_tick.cu
 int launch_tick(gpx_world *w, float dt, int substeps);
 int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n);

@@ -44,6 +44,8 @@ struct TickArgs
 	float4 *con_park;  // 9 float4 per manifold slot: parked solver constants of worlds with more manifolds than lanes
 	uint4 *cand;  // per body 8 x uint4: {count, -, -, -}, {fat lo xyz, -}, {fat hi xyz, -}... see cand_* below
 	// contact events (gpx_events_enable): per world the sorted touching pairs of the previous tick and this tick's events
+	const unsigned long long *ch_keys;  // the player character's contacts (gpx_char.cu), 64 per world, or nullptr
+	const uint32_t *ch_nkeys;
 	unsigned long long *ev_prev;
 	uint32_t *ev_nprev;
 	uint4 *ev_out;
@@ -81,7 +83,9 @@ struct PhaseClock
 // sub-step's manifolds (a, b, np) and the list of active manifolds.
 __host__ __device__ inline size_t world_scratch_bytes(uint32_t tile, uint32_t cap_m)
 {
-	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 3 * cap_m;
+	// also: (cap_m + 64) 8-byte keys for the contact-event pass at the end of the tick
+	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 3 * cap_m, c = 8u * ((size_t)cap_m + CHARACTER_MAX_CONTACTS);
+	if (c > b) b = c;
 	return a > b ? a : b;
 }
 
@@ -574,9 +578,31 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			keys[k] = key;
 			n++;
 		}
-		unsigned long long *prev = a.ev_prev + (size_t)world * cap_m;
+		// the player character's contacts join the same list (pseudo body id CHARACTER_BODY_ID)
+		const uint32_t nch = a.ch_keys ? min(a.ch_nkeys[world], CHARACTER_MAX_CONTACTS) : 0u;
+		for (uint32_t ci = 0; ci < nch; ci++)
+		{
+			const unsigned long long key = a.ch_keys[(size_t)world * CHARACTER_MAX_CONTACTS + ci];
+			uint32_t k = n;
+			bool dup = false;
+			while (k > 0 && keys[k - 1] >= key)
+			{
+				if (keys[k - 1] == key)
+				{
+					dup = true;
+					break;
+				}
+				k--;
+			}
+			if (dup) continue;
+			for (uint32_t t = n; t > k; t--) keys[t] = keys[t - 1];
+			keys[k] = key;
+			n++;
+		}
+		const uint32_t ev_stride = cap_m + CHARACTER_MAX_CONTACTS;
+		unsigned long long *prev = a.ev_prev + (size_t)world * ev_stride;
 		const uint32_t np = a.ev_nprev[world];
-		uint4 *out = a.ev_out + (size_t)world * 2u * cap_m;
+		uint4 *out = a.ev_out + (size_t)world * 2u * ev_stride;
 		uint32_t e = 0, j = 0;
 		for (uint32_t i = 0; i < n; i++)
 		{
@@ -746,6 +772,8 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.err = w->d_err;
 	a.phase_cycles = w->d_phase;
 	a.cand = w->d_cand;
+	a.ch_keys = w->d_ch_keys;
+	a.ch_nkeys = w->d_ch_nkeys;
 	a.ev_prev = w->d_ev_prev;
 	a.ev_nprev = w->d_ev_nprev;
 	a.ev_out = w->d_ev_out;

@@ -218,6 +218,48 @@ int gpx_read_velocities(gpx_world *w, float *out_lin_ang6, uint64_t capacity);
 /* Per-world stats computed on device, `out` has `worlds` entries (host). */
 int gpx_read_stats(gpx_world *w, gpx_world_stats *out);
 
+/* ---- player character -------------------------------------------------------------------------------------------- */
+
+/* JPH_CharacterVirtual as the engine uses it (engine/src/physics/PlayerPhysics.c:173-194): a capsule that is not a
+ * body of the world; one per world instance.  Its contacts are reported by gpx_poll_events with the pseudo body id
+ * GPX_CHARACTER_BODY (the CharacterContactListener callbacks, PlayerPhysics.c:89-152). */
+#define GPX_CHARACTER_BODY 0x3FFFFFu
+enum gpx_ground_state /* JPH_GroundState */
+{
+	GPX_GROUND_ON_GROUND = 0,
+	GPX_GROUND_ON_STEEP_GROUND = 1,
+	GPX_GROUND_NOT_SUPPORTED = 2,
+	GPX_GROUND_IN_AIR = 3,
+};
+typedef struct gpx_character_desc /* JPH_CharacterVirtualSettings + JPH_CapsuleShape_Create(halfHeight, radius) */
+{
+	float half_height;   /* 0.2  (PlayerPhysics.c:176) */
+	float radius;        /* 0.25 */
+	float max_slope_deg; /* MAX_WALKABLE_SLOPE = 50 */
+	float mass;          /* 10; carried (the character does not push bodies yet) */
+	float position[3];
+} gpx_character_desc;
+typedef struct gpx_character_state
+{
+	float position[3];        /* JPH_CharacterVirtual_GetPosition (MapPhysics.c:77) */
+	float linear_velocity[3]; /* JPH_CharacterVirtual_GetLinearVelocity (PlayerPhysics.c:287) */
+	float ground_normal[3];
+	uint32_t ground_state;    /* JPH_CharacterBase_GetGroundState (PlayerPhysics.c:284) */
+	uint32_t ground_body;     /* body or static mesh stood on, GPX_INVALID_BODY in the air */
+} gpx_character_state;
+/* JPH_CharacterVirtual_Create / _Destroy */
+int gpx_character_create(gpx_world *w, uint32_t world, const gpx_character_desc *desc);
+int gpx_character_destroy(gpx_world *w, uint32_t world);
+/* JPH_CharacterVirtual_SetLinearVelocity (PlayerPhysics.c:294) / _SetPosition (PlayerPhysics.c:198) */
+int gpx_character_set_linear_velocity(gpx_world *w, uint32_t world, const float v[3]);
+int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3]);
+/* JPH_CharacterVirtual_ExtendedUpdate (PlayerPhysics.c:447) for the character of every world: move by velocity * dt,
+ * collide and slide against the map and the solid bodies, ground state, stick to the floor.  Call before gpx_step, as
+ * MapFixedUpdate does (MapPhysics.c:74 then :105).  Asynchronous on the world's stream. */
+int gpx_character_update(gpx_world *w, float dt);
+/* Waits for the stream and reads the character back. */
+int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out);
+
 /* ---- contact events ------------------------------------------------------------------------------------------------ */
 
 /* The listener the engine registers (JPH_CharacterContactListener: OnContactAdded / Persisted / Removed ->

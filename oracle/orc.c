@@ -105,6 +105,13 @@ struct orc_world
 	uint32_t nsens, nev_cur, nev_prev;
 	uint32_t *events; /* triples a, b, kind (1 added, 2 persisted, 3 removed) of the last tick */
 	uint32_t nevents;
+	/* player character (capsule), see the character section */
+	int ch_alive;
+	v3 ch_x, ch_v, ch_ground_n;
+	float ch_hh, ch_r, ch_cos_slope;
+	uint32_t ch_ground, ch_ground_body;
+	uint64_t ch_keys[64];
+	uint32_t ch_nkeys;
 	int mode; /* 0: greedy colouring in canonical order (ensembles); 1: hashed-priority rounds (wide worlds) */
 };
 
@@ -124,9 +131,9 @@ orc_world *orc_world_create(uint32_t max_bodies, uint32_t max_manifolds, const f
 	w->prev = (manifold_t *)calloc(w->max_manifolds, sizeof(manifold_t));
 	w->order = (uint32_t *)calloc(w->max_manifolds, sizeof(uint32_t));
 	w->sens = (uint64_t *)calloc(w->max_manifolds, sizeof(uint64_t));
-	w->ev_cur = (uint64_t *)calloc(2 * w->max_manifolds, sizeof(uint64_t));
-	w->ev_prev = (uint64_t *)calloc(2 * w->max_manifolds, sizeof(uint64_t));
-	w->events = (uint32_t *)calloc(12 * w->max_manifolds, sizeof(uint32_t));
+	w->ev_cur = (uint64_t *)calloc(2 * w->max_manifolds + 64, sizeof(uint64_t));
+	w->ev_prev = (uint64_t *)calloc(2 * w->max_manifolds + 64, sizeof(uint64_t));
+	w->events = (uint32_t *)calloc(12 * w->max_manifolds + 6 * 64, sizeof(uint32_t));
 	return w;
 }
 
@@ -1481,6 +1488,7 @@ static void make_events(orc_world *w)
 	uint32_t n = 0;
 	for (uint32_t i = 0; i < w->nprev; i++) w->ev_cur[n++] = ((uint64_t)w->prev[i].a << 32) | w->prev[i].b;
 	for (uint32_t i = 0; i < w->nsens; i++) w->ev_cur[n++] = w->sens[i];
+	for (uint32_t i = 0; i < w->ch_nkeys; i++) w->ev_cur[n++] = w->ch_keys[i];
 	qsort(w->ev_cur, n, sizeof(uint64_t), cmp_u64);
 	uint32_t m = 0;
 	for (uint32_t i = 0; i < n; i++)
@@ -1588,4 +1596,372 @@ int orc_step_many(orc_world **ws, uint32_t n, float dt, int collision_steps, int
 	stepjob_t j = {ws, dt, collision_steps, ticks, 0};
 	parallel_for((int64_t)n, step_range, &j);
 	return j.err;
+}
+
+
+/* ------------------------------------------------------------------------------------------ player character
+ *
+ * The engine's player is a JPH_CharacterVirtual: a capsule (half height 0.2, radius 0.25) that is not a body of the
+ * physics system; every tick MovePlayer sets its velocity and UpdatePlayer calls JPH_CharacterVirtual_ExtendedUpdate
+ * BEFORE the physics update (engine/src/physics/PlayerPhysics.c:173-194,203-295,439-453; MapPhysics.c:66-77), and a
+ * contact listener turns its contacts into actor callbacks (PlayerPhysics.c:89-152).  Jolt's CharacterVirtual is not
+ * available here (PARITY UNPINNED, see orc.h); this restates the behaviour the engine relies on with a discrete
+ * collide-and-slide:
+ *   move by v * dt; up to 8 times: find the deepest penetration of the capsule against the static triangles and the
+ *   solid bodies, push the capsule out along that contact normal and remove the velocity component into it;
+ *   ground state from the contact normals (max slope 50 degrees) and, failing that, from a 5 cm probe below;
+ *   contacts (for the callbacks): every body or static mesh within the contact margin of the capsule, sensors included.
+ * The stick-to-floor step of ExtendedUpdate is restated as closing gaps of up to 5 cm over walkable ground; stair
+ * stepping is not. */
+
+#define CH_MAX_ITERS 8
+#define CH_CONTACT_MARGIN 0.02f
+#define CH_GROUND_PROBE 0.05f
+#define CH_ID 0x3FFFFFu
+
+static float clamp01(float t) { return t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t); }
+
+/* closest points of segments p1-q1 and p2-q2 (Ericson, Real-Time Collision Detection 5.1.9) */
+static void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3 *c1, v3 *c2)
+{
+	v3 d1 = vsub(q1, p1), d2 = vsub(q2, p2), r = vsub(p1, p2);
+	float a = vdot(d1, d1), e = vdot(d2, d2), f = vdot(d2, r);
+	float s, t;
+	const float EPS = 1.0e-12f;
+	if (a <= EPS && e <= EPS)
+	{
+		s = t = 0.0f;
+	}
+	else if (a <= EPS)
+	{
+		s = 0.0f;
+		t = clamp01(f / e);
+	}
+	else
+	{
+		float c = vdot(d1, r);
+		if (e <= EPS)
+		{
+			t = 0.0f;
+			s = clamp01(-c / a);
+		}
+		else
+		{
+			float b = vdot(d1, d2);
+			float denom = (a * e) - (b * b);
+			s = denom != 0.0f ? clamp01(((b * f) - (c * e)) / denom) : 0.0f;
+			t = ((b * s) + f) / e;
+			if (t < 0.0f)
+			{
+				t = 0.0f;
+				s = clamp01(-c / a);
+			}
+			else if (t > 1.0f)
+			{
+				t = 1.0f;
+				s = clamp01((b - c) / a);
+			}
+		}
+	}
+	*c1 = vadd(p1, vscale(d1, s));
+	*c2 = vadd(p2, vscale(d2, t));
+}
+
+/* closest points between segment p0-p1 and a triangle; returns squared distance (0 when the segment pierces it) */
+static float seg_tri(v3 p0, v3 p1, v3 a, v3 b, v3 c, v3 *cs, v3 *ct)
+{
+	/* piercing: the segment as a ray of length 1 */
+	{
+		v3 d = vsub(p1, p0), e1 = vsub(b, a), e2 = vsub(c, a);
+		v3 pv = vcross(d, e2);
+		float det = vdot(e1, pv);
+		if (fabsf(det) >= 1.0e-12f)
+		{
+			float inv = 1.0f / det;
+			v3 tv = vsub(p0, a);
+			float u = vdot(tv, pv) * inv;
+			if (u >= 0.0f && u <= 1.0f)
+			{
+				v3 q = vcross(tv, e1);
+				float v = vdot(d, q) * inv;
+				if (v >= 0.0f && (u + v) <= 1.0f)
+				{
+					float t = vdot(e2, q) * inv;
+					if (t >= 0.0f && t <= 1.0f)
+					{
+						*cs = *ct = vadd(p0, vscale(d, t));
+						return 0.0f;
+					}
+				}
+			}
+		}
+	}
+	float best = 3.0e38f;
+	const v3 tv[3] = {a, b, c};
+	for (int i = 0; i < 3; i++)
+	{
+		v3 x, y;
+		seg_seg(p0, p1, tv[i], tv[(i + 1) % 3], &x, &y);
+		float d2 = vlen2(vsub(x, y));
+		if (d2 < best) { best = d2; *cs = x; *ct = y; }
+	}
+	const v3 ends[2] = {p0, p1};
+	for (int i = 0; i < 2; i++)
+	{
+		v3 y = closest_on_tri(ends[i], a, b, c);
+		float d2 = vlen2(vsub(ends[i], y));
+		if (d2 < best) { best = d2; *cs = ends[i]; *ct = y; }
+	}
+	return best;
+}
+
+/* closest points between segment p0-p1 and an oriented box; returns squared distance (0 when the segment enters it) */
+static float seg_box(v3 p0, v3 p1, const body_t *B, v3 *cs, v3 *cb)
+{
+	m33 R = qmat(B->q);
+	v3 l0 = mtmul(&R, vsub(p0, B->x)), l1 = mtmul(&R, vsub(p1, B->x));
+	const v3 he = B->he;
+	/* slab test of the segment against the box */
+	{
+		v3 d = vsub(l1, l0);
+		float tn = 0.0f, tf = 1.0f;
+		int hit = 1;
+		for (int k = 0; k < 3 && hit; k++)
+		{
+			float ok = vget(l0, k), dk = vget(d, k), hk = vget(he, k);
+			if (dk == 0.0f)
+			{
+				if (ok < -hk || ok > hk) hit = 0;
+				continue;
+			}
+			float inv = 1.0f / dk;
+			float t1 = (-hk - ok) * inv, t2 = (hk - ok) * inv;
+			if (t1 > t2) { float tt = t1; t1 = t2; t2 = tt; }
+			if (t1 > tn) tn = t1;
+			if (t2 < tf) tf = t2;
+			if (tn > tf) hit = 0;
+		}
+		if (hit)
+		{
+			v3 lp = vadd(l0, vscale(d, tn));
+			*cs = *cb = vadd(B->x, mmul(&R, lp));
+			return 0.0f;
+		}
+	}
+	float best = 3.0e38f;
+	v3 bs = l0, bb = l0;
+	const v3 ends[2] = {l0, l1};
+	for (int i = 0; i < 2; i++)
+	{
+		v3 l = ends[i];
+		v3 q = V(fminf(fmaxf(l.x, -he.x), he.x), fminf(fmaxf(l.y, -he.y), he.y), fminf(fmaxf(l.z, -he.z), he.z));
+		float d2 = vlen2(vsub(l, q));
+		if (d2 < best) { best = d2; bs = l; bb = q; }
+	}
+	for (int k = 0; k < 3; k++)
+	{
+		const int u = (k + 1) % 3, v = (k + 2) % 3;
+		for (int sgn = 0; sgn < 4; sgn++)
+		{
+			float e0[3], e1[3];
+			const float su = (sgn & 1) ? 1.0f : -1.0f, sv = (sgn & 2) ? 1.0f : -1.0f;
+			e0[k] = -vget(he, k); e1[k] = vget(he, k);
+			e0[u] = e1[u] = su * vget(he, u);
+			e0[v] = e1[v] = sv * vget(he, v);
+			v3 x, y;
+			seg_seg(l0, l1, V(e0[0], e0[1], e0[2]), V(e1[0], e1[1], e1[2]), &x, &y);
+			float d2 = vlen2(vsub(x, y));
+			if (d2 < best) { best = d2; bs = x; bb = y; }
+		}
+	}
+	*cs = vadd(B->x, mmul(&R, bs));
+	*cb = vadd(B->x, mmul(&R, bb));
+	return best;
+}
+
+static float seg_point(v3 p0, v3 p1, v3 c, v3 *cs)
+{
+	v3 d = vsub(p1, p0);
+	float a = vdot(d, d);
+	float t = a > 1.0e-12f ? clamp01(vdot(vsub(c, p0), d) / a) : 0.0f;
+	*cs = vadd(p0, vscale(d, t));
+	return vlen2(vsub(*cs, c));
+}
+
+void orc_character_create(orc_world *w, const float pos[3], float half_height, float radius, float max_slope_deg)
+{
+	w->ch_alive = 1;
+	w->ch_x = V(pos[0], pos[1], pos[2]);
+	w->ch_v = V(0, 0, 0);
+	w->ch_hh = half_height;
+	w->ch_r = radius;
+	w->ch_cos_slope = cosf(max_slope_deg * 0.0174532925f);
+	w->ch_ground = 3;
+	w->ch_ground_body = ORC_INVALID;
+	w->ch_ground_n = V(0, 1, 0);
+	w->ch_nkeys = 0;
+}
+void orc_character_destroy(orc_world *w) { w->ch_alive = 0; w->ch_nkeys = 0; }
+void orc_character_set_velocity(orc_world *w, const float v[3]) { w->ch_v = V(v[0], v[1], v[2]); }
+void orc_character_set_position(orc_world *w, const float p[3]) { w->ch_x = V(p[0], p[1], p[2]); }
+void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body)
+{
+	pos[0] = w->ch_x.x; pos[1] = w->ch_x.y; pos[2] = w->ch_x.z;
+	vel[0] = w->ch_v.x; vel[1] = w->ch_v.y; vel[2] = w->ch_v.z;
+	*ground = w->ch_ground;
+	*ground_body = w->ch_ground_body;
+}
+
+/* does the character's layer (PLAYER) collide with this body as a solid obstacle? */
+static int ch_solid(const body_t *b)
+{
+	return b->alive && b->shape != ORC_SHAPE_EMPTY && !b->sensor && (b->layer == 0 || b->layer == 1);
+}
+
+/* deepest penetration of the capsule at x; id = triangle index or ORC_STATIC_BODY_BASE-less body id + 0x80000000 */
+static float ch_deepest(const orc_world *w, v3 x, v3 *n_out, uint32_t *hit_body)
+{
+	const v3 p0 = V(x.x, x.y - w->ch_hh, x.z), p1 = V(x.x, x.y + w->ch_hh, x.z);
+	const float r = w->ch_r;
+	float best = 0.0f;
+	uint32_t best_id = 0xFFFFFFFFu;
+	for (uint32_t t = 0; t < w->ntris; t++)
+	{
+		const tri_t *T = &w->tris[t];
+		if (p0.x - r > T->hi.x || p1.x + r < T->lo.x || p0.y - r > T->hi.y || p1.y + r < T->lo.y || p0.z - r > T->hi.z ||
+			p1.z + r < T->lo.z)
+			continue;
+		v3 cs, ct;
+		float d2 = seg_tri(p0, p1, T->v0, T->vb, T->vc, &cs, &ct);
+		float dist = sqrtf(d2);
+		float pen = r - dist;
+		if (pen > best || (pen == best && pen > 0.0f && t < best_id))
+		{
+			v3 n;
+			if (dist > 1.0e-6f) n = vscale(vsub(cs, ct), 1.0f / dist);
+			else n = vdot(vsub(x, T->v0), T->n) >= 0.0f ? T->n : vneg(T->n);
+			best = pen;
+			best_id = t;
+			*n_out = n;
+			*hit_body = ORC_STATIC_BODY_BASE + T->body;
+		}
+	}
+	for (uint32_t i = 0; i < w->max_bodies; i++)
+	{
+		const body_t *B = &w->bodies[i];
+		if (!ch_solid(B)) continue;
+		v3 cs, cb;
+		float d2, rr = r;
+		if (B->shape == ORC_SHAPE_BOX) d2 = seg_box(p0, p1, B, &cs, &cb);
+		else
+		{
+			d2 = seg_point(p0, p1, B->x, &cs);
+			cb = B->x;
+			rr = r + B->he.x;
+		}
+		float dist = sqrtf(d2);
+		float pen = rr - dist;
+		const uint32_t id = 0x80000000u + i;
+		if (pen > best || (pen == best && pen > 0.0f && id < best_id))
+		{
+			v3 n;
+			if (dist > 1.0e-6f) n = vscale(vsub(cs, cb), 1.0f / dist);
+			else
+			{
+				v3 d = vsub(x, B->x);
+				float l = vlen(d);
+				n = l > 1.0e-6f ? vscale(d, 1.0f / l) : V(0, 1, 0);
+			}
+			best = pen;
+			best_id = id;
+			*n_out = n;
+			*hit_body = i;
+		}
+	}
+	return best;
+}
+
+void orc_character_update(orc_world *w, float dt)
+{
+	if (!w->ch_alive) return;
+	v3 x = vadd(w->ch_x, vscale(w->ch_v, dt));
+	v3 v = w->ch_v;
+	uint32_t ground = 3, ground_body = ORC_INVALID;
+	v3 ground_n = V(0, 1, 0);
+	for (int it = 0; it < CH_MAX_ITERS; it++)
+	{
+		v3 n;
+		uint32_t hb;
+		float pen = ch_deepest(w, x, &n, &hb);
+		if (!(pen > 0.0f)) break;
+		x = vadd(x, vscale(n, pen));
+		float vn = vdot(v, n);
+		if (vn < 0.0f) v = vsub(v, vscale(n, vn));
+		if (n.y >= w->ch_cos_slope)
+		{
+			ground = 0;
+			ground_body = hb;
+			ground_n = n;
+		}
+		else if (n.y > 0.0f && ground != 0)
+		{
+			ground = 1;
+			ground_body = hb;
+			ground_n = n;
+		}
+	}
+	if (ground == 3)
+	{
+		v3 n;
+		uint32_t hb;
+		float pen = ch_deepest(w, V(x.x, x.y - CH_GROUND_PROBE, x.z), &n, &hb);
+		if (pen > 0.0f && n.y > 0.0f)
+		{
+			ground = n.y >= w->ch_cos_slope ? 0u : 1u;
+			ground_body = hb;
+			ground_n = n;
+			/* stick to the floor (the stickToFloorStepDown of ExtendedUpdate, PlayerPhysics.c:439-446): close the gap
+			 * when standing on walkable ground and not moving up */
+			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, CH_GROUND_PROBE - pen);
+		}
+	}
+	w->ch_x = x;
+	w->ch_v = v;
+	w->ch_ground = ground;
+	w->ch_ground_body = ground_body;
+	w->ch_ground_n = ground_n;
+	/* contacts for the callbacks: bodies (sensors included) and static meshes within the contact margin */
+	const v3 p0 = V(x.x, x.y - w->ch_hh, x.z), p1 = V(x.x, x.y + w->ch_hh, x.z);
+	const float reach = w->ch_r + CH_CONTACT_MARGIN;
+	w->ch_nkeys = 0;
+	for (uint32_t i = 0; i < w->max_bodies && w->ch_nkeys < 64; i++)
+	{
+		const body_t *B = &w->bodies[i];
+		if (!B->alive || B->shape == ORC_SHAPE_EMPTY || !(B->layer == 0 || B->layer == 1 || B->layer == 3)) continue;
+		v3 cs, cb;
+		float d2, rr = reach;
+		if (B->shape == ORC_SHAPE_BOX) d2 = seg_box(p0, p1, B, &cs, &cb);
+		else
+		{
+			d2 = seg_point(p0, p1, B->x, &cs);
+			rr = reach + B->he.x;
+		}
+		if (d2 <= rr * rr) w->ch_keys[w->ch_nkeys++] = ((uint64_t)i << 32) | CH_ID;
+	}
+	uint32_t last_sb = ORC_INVALID;
+	for (uint32_t t = 0; t < w->ntris && w->ch_nkeys < 64; t++)
+	{
+		const tri_t *T = &w->tris[t];
+		if (T->body == last_sb) continue; /* one contact per static mesh; triangles of a mesh are contiguous */
+		if (p0.x - reach > T->hi.x || p1.x + reach < T->lo.x || p0.y - reach > T->hi.y || p1.y + reach < T->lo.y ||
+			p0.z - reach > T->hi.z || p1.z + reach < T->lo.z)
+			continue;
+		v3 cs, ct;
+		float d2 = seg_tri(p0, p1, T->v0, T->vb, T->vc, &cs, &ct);
+		if (d2 <= reach * reach)
+		{
+			w->ch_keys[w->ch_nkeys++] = ((uint64_t)CH_ID << 32) | (ORC_STATIC_BODY_BASE + T->body);
+			last_sb = T->body;
+		}
+	}
 }

@@ -85,6 +85,15 @@ uint32_t orc_body_active(const orc_world *w, uint32_t id);
 uint32_t orc_manifold_count(const orc_world *w);
 /* contact events of the last step: triples (a, b, kind) */
 uint32_t orc_events(const orc_world *w, uint32_t *out, uint32_t cap);
+/* player character: a capsule moved by discrete collide-and-slide before the tick (see the character section of orc.c);
+ * ground: 0 on ground, 1 on steep ground, 3 in air (JPH_GroundState values); its contacts appear in orc_events with
+ * the pseudo body id 0x3FFFFF */
+void orc_character_create(orc_world *w, const float pos[3], float half_height, float radius, float max_slope_deg);
+void orc_character_destroy(orc_world *w);
+void orc_character_set_velocity(orc_world *w, const float v[3]);
+void orc_character_set_position(orc_world *w, const float p[3]);
+void orc_character_update(orc_world *w, float dt);
+void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body);
 /* closest-hit rays, brute force over every static triangle and every body */
 void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);
 uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_body, uint32_t cap);

@@ -111,6 +111,12 @@ def lib():
     L.orc_step.restype = C.c_int
     L.orc_step.argtypes = [C.c_void_p, C.c_float, C.c_int]
     L.orc_body_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_character_create.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
+    L.orc_character_destroy.argtypes = [C.c_void_p]
+    L.orc_character_set_velocity.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.orc_character_set_position.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.orc_character_update.argtypes = [C.c_void_p, C.c_float]
+    L.orc_character_get.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_events.restype = C.c_uint32
     L.orc_events.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.orc_manifold_count.restype = C.c_uint32
@@ -180,6 +186,25 @@ class World:
         for i in range(n):
             self.L.orc_body_get(self.h, i, xf[i].ctypes.data, vel[i].ctypes.data)
         return xf, vel
+
+    # ---- player character (capsule), PlayerPhysics.c:173-194
+    def character_create(self, pos, half_height=0.2, radius=0.25, max_slope_deg=50.0):
+        self.L.orc_character_create(self.h, (C.c_float * 3)(*pos), half_height, radius, max_slope_deg)
+
+    def character_set_velocity(self, v):
+        self.L.orc_character_set_velocity(self.h, (C.c_float * 3)(*v))
+
+    def character_set_position(self, p):
+        self.L.orc_character_set_position(self.h, (C.c_float * 3)(*p))
+
+    def character_update(self, dt=1.0 / 60.0):
+        self.L.orc_character_update(self.h, dt)
+
+    def character_get(self):
+        p, v = (C.c_float * 3)(), (C.c_float * 3)()
+        g, gb = C.c_uint32(), C.c_uint32()
+        self.L.orc_character_get(self.h, p, v, C.byref(g), C.byref(gb))
+        return np.array(list(p), np.float32), np.array(list(v), np.float32), g.value, gb.value
 
     def events(self) -> np.ndarray:
         """(n, 3) triples a, b, kind of the last tick."""

@@ -1,0 +1,117 @@
+"""GPU parity: the player character (capsule collide-and-slide, ground state, contact callbacks) through the C ABI vs
+the oracle.  Call order per tick is MapFixedUpdate's: MovePlayer sets the velocity, UpdatePlayer advances the
+character, then the physics update (engine/src/physics/MapPhysics.c:66-108, PlayerPhysics.c:283-294,447)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(gpx, orc, scenes, static="stacked", cap=8, worlds=1):
+    g = gpx.World(worlds=worlds, max_bodies=cap)
+    os_ = [orc.World(cap) for _ in range(worlds)]
+    for pos, tris in scenes.load_static(static):
+        g.add_mesh(pos, tris)
+        for o in os_:
+            o.add_mesh(pos, tris)
+    g.commit()
+    return g, os_
+
+
+def _move(side, v, gravity=True):
+    p, vel, ground, _ = side.character_get()
+    vy = 0.0
+    if gravity and ground != 0:
+        vy = float(vel[1]) + (-9.81 / 60.0)
+    side.character_set_velocity((v[0], vy, v[2]))
+
+
+def _same(g, o, what):
+    pg, vg, gg, bg = g.character_get()
+    po, vo, go, bo = o.character_get()
+    assert np.array_equal(pg.view(np.uint32), po.view(np.uint32)), f"{what}: position {pg} vs {po}"
+    assert np.array_equal(vg.view(np.uint32), vo.view(np.uint32)), f"{what}: velocity {vg} vs {vo}"
+    assert (gg, bg) == (go, bo), f"{what}: ground {gg}/{bg:#x} vs {go}/{bo:#x}"
+
+
+def test_character_walk_matches_oracle_on_stacked_map(gpx, orc, scenes):
+    g, (o,) = _pair(gpx, orc, scenes)
+    descs = [dict(position=(1.0, -1.3, -1.5), motion_type=0, layer=0),                                        # crate
+             dict(position=(-1.0, -1.25, -1.5), half_extents=(0.25, 0.25, 0.25), motion_type=0, layer=3, is_sensor=1),  # coin
+             dict(position=(0.3, -1.2, 0.5)),                                                                 # dynamic box
+             dict(shape=2, half_extents=(0.3, 0, 0), position=(0.0, -1.2, -3.0), motion_type=0, layer=0)]      # pillar cap
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    g.enable_events()
+    g.character_create((0.0, 0.0, -1.5))
+    o.character_create((0.0, 0.0, -1.5))
+    rng = np.random.default_rng(3)
+    heading = np.array([1.5, 0.0, 0.0])
+    seen = set()
+    for tick in range(1, 361):
+        if tick % 45 == 0:
+            a = rng.uniform(0, 2 * np.pi)
+            heading = np.array([2.5 * np.cos(a), 0.0, 2.5 * np.sin(a)])
+        for side in (g, o):
+            _move(side, heading if tick > 40 else (0.0, 0.0, 0.0))
+            side.character_update()
+        assert g.step() == 0 and o.step() == 0
+        _same(g, o, f"tick {tick}")
+        eg = g.poll_events()
+        got = np.stack([eg["body_a"], eg["body_b"], eg["kind"]], axis=1) if len(eg) else np.zeros((0, 3), np.uint32)
+        assert np.array_equal(got, o.events()), f"tick {tick}: events differ"
+        for a_, b_, k_ in got:
+            if gpx.lib() and (a_ == 0x3FFFFF or b_ == 0x3FFFFF):
+                seen.add((int(a_), int(b_), int(k_)))
+    p, v, ground, gb = g.character_get()
+    assert ground == 0 and gb >= gpx.STATIC_BODY_BASE                    # standing on some sector's floor mesh
+    assert any(a == 0x3FFFFF and b >= gpx.STATIC_BODY_BASE for a, b, k in seen)
+    # bodies keep matching too (the character does not push them)
+    assert np.array_equal(g.transforms()[0, :4].view(np.uint32), o.state(4)[0].view(np.uint32))
+
+
+def test_character_lands_slides_and_is_blocked(gpx, orc, scenes):
+    g, (o,) = _pair(gpx, orc, scenes)
+    d = dict(position=(1.0, -1.3, -1.5), motion_type=0, layer=0)
+    assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    g.character_create((0.0, 0.0, -1.5))
+    o.character_create((0.0, 0.0, -1.5))
+    for tick in range(90):
+        for side in (g, o):
+            _move(side, (0.0, 0.0, 0.0))
+            side.character_update()
+    _same(g, o, "landing")
+    p, v, ground, gb = g.character_get()
+    assert abs(p[1] - (-1.5 + 0.45)) < 1e-3 and ground == 0 and gb >= gpx.STATIC_BODY_BASE
+    for tick in range(60):
+        for side in (g, o):
+            _move(side, (1.5, 0.0, 0.0))
+            side.character_update()
+    _same(g, o, "crate")
+    assert abs(g.character_get()[0][0] - (1.0 - 0.2 - 0.25)) < 2e-3       # stopped at the crate's face
+    for tick in range(150):
+        for side in (g, o):
+            _move(side, (0.7, 0.0, -3.0))
+            side.character_update()
+    _same(g, o, "wall")
+    assert abs(g.character_get()[0][2] - (-4.0 + 0.25)) < 2e-3            # held at radius distance from the z = -4 wall
+
+
+def test_characters_of_an_ensemble_are_independent(gpx, orc, scenes):
+    W = 5
+    g, os_ = _pair(gpx, orc, scenes, worlds=W)
+    for wi, o in enumerate(os_):
+        g.character_create((0.2 * wi, -1.0, -1.5), world=wi)
+        o.character_create((0.2 * wi, -1.0, -1.5))
+    for tick in range(80):
+        for wi, o in enumerate(os_):
+            p, vel, ground, _ = o.character_get()
+            v = (0.5 * (wi - 2), 0.0 if ground == 0 else float(vel[1]) - 9.81 / 60.0, -0.4 * wi)
+            o.character_set_velocity(v)
+            o.character_update()
+            g.character_set_velocity(v, world=wi)
+        g.character_update()
+    for wi, o in enumerate(os_):
+        pg, vg, gg, bg = g.character_get(world=wi)
+        po, vo, go, bo = o.character_get()
+        assert np.array_equal(pg.view(np.uint32), po.view(np.uint32)) and (gg, bg) == (go, bo), f"world {wi}"

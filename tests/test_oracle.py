@@ -202,3 +202,71 @@ def test_step_many_equals_sequential_steps(orc, scenes):
             o.step()
     for x, y in zip(a, b):
         assert np.array_equal(x.state(8)[0].view(np.uint32), y.state(8)[0].view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ player character
+
+def _walk(o, v, ticks, gravity=True):
+    """MovePlayer + UpdatePlayer for `ticks` ticks: horizontal velocity v, gravity while not on the ground
+    (engine/src/physics/PlayerPhysics.c:283-294)."""
+    for _ in range(ticks):
+        p, vel, ground, _ = o.character_get()
+        vy = 0.0
+        if gravity and ground != 0:
+            vy = float(vel[1]) + (-9.81 / 60.0)
+        o.character_set_velocity((v[0], vy, v[2]))
+        o.character_update()
+    return o.character_get()
+
+
+def test_character_lands_and_stands_on_the_sector_floor(orc, scenes):
+    o = _stacked_world(orc, scenes)
+    o.character_create((0.0, 0.0, -1.5))
+    p, v, ground, gb = o.character_get()
+    assert ground == 3                                   # in air until the first update finds the floor
+    p, v, ground, gb = _walk(o, (0.0, 0.0, 0.0), 90)
+    # capsule: half height 0.2 + radius 0.25 above the floor at y = -1.5
+    assert abs(p[1] - (-1.5 + 0.45)) < 1e-3 and ground == 0 and gb >= orc.STATIC_BASE
+    assert abs(p[0]) < 1e-6 and abs(p[2] + 1.5) < 1e-6 and abs(v[1]) < 1e-6
+
+
+def test_character_walks_and_slides_along_a_wall(orc, scenes):
+    o = _stacked_world(orc, scenes)
+    o.character_create((0.0, -1.05, -1.5))
+    _walk(o, (0.0, 0.0, 0.0), 5)
+    # sector 0 is the triangle (0,4) (4,-4) (-4,-4) in xz (mapSources/stacked.json): its z = -4 wall stops the capsule
+    p, v, ground, _ = _walk(o, (0.7, 0.0, -3.0), 120)
+    assert ground == 0
+    assert abs(p[2] - (-4.0 + 0.25)) < 2e-3              # held at radius distance from the wall
+    assert p[0] > 0.7                                    # kept sliding along it
+    assert abs(p[1] - (-1.05)) < 2e-3
+
+
+def test_character_is_blocked_by_boxes_and_reports_contacts(orc, scenes):
+    o = _stacked_world(orc, scenes)
+    o.create(orc.body_desc(position=(1.0, -1.3, -1.5), motion_type=orc.MOTION_STATIC, layer=orc.LAYER_STATIC))          # crate
+    o.create(orc.body_desc(position=(-1.0, -1.25, -1.5), half_extents=(0.25, 0.25, 0.25), motion_type=orc.MOTION_STATIC,
+                           layer=orc.LAYER_SENSOR, is_sensor=1))                                                        # coin
+    o.character_create((0.0, -1.05, -1.5))
+    for _ in range(3):
+        _walk(o, (0.0, 0.0, 0.0), 1)
+        o.step()
+    seen = {1: set(), 2: set(), 3: set()}
+
+    def tick(v):
+        _walk(o, v, 1)
+        o.step()
+        for a, b, k in o.events():
+            seen[int(k)].add((int(a), int(b)))
+    for _ in range(60):
+        tick((1.5, 0.0, 0.0))
+    p, _, _, _ = o.character_get()
+    assert abs(p[0] - (1.0 - 0.2 - 0.25)) < 2e-3         # stopped at the crate's face
+    assert (0, 0x3FFFFF) in seen[1] and (0, 0x3FFFFF) in seen[2]
+    for _ in range(90):
+        tick((-1.5, 0.0, 0.0))
+    assert (0, 0x3FFFFF) in seen[3]                      # left the crate
+    assert (1, 0x3FFFFF) in seen[1]                      # walked into the coin sensor (not blocked by it)
+    p, _, _, _ = o.character_get()
+    assert p[0] < -1.0
+    assert any(a == 0x3FFFFF and b >= orc.STATIC_BASE for a, b in seen[2])   # standing on the floor mesh throughout
