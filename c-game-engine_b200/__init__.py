@@ -157,6 +157,8 @@ def lib() -> C.CDLL:
         "gpx_static_add_mesh": (i32, [vp, C.POINTER(Transform), vp, u64, f32, u64, C.POINTER(u32)]),
         "gpx_static_commit": (i32, [vp]),
         "gpx_static_load_gmap": (i32, [vp, vp, u64]),
+        "gpx_static_load_gmap_container": (i32, [vp, vp, u64]),
+        "gpx_static_load_gmap_file": (i32, [vp, C.c_char_p]),
         "gpx_static_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "gpx_body_create": (u32, [vp, u32, C.POINTER(BodyDesc)]),
         "gpx_body_create_all": (i32, [vp, C.POINTER(BodyDesc), u32, vp, vp, vp]),
@@ -177,6 +179,7 @@ def lib() -> C.CDLL:
         "gpx_read_stats": (i32, [vp, vp]),
         "gpx_raycast_batch": (i32, [vp, vp, u64, vp]),
         "gpx_raycast_batch_device": (i32, [vp, vp, u64, vp]),
+        "gpx_raycast_batch_async": (i32, [vp, vp, u64, vp]),
         "gpx_raycast_transform": (i32, [vp, u32, C.POINTER(Transform), f32, u32, vp]),
         "gpx_device_alloc": (vp, [u64]),
         "gpx_device_free": (None, [vp]),
@@ -269,6 +272,13 @@ class World:
             raise GpxError(f"gpx_static_load_gmap failed ({rc})")
         return rc
 
+    def load_gmap_file(self, path: str) -> int:
+        """A .gmap asset file: container header + gzip + map layout, parsed by the library (AssetReader.c, MapLoader.c)."""
+        rc = self.L.gpx_static_load_gmap_file(self.h, path.encode())
+        if rc < 0:
+            raise GpxError(f"gpx_static_load_gmap_file({path}) failed ({rc})")
+        return rc
+
     def commit(self):
         _check(self.L.gpx_static_commit(self.h), "gpx_static_commit")
 
@@ -359,6 +369,11 @@ class World:
         """gpx_raycast_batch on caller-owned host arrays (e.g. pinned ones from pinned_array): no allocation."""
         assert rays.dtype == RAY_DTYPE and hits.dtype == HIT_DTYPE and len(hits) >= len(rays)
         _check(self.L.gpx_raycast_batch(self.h, rays.ctypes.data, len(rays), hits.ctypes.data), "gpx_raycast_batch")
+
+    def raycast_into_async(self, rays: np.ndarray, hits: np.ndarray) -> None:
+        """gpx_raycast_batch_async on pinned arrays: hits are valid after the next sync()."""
+        assert rays.dtype == RAY_DTYPE and hits.dtype == HIT_DTYPE and len(hits) >= len(rays)
+        _check(self.L.gpx_raycast_batch_async(self.h, rays.ctypes.data, len(rays), hits.ctypes.data), "gpx_raycast_batch_async")
 
     def raycast_device(self, d_rays: int, n: int, d_hits: int) -> None:
         """gpx_raycast_batch_device: buffers already resident in HBM; asynchronous on the world's stream."""

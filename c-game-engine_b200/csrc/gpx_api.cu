@@ -7,6 +7,8 @@
 #include <string>
 #include <unordered_map>
 
+#include <zlib.h>
+
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
 
@@ -422,6 +424,51 @@ int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size)
 	return added;
 }
 
+/* The asset container around a map (engine/src/assets/AssetReader.c:150-257, AssetReader.h:15-17): 23-byte header
+ * <u32 magic "GAME"><u8 version = 2><u8 type><u8 typeVersion><u64 rawSize><u64 gzSize>, then one gzip member.  The
+ * same size checks as DecompressAsset; the decompressed body goes to gpx_static_load_gmap. */
+int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t size)
+{
+	if (!w || !blob) return -GPX_ERR_INVALID_ARG;
+	const uint64_t HEADER = 23;
+	if (size < HEADER) return -GPX_ERR_INVALID_ARG;
+	uint32_t magic;
+	uint64_t raw_size, gz_size;
+	memcpy(&magic, blob, 4);
+	memcpy(&raw_size, blob + 7, 8);
+	memcpy(&gz_size, blob + 15, 8);
+	if (magic != 0x454D4147u || blob[4] != 2u) return -GPX_ERR_INVALID_ARG;
+	if (size - HEADER != gz_size || raw_size > (1ull << 32)) return -GPX_ERR_INVALID_ARG;
+	std::vector<uint8_t> body((size_t)raw_size);
+	z_stream zs;
+	memset(&zs, 0, sizeof(zs));
+	if (inflateInit2(&zs, MAX_WBITS | 16) != Z_OK) return -GPX_ERR_INVALID_ARG;
+	zs.next_in = const_cast<Bytef *>(blob + HEADER);
+	zs.avail_in = (uInt)gz_size;
+	zs.next_out = body.data();
+	zs.avail_out = (uInt)raw_size;
+	const int zrc = inflate(&zs, Z_FINISH);
+	const uint64_t got = zs.total_out;
+	inflateEnd(&zs);
+	if (zrc != Z_STREAM_END || got != raw_size) return -GPX_ERR_INVALID_ARG;
+	return gpx_static_load_gmap(w, body.data(), raw_size);
+}
+
+int gpx_static_load_gmap_file(gpx_world *w, const char *path)
+{
+	if (!w || !path) return -GPX_ERR_INVALID_ARG;
+	FILE *f = fopen(path, "rb");
+	if (!f) return -GPX_ERR_INVALID_ARG;
+	fseek(f, 0, SEEK_END);
+	const long n = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	std::vector<uint8_t> blob(n > 0 ? (size_t)n : 0);
+	const size_t got = blob.empty() ? 0 : fread(blob.data(), 1, blob.size(), f);
+	fclose(f);
+	if (got != blob.size()) return -GPX_ERR_INVALID_ARG;
+	return gpx_static_load_gmap_container(w, blob.data(), blob.size());
+}
+
 /* ---- bodies */
 
 static inline bool valid_slot(const gpx_world *w, uint32_t world, uint32_t body)
@@ -704,15 +751,14 @@ int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void 
 	return launch_raycast(w, d_rays, n, d_hits);
 }
 
-int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
+static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
 {
-	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
-	if (n == 0) return GPX_OK;
 	{
 		std::lock_guard<std::mutex> lk(w->mu);
 		cudaSetDevice(w->device);
 		if (n > w->ray_cap)
 		{
+			GPX_CUDA(cudaStreamSynchronize(w->stream));  // a batch still in flight may be using the old buffers
 			cudaFree(w->d_rays);
 			cudaFree(w->d_hits);
 			w->d_rays = w->d_hits = nullptr;
@@ -726,8 +772,24 @@ int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hi
 	int rc = gpx_raycast_batch_device(w, w->d_rays, n, w->d_hits);
 	if (rc != GPX_OK) return rc;
 	GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream));
+	return GPX_OK;
+}
+
+int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
+{
+	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
+	if (n == 0) return GPX_OK;
+	int rc = raycast_enqueue(w, rays, n, hits);
+	if (rc != GPX_OK) return rc;
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;
+}
+
+int gpx_raycast_batch_async(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
+{
+	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
+	if (n == 0) return GPX_OK;
+	return raycast_enqueue(w, rays, n, hits);
 }
 
 int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *origin, float max_distance, uint32_t mask,

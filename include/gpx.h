@@ -177,6 +177,10 @@ int gpx_static_commit(gpx_world *w);
 /* Parse a decompressed .gmap collision section straight into the static soup (MapLoader.c:200-273).
  * `body` points at the whole decompressed map; returns number of static bodies added or negative error. */
 int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size);
+/* The same from the asset container (23-byte header + gzip member; engine/src/assets/AssetReader.c:150-257), in memory
+ * or on disk (LoadAsset, AssetReader.c:271-305).  Same return value. */
+int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t size);
+int gpx_static_load_gmap_file(gpx_world *w, const char *path);
 
 /* ---- bodies --------------------------------------------------------------------------------------------------- */
 
@@ -285,6 +289,10 @@ int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uin
 /* Batched closest-hit rays (JPH_NarrowPhaseQuery_CastRay_GAME / CastRay2_GAME; PlayerPhysics.c:305, Laser.c:142).
  * Host buffers; copies are part of the call. */
 int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits);
+/* Same, but only enqueued on the world's stream: `rays` and `hits` must be page-locked (gpx_host_alloc) and stay
+ * untouched until the next gpx_sync_transforms / gpx_device_sync, which is when `hits` becomes valid.  Lets a tick's
+ * laser batch, the step and the transform readback share ONE synchronisation. */
+int gpx_raycast_batch_async(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits);
 /* Same with device-resident buffers (cudaMalloc'd by the caller or by gpx_device_alloc), async on the world's stream. */
 int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 /* Engine-style single ray: origin transform, direction = transform's local -Z. */

@@ -137,3 +137,20 @@ def test_engine_style_single_ray(gpx, orc, scenes):
     assert h["body"] == gpx.STATIC_BODY_BASE + 0 and abs(h["fraction"] * 10.0 - 4.0) < 1e-5  # wall z = -4
     h = g.raycast_transform((0, 0, 0), (0, 0, 0, 1), 3.0)
     assert h["body"] == gpx.INVALID_BODY
+
+
+def test_async_batch_is_valid_after_the_tick_sync(gpx, orc, scenes):
+    """gpx_raycast_batch_async: enqueue only; hits land in the pinned buffer by the next gpx_sync_transforms."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "stacked")
+    d = gpx.body_desc(position=(0.0, -1.0, -1.5))
+    assert g.create(d) == o.create(d)
+    rays = scenes.shapes_rays(3000, np.array([p for p, _ in meshes]), mask=gpx.RAYMASK_STATIC_DYNAMIC)
+    h_rays = gpx.pinned_array(len(rays), gpx.RAY_DTYPE)
+    h_hits = gpx.pinned_array(len(rays), gpx.HIT_DTYPE)
+    h_rays[:] = rays
+    for _ in range(5):
+        ref = o.raycast(rays)                 # rays see the state BEFORE this tick's step, as in MapFixedUpdate
+        g.raycast_into_async(h_rays, h_hits)
+        assert g.step() == 0 and o.step() == 0
+        assert g.sync() == 0
+        _assert_hits_equal(np.asarray(h_hits), ref)

@@ -193,6 +193,30 @@ def test_gmap_loader_feeds_the_same_static_soup(gpx, orc, scenes):
         assert np.array_equal(hg.view(np.uint8), ho.view(np.uint8))
 
 
+def test_gmap_asset_file_is_decoded_by_the_library(gpx, orc, scenes, tmp_path):
+    """Container header + gzip + map layout in C (AssetReader.c:150-257 + MapLoader.c:200-273), including the
+    container's integrity checks."""
+    path = f"{scenes.GOLDEN}/shapes_min.gmap"
+    g = gpx.World(worlds=1, max_bodies=8)
+    meshes = scenes.load_static("shapes")
+    assert g.load_gmap_file(path) == sum(1 for _, t in meshes if len(t))
+    g.commit()
+    o = orc.World(8)
+    for pos, tris in meshes:
+        if len(tris):
+            o.add_mesh(pos, tris)
+    rays = scenes.shapes_rays(4000, np.array([p for p, _ in meshes]))
+    assert np.array_equal(g.raycast(rays).view(np.uint8), o.raycast(rays).view(np.uint8))
+    blob = open(path, "rb").read()
+    for bad in (b"XXXX" + blob[4:], blob[:-5], blob[:4] + b"\x03" + blob[5:]):
+        p = tmp_path / "bad.gmap"
+        p.write_bytes(bad)
+        with pytest.raises(gpx.GpxError):
+            gpx.World(worlds=1, max_bodies=8).load_gmap_file(str(p))
+    with pytest.raises(gpx.GpxError):
+        g.load_gmap_file(str(tmp_path / "missing.gmap"))
+
+
 def test_manifold_capacity_overflow_reports_error(gpx, scenes):
     """JPH_PhysicsUpdateError_ContactConstraintsFull analogue: the step reports instead of corrupting memory."""
     g = gpx.World(worlds=1, max_bodies=16, max_manifolds=4)
