@@ -227,3 +227,67 @@ def test_manifold_capacity_overflow_reports_error(gpx, scenes):
         g.create(gpx.body_desc(position=tuple(p)))
     g.step()
     assert g.sync() & 4
+
+
+def test_sixty_four_bodies_in_one_world(gpx, orc, scenes):
+    """The largest ensemble world: 64 bodies on 32 lanes (two bodies per lane), 4 x 4 x 4 block collapsing."""
+    g, (o,) = _pair(gpx, orc, scenes, max_bodies=64, max_manifolds=384)
+    rng = np.random.default_rng(21)
+    for p in scenes.block_positions(4, 4, 4, 0.43):
+        d = gpx.body_desc(position=tuple(p), linear_velocity=tuple(rng.uniform(-0.3, 0.3, 3)))
+        assert g.create(d) == o.create(d)
+    for tick in range(1, 61):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 15, 60):
+            _assert_state(g.transforms()[0], o.state(64)[0], f"64 bodies tick {tick}")
+
+
+def test_empty_and_ragged_worlds(gpx, orc, scenes):
+    """Worlds of one ensemble may hold different numbers of bodies, including none; an empty map is legal too."""
+    W = 5
+    g, os_ = _pair(gpx, orc, scenes, worlds=W)
+    pos = scenes.stack_positions(8)
+    for wi, o in enumerate(os_):
+        for k in range(wi * 2):                       # 0, 2, 4, 6, 8 bodies
+            d = gpx.body_desc(position=tuple(pos[k]))
+            assert g.create(d, world=wi) == o.create(d) == k
+    for tick in range(1, 91):
+        assert g.step() == 0
+        for o in os_:
+            assert o.step() == 0
+    x = g.transforms()
+    for wi, o in enumerate(os_):
+        n = wi * 2
+        if n:
+            _assert_state(x[wi, :n], o.state(n)[0], f"ragged world {wi}")
+    st = g.stats()
+    assert list(st["awake_bodies"]) == [0, 2, 4, 6, 8] and (st["error"] == 0).all()
+    # no static geometry at all: bodies fall freely, rays miss
+    e = gpx.World(worlds=2, max_bodies=8)
+    e.commit()
+    assert e.create(gpx.body_desc(position=(0, 0, 0)), world=1) == 0
+    for _ in range(30):
+        assert e.step() == 0
+    y = e.transforms()[:, 0, 1]
+    assert y[0] == 0.0 and y[1] < -1.0
+
+
+def test_destroy_everything_then_reuse(gpx, orc, scenes):
+    g, (o,) = _pair(gpx, orc, scenes)
+    for p in scenes.stack_positions(8):
+        d = gpx.body_desc(position=tuple(p))
+        assert g.create(d) == o.create(d)
+    for _ in range(20):
+        assert g.step() == 0 and o.step() == 0
+    for b in range(8):
+        g.destroy(b)
+        o.destroy(b)
+    for _ in range(5):
+        assert g.step() == 0 and o.step() == 0
+    assert g.stats()["awake_bodies"][0] == 0 and g.stats()["manifolds"][0] == 0
+    assert g.create(gpx.body_desc(position=(0.0, -1.0, -1.5))) == o.create(orc.body_desc(position=(0.0, -1.0, -1.5))) == 0
+    with pytest.raises(gpx.GpxError):
+        g.destroy(5)                                  # already gone
+    for _ in range(60):
+        assert g.step() == 0 and o.step() == 0
+    _assert_state(g.transforms()[0, :1], o.state(1)[0], "after wipe and reuse")
