@@ -192,6 +192,7 @@ def lib() -> C.CDLL:
         "gpx_timer_end": (f32, [vp]),
         "gpx_launch_count": (u64, []),
         "gpx_debug_phase_cycles": (i32, [vp, i32, vp]),
+        "gpx_debug_wide_counters": (i32, [vp, vp]),
         "gpx_character_create": (i32, [vp, u32, C.POINTER(CharacterDesc)]),
         "gpx_character_destroy": (i32, [vp, u32]),
         "gpx_character_set_linear_velocity": (i32, [vp, u32, C.POINTER(f32)]),

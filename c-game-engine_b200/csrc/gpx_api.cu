@@ -993,6 +993,14 @@ int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uin
 	return n > capacity ? GPX_ERR_CAPACITY : GPX_OK;
 }
 
+int gpx_debug_wide_counters(gpx_world *w, uint32_t *out8)
+{
+	if (!w || !w->wide || !out8) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	return wide_counters(w, out8);
+}
+
 int gpx_debug_phase_cycles(gpx_world *w, int enable, uint64_t *out16)
 {
 	if (!w) return GPX_ERR_INVALID_ARG;

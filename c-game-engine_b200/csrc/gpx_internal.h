@@ -162,6 +162,7 @@ struct WideDevice;
 int wide_create(gpx_world *w);
 void wide_destroy(gpx_world *w);
 int launch_wide_tick(gpx_world *w, float dt, int substeps);
+int wide_counters(gpx_world *w, uint32_t *out8);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 // gpx_char.cu

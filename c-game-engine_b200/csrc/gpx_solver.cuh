@@ -422,7 +422,9 @@ __device__ __forceinline__ void unpark_con(ConPts &pt, const float4 *g)
 	}
 }
 
-__device__ __forceinline__ void warm_start(const Con &c, const ConPts &pt, const SMan &m, Vel &u)
+// `M` is any record with ln / lt1 / lt2 (and, for solve_velocity, bias) arrays: the manifold itself or a solver record
+template <typename M>
+__device__ __forceinline__ void warm_start(const Con &c, const ConPts &pt, const M &m, Vel &u)
 {
 #pragma unroll 1
 	for (int k = 0; k < c.np; k++)
@@ -434,7 +436,8 @@ __device__ __forceinline__ void warm_start(const Con &c, const ConPts &pt, const
 	}
 }
 
-__device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, SMan &m, Vel &u)
+template <typename M>
+__device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M &m, Vel &u)
 {
 	// friction first: non-penetration is more important, so it goes last
 #pragma unroll 1

@@ -38,6 +38,18 @@ constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase ker
 enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_MAXEXT_X, WC_MAXEXT_Z, WC_COLCNT = 8,
 				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_COUNT = WC_COLCUR + WIDE_MAXCOL };
 
+// Everything a velocity phase needs about one manifold, in colour order: the phases stream these records (coalesced)
+// instead of chasing list -> manifold -> bodies -> parked constants.
+struct __align__(16) SolveRec
+{
+	Con con;
+	ConPts pts;
+	float bias[4];
+	float ln[4], lt1[4], lt2[4];
+	uint32_t mi;
+};
+static_assert(sizeof(SolveRec) % 16 == 0, "solver records are copied in 16-byte pieces");
+
 struct WideDevice
 {
 	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0;
@@ -47,7 +59,7 @@ struct WideDevice
 	SMan *man[2] = {nullptr, nullptr};
 	uint32_t *ord[2] = {nullptr, nullptr};  // ordinal of a manifold among those with the same (a, b)
 	int cur = 0;
-	float4 *park = nullptr;
+	SolveRec *recs = nullptr;
 	uint32_t *counters = nullptr;
 	unsigned long long *hkeys = nullptr;
 	uint32_t *hvals = nullptr;
@@ -66,7 +78,7 @@ struct WideArgs
 	float4 *boxlo, *boxhi;
 	SMan *man, *prev;
 	uint32_t *ord, *prev_ord;
-	float4 *park;
+	SolveRec *recs;
 	uint32_t *cnt;
 	unsigned long long *hkeys;
 	uint32_t *hvals;
@@ -422,8 +434,9 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
 	for (int round = 0; round < 4096; round++)
 	{
-		if (a.cnt[WC_UNCOLOURED] == 0) break;
-		grid.sync();
+		// everyone reads the counter between the barrier that ended the previous round and the next one, and nobody
+		// changes it before that next barrier, so all threads take the same branch
+		if (*(volatile uint32_t *)&a.cnt[WC_UNCOLOURED] == 0) break;
 		for (uint32_t mi = tid; mi < n; mi += stride)
 		{
 			const SMan &m = a.man[mi];
@@ -511,19 +524,31 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 {
 	cg::grid_group grid = cg::this_grid();
+	extern __shared__ __align__(16) unsigned char stage_raw[];
+	SolveRec *stage = reinterpret_cast<SolveRec *>(stage_raw);
+	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
 	const uint32_t nact = a.cnt[WC_NACTIVE];
 	const int ncol = (int)a.cnt[WC_NCOL];
 	const float h = a.h;
-	// set-up: lever arms, effective masses, bias; parked next to the manifold
-	__shared__ ConPts pts[256];
-	ConPts &pt = pts[threadIdx.x];
+	// set-up: lever arms, effective masses, bias -> one solver record per active manifold, in colour order
 	for (uint32_t k = tid; k < nact; k += stride)
 	{
 		const uint32_t mi = a.col_list[k];
+		SMan &m = a.man[mi];
+		SolveRec &r = a.recs[k];
 		Con c;
-		build_con(c, pt, a.man[mi], a.bodies, h);
-		park_con(pt, a.park + 9ull * mi);
+		build_con(c, r.pts, m, a.bodies, h);
+		r.con = c;
+		r.mi = mi;
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			r.bias[p] = m.bias[p];
+			r.ln[p] = m.ln[p];
+			r.lt1[p] = m.lt1[p];
+			r.lt2[p] = m.lt2[p];
+		}
 	}
 	grid.sync();
 	// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
@@ -532,23 +557,53 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 		for (int col = 0; col < ncol; col++)
 		{
 			const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
-			for (uint32_t k = lo + tid; k < hi; k += stride)
+			// each warp stages its 32 consecutive records in shared memory with coalesced 16-byte copies, solves from
+			// there and writes back only the accumulated impulses
+			for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
 			{
-				const uint32_t mi = a.col_list[k];
-				SMan &m = a.man[mi];
-				Con c;
-				con_header(c, m, a.bodies);
-				unpark_con(pt, a.park + 9ull * mi);
-				Vel u;
-				load_vel(c, a.bodies, u);
-				if (it == 0)
-					warm_start(c, pt, m, u);
-				else
-					solve_velocity(c, pt, m, u);
-				store_vel(c, a.bodies, u);
+				const uint32_t cnt32 = min(32u, hi - k0);
+				const float4 *src = reinterpret_cast<const float4 *>(a.recs + k0);
+				float4 *dst = reinterpret_cast<float4 *>(stage + (threadIdx.x & ~31u));
+				const uint32_t n16 = cnt32 * (uint32_t)(sizeof(SolveRec) / 16);
+				for (uint32_t q = lane; q < n16; q += 32u) dst[q] = __ldcg(&src[q]);
+				__syncwarp();
+				if (lane < cnt32)
+				{
+					SolveRec &r = stage[threadIdx.x];
+					const Con c = r.con;
+					Vel u;
+					load_vel(c, a.bodies, u);
+					if (it == 0)
+						warm_start(c, r.pts, r, u);
+					else
+						solve_velocity(c, r.pts, r, u);
+					store_vel(c, a.bodies, u);
+					SolveRec &g = a.recs[k0 + lane];
+#pragma unroll
+					for (int p = 0; p < 4; p++)
+					{
+						g.ln[p] = r.ln[p];
+						g.lt1[p] = r.lt1[p];
+						g.lt2[p] = r.lt2[p];
+					}
+				}
+				__syncwarp();
 			}
 			grid.sync();
 		}
+	// accumulated impulses back into the manifolds (next sub-step's warm start reads them there)
+	for (uint32_t k = tid; k < nact; k += stride)
+	{
+		const SolveRec &r = a.recs[k];
+		SMan &m = a.man[r.mi];
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			m.ln[p] = r.ln[p];
+			m.lt1[p] = r.lt1[p];
+			m.lt2[p] = r.lt2[p];
+		}
+	}
 	// integrate
 	for (uint32_t i = tid; i < a.nb; i += stride)
 	{
@@ -623,7 +678,7 @@ int wide_create(gpx_world *w)
 	d->hsize = next_pow2(2u * d->cap_m);
 	bool ok = walloc(&d->bodies, d->nb) && walloc(&d->keys, d->n_pad) && walloc(&d->boxlo, d->n_pad) &&
 			  walloc(&d->boxhi, d->n_pad) && walloc(&d->man[0], d->cap_m) && walloc(&d->man[1], d->cap_m) &&
-			  walloc(&d->ord[0], d->cap_m) && walloc(&d->ord[1], d->cap_m) && walloc(&d->park, (size_t)d->cap_m * 9) &&
+			  walloc(&d->ord[0], d->cap_m) && walloc(&d->ord[1], d->cap_m) && walloc(&d->recs, d->cap_m) &&
 			  walloc(&d->counters, (size_t)WC_COUNT) && walloc(&d->hkeys, d->hsize) && walloc(&d->hvals, d->hsize) &&
 			  walloc(&d->adj, (size_t)d->nb * WIDE_MAXADJ) && walloc(&d->adj_n, d->nb) && walloc(&d->prio, d->cap_m) &&
 			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m);
@@ -636,7 +691,8 @@ int wide_create(gpx_world *w)
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
 	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_colour, 256, 0));
 	d->coop_grid_colour = sms * (per_sm > 0 ? per_sm : 1);
-	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_solve, 256, 0));
+	GPX_CUDA(cudaFuncSetAttribute(kw_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * sizeof(SolveRec))));
+	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_solve, 256, 256 * sizeof(SolveRec)));
 	d->coop_grid_solve = sms * (per_sm > 0 ? per_sm : 1);
 	return GPX_OK;
 }
@@ -646,17 +702,24 @@ void wide_destroy(gpx_world *w)
 	WideDevice *d = w->wide;
 	if (!d) return;
 	cudaFree(d->bodies); cudaFree(d->keys); cudaFree(d->boxlo); cudaFree(d->boxhi); cudaFree(d->man[0]); cudaFree(d->man[1]);
-	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->park); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
+	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	delete d;
 	w->wide = nullptr;
 }
 
-static int coop_launch(const void *fn, int grid, WideArgs &a, cudaStream_t st)
+static int coop_launch(const void *fn, int grid, WideArgs &a, cudaStream_t st, size_t smem = 0)
 {
 	void *params[] = {&a};
-	GPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), params, 0, st));
+	GPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), params, smem, st));
 	count_launch();
+	return GPX_OK;
+}
+
+int wide_counters(gpx_world *w, uint32_t *out8)
+{
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	GPX_CUDA(cudaMemcpy(out8, w->wide->counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return GPX_OK;
 }
 
@@ -671,7 +734,7 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.keys = d->keys;
 	a.boxlo = d->boxlo;
 	a.boxhi = d->boxhi;
-	a.park = d->park;
+	a.recs = d->recs;
 	a.cnt = d->counters;
 	a.hkeys = d->hkeys;
 	a.hvals = d->hvals;
@@ -718,7 +781,7 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		count_launch(5);
 		int rc;
 		if ((rc = coop_launch((const void *)kw_colour, d->coop_grid_colour, a, st)) != GPX_OK) return rc;
-		if ((rc = coop_launch((const void *)kw_solve, d->coop_grid_solve, a, st)) != GPX_OK) return rc;
+		if ((rc = coop_launch((const void *)kw_solve, d->coop_grid_solve, a, st, 256 * sizeof(SolveRec))) != GPX_OK) return rc;
 		// this sub-step's manifolds become the next one's warm-start table
 		GPX_CUDA(cudaMemsetAsync(d->hkeys, 0, sizeof(unsigned long long) * d->hsize, st));
 		kw_finish<<<max(gm, gb), WT, 0, st>>>(a);
