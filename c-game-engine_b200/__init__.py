@@ -76,6 +76,10 @@ class BodyDesc(C.Structure):
     ]
 
 
+class HullShape(C.Structure):
+    _fields_ = [("shape", C.c_uint32), ("half_extents", C.c_float * 3), ("center", C.c_float * 3), ("exact", C.c_uint32)]
+
+
 class CharacterDesc(C.Structure):
     _fields_ = [("half_height", C.c_float), ("radius", C.c_float), ("max_slope_deg", C.c_float), ("mass", C.c_float),
                 ("position", C.c_float * 3)]
@@ -160,6 +164,7 @@ def lib() -> C.CDLL:
         "gpx_static_load_gmap_container": (i32, [vp, vp, u64]),
         "gpx_static_load_gmap_file": (i32, [vp, C.c_char_p]),
         "gpx_static_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "gpx_shape_from_hull": (i32, [vp, u64, f32, C.POINTER(HullShape)]),
         "gpx_body_create": (u32, [vp, u32, C.POINTER(BodyDesc)]),
         "gpx_body_create_all": (i32, [vp, C.POINTER(BodyDesc), u32, vp, vp, vp]),
         "gpx_body_destroy": (i32, [vp, u32, u32]),
@@ -477,3 +482,11 @@ def pinned_array(n: int, dtype) -> np.ndarray:
 
 
 _PINNED: list = []
+
+
+def shape_from_hull(points, tolerance=0.03):
+    """gpx_shape_from_hull: classify a convex hull's points as BOX / SPHERE.  Host-side, needs no device."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = HullShape()
+    _check(lib().gpx_shape_from_hull(pts.ctypes.data, len(pts), tolerance, C.byref(out)), "gpx_shape_from_hull")
+    return out.shape, np.array(list(out.half_extents), np.float32), np.array(list(out.center), np.float32), bool(out.exact)

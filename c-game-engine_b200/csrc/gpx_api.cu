@@ -469,6 +469,83 @@ int gpx_static_load_gmap_file(gpx_world *w, const char *path)
 	return gpx_static_load_gmap_container(w, blob.data(), blob.size());
 }
 
+/* JPH_ConvexHullShape_Create as the model loader uses it (engine/src/assets/ModelLoader.c:324-341: one hull per
+ * ModelConvexHull of a .gmdl, ModelLoader.c:154-183).  The body store knows boxes and spheres, so a hull is
+ * classified: all points at the same distance from the centroid (to 2 %) -> SPHERE (orb.gmdl, 32 514 points);
+ * every point on or just inside the surface of its bounding box, with points near all eight corners -> BOX
+ * (cube.gmdl: a bevelled 0.4 m cube); anything else -> its bounding box, reported as approximate. */
+int gpx_shape_from_hull(const float *points, uint64_t n, float tolerance, gpx_hull_shape *out)
+{
+	if (!points || n < 4 || !out || !(tolerance >= 0.0f)) return GPX_ERR_INVALID_ARG;
+	double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30}, c[3] = {0, 0, 0};
+	for (uint64_t i = 0; i < n; i++)
+		for (int k = 0; k < 3; k++)
+		{
+			const double v = points[3 * i + k];
+			lo[k] = v < lo[k] ? v : lo[k];
+			hi[k] = v > hi[k] ? v : hi[k];
+			c[k] += v;
+		}
+	for (int k = 0; k < 3; k++) c[k] /= (double)n;
+	double rmin = 1e30, rmax = 0.0;
+	for (uint64_t i = 0; i < n; i++)
+	{
+		double r2 = 0.0;
+		for (int k = 0; k < 3; k++)
+		{
+			const double d = points[3 * i + k] - c[k];
+			r2 += d * d;
+		}
+		const double r = sqrt(r2);
+		rmin = r < rmin ? r : rmin;
+		rmax = r > rmax ? r : rmax;
+	}
+	memset(out, 0, sizeof(*out));
+	double he[3], bc[3];
+	for (int k = 0; k < 3; k++)
+	{
+		he[k] = 0.5 * (hi[k] - lo[k]);
+		bc[k] = 0.5 * (hi[k] + lo[k]);
+	}
+	/* radii agree to 2 % and the points reach that radius along every axis (a cube's corner points also share one radius) */
+	const bool round_box = fabs(he[0] - rmax) <= 0.03 * rmax && fabs(he[1] - rmax) <= 0.03 * rmax && fabs(he[2] - rmax) <= 0.03 * rmax;
+	if (rmax - rmin <= 0.02 * rmax && rmax - rmin <= 2.0 * tolerance && round_box)
+	{
+		out->shape = GPX_SHAPE_SPHERE;
+		out->half_extents[0] = (float)(0.5 * (rmax + rmin));
+		for (int k = 0; k < 3; k++) out->center[k] = (float)c[k];
+		out->exact = 1;
+		return GPX_OK;
+	}
+	/* box: all points near the surface (a bevel cuts at most `tolerance` off edges and corners), every corner region hit */
+	bool on_surface = true;
+	uint32_t corners = 0;
+	for (uint64_t i = 0; i < n; i++)
+	{
+		double gap = 1e30;
+		uint32_t oct = 0;
+		bool near_corner = true;
+		for (int k = 0; k < 3; k++)
+		{
+			const double d = points[3 * i + k] - bc[k];
+			const double g = he[k] - fabs(d);
+			gap = g < gap ? g : gap;
+			if (d > 0) oct |= 1u << k;
+			if (g > 4.0 * tolerance) near_corner = false;
+		}
+		if (gap > tolerance) on_surface = false;
+		if (near_corner) corners |= 1u << oct;
+	}
+	out->shape = GPX_SHAPE_BOX;
+	for (int k = 0; k < 3; k++)
+	{
+		out->half_extents[k] = (float)he[k];
+		out->center[k] = (float)bc[k];
+	}
+	out->exact = (on_surface && corners == 0xFFu) ? 1u : 0u;
+	return GPX_OK;
+}
+
 /* ---- bodies */
 
 static inline bool valid_slot(const gpx_world *w, uint32_t world, uint32_t body)

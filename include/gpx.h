@@ -182,6 +182,22 @@ int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size);
 int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t size);
 int gpx_static_load_gmap_file(gpx_world *w, const char *path);
 
+/* ---- shapes ------------------------------------------------------------------------------------------------------ */
+
+/* JPH_ConvexHullShape_Create(points, n, radius) as the model loader calls it (engine/src/assets/ModelLoader.c:324-341).
+ * The body store represents boxes and spheres; a convex hull is classified into one of them.  `exact` = 1 when the
+ * hull IS that primitive up to `tolerance` (cube.gmdl -> its 0.4 m box, orb.gmdl -> radius 0.4 sphere), 0 when the
+ * result is only the hull's bounding box (leafy.gmdl) — the same stand-in the engine uses for `collision = 1` models
+ * (ModelLoader.c:152).  Host-side; needs no device. */
+typedef struct gpx_hull_shape
+{
+	uint32_t shape;        /* GPX_SHAPE_BOX or GPX_SHAPE_SPHERE */
+	float half_extents[3]; /* sphere: x = radius */
+	float center[3];       /* offset of the primitive's centre from the hull's origin */
+	uint32_t exact;
+} gpx_hull_shape;
+int gpx_shape_from_hull(const float *points, uint64_t n, float tolerance, gpx_hull_shape *out);
+
 /* ---- bodies --------------------------------------------------------------------------------------------------- */
 
 /* JPH_BodyInterface_CreateAndAddBody (17 call sites).  Returns body id or GPX_INVALID_BODY. */

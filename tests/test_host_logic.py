@@ -174,3 +174,30 @@ def test_two_rank_sharding_and_stats_gather_over_gloo(tmp_path):
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert out["n"] == 12 and out["tmax"] == 2.0 and out["ticks"] == 5 and out["distinct"] == 12
     assert out["first_ke"] > 0 and out["last_ke"] > 0
+
+
+# ------------------------------------------------------------------------------------------------ hull -> primitive
+
+def test_hull_classifier_on_the_shipped_models(gpx, scenes):
+    """gpx_shape_from_hull (host-side, no device): what CreateDynamicModelShape's convex hulls become in the body store
+    (engine/src/assets/ModelLoader.c:324-341).  Hull points decoded from assets/game/model/*.gmdl by tools/make_golden.py."""
+    m = np.load(scenes.GOLDEN + "/models.npz")
+    shape, he, c, exact = gpx.shape_from_hull(m["cube_hull_points"])
+    assert shape == gpx.SHAPE_BOX and exact and np.allclose(he, 0.2, atol=1e-6) and np.allclose(c, 0, atol=1e-6)
+    shape, he, c, exact = gpx.shape_from_hull(m["orb_hull_points"])
+    assert shape == gpx.SHAPE_SPHERE and exact and abs(he[0] - 0.4) < 2e-3 and np.abs(c).max() < 2e-3
+    shape, he, c, exact = gpx.shape_from_hull(m["leafy_hull_points"])
+    assert shape == gpx.SHAPE_BOX and not exact                       # two tall hulls: only the bounding box is used
+    assert np.allclose(he, (m["leafy_hull_aabb"][3:] - m["leafy_hull_aabb"][:3]) / 2, atol=1e-6)
+    shape, he, c, exact = gpx.shape_from_hull(m["eraser_w_hull_points"])
+    assert shape == gpx.SHAPE_BOX
+    # synthetic: an exact box, a cylinder (NpcJohn.c:29 — neither a box nor a sphere), too few points
+    box = np.array([[sx * 0.3, sy * 0.1, sz * 0.5] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) + 1.0
+    shape, he, c, exact = gpx.shape_from_hull(box)
+    assert shape == gpx.SHAPE_BOX and exact and np.allclose(he, (0.3, 0.1, 0.5), atol=1e-6) and np.allclose(c, 1.0, atol=1e-6)
+    ang = np.linspace(0, 2 * np.pi, 24, endpoint=False)
+    cyl = np.array([[0.25 * np.cos(a), y, 0.25 * np.sin(a)] for a in ang for y in (-0.5, 0.5)], np.float32)
+    shape, he, c, exact = gpx.shape_from_hull(cyl, tolerance=0.01)
+    assert shape == gpx.SHAPE_BOX and not exact and np.allclose(he, (0.25, 0.5, 0.25), atol=1e-6)
+    with pytest.raises(gpx.GpxError):
+        gpx.shape_from_hull(cyl[:3])

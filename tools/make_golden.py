@@ -57,6 +57,9 @@ def main():
             models[f"{name}_hull_aabb"] = np.concatenate([pts.min(0), pts.max(0)]).astype(np.float32)
             models[f"{name}_hull_maxr"] = np.float32(np.linalg.norm(pts, axis=1).max())
             models[f"{name}_hull_minr"] = np.float32(np.linalg.norm(pts, axis=1).min())
+            # the points themselves (orb: every 16th of its 32 514) for the hull -> primitive classifier
+            keep = pts if len(pts) <= 4096 else pts[::16]
+            models[f"{name}_hull_points"] = keep.astype(np.float32)
         if g.tris is not None:
             models[f"{name}_tris"] = g.tris.astype(np.float32)
     np.savez_compressed(os.path.join(OUT, "models.npz"), **models)
