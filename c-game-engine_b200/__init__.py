@@ -160,6 +160,7 @@ def lib() -> C.CDLL:
         "gpx_world_destroy": (None, [vp]),
         "gpx_static_add_mesh": (i32, [vp, C.POINTER(Transform), vp, u64, f32, u64, C.POINTER(u32)]),
         "gpx_static_commit": (i32, [vp]),
+        "gpx_static_remove_mesh": (i32, [vp, u32]),
         "gpx_static_load_gmap": (i32, [vp, vp, u64]),
         "gpx_static_load_gmap_container": (i32, [vp, vp, u64]),
         "gpx_static_load_gmap_file": (i32, [vp, C.c_char_p]),
@@ -168,6 +169,7 @@ def lib() -> C.CDLL:
         "gpx_body_create": (u32, [vp, u32, C.POINTER(BodyDesc)]),
         "gpx_body_create_all": (i32, [vp, C.POINTER(BodyDesc), u32, vp, vp, vp]),
         "gpx_body_destroy": (i32, [vp, u32, u32]),
+        "gpx_body_set_ray_flags": (i32, [vp, u32, u32, u32]),
         "gpx_body_set_linear_velocity": (i32, [vp, u32, u32, C.POINTER(f32)]),
         "gpx_body_set_linear_and_angular_velocity": (i32, [vp, u32, u32, C.POINTER(f32), C.POINTER(f32)]),
         "gpx_body_set_position": (i32, [vp, u32, u32, C.POINTER(f32), i32]),
@@ -288,6 +290,10 @@ class World:
     def commit(self):
         _check(self.L.gpx_static_commit(self.h), "gpx_static_commit")
 
+    def remove_mesh(self, body):
+        """Drop one static mesh body (RemoveAndDestroyBody on map / static-model geometry); takes effect at the next commit."""
+        _check(self.L.gpx_static_remove_mesh(self.h, body), "gpx_static_remove_mesh")
+
     def static_info(self):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         self.L.gpx_static_info(self.h, C.byref(a), C.byref(b), C.byref(c))
@@ -309,6 +315,9 @@ class World:
 
     def destroy(self, body, world=0):
         _check(self.L.gpx_body_destroy(self.h, world, body), "gpx_body_destroy")
+
+    def set_ray_flags(self, body, flags, world=0):
+        _check(self.L.gpx_body_set_ray_flags(self.h, world, body, flags), "gpx_body_set_ray_flags")
 
     def set_velocity(self, body, v, av=None, world=0):
         fv = (C.c_float * 3)(*v)

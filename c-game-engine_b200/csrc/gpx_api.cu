@@ -121,6 +121,7 @@ static int flush_commands(gpx_world *w)
 				e.prop2 = c.prop2;
 				e.flags = c.flags;
 			}
+			if (c.mask & 32u) e.flags = (e.flags & ~(0xFFu << BF_RAYFLAG_SHIFT)) | (c.flags & (0xFFu << BF_RAYFLAG_SHIFT));
 			e.mask |= c.mask;
 		}
 		w->pending.swap(merged);
@@ -349,6 +350,22 @@ int gpx_static_commit(gpx_world *w)
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	return build_static(w);
+}
+
+int gpx_static_remove_mesh(gpx_world *w, uint32_t body)
+{
+	if (!w || body < STATIC_BODY_BASE || body - STATIC_BODY_BASE >= w->sbodies.size()) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	StaticBodyHost &sb = w->sbodies[body - STATIC_BODY_BASE];
+	if (sb.count == 0) return GPX_OK;
+	const uint32_t first = sb.first, count = sb.count;
+	w->h_tris.erase(w->h_tris.begin() + 9ull * first, w->h_tris.begin() + 9ull * (first + count));
+	w->h_tri_body.erase(w->h_tri_body.begin() + first, w->h_tri_body.begin() + first + count);
+	for (StaticBodyHost &o : w->sbodies)
+		if (o.first > first) o.first -= count;
+	sb.count = 0;
+	w->static_dirty = true;
+	return GPX_OK;
 }
 
 int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *n_bodies)
@@ -680,6 +697,35 @@ int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const flo
 int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int /*activate*/)
 {
 	return q ? queue_write(w, world, body, 2u, q, nullptr) : GPX_ERR_INVALID_ARG;
+}
+
+int gpx_body_set_ray_flags(gpx_world *w, uint32_t world, uint32_t body, uint32_t ray_flags)
+{
+	if (w && body >= STATIC_BODY_BASE && body - STATIC_BODY_BASE < w->sbodies.size())
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		StaticBodyHost &sb = w->sbodies[body - STATIC_BODY_BASE];
+		if (sb.ray_flags != (ray_flags & 0xFFu))
+		{
+			sb.ray_flags = ray_flags & 0xFFu;
+			w->static_dirty = true;  // the per-body table travels with the static upload
+		}
+		return GPX_OK;
+	}
+	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	const size_t g = (size_t)world * w->cap + body;
+	if (!(w->h_flags[g] & BF_ALIVE)) return GPX_ERR_INVALID_ARG;
+	const uint32_t f = (w->h_flags[g] & ~(0xFFu << BF_RAYFLAG_SHIFT)) | ((ray_flags & 0xFFu) << BF_RAYFLAG_SHIFT);
+	if (f == w->h_flags[g]) return GPX_OK;
+	w->h_flags[g] = f;
+	BodyCommand c;
+	memset(&c, 0, sizeof(c));
+	c.index = (uint32_t)g;
+	c.mask = 32u;
+	c.flags = f;
+	w->pending.push_back(c);
+	return GPX_OK;
 }
 
 int gpx_body_get_transform(const gpx_world *w, uint32_t world, uint32_t body, gpx_transform *out)

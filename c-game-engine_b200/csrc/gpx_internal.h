@@ -68,7 +68,7 @@ struct CharDev
 struct BodyCommand  // host -> device write, applied by k_apply_commands before the next step
 {
 	uint32_t index;
-	uint32_t mask;  // 1 pos, 2 quat, 4 lin, 8 ang, 16 props+flags
+	uint32_t mask;  // 1 pos, 2 quat, 4 lin, 8 ang, 16 props+flags, 32 ray-flag byte of the flag word
 	uint32_t flags;
 	uint32_t pad;
 	float4 pos, quat, lin, ang, prop0, prop1, prop2;

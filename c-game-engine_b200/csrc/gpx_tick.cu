@@ -661,6 +661,8 @@ __global__ void k_apply_commands(BodyStore bs, const BodyCommand *__restrict__ c
 		bs.prop2[c.index] = c.prop2;
 		bs.flags[c.index] = c.flags;
 	}
+	if ((c.mask & 48u) == 32u)
+		bs.flags[c.index] = (bs.flags[c.index] & ~(0xFFu << BF_RAYFLAG_SHIFT)) | (c.flags & (0xFFu << BF_RAYFLAG_SHIFT));
 }
 
 // per-world summary for the end-of-run gather: one warp per world

@@ -172,6 +172,9 @@ void gpx_world_destroy(gpx_world *w);
  * Shared by every world of the ensemble.  Returns the static body id in *out_body. */
 int gpx_static_add_mesh(gpx_world *w, const gpx_transform *xfm, const float *tris, uint64_t ntris, float friction,
 						uint64_t user_data, uint32_t *out_body);
+/* JPH_BodyInterface_RemoveAndDestroyBody for a static mesh body (Map.c:113, Actor.c:68): its triangles leave the soup at
+ * the next commit.  The body id is not reused; canonical face ids of later meshes move down. */
+int gpx_static_remove_mesh(gpx_world *w, uint32_t body);
 /* JPH_PhysicsSystem_OptimizeBroadPhase (MapLoader.c:273): uploads the soup and (re)builds the LBVH on device. */
 int gpx_static_commit(gpx_world *w);
 /* Parse a decompressed .gmap collision section straight into the static soup (MapLoader.c:200-273).
@@ -215,6 +218,9 @@ int gpx_body_set_linear_and_angular_velocity(gpx_world *w, uint32_t world, uint3
 											 const float av[3]);
 int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int activate);
 int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int activate);
+
+/* Re-evaluates the laser BodyFilter for one body (Laser.c:74-85 reads actor->flags, which may change after create). */
+int gpx_body_set_ray_flags(gpx_world *w, uint32_t world, uint32_t body, uint32_t ray_flags);
 
 /* Getters served from the host mirror refreshed by gpx_sync_transforms (rows a9: GetPosition/Rotation/
  * PositionAndRotation/WorldTransform/UserData) */

@@ -286,6 +286,19 @@ void orc_body_set_velocity(orc_world *w, uint32_t id, const float v[3], const fl
 	if (av) w->bodies[id].w = V(av[0], av[1], av[2]);
 }
 
+/* JPH_BodyInterface_SetPosition (Door.c:82-96) and the re-evaluated laser body filter (Laser.c:74-85) */
+void orc_body_set_position(orc_world *w, uint32_t id, const float p[3])
+{
+	if (id >= w->max_bodies || !p) return;
+	w->bodies[id].x = V(p[0], p[1], p[2]);
+}
+
+void orc_body_set_ray_flags(orc_world *w, uint32_t id, uint32_t ray_flags)
+{
+	if (id >= w->max_bodies) return;
+	w->bodies[id].ray_flags = ray_flags;
+}
+
 void orc_body_get(const orc_world *w, uint32_t id, float *xf7, float *vel6)
 {
 	const body_t *b = &w->bodies[id];

@@ -108,6 +108,8 @@ def lib():
     L.orc_body_create.argtypes = [C.c_void_p, C.c_void_p]  # same layout as gpx_body_desc
     L.orc_body_destroy.argtypes = [C.c_void_p, C.c_uint32]
     L.orc_body_set_velocity.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.orc_body_set_position.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    L.orc_body_set_ray_flags.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.orc_step.restype = C.c_int
     L.orc_step.argtypes = [C.c_void_p, C.c_float, C.c_int]
     L.orc_body_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -170,6 +172,16 @@ class World:
 
     def destroy(self, bid: int):
         self.L.orc_body_destroy(self.h, bid)
+
+    def set_velocity(self, bid: int, v=None, av=None):
+        self.L.orc_body_set_velocity(self.h, bid, (C.c_float * 3)(*v) if v is not None else None,
+                                     (C.c_float * 3)(*av) if av is not None else None)
+
+    def set_position(self, bid: int, p):
+        self.L.orc_body_set_position(self.h, bid, (C.c_float * 3)(*p))
+
+    def set_ray_flags(self, bid: int, flags: int):
+        self.L.orc_body_set_ray_flags(self.h, bid, flags)
 
     def step(self, dt=1.0 / 60.0, collision_steps=2) -> int:
         return self.L.orc_step(self.h, dt, collision_steps)
