@@ -316,6 +316,13 @@ class World:
     def destroy(self, body, world=0):
         _check(self.L.gpx_body_destroy(self.h, world, body), "gpx_body_destroy")
 
+    def wide_counters(self):
+        """Counters of the last sub-step of a wide world (profiling / test aid)."""
+        c = np.zeros(8, np.uint32)
+        _check(self.L.gpx_debug_wide_counters(self.h, c.ctypes.data), "gpx_debug_wide_counters")
+        return dict(manifold_slots=int(c[0]), small_islands=int(c[1]), colours=int(c[2]), error=int(c[3]),
+                    large_island_manifolds=int(c[5]))
+
     def set_ray_flags(self, body, flags, world=0):
         _check(self.L.gpx_body_set_ray_flags(self.h, world, body, flags), "gpx_body_set_ray_flags")
 

@@ -13,15 +13,21 @@
 //   kw_pairs      thread/pair      box-box / sphere contact manifolds
 //   kw_static     thread/body      LBVH candidates (cached), box/sphere-vs-triangle manifolds grouped by normal
 //   kw_link       thread/manifold  warm-start lookup in a hash table of the previous sub-step's manifolds, incidence
-//                                  lists per dynamic body, colouring priority
-//   kw_colour     cooperative      Jones-Plassmann colouring with hashed priorities (result depends on the contact
-//                                  graph only, not on list order), then per-colour manifold lists
-//   kw_solve      cooperative      set-up; warm start; 10 x (colour by colour) velocity rows; integrate;
+//                                  lists per dynamic body, colouring priority, union-find over dynamic-dynamic contacts
+//   kw_isl_*      thread/item      simulation islands (connected components of the contact graph): manifold count per
+//                                  island; islands of at most 32 manifolds packed into 32-slot windows
+//   kw_island     warp/window      small islands, start to finish inside one warp: the same colouring, set-up, warm
+//                                  start, velocity rows, integration and position rows, with warp barriers in place of
+//                                  grid-wide ones (a stack of boxes is an island; the lattice of config 4 is 10 000)
+//   kw_colour     cooperative      the remaining (large) islands: Jones-Plassmann colouring with hashed priorities
+//                                  (result depends on the contact graph only, not on list order), per-colour lists
+//   kw_solve      cooperative      large islands: set-up; warm start; 10 x (colour by colour) velocity rows; integrate;
 //                                  2 x (colour by colour) position rows — grid-wide barriers between colours
 //   kw_finish     thread/manifold  hash table for the next sub-step; last sub-step: work records -> SoA
 //
 // No float atomics and no order-dependent reductions: within a colour no two manifolds share a dynamic body, so the
-// result is a pure function of the contact set.
+// result is a pure function of the contact set.  Islands do not share dynamic bodies either, and the colouring of a
+// manifold depends only on its own island, so solving an island inside a warp gives the bits the grid-wide phases give.
 #include <cooperative_groups.h>
 
 #include "gpx_solver.cuh"
@@ -36,7 +42,12 @@ constexpr uint32_t WT = 128;         // threads per block of the per-item kernel
 constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase kernels (shared polygon scratch)
 
 enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_MAXEXT_X, WC_MAXEXT_Z, WC_COLCNT = 8,
-				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_COUNT = WC_COLCUR + WIDE_MAXCOL };
+				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_NISL = WC_COLCUR + WIDE_MAXCOL,
+				   WC_ISLCUR, WC_NBIG, WC_COUNT };
+constexpr uint32_t SINGLE_BLOCK_MAX = 4096;  // manifolds of large islands up to which ONE block colours and solves them
+constexpr uint32_t ISLAND_MAX = 32;      // manifolds of an island solved inside one warp (one per lane)
+constexpr uint32_t ISLAND_WARPS = 4;     // warps (islands) per block of kw_island
+constexpr uint32_t ROOT_SMALL = 0x80000000u;
 
 // Everything a velocity phase needs about one manifold, in colour order: the phases stream these records (coalesced)
 // instead of chasing list -> manifold -> bodies -> parked constants.
@@ -52,7 +63,7 @@ static_assert(sizeof(SolveRec) % 16 == 0, "solver records are copied in 16-byte 
 
 struct WideDevice
 {
-	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0;
+	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0, isl_slots = 0;
 	SBody *bodies = nullptr;
 	unsigned long long *keys = nullptr;
 	float4 *boxlo = nullptr, *boxhi = nullptr;
@@ -67,6 +78,10 @@ struct WideDevice
 	uint32_t *prio = nullptr;
 	int *pending = nullptr;
 	uint32_t *col_list = nullptr;
+	// islands: union-find parent per body, flattened root (| ROOT_SMALL when the body is solved by kw_island), manifold
+	// count / list offset / fill cursor per root, roots of the small islands, their manifold lists
+	uint32_t *parent = nullptr, *root_of = nullptr, *isl_cnt = nullptr, *isl_off = nullptr, *isl_cur = nullptr;
+	uint32_t *isl_man = nullptr, *big_list = nullptr;
 	int coop_grid_colour = 0, coop_grid_solve = 0;
 };
 
@@ -86,6 +101,7 @@ struct WideArgs
 	uint32_t *prio;
 	int *pending;
 	uint32_t *col_list;
+	uint32_t *parent, *root_of, *isl_cnt, *isl_off, *isl_cur, *isl_man, *big_list;
 	uint4 *cand;
 	StaticView sv;
 	uint32_t nb, n_pad, cap_m, hmask;
@@ -156,6 +172,9 @@ __global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
 		b.flags = a.bs.flags[i];
 	}
 	a.adj_n[i] = 0;
+	a.parent[i] = i;
+	a.isl_cnt[i] = 0;
+	a.isl_cur[i] = 0;
 	const uint32_t f = b.flags;
 	if (!(f & BF_ALIVE))
 	{
@@ -362,6 +381,37 @@ __device__ __forceinline__ int hash_find(const WideArgs &a, unsigned long long k
 	return -1;
 }
 
+// Union-find over bodies, lock-free: a root is only ever hooked under a smaller index, so the root of a finished
+// component is its smallest body whatever the interleaving.
+__device__ __forceinline__ uint32_t isl_find(uint32_t *parent, uint32_t x)
+{
+	uint32_t p = *(volatile uint32_t *)&parent[x];
+	while (p != x)
+	{
+		const uint32_t g = *(volatile uint32_t *)&parent[p];
+		if (g != p) atomicMin(&parent[x], g);  // path halving; only ever lowers an entry towards its root
+		x = p;
+		p = g;
+	}
+	return x;
+}
+__device__ __forceinline__ void isl_unite(uint32_t *parent, uint32_t x, uint32_t y)
+{
+	for (;;)
+	{
+		x = isl_find(parent, x);
+		y = isl_find(parent, y);
+		if (x == y) return;
+		if (x > y)
+		{
+			const uint32_t t = x;
+			x = y;
+			y = t;
+		}
+		if (atomicCAS(&parent[y], y, x) == y) return;
+	}
+}
+
 __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 {
 	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
@@ -411,7 +461,328 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 	}
 	a.prio[mi] = man_prio(m.a, m.b, a.ord[mi]);
 	m.colour = -1;
-	atomicAdd(&a.cnt[WC_UNCOLOURED], 1u);
+	if (a_dyn && b_dyn) isl_unite(a.parent, m.a, m.b);
+}
+
+
+// ---------------------------------------------------------------------------------------------------- islands
+
+// the dynamic end of a manifold names its island (both ends of a dynamic-dynamic contact share one root)
+__device__ __forceinline__ uint32_t man_island_body(const WideArgs &a, const SMan &m)
+{
+	return is_dynamic(a.bodies[m.a].flags) ? m.a : m.b;
+}
+
+__global__ void __launch_bounds__(WT) kw_isl_count(WideArgs a)
+{
+	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	if (mi >= n) return;
+	const SMan &m = a.man[mi];
+	if (m.np == 0) return;
+	const uint32_t r = isl_find(a.parent, man_island_body(a, m));
+	a.pending[mi] = (int)r;
+	atomicAdd(&a.isl_cnt[r], 1u);
+}
+
+// Small islands are packed into 32-slot windows of isl_man, one window per warp of kw_island: an island never
+// straddles a window, several short ones share one.  Each block packs the roots among its bodies and reserves whole
+// windows with one atomic; unused slots keep the 0xFFFFFFFF the list was cleared to.
+__global__ void __launch_bounds__(WT) kw_isl_place(WideArgs a)
+{
+	__shared__ uint32_t scnt[WT], soff[WT], sbase;
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	uint32_t c = 0;
+	if (i < a.nb)
+	{
+		const uint32_t f = a.bodies[i].flags;
+		uint32_t r = i;
+		bool small = false;
+		if ((f & BF_ALIVE) && is_dynamic(f) && a.adj_n[i] > 0)
+		{
+			r = isl_find(a.parent, i);
+			small = a.isl_cnt[r] <= ISLAND_MAX;
+		}
+		a.root_of[i] = small ? (r | ROOT_SMALL) : r;
+		c = a.isl_cnt[i];  // non-zero only at roots
+		if (c > ISLAND_MAX) c = 0;
+	}
+	scnt[threadIdx.x] = c;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t pos = 0, islands = 0;
+		for (uint32_t k = 0; k < WT; k++)
+		{
+			const uint32_t ck = scnt[k];
+			if (!ck) continue;
+			if ((pos & 31u) + ck > 32u) pos = (pos + 31u) & ~31u;
+			soff[k] = pos;
+			pos += ck;
+			islands++;
+		}
+		const uint32_t total = (pos + 31u) & ~31u;
+		sbase = total ? atomicAdd(&a.cnt[WC_ISLCUR], total) : 0u;
+		if (islands) atomicAdd(&a.cnt[WC_NISL], islands);
+	}
+	__syncthreads();
+	if (c) a.isl_off[i] = sbase + soff[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(WT) kw_isl_fill(WideArgs a)
+{
+	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
+	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	bool big = false;
+	if (mi < n)
+	{
+		SMan &m = a.man[mi];
+		if (m.np > 0)
+		{
+			const uint32_t r = (uint32_t)a.pending[mi];
+			if (a.isl_cnt[r] <= ISLAND_MAX)
+			{
+				a.isl_man[a.isl_off[r] + atomicAdd(&a.isl_cur[r], 1u)] = mi;
+				m.colour = -3;  // not the cooperative kernels' business
+			}
+			else
+				big = true;
+		}
+	}
+	// what is left for kw_colour / kw_solve: one list slot each, one atomic per warp
+	const uint32_t votes = __ballot_sync(0xFFFFFFFFu, big);
+	if (!votes) return;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t base = 0;
+	if (lane == 0)
+	{
+		base = atomicAdd(&a.cnt[WC_NBIG], (uint32_t)__popc(votes));
+		atomicAdd(&a.cnt[WC_UNCOLOURED], (uint32_t)__popc(votes));
+	}
+	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	if (big) a.big_list[base + (uint32_t)__popc(votes & ((1u << lane) - 1u))] = mi;
+}
+
+// per-lane working set of kw_island: lever arms / effective masses, accumulated impulses, bias.  53 words: odd, so the
+// 32 lanes of a warp fall on different banks.
+struct IslLane
+{
+	ConPts pts;
+	float ln[4], lt1[4], lt2[4], bias[4];
+	float pad;
+};
+
+// One warp = one 32-slot window of isl_man = a few whole islands, one manifold per lane.  The sequence per manifold
+// is exactly kw_colour + kw_solve's; only the barriers are warp barriers.  Lanes of different islands never refer to
+// each other (neighbour masks stay inside an island), so they simply share the colour phases.
+__global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
+{
+	__shared__ IslLane lanes[ISLAND_WARPS * 32];
+	__shared__ float vel[ISLAND_WARPS][64][6];
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t win = blockIdx.x * ISLAND_WARPS + (threadIdx.x >> 5);
+	if (win * 32u >= a.cnt[WC_ISLCUR]) return;
+	const uint32_t mi = a.isl_man[win * 32u + lane];
+	const bool have = mi != 0xFFFFFFFFu;
+	const uint32_t FULL = 0xFFFFFFFFu;
+	IslLane &L = lanes[threadIdx.x];
+
+	// --- neighbours (manifolds sharing a dynamic body) as a lane mask
+	if (have) a.pending[mi] = (int)lane;
+	__syncwarp();
+	uint32_t nbr = 0, ma = 0, mb = 0, mord = 0, mprio = 0;
+	bool a_dyn = false, b_dyn = false;
+	if (have)
+	{
+		const SMan &m = a.man[mi];
+		ma = m.a;
+		mb = m.b;
+		mord = a.ord[mi];
+		mprio = a.prio[mi];
+		a_dyn = is_dynamic(a.bodies[ma].flags);
+		b_dyn = mb < STATIC_BODY_BASE && is_dynamic(a.bodies[mb].flags);
+		const uint32_t ends[2] = {ma, mb};
+		const bool dyn[2] = {a_dyn, b_dyn};
+		for (int e = 0; e < 2; e++)
+		{
+			if (!dyn[e]) continue;
+			const uint32_t cntb = min(a.adj_n[ends[e]], (uint32_t)WIDE_MAXADJ);
+			for (uint32_t k = 0; k < cntb; k++)
+			{
+				const uint32_t other = a.adj[ends[e] * WIDE_MAXADJ + k];
+				if (other != mi) nbr |= 1u << (uint32_t)a.pending[other];
+			}
+		}
+	}
+	// lanes anybody has as a neighbour: the only ones worth broadcasting from
+	uint32_t any_nbr = nbr;
+	for (int o = 16; o > 0; o >>= 1) any_nbr |= __shfl_xor_sync(FULL, any_nbr, o);
+	// --- which neighbours outrank this manifold (same total order as `outranks`)
+	uint32_t higher = 0;
+	for (uint32_t rest = any_nbr; rest; rest &= rest - 1u)
+	{
+		const uint32_t j = (uint32_t)__ffs((int)rest) - 1u;
+		const uint32_t pj = __shfl_sync(FULL, mprio, j), aj = __shfl_sync(FULL, ma, j), bj = __shfl_sync(FULL, mb, j),
+					   oj = __shfl_sync(FULL, mord, j);
+		if (!((nbr >> j) & 1u)) continue;
+		bool up;
+		if (pj != mprio) up = pj > mprio;
+		else if (aj != ma) up = aj > ma;
+		else if (bj != mb) up = bj > mb;
+		else up = oj > mord;
+		if (up) higher |= 1u << j;
+	}
+	// --- Jones-Plassmann rounds
+	int colour = have ? -1 : -2;
+	for (int round = 0; round < 64; round++)
+	{
+		const uint32_t uncol = __ballot_sync(FULL, colour == -1);
+		if (!uncol) break;
+		unsigned long long used = 0ull;
+		for (uint32_t rest = any_nbr; rest; rest &= rest - 1u)
+		{
+			const uint32_t j = (uint32_t)__ffs((int)rest) - 1u;
+			const int cj = __shfl_sync(FULL, colour, j);
+			if (((nbr >> j) & 1u) && cj >= 0) used |= 1ull << cj;
+		}
+		if (colour == -1 && !(higher & uncol))
+		{
+			int d = __ffsll((long long)~used) - 1;
+			if (d < 0 || d >= WIDE_MAXCOL)
+			{
+				d = WIDE_MAXCOL - 1;
+				atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+			}
+			colour = d;
+		}
+	}
+	int ncol = colour + 1;
+	for (int o = 16; o > 0; o >>= 1) ncol = max(ncol, __shfl_xor_sync(FULL, ncol, o));
+
+	// --- set-up
+	const float h = a.h;
+	Con c;
+	if (have)
+	{
+		SMan &m = a.man[mi];
+		build_con(c, L.pts, m, a.bodies, h);
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			L.bias[p] = m.bias[p];
+			L.ln[p] = m.ln[p];
+			L.lt1[p] = m.lt1[p];
+			L.lt2[p] = m.lt2[p];
+		}
+	}
+	// --- velocities of the island's dynamic bodies live in shared memory while the rows run.  A body belongs to the
+	// lane that holds the first manifold of its incidence list (slot 2 * lane + end); the other lanes look the slot up.
+	float(*sv)[6] = vel[threadIdx.x >> 5];
+	const bool own_a = have && a_dyn && a.adj[ma * WIDE_MAXADJ] == mi;
+	const bool own_b = have && b_dyn && a.adj[mb * WIDE_MAXADJ] == mi;
+	if (own_a)
+	{
+		const SBody &b = a.bodies[ma];
+		a.isl_cur[ma] = 2u * lane;
+		float *d = sv[2u * lane];
+		d[0] = b.v.x; d[1] = b.v.y; d[2] = b.v.z; d[3] = b.w.x; d[4] = b.w.y; d[5] = b.w.z;
+	}
+	if (own_b)
+	{
+		const SBody &b = a.bodies[mb];
+		a.isl_cur[mb] = 2u * lane + 1u;
+		float *d = sv[2u * lane + 1u];
+		d[0] = b.v.x; d[1] = b.v.y; d[2] = b.v.z; d[3] = b.w.x; d[4] = b.w.y; d[5] = b.w.z;
+	}
+	__syncwarp();
+	// ends that do not move under impulses (kinematic, or no second body) keep their velocity in registers
+	Vel fixed;
+	fixed.va = fixed.wa = fixed.vb = fixed.wb = V(0.0f, 0.0f, 0.0f);
+	float *pa = nullptr, *pb = nullptr;
+	if (have)
+	{
+		load_vel(c, a.bodies, fixed);
+		if (a_dyn) pa = sv[a.isl_cur[ma]];
+		if (b_dyn) pb = sv[a.isl_cur[mb]];
+	}
+	// --- warm start (it == 0), then the velocity iterations, colour by colour
+	for (uint32_t it = 0; it <= a.vel_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			if (colour == col)
+			{
+				Vel u = fixed;
+				if (pa)
+				{
+					u.va = V(pa[0], pa[1], pa[2]);
+					u.wa = V(pa[3], pa[4], pa[5]);
+				}
+				if (pb)
+				{
+					u.vb = V(pb[0], pb[1], pb[2]);
+					u.wb = V(pb[3], pb[4], pb[5]);
+				}
+				if (it == 0)
+					warm_start(c, L.pts, L, u);
+				else
+					solve_velocity(c, L.pts, L, u);
+				if (pa)
+				{
+					pa[0] = u.va.x; pa[1] = u.va.y; pa[2] = u.va.z; pa[3] = u.wa.x; pa[4] = u.wa.y; pa[5] = u.wa.z;
+				}
+				if (pb)
+				{
+					pb[0] = u.vb.x; pb[1] = u.vb.y; pb[2] = u.vb.z; pb[3] = u.wb.x; pb[4] = u.wb.y; pb[5] = u.wb.z;
+				}
+			}
+			__syncwarp();
+		}
+	if (have)
+	{
+		SMan &m = a.man[mi];
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			m.ln[p] = L.ln[p];
+			m.lt1[p] = L.lt1[p];
+			m.lt2[p] = L.lt2[p];
+		}
+		// --- velocities back, and integrate: every dynamic body of the island once, by the lane that owns it
+		const uint32_t ends[2] = {ma, mb};
+		const bool own[2] = {own_a, own_b};
+		for (int e = 0; e < 2; e++)
+		{
+			if (!own[e]) continue;
+			SBody &b = a.bodies[ends[e]];
+			const float *d = sv[2u * lane + (uint32_t)e];
+			const v3 v = V(d[0], d[1], d[2]), w = V(d[3], d[4], d[5]);
+			b.v = v;
+			b.w = w;
+			b.x = b.x + (v * h);
+			b.q = qstep(b.q, w * h);
+		}
+	}
+	// the position rows run in kw_island_pos, after the kinematic bodies have moved (kw_solve integrates them)
+	if (have) a.man[mi].colour = -4 - colour;
+}
+
+// Position iterations of the small islands (one window per warp), colours as left by kw_island.
+__global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island_pos(WideArgs a)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t win = blockIdx.x * ISLAND_WARPS + (threadIdx.x >> 5);
+	if (win * 32u >= a.cnt[WC_ISLCUR]) return;
+	const uint32_t mi = a.isl_man[win * 32u + lane];
+	const bool have = mi != 0xFFFFFFFFu;
+	const int colour = have ? -4 - a.man[mi].colour : -2;
+	int ncol = colour + 1;
+	for (int o = 16; o > 0; o >>= 1) ncol = max(ncol, __shfl_xor_sync(0xFFFFFFFFu, ncol, o));
+	for (uint32_t it = 0; it < a.pos_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			if (colour == col) solve_position(a.man[mi], a.bodies);
+			__syncwarp();
+		}
 }
 
 // total order on manifolds for the colouring: priority, then identity
@@ -425,20 +796,37 @@ __device__ __forceinline__ bool outranks(const WideArgs &a, uint32_t x, uint32_t
 	return a.ord[x] > a.ord[y];
 }
 
+// Barrier of the cooperative kernels.  When the large islands are few, ONE block does the phased work and a block
+// barrier is all it needs; the other blocks only help with the grid-wide integration pass of kw_solve.
+struct PhaseSync
+{
+	cg::grid_group grid;
+	bool single;
+	__device__ __forceinline__ void operator()() const
+	{
+		if (single) __syncthreads();
+		else grid.sync();
+	}
+};
+
 // Jones-Plassmann: in each round every uncoloured manifold that outranks all its uncoloured neighbours takes the
 // smallest colour none of its coloured neighbours has.  Decisions of a round only read colours of earlier rounds.
+// Works on the manifolds of the large islands (big_list); the small ones were coloured inside kw_island.
 __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 {
-	cg::grid_group grid = cg::this_grid();
-	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
+	const uint32_t n = a.cnt[WC_NBIG];
+	PhaseSync bar{cg::this_grid(), n <= SINGLE_BLOCK_MAX};
+	if (bar.single && blockIdx.x != 0) return;
+	const uint32_t tid = bar.single ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t stride = bar.single ? blockDim.x : gridDim.x * blockDim.x;
 	for (int round = 0; round < 4096; round++)
 	{
 		// everyone reads the counter between the barrier that ended the previous round and the next one, and nobody
 		// changes it before that next barrier, so all threads take the same branch
 		if (*(volatile uint32_t *)&a.cnt[WC_UNCOLOURED] == 0) break;
-		for (uint32_t mi = tid; mi < n; mi += stride)
+		for (uint32_t k = tid; k < n; k += stride)
 		{
+			const uint32_t mi = a.big_list[k];
 			const SMan &m = a.man[mi];
 			int decision = -1;
 			if (m.colour == -1)
@@ -451,9 +839,9 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 					const uint32_t body = ends[e];
 					if (body >= STATIC_BODY_BASE || !is_dynamic(a.bodies[body].flags)) continue;
 					const uint32_t cntb = min(a.adj_n[body], (uint32_t)WIDE_MAXADJ);
-					for (uint32_t k = 0; k < cntb; k++)
+					for (uint32_t j = 0; j < cntb; j++)
 					{
-						const uint32_t other = a.adj[body * WIDE_MAXADJ + k];
+						const uint32_t other = a.adj[body * WIDE_MAXADJ + j];
 						if (other == mi) continue;
 						const int oc = a.man[other].colour;
 						if (oc == -1)
@@ -480,10 +868,11 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 			}
 			a.pending[mi] = decision;
 		}
-		grid.sync();
+		bar();
 		uint32_t done = 0;
-		for (uint32_t mi = tid; mi < n; mi += stride)
+		for (uint32_t k = tid; k < n; k += stride)
 		{
+			const uint32_t mi = a.big_list[k];
 			const int d = a.pending[mi];
 			if (d >= 0)
 			{
@@ -493,9 +882,10 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 			}
 		}
 		if (done) atomicSub(&a.cnt[WC_UNCOLOURED], done);
-		grid.sync();
+		__threadfence();
+		bar();
 	}
-	grid.sync();
+	bar();
 	// per-colour lists
 	if (tid == 0)
 	{
@@ -510,10 +900,12 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 		a.cnt[WC_COLOFF + WIDE_MAXCOL] = off;
 		a.cnt[WC_NCOL] = ncol;
 		a.cnt[WC_NACTIVE] = off;
+		__threadfence();
 	}
-	grid.sync();
-	for (uint32_t mi = tid; mi < n; mi += stride)
+	bar();
+	for (uint32_t k = tid; k < n; k += stride)
 	{
+		const uint32_t mi = a.big_list[k];
 		const int c = a.man[mi].colour;
 		if (c >= 0) a.col_list[atomicAdd(&a.cnt[WC_COLCUR + c], 1u)] = mi;
 	}
@@ -527,99 +919,109 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 	extern __shared__ __align__(16) unsigned char stage_raw[];
 	SolveRec *stage = reinterpret_cast<SolveRec *>(stage_raw);
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
 	const uint32_t nact = a.cnt[WC_NACTIVE];
+	PhaseSync bar{grid, nact <= SINGLE_BLOCK_MAX};
+	const bool phased = !bar.single || blockIdx.x == 0;  // this block takes part in the colour phases
+	const uint32_t tid = bar.single ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t stride = bar.single ? blockDim.x : gridDim.x * blockDim.x;
 	const int ncol = (int)a.cnt[WC_NCOL];
 	const float h = a.h;
-	// set-up: lever arms, effective masses, bias -> one solver record per active manifold, in colour order
-	for (uint32_t k = tid; k < nact; k += stride)
+	if (phased)
 	{
-		const uint32_t mi = a.col_list[k];
-		SMan &m = a.man[mi];
-		SolveRec &r = a.recs[k];
-		Con c;
-		build_con(c, r.pts, m, a.bodies, h);
-		r.con = c;
-		r.mi = mi;
-#pragma unroll
-		for (int p = 0; p < 4; p++)
+		// set-up: lever arms, effective masses, bias -> one solver record per active manifold, in colour order
+		for (uint32_t k = tid; k < nact; k += stride)
 		{
-			r.bias[p] = m.bias[p];
-			r.ln[p] = m.ln[p];
-			r.lt1[p] = m.lt1[p];
-			r.lt2[p] = m.lt2[p];
+			const uint32_t mi = a.col_list[k];
+			SMan &m = a.man[mi];
+			SolveRec &r = a.recs[k];
+			Con c;
+			build_con(c, r.pts, m, a.bodies, h);
+			r.con = c;
+			r.mi = mi;
+#pragma unroll
+			for (int p = 0; p < 4; p++)
+			{
+				r.bias[p] = m.bias[p];
+				r.ln[p] = m.ln[p];
+				r.lt1[p] = m.lt1[p];
+				r.lt2[p] = m.lt2[p];
+			}
+		}
+		bar();
+		// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
+		// dynamic body, so every body is written by at most one thread per phase.
+		for (uint32_t it = 0; it <= a.vel_steps; it++)
+			for (int col = 0; col < ncol; col++)
+			{
+				const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
+				// each warp stages its 32 consecutive records in shared memory with coalesced 16-byte copies, solves
+				// from there and writes back only the accumulated impulses
+				for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
+				{
+					const uint32_t cnt32 = min(32u, hi - k0);
+					const float4 *src = reinterpret_cast<const float4 *>(a.recs + k0);
+					float4 *dst = reinterpret_cast<float4 *>(stage + (threadIdx.x & ~31u));
+					const uint32_t n16 = cnt32 * (uint32_t)(sizeof(SolveRec) / 16);
+					for (uint32_t q = lane; q < n16; q += 32u) dst[q] = __ldcg(&src[q]);
+					__syncwarp();
+					if (lane < cnt32)
+					{
+						SolveRec &r = stage[threadIdx.x];
+						const Con c = r.con;
+						Vel u;
+						load_vel(c, a.bodies, u);
+						if (it == 0)
+							warm_start(c, r.pts, r, u);
+						else
+							solve_velocity(c, r.pts, r, u);
+						store_vel(c, a.bodies, u);
+						SolveRec &g = a.recs[k0 + lane];
+#pragma unroll
+						for (int p = 0; p < 4; p++)
+						{
+							g.ln[p] = r.ln[p];
+							g.lt1[p] = r.lt1[p];
+							g.lt2[p] = r.lt2[p];
+						}
+					}
+					__syncwarp();
+				}
+				bar();
+			}
+		// accumulated impulses back into the manifolds (next sub-step's warm start reads them there)
+		for (uint32_t k = tid; k < nact; k += stride)
+		{
+			const SolveRec &r = a.recs[k];
+			SMan &m = a.man[r.mi];
+#pragma unroll
+			for (int p = 0; p < 4; p++)
+			{
+				m.ln[p] = r.ln[p];
+				m.lt1[p] = r.lt1[p];
+				m.lt2[p] = r.lt2[p];
+			}
 		}
 	}
 	grid.sync();
-	// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
-	// dynamic body, so every body is written by at most one thread per phase.
-	for (uint32_t it = 0; it <= a.vel_steps; it++)
-		for (int col = 0; col < ncol; col++)
-		{
-			const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
-			// each warp stages its 32 consecutive records in shared memory with coalesced 16-byte copies, solves from
-			// there and writes back only the accumulated impulses
-			for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
-			{
-				const uint32_t cnt32 = min(32u, hi - k0);
-				const float4 *src = reinterpret_cast<const float4 *>(a.recs + k0);
-				float4 *dst = reinterpret_cast<float4 *>(stage + (threadIdx.x & ~31u));
-				const uint32_t n16 = cnt32 * (uint32_t)(sizeof(SolveRec) / 16);
-				for (uint32_t q = lane; q < n16; q += 32u) dst[q] = __ldcg(&src[q]);
-				__syncwarp();
-				if (lane < cnt32)
-				{
-					SolveRec &r = stage[threadIdx.x];
-					const Con c = r.con;
-					Vel u;
-					load_vel(c, a.bodies, u);
-					if (it == 0)
-						warm_start(c, r.pts, r, u);
-					else
-						solve_velocity(c, r.pts, r, u);
-					store_vel(c, a.bodies, u);
-					SolveRec &g = a.recs[k0 + lane];
-#pragma unroll
-					for (int p = 0; p < 4; p++)
-					{
-						g.ln[p] = r.ln[p];
-						g.lt1[p] = r.lt1[p];
-						g.lt2[p] = r.lt2[p];
-					}
-				}
-				__syncwarp();
-			}
-			grid.sync();
-		}
-	// accumulated impulses back into the manifolds (next sub-step's warm start reads them there)
-	for (uint32_t k = tid; k < nact; k += stride)
-	{
-		const SolveRec &r = a.recs[k];
-		SMan &m = a.man[r.mi];
-#pragma unroll
-		for (int p = 0; p < 4; p++)
-		{
-			m.ln[p] = r.ln[p];
-			m.lt1[p] = r.lt1[p];
-			m.lt2[p] = r.lt2[p];
-		}
-	}
-	// integrate
-	for (uint32_t i = tid; i < a.nb; i += stride)
+	// integrate: everything that moves and was not integrated inside a small island — the large islands, bodies
+	// without contacts, kinematic bodies.  After every set-up (kw_island ran earlier), before every position row.
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nb; i += gridDim.x * blockDim.x)
 	{
 		SBody &b = a.bodies[i];
 		if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC) continue;
+		if (a.root_of[i] & ROOT_SMALL) continue;  // integrated by kw_island
 		b.x = b.x + (b.v * h);
 		b.q = qstep(b.q, b.w * h);
 	}
 	grid.sync();
+	if (!phased) return;
 	// position iterations
 	for (uint32_t it = 0; it < a.pos_steps; it++)
 		for (int col = 0; col < ncol; col++)
 		{
 			const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
 			for (uint32_t k = lo + tid; k < hi; k += stride) solve_position(a.man[a.col_list[k]], a.bodies);
-			grid.sync();
+			bar();
 		}
 }
 
@@ -676,12 +1078,16 @@ int wide_create(gpx_world *w)
 	d->n_pad = next_pow2(d->nb);
 	d->cap_m = w->cap_m;
 	d->hsize = next_pow2(2u * d->cap_m);
+	// worst case of the window packing: every window half empty, plus one open window per kw_isl_place block
+	d->isl_slots = 2u * d->cap_m + 32u * ((d->nb + WT - 1) / WT);
 	bool ok = walloc(&d->bodies, d->nb) && walloc(&d->keys, d->n_pad) && walloc(&d->boxlo, d->n_pad) &&
 			  walloc(&d->boxhi, d->n_pad) && walloc(&d->man[0], d->cap_m) && walloc(&d->man[1], d->cap_m) &&
 			  walloc(&d->ord[0], d->cap_m) && walloc(&d->ord[1], d->cap_m) && walloc(&d->recs, d->cap_m) &&
 			  walloc(&d->counters, (size_t)WC_COUNT) && walloc(&d->hkeys, d->hsize) && walloc(&d->hvals, d->hsize) &&
 			  walloc(&d->adj, (size_t)d->nb * WIDE_MAXADJ) && walloc(&d->adj_n, d->nb) && walloc(&d->prio, d->cap_m) &&
-			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m);
+			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m) && walloc(&d->parent, d->nb) &&
+			  walloc(&d->root_of, d->nb) && walloc(&d->isl_cnt, d->nb) && walloc(&d->isl_off, d->nb) && walloc(&d->isl_cur, d->nb) &&
+			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m);
 	if (!ok)
 	{
 		set_error("wide_create", cudaGetLastError());
@@ -704,6 +1110,8 @@ void wide_destroy(gpx_world *w)
 	cudaFree(d->bodies); cudaFree(d->keys); cudaFree(d->boxlo); cudaFree(d->boxhi); cudaFree(d->man[0]); cudaFree(d->man[1]);
 	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
+	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
+	cudaFree(d->isl_man); cudaFree(d->big_list);
 	delete d;
 	w->wide = nullptr;
 }
@@ -720,6 +1128,7 @@ int wide_counters(gpx_world *w, uint32_t *out8)
 {
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	GPX_CUDA(cudaMemcpy(out8, w->wide->counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	GPX_CUDA(cudaMemcpy(out8 + WC_NPREV, w->wide->counters + WC_NISL, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return GPX_OK;
 }
 
@@ -743,6 +1152,13 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.prio = d->prio;
 	a.pending = d->pending;
 	a.col_list = d->col_list;
+	a.parent = d->parent;
+	a.root_of = d->root_of;
+	a.isl_cnt = d->isl_cnt;
+	a.isl_off = d->isl_off;
+	a.isl_cur = d->isl_cur;
+	a.isl_man = d->isl_man;
+	a.big_list = d->big_list;
 	a.cand = w->d_cand;
 	a.sv.nodes = w->sd.nodes;
 	a.sv.tris = w->sd.tri;
@@ -778,10 +1194,19 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		kw_pairs<<<(d->cap_m + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);
 		kw_static<<<(d->nb + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);
 		kw_link<<<gm, WT, 0, st>>>(a);
-		count_launch(5);
+		GPX_CUDA(cudaMemsetAsync(d->isl_man, 0xFF, sizeof(uint32_t) * d->isl_slots, st));
+		kw_isl_count<<<gm, WT, 0, st>>>(a);
+		kw_isl_place<<<(d->nb + WT - 1) / WT, WT, 0, st>>>(a);
+		kw_isl_fill<<<gm, WT, 0, st>>>(a);
+		// one warp per 32-slot window; warps beyond the windows in use leave at once
+		const uint32_t gi = (d->isl_slots / 32u + ISLAND_WARPS - 1) / ISLAND_WARPS;
+		kw_island<<<gi, ISLAND_WARPS * 32, 0, st>>>(a);
+		count_launch(9);
 		int rc;
 		if ((rc = coop_launch((const void *)kw_colour, d->coop_grid_colour, a, st)) != GPX_OK) return rc;
 		if ((rc = coop_launch((const void *)kw_solve, d->coop_grid_solve, a, st, 256 * sizeof(SolveRec))) != GPX_OK) return rc;
+		kw_island_pos<<<gi, ISLAND_WARPS * 32, 0, st>>>(a);
+		count_launch();
 		// this sub-step's manifolds become the next one's warm-start table
 		GPX_CUDA(cudaMemsetAsync(d->hkeys, 0, sizeof(unsigned long long) * d->hsize, st));
 		kw_finish<<<max(gm, gb), WT, 0, st>>>(a);

@@ -82,6 +82,40 @@ def test_pile_on_shipped_map_with_mixed_bodies(gpx, orc, scenes):
             _assert_same(g, o, n, f"pile tick {tick}")
 
 
+def test_islands_small_large_kinematic_and_free_bodies(gpx, orc, scenes):
+    """The island split of the wide path: separate short columns (islands solved inside one warp), an 8 x 5 wall
+    whose boxes all touch (one large island -> the phased kernels), a column riding a moving kinematic platform (its
+    contacts are set up before the platform moves and position-corrected after), and bodies still in free fall."""
+    descs = []
+    for ix in range(6):                                   # six 3-box columns, 1.5 m apart: six small islands
+        for k in range(3):
+            descs.append(dict(position=(-6.0 + 1.5 * ix, -511.75 + 0.41 * k, -4.0)))
+    for j in range(5):                                    # an 8 x 5 wall of touching boxes: one island of > 32 manifolds
+        for i in range(8):
+            descs.append(dict(position=(4.0 + 0.4 * i, -511.75 + 0.4 * j, 6.0)))
+    descs.append(dict(half_extents=(0.8, 0.05, 0.8), position=(-2.0, -511.0, 3.0), motion_type=1, linear_velocity=(0.3, 0.05, 0.0)))
+    for k in range(3):                                    # column on the platform
+        descs.append(dict(position=(-2.0, -510.74 + 0.41 * k, 3.0), friction=0.8))
+    for k in range(5):                                    # free fall for the whole run
+        descs.append(dict(shape=2, half_extents=(0.2, 0, 0), position=(10.0 + k, -400.0, -10.0), angular_velocity=(0.3 * k, 0.1, 0.0)))
+    n = len(descs)
+    assert n > 64
+    g, o = _pair(gpx, orc, scenes.box_map(), n)
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    for tick in range(1, 101):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 2, 10, 40, 100):
+            assert g.sync() == 0
+            _assert_same(g, o, n, f"islands tick {tick}")
+    c = g.wide_counters()
+    assert c["small_islands"] >= 7 and c["large_island_manifolds"] > 32
+    x = g.transforms()[0, :n]
+    plat = 18 + 40
+    assert abs(x[plat, 0] - (-2.0 + 0.3 * 100 / 60)) < 1e-3                   # the platform went where its velocity says
+    assert np.all(x[plat + 1:plat + 4, 0] > -1.9)                              # and carried its column along
+
+
 def test_two_thousand_boxes_match_oracle(gpx, orc, scenes):
     """20 x 5 x 20 lattice: exercises the sort-and-sweep at a size the all-pairs oracle still finishes in seconds."""
     pos = scenes.lattice_positions(20, 5, 20)
