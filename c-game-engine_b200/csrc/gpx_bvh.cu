@@ -137,6 +137,132 @@ void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t s
 	else bitonic_sort_tiles<2048u>(d_keys, n_pad, st);
 }
 
+// ---- LSD radix sort, 8 bits per pass, stable.  Used where a key array is re-sorted every sub-step (the wide-world
+// broadphase): three launches per pass — per-block digit histograms, one scan over (digit, block), a scatter that
+// ranks keys inside each warp with match_any so equal digits keep their order.
+constexpr uint32_t RADIX_BLOCK = 256, RADIX_ITEMS = 4, RADIX_TILE = RADIX_BLOCK * RADIX_ITEMS;  // 1024 keys per block
+
+__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long long *__restrict__ keys, uint32_t shift,
+															uint32_t *__restrict__ ghist)
+{
+	__shared__ uint32_t hist[256];
+	hist[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t base = blockIdx.x * RADIX_TILE;
+#pragma unroll
+	for (uint32_t i = 0; i < RADIX_ITEMS; i++)
+		atomicAdd(&hist[(uint32_t)(keys[base + i * RADIX_BLOCK + threadIdx.x] >> shift) & 255u], 1u);
+	__syncthreads();
+	ghist[threadIdx.x * gridDim.x + blockIdx.x] = hist[threadIdx.x];  // digit-major: the scan order of the scatter
+}
+
+// exclusive scan of `n` counters by one block (n = 256 digits x blocks, a few 10^4): each warp owns a contiguous
+// chunk and walks it 32 entries at a time (coalesced); the loads of the first pass are independent, the second pass
+// re-reads from cache
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ ghist, uint32_t n)
+{
+	__shared__ uint32_t warp_sum[32];
+	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const uint32_t chunk = (((n + 31u) / 32u) + 31u) & ~31u;
+	const uint32_t lo = wid * chunk, hi = min(lo + chunk, n);
+	uint32_t sum = 0;
+#pragma unroll 8
+	for (uint32_t i = lo + lane; i < hi; i += 32u) sum += ghist[i];
+	for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+	if (lane == 0) warp_sum[wid] = sum;
+	__syncthreads();
+	if (wid == 0)
+	{
+		const uint32_t w = warp_sum[lane];
+		uint32_t wi = w;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+			if (lane >= (uint32_t)o) wi += v;
+		}
+		warp_sum[lane] = wi - w;  // exclusive prefix of the warp totals
+	}
+	__syncthreads();
+	uint32_t run = warp_sum[wid];
+	for (uint32_t base = lo; base < hi; base += 32u)  // uniform per warp
+	{
+		const uint32_t i = base + lane;
+		const uint32_t c = i < hi ? ghist[i] : 0u;
+		uint32_t incl = c;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= (uint32_t)o) incl += v;
+		}
+		if (i < hi) ghist[i] = run + (incl - c);
+		run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+	}
+}
+
+__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned long long *__restrict__ keys,
+															   unsigned long long *__restrict__ out, uint32_t shift,
+															   const uint32_t *__restrict__ ghist)
+{
+	__shared__ uint32_t wcnt[RADIX_BLOCK / 32][256];
+	const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	for (uint32_t k = threadIdx.x; k < (RADIX_BLOCK / 32) * 256; k += RADIX_BLOCK) (&wcnt[0][0])[k] = 0;
+	__syncthreads();
+	// a warp owns 32 * RADIX_ITEMS consecutive keys; key order inside it is (item, lane)
+	const uint32_t base = blockIdx.x * RADIX_TILE + w * (32u * RADIX_ITEMS);
+	unsigned long long key[RADIX_ITEMS];
+	uint32_t local[RADIX_ITEMS];
+#pragma unroll
+	for (uint32_t i = 0; i < RADIX_ITEMS; i++)
+	{
+		key[i] = keys[base + i * 32u + lane];
+		const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+		const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+		const uint32_t before = wcnt[w][d];
+		__syncwarp();
+		if (lane == (uint32_t)__ffs((int)peers) - 1u) wcnt[w][d] = before + (uint32_t)__popc(peers);
+		__syncwarp();
+		local[i] = before + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+	}
+	__syncthreads();
+	{
+		// thread = digit: turn the per-warp counts into global start positions, warp after warp
+		const uint32_t d = threadIdx.x;
+		uint32_t run = ghist[d * gridDim.x + blockIdx.x];
+		for (uint32_t ww = 0; ww < RADIX_BLOCK / 32; ww++)
+		{
+			const uint32_t c = wcnt[ww][d];
+			wcnt[ww][d] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (uint32_t i = 0; i < RADIX_ITEMS; i++) out[wcnt[w][(uint32_t)(key[i] >> shift) & 255u] + local[i]] = key[i];
+}
+
+// Ascending stable sort of bits [first_bit, 64) of `n` keys (n a multiple of 1024); bits below first_bit keep their
+// input order.  `tmp` holds n keys, `ghist` 256 * n / 1024 counters.  The result ends in `d_keys`.
+void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_t *ghist, uint32_t n, uint32_t first_bit,
+					cudaStream_t st)
+{
+	const uint32_t blocks = n / RADIX_TILE;
+	uint32_t shifts[8];
+	int passes = 0;
+	for (uint32_t sh = first_bit; sh < 64u; sh += 8u) shifts[passes++] = sh > 56u ? 56u : sh;
+	if (passes & 1) shifts[passes++] = 56u;  // an even number of passes leaves the result in d_keys (a repeat is harmless)
+	unsigned long long *src = d_keys, *dst = tmp;
+	for (int p = 0; p < passes; p++)
+	{
+		k_radix_hist<<<blocks, RADIX_BLOCK, 0, st>>>(src, shifts[p], ghist);
+		k_radix_scan<<<1, 1024, 0, st>>>(ghist, 256u * blocks);
+		k_radix_scatter<<<blocks, RADIX_BLOCK, 0, st>>>(src, dst, shifts[p], ghist);
+		count_launch(3);
+		unsigned long long *t = src;
+		src = dst;
+		dst = t;
+	}
+}
+
 __device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j)
 {
 	if (j < 0 || j >= n) return -1;

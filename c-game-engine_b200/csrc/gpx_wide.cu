@@ -6,7 +6,7 @@
 //
 //   kw_begin      thread/body      SoA -> work record (first sub-step), forces, inertia, AABB, largest extents
 //   kw_keys       thread/body      sort key = (row along z, lower x bound, body)
-//   bitonic sort  (gpx_bvh.cu)     bodies ordered by row, then by the lower x bound of their boxes
+//   radix sort    (gpx_bvh.cu)     bodies ordered by row, then by the lower x bound of their boxes (bitonic below 4096)
 //   kw_gather     thread/slot      sorted boxes packed into two float4 streams
 //   kw_sweep      thread/body      sort-and-sweep broadphase: walk forward in the own row and through the reachable
 //                                  part of the next row, exact box test, layer matrix -> pair list (atomic append)
@@ -65,7 +65,8 @@ struct WideDevice
 {
 	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0, isl_slots = 0;
 	SBody *bodies = nullptr;
-	unsigned long long *keys = nullptr;
+	unsigned long long *keys = nullptr, *keys_tmp = nullptr;  // keys_tmp / sort_hist: radix sort scratch
+	uint32_t *sort_hist = nullptr;
 	float4 *boxlo = nullptr, *boxhi = nullptr;
 	SMan *man[2] = {nullptr, nullptr};
 	uint32_t *ord[2] = {nullptr, nullptr};  // ordinal of a manifold among those with the same (a, b)
@@ -1087,7 +1088,8 @@ int wide_create(gpx_world *w)
 			  walloc(&d->adj, (size_t)d->nb * WIDE_MAXADJ) && walloc(&d->adj_n, d->nb) && walloc(&d->prio, d->cap_m) &&
 			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m) && walloc(&d->parent, d->nb) &&
 			  walloc(&d->root_of, d->nb) && walloc(&d->isl_cnt, d->nb) && walloc(&d->isl_off, d->nb) && walloc(&d->isl_cur, d->nb) &&
-			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m);
+			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m) &&
+			  walloc(&d->keys_tmp, d->n_pad) && walloc(&d->sort_hist, (size_t)256 * (d->n_pad / 1024u + 1u));
 	if (!ok)
 	{
 		set_error("wide_create", cudaGetLastError());
@@ -1111,7 +1113,7 @@ void wide_destroy(gpx_world *w)
 	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
-	cudaFree(d->isl_man); cudaFree(d->big_list);
+	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->keys_tmp); cudaFree(d->sort_hist);
 	delete d;
 	w->wide = nullptr;
 }
@@ -1188,7 +1190,10 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		kw_begin<<<gb, WT, 0, st>>>(a);
 		kw_keys<<<gb, WT, 0, st>>>(a);
 		count_launch(2);
-		bitonic_sort_u64(d->keys, d->n_pad, st);
+		// keys arrive in body order with the body index in the low 20 bits: a stable sort of the bits above it is the
+		// full sort
+		if (d->n_pad >= 4096u) radix_sort_u64(d->keys, d->keys_tmp, d->sort_hist, d->n_pad, 20u, st);
+		else bitonic_sort_u64(d->keys, d->n_pad, st);
 		kw_gather<<<gb, WT, 0, st>>>(a);
 		kw_sweep<<<gb, WT, 0, st>>>(a);
 		kw_pairs<<<(d->cap_m + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);
