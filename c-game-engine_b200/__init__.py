@@ -94,6 +94,10 @@ class Transform(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("rotation", C.c_float * 4)]
 
 
+FIXED_UPDATE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double)          # gpx_fixed_update_fn
+INPUT_EVENT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)  # gpx_input_event_fn
+
+
 def body_desc(shape=SHAPE_BOX, half_extents=(0.2, 0.2, 0.2), position=(0, 0, 0), rotation=(0, 0, 0, 1),
               linear_velocity=(0, 0, 0), angular_velocity=(0, 0, 0), motion_type=MOTION_DYNAMIC,
               layer=LAYER_DYNAMIC, mass=10.0, friction=0.2, restitution=0.0, linear_damping=0.05,
@@ -159,6 +163,16 @@ def lib() -> C.CDLL:
         "gpx_world_create": (vp, [C.POINTER(WorldConfig)]),
         "gpx_world_destroy": (None, [vp]),
         "gpx_static_add_mesh": (i32, [vp, C.POINTER(Transform), vp, u64, f32, u64, C.POINTER(u32)]),
+        "gpx_thread_init": (i32, [vp]),
+        "gpx_thread_set_function": (None, [vp]),
+        "gpx_thread_queue_input_event": (None, [vp, u64]),
+        "gpx_thread_set_input_handler": (None, [vp]),
+        "gpx_thread_terminate": (None, []),
+        "gpx_thread_lock_tick_mutex": (None, []),
+        "gpx_thread_unlock_tick_mutex": (None, []),
+        "gpx_thread_set_pinned_delta": (None, [i32]),
+        "gpx_thread_frame": (u64, []),
+        "gpx_thread_last_tick_ns": (u64, []),
         "gpx_static_commit": (i32, [vp]),
         "gpx_static_remove_mesh": (i32, [vp, u32]),
         "gpx_static_load_gmap": (i32, [vp, vp, u64]),

@@ -244,6 +244,32 @@ int gpx_read_velocities(gpx_world *w, float *out_lin_ang6, uint64_t capacity);
 /* Per-world stats computed on device, `out` has `worlds` entries (host). */
 int gpx_read_stats(gpx_world *w, gpx_world_stats *out);
 
+/* ---- the step loop ---------------------------------------------------------------------------------------------------- */
+
+/* PhysicsThreadMain and its controls (engine/src/subsystem/threads/PhysicsThread.c:59-159, PhysicsThread.h:10-36),
+ * without SDL: one thread calls `function(state, delta)` at 60 Hz while holding the tick mutex.  `delta` is the wall
+ * time of the previous tick, idle time included, in units of 1/60 s, clamped to 6 (the 10 ticks/s floor of
+ * engine/include/engine/physics/Physics.h:12-22); MapFixedUpdate turns it into dt = delta / 60 (MapPhysics.c:72).
+ * Host code only.  One loop per process, as in the engine. */
+typedef void (*gpx_fixed_update_fn)(void *state, double delta);               /* GameStateFixedUpdateFunction */
+typedef void (*gpx_input_event_fn)(void *state, const void *event, uint64_t size);
+/* PhysicsThreadInit: starts the thread; it idles at 60 Hz (counting frames) until a function is set. */
+int gpx_thread_init(void *state);
+/* PhysicsThreadSetFunction: waits for the running iteration to pick up its function, resets the frame counter. */
+void gpx_thread_set_function(gpx_fixed_update_fn function);
+/* PhysicsThreadQueueInputEvent: the bytes are copied and handed to the input handler at the start of the next tick. */
+void gpx_thread_queue_input_event(const void *event, uint64_t size);
+void gpx_thread_set_input_handler(gpx_input_event_fn handler);
+/* PhysicsThreadTerminate: posts quit, joins. */
+void gpx_thread_terminate(void);
+/* PhysicsThreadLockTickMutex / UnlockTickMutex: exclude the fixed update (GlobalState.c:179-192 changes maps under it). */
+void gpx_thread_lock_tick_mutex(void);
+void gpx_thread_unlock_tick_mutex(void);
+/* Not in the engine: pinned != 0 makes every delta exactly 1 and drops the sleep — headless, reproducible runs. */
+void gpx_thread_set_pinned_delta(int pinned);
+uint64_t gpx_thread_frame(void);        /* GlobalState.physicsFrame */
+uint64_t gpx_thread_last_tick_ns(void); /* what TickGraphUpdate is fed (PhysicsThread.c:109) */
+
 /* ---- player character -------------------------------------------------------------------------------------------- */
 
 /* JPH_CharacterVirtual as the engine uses it (engine/src/physics/PlayerPhysics.c:173-194): a capsule that is not a
