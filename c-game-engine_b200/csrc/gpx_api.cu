@@ -18,6 +18,9 @@ static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
 static int g_device = -1;
 
+static inline float4 *front_pos(const gpx_world *w) { return w->mb_pos[w->mirror_gen.load(std::memory_order_acquire) & 1u]; }
+static inline float4 *front_quat(const gpx_world *w) { return w->mb_quat[w->mirror_gen.load(std::memory_order_acquire) & 1u]; }
+
 void set_error(const char *what, cudaError_t e)
 {
 	g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -263,8 +266,10 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	ok = ok && cudaMalloc(&w->d_cand, sizeof(uint4) * 8 * nb) == cudaSuccess &&
 		 cudaMemset(w->d_cand, 0xFF, sizeof(uint4) * 8 * nb) == cudaSuccess;
 	ok = ok && dalloc(&w->d_err, (size_t)w->W + 1) == GPX_OK && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
-	ok = ok && cudaMallocHost(&w->m_pos, sizeof(float4) * nb) == cudaSuccess &&
-		 cudaMallocHost(&w->m_quat, sizeof(float4) * nb) == cudaSuccess &&
+	ok = ok && cudaMallocHost(&w->mb_pos[0], sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->mb_pos[1], sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->mb_quat[0], sizeof(float4) * nb) == cudaSuccess &&
+		 cudaMallocHost(&w->mb_quat[1], sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_lin, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_ang, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_err, sizeof(uint32_t) * 4) == cudaSuccess;
@@ -274,8 +279,11 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		gpx_world_destroy(w);
 		return nullptr;
 	}
-	memset(w->m_pos, 0, sizeof(float4) * nb);
-	memset(w->m_quat, 0, sizeof(float4) * nb);
+	for (int k = 0; k < 2; k++)
+	{
+		memset(w->mb_pos[k], 0, sizeof(float4) * nb);
+		memset(w->mb_quat[k], 0, sizeof(float4) * nb);
+	}
 	memset(w->m_lin, 0, sizeof(float4) * nb);
 	memset(w->m_ang, 0, sizeof(float4) * nb);
 	w->m_err[0] = 0;
@@ -298,7 +306,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);
-	cudaFreeHost(w->m_pos); cudaFreeHost(w->m_quat); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
+	cudaFreeHost(w->mb_pos[0]); cudaFreeHost(w->mb_pos[1]); cudaFreeHost(w->mb_quat[0]); cudaFreeHost(w->mb_quat[1]); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->ev_fork) cudaEventDestroy(w->ev_fork);
@@ -583,8 +591,8 @@ uint32_t gpx_body_create(gpx_world *w, uint32_t world, const gpx_body_desc *desc
 			BodyCommand c = command_from_desc((uint32_t)(base + i), *desc);
 			w->h_flags[base + i] = c.flags;
 			w->h_user_data[base + i] = desc->user_data;
-			w->m_pos[base + i] = c.pos;
-			w->m_quat[base + i] = c.quat;
+			front_pos(w)[base + i] = c.pos;
+			front_quat(w)[base + i] = c.quat;
 			w->m_lin[base + i] = c.lin;
 			w->m_ang[base + i] = c.ang;
 			w->pending.push_back(c);
@@ -625,8 +633,8 @@ int gpx_body_create_all(gpx_world *w, const gpx_body_desc *descs, uint32_t count
 			}
 			w->h_flags[g] = c.flags;
 			w->h_user_data[g] = descs[k].user_data;
-			w->m_pos[g] = c.pos;
-			w->m_quat[g] = c.quat;
+			front_pos(w)[g] = c.pos;
+			front_quat(w)[g] = c.quat;
 			w->m_lin[g] = c.lin;
 			w->m_ang[g] = c.ang;
 			w->pending.push_back(c);
@@ -664,13 +672,13 @@ static int queue_write(gpx_world *w, uint32_t world, uint32_t body, uint32_t mas
 	memset(&c, 0, sizeof(c));
 	c.index = (uint32_t)g;
 	c.mask = mask;
-	if (mask & 1u) w->m_pos[g] = c.pos = make_float4(a[0], a[1], a[2], 0.0f);
+	if (mask & 1u) front_pos(w)[g] = c.pos = make_float4(a[0], a[1], a[2], 0.0f);
 	if (mask & 2u)
 	{
 		q4 q;
 		q.x = a[0]; q.y = a[1]; q.z = a[2]; q.w = a[3];
 		q = qnormalize(q);
-		w->m_quat[g] = c.quat = make_float4(q.x, q.y, q.z, q.w);
+		front_quat(w)[g] = c.quat = make_float4(q.x, q.y, q.z, q.w);
 	}
 	if (mask & 4u) w->m_lin[g] = c.lin = make_float4(a[0], a[1], a[2], 0.0f);
 	if (mask & 8u)
@@ -738,7 +746,15 @@ int gpx_body_get_transform(const gpx_world *w, uint32_t world, uint32_t body, gp
 	}
 	if (!valid_slot(w, world, body)) return GPX_ERR_INVALID_ARG;
 	const size_t g = (size_t)world * w->cap + body;
-	const float4 p = w->m_pos[g], q = w->m_quat[g];
+	float4 p, q;
+	for (;;)
+	{
+		// wait-free unless a whole readback completes in between (then read the new front)
+		const uint32_t gen = w->mirror_gen.load(std::memory_order_acquire);
+		p = w->mb_pos[gen & 1u][g];
+		q = w->mb_quat[gen & 1u][g];
+		if (w->mirror_gen.load(std::memory_order_acquire) == gen) break;
+	}
 	out->position[0] = p.x; out->position[1] = p.y; out->position[2] = p.z;
 	out->rotation[0] = q.x; out->rotation[1] = q.y; out->rotation[2] = q.z; out->rotation[3] = q.w;
 	return GPX_OK;
@@ -806,10 +822,12 @@ int gpx_sync_transforms(gpx_world *w)
 	int rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	const size_t nb = (size_t)w->W * w->cap;
-	GPX_CUDA(cudaMemcpyAsync(w->m_pos, w->bs.pos, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
-	GPX_CUDA(cudaMemcpyAsync(w->m_quat, w->bs.quat, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	const uint32_t gen = w->mirror_gen.load(std::memory_order_relaxed), back = (gen + 1u) & 1u;
+	GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(w->mb_quat[back], w->bs.quat, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
 	GPX_CUDA(cudaMemcpyAsync(w->m_err, w->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	w->mirror_gen.store(gen + 1u, std::memory_order_release);  // the tick just read back becomes the front
 	return (int)w->m_err[0];
 }
 
@@ -821,7 +839,7 @@ int gpx_read_transforms(gpx_world *w, gpx_transform *out, uint64_t capacity)
 	int rc = gpx_sync_transforms(w);
 	for (size_t g = 0; g < nb; g++)
 	{
-		const float4 p = w->m_pos[g], q = w->m_quat[g];
+		const float4 p = front_pos(w)[g], q = front_quat(w)[g];
 		out[g].position[0] = p.x; out[g].position[1] = p.y; out[g].position[2] = p.z;
 		out[g].rotation[0] = q.x; out[g].rotation[1] = q.y; out[g].rotation[2] = q.z; out[g].rotation[3] = q.w;
 	}

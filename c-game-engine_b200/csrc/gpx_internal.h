@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -126,7 +127,11 @@ struct gpx_world
 	std::mutex mu;  // guards pending/h_flags: create/destroy/set arrive from several engine threads
 
 	// host mirror (pinned) served to getters
-	float4 *m_pos = nullptr, *m_quat = nullptr, *m_lin = nullptr, *m_ang = nullptr;
+	// transforms are double-buffered: a readback fills the back pair, then mirror_gen is bumped (front = mirror_gen & 1), so
+	// getters on other threads (render, LOD) never see a half-written tick
+	float4 *mb_pos[2] = {nullptr, nullptr}, *mb_quat[2] = {nullptr, nullptr};
+	std::atomic<uint32_t> mirror_gen{0};
+	float4 *m_lin = nullptr, *m_ang = nullptr;
 	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors
 	uint32_t *m_err = nullptr;  // pinned
 	gpx_world_stats *d_stats = nullptr;

@@ -53,3 +53,40 @@ def test_stack8_under_the_step_loop_matches_the_oracle(gpx, orc, scenes):
     for _ in range(TICKS):
         assert o.step() == 0
     assert np.array_equal(g.transforms()[0].view(np.uint32), o.state(8)[0].view(np.uint32))
+
+
+def test_getters_never_see_half_a_tick(gpx, scenes):
+    """The transform mirror is double-buffered: position and rotation read by another thread belong to one tick.
+    A kinematic body moves 1 cm and turns 0.01 rad per tick, so both fields encode the tick they were written in."""
+    worlds = 64                                        # a mirror of a few hundred KB: the two copies are not instantaneous
+    g = gpx.World(worlds=worlds, max_bodies=64)
+    g.commit()
+    d = gpx.body_desc(half_extents=(0.5, 0.1, 0.5), motion_type=gpx.MOTION_KINEMATIC, layer=0, position=(0.0, 0.0, 0.0),
+                      linear_velocity=(0.6, 0.0, 0.0), angular_velocity=(0.0, 0.6, 0.0), linear_damping=0.0, angular_damping=0.0)
+    ids = g.create_all([d] * 64)
+    last = (worlds - 1, int(ids[-1]))                  # the last slot: its position arrives long before its rotation
+    stop = threading.Event()
+    bad, reads = [], [0]
+
+    def reader():
+        while not stop.is_set():
+            x = g.get_transform(last[1], world=last[0])
+            tick_p = x[0] / 0.01
+            tick_q = 2.0 * np.arctan2(x[4], x[6]) / 0.01
+            reads[0] += 1
+            if abs(tick_p - tick_q) > 0.25:
+                bad.append((float(tick_p), float(tick_q)))
+
+    t = threading.Thread(target=reader)
+    t.start()
+    try:
+        for _ in range(300):
+            assert g.step() == 0
+            assert g.sync() == 0
+    finally:
+        stop.set()
+        t.join()
+    assert reads[0] > 100
+    assert not bad, f"{len(bad)} torn reads, e.g. {bad[:3]}"
+    x = g.get_transform(last[1], world=last[0])
+    assert abs(x[0] - 3.0) < 1e-3 and abs(2.0 * np.arctan2(x[4], x[6]) - 3.0) < 1e-3
