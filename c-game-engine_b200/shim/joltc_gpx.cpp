@@ -21,6 +21,10 @@ namespace {
 constexpr uint32_t N_LAYERS = 4;     // enum ObjectLayers, engine/include/engine/physics/Physics.h:36-42
 constexpr uint32_t N_BP_LAYERS = 2;  // enum BroadPhaseLayers, Physics.h:44-51
 constexpr uint32_t STATIC_BASE = 0x400000u;
+// Public body ids carry a sequence number in the top byte, like Jolt's (index in the low 23 bits): a slot that is reused
+// gets a new id, and calls made with the old one find nothing.
+constexpr uint32_t ID_INDEX_MASK = 0x007FFFFFu;
+constexpr uint32_t ID_SEQ_SHIFT = 24;
 constexpr float MIN_HALF_EXTENT = 0.01f;  // a flat 4-point hull (ActorWall.c:20-49) becomes a 2 cm slab
 
 void complain(const char *what) { fprintf(stderr, "joltc_gpx: %s\n", what); }
@@ -129,7 +133,15 @@ struct JPH_PhysicsSystem
 	JPH_NarrowPhaseQuery npq{this};
 	uint8_t bp_of_layer[N_LAYERS] = {0, 1, 1, 0};
 	std::mutex mu;  // guards `bodies`
-	std::unordered_map<JPH_BodyID, BodyRecord> bodies;
+	std::unordered_map<JPH_BodyID, BodyRecord> bodies;        // keyed by public id
+	std::unordered_map<uint32_t, uint32_t> slot_seq;           // device id -> uses so far
+	std::unordered_map<uint32_t, JPH_BodyID> public_of;        // device id -> public id of the body living there
+	JPH_BodyID to_public(uint32_t raw)
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		auto it = public_of.find(raw);
+		return it == public_of.end() ? raw : it->second;
+	}
 	JPH_CharacterVirtual *character = nullptr;
 	std::vector<gpx_contact_event> events;
 	float gravity[3] = {0.0f, -9.81f, 0.0f};
@@ -393,6 +405,7 @@ static void deliver_character_events(JPH_PhysicsSystem *sys)
 		if (e.body_a == GPX_CHARACTER_BODY) other = e.body_b;
 		else if (e.body_b == GPX_CHARACTER_BODY) other = e.body_a;
 		else continue;
+		other = sys->to_public(other);
 		if (e.kind == GPX_EVENT_REMOVED)
 		{
 			if (cb.OnContactRemoved) cb.OnContactRemoved(ch, other, 0);
@@ -659,8 +672,20 @@ JPH_BodyID make_body(JPH_PhysicsSystem *sys, const JPH_BodyCreationSettings *st)
 		st->shape->refs.fetch_add(1);
 	}
 	std::lock_guard<std::mutex> lk(sys->mu);
-	sys->bodies[id] = rec;
-	return id;
+	const uint32_t seq = sys->slot_seq[id]++ % 255u;  // 255 is left out so no id can equal JPH_BodyId_InvalidBodyID
+	const JPH_BodyID pub = id | (seq << ID_SEQ_SHIFT);
+	sys->bodies[pub] = rec;
+	sys->public_of[id] = pub;
+	return pub;
+}
+
+// The device slot behind a public id, if that body is still alive and lives in a body slot (not the static soup).
+bool live_slot(JPH_PhysicsSystem *sys, JPH_BodyID id, uint32_t &raw)
+{
+	raw = id & ID_INDEX_MASK;
+	if (!sys->w || raw >= STATIC_BASE) return false;
+	std::lock_guard<std::mutex> lk(sys->mu);
+	return sys->bodies.find(id) != sys->bodies.end();
 }
 
 // Body origin and rotation from the device primitive's centre.
@@ -675,7 +700,7 @@ bool body_pose(JPH_PhysicsSystem *sys, JPH_BodyID id, v3 &pos, JPH_Quat &rot)
 	}
 	// The mirror is written by Update's readback and, in between, by gpx_body_create and the setters themselves.
 	gpx_transform t;
-	if (gpx_body_get_transform(sys->w, 0, id, &t) != GPX_OK) return false;
+	if (gpx_body_get_transform(sys->w, 0, id & ID_INDEX_MASK, &t) != GPX_OK) return false;
 	rot = {t.rotation[0], t.rotation[1], t.rotation[2], t.rotation[3]};
 	pos = v3{t.position[0], t.position[1], t.position[2]} - qrot(rot, center);
 	return true;
@@ -759,10 +784,11 @@ void JPH_BodyInterface_RemoveAndDestroyBody(JPH_BodyInterface *bi, JPH_BodyID id
 		auto it = sys->bodies.find(id);
 		if (it == sys->bodies.end()) return;
 		shape = it->second.shape;
-		sys->bodies.erase(it);
+		sys->bodies.erase(it);  // public_of keeps the last id of the slot: a late 'removed' event still names this body
 	}
-	if (id >= STATIC_BASE) gpx_static_remove_mesh(sys->w, id);
-	else gpx_body_destroy(sys->w, 0, id);
+	const uint32_t raw = id & ID_INDEX_MASK;
+	if (raw >= STATIC_BASE) gpx_static_remove_mesh(sys->w, raw);
+	else gpx_body_destroy(sys->w, 0, raw);
 	JPH_Shape_Destroy(shape);
 }
 
@@ -804,16 +830,18 @@ uint64_t JPH_BodyInterface_GetUserData(JPH_BodyInterface *bi, JPH_BodyID id)
 }
 void JPH_BodyInterface_SetLinearVelocity(JPH_BodyInterface *bi, JPH_BodyID id, const Vector3 *v)
 {
-	if (bi && bi->sys && bi->sys->w && v && id < STATIC_BASE) gpx_body_set_linear_velocity(bi->sys->w, 0, id, &v->x);
+	uint32_t raw;
+	if (bi && bi->sys && v && live_slot(bi->sys, id, raw)) gpx_body_set_linear_velocity(bi->sys->w, 0, raw, &v->x);
 }
 void JPH_BodyInterface_SetLinearAndAngularVelocity(JPH_BodyInterface *bi, JPH_BodyID id, const Vector3 *lin, const Vector3 *ang)
 {
-	if (bi && bi->sys && bi->sys->w && lin && ang && id < STATIC_BASE)
-		gpx_body_set_linear_and_angular_velocity(bi->sys->w, 0, id, &lin->x, &ang->x);
+	uint32_t raw;
+	if (bi && bi->sys && lin && ang && live_slot(bi->sys, id, raw))
+		gpx_body_set_linear_and_angular_velocity(bi->sys->w, 0, raw, &lin->x, &ang->x);
 }
 void JPH_BodyInterface_SetPosition(JPH_BodyInterface *bi, JPH_BodyID id, const JPH_RVec3 *position, JPH_Activation activation)
 {
-	if (!bi || !bi->sys || !bi->sys->w || !position || id >= STATIC_BASE) return;
+	if (!bi || !bi->sys || !bi->sys->w || !position || (id & ID_INDEX_MASK) >= STATIC_BASE) return;
 	v3 p;
 	JPH_Quat q;
 	v3 center{0, 0, 0};
@@ -825,11 +853,11 @@ void JPH_BodyInterface_SetPosition(JPH_BodyInterface *bi, JPH_BodyID id, const J
 	}
 	if (!body_pose(bi->sys, id, p, q)) return;
 	const v3 c = V(*position) + qrot(q, center);
-	gpx_body_set_position(bi->sys->w, 0, id, &c.x, activation == JPH_Activation_Activate);
+	gpx_body_set_position(bi->sys->w, 0, id & ID_INDEX_MASK, &c.x, activation == JPH_Activation_Activate);
 }
 void JPH_BodyInterface_SetRotation(JPH_BodyInterface *bi, JPH_BodyID id, const JPH_Quat *rotation, JPH_Activation activation)
 {
-	if (!bi || !bi->sys || !bi->sys->w || !rotation || id >= STATIC_BASE) return;
+	if (!bi || !bi->sys || !bi->sys->w || !rotation || (id & ID_INDEX_MASK) >= STATIC_BASE) return;
 	v3 p;
 	JPH_Quat q;
 	v3 center{0, 0, 0};
@@ -840,14 +868,14 @@ void JPH_BodyInterface_SetRotation(JPH_BodyInterface *bi, JPH_BodyID id, const J
 		center = it->second.center;
 	}
 	if (!body_pose(bi->sys, id, p, q)) return;
-	gpx_body_set_rotation(bi->sys->w, 0, id, &rotation->x, activation == JPH_Activation_Activate);
+	gpx_body_set_rotation(bi->sys->w, 0, id & ID_INDEX_MASK, &rotation->x, activation == JPH_Activation_Activate);
 	if (center.x != 0.0f || center.y != 0.0f || center.z != 0.0f)
 	{
 		// the body turns about its origin, so an off-centre primitive moves
 		JPH_Quat nq;
 		JPH_Quat_Normalized(rotation, &nq);
 		const v3 c = p + qrot(nq, center);
-		gpx_body_set_position(bi->sys->w, 0, id, &c.x, activation == JPH_Activation_Activate);
+		gpx_body_set_position(bi->sys->w, 0, id & ID_INDEX_MASK, &c.x, activation == JPH_Activation_Activate);
 	}
 }
 uint64_t JPH_Body_GetUserData(const JPH_Body *body) { return body ? JPH_BodyInterface_GetUserData(&body->sys->bi, body->id) : 0; }
@@ -928,7 +956,7 @@ void refresh_body_filter(JPH_PhysicsSystem *sys, const JPH_BodyFilter *f)
 		auto it = sys->bodies.find(id);
 		if (it == sys->bodies.end() || it->second.ray_flag == (int)pass) continue;
 		it->second.ray_flag = (int)pass;
-		gpx_body_set_ray_flags(sys->w, 0, id, pass ? GPX_BODY_BLOCKS_LASERS : 0u);
+		gpx_body_set_ray_flags(sys->w, 0, id & ID_INDEX_MASK, pass ? GPX_BODY_BLOCKS_LASERS : 0u);
 	}
 }
 
@@ -942,7 +970,7 @@ bool cast(JPH_PhysicsSystem *sys, const Transform *origin, float maxDistance, ui
 	if (h.body == GPX_INVALID_BODY) return false;
 	if (result)
 	{
-		result->bodyID = h.body;
+		result->bodyID = sys->to_public(h.body);
 		result->fraction = h.fraction;
 		result->subShapeID2 = h.face;
 	}

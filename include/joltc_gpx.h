@@ -31,7 +31,9 @@ extern "C" {
 
 /* ---- scalar types, constants, enums ------------------------------------------------------------------------------- */
 
-typedef uint32_t JPH_BodyID;       /* stored in a LIST_UINT32, engine/src/structs/Map.c:52 */
+typedef uint32_t JPH_BodyID;       /* stored in a LIST_UINT32, engine/src/structs/Map.c:52.  Low 23 bits: index (body slot, or
+                                    * 0x400000 + k for static mesh bodies); top byte: sequence number, bumped when a slot is
+                                    * reused, so calls with the id of a destroyed body find nothing (as in Jolt) */
 typedef uint32_t JPH_SubShapeID;
 typedef uint32_t JPH_ObjectLayer;  /* enum ObjectLayers, engine/include/engine/physics/Physics.h:36-42 */
 typedef uint8_t JPH_BroadPhaseLayer;

@@ -196,6 +196,49 @@ def test_shim_rejects_foreign_layer_tables_and_reports_inexact_shapes(tmp_path):
     assert L.JPH_GPX_ShapeIsExact(cyl) == 0
     L.JPH_Shape_Destroy.argtypes = [C.c_void_p]
     L.JPH_Shape_Destroy(cyl)
+
+    # body ids carry a sequence number: a reused slot gets a new id and the old one goes dead
+    class V3(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    class Xfm(C.Structure):
+        _fields_ = [("p", V3), ("q", C.c_float * 4)]
+
+    L.JPH_PhysicsSystem_GetBodyInterface.restype = C.c_void_p
+    L.JPH_PhysicsSystem_GetBodyInterface.argtypes = [C.c_void_p]
+    L.JPH_BoxShape_Create.restype = C.c_void_p
+    L.JPH_BoxShape_Create.argtypes = [C.POINTER(V3), C.c_float]
+    L.JPH_BodyCreationSettings_Create2_GAME.restype = C.c_void_p
+    L.JPH_BodyCreationSettings_Create2_GAME.argtypes = [C.c_void_p, C.POINTER(Xfm), C.c_int, C.c_uint32, C.c_void_p]
+    L.JPH_BodyCreationSettings_Destroy.argtypes = [C.c_void_p]
+    L.JPH_BodyInterface_CreateAndAddBody.restype = C.c_uint32
+    L.JPH_BodyInterface_CreateAndAddBody.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.JPH_BodyInterface_RemoveAndDestroyBody.argtypes = [C.c_void_p, C.c_uint32]
+    L.JPH_BodyInterface_GetPosition.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(V3)]
+    L.JPH_BodyInterface_GetUserData.restype = C.c_uint64
+    L.JPH_BodyInterface_GetUserData.argtypes = [C.c_void_p, C.c_uint32]
+    bi = L.JPH_PhysicsSystem_GetBodyInterface(sys_)
+    box = L.JPH_BoxShape_Create(C.byref(V3(0.2, 0.2, 0.2)), 0.05)
+
+    def make(x, tag):
+        st = L.JPH_BodyCreationSettings_Create2_GAME(box, C.byref(Xfm(V3(x, 5.0, 0.0), (C.c_float * 4)(0, 0, 0, 1))), 2, 1, tag)
+        b = L.JPH_BodyInterface_CreateAndAddBody(bi, st, 0)
+        L.JPH_BodyCreationSettings_Destroy(st)
+        return b
+
+    a = make(1.0, 0x1111)
+    assert a == 0 and L.JPH_BodyInterface_GetUserData(bi, a) == 0x1111
+    L.JPH_BodyInterface_RemoveAndDestroyBody(bi, a)
+    b = make(2.0, 0x2222)
+    assert b != a and (b & 0x7FFFFF) == (a & 0x7FFFFF) and (b >> 24) == 1      # same slot, next sequence number
+    out = V3(-1.0, -1.0, -1.0)
+    L.JPH_BodyInterface_GetPosition(bi, a, C.byref(out))                       # the stale id finds nothing
+    assert (out.x, out.y, out.z) == (-1.0, -1.0, -1.0) and L.JPH_BodyInterface_GetUserData(bi, a) == 0
+    L.JPH_BodyInterface_GetPosition(bi, b, C.byref(out))
+    assert (out.x, out.y, out.z) == (2.0, 5.0, 0.0) and L.JPH_BodyInterface_GetUserData(bi, b) == 0x2222
+    L.JPH_BodyInterface_RemoveAndDestroyBody(bi, a)                            # and cannot destroy the new tenant
+    assert L.JPH_BodyInterface_GetUserData(bi, b) == 0x2222
+    L.JPH_Shape_Destroy(box)
     L.JPH_PhysicsSystem_Destroy.argtypes = [C.c_void_p]
     L.JPH_PhysicsSystem_Destroy(sys_)
     L.JPH_Shutdown()
