@@ -184,6 +184,8 @@ def lib() -> C.CDLL:
         "gpx_body_create_all": (i32, [vp, C.POINTER(BodyDesc), u32, vp, vp, vp]),
         "gpx_body_destroy": (i32, [vp, u32, u32]),
         "gpx_body_set_ray_flags": (i32, [vp, u32, u32, u32]),
+        "gpx_body_wake": (i32, [vp, u32, u32]),
+        "gpx_read_sleeping": (i32, [vp, vp, u64]),
         "gpx_body_set_linear_velocity": (i32, [vp, u32, u32, C.POINTER(f32)]),
         "gpx_body_set_linear_and_angular_velocity": (i32, [vp, u32, u32, C.POINTER(f32), C.POINTER(f32)]),
         "gpx_body_set_position": (i32, [vp, u32, u32, C.POINTER(f32), i32]),
@@ -336,6 +338,15 @@ class World:
         _check(self.L.gpx_debug_wide_counters(self.h, c.ctypes.data), "gpx_debug_wide_counters")
         return dict(manifold_slots=int(c[0]), small_islands=int(c[1]), colours=int(c[2]), error=int(c[3]),
                     large_island_manifolds=int(c[5]))
+
+    def wake(self, body, world=0):
+        _check(self.L.gpx_body_wake(self.h, world, body), "gpx_body_wake")
+
+    def sleeping(self) -> np.ndarray:
+        """(worlds, max_bodies) bool: which bodies are asleep."""
+        out = np.zeros(self.worlds * self.max_bodies, np.uint8)
+        _check(self.L.gpx_read_sleeping(self.h, out.ctypes.data, out.size), "gpx_read_sleeping")
+        return out.reshape(self.worlds, self.max_bodies).astype(bool)
 
     def set_ray_flags(self, body, flags, world=0):
         _check(self.L.gpx_body_set_ray_flags(self.h, world, body, flags), "gpx_body_set_ray_flags")

@@ -125,6 +125,7 @@ static int flush_commands(gpx_world *w)
 				e.flags = c.flags;
 			}
 			if (c.mask & 32u) e.flags = (e.flags & ~(0xFFu << BF_RAYFLAG_SHIFT)) | (c.flags & (0xFFu << BF_RAYFLAG_SHIFT));
+			// (64 = wake carries no payload)
 			e.mask |= c.mask;
 		}
 		w->pending.swap(merged);
@@ -256,7 +257,8 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		 dalloc(&w->d_busy_flag, (size_t)cfg->worlds) == GPX_OK;
 	ok = ok && dalloc(&w->bs.pos, nb) == GPX_OK && dalloc(&w->bs.quat, nb) == GPX_OK && dalloc(&w->bs.lin, nb) == GPX_OK &&
 		 dalloc(&w->bs.ang, nb) == GPX_OK && dalloc(&w->bs.prop0, nb) == GPX_OK && dalloc(&w->bs.prop1, nb) == GPX_OK &&
-		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK;
+		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK && dalloc(&w->bs.sleep_c, 3 * nb) == GPX_OK &&
+		 dalloc(&w->bs.sleep_t, nb) == GPX_OK;
 	ok = ok && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
 	if (!wide)
 		ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
@@ -301,6 +303,7 @@ void gpx_world_destroy(gpx_world *w)
 	wide_destroy(w);
 	cudaFree(w->bs.pos); cudaFree(w->bs.quat); cudaFree(w->bs.lin); cudaFree(w->bs.ang);
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
+	cudaFree(w->bs.sleep_c); cudaFree(w->bs.sleep_t);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
 	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
@@ -589,6 +592,7 @@ uint32_t gpx_body_create(gpx_world *w, uint32_t world, const gpx_body_desc *desc
 		{
 			w->free_hint[world] = i + 1;
 			BodyCommand c = command_from_desc((uint32_t)(base + i), *desc);
+			if (desc->allow_sleeping && desc->motion_type == GPX_MOTION_DYNAMIC) w->sleep_enabled = true;
 			w->h_flags[base + i] = c.flags;
 			w->h_user_data[base + i] = desc->user_data;
 			front_pos(w)[base + i] = c.pos;
@@ -615,6 +619,7 @@ int gpx_body_create_all(gpx_world *w, const gpx_body_desc *descs, uint32_t count
 	for (uint32_t k = 0; k < count; k++)
 	{
 		BodyCommand proto = command_from_desc(0, descs[k]);
+		if (descs[k].allow_sleeping && descs[k].motion_type == GPX_MOTION_DYNAMIC) w->sleep_enabled = true;
 		for (uint32_t wi = 0; wi < w->W; wi++)
 		{
 			const size_t g = (size_t)wi * w->cap + ids[k];
@@ -690,21 +695,45 @@ static int queue_write(gpx_world *w, uint32_t world, uint32_t body, uint32_t mas
 	return GPX_OK;
 }
 
+// 64 = wake: a non-zero velocity activates a sleeping body (BodyInterface::SetLinearVelocity), and so does
+// JPH_Activation_Activate on SetPosition / SetRotation
+static inline uint32_t wake_if(bool on) { return on ? 64u : 0u; }
+static inline bool nonzero3(const float *v) { return v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f; }
+
 int gpx_body_set_linear_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3])
 {
-	return v ? queue_write(w, world, body, 4u, v, nullptr) : GPX_ERR_INVALID_ARG;
+	return v ? queue_write(w, world, body, 4u | wake_if(nonzero3(v)), v, nullptr) : GPX_ERR_INVALID_ARG;
 }
 int gpx_body_set_linear_and_angular_velocity(gpx_world *w, uint32_t world, uint32_t body, const float v[3], const float av[3])
 {
-	return (v && av) ? queue_write(w, world, body, 12u, v, av) : GPX_ERR_INVALID_ARG;
+	return (v && av) ? queue_write(w, world, body, 12u | wake_if(nonzero3(v) || nonzero3(av)), v, av) : GPX_ERR_INVALID_ARG;
 }
-int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int /*activate*/)
+int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int activate)
 {
-	return p ? queue_write(w, world, body, 1u, p, nullptr) : GPX_ERR_INVALID_ARG;
+	return p ? queue_write(w, world, body, 1u | wake_if(activate != 0), p, nullptr) : GPX_ERR_INVALID_ARG;
 }
-int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int /*activate*/)
+int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int activate)
 {
-	return q ? queue_write(w, world, body, 2u, q, nullptr) : GPX_ERR_INVALID_ARG;
+	return q ? queue_write(w, world, body, 2u | wake_if(activate != 0), q, nullptr) : GPX_ERR_INVALID_ARG;
+}
+int gpx_body_wake(gpx_world *w, uint32_t world, uint32_t body)
+{
+	return queue_write(w, world, body, 64u, nullptr, nullptr);
+}
+int gpx_read_sleeping(gpx_world *w, uint8_t *out, uint64_t capacity)
+{
+	if (!w || !out) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	const size_t nb = (size_t)w->W * w->cap;
+	if (capacity < nb) return GPX_ERR_CAPACITY;
+	int rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	std::vector<uint32_t> f(nb);
+	GPX_CUDA(cudaMemcpyAsync(f.data(), w->bs.flags, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	for (size_t g = 0; g < nb; g++) out[g] = (f[g] & BF_ALIVE) && (f[g] & BF_ASLEEP) ? 1 : 0;
+	return GPX_OK;
 }
 
 int gpx_body_set_ray_flags(gpx_world *w, uint32_t world, uint32_t body, uint32_t ray_flags)
@@ -810,6 +839,8 @@ int gpx_step(gpx_world *w, float dt, int collision_steps)
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	if ((rc = (w->wide ? launch_wide_tick(w, dt, collision_steps) : launch_tick(w, dt, collision_steps))) != GPX_OK) return rc;
+	// the sleep test runs once per tick, and only in worlds that hold a body allowed to sleep (wide worlds: not yet)
+	if (w->sleep_enabled && !w->wide && (rc = launch_sleep_test(w, dt)) != GPX_OK) return rc;
 	w->ticks++;
 	return (int)w->m_err[0];
 }

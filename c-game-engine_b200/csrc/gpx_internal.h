@@ -26,6 +26,8 @@ constexpr uint32_t BF_SENSOR = 1u << 8;
 constexpr uint32_t BF_DOF_SHIFT = 9;     // 6 bits
 constexpr uint32_t BF_ALLOW_SLEEP = 1u << 15;
 constexpr uint32_t BF_RAYFLAG_SHIFT = 16;  // 8 bits
+constexpr uint32_t BF_ASLEEP = 1u << 24;      // a dynamic body that is asleep: static for everything the tick does
+constexpr uint32_t BF_KIN_MOVING = 1u << 25;  // in shared memory only: a kinematic body with a non-zero velocity
 
 // Structure-of-arrays body store in HBM; index = world * cap + slot.  Every array is 16-byte vectorised.
 struct BodyStore
@@ -38,6 +40,8 @@ struct BodyStore
 	float4 *prop1;  // half extents xyz (sphere: radius in x), friction
 	float4 *prop2;  // linear damping, angular damping, gravity factor, restitution
 	uint32_t *flags;
+	float4 *sleep_c;  // 3 per body: sleep-test sphere (centre xyz, radius w)
+	float *sleep_t;   // time the test points stayed inside their spheres; < 0: spheres not set
 };
 
 // Contact cache carried between sub-steps and ticks (warm starting); index = world * cap_m + m
@@ -151,6 +155,7 @@ struct gpx_world
 	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)
 	unsigned long long *d_phase = nullptr;  // 16 counters, allocated by gpx_debug_phase_cycles(enable)
 	uint32_t ticks = 0;
+	bool sleep_enabled = false;  // some body was created with allow_sleeping: run the per-tick sleep test
 
 	// ray staging
 	void *d_rays = nullptr, *d_hits = nullptr;
@@ -176,6 +181,8 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 int launch_character(gpx_world *w, float dt);
 // gpx_tick.cu
 int launch_tick(gpx_world *w, float dt, int substeps);
+int launch_sleep_test(gpx_world *w, float dt);
+int launch_sleep_test(gpx_world *w, float dt);
 int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n);
 int launch_stats(gpx_world *w);
 // gpx_api.cu

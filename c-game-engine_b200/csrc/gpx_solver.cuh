@@ -60,7 +60,13 @@ struct ConPts  // 36 words
 };
 
 
-__device__ __forceinline__ bool is_dynamic(uint32_t f) { return ((f >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_DYNAMIC; }
+// "dynamic" for everything the tick does: a dynamic body that is awake.  A sleeping body is static until woken.
+__device__ __forceinline__ bool is_dynamic(uint32_t f)
+{
+	return (f & ((3u << BF_MOTION_SHIFT) | BF_ASLEEP)) == ((uint32_t)GPX_MOTION_DYNAMIC << BF_MOTION_SHIFT);
+}
+// bodies that find contacts and wake sleepers: awake dynamic ones and kinematic ones that move
+__device__ __forceinline__ bool is_active_body(uint32_t f) { return is_dynamic(f) || (f & BF_KIN_MOVING); }
 __device__ __forceinline__ uint32_t shape_of(uint32_t f) { return (f >> BF_SHAPE_SHIFT) & 7u; }
 __device__ __forceinline__ uint32_t layer_of(uint32_t f) { return (f >> BF_LAYER_SHIFT) & 3u; }
 __device__ __forceinline__ uint32_t dofs_of(uint32_t f) { return (f >> BF_DOF_SHIFT) & 63u; }

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	PhaseClock pc;
 	pc.start(a.phase_cycles, lane);
 	const uint32_t g0 = world * cap;
+	bool any_active = false, any_asleep = false;
 	// ---- load: HBM -> shared, lane = body, 16-byte vector loads
 	for (uint32_t i = lane; i < cap; i += TILE)
 	{
@@ -216,13 +217,28 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		b.ang_damp = p2.y;
 		b.grav = p2.z;
 		b.restitution = p2.w;
-		b.flags = a.bs.flags[g0 + i];
+		uint32_t f = a.bs.flags[g0 + i];
+		if ((f & BF_ALIVE) && ((f >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_KINEMATIC &&
+			(l.x != 0.0f || l.y != 0.0f || l.z != 0.0f || w.x != 0.0f || w.y != 0.0f || w.z != 0.0f))
+			f |= BF_KIN_MOVING;
+		b.flags = f;
+		if ((f & BF_ALIVE) && is_active_body(f)) any_active = true;
+		if ((f & BF_ALIVE) && (f & BF_ASLEEP)) any_asleep = true;
+	}
+	// A world in which everything sleeps (or nothing can move) has no tick to run: its state, contact cache included,
+	// stays as it is.  (With contact events on, the pass below still has to report the pairs as gone or persisting.)
+	if (!a.ev_out && !tile.any(any_active))
+	{
+		// sleepers keep their cached contacts for the moment they wake; a world with nothing dynamic has none
+		if (!tile.any(any_asleep) && lane == 0) a.mc.count[world] = 0;
+		return;
 	}
 	const uint32_t m0 = world * cap_m;
 	if (lane == 0)
 	{
 		hdr[1] = min(a.mc.count[world], cap_m);
 		hdr[3] = 0;
+		hdr[6] = hdr[7] = 0;  // sleepers touched by an active body in this sub-step (bit = body)
 	}
 	tile.sync();
 	pc.mark(PH_LOAD);
@@ -280,7 +296,10 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 					const SBody &B = bodies[j];
 					const uint32_t fb = B.flags;
 					if (!(fb & BF_ALIVE) || shape_of(fb) == GPX_SHAPE_EMPTY) continue;
-					if (!is_dynamic(fa) && !is_dynamic(fb)) continue;
+					// at least one awake dynamic body — or a moving kinematic body reaching a sleeper, which only wakes it
+					if (!is_dynamic(fa) && !is_dynamic(fb) &&
+						!(((fa & BF_KIN_MOVING) && (fb & BF_ASLEEP)) || ((fb & BF_KIN_MOVING) && (fa & BF_ASLEEP))))
+						continue;
 					if (!layers_collide(la, layer_of(fb))) continue;
 					if (!aabb_overlap(A.lo, A.hi, B.lo, B.hi, SPECULATIVE_DISTANCE)) continue;
 					mask |= 1ull << j;
@@ -353,6 +372,14 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			m.b = ib;
 			m.np = 0;
 			pair_contact(A, B, scratch, m);
+			const uint32_t fa = A.flags, fb = B.flags;
+			if (((fa | fb) & BF_ASLEEP) && m.np > 0 && !((fa | fb) & BF_SENSOR))
+			{
+				// a contact with an active body wakes a sleeper; it takes part in the solve from the next sub-step on
+				if ((fa & BF_ASLEEP) && is_active_body(fb)) atomicOr(&hdr[6 + (ia >> 5)], 1u << (ia & 31u));
+				if ((fb & BF_ASLEEP) && is_active_body(fa)) atomicOr(&hdr[6 + (ib >> 5)], 1u << (ib & 31u));
+				if (!is_dynamic(fa) && !is_dynamic(fb)) m.np = 0;  // kinematic against sleeper: nothing to solve
+			}
 		}
 		tile.sync();
 		pc.mark(PH_PAIRS);
@@ -514,7 +541,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		for (uint32_t i = lane; i < cap; i += TILE)
 		{
 			SBody &b = bodies[i];
-			if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC) continue;
+			if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC || (b.flags & BF_ASLEEP)) continue;
 			b.x = b.x + (b.v * h);
 			b.q = qstep(b.q, b.w * h);
 		}
@@ -545,6 +572,19 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			}
 		}
 		if (lane == 0) hdr[1] = nact;
+		if (hdr[6] | hdr[7])
+		{
+			// wake: awake from the next sub-step on; the sleep test starts over
+			for (uint32_t i = lane; i < cap; i += TILE)
+				if ((hdr[6 + (i >> 5)] >> (i & 31u)) & 1u)
+				{
+					bodies[i].flags &= ~BF_ASLEEP;
+					a.bs.flags[g0 + i] = bodies[i].flags & ~BF_KIN_MOVING;
+					a.bs.sleep_t[g0 + i] = -1.0f;
+				}
+			tile.sync();
+			if (lane == 0) hdr[6] = hdr[7] = 0;
+		}
 		__threadfence_block();
 		tile.sync();
 		pc.mark(PH_CACHE);
@@ -663,6 +703,140 @@ __global__ void k_apply_commands(BodyStore bs, const BodyCommand *__restrict__ c
 	}
 	if ((c.mask & 48u) == 32u)
 		bs.flags[c.index] = (bs.flags[c.index] & ~(0xFFu << BF_RAYFLAG_SHIFT)) | (c.flags & (0xFFu << BF_RAYFLAG_SHIFT));
+	if (c.mask & (16u | 64u))
+	{
+		// a new body, or one the host activated (a non-zero velocity, SetPosition(.., Activate)): awake, test restarts
+		if (!(c.mask & 16u)) bs.flags[c.index] &= ~BF_ASLEEP;
+		bs.sleep_t[c.index] = -1.0f;
+	}
+}
+
+
+// ---- sleeping: Jolt's sleep test, once per tick (0.03 m/s for 0.5 s).  Three test points per body
+// (centre of mass, the extents along the two larger local axes) each live in a sphere that grows to hold them; a
+// radius above 15 mm restarts the test, 0.5 s without a restart makes the body a candidate, and an island — awake
+// dynamic bodies joined by the contacts of the last sub-step — goes to sleep when all its bodies are candidates.
+// One warp per world; union-find over at most 64 bodies in shared memory.
+constexpr float SLEEP_POINT_VELOCITY = 0.03f, SLEEP_TIME = 0.5f;
+constexpr int SLEEP_WARPS = 4;
+
+__global__ void __launch_bounds__(SLEEP_WARPS * 32) k_sleep(BodyStore bs, ManifoldCache mc, uint32_t worlds, uint32_t cap, uint32_t cap_m,
+															float dt)
+{
+	__shared__ unsigned char parent_s[SLEEP_WARPS][64], can_s[SLEEP_WARPS][64];
+	const uint32_t lane = threadIdx.x & 31u, wi = threadIdx.x >> 5;
+	const uint32_t world = blockIdx.x * SLEEP_WARPS + wi;
+	if (world >= worlds) return;
+	unsigned char *parent = parent_s[wi], *can = can_s[wi];
+	const uint32_t g0 = world * cap, m0 = world * cap_m;
+	bool any = false;
+	for (uint32_t i = lane; i < cap; i += 32u)
+	{
+		parent[i] = (unsigned char)i;
+		can[i] = 1;
+		const uint32_t f = bs.flags[g0 + i];
+		if ((f & BF_ALIVE) && is_dynamic(f)) any = true;
+	}
+	if (!__any_sync(0xFFFFFFFFu, any)) return;
+	__syncwarp();
+	// islands: the smaller index becomes the root.  The cache holds the solved manifolds of the last sub-step.
+	const uint32_t nman = min(mc.count[world], cap_m);
+	for (uint32_t k0 = 0; k0 < nman; k0 += 32u)
+	{
+		const uint32_t k = k0 + lane;
+		uint4 key = make_uint4(0u, STATIC_BODY_BASE, 0u, 0u);
+		if (k < nman) key = __ldcg(&mc.key[m0 + k]);
+		bool link = key.y < STATIC_BODY_BASE && is_dynamic(bs.flags[g0 + key.x]) && is_dynamic(bs.flags[g0 + key.y]);
+		// unions one at a time, in list order (a handful per world)
+		uint32_t todo = __ballot_sync(0xFFFFFFFFu, link);
+		while (todo)
+		{
+			const int src = __ffs((int)todo) - 1;
+			todo &= todo - 1u;
+			const uint32_t xa = __shfl_sync(0xFFFFFFFFu, key.x, src), xb = __shfl_sync(0xFFFFFFFFu, key.y, src);
+			if (lane == 0)
+			{
+				uint32_t ra = xa, rb = xb;
+				while (parent[ra] != ra) ra = parent[ra];
+				while (parent[rb] != rb) rb = parent[rb];
+				if (ra < rb) parent[rb] = (unsigned char)ra;
+				else if (rb < ra) parent[ra] = (unsigned char)rb;
+			}
+			__syncwarp();
+		}
+	}
+	__syncwarp();
+	for (uint32_t i = lane; i < cap; i += 32u)
+	{
+		const uint32_t f = bs.flags[g0 + i];
+		if (!(f & BF_ALIVE) || !is_dynamic(f)) continue;
+		bool candidate = false;
+		if ((f & BF_ALLOW_SLEEP) && !(f & BF_SENSOR))
+		{
+			const v3 x = V(bs.pos[g0 + i]);
+			const q4 q = Q(bs.quat[g0 + i]);
+			const float4 p1 = bs.prop1[g0 + i];
+			const v3 e = shape_of(f) == GPX_SHAPE_SPHERE ? V(p1.x, p1.x, p1.x) : V(p1);
+			const int lowest = e.x < e.y ? (e.z < e.x ? 2 : 0) : (e.z < e.y ? 2 : 1);
+			const v3 ax = qrot(q, V(1.0f, 0.0f, 0.0f)), ay = qrot(q, V(0.0f, 1.0f, 0.0f)), az = qrot(q, V(0.0f, 0.0f, 1.0f));
+			v3 pts[3];
+			pts[0] = x;
+			pts[1] = lowest == 0 ? madd(x, ay, e.y) : madd(x, ax, e.x);
+			pts[2] = lowest == 2 ? madd(x, ay, e.y) : madd(x, az, e.z);
+			float t = bs.sleep_t[g0 + i];
+			bool restart = t < 0.0f;
+			float4 sp[3];
+#pragma unroll
+			for (int k = 0; k < 3; k++)
+			{
+				sp[k] = bs.sleep_c[3ull * (g0 + i) + k];
+				if (restart) continue;
+				// grow the sphere just enough to hold the point
+				const v3 d = pts[k] - V(sp[k]);
+				const float d2 = len2(d), r = sp[k].w;
+				if (d2 > (r * r))
+				{
+					const float dist = sqrtf(d2), nr = 0.5f * (r + dist);
+					sp[k] = F4(madd(V(sp[k]), d, (nr - r) / dist), nr);
+				}
+				if (sp[k].w > (SLEEP_POINT_VELOCITY * SLEEP_TIME)) restart = true;
+			}
+			if (restart)
+			{
+#pragma unroll
+				for (int k = 0; k < 3; k++) sp[k] = F4(pts[k], 0.0f);
+				t = 0.0f;
+			}
+			else
+			{
+				t += dt;
+				candidate = t >= SLEEP_TIME;
+			}
+#pragma unroll
+			for (int k = 0; k < 3; k++) bs.sleep_c[3ull * (g0 + i) + k] = sp[k];
+			bs.sleep_t[g0 + i] = t;
+		}
+		else
+			bs.sleep_t[g0 + i] = -1.0f;
+		if (!candidate)
+		{
+			uint32_t r = i;
+			while (parent[r] != r) r = parent[r];
+			can[r] = 0;
+		}
+	}
+	__syncwarp();
+	for (uint32_t i = lane; i < cap; i += 32u)
+	{
+		const uint32_t f = bs.flags[g0 + i];
+		if (!(f & BF_ALIVE) || !is_dynamic(f)) continue;
+		uint32_t r = i;
+		while (parent[r] != r) r = parent[r];
+		if (!can[r]) continue;
+		bs.flags[g0 + i] = f | BF_ASLEEP;
+		bs.lin[g0 + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		bs.ang[g0 + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
 }
 
 // per-world summary for the end-of-run gather: one warp per world
@@ -813,6 +987,14 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	rc = tile == 8u ? launch_tick_t<8>(w, a, w->stream, w->W) : launch_tick_t<16>(w, a, w->stream, w->W);
 	GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
 	return rc;
+}
+
+int launch_sleep_test(gpx_world *w, float dt)
+{
+	k_sleep<<<(w->W + SLEEP_WARPS - 1) / SLEEP_WARPS, SLEEP_WARPS * 32, 0, w->stream>>>(w->bs, w->mc, w->W, w->cap, w->cap_m, dt);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
 }
 
 int launch_apply_commands(gpx_world *w, const BodyCommand *d_cmd, uint32_t n)

@@ -112,7 +112,7 @@ typedef struct gpx_body_desc
 	float gravity_factor;    /* Jolt default 1 */
 	uint32_t is_sensor;      /* JPH_BodyCreationSettings_SetIsSensor (Trigger.c:44) */
 	uint32_t allowed_dofs;   /* gpx_allowed_dofs; 0 = all */
-	uint32_t allow_sleeping; /* Jolt default 1 */
+	uint32_t allow_sleeping; /* Jolt default 1; 0 keeps the body awake for ever */
 	uint32_t ray_flags;      /* GPX_BODY_* */
 	uint64_t user_data;      /* Actor* */
 } gpx_body_desc;
@@ -219,6 +219,14 @@ int gpx_body_set_linear_and_angular_velocity(gpx_world *w, uint32_t world, uint3
 int gpx_body_set_position(gpx_world *w, uint32_t world, uint32_t body, const float p[3], int activate);
 int gpx_body_set_rotation(gpx_world *w, uint32_t world, uint32_t body, const float q[4], int activate);
 
+/* JPH_BodyInterface_ActivateBody: wakes a sleeping body (also done by a non-zero velocity and by activate != 0 above). */
+int gpx_body_wake(gpx_world *w, uint32_t world, uint32_t body);
+/* Sleeping (the sleep test of JPH_PhysicsSystem_Update): bodies created with allow_sleeping whose three
+ * test points stay within 15 mm (0.03 m/s x 0.5 s) for 0.5 s become candidates; an island of candidates goes to sleep
+ * (velocities zeroed, static for the tick) until an active body touches it or the host wakes it.  A world in which
+ * nothing is active costs no tick.  Evaluated once per tick; ensemble worlds only (<= 64 bodies per world).
+ * `out` receives worlds * max_bodies bytes: 1 = asleep. */
+int gpx_read_sleeping(gpx_world *w, uint8_t *out, uint64_t capacity);
 /* Re-evaluates the laser BodyFilter for one body (Laser.c:74-85 reads actor->flags, which may change after create). */
 int gpx_body_set_ray_flags(gpx_world *w, uint32_t world, uint32_t body, uint32_t ray_flags);
 

@@ -51,7 +51,22 @@ typedef struct
 	/* per sub-step solver view */
 	float im;   /* inverse mass, 0 unless dynamic */
 	float M[6]; /* world inverse inertia xx xy xz yy yz zz */
+	/* sleeping (see the sleeping section): asleep bodies behave as static until something active touches them */
+	int asleep, wake_mark;
+	float sleep_t;  /* time the test points have stayed inside their spheres; < 0: spheres not set yet */
+	v3 sleep_c[3];
+	float sleep_r[3];
 } body_t;
+
+/* "dynamic" for everything the tick does: a dynamic body that is awake */
+static inline int is_dyn(const body_t *b) { return b->motion == ORC_MOTION_DYNAMIC && !b->asleep; }
+/* bodies that find contacts and wake sleepers: awake dynamic ones and kinematic ones that move */
+static inline int is_active(const body_t *b)
+{
+	if (is_dyn(b)) return 1;
+	return b->motion == ORC_MOTION_KINEMATIC &&
+		   (b->v.x != 0.0f || b->v.y != 0.0f || b->v.z != 0.0f || b->w.x != 0.0f || b->w.y != 0.0f || b->w.z != 0.0f);
+}
 
 typedef struct
 {
@@ -245,6 +260,7 @@ uint32_t orc_body_create(orc_world *w, const orc_body_desc *d)
 	b->sensor = d->is_sensor;
 	b->dofs = d->allowed_dofs ? d->allowed_dofs : 63u;
 	b->allow_sleep = d->allow_sleeping;
+	b->sleep_t = -1.0f;
 	b->ray_flags = d->ray_flags;
 	b->user_data = d->user_data;
 	if (b->motion == ORC_MOTION_DYNAMIC && b->shape != ORC_SHAPE_EMPTY)
@@ -279,11 +295,29 @@ void orc_body_destroy(orc_world *w, uint32_t id)
 	if (id < w->max_bodies) w->bodies[id].alive = 0;
 }
 
+static void wake_body(body_t *b)
+{
+	b->asleep = 0;
+	b->wake_mark = 0;
+	b->sleep_t = -1.0f;
+}
+
+/* JPH_BodyInterface_ActivateBody, and what SetPosition(.., JPH_Activation_Activate) implies */
+void orc_body_wake(orc_world *w, uint32_t id)
+{
+	if (id < w->max_bodies) wake_body(&w->bodies[id]);
+}
+
+uint32_t orc_body_asleep(const orc_world *w, uint32_t id) { return id < w->max_bodies && w->bodies[id].asleep; }
+
 void orc_body_set_velocity(orc_world *w, uint32_t id, const float v[3], const float av[3])
 {
 	if (id >= w->max_bodies) return;
 	if (v) w->bodies[id].v = V(v[0], v[1], v[2]);
 	if (av) w->bodies[id].w = V(av[0], av[1], av[2]);
+	/* a non-zero velocity activates the body (BodyInterface::SetLinearVelocity) */
+	if ((v && (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f)) || (av && (av[0] != 0.0f || av[1] != 0.0f || av[2] != 0.0f)))
+		wake_body(&w->bodies[id]);
 }
 
 /* JPH_BodyInterface_SetPosition (Door.c:82-96) and the re-evaluated laser body filter (Laser.c:74-85) */
@@ -1027,7 +1061,7 @@ static void find_contacts(orc_world *w, int *err)
 		v3 alo, ahi;
 		body_aabb(A, &alo, &ahi);
 		/* (a) against the static triangle soup: dynamic bodies of layers that collide with STATIC */
-		if (A->motion == ORC_MOTION_DYNAMIC && !A->sensor && (A->layer == 1 || A->layer == 2))
+		if (is_dyn(A) && !A->sensor && (A->layer == 1 || A->layer == 2))
 		{
 			/* per static body: up to MAX_SLOTS manifolds grouped by normal */
 			uint32_t cur_body = ORC_INVALID;
@@ -1094,7 +1128,9 @@ static void find_contacts(orc_world *w, int *err)
 		{
 			body_t *B = &w->bodies[j];
 			if (!B->alive || B->shape == ORC_SHAPE_EMPTY) continue;
-			if (A->motion != ORC_MOTION_DYNAMIC && B->motion != ORC_MOTION_DYNAMIC) continue;
+			/* at least one awake dynamic body — or a moving kinematic body reaching a sleeper, which only wakes it */
+			const int solved = is_dyn(A) || is_dyn(B);
+			if (!solved && !((is_active(A) && B->asleep) || (is_active(B) && A->asleep))) continue;
 			if (!layers_collide(A, B)) continue;
 			v3 blo, bhi;
 			body_aabb(B, &blo, &bhi);
@@ -1126,6 +1162,13 @@ static void find_contacts(orc_world *w, int *err)
 				continue;
 			}
 			prune_points(A->x, h.n, &h.np, h.p1, h.p2);
+			/* a contact with an active body wakes a sleeper; it takes part in the solve from the next sub-step on */
+			if (h.np > 0)
+			{
+				if (A->asleep && is_active(B)) A->wake_mark = 1;
+				if (B->asleep && is_active(A)) B->wake_mark = 1;
+			}
+			if (!solved) continue;
 			manifold_t *m = push_manifold(w, err);
 			if (!m) return;
 			m->a = i;
@@ -1177,8 +1220,8 @@ static int colour_manifolds(orc_world *w)
 	{
 		manifold_t *m = &w->man[i];
 		uint64_t u = 0;
-		int a_dyn = w->bodies[m->a].motion == ORC_MOTION_DYNAMIC;
-		int b_dyn = m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC;
+		int a_dyn = is_dyn(&w->bodies[m->a]);
+		int b_dyn = m->b < ORC_STATIC_BODY_BASE && is_dyn(&w->bodies[m->b]);
 		if (a_dyn) u |= used[m->a];
 		if (b_dyn) u |= used[m->b];
 		int c = 0;
@@ -1229,8 +1272,8 @@ static int colour_manifolds_jp(orc_world *w)
 		manifold_t *m = &w->man[i];
 		m->prio = man_prio(m->a, m->b, m->ord);
 		m->colour = -1;
-		if (w->bodies[m->a].motion == ORC_MOTION_DYNAMIC) cnt[m->a + 1]++;
-		if (m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC) cnt[m->b + 1]++;
+		if (is_dyn(&w->bodies[m->a])) cnt[m->a + 1]++;
+		if (m->b < ORC_STATIC_BODY_BASE && is_dyn(&w->bodies[m->b])) cnt[m->b + 1]++;
 	}
 	for (uint32_t i = 0; i < nb; i++) cnt[i + 1] += cnt[i];
 	uint32_t *adj = (uint32_t *)malloc((cnt[nb] + 1) * sizeof(uint32_t));
@@ -1239,8 +1282,8 @@ static int colour_manifolds_jp(orc_world *w)
 	for (uint32_t i = 0; i < n; i++)
 	{
 		manifold_t *m = &w->man[i];
-		if (w->bodies[m->a].motion == ORC_MOTION_DYNAMIC) adj[cur[m->a]++] = i;
-		if (m->b < ORC_STATIC_BODY_BASE && w->bodies[m->b].motion == ORC_MOTION_DYNAMIC) adj[cur[m->b]++] = i;
+		if (is_dyn(&w->bodies[m->a])) adj[cur[m->a]++] = i;
+		if (m->b < ORC_STATIC_BODY_BASE && is_dyn(&w->bodies[m->b])) adj[cur[m->b]++] = i;
 	}
 	int *pending = (int *)malloc((n + 1) * sizeof(int));
 	uint32_t left = n;
@@ -1258,7 +1301,7 @@ static int colour_manifolds_jp(orc_world *w)
 			for (int e = 0; e < 2 && top; e++)
 			{
 				uint32_t body = ends[e];
-				if (body >= ORC_STATIC_BODY_BASE || w->bodies[body].motion != ORC_MOTION_DYNAMIC) continue;
+				if (body >= ORC_STATIC_BODY_BASE || !is_dyn(&w->bodies[body])) continue;
 				for (uint32_t k = cnt[body]; k < cnt[body + 1]; k++)
 				{
 					uint32_t other = adj[k];
@@ -1306,7 +1349,7 @@ static int colour_manifolds_jp(orc_world *w)
  * Refreshed once per sub-step (after forces) and at the start of each manifold's position pass. */
 static void body_world_inertia(body_t *b)
 {
-	if (b->motion != ORC_MOTION_DYNAMIC)
+	if (!is_dyn(b))
 	{
 		memset(b->M, 0, sizeof(b->M));
 		b->im = 0.0f;
@@ -1365,12 +1408,12 @@ static v3 rel_vel(const body_t *A, const body_t *B, v3 r1, v3 r2)
 /* impulse P pushes b along +P and a along -P */
 static void apply_impulse(body_t *A, body_t *B, v3 r1, v3 r2, v3 P)
 {
-	if (A->motion == ORC_MOTION_DYNAMIC)
+	if (is_dyn(A))
 	{
 		A->v = vsub(A->v, mask_lin(A->dofs, vscale(P, A->im)));
 		A->w = vsub(A->w, sym_mul(A->M, vcross(r1, P)));
 	}
-	if (B && B->motion == ORC_MOTION_DYNAMIC)
+	if (B && is_dyn(B))
 	{
 		B->v = vadd(B->v, mask_lin(B->dofs, vscale(P, B->im)));
 		B->w = vadd(B->w, sym_mul(B->M, vcross(r2, P)));
@@ -1474,12 +1517,12 @@ static void solve_position(orc_world *w, manifold_t *m)
 		float c = fmaxf(sep, -MAX_PENETRATION_DISTANCE);
 		float lambda = (-e * BAUMGARTE) * c;
 		v3 P = vscale(m->n, lambda);
-		if (A->motion == ORC_MOTION_DYNAMIC)
+		if (is_dyn(A))
 		{
 			A->x = vsub(A->x, mask_lin(A->dofs, vscale(P, A->im)));
 			A->q = qstep(A->q, vneg(sym_mul(A->M, vcross(r1, P))));
 		}
-		if (B && B->motion == ORC_MOTION_DYNAMIC)
+		if (B && is_dyn(B))
 		{
 			B->x = vadd(B->x, mask_lin(B->dofs, vscale(P, B->im)));
 			B->q = qstep(B->q, sym_mul(B->M, vcross(r2, P)));
@@ -1543,6 +1586,126 @@ static v3 clamp_len(v3 v, float maxl)
 	return v;
 }
 
+
+/* ------------------------------------------------------------------------------------------ sleeping
+ * Jolt's sleep test [upstream, restated from its documented behaviour; SURVEY §8 row a2: "0.03 m/s for 0.5 s"]: three
+ * test points per body (centre of mass and the box extents along its two larger local axes) are each kept inside a
+ * growing sphere; a sphere radius above 0.03 m/s * 0.5 s = 15 mm restarts the test, 0.5 s without a restart makes the
+ * body a sleep candidate, and an island (bodies connected by contacts) goes to sleep when all its bodies are candidates:
+ * velocities are zeroed and the bodies behave as static until an active body touches them or the host wakes them.
+ * Evaluated once per tick (Jolt: once per collision step), on the contacts of the tick's last sub-step.  Sensors and
+ * bodies created with allow_sleeping = 0 never sleep.  Wide worlds (mode 1) do not deactivate yet. */
+#define SLEEP_POINT_VELOCITY 0.03f
+#define SLEEP_TIME 0.5f
+
+static void sleep_points(const body_t *b, v3 *pts)
+{
+	const v3 e = b->shape == ORC_SHAPE_SPHERE ? V(b->he.x, b->he.x, b->he.x) : b->he;
+	const int lowest = e.x < e.y ? (e.z < e.x ? 2 : 0) : (e.z < e.y ? 2 : 1);
+	const v3 ax = qrot(b->q, V(1.0f, 0.0f, 0.0f)), ay = qrot(b->q, V(0.0f, 1.0f, 0.0f)), az = qrot(b->q, V(0.0f, 0.0f, 1.0f));
+	pts[0] = b->x;
+	if (lowest == 0)
+	{
+		pts[1] = vmadd(b->x, ay, e.y);
+		pts[2] = vmadd(b->x, az, e.z);
+	}
+	else if (lowest == 1)
+	{
+		pts[1] = vmadd(b->x, ax, e.x);
+		pts[2] = vmadd(b->x, az, e.z);
+	}
+	else
+	{
+		pts[1] = vmadd(b->x, ax, e.x);
+		pts[2] = vmadd(b->x, ay, e.y);
+	}
+}
+
+static int sleep_candidate(body_t *b, float dt)
+{
+	if (!b->allow_sleep || b->sensor)
+	{
+		b->sleep_t = -1.0f;
+		return 0;
+	}
+	v3 pts[3];
+	sleep_points(b, pts);
+	int restart = b->sleep_t < 0.0f;
+	for (int i = 0; i < 3 && !restart; i++)
+	{
+		/* grow the sphere just enough to hold the point */
+		const v3 d = vsub(pts[i], b->sleep_c[i]);
+		const float d2 = vlen2(d), r = b->sleep_r[i];
+		if (d2 > (r * r))
+		{
+			const float dist = sqrtf(d2), nr = 0.5f * (r + dist);
+			b->sleep_c[i] = vmadd(b->sleep_c[i], d, (nr - r) / dist);
+			b->sleep_r[i] = nr;
+		}
+		if (b->sleep_r[i] > (SLEEP_POINT_VELOCITY * SLEEP_TIME)) restart = 1;
+	}
+	if (restart)
+	{
+		for (int i = 0; i < 3; i++)
+		{
+			b->sleep_c[i] = pts[i];
+			b->sleep_r[i] = 0.0f;
+		}
+		b->sleep_t = 0.0f;
+		return 0;
+	}
+	b->sleep_t += dt;
+	return b->sleep_t >= SLEEP_TIME;
+}
+
+static uint32_t uf_find(uint32_t *parent, uint32_t x)
+{
+	while (parent[x] != x)
+	{
+		parent[x] = parent[parent[x]];
+		x = parent[x];
+	}
+	return x;
+}
+
+static void sleep_pass(orc_world *w, float dt)
+{
+	const uint32_t nb = w->max_bodies;
+	uint32_t *parent = (uint32_t *)malloc(sizeof(uint32_t) * nb);
+	unsigned char *can = (unsigned char *)malloc(nb);
+	for (uint32_t i = 0; i < nb; i++)
+	{
+		parent[i] = i;
+		can[i] = 1;
+	}
+	/* islands: awake dynamic bodies joined by the contacts of the last sub-step; the smaller index becomes the root */
+	for (uint32_t k = 0; k < w->nprev; k++)
+	{
+		const manifold_t *m = &w->prev[k];
+		if (m->b >= ORC_STATIC_BODY_BASE || !is_dyn(&w->bodies[m->a]) || !is_dyn(&w->bodies[m->b])) continue;
+		uint32_t ra = uf_find(parent, m->a), rb = uf_find(parent, m->b);
+		if (ra == rb) continue;
+		if (ra < rb) parent[rb] = ra;
+		else parent[ra] = rb;
+	}
+	for (uint32_t i = 0; i < nb; i++)
+	{
+		body_t *b = &w->bodies[i];
+		if (!b->alive || !is_dyn(b)) continue;
+		if (!sleep_candidate(b, dt)) can[uf_find(parent, i)] = 0;
+	}
+	for (uint32_t i = 0; i < nb; i++)
+	{
+		body_t *b = &w->bodies[i];
+		if (!b->alive || !is_dyn(b) || !can[uf_find(parent, i)]) continue;
+		b->asleep = 1;
+		b->v = V(0.0f, 0.0f, 0.0f);
+		b->w = V(0.0f, 0.0f, 0.0f);
+	}
+	free(parent);
+	free(can);
+}
+
 int orc_step(orc_world *w, float dt, int collision_steps)
 {
 	int err = 0;
@@ -1554,7 +1717,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		{
 			body_t *b = &w->bodies[i];
 			if (!b->alive) continue;
-			if (b->motion == ORC_MOTION_DYNAMIC)
+			if (is_dyn(b))
 			{
 				b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
 				b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
@@ -1579,7 +1742,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t i = 0; i < w->max_bodies; i++)
 		{
 			body_t *b = &w->bodies[i];
-			if (!b->alive || b->motion == ORC_MOTION_STATIC) continue;
+			if (!b->alive || b->motion == ORC_MOTION_STATIC || b->asleep) continue;
 			b->x = vadd(b->x, vscale(b->v, h));
 			b->q = qstep(b->q, vscale(b->w, h));
 		}
@@ -1589,7 +1752,11 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		w->prev = w->man;
 		w->man = t;
 		w->nprev = w->nman;
+		/* sleepers touched by something active in this sub-step are awake from the next one on */
+		for (uint32_t i = 0; i < w->max_bodies; i++)
+			if (w->bodies[i].alive && w->bodies[i].wake_mark) wake_body(&w->bodies[i]);
 	}
+	if (w->mode == 0) sleep_pass(w, dt);
 	make_events(w);
 	return err;
 }

@@ -78,6 +78,8 @@ uint32_t orc_body_create(orc_world *w, const orc_body_desc *d);
 void orc_body_destroy(orc_world *w, uint32_t id);
 void orc_body_set_velocity(orc_world *w, uint32_t id, const float v[3], const float av[3]);
 void orc_body_set_position(orc_world *w, uint32_t id, const float p[3]);
+void orc_body_wake(orc_world *w, uint32_t id);
+uint32_t orc_body_asleep(const orc_world *w, uint32_t id);
 void orc_body_set_ray_flags(orc_world *w, uint32_t id, uint32_t ray_flags);
 /* one tick = collision_steps sub-steps of dt/collision_steps; returns 0 or an error code (4 = contact constraints full) */
 int orc_step(orc_world *w, float dt, int collision_steps);

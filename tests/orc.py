@@ -110,6 +110,9 @@ def lib():
     L.orc_body_set_velocity.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.orc_body_set_position.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
     L.orc_body_set_ray_flags.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.orc_body_wake.argtypes = [C.c_void_p, C.c_uint32]
+    L.orc_body_asleep.argtypes = [C.c_void_p, C.c_uint32]
+    L.orc_body_asleep.restype = C.c_uint32
     L.orc_step.restype = C.c_int
     L.orc_step.argtypes = [C.c_void_p, C.c_float, C.c_int]
     L.orc_body_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -179,6 +182,12 @@ class World:
 
     def set_position(self, bid: int, p):
         self.L.orc_body_set_position(self.h, bid, (C.c_float * 3)(*p))
+
+    def wake(self, bid: int):
+        self.L.orc_body_wake(self.h, bid)
+
+    def asleep(self, n: int) -> np.ndarray:
+        return np.array([self.L.orc_body_asleep(self.h, i) for i in range(n)], bool)
 
     def set_ray_flags(self, bid: int, flags: int):
         self.L.orc_body_set_ray_flags(self.h, bid, flags)
