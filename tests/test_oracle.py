@@ -270,3 +270,63 @@ def test_character_is_blocked_by_boxes_and_reports_contacts(orc, scenes):
     p, _, _, _ = o.character_get()
     assert p[0] < -1.0
     assert any(a == 0x3FFFFF and b >= orc.STATIC_BASE for a, b in seen[2])   # standing on the floor mesh throughout
+
+
+# ---- sleeping (the sleep test)
+
+def test_sleep_test_known_answers(orc):
+    """A body drifting in a straight line keeps its test points inside spheres of radius (distance travelled) / 2, so
+    it becomes a sleep candidate iff it covers less than 2 x 15 mm in 0.5 s: 0.05 m/s sleeps, 0.07 m/s never does."""
+    def run(speed, ticks=90, **kw):
+        o = orc.World(4)
+        o.create(orc.body_desc(position=(0, 0, 0), linear_velocity=(speed, 0, 0), gravity_factor=0.0, linear_damping=0.0,
+                               angular_damping=0.0, allow_sleeping=1, **kw))
+        first = None
+        for t in range(1, ticks + 1):
+            assert o.step() == 0
+            if first is None and o.asleep(1)[0]:
+                first = t
+        return first, o
+    first, o = run(0.05)
+    assert first == 31                      # tick 1 sets the spheres, then 30 ticks of 1/60 s reach 0.5 s
+    x, v = o.state(1)
+    assert np.all(v == 0.0) and abs(x[0, 0] - 0.05 * 31 / 60) < 1e-6          # stopped where it fell asleep
+    assert run(0.07)[0] is None
+    assert run(0.05, is_sensor=1)[0] is None                                   # sensors never sleep
+    o2 = orc.World(4)
+    o2.create(orc.body_desc(position=(0, 0, 0), gravity_factor=0.0, allow_sleeping=0))
+    for _ in range(90):
+        o2.step()
+    assert not o2.asleep(1)[0]                                                 # allow_sleeping = 0 keeps it awake
+    # a spinning body moves its off-centre test points: 1 rad/s on a 0.2 m box sweeps them well past 15 mm
+    o3 = orc.World(4)
+    o3.create(orc.body_desc(position=(0, 0, 0), angular_velocity=(0, 0, 1.0), gravity_factor=0.0, angular_damping=0.0,
+                            allow_sleeping=1))
+    for _ in range(90):
+        o3.step()
+    assert not o3.asleep(1)[0]
+
+
+def test_island_sleeps_together_and_wakes_in_a_cascade(orc, scenes):
+    o = orc.World(16)
+    for pos, tris in scenes.load_static("stacked"):
+        o.add_mesh(pos, tris)
+    for p in scenes.stack_positions(8):
+        o.create(orc.body_desc(position=tuple(p), allow_sleeping=1))
+    states = []
+    for _ in range(60):
+        assert o.step() == 0
+        states.append(o.asleep(8).sum())
+    assert set(states) == {0, 8}                                               # the column is one island: all or nothing
+    x0 = o.state(8)[0].copy()
+    for _ in range(30):
+        o.step()
+    assert np.array_equal(o.state(8)[0], x0)
+    o.create(orc.body_desc(position=(0.0, 3.0, -1.5), allow_sleeping=1))
+    counts = []
+    for _ in range(240):
+        o.step()
+        counts.append(int(o.asleep(9).sum()))
+    woke = [c for c in counts if c < 8]
+    assert woke[0] == 7 and min(counts) == 0 and counts[-1] == 9               # top box first, then everything, then rest
+    assert sorted(woke[:woke.index(0) + 1], reverse=True) == woke[:woke.index(0) + 1]   # one way down the column
