@@ -839,7 +839,8 @@ int gpx_step(gpx_world *w, float dt, int collision_steps)
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	if ((rc = (w->wide ? launch_wide_tick(w, dt, collision_steps) : launch_tick(w, dt, collision_steps))) != GPX_OK) return rc;
-	// the sleep test runs once per tick, and only in worlds that hold a body allowed to sleep (wide worlds: not yet)
+	// the sleep test runs once per tick, and only in worlds that hold a body allowed to sleep (wide worlds run theirs
+	// at the end of launch_wide_tick)
 	if (w->sleep_enabled && !w->wide && (rc = launch_sleep_test(w, dt)) != GPX_OK) return rc;
 	w->ticks++;
 	return (int)w->m_err[0];

@@ -27,7 +27,8 @@ constexpr uint32_t BF_DOF_SHIFT = 9;     // 6 bits
 constexpr uint32_t BF_ALLOW_SLEEP = 1u << 15;
 constexpr uint32_t BF_RAYFLAG_SHIFT = 16;  // 8 bits
 constexpr uint32_t BF_ASLEEP = 1u << 24;      // a dynamic body that is asleep: static for everything the tick does
-constexpr uint32_t BF_KIN_MOVING = 1u << 25;  // in shared memory only: a kinematic body with a non-zero velocity
+constexpr uint32_t BF_KIN_MOVING = 1u << 25;  // work records only: a kinematic body with a non-zero velocity
+constexpr uint32_t BF_WAKE_MARK = 1u << 26;   // work records only (wide worlds): a sleeper touched by an active body
 
 // Structure-of-arrays body store in HBM; index = world * cap + slot.  Every array is 16-byte vectorised.
 struct BodyStore

@@ -71,6 +71,63 @@ __device__ __forceinline__ uint32_t shape_of(uint32_t f) { return (f >> BF_SHAPE
 __device__ __forceinline__ uint32_t layer_of(uint32_t f) { return (f >> BF_LAYER_SHIFT) & 3u; }
 __device__ __forceinline__ uint32_t dofs_of(uint32_t f) { return (f >> BF_DOF_SHIFT) & 63u; }
 
+// ---- sleeping: one body's sleep test (Jolt's: three test points, each in a sphere that grows to hold it; a radius above
+// 0.03 m/s x 0.5 s restarts the test, 0.5 s without a restart makes the body a candidate).  Updates the 13 floats of test
+// state in `bs`; returns true for a candidate.  `g` = global body index, `f` = its flags (alive, awake, dynamic).
+constexpr float SLEEP_POINT_VELOCITY = 0.03f, SLEEP_TIME = 0.5f;
+
+__device__ __forceinline__ bool sleep_test_body(const BodyStore &bs, size_t g, uint32_t f, float dt)
+{
+	if (!(f & BF_ALLOW_SLEEP) || (f & BF_SENSOR))
+	{
+		bs.sleep_t[g] = -1.0f;
+		return false;
+	}
+	const v3 x = V(bs.pos[g]);
+	const q4 q = Q(bs.quat[g]);
+	const float4 p1 = bs.prop1[g];
+	const v3 e = shape_of(f) == GPX_SHAPE_SPHERE ? V(p1.x, p1.x, p1.x) : V(p1);
+	const int lowest = e.x < e.y ? (e.z < e.x ? 2 : 0) : (e.z < e.y ? 2 : 1);
+	const v3 ax = qrot(q, V(1.0f, 0.0f, 0.0f)), ay = qrot(q, V(0.0f, 1.0f, 0.0f)), az = qrot(q, V(0.0f, 0.0f, 1.0f));
+	v3 pts[3];
+	pts[0] = x;
+	pts[1] = lowest == 0 ? madd(x, ay, e.y) : madd(x, ax, e.x);
+	pts[2] = lowest == 2 ? madd(x, ay, e.y) : madd(x, az, e.z);
+	float t = bs.sleep_t[g];
+	bool restart = t < 0.0f, candidate = false;
+	float4 sp[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		sp[k] = bs.sleep_c[3ull * g + k];
+		if (restart) continue;
+		// grow the sphere just enough to hold the point
+		const v3 d = pts[k] - V(sp[k]);
+		const float d2 = len2(d), r = sp[k].w;
+		if (d2 > (r * r))
+		{
+			const float dist = sqrtf(d2), nr = 0.5f * (r + dist);
+			sp[k] = F4(madd(V(sp[k]), d, (nr - r) / dist), nr);
+		}
+		if (sp[k].w > (SLEEP_POINT_VELOCITY * SLEEP_TIME)) restart = true;
+	}
+	if (restart)
+	{
+#pragma unroll
+		for (int k = 0; k < 3; k++) sp[k] = F4(pts[k], 0.0f);
+		t = 0.0f;
+	}
+	else
+	{
+		t += dt;
+		candidate = t >= SLEEP_TIME;
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++) bs.sleep_c[3ull * g + k] = sp[k];
+	bs.sleep_t[g] = t;
+	return candidate;
+}
+
 __device__ __forceinline__ v3 mask_lin(uint32_t dofs, v3 a)
 {
 	if (!(dofs & 1u)) a.x = 0.0f;

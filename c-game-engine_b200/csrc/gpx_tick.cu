@@ -717,7 +717,6 @@ __global__ void k_apply_commands(BodyStore bs, const BodyCommand *__restrict__ c
 // radius above 15 mm restarts the test, 0.5 s without a restart makes the body a candidate, and an island — awake
 // dynamic bodies joined by the contacts of the last sub-step — goes to sleep when all its bodies are candidates.
 // One warp per world; union-find over at most 64 bodies in shared memory.
-constexpr float SLEEP_POINT_VELOCITY = 0.03f, SLEEP_TIME = 0.5f;
 constexpr int SLEEP_WARPS = 4;
 
 __global__ void __launch_bounds__(SLEEP_WARPS * 32) k_sleep(BodyStore bs, ManifoldCache mc, uint32_t worlds, uint32_t cap, uint32_t cap_m,
@@ -770,54 +769,7 @@ __global__ void __launch_bounds__(SLEEP_WARPS * 32) k_sleep(BodyStore bs, Manifo
 	{
 		const uint32_t f = bs.flags[g0 + i];
 		if (!(f & BF_ALIVE) || !is_dynamic(f)) continue;
-		bool candidate = false;
-		if ((f & BF_ALLOW_SLEEP) && !(f & BF_SENSOR))
-		{
-			const v3 x = V(bs.pos[g0 + i]);
-			const q4 q = Q(bs.quat[g0 + i]);
-			const float4 p1 = bs.prop1[g0 + i];
-			const v3 e = shape_of(f) == GPX_SHAPE_SPHERE ? V(p1.x, p1.x, p1.x) : V(p1);
-			const int lowest = e.x < e.y ? (e.z < e.x ? 2 : 0) : (e.z < e.y ? 2 : 1);
-			const v3 ax = qrot(q, V(1.0f, 0.0f, 0.0f)), ay = qrot(q, V(0.0f, 1.0f, 0.0f)), az = qrot(q, V(0.0f, 0.0f, 1.0f));
-			v3 pts[3];
-			pts[0] = x;
-			pts[1] = lowest == 0 ? madd(x, ay, e.y) : madd(x, ax, e.x);
-			pts[2] = lowest == 2 ? madd(x, ay, e.y) : madd(x, az, e.z);
-			float t = bs.sleep_t[g0 + i];
-			bool restart = t < 0.0f;
-			float4 sp[3];
-#pragma unroll
-			for (int k = 0; k < 3; k++)
-			{
-				sp[k] = bs.sleep_c[3ull * (g0 + i) + k];
-				if (restart) continue;
-				// grow the sphere just enough to hold the point
-				const v3 d = pts[k] - V(sp[k]);
-				const float d2 = len2(d), r = sp[k].w;
-				if (d2 > (r * r))
-				{
-					const float dist = sqrtf(d2), nr = 0.5f * (r + dist);
-					sp[k] = F4(madd(V(sp[k]), d, (nr - r) / dist), nr);
-				}
-				if (sp[k].w > (SLEEP_POINT_VELOCITY * SLEEP_TIME)) restart = true;
-			}
-			if (restart)
-			{
-#pragma unroll
-				for (int k = 0; k < 3; k++) sp[k] = F4(pts[k], 0.0f);
-				t = 0.0f;
-			}
-			else
-			{
-				t += dt;
-				candidate = t >= SLEEP_TIME;
-			}
-#pragma unroll
-			for (int k = 0; k < 3; k++) bs.sleep_c[3ull * (g0 + i) + k] = sp[k];
-			bs.sleep_t[g0 + i] = t;
-		}
-		else
-			bs.sleep_t[g0 + i] = -1.0f;
+		const bool candidate = sleep_test_body(bs, g0 + i, f, dt);
 		if (!candidate)
 		{
 			uint32_t r = i;

@@ -83,6 +83,7 @@ struct WideDevice
 	// count / list offset / fill cursor per root, roots of the small islands, their manifold lists
 	uint32_t *parent = nullptr, *root_of = nullptr, *isl_cnt = nullptr, *isl_off = nullptr, *isl_cur = nullptr;
 	uint32_t *isl_man = nullptr, *big_list = nullptr;
+	unsigned char *can_sleep = nullptr;  // per island root: every body of the island is a sleep candidate
 	int coop_grid_colour = 0, coop_grid_solve = 0;
 };
 
@@ -170,7 +171,11 @@ __global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
 		b.ang_damp = p2.y;
 		b.grav = p2.z;
 		b.restitution = p2.w;
-		b.flags = a.bs.flags[i];
+		uint32_t f0 = a.bs.flags[i];
+		if ((f0 & BF_ALIVE) && ((f0 >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_KINEMATIC &&
+			(l.x != 0.0f || l.y != 0.0f || l.z != 0.0f || w.x != 0.0f || w.y != 0.0f || w.z != 0.0f))
+			f0 |= BF_KIN_MOVING;
+		b.flags = f0;
 	}
 	a.adj_n[i] = 0;
 	a.parent[i] = i;
@@ -258,7 +263,10 @@ __device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p
 {
 	const float4 lo_q = a.boxlo[q], hi_q = a.boxhi[q];
 	const uint32_t iq = __float_as_uint(lo_q.w), fq = __float_as_uint(hi_q.w);
-	if (!is_dynamic(fp) && !is_dynamic(fq)) return;
+	// at least one awake dynamic body — or a moving kinematic body reaching a sleeper, which only wakes it
+	if (!is_dynamic(fp) && !is_dynamic(fq) &&
+		!(((fp & BF_KIN_MOVING) && (fq & BF_ASLEEP)) || ((fq & BF_KIN_MOVING) && (fp & BF_ASLEEP))))
+		return;
 	if (!layers_collide(layer_of(fp), layer_of(fq))) return;
 	if ((fp & BF_SENSOR) || (fq & BF_SENSOR)) return;  // sensor overlaps are events, not contacts (not reported by this path yet)
 	const bool p_first = ip < iq;
@@ -327,6 +335,14 @@ __global__ void __launch_bounds__(NARROW_T) kw_pairs(WideArgs a)
 	if (k >= n) return;
 	SMan &m = a.man[k];
 	pair_contact(a.bodies[m.a], a.bodies[m.b], scratch[threadIdx.x], m);
+	const uint32_t fa = a.bodies[m.a].flags, fb = a.bodies[m.b].flags;
+	if (((fa | fb) & BF_ASLEEP) && m.np > 0)
+	{
+		// a contact with an active body wakes a sleeper (applied by kw_finish: awake from the next sub-step on)
+		if ((fa & BF_ASLEEP) && is_active_body(fb)) atomicOr(&a.bodies[m.a].flags, BF_WAKE_MARK);
+		if ((fb & BF_ASLEEP) && is_active_body(fa)) atomicOr(&a.bodies[m.b].flags, BF_WAKE_MARK);
+		if (!is_dynamic(fa) && !is_dynamic(fb)) m.np = 0;  // kinematic against sleeper: nothing to solve
+	}
 }
 
 __global__ void __launch_bounds__(NARROW_T) kw_static(WideArgs a)
@@ -1009,7 +1025,7 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nb; i += gridDim.x * blockDim.x)
 	{
 		SBody &b = a.bodies[i];
-		if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC) continue;
+		if (!(b.flags & BF_ALIVE) || ((b.flags >> BF_MOTION_SHIFT) & 3u) == GPX_MOTION_STATIC || (b.flags & BF_ASLEEP)) continue;
 		if (a.root_of[i] & ROOT_SMALL) continue;  // integrated by kw_island
 		b.x = b.x + (b.v * h);
 		b.q = qstep(b.q, b.w * h);
@@ -1049,17 +1065,65 @@ __global__ void __launch_bounds__(WT) kw_finish(WideArgs a)
 			}
 		}
 	}
-	if (a.last && t < a.nb)
+	if (t < a.nb)
 	{
-		const SBody &b = a.bodies[t];
-		if (b.flags & BF_ALIVE)
+		SBody &b = a.bodies[t];
+		bool woke = false;
+		if (b.flags & BF_WAKE_MARK)
+		{
+			b.flags &= ~(BF_WAKE_MARK | BF_ASLEEP);
+			a.bs.sleep_t[t] = -1.0f;
+			woke = true;
+		}
+		if (a.last && (b.flags & BF_ALIVE))
 		{
 			a.bs.pos[t] = F4(b.x, 0.0f);
 			a.bs.quat[t] = make_float4(b.q.x, b.q.y, b.q.z, b.q.w);
 			a.bs.lin[t] = F4(b.v, 0.0f);
 			a.bs.ang[t] = F4(b.w, 0.0f);
 		}
+		if (woke) a.bs.flags[t] = b.flags & ~BF_KIN_MOVING;
 	}
+}
+
+
+// ---- sleeping, once per tick after the last sub-step (see k_sleep in gpx_tick.cu for the rule): islands of the awake
+// dynamic bodies from the last sub-step's contacts, the per-body test, then whole islands of candidates go to sleep
+__global__ void __launch_bounds__(WT) kw_sleep_init(WideArgs a, unsigned char *can)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= a.nb) return;
+	a.parent[i] = i;
+	can[i] = 1;
+}
+
+__global__ void __launch_bounds__(WT) kw_sleep_link(WideArgs a)
+{
+	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
+	if (mi >= min(a.cnt[WC_NMAN], a.cap_m)) return;
+	const SMan &m = a.man[mi];
+	if (m.np == 0 || m.b >= STATIC_BODY_BASE) return;
+	if (is_dynamic(a.bodies[m.a].flags) && is_dynamic(a.bodies[m.b].flags)) isl_unite(a.parent, m.a, m.b);
+}
+
+__global__ void __launch_bounds__(WT) kw_sleep_test(WideArgs a, unsigned char *can, float dt)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= a.nb) return;
+	const uint32_t f = a.bodies[i].flags;
+	if (!(f & BF_ALIVE) || !is_dynamic(f)) return;
+	if (!sleep_test_body(a.bs, i, f, dt)) can[isl_find(a.parent, i)] = 0;
+}
+
+__global__ void __launch_bounds__(WT) kw_sleep_apply(WideArgs a, const unsigned char *can)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= a.nb) return;
+	const uint32_t f = a.bodies[i].flags;
+	if (!(f & BF_ALIVE) || !is_dynamic(f) || !can[isl_find(a.parent, i)]) return;
+	a.bs.flags[i] = (f | BF_ASLEEP) & ~(BF_KIN_MOVING | BF_WAKE_MARK);
+	a.bs.lin[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	a.bs.ang[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------- host
@@ -1089,7 +1153,8 @@ int wide_create(gpx_world *w)
 			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m) && walloc(&d->parent, d->nb) &&
 			  walloc(&d->root_of, d->nb) && walloc(&d->isl_cnt, d->nb) && walloc(&d->isl_off, d->nb) && walloc(&d->isl_cur, d->nb) &&
 			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m) &&
-			  walloc(&d->keys_tmp, d->n_pad) && walloc(&d->sort_hist, (size_t)256 * (d->n_pad / 1024u + 1u));
+			  walloc(&d->keys_tmp, d->n_pad) && walloc(&d->sort_hist, (size_t)256 * (d->n_pad / 1024u + 1u)) &&
+			  walloc(&d->can_sleep, d->nb);
 	if (!ok)
 	{
 		set_error("wide_create", cudaGetLastError());
@@ -1113,7 +1178,7 @@ void wide_destroy(gpx_world *w)
 	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
-	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->keys_tmp); cudaFree(d->sort_hist);
+	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->keys_tmp); cudaFree(d->sort_hist); cudaFree(d->can_sleep);
 	delete d;
 	w->wide = nullptr;
 }
@@ -1217,6 +1282,17 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		kw_finish<<<max(gm, gb), WT, 0, st>>>(a);
 		count_launch();
 		d->cur ^= 1;
+	}
+	if (w->sleep_enabled)
+	{
+		// the manifolds of the last sub-step sit in the buffer `cur` just left
+		a.man = d->man[d->cur ^ 1];
+		const uint32_t gn = (d->nb + WT - 1) / WT;
+		kw_sleep_init<<<gn, WT, 0, st>>>(a, d->can_sleep);
+		kw_sleep_link<<<gm, WT, 0, st>>>(a);
+		kw_sleep_test<<<gn, WT, 0, st>>>(a, d->can_sleep, dt);
+		kw_sleep_apply<<<gn, WT, 0, st>>>(a, d->can_sleep);
+		count_launch(4);
 	}
 	// merge the error word into the world's error slot (d_err[0], d_err[1])
 	GPX_CUDA(cudaMemcpyAsync(w->d_err, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

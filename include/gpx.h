@@ -224,7 +224,7 @@ int gpx_body_wake(gpx_world *w, uint32_t world, uint32_t body);
 /* Sleeping (the sleep test of JPH_PhysicsSystem_Update): bodies created with allow_sleeping whose three
  * test points stay within 15 mm (0.03 m/s x 0.5 s) for 0.5 s become candidates; an island of candidates goes to sleep
  * (velocities zeroed, static for the tick) until an active body touches it or the host wakes it.  A world in which
- * nothing is active costs no tick.  Evaluated once per tick; ensemble worlds only (<= 64 bodies per world).
+ * nothing is active costs no tick (ensemble worlds; a wide world still runs its broadphase).  Evaluated once per tick.
  * `out` receives worlds * max_bodies bytes: 1 = asleep. */
 int gpx_read_sleeping(gpx_world *w, uint8_t *out, uint64_t capacity);
 /* Re-evaluates the laser BodyFilter for one body (Laser.c:74-85 reads actor->flags, which may change after create). */

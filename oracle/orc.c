@@ -1594,7 +1594,7 @@ static v3 clamp_len(v3 v, float maxl)
  * body a sleep candidate, and an island (bodies connected by contacts) goes to sleep when all its bodies are candidates:
  * velocities are zeroed and the bodies behave as static until an active body touches them or the host wakes them.
  * Evaluated once per tick (Jolt: once per collision step), on the contacts of the tick's last sub-step.  Sensors and
- * bodies created with allow_sleeping = 0 never sleep.  Wide worlds (mode 1) do not deactivate yet. */
+ * bodies created with allow_sleeping = 0 never sleep. */
 #define SLEEP_POINT_VELOCITY 0.03f
 #define SLEEP_TIME 0.5f
 
@@ -1756,7 +1756,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t i = 0; i < w->max_bodies; i++)
 			if (w->bodies[i].alive && w->bodies[i].wake_mark) wake_body(&w->bodies[i]);
 	}
-	if (w->mode == 0) sleep_pass(w, dt);
+	sleep_pass(w, dt);
 	make_events(w);
 	return err;
 }

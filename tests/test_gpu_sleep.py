@@ -147,3 +147,50 @@ def test_a_sleeping_ensemble_skips_its_ticks(gpx, scenes):
     idle_ms = min(timed_tick() for _ in range(5))
     assert idle_ms < 0.25 * awake_ms, f"idle tick {idle_ms:.3f} ms vs awake {awake_ms:.3f} ms"
     assert g.stats()["error"].max() == 0
+
+
+def test_wide_world_islands_sleep_and_wake(gpx, orc, scenes):
+    """The wide-world kernels (> 64 bodies): 36 separate 3-box columns fall asleep island by island; a sphere rolled into
+    one column wakes that island only; a kinematic slab swept through another wakes it too."""
+    pos = scenes.lattice_positions(6, 3, 6)
+    n0 = len(pos)
+    n = n0 + 2
+    g = gpx.World(worlds=1, max_bodies=n)
+    o = orc.World(n)
+    for p, t in scenes.box_map():
+        g.add_mesh(p, t)
+        o.add_mesh(p, t)
+    g.commit()
+    for p in pos:
+        d = dict(position=tuple(p), allow_sleeping=1)
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+
+    def same(what):
+        assert g.sync() == 0
+        xo, vo = o.state(n)
+        assert np.array_equal(g.transforms()[0, :n].view(np.uint32), xo.view(np.uint32)), f"{what}: transforms differ"
+        assert np.array_equal(g.velocities()[0, :n].view(np.uint32), vo.view(np.uint32)), f"{what}: velocities differ"
+        assert np.array_equal(g.sleeping()[0, :n], o.asleep(n)), f"{what}: sleep states differ"
+
+    for tick in range(1, 151):
+        assert g.step() == 0 and o.step() == 0
+        if tick in (1, 30, 60, 90, 120, 150):
+            same(f"settling tick {tick}")
+    s = g.sleeping()[0, :n0]
+    assert s.all(), f"{s.sum()} of {n0} asleep"
+    x = g.transforms()[0, :n0]
+    target = int(np.argmin(np.abs(x[:, 0] - x[:, 0].max()) + np.abs(x[:, 1] - x[:, 1].min())))   # a bottom box at the +x edge
+    ball = dict(shape=2, half_extents=(0.15, 0, 0), position=(float(x[target, 0]) + 1.5, float(x[target, 1]), float(x[target, 2])),
+                linear_velocity=(-3.0, 0.0, 0.0), mass=5.0, allow_sleeping=1)
+    assert g.create(gpx.body_desc(**ball)) == o.create(orc.body_desc(**ball)) == n0
+    slab = dict(half_extents=(0.1, 0.3, 0.3), position=(float(x[:, 0].min()) - 1.0, float(x[:, 1].min()) + 0.5, float(x[0, 2])),
+                motion_type=1, layer=0, linear_velocity=(1.5, 0.0, 0.0))
+    assert g.create(gpx.body_desc(**slab)) == o.create(orc.body_desc(**slab)) == n0 + 1
+    woke = np.zeros(n0, bool)
+    for tick in range(1, 91):
+        assert g.step() == 0 and o.step() == 0
+        if tick % 10 == 0:
+            same(f"after the hits, tick {tick}")
+        woke |= ~g.sleeping()[0, :n0]
+    assert woke[target]                                             # the ball's column woke
+    assert 3 <= woke.sum() < n0                                     # ... and not the whole world
