@@ -305,7 +305,9 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->bs.sleep_c); cudaFree(w->bs.sleep_t);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
-	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
+	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); if (w->sd.ray_tri != w->sd.tri) cudaFree(w->sd.ray_tri);
+	if (w->sd.ray_nodes != w->sd.nodes) cudaFree(w->sd.ray_nodes);
+	cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);

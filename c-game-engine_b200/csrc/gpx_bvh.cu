@@ -7,6 +7,11 @@
 // order.  The whole tree of a shipped map (<= 2k triangles) is <= 250 KB and is read through shared memory / L2.
 #include <cfloat>
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
 
@@ -23,8 +28,10 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
 
 // key = 30-bit Morton code of the centroid (high word) | original triangle index (low word): unique, so the radix
 // tree never has to break ties.
-__global__ void k_morton_keys(const float *__restrict__ tris, uint32_t n, uint32_t n_pad, float3 lo, float3 inv_ext,
-							  unsigned long long *__restrict__ keys)
+// `refb` (6 floats per primitive: lo xyz, hi xyz) is given when the primitives are split references to triangles (the
+// ray tree); the key then comes from the centre of the reference's box instead of the triangle's centroid.
+__global__ void k_morton_keys(const float *__restrict__ tris, const float *__restrict__ refb, uint32_t n, uint32_t n_pad, float3 lo,
+							  float3 inv_ext, unsigned long long *__restrict__ keys)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_pad) return;
@@ -34,8 +41,20 @@ __global__ void k_morton_keys(const float *__restrict__ tris, uint32_t n, uint32
 		return;
 	}
 	const float *t = tris + 9ull * i;
-	float cx = (t[0] + t[3] + t[6]) * (1.0f / 3.0f), cy = (t[1] + t[4] + t[7]) * (1.0f / 3.0f),
-		  cz = (t[2] + t[5] + t[8]) * (1.0f / 3.0f);
+	float cx, cy, cz;
+	if (refb)
+	{
+		const float *b = refb + 6ull * i;
+		cx = 0.5f * (b[0] + b[3]);
+		cy = 0.5f * (b[1] + b[4]);
+		cz = 0.5f * (b[2] + b[5]);
+	}
+	else
+	{
+		cx = (t[0] + t[3] + t[6]) * (1.0f / 3.0f);
+		cy = (t[1] + t[4] + t[7]) * (1.0f / 3.0f);
+		cz = (t[2] + t[5] + t[8]) * (1.0f / 3.0f);
+	}
 	float fx = fminf(fmaxf((cx - lo.x) * inv_ext.x * 1024.0f, 0.0f), 1023.0f);
 	float fy = fminf(fmaxf((cy - lo.y) * inv_ext.y * 1024.0f, 0.0f), 1023.0f);
 	float fz = fminf(fmaxf((cz - lo.z) * inv_ext.z * 1024.0f, 0.0f), 1023.0f);
@@ -328,8 +347,21 @@ __device__ __forceinline__ void tri_bounds(const float *t, float3 &lo, float3 &h
 	hi.z = fmaxf(t[2], fmaxf(t[5], t[8]));
 }
 
+// bounds of primitive `p`: its reference box when the tree is built over split references, else the triangle's
+__device__ __forceinline__ void prim_bounds(const float *tris, const float *refb, uint32_t p, float3 &lo, float3 &hi)
+{
+	if (refb)
+	{
+		const float *b = refb + 6ull * p;
+		lo = make_float3(b[0], b[1], b[2]);
+		hi = make_float3(b[3], b[4], b[5]);
+	}
+	else
+		tri_bounds(tris + 9ull * p, lo, hi);
+}
+
 // Bottom-up refit: the second thread to reach a node owns it (its sibling subtree is complete and fenced).
-__global__ void k_refit(const float *__restrict__ tris, const unsigned long long *__restrict__ keys, int n,
+__global__ void k_refit(const float *__restrict__ tris, const float *__restrict__ refb, const unsigned long long *__restrict__ keys, int n,
 						const int2 *__restrict__ children, const int *__restrict__ parent_internal,
 						const int *__restrict__ parent_leaf, float *lo_out, float *hi_out, int *visit)
 {
@@ -348,7 +380,7 @@ __global__ void k_refit(const float *__restrict__ tris, const unsigned long long
 		{
 			float3 l, h;
 			if (cc[k] < 0)
-				tri_bounds(tris + 9ull * (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), l, h);
+				prim_bounds(tris, refb, (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), l, h);
 			else
 			{
 				volatile float *vl = lo_out + 3 * cc[k], *vh = hi_out + 3 * cc[k];
@@ -365,8 +397,9 @@ __global__ void k_refit(const float *__restrict__ tris, const unsigned long long
 }
 
 // Emit traversal nodes (both children's padded boxes per node) and leaf-ordered triangle records.
-__global__ void k_pack(const float *__restrict__ tris, const uint32_t *__restrict__ tri_body,
-					   const float *__restrict__ body_friction, const uint32_t *__restrict__ body_rayflags,
+__global__ void k_pack(const float *__restrict__ tris, const float *__restrict__ refb, const uint32_t *__restrict__ ref_orig,
+					   const uint32_t *__restrict__ tri_body, const float *__restrict__ body_friction,
+					   const uint32_t *__restrict__ body_rayflags,
 					   const unsigned long long *__restrict__ keys, int n, const int2 *__restrict__ children,
 					   const float *__restrict__ lo_in, const float *__restrict__ hi_in, float4 *__restrict__ nodes,
 					   float4 *__restrict__ tri_out)
@@ -374,7 +407,8 @@ __global__ void k_pack(const float *__restrict__ tris, const uint32_t *__restric
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n)
 	{
-		uint32_t orig = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+		const uint32_t prim = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+		const uint32_t orig = ref_orig ? ref_orig[prim] : prim;  // the face id a hit reports
 		const float *t = tris + 9ull * orig;
 		v3 a = V(t[0], t[1], t[2]), b = V(t[3], t[4], t[5]), c = V(t[6], t[7], t[8]);
 		v3 nn = cross(b - a, c - a);
@@ -403,7 +437,7 @@ __global__ void k_pack(const float *__restrict__ tris, const uint32_t *__restric
 				continue;
 			}
 			if (cc[k] < 0)
-				tri_bounds(tris + 9ull * (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), lo[k], hi[k]);
+				prim_bounds(tris, refb, (uint32_t)(keys[~cc[k]] & 0xFFFFFFFFull), lo[k], hi[k]);
 			else
 			{
 				lo[k] = make_float3(lo_in[3 * cc[k]], lo_in[3 * cc[k] + 1], lo_in[3 * cc[k] + 2]);
@@ -426,15 +460,179 @@ uint32_t next_pow2(uint32_t v)
 	return p;
 }
 
+// ---- split references for the ray tree -----------------------------------------------------------------------------
+// A shipped map is a few hundred triangles of which some span a whole sector; their boxes make every ray test them.
+// For rays the tree is therefore built over REFERENCES: a large triangle is cut along the longest axis of its box,
+// again and again (largest box first), and every piece becomes a leaf with the box of that piece — pointing at the
+// original triangle, which is what the leaf test intersects and what the hit reports.  The pieces cover the triangle,
+// so the set of triangles a ray can reach is unchanged and so is the closest hit.
+struct Ref
+{
+	uint32_t orig;
+	int nv;
+	double v[10][3];  // the piece: a convex polygon (a triangle cut by axis-aligned planes)
+	double lo[3], hi[3], area;
+};
+
+static void ref_bounds(Ref &r)
+{
+	for (int k = 0; k < 3; k++)
+	{
+		r.lo[k] = 1e300;
+		r.hi[k] = -1e300;
+	}
+	for (int i = 0; i < r.nv; i++)
+		for (int k = 0; k < 3; k++)
+		{
+			r.lo[k] = r.v[i][k] < r.lo[k] ? r.v[i][k] : r.lo[k];
+			r.hi[k] = r.v[i][k] > r.hi[k] ? r.v[i][k] : r.hi[k];
+		}
+	const double ex = r.hi[0] - r.lo[0], ey = r.hi[1] - r.lo[1], ez = r.hi[2] - r.lo[2];
+	r.area = 2.0 * (ex * ey + ey * ez + ez * ex);
+}
+
+// Sutherland-Hodgman against one axis-aligned half space: keep = below (sign < 0) or above (sign > 0) the plane
+static int clip_axis(const double (*in)[3], int n, int axis, double pos, double sign, double (*out)[3])
+{
+	int m = 0;
+	for (int i = 0; i < n; i++)
+	{
+		const double *a = in[i], *b = in[(i + 1) % n];
+		const double da = sign * (a[axis] - pos), db = sign * (b[axis] - pos);
+		if (da >= 0.0)
+		{
+			if (m < 10) memcpy(out[m++], a, sizeof(double) * 3);
+		}
+		if ((da >= 0.0) != (db >= 0.0))
+		{
+			const double t = da / (da - db);
+			if (m < 10)
+			{
+				for (int k = 0; k < 3; k++) out[m][k] = a[k] + t * (b[k] - a[k]);
+				out[m][axis] = pos;
+				m++;
+			}
+		}
+	}
+	return m;
+}
+
+static void split_references(const std::vector<float> &tris, uint32_t n, uint32_t budget, std::vector<uint32_t> &ref_orig,
+							 std::vector<float> &ref_box)
+{
+	std::vector<Ref> refs(n);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		Ref &r = refs[i];
+		r.orig = i;
+		r.nv = 3;
+		for (int v = 0; v < 3; v++)
+			for (int k = 0; k < 3; k++) r.v[v][k] = tris[9ull * i + 3 * v + k];
+		ref_bounds(r);
+	}
+	// largest box first; stop when the budget is spent or the largest box is no bigger than four average ones
+	double total = 0.0;
+	for (const Ref &r : refs) total += r.area;
+	const double floor_area = 4.0 * total / (double)(n ? n : 1) * ((double)n / (double)budget);
+	auto cmp = [&refs](uint32_t a, uint32_t b) { return refs[a].area < refs[b].area || (refs[a].area == refs[b].area && a > b); };
+	std::vector<uint32_t> heap(n);
+	for (uint32_t i = 0; i < n; i++) heap[i] = i;
+	std::make_heap(heap.begin(), heap.end(), cmp);
+	while (refs.size() < budget && !heap.empty())
+	{
+		std::pop_heap(heap.begin(), heap.end(), cmp);
+		const uint32_t top = heap.back();
+		heap.pop_back();
+		if (refs[top].area <= floor_area) break;
+		const Ref r = refs[top];
+		int axis = 0;
+		for (int k = 1; k < 3; k++)
+			if (r.hi[k] - r.lo[k] > r.hi[axis] - r.lo[axis]) axis = k;
+		const double pos = 0.5 * (r.lo[axis] + r.hi[axis]);
+		Ref a = r, b = r;
+		a.nv = clip_axis(r.v, r.nv, axis, pos, -1.0, a.v);
+		b.nv = clip_axis(r.v, r.nv, axis, pos, +1.0, b.v);
+		if (a.nv < 3 || b.nv < 3 || a.nv > 9 || b.nv > 9) continue;  // does not split cleanly: stays one leaf
+		ref_bounds(a);
+		ref_bounds(b);
+		refs[top] = a;
+		refs.push_back(b);
+		heap.push_back(top);
+		std::push_heap(heap.begin(), heap.end(), cmp);
+		heap.push_back((uint32_t)refs.size() - 1u);
+		std::push_heap(heap.begin(), heap.end(), cmp);
+	}
+	ref_orig.resize(refs.size());
+	ref_box.resize(6 * refs.size());
+	for (size_t i = 0; i < refs.size(); i++)
+	{
+		ref_orig[i] = refs[i].orig;
+		for (int k = 0; k < 3; k++)
+		{
+			// outward, past the rounding of the cut positions and of the conversion to float
+			const double pad = 1.0e-5 + 1.0e-6 * (fabs(refs[i].lo[k]) + fabs(refs[i].hi[k]));
+			ref_box[6 * i + k] = nextafterf((float)(refs[i].lo[k] - pad), -FLT_MAX);
+			ref_box[6 * i + 3 + k] = nextafterf((float)(refs[i].hi[k] + pad), FLT_MAX);
+		}
+	}
+}
+
+// Device LBVH over `n` primitives (triangles, or references when d_refb/d_ref_orig are given): Morton keys, sort,
+// Karras hierarchy, refit, pack.  Allocates *nodes_out / *tri_out.
+static int build_tree(gpx_world *w, uint32_t n, const float *d_tris, const float *d_refb, const uint32_t *d_ref_orig,
+					  const uint32_t *d_body, const float *d_fr, const uint32_t *d_rf, float3 flo, float3 inv, float4 **nodes_out,
+					  float4 **tri_out)
+{
+	const uint32_t n_nodes = n > 1 ? n - 1 : 1;
+	const uint32_t n_pad = next_pow2(n);
+	float *d_lo = nullptr, *d_hi = nullptr;
+	unsigned long long *d_keys = nullptr;
+	int2 *d_children = nullptr;
+	int *d_pi = nullptr, *d_pl = nullptr, *d_visit = nullptr;
+	cudaStream_t st = w->stream;
+	GPX_CUDA(cudaMalloc(&d_keys, sizeof(unsigned long long) * n_pad));
+	GPX_CUDA(cudaMalloc(&d_children, sizeof(int2) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_pi, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_pl, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_visit, sizeof(int) * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_lo, sizeof(float) * 3ull * (n + 1)));
+	GPX_CUDA(cudaMalloc(&d_hi, sizeof(float) * 3ull * (n + 1)));
+	GPX_CUDA(cudaMalloc(tri_out, sizeof(float4) * 4ull * n));
+	GPX_CUDA(cudaMalloc(nodes_out, sizeof(float4) * 4ull * n_nodes));
+	GPX_CUDA(cudaMemsetAsync(d_visit, 0, sizeof(int) * (n + 1), st));
+	GPX_CUDA(cudaMemsetAsync(d_pl, 0xFF, sizeof(int) * (n + 1), st));
+	const uint32_t tb = 256;
+	k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, n, n_pad, flo, inv, d_keys);
+	count_launch();
+	bitonic_sort_u64(d_keys, n_pad, st);
+	if (n > 1)
+	{
+		k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);
+		count_launch();
+		k_refit<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, d_keys, (int)n, d_children, d_pi, d_pl, d_lo, d_hi, d_visit);
+		count_launch();
+	}
+	k_pack<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, d_ref_orig, d_body, d_fr, d_rf, d_keys, (int)n, d_children, d_lo, d_hi,
+											 *nodes_out, *tri_out);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	GPX_CUDA(cudaStreamSynchronize(st));
+	cudaFree(d_keys); cudaFree(d_children); cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_visit); cudaFree(d_lo); cudaFree(d_hi);
+	return GPX_OK;
+}
+
 int build_static(gpx_world *w)
 {
 	StaticDevice &sd = w->sd;
+	if (sd.ray_tri && sd.ray_tri != sd.tri) cudaFree(sd.ray_tri);
+	if (sd.ray_nodes && sd.ray_nodes != sd.nodes) cudaFree(sd.ray_nodes);
 	if (sd.tri) cudaFree(sd.tri);
 	if (sd.nodes) cudaFree(sd.nodes);
-	sd.tri = sd.nodes = nullptr;
+	sd.tri = sd.nodes = sd.ray_tri = sd.ray_nodes = nullptr;
 	const uint32_t n = (uint32_t)w->h_tri_body.size();
 	sd.n_tris = n;
 	sd.n_nodes = n == 0 ? 0 : (n > 1 ? n - 1 : 1);
+	sd.n_ray_leaves = sd.n_ray_nodes = 0;
 	w->static_dirty = false;
 	// leaf indices change with every rebuild: forget the per-body candidate lists
 	if (w->d_cand) GPX_CUDA(cudaMemsetAsync(w->d_cand, 0xFF, sizeof(uint4) * 8 * (size_t)w->W * w->cap, w->stream));
@@ -461,52 +659,46 @@ int build_static(gpx_world *w)
 		rf[i] = w->sbodies[i].ray_flags;
 	}
 
-	const uint32_t n_pad = next_pow2(n);
-	float *d_tris = nullptr, *d_fr = nullptr, *d_lo = nullptr, *d_hi = nullptr;
-	uint32_t *d_body = nullptr, *d_rf = nullptr;
-	unsigned long long *d_keys = nullptr;
-	int2 *d_children = nullptr;
-	int *d_pi = nullptr, *d_pl = nullptr, *d_visit = nullptr;
+	float *d_tris = nullptr, *d_fr = nullptr, *d_refb = nullptr;
+	uint32_t *d_body = nullptr, *d_rf = nullptr, *d_ref_orig = nullptr;
 	cudaStream_t st = w->stream;
 	GPX_CUDA(cudaMalloc(&d_tris, sizeof(float) * 9ull * n));
 	GPX_CUDA(cudaMalloc(&d_body, sizeof(uint32_t) * n));
 	GPX_CUDA(cudaMalloc(&d_fr, sizeof(float) * fr.size()));
 	GPX_CUDA(cudaMalloc(&d_rf, sizeof(uint32_t) * rf.size()));
-	GPX_CUDA(cudaMalloc(&d_keys, sizeof(unsigned long long) * n_pad));
-	GPX_CUDA(cudaMalloc(&d_children, sizeof(int2) * (n + 1)));
-	GPX_CUDA(cudaMalloc(&d_pi, sizeof(int) * (n + 1)));
-	GPX_CUDA(cudaMalloc(&d_pl, sizeof(int) * (n + 1)));
-	GPX_CUDA(cudaMalloc(&d_visit, sizeof(int) * (n + 1)));
-	GPX_CUDA(cudaMalloc(&d_lo, sizeof(float) * 3ull * (n + 1)));
-	GPX_CUDA(cudaMalloc(&d_hi, sizeof(float) * 3ull * (n + 1)));
-	GPX_CUDA(cudaMalloc(&sd.tri, sizeof(float4) * 4ull * n));
-	GPX_CUDA(cudaMalloc(&sd.nodes, sizeof(float4) * 4ull * sd.n_nodes));
 	GPX_CUDA(cudaMemcpyAsync(d_tris, w->h_tris.data(), sizeof(float) * 9ull * n, cudaMemcpyHostToDevice, st));
 	GPX_CUDA(cudaMemcpyAsync(d_body, w->h_tri_body.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
 	GPX_CUDA(cudaMemcpyAsync(d_fr, fr.data(), sizeof(float) * fr.size(), cudaMemcpyHostToDevice, st));
 	GPX_CUDA(cudaMemcpyAsync(d_rf, rf.data(), sizeof(uint32_t) * rf.size(), cudaMemcpyHostToDevice, st));
-	GPX_CUDA(cudaMemsetAsync(d_visit, 0, sizeof(int) * (n + 1), st));
-	GPX_CUDA(cudaMemsetAsync(d_pl, 0xFF, sizeof(int) * (n + 1), st));
 
-	const uint32_t tb = 256;
-	k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, n, n_pad, flo, inv, d_keys);
-	count_launch();
-	bitonic_sort_u64(d_keys, n_pad, st);
-	if (n > 1)
+	// the tick's tree: one leaf per triangle (body-vs-map candidates must name each triangle once)
+	int rc = build_tree(w, n, d_tris, nullptr, nullptr, d_body, d_fr, d_rf, flo, inv, &sd.nodes, &sd.tri);
+	sd.ray_nodes = sd.nodes;
+	sd.ray_tri = sd.tri;
+	sd.n_ray_leaves = n;
+	sd.n_ray_nodes = sd.n_nodes;
+	// the rays' tree: split references, as many as still let the whole tree sit in one SM's shared memory
+	uint32_t budget = RAY_TREE_MAX_LEAVES;
+	if (const char *e = getenv("GPX_RAY_LEAVES")) budget = (uint32_t)atoi(e);
+	if (rc == GPX_OK && n >= 2 && n < budget)
 	{
-		k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);
-		count_launch();
-		k_refit<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_keys, (int)n, d_children, d_pi, d_pl, d_lo, d_hi, d_visit);
-		count_launch();
+		std::vector<uint32_t> ref_orig;
+		std::vector<float> ref_box;
+		split_references(w->h_tris, n, budget, ref_orig, ref_box);
+		const uint32_t nr = (uint32_t)ref_orig.size();
+		if (nr > n)
+		{
+			GPX_CUDA(cudaMalloc(&d_refb, sizeof(float) * 6ull * nr));
+			GPX_CUDA(cudaMalloc(&d_ref_orig, sizeof(uint32_t) * nr));
+			GPX_CUDA(cudaMemcpyAsync(d_refb, ref_box.data(), sizeof(float) * 6ull * nr, cudaMemcpyHostToDevice, st));
+			GPX_CUDA(cudaMemcpyAsync(d_ref_orig, ref_orig.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, st));
+			rc = build_tree(w, nr, d_tris, d_refb, d_ref_orig, d_body, d_fr, d_rf, flo, inv, &sd.ray_nodes, &sd.ray_tri);
+			sd.n_ray_leaves = nr;
+			sd.n_ray_nodes = nr - 1;
+		}
 	}
-	k_pack<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_body, d_fr, d_rf, d_keys, (int)n, d_children, d_lo, d_hi, sd.nodes,
-											 sd.tri);
-	count_launch();
-	GPX_CUDA(cudaGetLastError());
-	GPX_CUDA(cudaStreamSynchronize(st));
-	cudaFree(d_tris); cudaFree(d_body); cudaFree(d_fr); cudaFree(d_rf); cudaFree(d_keys); cudaFree(d_children);
-	cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_visit); cudaFree(d_lo); cudaFree(d_hi);
-	return GPX_OK;
+	cudaFree(d_tris); cudaFree(d_body); cudaFree(d_fr); cudaFree(d_rf); cudaFree(d_refb); cudaFree(d_ref_orig);
+	return rc;
 }
 
 }  // namespace gpx

@@ -60,7 +60,13 @@ struct StaticDevice
 	uint32_t n_tris = 0, n_nodes = 0;
 	float4 *tri = nullptr;    // 4 float4 per triangle in LBVH order: (a, orig index) (b, static body) (c, friction) (n, ray flags)
 	float4 *nodes = nullptr;  // 4 float4 per internal node: c0 xy bounds, c1 xy bounds, both z bounds, child indices
+	// the rays' tree: same record formats over split references (large triangles cut into several leaves that all
+	// point at the original triangle); aliases the tree above when nothing was split
+	uint32_t n_ray_leaves = 0, n_ray_nodes = 0;
+	float4 *ray_tri = nullptr, *ray_nodes = nullptr;
 };
+constexpr uint32_t RAY_TREE_MAX_LEAVES = 1000;  // (2 * 1000 - 1) * 64 B = 128 KB in one SM's shared memory; measured optimum
+                                                // on shapes.gmap (850: 3.60, 1000: 3.83, 1250: 3.67 G rays/s)
 
 // player character of one world (gpx_char.cu)
 struct CharDev

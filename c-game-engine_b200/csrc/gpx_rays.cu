@@ -12,7 +12,8 @@
 
 namespace gpx {
 
-constexpr int RAY_THREADS = 256;
+constexpr int RAY_THREADS = 256;       // CTA size when several CTAs share an SM
+constexpr int RAY_THREADS_MAX = 1024;  // one CTA per SM (a large tree in shared memory): as many warps as registers allow
 constexpr int STACK_DEPTH = 64;  // a radix tree over 64-bit keys is at most 64 levels deep
 
 struct RayArgs
@@ -211,7 +212,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 
 // SMEM = tree staged in shared memory (TMA bulk copy); otherwise read through L1/L2.
 template <bool SMEM>
-__global__ void __launch_bounds__(RAY_THREADS) k_raycast(RayArgs a)
+__global__ void __launch_bounds__(RAY_THREADS_MAX) k_raycast(RayArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const float4 *NODES = a.nodes;
@@ -254,8 +255,8 @@ __global__ void __launch_bounds__(RAY_THREADS) k_raycast(RayArgs a)
 		NODES = s_nodes;
 		TRIS = s_tris;
 	}
-	const unsigned long long stride = (unsigned long long)gridDim.x * RAY_THREADS;
-	for (unsigned long long i = (unsigned long long)blockIdx.x * RAY_THREADS + threadIdx.x; i < a.n; i += stride)
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
 	{
 		const float4 r0 = __ldg(&a.rays[2 * i]), r1 = __ldg(&a.rays[2 * i + 1]);
 		const v3 o = V(r0), d = V(r1);
@@ -281,10 +282,10 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 {
 	if (n == 0) return GPX_OK;
 	RayArgs a;
-	a.nodes = w->sd.nodes;
-	a.tris = w->sd.tri;
-	a.n_nodes = w->sd.n_nodes;
-	a.n_tris = w->sd.n_tris;
+	a.nodes = w->sd.ray_nodes;
+	a.tris = w->sd.ray_tri;
+	a.n_nodes = w->sd.n_ray_nodes;
+	a.n_tris = w->sd.n_ray_leaves;
 	a.rays = (const float4 *)d_rays;
 	a.hits = (float4 *)d_hits;
 	a.n = n;
@@ -309,10 +310,13 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 		}
 		int per_sm = (int)((227u * 1024u) / (tree_bytes + 1024u));
 		if (per_sm < 1) per_sm = 1;
-		if (per_sm > 8) per_sm = 8;
+		if (per_sm > 4) per_sm = 4;
+		// about 1024 threads per SM whatever the number of tree copies that fit
+		const int threads = per_sm >= 4 ? 256 : (per_sm == 3 ? 320 : (per_sm == 2 ? 512 : RAY_THREADS_MAX));
+		want = (n + threads - 1) / threads;
 		unsigned long long grid = (unsigned long long)sms * per_sm;
 		if (grid > want) grid = want;
-		k_raycast<true><<<(unsigned)grid, RAY_THREADS, tree_bytes, w->stream>>>(a);
+		k_raycast<true><<<(unsigned)grid, threads, tree_bytes, w->stream>>>(a);
 	}
 	else
 	{
