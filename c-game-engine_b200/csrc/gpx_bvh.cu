@@ -577,11 +577,140 @@ static void split_references(const std::vector<float> &tris, uint32_t n, uint32_
 	}
 }
 
+// ---- topology of the rays' tree: binned SAH, top-down, on the host.  The tree has at most RAY_TREE_MAX_LEAVES leaves and
+// is built once per map, so a surface-area-heuristic build costs nothing and saves traversal steps on every ray; the
+// device kernels (refit, pack) then run on this topology exactly as they do on Karras' radix tree.
+struct SahTopology
+{
+	std::vector<unsigned long long> keys;  // leaf -> primitive (reference) index
+	std::vector<int2> children;            // >= 0 internal node, < 0 ~leaf
+	std::vector<int> parent_internal, parent_leaf;
+	int depth = 0;  // deepest leaf; the traversal keeps a 64-entry stack per lane
+};
+
+static int sah_build(const std::vector<float> &box, std::vector<uint32_t> &idx, uint32_t lo, uint32_t hi, int parent, SahTopology &t,
+					 int level = 0)
+{
+	if (level > t.depth) t.depth = level;
+	// returns the child code of the subtree over idx[lo, hi)
+	if (hi - lo == 1)
+	{
+		const int leaf = (int)t.keys.size();
+		t.keys.push_back((unsigned long long)idx[lo]);
+		t.parent_leaf.push_back(parent);
+		return ~leaf;
+	}
+	const int node = (int)t.children.size();
+	t.children.push_back(make_int2(0, 0));
+	t.parent_internal.push_back(parent);
+	// centroid bounds
+	double cl[3] = {1e300, 1e300, 1e300}, ch[3] = {-1e300, -1e300, -1e300};
+	for (uint32_t i = lo; i < hi; i++)
+		for (int k = 0; k < 3; k++)
+		{
+			const double c = 0.5 * ((double)box[6ull * idx[i] + k] + (double)box[6ull * idx[i] + 3 + k]);
+			cl[k] = c < cl[k] ? c : cl[k];
+			ch[k] = c > ch[k] ? c : ch[k];
+		}
+	constexpr int BINS = 16;
+	double best_cost = 1e300;
+	int best_axis = -1, best_bin = 0;
+	for (int axis = 0; axis < 3; axis++)
+	{
+		const double ext = ch[axis] - cl[axis];
+		if (!(ext > 1e-12)) continue;
+		double blo[BINS][3], bhi[BINS][3];
+		int cnt[BINS];
+		for (int b = 0; b < BINS; b++)
+		{
+			cnt[b] = 0;
+			for (int k = 0; k < 3; k++)
+			{
+				blo[b][k] = 1e300;
+				bhi[b][k] = -1e300;
+			}
+		}
+		for (uint32_t i = lo; i < hi; i++)
+		{
+			const float *bx = &box[6ull * idx[i]];
+			const double c = 0.5 * ((double)bx[axis] + (double)bx[3 + axis]);
+			int b = (int)((c - cl[axis]) / ext * BINS);
+			b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+			cnt[b]++;
+			for (int k = 0; k < 3; k++)
+			{
+				blo[b][k] = bx[k] < blo[b][k] ? bx[k] : blo[b][k];
+				bhi[b][k] = bx[3 + k] > bhi[b][k] ? bx[3 + k] : bhi[b][k];
+			}
+		}
+		// sweep: cost of splitting after bin s = area(left) * n(left) + area(right) * n(right)
+		double rl[BINS][3], rh[BINS][3];
+		int rc[BINS];
+		double al[3] = {1e300, 1e300, 1e300}, ah[3] = {-1e300, -1e300, -1e300};
+		int ac = 0;
+		for (int b = BINS - 1; b >= 0; b--)
+		{
+			ac += cnt[b];
+			for (int k = 0; k < 3; k++)
+			{
+				al[k] = blo[b][k] < al[k] ? blo[b][k] : al[k];
+				ah[k] = bhi[b][k] > ah[k] ? bhi[b][k] : ah[k];
+				rl[b][k] = al[k];
+				rh[b][k] = ah[k];
+			}
+			rc[b] = ac;
+		}
+		double ll[3] = {1e300, 1e300, 1e300}, lh[3] = {-1e300, -1e300, -1e300};
+		int lc = 0;
+		for (int sbin = 0; sbin < BINS - 1; sbin++)
+		{
+			lc += cnt[sbin];
+			for (int k = 0; k < 3; k++)
+			{
+				ll[k] = blo[sbin][k] < ll[k] ? blo[sbin][k] : ll[k];
+				lh[k] = bhi[sbin][k] > lh[k] ? bhi[sbin][k] : lh[k];
+			}
+			if (lc == 0 || rc[sbin + 1] == 0) continue;
+			auto area = [](const double *a, const double *b) {
+				const double x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2];
+				return 2.0 * (x * y + y * z + z * x);
+			};
+			const double cost = area(ll, lh) * lc + area(rl[sbin + 1], rh[sbin + 1]) * rc[sbin + 1];
+			if (cost < best_cost)
+			{
+				best_cost = cost;
+				best_axis = axis;
+				best_bin = sbin;
+			}
+		}
+	}
+	uint32_t mid;
+	if (best_axis < 0)
+		mid = lo + (hi - lo) / 2;  // all centroids coincide: any balanced split
+	else
+	{
+		const double ext = ch[best_axis] - cl[best_axis];
+		auto left = [&](uint32_t p) {
+			const float *bx = &box[6ull * p];
+			const double c = 0.5 * ((double)bx[best_axis] + (double)bx[3 + best_axis]);
+			int b = (int)((c - cl[best_axis]) / ext * BINS);
+			b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+			return b <= best_bin;
+		};
+		mid = (uint32_t)(std::stable_partition(idx.begin() + lo, idx.begin() + hi, left) - idx.begin());
+		if (mid == lo || mid == hi) mid = lo + (hi - lo) / 2;
+	}
+	const int c0 = sah_build(box, idx, lo, mid, node, t, level + 1);
+	const int c1 = sah_build(box, idx, mid, hi, node, t, level + 1);
+	t.children[node] = make_int2(c0, c1);
+	return node;
+}
+
 // Device LBVH over `n` primitives (triangles, or references when d_refb/d_ref_orig are given): Morton keys, sort,
 // Karras hierarchy, refit, pack.  Allocates *nodes_out / *tri_out.
 static int build_tree(gpx_world *w, uint32_t n, const float *d_tris, const float *d_refb, const uint32_t *d_ref_orig,
 					  const uint32_t *d_body, const float *d_fr, const uint32_t *d_rf, float3 flo, float3 inv, float4 **nodes_out,
-					  float4 **tri_out)
+					  float4 **tri_out, const SahTopology *topo = nullptr)
 {
 	const uint32_t n_nodes = n > 1 ? n - 1 : 1;
 	const uint32_t n_pad = next_pow2(n);
@@ -602,13 +731,27 @@ static int build_tree(gpx_world *w, uint32_t n, const float *d_tris, const float
 	GPX_CUDA(cudaMemsetAsync(d_visit, 0, sizeof(int) * (n + 1), st));
 	GPX_CUDA(cudaMemsetAsync(d_pl, 0xFF, sizeof(int) * (n + 1), st));
 	const uint32_t tb = 256;
-	k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, n, n_pad, flo, inv, d_keys);
-	count_launch();
-	bitonic_sort_u64(d_keys, n_pad, st);
+	if (topo)
+	{
+		// topology from the host (SAH): leaf order, children, parents
+		GPX_CUDA(cudaMemcpyAsync(d_keys, topo->keys.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
+		GPX_CUDA(cudaMemcpyAsync(d_children, topo->children.data(), sizeof(int2) * (n - 1), cudaMemcpyHostToDevice, st));
+		GPX_CUDA(cudaMemcpyAsync(d_pi, topo->parent_internal.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice, st));
+		GPX_CUDA(cudaMemcpyAsync(d_pl, topo->parent_leaf.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+	}
+	else
+	{
+		k_morton_keys<<<(n_pad + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, n, n_pad, flo, inv, d_keys);
+		count_launch();
+		bitonic_sort_u64(d_keys, n_pad, st);
+	}
 	if (n > 1)
 	{
-		k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);
-		count_launch();
+		if (!topo)
+		{
+			k_hierarchy<<<(n + tb - 1) / tb, tb, 0, st>>>(d_keys, (int)n, d_children, d_pi, d_pl);
+			count_launch();
+		}
 		k_refit<<<(n + tb - 1) / tb, tb, 0, st>>>(d_tris, d_refb, d_keys, (int)n, d_children, d_pi, d_pl, d_lo, d_hi, d_visit);
 		count_launch();
 	}
@@ -677,25 +820,29 @@ int build_static(gpx_world *w)
 	sd.ray_tri = sd.tri;
 	sd.n_ray_leaves = n;
 	sd.n_ray_nodes = sd.n_nodes;
-	// the rays' tree: split references, as many as still let the whole tree sit in one SM's shared memory
+	// the rays' tree: split references, as many as still let the whole tree sit in one SM's shared memory, under a SAH
+	// topology built on the host (maps too large for shared memory keep one leaf per triangle but still get the SAH)
 	uint32_t budget = RAY_TREE_MAX_LEAVES;
 	if (const char *e = getenv("GPX_RAY_LEAVES")) budget = (uint32_t)atoi(e);
-	if (rc == GPX_OK && n >= 2 && n < budget)
+	if (rc == GPX_OK && n >= 2 && n <= RAY_TREE_MAX_HOST_BUILD && getenv("GPX_RAY_LBVH") == nullptr)
 	{
 		std::vector<uint32_t> ref_orig;
 		std::vector<float> ref_box;
-		split_references(w->h_tris, n, budget, ref_orig, ref_box);
+		split_references(w->h_tris, n, budget > n ? budget : n, ref_orig, ref_box);
 		const uint32_t nr = (uint32_t)ref_orig.size();
-		if (nr > n)
-		{
-			GPX_CUDA(cudaMalloc(&d_refb, sizeof(float) * 6ull * nr));
-			GPX_CUDA(cudaMalloc(&d_ref_orig, sizeof(uint32_t) * nr));
-			GPX_CUDA(cudaMemcpyAsync(d_refb, ref_box.data(), sizeof(float) * 6ull * nr, cudaMemcpyHostToDevice, st));
-			GPX_CUDA(cudaMemcpyAsync(d_ref_orig, ref_orig.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, st));
-			rc = build_tree(w, nr, d_tris, d_refb, d_ref_orig, d_body, d_fr, d_rf, flo, inv, &sd.ray_nodes, &sd.ray_tri);
-			sd.n_ray_leaves = nr;
-			sd.n_ray_nodes = nr - 1;
-		}
+		GPX_CUDA(cudaMalloc(&d_refb, sizeof(float) * 6ull * nr));
+		GPX_CUDA(cudaMalloc(&d_ref_orig, sizeof(uint32_t) * nr));
+		GPX_CUDA(cudaMemcpyAsync(d_refb, ref_box.data(), sizeof(float) * 6ull * nr, cudaMemcpyHostToDevice, st));
+		GPX_CUDA(cudaMemcpyAsync(d_ref_orig, ref_orig.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, st));
+		SahTopology topo;
+		std::vector<uint32_t> idx(nr);
+		for (uint32_t i = 0; i < nr; i++) idx[i] = i;
+		sah_build(ref_box, idx, 0, nr, -1, topo);
+		// a SAH tree deeper than the traversal stack (pathological input) falls back to the radix tree, which never is
+		rc = build_tree(w, nr, d_tris, d_refb, d_ref_orig, d_body, d_fr, d_rf, flo, inv, &sd.ray_nodes, &sd.ray_tri,
+						topo.depth <= 56 ? &topo : nullptr);
+		sd.n_ray_leaves = nr;
+		sd.n_ray_nodes = nr - 1;
 	}
 	cudaFree(d_tris); cudaFree(d_body); cudaFree(d_fr); cudaFree(d_rf); cudaFree(d_refb); cudaFree(d_ref_orig);
 	return rc;

@@ -65,6 +65,7 @@ struct StaticDevice
 	uint32_t n_ray_leaves = 0, n_ray_nodes = 0;
 	float4 *ray_tri = nullptr, *ray_nodes = nullptr;
 };
+constexpr uint32_t RAY_TREE_MAX_HOST_BUILD = 1u << 18;  // triangles up to which the rays' tree gets its SAH topology on the host
 constexpr uint32_t RAY_TREE_MAX_LEAVES = 1000;  // (2 * 1000 - 1) * 64 B = 128 KB in one SM's shared memory; measured optimum
                                                 // on shapes.gmap (850: 3.60, 1000: 3.83, 1250: 3.67 G rays/s)
 
