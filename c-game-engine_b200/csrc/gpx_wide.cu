@@ -16,14 +16,17 @@
 //                                  lists per dynamic body, colouring priority, union-find over dynamic-dynamic contacts
 //   kw_isl_*      thread/item      simulation islands (connected components of the contact graph): manifold count per
 //                                  island; islands of at most 32 manifolds packed into 32-slot windows
-//   kw_island     warp/window      small islands, start to finish inside one warp: the same colouring, set-up, warm
-//                                  start, velocity rows, integration and position rows, with warp barriers in place of
-//                                  grid-wide ones (a stack of boxes is an island; the lattice of config 4 is 10 000)
+//   kw_island     warp/window      small islands inside one warp: the same colouring, set-up, warm start, velocity rows
+//                                  and integration, with warp barriers in place of grid-wide ones and the bodies'
+//                                  velocities in shared memory (a stack of boxes is an island; config 4 has 10 000)
 //   kw_colour     cooperative      the remaining (large) islands: Jones-Plassmann colouring with hashed priorities
 //                                  (result depends on the contact graph only, not on list order), per-colour lists
-//   kw_solve      cooperative      large islands: set-up; warm start; 10 x (colour by colour) velocity rows; integrate;
-//                                  2 x (colour by colour) position rows — grid-wide barriers between colours
-//   kw_finish     thread/manifold  hash table for the next sub-step; last sub-step: work records -> SoA
+//   kw_solve      cooperative      large islands: set-up; warm start; 10 x (colour by colour) velocity rows; integrate
+//                                  (also free and kinematic bodies); 2 x (colour by colour) position rows — grid-wide
+//                                  barriers between colours, or block barriers in one block when the islands are few
+//   kw_island_pos warp/window      the small islands' position rows, after the kinematic bodies have moved
+//   kw_finish     thread/item      hash table for the next sub-step; wake marks; last sub-step: work records -> SoA
+//   kw_sleep_*    thread/item      once per tick: islands of the awake bodies, sleep test, whole islands to sleep
 //
 // No float atomics and no order-dependent reductions: within a colour no two manifolds share a dynamic body, so the
 // result is a pure function of the contact set.  Islands do not share dynamic bodies either, and the colouring of a
