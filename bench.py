@@ -320,6 +320,7 @@ def run_gpu(args):
     rays_res = bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- C4: one wide world of 100k boxes (replicated per rank)
+    single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if rank == 0 else None
     wide_res = None if args.no_wide else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- end-of-run stats gather over NCCL (the only collective)
@@ -353,6 +354,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "rays": rays_res,
             "wide": wide_res,
+            "single_world": single_res,
             "wall_ms_timed_region": wall_ms,
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
@@ -377,6 +379,44 @@ def make_wide_world(gpx, scenes, pos, device):
     ids = np.zeros(n, np.uint32)
     assert g.L.gpx_body_create_all(g.h, arr, n, None, None, ids.ctypes.data) == 0
     return g
+
+
+def bench_single_world(gpx, scenes, args, device, rank):
+    """BASELINE configs[1]: ONE stacked.gmap world, the 8-box column, 600 ticks.  A latency figure, not a throughput
+    one — a single small world occupies one warp of one SM (the GPU path exists for thousands of them); reported so the
+    configuration has a measured line next to the CPU restatement."""
+    g = gpx.World(worlds=1, max_bodies=8, device=device)
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+    g.commit()
+    for p in scenes.stack_positions(BOXES):
+        g.create(gpx.body_desc(position=tuple(p)))
+    for _ in range(10):
+        assert g.step() == 0
+    assert g.sync() == 0
+    ticks = 600
+    g.timer_begin()
+    for _ in range(ticks):
+        rc = g.step()
+    ms = g.timer_end() / ticks
+    assert rc == 0 and g.sync() == 0
+    res = {"workload": "C2: one stacked.gmap world, 8-box column at rest height, 600 ticks (a single warp's latency)",
+           "ms_per_tick": ms, "body_steps_per_s": BOXES / (ms * 1e-3)}
+    if rank == 0 and not args.no_cpu:
+        import orc
+        o = orc.World(BOXES)
+        for pos, tris in scenes.load_static("stacked"):
+            o.add_mesh(pos, tris)
+        for p in scenes.stack_positions(BOXES):
+            o.create(orc.body_desc(position=tuple(p)))
+        for _ in range(10):
+            o.step()
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            o.step()
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / ticks
+        res["cpu_port"] = {"ms_per_tick": cpu_ms, "body_steps_per_s": BOXES / (cpu_ms * 1e-3), "cores": 1}
+    return res
 
 
 def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ranks, flush, hbm_peak):
