@@ -321,6 +321,7 @@ def run_gpu(args):
 
     # ---------------- C4: one wide world of 100k boxes (replicated per rank)
     single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if rank == 0 else None
+    test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if rank == 0 else None
     wide_res = None if args.no_wide else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- end-of-run stats gather over NCCL (the only collective)
@@ -355,6 +356,7 @@ def run_gpu(args):
             "rays": rays_res,
             "wide": wide_res,
             "single_world": single_res,
+            "test_map": test_map_res,
             "wall_ms_timed_region": wall_ms,
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
@@ -416,6 +418,54 @@ def bench_single_world(gpx, scenes, args, device, rank):
             o.step()
         cpu_ms = 1e3 * (time.perf_counter() - t0) / ticks
         res["cpu_port"] = {"ms_per_tick": cpu_ms, "body_steps_per_s": BOXES / (cpu_ms * 1e-3), "cores": 1}
+    return res
+
+
+def bench_test_map(gpx, scenes, args, device, rank):
+    """BASELINE configs[0]: the physics content of mapSources/test.json (test.gmap: 644 map triangles + 4 laser-emitter
+    meshes, 13 bodies of which 2 dynamic), 600 fixed ticks; per tick the four lasers cast their rays, then the update and
+    the transform readback — the engine-facing sequence with host buffers.  Latency again: one world."""
+    sc = scenes.test_map_scene()
+    g = gpx.World(worlds=1, max_bodies=16, device=device)
+    for pos, rot, tris, fr in sc["meshes"]:
+        g.add_mesh(pos, tris, friction=fr, rot=rot)
+    g.commit()
+    for d in sc["bodies"]:
+        g.create(gpx.body_desc(**d))
+    rays = scenes.laser_rays(sc["lasers"])
+    h_rays = gpx.pinned_array(len(rays), gpx.RAY_DTYPE)
+    h_hits = gpx.pinned_array(len(rays), gpx.HIT_DTYPE)
+    h_rays[:] = rays
+    for _ in range(10):
+        g.raycast_into_async(h_rays, h_hits)
+        assert (g.step() | g.sync()) == 0
+    ticks = 600
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        g.raycast_into_async(h_rays, h_hits)
+        rc = g.step() | g.sync()
+    ms = 1e3 * (time.perf_counter() - t0) / ticks
+    assert rc == 0
+    dyn = sum(1 for d in sc["bodies"] if d.get("motion_type", 2) == 2)
+    res = {"workload": "C1: test.gmap, its 13 bodies (2 dynamic) and 4 lasers, 600 ticks; per tick rays + gpx_step + "
+                       "gpx_sync_transforms with host buffers (wall clock)",
+           "ms_per_tick": ms, "dynamic_bodies": dyn, "body_steps_per_s": dyn / (ms * 1e-3)}
+    if rank == 0 and not args.no_cpu:
+        import orc
+        o = orc.World(16)
+        for pos, rot, tris, fr in sc["meshes"]:
+            o.add_mesh(pos, tris, friction=fr, rot=rot)
+        for d in sc["bodies"]:
+            o.create(orc.body_desc(**d))
+        for _ in range(10):
+            o.raycast(rays)
+            o.step()
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            o.raycast(rays)
+            o.step()
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / ticks
+        res["cpu_port"] = {"ms_per_tick": cpu_ms, "body_steps_per_s": dyn / (cpu_ms * 1e-3), "cores": 1}
     return res
 
 
