@@ -94,6 +94,8 @@ class Transform(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("rotation", C.c_float * 4)]
 
 
+CAPSULE_DTYPE = np.dtype([("center", "<f4", 3), ("half_height", "<f4"), ("radius", "<f4"), ("world", "<u4"), ("reserved", "<u4", 2)])
+OVERLAP_DTYPE = np.dtype([("depth", "<f4"), ("normal", "<f4", 3), ("body", "<u4"), ("world", "<u4"), ("reserved", "<u4", 2)])
 FIXED_UPDATE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double)          # gpx_fixed_update_fn
 INPUT_EVENT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)  # gpx_input_event_fn
 
@@ -185,6 +187,7 @@ def lib() -> C.CDLL:
         "gpx_body_destroy": (i32, [vp, u32, u32]),
         "gpx_body_set_ray_flags": (i32, [vp, u32, u32, u32]),
         "gpx_body_wake": (i32, [vp, u32, u32]),
+        "gpx_overlap_capsule_batch": (i32, [vp, vp, u64, vp]),
         "gpx_read_sleeping": (i32, [vp, vp, u64]),
         "gpx_body_set_linear_velocity": (i32, [vp, u32, u32, C.POINTER(f32)]),
         "gpx_body_set_linear_and_angular_velocity": (i32, [vp, u32, u32, C.POINTER(f32), C.POINTER(f32)]),
@@ -338,6 +341,13 @@ class World:
         _check(self.L.gpx_debug_wide_counters(self.h, c.ctypes.data), "gpx_debug_wide_counters")
         return dict(manifold_slots=int(c[0]), small_islands=int(c[1]), colours=int(c[2]), error=int(c[3]),
                     large_island_manifolds=int(c[5]))
+
+    def overlap_capsules(self, queries: np.ndarray) -> np.ndarray:
+        """gpx_overlap_capsule_batch: deepest penetration of each upright capsule against the map and the solid bodies."""
+        q = np.ascontiguousarray(queries, dtype=CAPSULE_DTYPE)
+        out = np.zeros(len(q), OVERLAP_DTYPE)
+        _check(self.L.gpx_overlap_capsule_batch(self.h, q.ctypes.data, len(q), out.ctypes.data), "gpx_overlap_capsule_batch")
+        return out
 
     def wake(self, body, world=0):
         _check(self.L.gpx_body_wake(self.h, world, body), "gpx_body_wake")

@@ -982,6 +982,33 @@ int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *ori
 	return gpx_raycast_batch(w, &r, 1, out);
 }
 
+int gpx_overlap_capsule_batch(gpx_world *w, const gpx_capsule_query *queries, uint64_t n, gpx_overlap *out)
+{
+	if (!w || (n && (!queries || !out))) return GPX_ERR_INVALID_ARG;
+	if (n == 0) return GPX_OK;
+	static_assert(sizeof(gpx_capsule_query) == 32 && sizeof(gpx_overlap) == 32, "two float4 per record");
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	void *d_q = nullptr, *d_o = nullptr;
+	GPX_CUDA(cudaMalloc(&d_q, 32ull * n));
+	if (cudaMalloc(&d_o, 32ull * n) != cudaSuccess)
+	{
+		cudaFree(d_q);
+		return GPX_ERR_CUDA;
+	}
+	rc = GPX_OK;
+	if (cudaMemcpyAsync(d_q, queries, 32ull * n, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
+	if (rc == GPX_OK) rc = launch_overlap_capsules(w, d_q, n, d_o);
+	if (rc == GPX_OK && cudaMemcpyAsync(out, d_o, 32ull * n, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
+	if (cudaStreamSynchronize(w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
+	cudaFree(d_q);
+	cudaFree(d_o);
+	return rc;
+}
+
 /* ---- harness helpers */
 
 void *gpx_device_alloc(uint64_t bytes)

@@ -433,6 +433,52 @@ __global__ void __launch_bounds__(128) k_character(CharArgs a)
 	}
 }
 
+// ---- batched capsule overlap queries: the collide-shape query the character controller is made of, for callers that
+// bring their own capsules (one warp per query; same routine, same tie-breaks as the character's push-out)
+__global__ void __launch_bounds__(128) k_overlap_capsules(CharArgs a, const float4 *__restrict__ q, unsigned long long n, float4 *__restrict__ out)
+{
+	__shared__ int s_orig[4][MAX_TRI_CANDIDATES], s_leaf[4][MAX_TRI_CANDIDATES], s_nc[4];
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned long long i = (unsigned long long)blockIdx.x * 4ull + wib;
+	if (i >= n) return;
+	const float4 q0 = __ldg(&q[2 * i]), q1 = __ldg(&q[2 * i + 1]);  // centre xyz, half height | radius, world, -, -
+	const uint32_t world = __float_as_uint(q1.y);
+	uint32_t err = 0;
+	Deepest d;
+	d.pen = 0.0f;
+	d.n = V(0.0f, 1.0f, 0.0f);
+	d.body = GPX_INVALID_BODY;
+	if (world < a.worlds) d = ch_deepest(a, world, V(q0), q0.w, q1.x, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+	if (lane == 0)
+	{
+		const bool hit = d.pen > 0.0f;
+		out[2 * i] = make_float4(hit ? d.pen : 0.0f, d.n.x, d.n.y, d.n.z);
+		out[2 * i + 1] = make_float4(__uint_as_float(hit ? d.body : GPX_INVALID_BODY), __uint_as_float(world), 0.0f, 0.0f);
+		if (err) atomicOr(&a.err[0], err);
+	}
+}
+
+int launch_overlap_capsules(gpx_world *w, const void *d_queries, uint64_t n, void *d_out)
+{
+	if (n == 0) return GPX_OK;
+	CharArgs a;
+	a.ch = nullptr;
+	a.keys = nullptr;
+	a.nkeys = nullptr;
+	a.bs = w->bs;
+	a.sv.nodes = w->sd.nodes;
+	a.sv.tris = w->sd.tri;
+	a.sv.n_nodes = w->sd.n_nodes;
+	a.worlds = w->W;
+	a.cap = w->cap;
+	a.err = w->d_err;
+	a.dt = 0.0f;
+	k_overlap_capsules<<<(unsigned)((n + 3) / 4), 128, 0, w->stream>>>(a, (const float4 *)d_queries, n, (float4 *)d_out);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
 int launch_character(gpx_world *w, float dt)
 {
 	CharArgs a;

@@ -355,6 +355,31 @@ int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void 
 int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *origin, float max_distance, uint32_t mask,
 						  gpx_hit *out);
 
+/* ---- shape queries ------------------------------------------------------------------------------------------------------ */
+
+/* Batched capsule overlap: the collide-shape query JPH_CharacterVirtual_ExtendedUpdate is built from
+ * (engine/src/physics/PlayerPhysics.c:447), for callers that bring their own upright capsules.  Each query reports the
+ * deepest penetration against the static map and the solid bodies (layers STATIC and DYNAMIC, no sensors) of its world:
+ * depth > 0, the unit normal that pushes the capsule out, and the body (>= 0x400000: a static mesh).  depth == 0 and
+ * body == GPX_INVALID_BODY when nothing is touched.  Ties go to the lower triangle index, then the lower body id. */
+typedef struct gpx_capsule_query /* 32 B */
+{
+	float center[3];
+	float half_height; /* of the cylinder part; the axis is +y */
+	float radius;
+	uint32_t world;
+	uint32_t reserved[2];
+} gpx_capsule_query;
+typedef struct gpx_overlap /* 32 B */
+{
+	float depth;
+	float normal[3];
+	uint32_t body;
+	uint32_t world;
+	uint32_t reserved[2];
+} gpx_overlap;
+int gpx_overlap_capsule_batch(gpx_world *w, const gpx_capsule_query *queries, uint64_t n, gpx_overlap *out);
+
 /* ---- device helpers for harnesses --------------------------------------------------------------------------------- */
 void *gpx_device_alloc(uint64_t bytes);
 void gpx_device_free(void *p);

@@ -1999,10 +1999,9 @@ static int ch_solid(const body_t *b)
 }
 
 /* deepest penetration of the capsule at x; id = triangle index or ORC_STATIC_BODY_BASE-less body id + 0x80000000 */
-static float ch_deepest(const orc_world *w, v3 x, v3 *n_out, uint32_t *hit_body)
+static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_out, uint32_t *hit_body)
 {
-	const v3 p0 = V(x.x, x.y - w->ch_hh, x.z), p1 = V(x.x, x.y + w->ch_hh, x.z);
-	const float r = w->ch_r;
+	const v3 p0 = V(x.x, x.y - hh, x.z), p1 = V(x.x, x.y + hh, x.z);
 	float best = 0.0f;
 	uint32_t best_id = 0xFFFFFFFFu;
 	for (uint32_t t = 0; t < w->ntris; t++)
@@ -2059,6 +2058,29 @@ static float ch_deepest(const orc_world *w, v3 x, v3 *n_out, uint32_t *hit_body)
 		}
 	}
 	return best;
+}
+
+static float ch_deepest(const orc_world *w, v3 x, v3 *n_out, uint32_t *hit_body)
+{
+	return capsule_deepest(w, x, w->ch_hh, w->ch_r, n_out, hit_body);
+}
+
+/* the same query for a caller's own upright capsule (gpx_overlap_capsule_batch): depth 0 and ORC_INVALID when free */
+float orc_overlap_capsule(const orc_world *w, const float center[3], float half_height, float radius, float normal[3],
+						  uint32_t *body)
+{
+	v3 n = V(0, 1, 0);
+	uint32_t hb = ORC_INVALID;
+	float pen = capsule_deepest(w, V(center[0], center[1], center[2]), half_height, radius, &n, &hb);
+	if (!(pen > 0.0f))
+	{
+		pen = 0.0f;
+		n = V(0, 1, 0);
+		hb = ORC_INVALID;
+	}
+	normal[0] = n.x; normal[1] = n.y; normal[2] = n.z;
+	*body = hb;
+	return pen;
 }
 
 void orc_character_update(orc_world *w, float dt)

@@ -97,6 +97,8 @@ void orc_character_destroy(orc_world *w);
 void orc_character_set_velocity(orc_world *w, const float v[3]);
 void orc_character_set_position(orc_world *w, const float p[3]);
 void orc_character_update(orc_world *w, float dt);
+float orc_overlap_capsule(const orc_world *w, const float center[3], float half_height, float radius, float normal[3],
+						  uint32_t *body);
 void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body);
 /* closest-hit rays, brute force over every static triangle and every body */
 void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);

@@ -111,6 +111,8 @@ def lib():
     L.orc_body_set_position.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
     L.orc_body_set_ray_flags.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.orc_body_wake.argtypes = [C.c_void_p, C.c_uint32]
+    L.orc_overlap_capsule.restype = C.c_float
+    L.orc_overlap_capsule.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.orc_body_asleep.argtypes = [C.c_void_p, C.c_uint32]
     L.orc_body_asleep.restype = C.c_uint32
     L.orc_step.restype = C.c_int
@@ -182,6 +184,11 @@ class World:
 
     def set_position(self, bid: int, p):
         self.L.orc_body_set_position(self.h, bid, (C.c_float * 3)(*p))
+
+    def overlap_capsule(self, center, half_height, radius):
+        n, b = (C.c_float * 3)(), C.c_uint32()
+        d = self.L.orc_overlap_capsule(self.h, (C.c_float * 3)(*[float(v) for v in center]), half_height, radius, n, C.byref(b))
+        return np.float32(d), np.array(list(n), np.float32), b.value
 
     def wake(self, bid: int):
         self.L.orc_body_wake(self.h, bid)

@@ -115,3 +115,38 @@ def test_characters_of_an_ensemble_are_independent(gpx, orc, scenes):
         pg, vg, gg, bg = g.character_get(world=wi)
         po, vo, go, bo = o.character_get()
         assert np.array_equal(pg.view(np.uint32), po.view(np.uint32)) and (gg, bg) == (go, bo), f"world {wi}"
+
+
+def test_batched_capsule_overlap_queries_match_the_oracle(gpx, orc, scenes):
+    """gpx_overlap_capsule_batch: the collide-shape query of the character controller for arbitrary upright capsules —
+    4096 of them scattered through stacked.gmap and a few bodies, depth / normal / body bit-identical to the oracle."""
+    g, (o,) = _pair(gpx, orc, scenes, cap=8)
+    descs = [dict(position=(1.0, -1.3, -1.5), motion_type=0, layer=0),
+             dict(position=(-0.5, -1.0, 0.5), half_extents=(0.3, 0.5, 0.2), rotation=(0.0, 0.38268343, 0.0, 0.92387953)),
+             dict(shape=2, half_extents=(0.35, 0, 0), position=(0.0, -1.1, -2.5)),
+             dict(position=(0.5, -1.25, 1.0), half_extents=(0.25, 0.25, 0.25), motion_type=0, layer=3, is_sensor=1)]   # ignored
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    rng = np.random.default_rng(5)
+    n = 4096
+    q = np.zeros(n, gpx.CAPSULE_DTYPE)
+    q["center"] = rng.uniform((-4.5, -1.9, -4.5), (4.5, 0.5, 4.5), (n, 3)).astype(np.float32)
+    q["half_height"] = rng.uniform(0.0, 0.4, n).astype(np.float32)
+    q["radius"] = rng.uniform(0.05, 0.4, n).astype(np.float32)
+    q[:8]["center"] = [(1.0, -1.3, -1.5), (0.0, -1.1, -2.5), (-0.5, -1.0, 0.5), (0.5, -1.25, 1.0),
+                       (0.0, 50.0, 0.0), (0.0, -1.45, 0.0), (1.0, -0.85, -1.5), (0.0, -1.05, -1.5)]
+    q[:8]["half_height"] = 0.0
+    q[:8]["radius"] = 0.1
+    out = g.overlap_capsules(q)
+    hits = 0
+    for i in range(n):
+        d, nrm, body = o.overlap_capsule(q["center"][i], float(q["half_height"][i]), float(q["radius"][i]))
+        assert out["body"][i] == body, f"query {i}: body {out['body'][i]:#x} vs {body:#x}"
+        assert np.array([out["depth"][i]], np.float32).view(np.uint32)[0] == np.array([d], np.float32).view(np.uint32)[0], f"query {i}: depth"
+        assert np.array_equal(out["normal"][i].view(np.uint32), nrm.view(np.uint32)), f"query {i}: normal"
+        hits += body != 0xFFFFFFFF
+    assert n // 10 < hits < n                                      # a real mix of touching and free capsules
+    assert out["body"][0] == 0 and out["body"][1] == 2 and out["body"][2] == 1      # inside the crate, the sphere, the turned box
+    assert out["body"][4] == gpx.INVALID_BODY and out["depth"][4] == 0.0             # far above everything
+    assert out["body"][5] >= gpx.STATIC_BODY_BASE and abs(out["normal"][5][1] - 1.0) < 1e-6   # on the floor: pushed up
+    assert (out["body"] != 3).all()                                                  # the sensor is never reported
