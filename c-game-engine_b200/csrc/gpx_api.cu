@@ -1052,7 +1052,7 @@ static int char_upload(gpx_world *w, uint32_t world)
 
 int gpx_character_create(gpx_world *w, uint32_t world, const gpx_character_desc *d)
 {
-	if (!w || !d || world >= w->W || w->wide) return GPX_ERR_INVALID_ARG;
+	if (!w || !d || world >= w->W) return GPX_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	if (!w->d_ch)
@@ -1145,10 +1145,11 @@ int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out)
 
 int gpx_events_enable(gpx_world *w, int enable)
 {
-	if (!w || w->wide) return GPX_ERR_INVALID_ARG;  // the wide-world path does not report contact events yet
+	if (!w) return GPX_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	if (w->wide) return wide_events_enable(w, enable != 0);
 	if (enable && !w->d_ev_out)
 	{
 		const size_t nm = (size_t)w->W * (w->cap_m + CHARACTER_MAX_CONTACTS);
@@ -1174,6 +1175,27 @@ int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uin
 	std::lock_guard<std::mutex> lk(w->mu);
 	if (!w->d_ev_out) return GPX_ERR_INVALID_ARG;
 	cudaSetDevice(w->device);
+	if (w->wide)
+	{
+		// one world: fetch the count, then only that many records
+		uint32_t n = 0;
+		GPX_CUDA(cudaMemcpyAsync(&n, w->d_ev_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+		GPX_CUDA(cudaStreamSynchronize(w->stream));
+		const uint32_t cap_ev = 2u * wide_event_capacity(w);
+		if (n > cap_ev) n = cap_ev;
+		w->h_ev_out.resize(n);
+		if (n) GPX_CUDA(cudaMemcpyAsync(w->h_ev_out.data(), w->d_ev_out, sizeof(uint4) * n, cudaMemcpyDeviceToHost, w->stream));
+		GPX_CUDA(cudaStreamSynchronize(w->stream));
+		for (uint32_t k = 0; k < n && k < capacity; k++)
+		{
+			out[k].world = 0;
+			out[k].body_a = w->h_ev_out[k].x;
+			out[k].body_b = w->h_ev_out[k].y;
+			out[k].kind = w->h_ev_out[k].z;
+		}
+		*count = n;
+		return n > capacity ? GPX_ERR_CAPACITY : GPX_OK;
+	}
 	const size_t per = 2u * ((size_t)w->cap_m + CHARACTER_MAX_CONTACTS);
 	w->h_ev_count.resize(w->W);
 	w->h_ev_out.resize((size_t)w->W * per);

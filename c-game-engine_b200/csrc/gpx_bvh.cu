@@ -259,6 +259,13 @@ __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned lo
 	for (uint32_t i = 0; i < RADIX_ITEMS; i++) out[wcnt[w][(uint32_t)(key[i] >> shift) & 255u] + local[i]] = key[i];
 }
 
+// In-place exclusive prefix sum of `n` counters (one block; the radix sort's scan).
+void exclusive_scan_u32(uint32_t *d, uint32_t n, cudaStream_t st)
+{
+	k_radix_scan<<<1, 1024, 0, st>>>(d, n);
+	count_launch();
+}
+
 // Ascending stable sort of bits [first_bit, 64) of `n` keys (n a multiple of 1024); bits below first_bit keep their
 // input order.  `tmp` holds n keys, `ghist` 256 * n / 1024 counters.  The result ends in `d_keys`.
 void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_t *ghist, uint32_t n, uint32_t first_bit,

@@ -174,6 +174,7 @@ namespace gpx {
 // gpx_bvh.cu
 int build_static(gpx_world *w);
 void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t st);
+void exclusive_scan_u32(uint32_t *d, uint32_t n, cudaStream_t st);
 void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_t *ghist, uint32_t n, uint32_t first_bit,
 					cudaStream_t st);
 uint32_t next_pow2(uint32_t v);
@@ -182,6 +183,8 @@ struct WideDevice;
 int wide_create(gpx_world *w);
 void wide_destroy(gpx_world *w);
 int launch_wide_tick(gpx_world *w, float dt, int substeps);
+int wide_events_enable(gpx_world *w, bool enable);
+uint32_t wide_event_capacity(const gpx_world *w);
 int wide_counters(gpx_world *w, uint32_t *out8);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);

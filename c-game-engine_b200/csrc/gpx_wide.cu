@@ -32,6 +32,7 @@
 // result is a pure function of the contact set.  Islands do not share dynamic bodies either, and the colouring of a
 // manifold depends only on its own island, so solving an island inside a warp gives the bits the grid-wide phases give.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "gpx_solver.cuh"
 
@@ -51,6 +52,8 @@ constexpr uint32_t SINGLE_BLOCK_MAX = 4096;  // manifolds of large islands up to
 constexpr uint32_t ISLAND_MAX = 32;      // manifolds of an island solved inside one warp (one per lane)
 constexpr uint32_t ISLAND_WARPS = 4;     // warps (islands) per block of kw_island
 constexpr uint32_t ROOT_SMALL = 0x80000000u;
+constexpr int SENSOR_COLOUR = -0x40000000;  // a touching pair with a sensor in it: a contact event, never solved (far from the
+                                           // -4 - colour codes kw_island leaves behind)
 
 // Everything a velocity phase needs about one manifold, in colour order: the phases stream these records (coalesced)
 // instead of chasing list -> manifold -> bodies -> parked constants.
@@ -87,6 +90,10 @@ struct WideDevice
 	uint32_t *parent = nullptr, *root_of = nullptr, *isl_cnt = nullptr, *isl_off = nullptr, *isl_cur = nullptr;
 	uint32_t *isl_man = nullptr, *big_list = nullptr;
 	unsigned char *can_sleep = nullptr;  // per island root: every body of the island is a sleep candidate
+	// contact events (gpx_events_enable): sorted keys of the touching pairs, scratch for the diff against the last tick
+	uint32_t n_ev = 0;
+	unsigned long long *ev_keys = nullptr, *ev_tmp = nullptr, *ev_cur = nullptr;
+	uint32_t *ev_hist = nullptr, *ev_flag = nullptr, *ev_pos = nullptr, *ev_ncur = nullptr;
 	int coop_grid_colour = 0, coop_grid_solve = 0;
 };
 
@@ -110,6 +117,7 @@ struct WideArgs
 	uint4 *cand;
 	StaticView sv;
 	uint32_t nb, n_pad, cap_m, hmask;
+	uint32_t isl_max;  // islands up to this many manifolds are solved inside a warp (ISLAND_MAX; 0 sends everything to the phased kernels)
 	uint32_t vel_steps, pos_steps;
 	float gx, gy, gz, h;
 	int first, last;
@@ -271,7 +279,6 @@ __device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p
 		!(((fp & BF_KIN_MOVING) && (fq & BF_ASLEEP)) || ((fq & BF_KIN_MOVING) && (fp & BF_ASLEEP))))
 		return;
 	if (!layers_collide(layer_of(fp), layer_of(fq))) return;
-	if ((fp & BF_SENSOR) || (fq & BF_SENSOR)) return;  // sensor overlaps are events, not contacts (not reported by this path yet)
 	const bool p_first = ip < iq;
 	const v3 alo = p_first ? V(lo_p) : V(lo_q), ahi = p_first ? V(hi_p) : V(hi_q);
 	const v3 blo = p_first ? V(lo_q) : V(lo_p), bhi = p_first ? V(hi_q) : V(hi_p);
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(NARROW_T) kw_pairs(WideArgs a)
 	SMan &m = a.man[k];
 	pair_contact(a.bodies[m.a], a.bodies[m.b], scratch[threadIdx.x], m);
 	const uint32_t fa = a.bodies[m.a].flags, fb = a.bodies[m.b].flags;
-	if (((fa | fb) & BF_ASLEEP) && m.np > 0)
+	if (((fa | fb) & BF_ASLEEP) && m.np > 0 && !((fa | fb) & BF_SENSOR))
 	{
 		// a contact with an active body wakes a sleeper (applied by kw_finish: awake from the next sub-step on)
 		if ((fa & BF_ASLEEP) && is_active_body(fb)) atomicOr(&a.bodies[m.a].flags, BF_WAKE_MARK);
@@ -443,6 +450,11 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 		m.colour = -2;
 		return;
 	}
+	if (m.b < STATIC_BODY_BASE && ((a.bodies[m.a].flags | a.bodies[m.b].flags) & BF_SENSOR))
+	{
+		m.colour = SENSOR_COLOUR;  // sensor overlaps are events, not contacts
+		return;
+	}
 	// warm start: previous manifolds of the same body pair, in creation order (ordinal 0, 1, ...)
 	for (uint32_t o = 0; o < (uint32_t)MAX_SLOTS; o++)
 	{
@@ -499,7 +511,7 @@ __global__ void __launch_bounds__(WT) kw_isl_count(WideArgs a)
 	const uint32_t n = min(a.cnt[WC_NMAN], a.cap_m);
 	if (mi >= n) return;
 	const SMan &m = a.man[mi];
-	if (m.np == 0) return;
+	if (m.np == 0 || m.colour == SENSOR_COLOUR) return;
 	const uint32_t r = isl_find(a.parent, man_island_body(a, m));
 	a.pending[mi] = (int)r;
 	atomicAdd(&a.isl_cnt[r], 1u);
@@ -521,11 +533,11 @@ __global__ void __launch_bounds__(WT) kw_isl_place(WideArgs a)
 		if ((f & BF_ALIVE) && is_dynamic(f) && a.adj_n[i] > 0)
 		{
 			r = isl_find(a.parent, i);
-			small = a.isl_cnt[r] <= ISLAND_MAX;
+			small = a.isl_cnt[r] <= a.isl_max;
 		}
 		a.root_of[i] = small ? (r | ROOT_SMALL) : r;
 		c = a.isl_cnt[i];  // non-zero only at roots
-		if (c > ISLAND_MAX) c = 0;
+		if (c > a.isl_max) c = 0;
 	}
 	scnt[threadIdx.x] = c;
 	__syncthreads();
@@ -557,10 +569,10 @@ __global__ void __launch_bounds__(WT) kw_isl_fill(WideArgs a)
 	if (mi < n)
 	{
 		SMan &m = a.man[mi];
-		if (m.np > 0)
+		if (m.np > 0 && m.colour != SENSOR_COLOUR)
 		{
 			const uint32_t r = (uint32_t)a.pending[mi];
-			if (a.isl_cnt[r] <= ISLAND_MAX)
+			if (a.isl_cnt[r] <= a.isl_max)
 			{
 				a.isl_man[a.isl_off[r] + atomicAdd(&a.isl_cur[r], 1u)] = mi;
 				m.colour = -3;  // not the cooperative kernels' business
@@ -1052,7 +1064,7 @@ __global__ void __launch_bounds__(WT) kw_finish(WideArgs a)
 	if (t < n)
 	{
 		const SMan &m = a.man[t];
-		if (m.np > 0)
+		if (m.np > 0 && m.colour != SENSOR_COLOUR)
 		{
 			const unsigned long long key = man_key(m.a, m.b, a.ord[t]);
 			uint32_t s = key_slot(key, a.hmask);
@@ -1105,7 +1117,7 @@ __global__ void __launch_bounds__(WT) kw_sleep_link(WideArgs a)
 	const uint32_t mi = blockIdx.x * WT + threadIdx.x;
 	if (mi >= min(a.cnt[WC_NMAN], a.cap_m)) return;
 	const SMan &m = a.man[mi];
-	if (m.np == 0 || m.b >= STATIC_BODY_BASE) return;
+	if (m.np == 0 || m.b >= STATIC_BODY_BASE || m.colour == SENSOR_COLOUR) return;
 	if (is_dynamic(a.bodies[m.a].flags) && is_dynamic(a.bodies[m.b].flags)) isl_unite(a.parent, m.a, m.b);
 }
 
@@ -1127,6 +1139,106 @@ __global__ void __launch_bounds__(WT) kw_sleep_apply(WideArgs a, const unsigned 
 	a.bs.flags[i] = (f | BF_ASLEEP) & ~(BF_KIN_MOVING | BF_WAKE_MARK);
 	a.bs.lin[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	a.bs.ang[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+
+// ---- contact events of a wide world (gpx_events_enable), once per tick: the keys (a << 32 | b) of every touching pair
+// of the last sub-step — solver manifolds, sensor overlaps, the character's contacts — are sorted and made unique, then
+// compared with the previous tick's list by binary search.  Output order as in the ensemble kernel: added and
+// persisted pairs sorted by key, then the removed ones sorted by key.
+struct EvArgs
+{
+	const SMan *man;
+	const uint32_t *cnt;
+	uint32_t cap_m, n_ev;
+	const unsigned long long *ch_keys;
+	const uint32_t *ch_nkeys;
+	unsigned long long *keys, *cur, *prev;
+	uint32_t *flag, *pos, *ncur, *nprev, *count;
+	uint4 *out;
+};
+
+__global__ void __launch_bounds__(WT) kw_ev_keys(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	unsigned long long key = ~0ull;
+	if (i < e.cap_m)
+	{
+		if (i < min(e.cnt[WC_NMAN], e.cap_m) && e.man[i].np > 0) key = ((unsigned long long)e.man[i].a << 32) | e.man[i].b;
+	}
+	else if (e.ch_keys && i - e.cap_m < min(e.ch_nkeys[0], (uint32_t)CHARACTER_MAX_CONTACTS))
+		key = e.ch_keys[i - e.cap_m];
+	e.keys[i] = key;
+}
+
+__global__ void __launch_bounds__(WT) kw_ev_unique(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	const unsigned long long k = e.keys[i];
+	const uint32_t f = (k != ~0ull && (i == 0 || e.keys[i - 1] != k)) ? 1u : 0u;
+	e.flag[i] = f;
+	e.pos[i] = f;
+}
+
+__global__ void __launch_bounds__(WT) kw_ev_compact(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	if (e.flag[i]) e.cur[e.pos[i]] = e.keys[i];
+	if (i == e.n_ev - 1) e.ncur[0] = e.pos[i] + e.flag[i];
+}
+
+__device__ __forceinline__ bool ev_contains(const unsigned long long *s, uint32_t n, unsigned long long k)
+{
+	uint32_t lo = 0, hi = n;
+	while (lo < hi)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (s[mid] < k) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo < n && s[lo] == k;
+}
+
+// pass 0: added / persisted records, and which previous keys are gone (flag for the second compaction)
+__global__ void __launch_bounds__(WT) kw_ev_diff(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	const uint32_t ncur = e.ncur[0], nprev = e.nprev[0];
+	if (i < ncur)
+	{
+		const unsigned long long k = e.cur[i];
+		e.out[i] = make_uint4((uint32_t)(k >> 32), (uint32_t)(k & 0xFFFFFFFFull), ev_contains(e.prev, nprev, k) ? 2u : 1u, 0u);
+	}
+	const uint32_t gone = (i < nprev && !ev_contains(e.cur, ncur, e.prev[i])) ? 1u : 0u;
+	e.flag[i] = gone;
+	e.pos[i] = gone;
+}
+
+__global__ void __launch_bounds__(WT) kw_ev_removed(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	const uint32_t ncur = e.ncur[0];
+	if (e.flag[i])
+	{
+		const unsigned long long k = e.prev[i];
+		e.out[ncur + e.pos[i]] = make_uint4((uint32_t)(k >> 32), (uint32_t)(k & 0xFFFFFFFFull), 3u, 0u);
+	}
+	if (i == e.n_ev - 1) e.count[0] = ncur + e.pos[i] + e.flag[i];
+}
+
+// the current list becomes the previous one (after kw_ev_removed has read the old one)
+__global__ void __launch_bounds__(WT) kw_ev_roll(EvArgs e)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	if (i >= e.n_ev) return;
+	const uint32_t ncur = e.ncur[0];
+	if (i < ncur) e.prev[i] = e.cur[i];
+	if (i == 0) e.nprev[0] = ncur;
 }
 
 // ---------------------------------------------------------------------------------------------------- host
@@ -1182,8 +1294,78 @@ void wide_destroy(gpx_world *w)
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
 	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->keys_tmp); cudaFree(d->sort_hist); cudaFree(d->can_sleep);
+	cudaFree(d->ev_keys); cudaFree(d->ev_tmp); cudaFree(d->ev_cur); cudaFree(d->ev_hist); cudaFree(d->ev_flag); cudaFree(d->ev_pos);
+	cudaFree(d->ev_ncur);
 	delete d;
 	w->wide = nullptr;
+}
+
+uint32_t wide_event_capacity(const gpx_world *w) { return w->wide ? w->wide->n_ev : 0u; }
+
+int wide_events_enable(gpx_world *w, bool enable)
+{
+	WideDevice *d = w->wide;
+	if (enable && !d->ev_keys)
+	{
+		d->n_ev = ((d->cap_m + CHARACTER_MAX_CONTACTS + 1023u) / 1024u) * 1024u;
+		const bool ok = walloc(&d->ev_keys, d->n_ev) && walloc(&d->ev_tmp, d->n_ev) && walloc(&d->ev_cur, d->n_ev) &&
+						walloc(&d->ev_hist, (size_t)256 * (d->n_ev / 1024u + 1u)) && walloc(&d->ev_flag, d->n_ev) &&
+						walloc(&d->ev_pos, d->n_ev) && walloc(&d->ev_ncur, 1) && walloc(&w->d_ev_prev, d->n_ev) &&
+						walloc(&w->d_ev_nprev, 1) && walloc(&w->d_ev_count, 1) && walloc(&w->d_ev_out, 2 * (size_t)d->n_ev);
+		if (!ok)
+		{
+			set_error("wide_events_enable", cudaGetLastError());
+			return GPX_ERR_CUDA;
+		}
+	}
+	else if (!enable && d->ev_keys)
+	{
+		cudaFree(d->ev_keys); cudaFree(d->ev_tmp); cudaFree(d->ev_cur); cudaFree(d->ev_hist); cudaFree(d->ev_flag);
+		cudaFree(d->ev_pos); cudaFree(d->ev_ncur);
+		cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
+		d->ev_keys = d->ev_tmp = d->ev_cur = nullptr;
+		d->ev_hist = d->ev_flag = d->ev_pos = d->ev_ncur = nullptr;
+		w->d_ev_prev = nullptr;
+		w->d_ev_nprev = w->d_ev_count = nullptr;
+		w->d_ev_out = nullptr;
+	}
+	return GPX_OK;
+}
+
+static int wide_events(gpx_world *w, const SMan *man)
+{
+	WideDevice *d = w->wide;
+	cudaStream_t st = w->stream;
+	EvArgs e;
+	e.man = man;
+	e.cnt = d->counters;
+	e.cap_m = d->cap_m;
+	e.n_ev = d->n_ev;
+	e.ch_keys = w->d_ch_keys;
+	e.ch_nkeys = w->d_ch_nkeys;
+	e.keys = d->ev_keys;
+	e.cur = d->ev_cur;
+	e.prev = w->d_ev_prev;
+	e.flag = d->ev_flag;
+	e.pos = d->ev_pos;
+	e.ncur = d->ev_ncur;
+	e.nprev = w->d_ev_nprev;
+	e.count = w->d_ev_count;
+	e.out = w->d_ev_out;
+	const uint32_t g = d->n_ev / WT;
+	kw_ev_keys<<<g, WT, 0, st>>>(e);
+	count_launch();
+	radix_sort_u64(d->ev_keys, d->ev_tmp, d->ev_hist, d->n_ev, 0u, st);
+	kw_ev_unique<<<g, WT, 0, st>>>(e);
+	exclusive_scan_u32(d->ev_pos, d->n_ev, st);
+	kw_ev_compact<<<g, WT, 0, st>>>(e);
+	kw_ev_diff<<<g, WT, 0, st>>>(e);
+	exclusive_scan_u32(d->ev_pos, d->n_ev, st);
+	kw_ev_removed<<<g, WT, 0, st>>>(e);
+	kw_ev_roll<<<g, WT, 0, st>>>(e);
+	count_launch(5);
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
 }
 
 static int coop_launch(const void *fn, int grid, WideArgs &a, cudaStream_t st, size_t smem = 0)
@@ -1237,6 +1419,7 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.n_pad = d->n_pad;
 	a.cap_m = d->cap_m;
 	a.hmask = d->hsize - 1u;
+	a.isl_max = getenv("GPX_WIDE_NO_ISLANDS") ? 0u : ISLAND_MAX;
 	a.vel_steps = w->cfg.velocity_steps ? w->cfg.velocity_steps : 10u;
 	a.pos_steps = w->cfg.position_steps ? w->cfg.position_steps : 2u;
 	a.gx = w->cfg.gravity[0];
@@ -1296,6 +1479,11 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		kw_sleep_test<<<gn, WT, 0, st>>>(a, d->can_sleep, dt);
 		kw_sleep_apply<<<gn, WT, 0, st>>>(a, d->can_sleep);
 		count_launch(4);
+	}
+	if (w->d_ev_out)
+	{
+		int rc = wide_events(w, d->man[d->cur ^ 1]);
+		if (rc != GPX_OK) return rc;
 	}
 	// merge the error word into the world's error slot (d_err[0], d_err[1])
 	GPX_CUDA(cudaMemcpyAsync(w->d_err, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

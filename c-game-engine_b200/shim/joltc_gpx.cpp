@@ -332,8 +332,6 @@ JPH_PhysicsSystem *JPH_PhysicsSystem_Create(const JPH_PhysicsSystemSettings *s)
 	auto *sys = new JPH_PhysicsSystem;
 	const char *env = getenv("GPX_MAX_BODIES");
 	sys->max_bodies = env ? (uint32_t)atoi(env) : (s->maxBodies ? s->maxBodies : 64u);
-	if (sys->max_bodies > 64u)
-		complain("more than 64 bodies selects the wide-world kernels: no contact events, hence no character callbacks");
 	// The engine's MAX_CONTACT_CONSTRAINTS (16384) is a pool bound, not a need: the default sizing (3 per body) applies
 	// unless the limit is smaller.
 	sys->max_manifolds = 0;

@@ -335,7 +335,8 @@ typedef struct gpx_contact_event
 	uint32_t body_b;
 	uint32_t kind;   /* gpx_event_kind */
 } gpx_contact_event;
-/* Events cost one pass per tick on the device and are off by default (ensemble worlds only, <= 64 bodies per world). */
+/* Events cost one pass per tick on the device and are off by default.  (A wide world sorts its touching pairs once per
+ * tick for them.) */
 int gpx_events_enable(gpx_world *w, int enable);
 /* Waits for the stream and returns the events of the last completed tick; *count is the number available. */
 int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uint64_t *count);

@@ -70,10 +70,57 @@ def test_events_per_world_in_an_ensemble(gpx, orc, scenes):
     assert len(eg) == W * 8 and (eg["kind"] == 2).all()     # settled column: 8 persisted contacts per world
 
 
-def test_events_must_be_enabled_and_are_refused_for_wide_worlds(gpx):
+def test_events_must_be_enabled(gpx):
     g = gpx.World(worlds=1, max_bodies=8)
     with pytest.raises(gpx.GpxError):
         g.poll_events()
-    w = gpx.World(worlds=1, max_bodies=128)
-    with pytest.raises(gpx.GpxError):
-        w.enable_events()
+
+
+def test_wide_world_events_sensors_and_character_contacts(gpx, orc, scenes):
+    """The wide-world path (> 64 bodies): touching pairs are sorted and diffed once per tick.  A lattice settling on the
+    shipped map, a box falling through a sensor, the player capsule walking into the columns: event streams, bodies and
+    character state identical to the oracle's wide mode."""
+    n = 80
+    g = gpx.World(worlds=1, max_bodies=n)
+    o = orc.World(n)
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    descs = []
+    for ix in range(5):
+        for iz in range(4):
+            for k in range(3):
+                descs.append(dict(position=(-1.6 + 0.8 * ix, -1.25 + 0.43 * k, -2.6 + 0.7 * iz)))
+    descs.append(dict(position=(0.3, 0.6, 0.8)))                                                               # 60: falls ...
+    descs.append(dict(half_extents=(0.5, 0.15, 0.5), position=(0.3, -0.2, 0.8), layer=3, motion_type=0, is_sensor=1))  # 61: ... through this
+    descs.append(dict(half_extents=(0.25, 0.25, 0.25), position=(0.0, -1.25, 1.6), layer=3, motion_type=0, is_sensor=1))  # 62: a coin
+    for d in descs:
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    g.character_create((0.0, -0.9, 2.6))
+    o.character_create((0.0, -0.9, 2.6))
+    seen = {1: set(), 2: set(), 3: set()}
+    CH = 0x3FFFFF
+    for tick in range(1, 151):
+        for side in (g, o):
+            p, vel, ground, _ = side.character_get()
+            vy = 0.0 if ground == 0 else float(vel[1]) + (-9.81 / 60.0)
+            side.character_set_velocity((0.0, vy, -1.5 if tick > 20 else 0.0))
+            side.character_update()
+        assert g.step() == 0 and o.step() == 0
+        eg = g.poll_events()
+        got = np.stack([eg["body_a"], eg["body_b"], eg["kind"]], axis=1) if len(eg) else np.zeros((0, 3), np.uint32)
+        eo = o.events()
+        assert np.array_equal(got, eo), f"tick {tick}: {len(got)} vs {len(eo)} events"
+        for a, b, k in got:
+            seen[int(k)].add((int(a), int(b)))
+    assert (60, 61) in seen[1] and (60, 61) in seen[3]                       # through the sensor
+    assert (62, CH) in seen[1] and (62, CH) in seen[3]                       # the character crossed the coin
+    assert any(a == CH and b >= gpx.STATIC_BODY_BASE for a, b in seen[2])    # and stands on the map
+    assert any(b == CH and a < 60 for a, b in seen[1])                       # and reached the columns
+    assert len(seen[2]) > 60
+    assert g.sync() == 0
+    assert np.array_equal(g.transforms()[0, :63].view(np.uint32), o.state(63)[0].view(np.uint32))
+    pg, po = g.character_get(), o.character_get()
+    assert np.array_equal(pg[0].view(np.uint32), po[0].view(np.uint32)) and pg[2:] == po[2:]

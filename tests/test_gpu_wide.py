@@ -189,3 +189,33 @@ def test_full_size_100k_boxes_properties(gpx, scenes):
     assert np.isfinite(x1).all()
     # columns keep their footprint: nothing was pushed sideways by more than a few centimetres
     assert np.abs(x1[:, [0, 2]] - pos[:, [0, 2]]).max() < 0.1
+
+
+def test_islands_are_a_pure_rescheduling(gpx, scenes, monkeypatch):
+    """Solving small islands inside warps must not change a single bit against sending every manifold through the
+    grid-wide colour phases (GPX_WIDE_NO_ISLANDS=1, a debugging switch read at every tick)."""
+    def run(no_islands):
+        if no_islands:
+            monkeypatch.setenv("GPX_WIDE_NO_ISLANDS", "1")
+        else:
+            monkeypatch.delenv("GPX_WIDE_NO_ISLANDS", raising=False)
+        n = 80
+        g = gpx.World(worlds=1, max_bodies=n)
+        for pos, tris in scenes.load_static("stacked"):
+            g.add_mesh(pos, tris)
+        g.commit()
+        rng = np.random.default_rng(2)
+        for ix in range(5):
+            for iz in range(4):
+                for k in range(3):
+                    g.create(gpx.body_desc(position=(-1.6 + 0.8 * ix, -1.25 + 0.43 * k, -2.6 + 0.7 * iz),
+                                           angular_velocity=tuple(rng.uniform(-0.5, 0.5, 3))))
+        for _ in range(90):
+            assert g.step() == 0
+        assert g.sync() == 0
+        c = g.wide_counters()
+        return g.transforms()[0, :60].copy(), g.velocities()[0, :60].copy(), c
+    xa, va, ca = run(False)
+    xb, vb, cb = run(True)
+    assert ca["small_islands"] > 0 and cb["small_islands"] == 0
+    assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)) and np.array_equal(va.view(np.uint32), vb.view(np.uint32))
