@@ -41,10 +41,10 @@ def _scene_file(path, scenes):
     return meshes, boxes
 
 
-def _oracle_run(orc, scenes, meshes, boxes, ticks):
+def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
     """The driver's scene on the oracle, in the driver's call order.  Returns the lines the driver should print."""
     out = []
-    o = orc.World(64)
+    o = orc.World(max_bodies)
     o.character_create((-0.2, 0.0, -0.5))
     first_map = None
     for pos, tris in meshes:
@@ -135,14 +135,18 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks):
     return out, dict(coin=coin, door=door, boxes=box_ids, first_map=first_map)
 
 
-def test_engine_call_sequence_through_the_shim_matches_the_oracle(orc, scenes, tmp_path):
+@pytest.mark.parametrize("max_bodies", [64, 128], ids=["ensemble-kernel world", "wide-world kernels"])
+def test_engine_call_sequence_through_the_shim_matches_the_oracle(orc, scenes, tmp_path, max_bodies):
+    """The same engine-style run twice: in the default 64-slot world (the fused ensemble kernel) and, with
+    GPX_MAX_BODIES=128, in a wide world (sort-and-sweep, islands, per-tick event kernels) against the oracle's wide mode."""
     import shim_build
     driver = shim_build.build_driver()
     meshes, boxes = _scene_file(tmp_path / "scene.bin", scenes)
-    r = subprocess.run([driver, str(tmp_path / "scene.bin"), str(TICKS)], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, GPX_MAX_BODIES=str(max_bodies))
+    r = subprocess.run([driver, str(tmp_path / "scene.bin"), str(TICKS)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, f"driver exit {r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     got = r.stdout.strip().splitlines()
-    want, ids = _oracle_run(orc, scenes, meshes, boxes, TICKS)
+    want, ids = _oracle_run(orc, scenes, meshes, boxes, TICKS, max_bodies)
     for i, (g, w) in enumerate(zip(got, want)):
         assert g == w, f"line {i}: shim printed\n  {g}\noracle says\n  {w}"
     assert len(got) == len(want)
