@@ -204,6 +204,7 @@ struct Deepest
 	uint32_t id;
 	v3 n;
 	uint32_t body;
+	v3 cp;  // contact point on the thing hit
 };
 
 // Deepest penetration of the capsule centred at x (warp-cooperative; every lane returns the same result).
@@ -226,6 +227,7 @@ __device__ __forceinline__ Deepest ch_deepest(const CharArgs &a, uint32_t world,
 	best.id = 0xFFFFFFFFu;
 	best.n = V(0.0f, 1.0f, 0.0f);
 	best.body = GPX_INVALID_BODY;
+	best.cp = V(0.0f, 0.0f, 0.0f);
 	for (int c = lane; c < nc; c += 32)
 	{
 		const int leaf = cand_leaf[c];
@@ -245,6 +247,7 @@ __device__ __forceinline__ Deepest ch_deepest(const CharArgs &a, uint32_t world,
 			best.id = id;
 			best.n = n;
 			best.body = STATIC_BODY_BASE + __float_as_uint(TB.w);
+			best.cp = ct;
 		}
 	}
 	const uint32_t g0 = world * a.cap;
@@ -281,6 +284,7 @@ __device__ __forceinline__ Deepest ch_deepest(const CharArgs &a, uint32_t world,
 			best.id = id;
 			best.n = n;
 			best.body = i;
+			best.cp = cb;
 		}
 	}
 	// warp reduction: largest penetration, ties to the lowest id
@@ -292,16 +296,65 @@ __device__ __forceinline__ Deepest ch_deepest(const CharArgs &a, uint32_t world,
 		const float onx = __shfl_xor_sync(0xFFFFFFFFu, best.n.x, o), ony = __shfl_xor_sync(0xFFFFFFFFu, best.n.y, o),
 					onz = __shfl_xor_sync(0xFFFFFFFFu, best.n.z, o);
 		const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, best.body, o);
+		const float ocx = __shfl_xor_sync(0xFFFFFFFFu, best.cp.x, o), ocy = __shfl_xor_sync(0xFFFFFFFFu, best.cp.y, o),
+					ocz = __shfl_xor_sync(0xFFFFFFFFu, best.cp.z, o);
 		if (open > best.pen || (open == best.pen && oid < best.id))
 		{
 			best.pen = open;
 			best.id = oid;
 			best.n = V(onx, ony, onz);
 			best.body = ob;
+			best.cp = V(ocx, ocy, ocz);
 		}
 	}
 	__syncwarp();
 	return best;
+}
+
+// The character pushes the dynamic bodies it runs into (CharacterVirtual's contact impulse): the body should move away
+// at 0.9 of the closing speed plus 0.4 of the penetration per update, through its effective mass at the contact point,
+// capped by the character's strength (100 N) times dt; no push along gravity; the body wakes.  Every lane computes the
+// same values, lane 0 stores.  `n` points from the body to the character, `v` is the character's velocity.
+constexpr float CH_PUSH_DAMPING = 0.9f, CH_PUSH_PENETRATION = 0.4f, CH_MAX_STRENGTH = 100.0f;
+
+__device__ __forceinline__ void ch_push_body(const CharArgs &a, uint32_t g, v3 n, float pen, v3 cp, v3 v, float dt, int lane)
+{
+	uint32_t f = a.bs.flags[g];
+	if (((f >> BF_MOTION_SHIFT) & 3u) != GPX_MOTION_DYNAMIC || (f & BF_SENSOR)) return;
+	SBody B;
+	B.x = V(a.bs.pos[g]);
+	B.q = Q(a.bs.quat[g]);
+	B.v = V(a.bs.lin[g]);
+	B.w = V(a.bs.ang[g]);
+	const float4 p0 = a.bs.prop0[g];
+	B.inv_mass = p0.x;
+	B.inv_i = V(p0.y, p0.z, p0.w);
+	const v3 rB = cp - B.x;
+	const v3 vB = B.v + cross(B.w, rB);
+	const float dv = (-(dot(v - vB, n)) * CH_PUSH_DAMPING) + ((pen * CH_PUSH_PENETRATION) / dt);
+	if (!(dv > 0.0f)) return;
+	const bool woke = (f & BF_ASLEEP) != 0;
+	f &= ~BF_ASLEEP;  // AddImpulse activates
+	B.flags = f;
+	body_world_inertia(B);
+	const v3 jac = cross(rB, n);
+	const float inv_eff = dot(sym_mul(B.M, jac), jac) + B.im;
+	if (lane == 0 && woke)
+	{
+		a.bs.flags[g] = f;
+		a.bs.sleep_t[g] = -1.0f;
+	}
+	if (!(inv_eff > 0.0f)) return;
+	const float impulse = fminf(dv / inv_eff, CH_MAX_STRENGTH * dt);
+	v3 P = n * (-impulse);
+	if (P.y < 0.0f) P.y = 0.0f;
+	const v3 nv = B.v + mask_lin(dofs_of(f), P * B.im);
+	const v3 nw = B.w + sym_mul(B.M, cross(rB, P));
+	if (lane == 0)
+	{
+		a.bs.lin[g] = F4(nv, 0.0f);
+		a.bs.ang[g] = F4(nw, 0.0f);
+	}
 }
 
 __global__ void __launch_bounds__(128) k_character(CharArgs a)
@@ -323,6 +376,11 @@ __global__ void __launch_bounds__(128) k_character(CharArgs a)
 	{
 		const Deepest d = ch_deepest(a, world, x, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
 		if (!(d.pen > 0.0f)) break;
+		if (d.body < STATIC_BODY_BASE)
+		{
+			ch_push_body(a, world * a.cap + d.body, d.n, d.pen, d.cp, v, a.dt, lane);
+			__syncwarp();  // the next round reads the body's new velocity
+		}
 		x = x + (d.n * d.pen);
 		const float vn = dot(v, d.n);
 		if (vn < 0.0f) v = v - (d.n * vn);

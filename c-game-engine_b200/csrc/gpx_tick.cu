@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	PhaseClock pc;
 	pc.start(a.phase_cycles, lane);
 	const uint32_t g0 = world * cap;
-	bool any_active = false, any_asleep = false;
+	bool any_active = false;
 	// ---- load: HBM -> shared, lane = body, 16-byte vector loads
 	for (uint32_t i = lane; i < cap; i += TILE)
 	{
@@ -223,14 +223,13 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			f |= BF_KIN_MOVING;
 		b.flags = f;
 		if ((f & BF_ALIVE) && is_active_body(f)) any_active = true;
-		if ((f & BF_ALIVE) && (f & BF_ASLEEP)) any_asleep = true;
 	}
-	// A world in which everything sleeps (or nothing can move) has no tick to run: its state, contact cache included,
-	// stays as it is.  (With contact events on, the pass below still has to report the pairs as gone or persisting.)
+	// A world in which everything sleeps (or nothing can move) has no tick to run.  Its bodies stay as they are; the
+	// contact cache empties, as it would if the tick ran (sleepers generate no contacts), so a wake-up starts cold
+	// whether or not this shortcut was taken.  (With contact events on, the pass below still has to report the pairs.)
 	if (!a.ev_out && !tile.any(any_active))
 	{
-		// sleepers keep their cached contacts for the moment they wake; a world with nothing dynamic has none
-		if (!tile.any(any_asleep) && lane == 0) a.mc.count[world] = 0;
+		if (lane == 0) a.mc.count[world] = 0;
 		return;
 	}
 	const uint32_t m0 = world * cap_m;

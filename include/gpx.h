@@ -296,7 +296,7 @@ typedef struct gpx_character_desc /* JPH_CharacterVirtualSettings + JPH_CapsuleS
 	float half_height;   /* 0.2  (PlayerPhysics.c:176) */
 	float radius;        /* 0.25 */
 	float max_slope_deg; /* MAX_WALKABLE_SLOPE = 50 */
-	float mass;          /* 10; carried (the character does not push bodies yet) */
+	float mass;          /* 10; carried.  The push on dynamic bodies is limited by the character's strength (Jolt default 100 N) */
 	float position[3];
 } gpx_character_desc;
 typedef struct gpx_character_state
@@ -314,7 +314,8 @@ int gpx_character_destroy(gpx_world *w, uint32_t world);
 int gpx_character_set_linear_velocity(gpx_world *w, uint32_t world, const float v[3]);
 int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3]);
 /* JPH_CharacterVirtual_ExtendedUpdate (PlayerPhysics.c:447) for the character of every world: move by velocity * dt,
- * collide and slide against the map and the solid bodies, ground state, stick to the floor.  Call before gpx_step, as
+ * collide and slide against the map and the solid bodies (dynamic ones are pushed and woken), ground state, stick to the
+ * floor.  Call before gpx_step, as
  * MapFixedUpdate does (MapPhysics.c:74 then :105).  Asynchronous on the world's stream. */
 int gpx_character_update(gpx_world *w, float dt);
 /* Waits for the stream and reads the character back. */

@@ -1999,7 +1999,7 @@ static int ch_solid(const body_t *b)
 }
 
 /* deepest penetration of the capsule at x; id = triangle index or ORC_STATIC_BODY_BASE-less body id + 0x80000000 */
-static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_out, uint32_t *hit_body)
+static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_out, uint32_t *hit_body, v3 *cp_out)
 {
 	const v3 p0 = V(x.x, x.y - hh, x.z), p1 = V(x.x, x.y + hh, x.z);
 	float best = 0.0f;
@@ -2023,6 +2023,7 @@ static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_
 			best_id = t;
 			*n_out = n;
 			*hit_body = ORC_STATIC_BODY_BASE + T->body;
+			*cp_out = ct;
 		}
 	}
 	for (uint32_t i = 0; i < w->max_bodies; i++)
@@ -2055,6 +2056,7 @@ static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_
 			best_id = id;
 			*n_out = n;
 			*hit_body = i;
+			*cp_out = cb;
 		}
 	}
 	return best;
@@ -2062,7 +2064,34 @@ static float capsule_deepest(const orc_world *w, v3 x, float hh, float r, v3 *n_
 
 static float ch_deepest(const orc_world *w, v3 x, v3 *n_out, uint32_t *hit_body)
 {
-	return capsule_deepest(w, x, w->ch_hh, w->ch_r, n_out, hit_body);
+	v3 cp;
+	return capsule_deepest(w, x, w->ch_hh, w->ch_r, n_out, hit_body, &cp);
+}
+
+/* The character pushes the dynamic bodies it runs into (CharacterVirtual's contact impulse [upstream, restated from its
+ * documented behaviour]): it wants the body to move away at 0.9 of the closing speed plus 0.4 of the penetration per
+ * update, through the body's effective mass at the contact point, capped by the character's strength (100 N) times
+ * dt; no push along gravity.  `n` points from the body to the character, `v` is the character's velocity. */
+#define CH_PUSH_DAMPING 0.9f
+#define CH_PUSH_PENETRATION 0.4f
+#define CH_MAX_STRENGTH 100.0f
+static void ch_push_body(body_t *B, v3 n, float pen, v3 cp, v3 v, float dt)
+{
+	if (B->motion != ORC_MOTION_DYNAMIC || B->sensor) return;
+	const v3 rB = vsub(cp, B->x);
+	const v3 vB = vadd(B->v, vcross(B->w, rB));
+	const float dv = (-(vdot(vsub(v, vB), n)) * CH_PUSH_DAMPING) + ((pen * CH_PUSH_PENETRATION) / dt);
+	if (!(dv > 0.0f)) return;
+	if (B->asleep) wake_body(B); /* AddImpulse activates a sleeping body; an awake one keeps its sleep timer */
+	body_world_inertia(B);
+	const v3 jac = vcross(rB, n);
+	const float inv_eff = vdot(sym_mul(B->M, jac), jac) + B->im;
+	if (!(inv_eff > 0.0f)) return;
+	const float impulse = fminf(dv / inv_eff, CH_MAX_STRENGTH * dt);
+	v3 P = vscale(n, -impulse);
+	if (P.y < 0.0f) P.y = 0.0f;
+	B->v = vadd(B->v, mask_lin(B->dofs, vscale(P, B->im)));
+	B->w = vadd(B->w, sym_mul(B->M, vcross(rB, P)));
 }
 
 /* the same query for a caller's own upright capsule (gpx_overlap_capsule_batch): depth 0 and ORC_INVALID when free */
@@ -2071,7 +2100,8 @@ float orc_overlap_capsule(const orc_world *w, const float center[3], float half_
 {
 	v3 n = V(0, 1, 0);
 	uint32_t hb = ORC_INVALID;
-	float pen = capsule_deepest(w, V(center[0], center[1], center[2]), half_height, radius, &n, &hb);
+	v3 cp;
+	float pen = capsule_deepest(w, V(center[0], center[1], center[2]), half_height, radius, &n, &hb, &cp);
 	if (!(pen > 0.0f))
 	{
 		pen = 0.0f;
@@ -2092,10 +2122,11 @@ void orc_character_update(orc_world *w, float dt)
 	v3 ground_n = V(0, 1, 0);
 	for (int it = 0; it < CH_MAX_ITERS; it++)
 	{
-		v3 n;
+		v3 n, cp;
 		uint32_t hb;
-		float pen = ch_deepest(w, x, &n, &hb);
+		float pen = capsule_deepest(w, x, w->ch_hh, w->ch_r, &n, &hb, &cp);
 		if (!(pen > 0.0f)) break;
+		if (hb < ORC_STATIC_BODY_BASE) ch_push_body(&w->bodies[hb], n, pen, cp, v, dt);
 		x = vadd(x, vscale(n, pen));
 		float vn = vdot(v, n);
 		if (vn < 0.0f) v = vsub(v, vscale(n, vn));

@@ -66,7 +66,7 @@ def test_character_walk_matches_oracle_on_stacked_map(gpx, orc, scenes):
     p, v, ground, gb = g.character_get()
     assert ground == 0 and gb >= gpx.STATIC_BODY_BASE                    # standing on some sector's floor mesh
     assert any(a == 0x3FFFFF and b >= gpx.STATIC_BODY_BASE for a, b, k in seen)
-    # bodies keep matching too (the character does not push them)
+    # bodies keep matching too (the dynamic box gets pushed around by the character on both sides)
     assert np.array_equal(g.transforms()[0, :4].view(np.uint32), o.state(4)[0].view(np.uint32))
 
 
@@ -150,3 +150,30 @@ def test_batched_capsule_overlap_queries_match_the_oracle(gpx, orc, scenes):
     assert out["body"][4] == gpx.INVALID_BODY and out["depth"][4] == 0.0             # far above everything
     assert out["body"][5] >= gpx.STATIC_BODY_BASE and abs(out["normal"][5][1] - 1.0) < 1e-6   # on the floor: pushed up
     assert (out["body"] != 3).all()                                                  # the sensor is never reported
+
+
+def test_character_wakes_and_pushes_a_sleeping_box(gpx, orc, scenes):
+    """Walking into a dynamic body applies CharacterVirtual's contact impulse: the box (asleep by then) wakes, is shoved
+    along and tumbles; the character is held up by it.  Bodies, sleep states and the character match the oracle bit for bit."""
+    g, (o,) = _pair(gpx, orc, scenes)
+    d = dict(position=(1.0, -1.3, -1.5), allow_sleeping=1)
+    assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d)) == 0
+    g.character_create((0.0, -1.0, -1.5))
+    o.character_create((0.0, -1.0, -1.5))
+    x_box = []
+    for tick in range(1, 161):
+        for side in (g, o):
+            _move(side, (1.5, 0.0, 0.0) if tick > 60 else (0.0, 0.0, 0.0))
+            side.character_update()
+        assert g.step() == 0 and o.step() == 0
+        if tick == 60:
+            assert g.sleeping()[0, 0] and o.asleep(1)[0]
+        if tick % 10 == 0:
+            _same(g, o, f"tick {tick}")
+            xo, vo = o.state(1)
+            assert np.array_equal(g.transforms()[0, :1].view(np.uint32), xo.view(np.uint32)), f"tick {tick}: box differs"
+            assert np.array_equal(g.velocities()[0, :1].view(np.uint32), vo.view(np.uint32))
+            assert g.sleeping()[0, 0] == o.asleep(1)[0]
+        x_box.append(float(g.get_transform(0)[0]) if tick % 10 == 0 else (x_box[-1] if x_box else 1.0))
+    assert x_box[5] == 1.0                       # untouched while the character stands still
+    assert max(x_box) > 1.5                      # shoved more than half a metre along +x
