@@ -292,7 +292,28 @@ static __device__ __noinline__ int static_candidates(const StaticView &a, uint4 
 		const v3 qlo = V((lo.x - m) - CAND_FAT, (lo.y - m) - CAND_FAT, (lo.z - m) - CAND_FAT);
 		const v3 qhi = V((hi.x + m) + CAND_FAT, (hi.y + m) + CAND_FAT, (hi.z + m) + CAND_FAT);
 		bool fat_overflow = false;
-		const int nf = query_static(a.nodes, a.tris, a.n_nodes, qlo, qhi, 0.0f, cand_orig, cand_leaf, fat_overflow);
+		int nf = query_static(a.nodes, a.tris, a.n_nodes, qlo, qhi, 0.0f, cand_orig, cand_leaf, fat_overflow);
+		if (!fat_overflow)
+		{
+			// A triangle whose PLANE stays clear of the fat box cannot touch the body while the body stays inside it
+			// (the box-triangle test starts with exactly this axis): a sloping wall's box covers half a sector, its plane
+			// does not.  1 mm of slack keeps the filter on the safe side of the exact test's rounding.
+			const v3 fc = V(0.5f * (qlo.x + qhi.x), 0.5f * (qlo.y + qhi.y), 0.5f * (qlo.z + qhi.z));
+			const v3 fe = V(0.5f * (qhi.x - qlo.x), 0.5f * (qhi.y - qlo.y), 0.5f * (qhi.z - qlo.z));
+			int kept = 0;
+			for (int c = 0; c < nf; c++)
+			{
+				const int leaf = cand_leaf[c];
+				const float4 A = __ldg(&a.tris[4 * leaf + 0]), N = __ldg(&a.tris[4 * leaf + 3]);
+				const float s = ((fc.x - A.x) * N.x) + ((fc.y - A.y) * N.y) + ((fc.z - A.z) * N.z);
+				const float r = (fabsf(N.x) * fe.x) + (fabsf(N.y) * fe.y) + (fabsf(N.z) * fe.z);
+				if (fabsf(s) - r > m + 1.0e-3f) continue;
+				cand_orig[kept] = cand_orig[c];
+				cand_leaf[kept] = leaf;
+				kept++;
+			}
+			nf = kept;
+		}
 		if (fat_overflow)
 		{
 			__stcg(&rec[0], make_uint4(CAND_INVALID, 0u, 0u, 0u));
