@@ -564,16 +564,29 @@ static __device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
 	SBody &A = bodies[m.a];
 	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
 	const float zero_m[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-	body_world_inertia(A);
-	if (B) body_world_inertia(*B);
-	const float imb = B ? B->im : 0.0f;
-	const float *MB = B ? B->M : zero_m;
+	// The world inertia of the two bodies is refreshed when the first point needs a correction — at the orientation the
+	// manifold's pass starts with, as the restatement does up front; a manifold inside the slop (the usual case at
+	// rest) costs four separations and nothing else.  Nothing reads M between here and the next sub-step's refresh.
+	bool ready = false;
+	float imb = 0.0f;
+	const float *MB = zero_m;
 	for (int k = 0; k < m.np; k++)
 	{
 		v3 p1 = A.x + qrot(A.q, m.p1l[k]);
 		v3 p2 = B ? B->x + qrot(B->q, m.p2l[k]) : m.p2l[k];
 		float sep = dot(p2 - p1, m.n) + PENETRATION_SLOP;
 		if (sep >= 0.0f) continue;
+		if (!ready)
+		{
+			body_world_inertia(A);
+			if (B)
+			{
+				body_world_inertia(*B);
+				imb = B->im;
+				MB = B->M;
+			}
+			ready = true;
+		}
 		v3 mid = (p1 + p2) * 0.5f;
 		v3 r1 = mid - A.x, r2 = B ? mid - B->x : V(0.0f, 0.0f, 0.0f);
 		float e = eff_mass(A.im, A.M, imb, MB, r1, r2, m.n);
