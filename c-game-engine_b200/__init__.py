@@ -249,7 +249,7 @@ class World:
     """An ensemble of `worlds` independent world instances sharing one static map (gpx_world)."""
 
     def __init__(self, worlds=1, max_bodies=8, max_manifolds=0, gravity=(0.0, -9.81, 0.0), device=0,
-                 velocity_steps=0, position_steps=0):
+                 velocity_steps=0, position_steps=0, wide=False):
         L = lib()
         rc = L.gpx_init(device)
         if rc < 0:
@@ -263,6 +263,7 @@ class World:
         cfg.device = device
         cfg.velocity_steps = velocity_steps
         cfg.position_steps = position_steps
+        cfg.flags = 1 if wide else 0        # GPX_WORLD_WIDE
         self.L = L
         self.worlds = worlds
         self.max_bodies = max_bodies

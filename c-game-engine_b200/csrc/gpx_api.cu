@@ -236,8 +236,8 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 {
 	if (!cfg || cfg->worlds == 0 || cfg->max_bodies_per_world == 0) return nullptr;
 	// up to 64 bodies per world: ensembles (one tile of lanes per world, gpx_tick.cu).  More: ONE wide world (gpx_wide.cu)
-	const bool wide = cfg->max_bodies_per_world > 64;
-	if (wide && (cfg->worlds != 1 || cfg->max_bodies_per_world > (1u << 20))) return nullptr;
+	const bool wide = cfg->max_bodies_per_world > 64 || (cfg->flags & GPX_WORLD_WIDE);
+	if (wide && (uint64_t)cfg->worlds * cfg->max_bodies_per_world > (1ull << 20)) return nullptr;
 	if (cudaSetDevice(cfg->device) != cudaSuccess) return nullptr;
 	gpx_world *w = new gpx_world();
 	w->cfg = *cfg;
@@ -1149,6 +1149,7 @@ int gpx_events_enable(gpx_world *w, int enable)
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	if (w->wide && w->W != 1) return GPX_ERR_INVALID_ARG;  // a wide ENSEMBLE keeps no per-world event lists
 	if (w->wide) return wide_events_enable(w, enable != 0);
 	if (enable && !w->d_ev_out)
 	{

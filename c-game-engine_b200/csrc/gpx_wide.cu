@@ -117,6 +117,7 @@ struct WideArgs
 	uint4 *cand;
 	StaticView sv;
 	uint32_t nb, n_pad, cap_m, hmask;
+	uint32_t cap, rows_per_world;  // bodies per world; rows of the sweep each world owns (4096 for a single world)
 	uint32_t isl_max;  // islands up to this many manifolds are solved inside a warp (ISLAND_MAX; 0 sends everything to the phased kernels)
 	uint32_t vel_steps, pos_steps;
 	float gx, gy, gz, h;
@@ -233,10 +234,14 @@ __device__ __forceinline__ float row_thickness(const WideArgs &a)
 {
 	return (__uint_as_float(a.cnt[WC_MAXEXT_Z]) + (4.0f * SPECULATIVE_DISTANCE)) + 1.0e-3f;
 }
-__device__ __forceinline__ uint32_t row_of(float lo_z, float thickness)
+// Every world owns `rows` consecutive rows (all 4096 when there is one world); bodies beyond a world's slab range share its
+// first / last row, which costs candidates, not correctness.  Worlds beyond the row count share rows too: the sweep's
+// exact test rejects pairs of different worlds.
+__device__ __forceinline__ uint32_t row_of(float lo_z, float thickness, uint32_t world, uint32_t rows)
 {
-	const float r = floorf(lo_z / thickness) + (float)(WIDE_ROWS / 2);
-	return (uint32_t)fminf(fmaxf(r, 0.0f), (float)(WIDE_ROWS - 1));
+	const float r = floorf(lo_z / thickness) + (float)(rows / 2u);
+	const uint32_t local = (uint32_t)fminf(fmaxf(r, 0.0f), (float)(rows - 1u));
+	return min(world * rows + local, (uint32_t)WIDE_ROWS - 1u);
 }
 __device__ __forceinline__ unsigned long long sweep_key(uint32_t row, float lo_x, uint32_t body)
 {
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(WT) kw_keys(WideArgs a)
 	const uint32_t i = blockIdx.x * WT + threadIdx.x;
 	if (i >= a.nb || a.keys[i] == ~0ull) return;
 	const SBody &b = a.bodies[i];
-	a.keys[i] = sweep_key(row_of(b.lo.z, row_thickness(a)), b.lo.x, i);
+	a.keys[i] = sweep_key(row_of(b.lo.z, row_thickness(a), i / a.cap, a.rows_per_world), b.lo.x, i);
 }
 
 __global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
@@ -274,6 +279,7 @@ __device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p
 {
 	const float4 lo_q = a.boxlo[q], hi_q = a.boxhi[q];
 	const uint32_t iq = __float_as_uint(lo_q.w), fq = __float_as_uint(hi_q.w);
+	if (ip / a.cap != iq / a.cap) return;  // bodies of different worlds never meet
 	// at least one awake dynamic body — or a moving kinematic body reaching a sleeper, which only wakes it
 	if (!is_dynamic(fp) && !is_dynamic(fq) &&
 		!(((fp & BF_KIN_MOVING) && (fq & BF_ASLEEP)) || ((fq & BF_KIN_MOVING) && (fp & BF_ASLEEP))))
@@ -491,7 +497,8 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 		if (k < (uint32_t)WIDE_MAXADJ) a.adj[m.b * WIDE_MAXADJ + k] = mi;
 		else atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
 	}
-	a.prio[mi] = man_prio(m.a, m.b, a.ord[mi]);
+	// priorities come from the bodies' indices inside their world, so a world colours the same wherever it sits
+	a.prio[mi] = man_prio(m.a % a.cap, m.b < STATIC_BODY_BASE ? m.b % a.cap : m.b, a.ord[mi]);
 	m.colour = -1;
 	if (a_dyn && b_dyn) isl_unite(a.parent, m.a, m.b);
 }
@@ -1254,9 +1261,9 @@ int wide_create(gpx_world *w)
 {
 	WideDevice *d = new WideDevice();
 	w->wide = d;
-	d->nb = w->cap;
+	d->nb = w->W * w->cap;  // all worlds' bodies in one array, world-major (the layout of the body store)
 	d->n_pad = next_pow2(d->nb);
-	d->cap_m = w->cap_m;
+	d->cap_m = w->W * w->cap_m;
 	d->hsize = next_pow2(2u * d->cap_m);
 	// worst case of the window packing: every window half empty, plus one open window per kw_isl_place block
 	d->isl_slots = 2u * d->cap_m + 32u * ((d->nb + WT - 1) / WT);
@@ -1420,6 +1427,8 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.cap_m = d->cap_m;
 	a.hmask = d->hsize - 1u;
 	a.isl_max = getenv("GPX_WIDE_NO_ISLANDS") ? 0u : ISLAND_MAX;
+	a.cap = w->cap;
+	a.rows_per_world = (uint32_t)WIDE_ROWS / (w->W < (uint32_t)WIDE_ROWS ? w->W : (uint32_t)WIDE_ROWS);
 	a.vel_steps = w->cfg.velocity_steps ? w->cfg.velocity_steps : 10u;
 	a.pos_steps = w->cfg.position_steps ? w->cfg.position_steps : 2u;
 	a.gx = w->cfg.gravity[0];

@@ -78,18 +78,24 @@ enum gpx_allowed_dofs /* JPH_AllowedDOFs (TestActor.c:42-46) */
 
 typedef struct gpx_world gpx_world;
 
+/* gpx_world_config.flags.  GPX_WORLD_WIDE runs the wide-world kernels (global sort-and-sweep, thread per pair, islands)
+ * for an ENSEMBLE of worlds too — what worlds of dozens of bodies in contact want (a 64-box pile has ~150 manifolds, far
+ * more than the lanes the fused ensemble kernel gives a world).  Implied by max_bodies_per_world > 64.  worlds *
+ * max_bodies_per_world <= 2^20.  Contact events are available for worlds == 1 only in this mode. */
+#define GPX_WORLD_WIDE 1u
+
 /* JPH_PhysicsSystemSettings (engine/src/physics/Physics.c:89-100) + the Jolt defaults the tick uses */
 typedef struct gpx_world_config
 {
 	uint32_t worlds;                  /* number of independent world instances sharing the static map */
-	uint32_t max_bodies_per_world;    /* body slots per world: <= 64 for ensembles; up to 2^20 when worlds == 1 (one wide world) */
+	uint32_t max_bodies_per_world;    /* body slots per world: <= 64 for the fused ensemble kernel; more selects GPX_WORLD_WIDE */
 	uint32_t max_manifolds_per_world; /* contact manifolds per world and sub-step; 0 = default */
 	uint32_t max_static_triangles;    /* capacity of the shared static triangle soup */
 	float gravity[3];                 /* JPH_PhysicsSystem_SetGravity (Physics.c:99) */
 	int32_t device;                   /* CUDA device ordinal */
 	uint32_t velocity_steps;          /* 0 = 10 */
 	uint32_t position_steps;          /* 0 = 2  */
-	uint32_t flags;                   /* reserved, 0 */
+	uint32_t flags;                   /* GPX_WORLD_* */
 } gpx_world_config;
 
 /* JPH_BodyCreationSettings as the reference fills it (Create2_GAME + setters) */

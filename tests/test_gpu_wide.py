@@ -219,3 +219,48 @@ def test_islands_are_a_pure_rescheduling(gpx, scenes, monkeypatch):
     xb, vb, cb = run(True)
     assert ca["small_islands"] > 0 and cb["small_islands"] == 0
     assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)) and np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+
+
+def test_wide_kernels_for_an_ensemble_of_mid_size_worlds(gpx, orc, scenes):
+    """GPX_WORLD_WIDE with worlds > 1: 12 independent worlds, each the 4 x 4 x 4 block of boxes tumbling onto stacked.gmap
+    (~150 manifolds per world — far more than the lanes the fused ensemble kernel has per world), in ONE global
+    sort-and-sweep / pair / island pipeline.  Every world must match its own oracle (wide mode) bit for bit, and the
+    worlds must not see each other although their bodies occupy the same space."""
+    W, n = 12, 64
+    g = gpx.World(worlds=W, max_bodies=n, wide=True)
+    os_ = [orc.World(n, wide=True) for _ in range(W)]
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+        for o in os_:
+            o.add_mesh(pos, tris)
+    g.commit()
+    pos = scenes.block_positions(4, 4, 4, 0.45)
+    vel = scenes.ensemble_velocities(W, n)
+    g.create_all([gpx.body_desc(position=tuple(p)) for p in pos], linvel=vel)
+    for wi, o in enumerate(os_):
+        for k, p in enumerate(pos):
+            o.create(orc.body_desc(position=tuple(p), linear_velocity=tuple(vel[wi, k])))
+    for tick in range(1, 61):
+        assert g.step() == 0
+        for o in os_:
+            assert o.step() == 0
+        if tick in (1, 5, 20, 60):
+            assert g.sync() == 0
+            xg, vg = g.transforms(), g.velocities()
+            for wi, o in enumerate(os_):
+                xo, vo = o.state(n)
+                assert np.array_equal(xg[wi].view(np.uint32), xo.view(np.uint32)), f"tick {tick} world {wi}: transforms differ"
+                assert np.array_equal(vg[wi].view(np.uint32), vo.view(np.uint32)), f"tick {tick} world {wi}: velocities differ"
+    assert not np.array_equal(xg[0], xg[1])                          # the worlds did evolve differently
+    # rays and getters address worlds as in any ensemble
+    r = np.zeros(W, gpx.RAY_DTYPE)
+    r["origin"], r["dir"], r["tmax"] = (0.0, 3.0, -1.5), (0.0, -1.0, 0.0), 10.0
+    r["mask"] = 0b11 | (np.arange(W, dtype=np.uint32) << 16)
+    hg = g.raycast(r)
+    for wi, o in enumerate(os_):
+        r1 = r[wi:wi + 1].copy()
+        r1["mask"] = 0b11
+        ho = o.raycast(r1)[0]
+        assert hg["body"][wi] == ho["body"] and hg["fraction"][wi] == ho["fraction"] and hg["world"][wi] == wi
+    with pytest.raises(gpx.GpxError):
+        g.enable_events()
