@@ -341,7 +341,7 @@ class World:
         c = np.zeros(8, np.uint32)
         _check(self.L.gpx_debug_wide_counters(self.h, c.ctypes.data), "gpx_debug_wide_counters")
         return dict(manifold_slots=int(c[0]), small_islands=int(c[1]), colours=int(c[2]), error=int(c[3]),
-                    large_island_manifolds=int(c[5]))
+                    medium_islands=int(c[4]), large_island_manifolds=int(c[5]))
 
     def overlap_capsules(self, queries: np.ndarray) -> np.ndarray:
         """gpx_overlap_capsule_batch: deepest penetration of each upright capsule against the map and the solid bodies."""

@@ -47,7 +47,9 @@ constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase ker
 
 enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_MAXEXT_X, WC_MAXEXT_Z, WC_COLCNT = 8,
 				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_NISL = WC_COLCUR + WIDE_MAXCOL,
-				   WC_ISLCUR, WC_NBIG, WC_COUNT };
+				   WC_ISLCUR, WC_NBIG, WC_NMED, WC_MEDCUR, WC_COUNT };
+constexpr uint32_t MEDIUM_MAX = 1024;    // manifolds of an island solved by one block (kw_island_block); more: the cooperative kernels
+constexpr uint32_t MEDIUM_T = 128;       // threads of that block
 constexpr uint32_t SINGLE_BLOCK_MAX = 4096;  // manifolds of large islands up to which ONE block colours and solves them
 constexpr uint32_t ISLAND_MAX = 32;      // manifolds of an island solved inside one warp (one per lane)
 constexpr uint32_t ISLAND_WARPS = 4;     // warps (islands) per block of kw_island
@@ -88,7 +90,8 @@ struct WideDevice
 	// islands: union-find parent per body, flattened root (| ROOT_SMALL when the body is solved by kw_island), manifold
 	// count / list offset / fill cursor per root, roots of the small islands, their manifold lists
 	uint32_t *parent = nullptr, *root_of = nullptr, *isl_cnt = nullptr, *isl_off = nullptr, *isl_cur = nullptr;
-	uint32_t *isl_man = nullptr, *big_list = nullptr;
+	uint32_t *isl_man = nullptr, *big_list = nullptr, *med_list = nullptr, *med_coloff = nullptr;
+	uint32_t med_slots = 0;  // most medium islands a world can hold
 	unsigned char *can_sleep = nullptr;  // per island root: every body of the island is a sleep candidate
 	// contact events (gpx_events_enable): sorted keys of the touching pairs, scratch for the diff against the last tick
 	uint32_t n_ev = 0;
@@ -114,6 +117,9 @@ struct WideArgs
 	int *pending;
 	uint32_t *col_list;
 	uint32_t *parent, *root_of, *isl_cnt, *isl_off, *isl_cur, *isl_man, *big_list;
+	uint32_t *med_list, *med_coloff;  // roots of the medium islands; 65 colour offsets per medium island
+	uint32_t med_max;                 // MEDIUM_MAX, or 0 with GPX_WIDE_NO_ISLANDS
+	uint32_t med_slots;               // capacity of med_list
 	uint4 *cand;
 	StaticView sv;
 	uint32_t nb, n_pad, cap_m, hmask;
@@ -540,11 +546,20 @@ __global__ void __launch_bounds__(WT) kw_isl_place(WideArgs a)
 		if ((f & BF_ALIVE) && is_dynamic(f) && a.adj_n[i] > 0)
 		{
 			r = isl_find(a.parent, i);
-			small = a.isl_cnt[r] <= a.isl_max;
+			small = a.isl_cnt[r] <= max(a.isl_max, a.med_max);  // solved (and integrated) outside the cooperative kernels
 		}
 		a.root_of[i] = small ? (r | ROOT_SMALL) : r;
 		c = a.isl_cnt[i];  // non-zero only at roots
-		if (c > a.isl_max) c = 0;
+		if (c > a.isl_max)
+		{
+			if (c <= a.med_max)
+			{
+				// a medium island: its own range, counted from the top of the large-island arrays, and a block
+				a.isl_off[i] = atomicAdd(&a.cnt[WC_MEDCUR], c);
+				a.med_list[atomicAdd(&a.cnt[WC_NMED], 1u)] = i;
+			}
+			c = 0;
+		}
 	}
 	scnt[threadIdx.x] = c;
 	__syncthreads();
@@ -579,11 +594,14 @@ __global__ void __launch_bounds__(WT) kw_isl_fill(WideArgs a)
 		if (m.np > 0 && m.colour != SENSOR_COLOUR)
 		{
 			const uint32_t r = (uint32_t)a.pending[mi];
-			if (a.isl_cnt[r] <= a.isl_max)
+			const uint32_t cnt_r = a.isl_cnt[r];
+			if (cnt_r <= a.isl_max)
 			{
 				a.isl_man[a.isl_off[r] + atomicAdd(&a.isl_cur[r], 1u)] = mi;
 				m.colour = -3;  // not the cooperative kernels' business
 			}
+			else if (cnt_r <= a.med_max)
+				a.big_list[(a.cap_m - a.isl_off[r] - cnt_r) + atomicAdd(&a.isl_cur[r], 1u)] = mi;  // stays -1: kw_island_block colours it
 			else
 				big = true;
 		}
@@ -835,6 +853,40 @@ __device__ __forceinline__ bool outranks(const WideArgs &a, uint32_t x, uint32_t
 	return a.ord[x] > a.ord[y];
 }
 
+// One Jones-Plassmann decision: the colour manifold `mi` may take now (it outranks all its uncoloured neighbours), or -1.
+__device__ __forceinline__ int jp_decide(const WideArgs &a, uint32_t mi)
+{
+	const SMan &m = a.man[mi];
+	if (m.colour != -1) return -1;
+	unsigned long long used = 0ull;
+	const uint32_t ends[2] = {m.a, m.b};
+	for (int e = 0; e < 2; e++)
+	{
+		const uint32_t body = ends[e];
+		if (body >= STATIC_BODY_BASE || !is_dynamic(a.bodies[body].flags)) continue;
+		const uint32_t cntb = min(a.adj_n[body], (uint32_t)WIDE_MAXADJ);
+		for (uint32_t j = 0; j < cntb; j++)
+		{
+			const uint32_t other = a.adj[body * WIDE_MAXADJ + j];
+			if (other == mi) continue;
+			const int oc = *(volatile int *)&a.man[other].colour;
+			if (oc == -1)
+			{
+				if (outranks(a, other, mi)) return -1;
+			}
+			else if (oc >= 0)
+				used |= 1ull << oc;
+		}
+	}
+	int decision = __ffsll((long long)~used) - 1;
+	if (decision < 0 || decision >= WIDE_MAXCOL)
+	{
+		decision = WIDE_MAXCOL - 1;
+		atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+	}
+	return decision;
+}
+
 // Barrier of the cooperative kernels.  When the large islands are few, ONE block does the phased work and a block
 // barrier is all it needs; the other blocks only help with the grid-wide integration pass of kw_solve.
 struct PhaseSync
@@ -866,45 +918,7 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 		for (uint32_t k = tid; k < n; k += stride)
 		{
 			const uint32_t mi = a.big_list[k];
-			const SMan &m = a.man[mi];
-			int decision = -1;
-			if (m.colour == -1)
-			{
-				bool top = true;
-				unsigned long long used = 0ull;
-				const uint32_t ends[2] = {m.a, m.b};
-				for (int e = 0; e < 2 && top; e++)
-				{
-					const uint32_t body = ends[e];
-					if (body >= STATIC_BODY_BASE || !is_dynamic(a.bodies[body].flags)) continue;
-					const uint32_t cntb = min(a.adj_n[body], (uint32_t)WIDE_MAXADJ);
-					for (uint32_t j = 0; j < cntb; j++)
-					{
-						const uint32_t other = a.adj[body * WIDE_MAXADJ + j];
-						if (other == mi) continue;
-						const int oc = a.man[other].colour;
-						if (oc == -1)
-						{
-							if (outranks(a, other, mi))
-							{
-								top = false;
-								break;
-							}
-						}
-						else if (oc >= 0)
-							used |= 1ull << oc;
-					}
-				}
-				if (top)
-				{
-					decision = __ffsll((long long)~used) - 1;
-					if (decision < 0 || decision >= WIDE_MAXCOL)
-					{
-						decision = WIDE_MAXCOL - 1;
-						atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
-					}
-				}
-			}
+			const int decision = jp_decide(a, mi);
 			a.pending[mi] = decision;
 		}
 		bar();
@@ -952,6 +966,44 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 
 // ---------------------------------------------------------------------------------------------------- solve
 
+// One colour phase over the solver records [lo, hi): each warp stages its 32 consecutive records in shared memory with
+// coalesced 16-byte copies, solves from there (warm start or one velocity iteration) and writes back only the impulses.
+__device__ __forceinline__ void solve_colour_range(const WideArgs &a, SolveRec *recs, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t stride,
+												   SolveRec *stage, uint32_t lane, bool warm)
+{
+	for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
+	{
+		const uint32_t cnt32 = min(32u, hi - k0);
+		const float4 *src = reinterpret_cast<const float4 *>(recs + k0);
+		float4 *dst = reinterpret_cast<float4 *>(stage + (threadIdx.x & ~31u));
+		const uint32_t n16 = cnt32 * (uint32_t)(sizeof(SolveRec) / 16);
+		for (uint32_t q = lane; q < n16; q += 32u) dst[q] = __ldcg(&src[q]);
+		__syncwarp();
+		if (lane < cnt32)
+		{
+			SolveRec &r = stage[threadIdx.x];
+			const Con c = r.con;
+			Vel u;
+			load_vel(c, a.bodies, u);
+			if (warm)
+				warm_start(c, r.pts, r, u);
+			else
+				solve_velocity(c, r.pts, r, u);
+			store_vel(c, a.bodies, u);
+			SolveRec &g = recs[k0 + lane];
+#pragma unroll
+			for (int p = 0; p < 4; p++)
+			{
+				g.ln[p] = r.ln[p];
+				g.lt1[p] = r.lt1[p];
+				g.lt2[p] = r.lt2[p];
+			}
+		}
+		__syncwarp();
+	}
+}
+
+
 __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 {
 	cg::grid_group grid = cg::this_grid();
@@ -993,38 +1045,7 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 			for (int col = 0; col < ncol; col++)
 			{
 				const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
-				// each warp stages its 32 consecutive records in shared memory with coalesced 16-byte copies, solves
-				// from there and writes back only the accumulated impulses
-				for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
-				{
-					const uint32_t cnt32 = min(32u, hi - k0);
-					const float4 *src = reinterpret_cast<const float4 *>(a.recs + k0);
-					float4 *dst = reinterpret_cast<float4 *>(stage + (threadIdx.x & ~31u));
-					const uint32_t n16 = cnt32 * (uint32_t)(sizeof(SolveRec) / 16);
-					for (uint32_t q = lane; q < n16; q += 32u) dst[q] = __ldcg(&src[q]);
-					__syncwarp();
-					if (lane < cnt32)
-					{
-						SolveRec &r = stage[threadIdx.x];
-						const Con c = r.con;
-						Vel u;
-						load_vel(c, a.bodies, u);
-						if (it == 0)
-							warm_start(c, r.pts, r, u);
-						else
-							solve_velocity(c, r.pts, r, u);
-						store_vel(c, a.bodies, u);
-						SolveRec &g = a.recs[k0 + lane];
-#pragma unroll
-						for (int p = 0; p < 4; p++)
-						{
-							g.ln[p] = r.ln[p];
-							g.lt1[p] = r.lt1[p];
-							g.lt2[p] = r.lt2[p];
-						}
-					}
-					__syncwarp();
-				}
+				solve_colour_range(a, a.recs, lo, hi, tid, stride, stage, lane, it == 0);
 				bar();
 			}
 		// accumulated impulses back into the manifolds (next sub-step's warm start reads them there)
@@ -1062,6 +1083,154 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 			for (uint32_t k = lo + tid; k < hi; k += stride) solve_position(a.man[a.col_list[k]], a.bodies);
 			bar();
 		}
+}
+
+// ---- medium islands (33 .. MEDIUM_MAX manifolds: a pile of a few dozen boxes): ONE block per island runs what kw_colour
+// and kw_solve run grid-wide — the same Jones-Plassmann decisions, the same records and colour phases — with block
+// barriers.  An island owns the range [base, base + count) of big_list / col_list / recs, counted from the top of those
+// arrays (the cooperative kernels fill them from the bottom; every manifold is in exactly one class).
+__global__ void __launch_bounds__(MEDIUM_T) kw_island_block(WideArgs a)
+{
+	extern __shared__ __align__(16) unsigned char stage_raw[];
+	SolveRec *stage = reinterpret_cast<SolveRec *>(stage_raw);
+	__shared__ uint32_t s_colcnt[WIDE_MAXCOL], s_coloff[WIDE_MAXCOL + 1], s_cur[WIDE_MAXCOL], s_uncol, s_ncol;
+	const uint32_t tid = threadIdx.x, lane = threadIdx.x & 31u;
+	const uint32_t n_med = min(a.cnt[WC_NMED], a.med_slots);
+	for (uint32_t isl = blockIdx.x; isl < n_med; isl += gridDim.x)
+	{
+	const uint32_t root = a.med_list[isl];
+	const uint32_t count = a.isl_cnt[root];
+	const uint32_t base = a.cap_m - a.isl_off[root] - count;
+	__syncthreads();  // the previous island's shared counters are done with
+	for (uint32_t c = tid; c < (uint32_t)WIDE_MAXCOL; c += MEDIUM_T) s_colcnt[c] = 0;
+	if (tid == 0) s_uncol = count;
+	__syncthreads();
+	// --- colouring
+	for (int round = 0; round < 4096; round++)
+	{
+		if (*(volatile uint32_t *)&s_uncol == 0) break;
+		for (uint32_t k = tid; k < count; k += MEDIUM_T)
+		{
+			const uint32_t mi = a.big_list[base + k];
+			a.pending[mi] = jp_decide(a, mi);
+		}
+		__syncthreads();
+		uint32_t done = 0;
+		for (uint32_t k = tid; k < count; k += MEDIUM_T)
+		{
+			const uint32_t mi = a.big_list[base + k];
+			const int d = a.pending[mi];
+			if (d >= 0)
+			{
+				a.man[mi].colour = d;
+				atomicAdd(&s_colcnt[d], 1u);
+				done++;
+			}
+		}
+		if (done) atomicSub(&s_uncol, done);
+		__threadfence_block();
+		__syncthreads();
+	}
+	if (tid == 0)
+	{
+		uint32_t off = 0, ncol = 0;
+		for (int c = 0; c < WIDE_MAXCOL; c++)
+		{
+			s_coloff[c] = off;
+			s_cur[c] = off;
+			off += s_colcnt[c];
+			if (s_colcnt[c]) ncol = (uint32_t)c + 1u;
+		}
+		s_coloff[WIDE_MAXCOL] = off;
+		s_ncol = ncol;
+	}
+	__syncthreads();
+	for (uint32_t k = tid; k < count; k += MEDIUM_T)
+	{
+		const uint32_t mi = a.big_list[base + k];
+		a.col_list[base + atomicAdd(&s_cur[a.man[mi].colour], 1u)] = mi;
+	}
+	for (uint32_t c = tid; c <= (uint32_t)WIDE_MAXCOL; c += MEDIUM_T) a.med_coloff[isl * (WIDE_MAXCOL + 1) + c] = s_coloff[c];
+	__threadfence_block();
+	__syncthreads();
+	// --- set-up: one solver record per manifold, in colour order
+	const float h = a.h;
+	const int ncol = (int)s_ncol;
+	for (uint32_t k = tid; k < count; k += MEDIUM_T)
+	{
+		const uint32_t mi = a.col_list[base + k];
+		SMan &m = a.man[mi];
+		SolveRec &r = a.recs[base + k];
+		Con c;
+		build_con(c, r.pts, m, a.bodies, h);
+		r.con = c;
+		r.mi = mi;
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			r.bias[p] = m.bias[p];
+			r.ln[p] = m.ln[p];
+			r.lt1[p] = m.lt1[p];
+			r.lt2[p] = m.lt2[p];
+		}
+	}
+	__threadfence_block();
+	__syncthreads();
+	// --- warm start, then the velocity iterations, colour by colour
+	for (uint32_t it = 0; it <= a.vel_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			solve_colour_range(a, a.recs + base, s_coloff[col], s_coloff[col + 1], tid, MEDIUM_T, stage, lane, it == 0);
+			__threadfence_block();
+			__syncthreads();
+		}
+	// --- impulses back into the manifolds; integrate the island's dynamic bodies (each by the thread that holds the
+	// first manifold of its incidence list)
+	for (uint32_t k = tid; k < count; k += MEDIUM_T)
+	{
+		const SolveRec &r = a.recs[base + k];
+		SMan &m = a.man[r.mi];
+#pragma unroll
+		for (int p = 0; p < 4; p++)
+		{
+			m.ln[p] = r.ln[p];
+			m.lt1[p] = r.lt1[p];
+			m.lt2[p] = r.lt2[p];
+		}
+		const uint32_t ends[2] = {m.a, m.b};
+		for (int e = 0; e < 2; e++)
+		{
+			const uint32_t body = ends[e];
+			if (body >= STATIC_BODY_BASE || !is_dynamic(a.bodies[body].flags) || a.adj[body * WIDE_MAXADJ] != r.mi) continue;
+			SBody &b = a.bodies[body];
+			b.x = b.x + (b.v * h);
+			b.q = qstep(b.q, b.w * h);
+		}
+	}
+	}
+}
+
+// position iterations of the medium islands, after the kinematic bodies have moved (kw_solve integrates them)
+__global__ void __launch_bounds__(MEDIUM_T) kw_island_block_pos(WideArgs a)
+{
+	const uint32_t n_med = min(a.cnt[WC_NMED], a.med_slots);
+	for (uint32_t isl = blockIdx.x; isl < n_med; isl += gridDim.x)
+	{
+	const uint32_t root = a.med_list[isl];
+	const uint32_t count = a.isl_cnt[root];
+	const uint32_t base = a.cap_m - a.isl_off[root] - count;
+	const uint32_t *coloff = a.med_coloff + isl * (WIDE_MAXCOL + 1);
+	int ncol = 0;
+	for (int c = 0; c < WIDE_MAXCOL; c++)
+		if (coloff[c + 1] > coloff[c]) ncol = c + 1;
+	for (uint32_t it = 0; it < a.pos_steps; it++)
+		for (int col = 0; col < ncol; col++)
+		{
+			for (uint32_t k = coloff[col] + threadIdx.x; k < coloff[col + 1]; k += MEDIUM_T) solve_position(a.man[a.col_list[base + k]], a.bodies);
+			__threadfence_block();
+			__syncthreads();
+		}
+	}
 }
 
 __global__ void __launch_bounds__(WT) kw_finish(WideArgs a)
@@ -1267,6 +1436,7 @@ int wide_create(gpx_world *w)
 	d->hsize = next_pow2(2u * d->cap_m);
 	// worst case of the window packing: every window half empty, plus one open window per kw_isl_place block
 	d->isl_slots = 2u * d->cap_m + 32u * ((d->nb + WT - 1) / WT);
+	d->med_slots = d->cap_m / (ISLAND_MAX + 1u) + 1u;  // a medium island has at least 33 manifolds
 	bool ok = walloc(&d->bodies, d->nb) && walloc(&d->keys, d->n_pad) && walloc(&d->boxlo, d->n_pad) &&
 			  walloc(&d->boxhi, d->n_pad) && walloc(&d->man[0], d->cap_m) && walloc(&d->man[1], d->cap_m) &&
 			  walloc(&d->ord[0], d->cap_m) && walloc(&d->ord[1], d->cap_m) && walloc(&d->recs, d->cap_m) &&
@@ -1274,7 +1444,8 @@ int wide_create(gpx_world *w)
 			  walloc(&d->adj, (size_t)d->nb * WIDE_MAXADJ) && walloc(&d->adj_n, d->nb) && walloc(&d->prio, d->cap_m) &&
 			  walloc(&d->pending, d->cap_m) && walloc(&d->col_list, d->cap_m) && walloc(&d->parent, d->nb) &&
 			  walloc(&d->root_of, d->nb) && walloc(&d->isl_cnt, d->nb) && walloc(&d->isl_off, d->nb) && walloc(&d->isl_cur, d->nb) &&
-			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m) &&
+			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m) && walloc(&d->med_list, (size_t)d->med_slots) &&
+			  walloc(&d->med_coloff, (size_t)d->med_slots * (WIDE_MAXCOL + 1)) &&
 			  walloc(&d->keys_tmp, d->n_pad) && walloc(&d->sort_hist, (size_t)256 * (d->n_pad / 1024u + 1u)) &&
 			  walloc(&d->can_sleep, d->nb);
 	if (!ok)
@@ -1287,6 +1458,7 @@ int wide_create(gpx_world *w)
 	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_colour, 256, 0));
 	d->coop_grid_colour = sms * (per_sm > 0 ? per_sm : 1);
 	GPX_CUDA(cudaFuncSetAttribute(kw_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * sizeof(SolveRec))));
+	GPX_CUDA(cudaFuncSetAttribute(kw_island_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MEDIUM_T * sizeof(SolveRec))));
 	GPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw_solve, 256, 256 * sizeof(SolveRec)));
 	d->coop_grid_solve = sms * (per_sm > 0 ? per_sm : 1);
 	return GPX_OK;
@@ -1300,7 +1472,7 @@ void wide_destroy(gpx_world *w)
 	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
-	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->keys_tmp); cudaFree(d->sort_hist); cudaFree(d->can_sleep);
+	cudaFree(d->isl_man); cudaFree(d->big_list); cudaFree(d->med_list); cudaFree(d->med_coloff); cudaFree(d->keys_tmp); cudaFree(d->sort_hist); cudaFree(d->can_sleep);
 	cudaFree(d->ev_keys); cudaFree(d->ev_tmp); cudaFree(d->ev_cur); cudaFree(d->ev_hist); cudaFree(d->ev_flag); cudaFree(d->ev_pos);
 	cudaFree(d->ev_ncur);
 	delete d;
@@ -1388,6 +1560,7 @@ int wide_counters(gpx_world *w, uint32_t *out8)
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	GPX_CUDA(cudaMemcpy(out8, w->wide->counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	GPX_CUDA(cudaMemcpy(out8 + WC_NPREV, w->wide->counters + WC_NISL, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	GPX_CUDA(cudaMemcpy(out8 + WC_UNCOLOURED, w->wide->counters + WC_NMED, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return GPX_OK;
 }
 
@@ -1418,6 +1591,9 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.isl_cur = d->isl_cur;
 	a.isl_man = d->isl_man;
 	a.big_list = d->big_list;
+	a.med_list = d->med_list;
+	a.med_coloff = d->med_coloff;
+	a.med_slots = d->med_slots;
 	a.cand = w->d_cand;
 	a.sv.nodes = w->sd.nodes;
 	a.sv.tris = w->sd.tri;
@@ -1427,6 +1603,7 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.cap_m = d->cap_m;
 	a.hmask = d->hsize - 1u;
 	a.isl_max = getenv("GPX_WIDE_NO_ISLANDS") ? 0u : ISLAND_MAX;
+	a.med_max = (getenv("GPX_WIDE_NO_ISLANDS") || getenv("GPX_WIDE_NO_BLOCKS")) ? 0u : MEDIUM_MAX;
 	a.cap = w->cap;
 	a.rows_per_world = (uint32_t)WIDE_ROWS / (w->W < (uint32_t)WIDE_ROWS ? w->W : (uint32_t)WIDE_ROWS);
 	a.vel_steps = w->cfg.velocity_steps ? w->cfg.velocity_steps : 10u;
@@ -1466,12 +1643,16 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		// one warp per 32-slot window; warps beyond the windows in use leave at once
 		const uint32_t gi = (d->isl_slots / 32u + ISLAND_WARPS - 1) / ISLAND_WARPS;
 		kw_island<<<gi, ISLAND_WARPS * 32, 0, st>>>(a);
-		count_launch(9);
+		// a fixed grid of blocks walks the medium islands, one island per block at a time
+		const uint32_t gmed = d->med_slots < (uint32_t)d->coop_grid_colour * 2u ? d->med_slots : (uint32_t)d->coop_grid_colour * 2u;
+		kw_island_block<<<gmed, MEDIUM_T, MEDIUM_T * sizeof(SolveRec), st>>>(a);
+		count_launch(10);
 		int rc;
 		if ((rc = coop_launch((const void *)kw_colour, d->coop_grid_colour, a, st)) != GPX_OK) return rc;
 		if ((rc = coop_launch((const void *)kw_solve, d->coop_grid_solve, a, st, 256 * sizeof(SolveRec))) != GPX_OK) return rc;
 		kw_island_pos<<<gi, ISLAND_WARPS * 32, 0, st>>>(a);
-		count_launch();
+		kw_island_block_pos<<<gmed, MEDIUM_T, 0, st>>>(a);
+		count_launch(2);
 		// this sub-step's manifolds become the next one's warm-start table
 		GPX_CUDA(cudaMemsetAsync(d->hkeys, 0, sizeof(unsigned long long) * d->hsize, st));
 		kw_finish<<<max(gm, gb), WT, 0, st>>>(a);

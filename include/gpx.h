@@ -408,8 +408,8 @@ uint64_t gpx_launch_count(void);
  * cache write, store. */
 int gpx_debug_phase_cycles(gpx_world *w, int enable, uint64_t *out16);
 /* Profiling aid for a wide world: counters of the last sub-step — manifold slots used, islands solved inside one warp,
- * colours of the large islands, sticky error word, uncoloured left (0), manifolds of the large islands, largest body
- * extent in x and z as float bits. */
+ * colours of the large islands, sticky error word, islands solved by one block each, manifolds of the large islands,
+ * largest body extent in x and z as float bits. */
 int gpx_debug_wide_counters(gpx_world *w, uint32_t *out8);
 /* Static LBVH introspection for tests: node count and triangle count after commit. */
 int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *n_bodies);

@@ -84,7 +84,7 @@ def test_pile_on_shipped_map_with_mixed_bodies(gpx, orc, scenes):
 
 def test_islands_small_large_kinematic_and_free_bodies(gpx, orc, scenes):
     """The island split of the wide path: separate short columns (islands solved inside one warp), an 8 x 5 wall
-    whose boxes all touch (one large island -> the phased kernels), a column riding a moving kinematic platform (its
+    whose boxes all touch (one medium island -> a block of its own), a column riding a moving kinematic platform (its
     contacts are set up before the platform moves and position-corrected after), and bodies still in free fall."""
     descs = []
     for ix in range(6):                                   # six 3-box columns, 1.5 m apart: six small islands
@@ -109,7 +109,7 @@ def test_islands_small_large_kinematic_and_free_bodies(gpx, orc, scenes):
             assert g.sync() == 0
             _assert_same(g, o, n, f"islands tick {tick}")
     c = g.wide_counters()
-    assert c["small_islands"] >= 7 and c["large_island_manifolds"] > 32
+    assert c["small_islands"] >= 7 and c["medium_islands"] >= 1      # the wall: one block solves it
     x = g.transforms()[0, :n]
     plat = 18 + 40
     assert abs(x[plat, 0] - (-2.0 + 0.3 * 100 / 60)) < 1e-3                   # the platform went where its velocity says
