@@ -536,7 +536,8 @@ __device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
-			float s = maxf / sqrtf(sq);
+			// no normal impulse yet (a speculative point): 0 / sqrt(sq) is that zero, skip the division and the root
+			float s = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}

@@ -1477,7 +1477,8 @@ static void solve_velocity(orc_world *w, manifold_t *m)
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
-			float s = maxf / sqrtf(sq);
+			/* no normal impulse yet: 0 / sqrt(sq) is that zero */
+			float s = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
