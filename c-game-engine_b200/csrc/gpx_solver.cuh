@@ -527,12 +527,14 @@ __device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M
 #pragma unroll 1
 	for (int k = 0; k < c.np; k++)
 	{
-		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
 		const float o1 = m.lt1[k], o2 = m.lt2[k];
+		const float maxf = c.friction * m.ln[k];
+		// nothing to hold with and nothing held (a speculative point that does not touch): the row stays at zero
+		if (maxf == 0.0f && o1 == 0.0f && o2 == 0.0f) continue;
+		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
 		v3 rv = rel_vel(c, u, r1, r2);
 		float l1 = o1 + (pt.em[k][1] * dot(c.t1, rv));
 		float l2 = o2 + (pt.em[k][2] * dot(c.t2, rv));
-		float maxf = c.friction * m.ln[k];
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
@@ -541,10 +543,11 @@ __device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
-		v3 P = (c.t1 * (l1 - o1)) + (c.t2 * (l2 - o2));
+		const float d1 = l1 - o1, d2 = l2 - o2;
 		m.lt1[k] = l1;
 		m.lt2[k] = l2;
-		apply_impulse(c, u, r1, r2, P);
+		// an impulse is applied only when it is not zero (Jolt's AxisConstraintPart::ApplyVelocityStep)
+		if (d1 != 0.0f || d2 != 0.0f) apply_impulse(c, u, r1, r2, (c.t1 * d1) + (c.t2 * d2));
 	}
 #pragma unroll 1
 	for (int k = 0; k < c.np; k++)
@@ -556,7 +559,7 @@ __device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M
 		float nt = fmaxf(0.0f, old + lambda);
 		lambda = nt - old;
 		m.ln[k] = nt;
-		apply_impulse(c, u, r1, r2, c.n * lambda);
+		if (lambda != 0.0f) apply_impulse(c, u, r1, r2, c.n * lambda);
 	}
 }
 

@@ -1470,10 +1470,12 @@ static void solve_velocity(orc_world *w, manifold_t *m)
 	/* friction first (non-penetration is more important, so it goes last) */
 	for (int k = 0; k < m->np; k++)
 	{
+		float maxf = m->friction * m->ln[k];
+		/* nothing to hold with and nothing held (a speculative point that does not touch): the row stays at zero */
+		if (maxf == 0.0f && m->lt1[k] == 0.0f && m->lt2[k] == 0.0f) continue;
 		v3 u = rel_vel(A, B, m->r1[k], m->r2[k]);
 		float l1 = m->lt1[k] + (m->em[k][1] * vdot(m->t1, u));
 		float l2 = m->lt2[k] + (m->em[k][2] * vdot(m->t2, u));
-		float maxf = m->friction * m->ln[k];
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
@@ -1482,10 +1484,11 @@ static void solve_velocity(orc_world *w, manifold_t *m)
 			l1 = l1 * s;
 			l2 = l2 * s;
 		}
-		v3 P = vadd(vscale(m->t1, l1 - m->lt1[k]), vscale(m->t2, l2 - m->lt2[k]));
+		const float d1 = l1 - m->lt1[k], d2 = l2 - m->lt2[k];
 		m->lt1[k] = l1;
 		m->lt2[k] = l2;
-		apply_impulse(A, B, m->r1[k], m->r2[k], P);
+		/* an impulse is applied only when it is not zero (Jolt: AxisConstraintPart::ApplyVelocityStep) */
+		if (d1 != 0.0f || d2 != 0.0f) apply_impulse(A, B, m->r1[k], m->r2[k], vadd(vscale(m->t1, d1), vscale(m->t2, d2)));
 	}
 	for (int k = 0; k < m->np; k++)
 	{
@@ -1494,7 +1497,7 @@ static void solve_velocity(orc_world *w, manifold_t *m)
 		float nt = fmaxf(0.0f, m->ln[k] + lambda);
 		lambda = nt - m->ln[k];
 		m->ln[k] = nt;
-		apply_impulse(A, B, m->r1[k], m->r2[k], vscale(m->n, lambda));
+		if (lambda != 0.0f) apply_impulse(A, B, m->r1[k], m->r2[k], vscale(m->n, lambda));
 	}
 }
 
