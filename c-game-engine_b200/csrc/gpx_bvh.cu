@@ -161,8 +161,10 @@ void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t s
 // ranks keys inside each warp with match_any so equal digits keep their order.
 constexpr uint32_t RADIX_BLOCK = 256, RADIX_ITEMS = 4, RADIX_TILE = RADIX_BLOCK * RADIX_ITEMS;  // 1024 keys per block
 
+// `fused` (a few hundred blocks at most): counters are stored block-major and every scatter block sums the table itself —
+// 256 threads read it coalesced out of L2 in a microsecond, where the one-block scan kernel in between cost ten.
 __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long long *__restrict__ keys, uint32_t shift,
-															uint32_t *__restrict__ ghist)
+															uint32_t *__restrict__ ghist, bool fused)
 {
 	__shared__ uint32_t hist[256];
 	hist[threadIdx.x] = 0;
@@ -172,7 +174,10 @@ __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long 
 	for (uint32_t i = 0; i < RADIX_ITEMS; i++)
 		atomicAdd(&hist[(uint32_t)(keys[base + i * RADIX_BLOCK + threadIdx.x] >> shift) & 255u], 1u);
 	__syncthreads();
-	ghist[threadIdx.x * gridDim.x + blockIdx.x] = hist[threadIdx.x];  // digit-major: the scan order of the scatter
+	if (fused)
+		ghist[blockIdx.x * 256u + threadIdx.x] = hist[threadIdx.x];
+	else
+		ghist[threadIdx.x * gridDim.x + blockIdx.x] = hist[threadIdx.x];  // digit-major: the scan order of the scatter
 }
 
 // exclusive scan of `n` counters by one block (n = 256 digits x blocks, a few 10^4): each warp owns a contiguous
@@ -220,9 +225,10 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ ghis
 
 __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned long long *__restrict__ keys,
 															   unsigned long long *__restrict__ out, uint32_t shift,
-															   const uint32_t *__restrict__ ghist)
+															   const uint32_t *__restrict__ ghist, bool fused)
 {
 	__shared__ uint32_t wcnt[RADIX_BLOCK / 32][256];
+	__shared__ uint32_t wtot[RADIX_BLOCK / 32];
 	const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	for (uint32_t k = threadIdx.x; k < (RADIX_BLOCK / 32) * 256; k += RADIX_BLOCK) (&wcnt[0][0])[k] = 0;
 	__syncthreads();
@@ -242,11 +248,39 @@ __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned lo
 		__syncwarp();
 		local[i] = before + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 	}
-	__syncthreads();
+	// thread = digit: where this block's keys with that digit start in the output
+	uint32_t run;
+	if (fused)
 	{
-		// thread = digit: turn the per-warp counts into global start positions, warp after warp
+		// keys with a smaller digit anywhere + keys with this digit in earlier blocks
+		uint32_t below = 0, all = 0;
+#pragma unroll 8
+		for (uint32_t b = 0; b < gridDim.x; b++)
+		{
+			const uint32_t c = ghist[b * 256u + threadIdx.x];
+			all += c;
+			if (b < blockIdx.x) below += c;
+		}
+		uint32_t incl = all;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= (uint32_t)o) incl += v;
+		}
+		if (lane == 31u) wtot[w] = incl;
+		__syncthreads();
+		uint32_t before = 0;
+		for (uint32_t ww = 0; ww < w; ww++) before += wtot[ww];
+		run = before + (incl - all) + below;
+	}
+	else
+	{
+		run = ghist[threadIdx.x * gridDim.x + blockIdx.x];
+		__syncthreads();
+	}
+	{
+		// turn the per-warp counts into global start positions, warp after warp
 		const uint32_t d = threadIdx.x;
-		uint32_t run = ghist[d * gridDim.x + blockIdx.x];
 		for (uint32_t ww = 0; ww < RADIX_BLOCK / 32; ww++)
 		{
 			const uint32_t c = wcnt[ww][d];
@@ -277,12 +311,13 @@ void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_
 	for (uint32_t sh = first_bit; sh < 64u; sh += 8u) shifts[passes++] = sh > 56u ? 56u : sh;
 	if (passes & 1) shifts[passes++] = 56u;  // an even number of passes leaves the result in d_keys (a repeat is harmless)
 	unsigned long long *src = d_keys, *dst = tmp;
+	const bool fused = blocks <= 256u;
 	for (int p = 0; p < passes; p++)
 	{
-		k_radix_hist<<<blocks, RADIX_BLOCK, 0, st>>>(src, shifts[p], ghist);
-		k_radix_scan<<<1, 1024, 0, st>>>(ghist, 256u * blocks);
-		k_radix_scatter<<<blocks, RADIX_BLOCK, 0, st>>>(src, dst, shifts[p], ghist);
-		count_launch(3);
+		k_radix_hist<<<blocks, RADIX_BLOCK, 0, st>>>(src, shifts[p], ghist, fused);
+		if (!fused) k_radix_scan<<<1, 1024, 0, st>>>(ghist, 256u * blocks);
+		k_radix_scatter<<<blocks, RADIX_BLOCK, 0, st>>>(src, dst, shifts[p], ghist, fused);
+		count_launch(fused ? 2 : 3);
 		unsigned long long *t = src;
 		src = dst;
 		dst = t;
