@@ -255,7 +255,20 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		 cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && dalloc(&w->d_busy, (size_t)cfg->worlds) == GPX_OK && dalloc(&w->d_busy_n, 1) == GPX_OK &&
 		 dalloc(&w->d_busy_flag, (size_t)cfg->worlds) == GPX_OK;
-	ok = ok && dalloc(&w->bs.pos, nb) == GPX_OK && dalloc(&w->bs.quat, nb) == GPX_OK && dalloc(&w->bs.lin, nb) == GPX_OK &&
+	// positions, orientations and the error words share ONE allocation (and so do their host mirrors): what
+	// gpx_sync_transforms reads back every tick is a single contiguous copy
+	{
+		const size_t pose_bytes = 2 * sizeof(float4) * nb + sizeof(uint32_t) * ((size_t)w->W + 1);
+		unsigned char *pose = nullptr;
+		ok = ok && cudaMalloc(&pose, pose_bytes) == cudaSuccess && cudaMemset(pose, 0, pose_bytes) == cudaSuccess;
+		w->bs.pos = reinterpret_cast<float4 *>(pose);
+		if (ok)
+		{
+			w->bs.quat = w->bs.pos + nb;
+			w->d_err = reinterpret_cast<uint32_t *>(pose + 2 * sizeof(float4) * nb);
+		}
+	}
+	ok = ok && dalloc(&w->bs.lin, nb) == GPX_OK &&
 		 dalloc(&w->bs.ang, nb) == GPX_OK && dalloc(&w->bs.prop0, nb) == GPX_OK && dalloc(&w->bs.prop1, nb) == GPX_OK &&
 		 dalloc(&w->bs.prop2, nb) == GPX_OK && dalloc(&w->bs.flags, nb) == GPX_OK && dalloc(&w->bs.sleep_c, 3 * nb) == GPX_OK &&
 		 dalloc(&w->bs.sleep_t, nb) == GPX_OK;
@@ -267,11 +280,9 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		ok = ok && wide_create(w) == GPX_OK;
 	ok = ok && cudaMalloc(&w->d_cand, sizeof(uint4) * 8 * nb) == cudaSuccess &&
 		 cudaMemset(w->d_cand, 0xFF, sizeof(uint4) * 8 * nb) == cudaSuccess;
-	ok = ok && dalloc(&w->d_err, (size_t)w->W + 1) == GPX_OK && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
-	ok = ok && cudaMallocHost(&w->mb_pos[0], sizeof(float4) * nb) == cudaSuccess &&
-		 cudaMallocHost(&w->mb_pos[1], sizeof(float4) * nb) == cudaSuccess &&
-		 cudaMallocHost(&w->mb_quat[0], sizeof(float4) * nb) == cudaSuccess &&
-		 cudaMallocHost(&w->mb_quat[1], sizeof(float4) * nb) == cudaSuccess &&
+	ok = ok && dalloc(&w->d_stats, (size_t)w->W) == GPX_OK;
+	ok = ok && cudaMallocHost(&w->mb_pos[0], sizeof(float4) * (2 * nb + 1)) == cudaSuccess &&
+		 cudaMallocHost(&w->mb_pos[1], sizeof(float4) * (2 * nb + 1)) == cudaSuccess &&
 		 cudaMallocHost(&w->m_lin, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_ang, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_err, sizeof(uint32_t) * 4) == cudaSuccess;
@@ -283,8 +294,8 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	}
 	for (int k = 0; k < 2; k++)
 	{
-		memset(w->mb_pos[k], 0, sizeof(float4) * nb);
-		memset(w->mb_quat[k], 0, sizeof(float4) * nb);
+		memset(w->mb_pos[k], 0, sizeof(float4) * (2 * nb + 1));
+		w->mb_quat[k] = w->mb_pos[k] + nb;  // the error word follows at [2 * nb]
 	}
 	memset(w->m_lin, 0, sizeof(float4) * nb);
 	memset(w->m_ang, 0, sizeof(float4) * nb);
@@ -301,17 +312,17 @@ void gpx_world_destroy(gpx_world *w)
 	cudaSetDevice(w->device);
 	if (w->stream) cudaStreamSynchronize(w->stream);
 	wide_destroy(w);
-	cudaFree(w->bs.pos); cudaFree(w->bs.quat); cudaFree(w->bs.lin); cudaFree(w->bs.ang);
+	cudaFree(w->bs.pos); /* + quat, d_err: one allocation */ cudaFree(w->bs.lin); cudaFree(w->bs.ang);
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->bs.sleep_c); cudaFree(w->bs.sleep_t);
 	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
-	cudaFree(w->d_err); cudaFree(w->d_stats); cudaFree(w->d_cmd); if (w->sd.ray_tri != w->sd.tri) cudaFree(w->sd.ray_tri);
+	cudaFree(w->d_stats); cudaFree(w->d_cmd); if (w->sd.ray_tri != w->sd.tri) cudaFree(w->sd.ray_tri);
 	if (w->sd.ray_nodes != w->sd.nodes) cudaFree(w->sd.ray_nodes);
 	cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);
-	cudaFreeHost(w->mb_pos[0]); cudaFreeHost(w->mb_pos[1]); cudaFreeHost(w->mb_quat[0]); cudaFreeHost(w->mb_quat[1]); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
+	cudaFreeHost(w->mb_pos[0]); cudaFreeHost(w->mb_pos[1]); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->ev_fork) cudaEventDestroy(w->ev_fork);
@@ -857,10 +868,11 @@ int gpx_sync_transforms(gpx_world *w)
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	const size_t nb = (size_t)w->W * w->cap;
 	const uint32_t gen = w->mirror_gen.load(std::memory_order_relaxed), back = (gen + 1u) & 1u;
-	GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
-	GPX_CUDA(cudaMemcpyAsync(w->mb_quat[back], w->bs.quat, sizeof(float4) * nb, cudaMemcpyDeviceToHost, w->stream));
-	GPX_CUDA(cudaMemcpyAsync(w->m_err, w->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+	// positions | orientations | error word: one allocation on each side, one copy
+	GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, 2 * sizeof(float4) * nb + sizeof(uint32_t), cudaMemcpyDeviceToHost,
+							 w->stream));
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	w->m_err[0] = *reinterpret_cast<const uint32_t *>(w->mb_pos[back] + 2 * nb);
 	w->mirror_gen.store(gen + 1u, std::memory_order_release);  // the tick just read back becomes the front
 	return (int)w->m_err[0];
 }
