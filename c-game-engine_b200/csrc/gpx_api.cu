@@ -250,6 +250,9 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	const size_t nb = (size_t)w->W * w->cap, nm = (size_t)w->W * w->cap_m;
 	bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&w->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
+		 cudaEventCreateWithFlags(&w->ev_rays_done, cudaEventDisableTiming) == cudaSuccess &&
+		 cudaEventCreateWithFlags(&w->ev_hits_done, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) == cudaSuccess &&
 		 cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
 		 cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -311,6 +314,7 @@ void gpx_world_destroy(gpx_world *w)
 	if (!w) return;
 	cudaSetDevice(w->device);
 	if (w->stream) cudaStreamSynchronize(w->stream);
+	if (w->stream_copy) cudaStreamSynchronize(w->stream_copy);
 	wide_destroy(w);
 	cudaFree(w->bs.pos); /* + quat, d_err: one allocation */ cudaFree(w->bs.lin); cudaFree(w->bs.ang);
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
@@ -328,6 +332,9 @@ void gpx_world_destroy(gpx_world *w)
 	if (w->ev_fork) cudaEventDestroy(w->ev_fork);
 	if (w->ev_join) cudaEventDestroy(w->ev_join);
 	if (w->stream2) cudaStreamDestroy(w->stream2);
+	if (w->ev_rays_done) cudaEventDestroy(w->ev_rays_done);
+	if (w->ev_hits_done) cudaEventDestroy(w->ev_hits_done);
+	if (w->stream_copy) cudaStreamDestroy(w->stream_copy);
 	cudaFree(w->d_busy); cudaFree(w->d_busy_n); cudaFree(w->d_busy_flag);
 	if (w->stream) cudaStreamDestroy(w->stream);
 	delete w;
@@ -859,6 +866,17 @@ int gpx_step(gpx_world *w, float dt, int collision_steps)
 	return (int)w->m_err[0];
 }
 
+// The world's stream waits for a hits copy still travelling on the copy stream (callers hold w->mu)
+static int join_hits(gpx_world *w)
+{
+	if (w->hits_pending)
+	{
+		GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_hits_done, 0));
+		w->hits_pending = false;
+	}
+	return GPX_OK;
+}
+
 int gpx_sync_transforms(gpx_world *w)
 {
 	if (!w) return GPX_ERR_INVALID_ARG;
@@ -866,6 +884,7 @@ int gpx_sync_transforms(gpx_world *w)
 	cudaSetDevice(w->device);
 	int rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	if ((rc = join_hits(w)) != GPX_OK) return rc;
 	const size_t nb = (size_t)w->W * w->cap;
 	const uint32_t gen = w->mirror_gen.load(std::memory_order_relaxed), back = (gen + 1u) & 1u;
 	// positions | orientations | error word: one allocation on each side, one copy
@@ -938,11 +957,13 @@ int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void 
 	return launch_raycast(w, d_rays, n, d_hits);
 }
 
-static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)
+static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async)
 {
 	{
 		std::lock_guard<std::mutex> lk(w->mu);
 		cudaSetDevice(w->device);
+		int jr = join_hits(w);  // the previous batch's hits leave d_hits before this one's kernel writes it
+		if (jr != GPX_OK) return jr;
 		if (n > w->ray_cap)
 		{
 			GPX_CUDA(cudaStreamSynchronize(w->stream));  // a batch still in flight may be using the old buffers
@@ -958,7 +979,19 @@ static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hi
 	}
 	int rc = gpx_raycast_batch_device(w, w->d_rays, n, w->d_hits);
 	if (rc != GPX_OK) return rc;
-	GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream));
+	if (!async)
+	{
+		GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream));
+		return GPX_OK;
+	}
+	// async: the copy back overlaps whatever the caller enqueues next (the tick); the world's stream picks it up again
+	// at the next gpx_sync_transforms / gpx_device_sync / ray batch
+	std::lock_guard<std::mutex> lk(w->mu);
+	GPX_CUDA(cudaEventRecord(w->ev_rays_done, w->stream));
+	GPX_CUDA(cudaStreamWaitEvent(w->stream_copy, w->ev_rays_done, 0));
+	GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream_copy));
+	GPX_CUDA(cudaEventRecord(w->ev_hits_done, w->stream_copy));
+	w->hits_pending = true;
 	return GPX_OK;
 }
 
@@ -966,7 +999,7 @@ int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hi
 {
 	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
 	if (n == 0) return GPX_OK;
-	int rc = raycast_enqueue(w, rays, n, hits);
+	int rc = raycast_enqueue(w, rays, n, hits, false);
 	if (rc != GPX_OK) return rc;
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;
@@ -976,7 +1009,7 @@ int gpx_raycast_batch_async(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_h
 {
 	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
 	if (n == 0) return GPX_OK;
-	return raycast_enqueue(w, rays, n, hits);
+	return raycast_enqueue(w, rays, n, hits, true);
 }
 
 int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *origin, float max_distance, uint32_t mask,
@@ -1050,6 +1083,10 @@ int gpx_memcpy_d2h(void *dst, const void *src, uint64_t bytes)
 int gpx_device_sync(gpx_world *w)
 {
 	if (!w) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc = join_hits(w);
+	if (rc != GPX_OK) return rc;
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;
 }

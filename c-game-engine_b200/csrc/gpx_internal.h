@@ -115,6 +115,10 @@ struct gpx_world
 	int device = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the 32-lane launch for busy worlds (gpx_tick.cu)
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	// gpx_raycast_batch_async: the hits travel back on their own stream while the tick runs on `stream`
+	cudaStream_t stream_copy = nullptr;
+	cudaEvent_t ev_rays_done = nullptr, ev_hits_done = nullptr;
+	bool hits_pending = false;
 	uint32_t *d_busy = nullptr, *d_busy_n = nullptr;
 	uint8_t *d_busy_flag = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
