@@ -154,3 +154,29 @@ def test_async_batch_is_valid_after_the_tick_sync(gpx, orc, scenes):
         assert g.step() == 0 and o.step() == 0
         assert g.sync() == 0
         _assert_hits_equal(np.asarray(h_hits), ref)
+
+
+def test_async_batches_back_to_back_and_device_sync(gpx, orc, scenes):
+    """The hits of an async batch travel back on a copy stream: two batches in a row (the second must not overwrite the
+    first one's device buffer before it has left), a step in between, and gpx_device_sync as the joining call."""
+    g, o, meshes = _worlds(gpx, orc, scenes, "stacked")
+    d = gpx.body_desc(position=(0.0, -1.0, -1.5))
+    assert g.create(d) == o.create(d)
+    rays_a = scenes.shapes_rays(4000, np.array([p for p, _ in meshes]), mask=gpx.RAYMASK_STATIC_DYNAMIC)
+    rays_b = np.ascontiguousarray(rays_a[::-1])
+    ha, hb = gpx.pinned_array(len(rays_a), gpx.RAY_DTYPE), gpx.pinned_array(len(rays_b), gpx.RAY_DTYPE)
+    oa, ob = gpx.pinned_array(len(rays_a), gpx.HIT_DTYPE), gpx.pinned_array(len(rays_b), gpx.HIT_DTYPE)
+    ha[:] = rays_a
+    hb[:] = rays_b
+    for k in range(4):
+        ref_a = o.raycast(rays_a)
+        g.raycast_into_async(ha, oa)
+        g.raycast_into_async(hb, ob)              # same pre-step state, same device staging buffer
+        ref_b = o.raycast(rays_b)
+        assert g.step() == 0 and o.step() == 0
+        if k & 1:
+            g.device_sync()
+        else:
+            assert g.sync() == 0
+        _assert_hits_equal(np.asarray(oa), ref_a)
+        _assert_hits_equal(np.asarray(ob), ref_b)
