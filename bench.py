@@ -209,7 +209,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(args):
@@ -332,6 +332,7 @@ def run_gpu(args):
         dist.all_gather(out, t)
         gathered_worlds = sum(o.numel() for o in out) // 32
 
+    line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -361,10 +362,10 @@ def run_gpu(args):
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
         }
-        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def make_wide_world(gpx, scenes, pos, device):
@@ -605,10 +606,19 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner at the first
+    # communicator) are sent to stderr by pointing fd 1 at fd 2 while the run lasts
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        os.close(json_fd)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

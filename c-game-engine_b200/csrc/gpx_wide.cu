@@ -163,10 +163,9 @@ __device__ __forceinline__ uint32_t man_prio(uint32_t a, uint32_t b, uint32_t or
 
 // ---------------------------------------------------------------------------------------------------- per body
 
-__global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
+// one body of kw_begin; `ex` / `ez` return the extents of its box along x and z (0 when it has none)
+__device__ __forceinline__ void begin_body(const WideArgs &a, uint32_t i, float &ex, float &ez)
 {
-	const uint32_t i = blockIdx.x * WT + threadIdx.x;
-	if (i >= a.n_pad) return;
 	if (i >= a.nb)
 	{
 		a.keys[i] = ~0ull;
@@ -228,8 +227,24 @@ __global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
 		return;
 	}
 	a.keys[i] = 0ull;  // filled by kw_keys once the largest extents are known
-	atomicMax(&a.cnt[WC_MAXEXT_X], __float_as_uint(fmaxf(b.hi.x - b.lo.x, 0.0f)));
-	atomicMax(&a.cnt[WC_MAXEXT_Z], __float_as_uint(fmaxf(b.hi.z - b.lo.z, 0.0f)));
+	ex = fmaxf(b.hi.x - b.lo.x, 0.0f);
+	ez = fmaxf(b.hi.z - b.lo.z, 0.0f);
+}
+
+__global__ void __launch_bounds__(WT) kw_begin(WideArgs a)
+{
+	const uint32_t i = blockIdx.x * WT + threadIdx.x;
+	float ex = 0.0f, ez = 0.0f;
+	if (i < a.n_pad) begin_body(a, i, ex, ez);
+	// the largest extents: one atomic per warp, not one per body (10^5 atomics on two words of one sector serialise);
+	// non-negative floats order like their bit patterns
+	const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(ex));
+	const uint32_t mz = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(ez));
+	if ((threadIdx.x & 31u) == 0u)
+	{
+		if (mx) atomicMax(&a.cnt[WC_MAXEXT_X], mx);
+		if (mz) atomicMax(&a.cnt[WC_MAXEXT_Z], mz);
+	}
 }
 
 // Sort key: [row: 12 bits][lower x bound, order-preserving: 32 bits][body: 20 bits].  Rows are slabs along z at least
@@ -295,7 +310,14 @@ __device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p
 	const v3 alo = p_first ? V(lo_p) : V(lo_q), ahi = p_first ? V(hi_p) : V(hi_q);
 	const v3 blo = p_first ? V(lo_q) : V(lo_p), bhi = p_first ? V(hi_q) : V(hi_p);
 	if (!aabb_overlap(alo, ahi, blo, bhi, SPECULATIVE_DISTANCE)) return;
-	const uint32_t k = atomicAdd(&a.cnt[WC_NMAN], 1u);
+	// one slot per pair, one atomic per group of lanes that found a pair together (slot order never matters: every
+	// later decision goes by body indices)
+	const unsigned found = __activemask();
+	const unsigned lane = threadIdx.x & 31u;
+	const int leader = __ffs((int)found) - 1;
+	uint32_t k = 0;
+	if ((int)lane == leader) k = atomicAdd(&a.cnt[WC_NMAN], (uint32_t)__popc(found));
+	k = __shfl_sync(found, k, leader) + (uint32_t)__popc(found & ((1u << lane) - 1u));
 	if (k >= a.cap_m)
 	{
 		atomicOr(&a.cnt[WC_ERR], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
