@@ -317,12 +317,13 @@ def run_gpu(args):
     assert (stats["error"] == 0).all()
 
     # ---------------- secondary metric: 2^20 hitscan rays against shapes.gmap (C3)
-    rays_res = bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
+    only = args.headline_only  # profiling runs: the launch list then holds the headline step's kernels and nothing else
+    rays_res = None if only else bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- C4: one wide world of 100k boxes (replicated per rank)
-    single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if rank == 0 else None
-    test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if rank == 0 else None
-    wide_res = None if args.no_wide else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
+    single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if rank == 0 and not only else None
+    test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if rank == 0 and not only else None
+    wide_res = None if args.no_wide or only else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- end-of-run stats gather over NCCL (the only collective)
     gathered_worlds = W
@@ -601,6 +602,7 @@ def main():
     ap.add_argument("--no-wide", action="store_true", help="skip the C4 wide-world section")
     ap.add_argument("--wide-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiling runs)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary sections (rays, C1, C2, C4): profiling runs")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per k_tick launch (profiles/), if known")
     ap.add_argument("--ray-traffic", type=float, default=None)
     args = ap.parse_args()

@@ -323,7 +323,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->d_stats); cudaFree(w->d_cmd); if (w->sd.ray_tri != w->sd.tri) cudaFree(w->sd.ray_tri);
 	if (w->sd.ray_nodes != w->sd.nodes) cudaFree(w->sd.ray_nodes);
 	cudaFree(w->sd.tri); cudaFree(w->sd.nodes);
-	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
+	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_capq); cudaFree(w->d_capo); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);
 	cudaFreeHost(w->mb_pos[0]); cudaFreeHost(w->mb_pos[1]); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
@@ -1037,21 +1037,22 @@ int gpx_overlap_capsule_batch(gpx_world *w, const gpx_capsule_query *queries, ui
 	int rc;
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
-	void *d_q = nullptr, *d_o = nullptr;
-	GPX_CUDA(cudaMalloc(&d_q, 32ull * n));
-	if (cudaMalloc(&d_o, 32ull * n) != cudaSuccess)
+	if (n > w->capq_cap)
 	{
-		cudaFree(d_q);
-		return GPX_ERR_CUDA;
+		GPX_CUDA(cudaStreamSynchronize(w->stream));
+		cudaFree(w->d_capq);
+		cudaFree(w->d_capo);
+		w->d_capq = w->d_capo = nullptr;
+		w->capq_cap = 0;
+		GPX_CUDA(cudaMalloc(&w->d_capq, 32ull * n));
+		GPX_CUDA(cudaMalloc(&w->d_capo, 32ull * n));
+		w->capq_cap = n;
 	}
-	rc = GPX_OK;
-	if (cudaMemcpyAsync(d_q, queries, 32ull * n, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
-	if (rc == GPX_OK) rc = launch_overlap_capsules(w, d_q, n, d_o);
-	if (rc == GPX_OK && cudaMemcpyAsync(out, d_o, 32ull * n, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
-	if (cudaStreamSynchronize(w->stream) != cudaSuccess) rc = GPX_ERR_CUDA;
-	cudaFree(d_q);
-	cudaFree(d_o);
-	return rc;
+	GPX_CUDA(cudaMemcpyAsync(w->d_capq, queries, 32ull * n, cudaMemcpyHostToDevice, w->stream));
+	if ((rc = launch_overlap_capsules(w, w->d_capq, n, w->d_capo)) != GPX_OK) return rc;
+	GPX_CUDA(cudaMemcpyAsync(out, w->d_capo, 32ull * n, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
 }
 
 /* ---- harness helpers */

@@ -172,6 +172,8 @@ struct gpx_world
 	// ray staging
 	void *d_rays = nullptr, *d_hits = nullptr;
 	size_t ray_cap = 0;
+	void *d_capq = nullptr, *d_capo = nullptr;  // staging of gpx_overlap_capsule_batch, grown on demand
+	size_t capq_cap = 0;
 };
 
 namespace gpx {

@@ -9,7 +9,8 @@ python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest 
 python bench.py --impl reference --steps 100 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err
 python tools/phase_profile.py 4096 20 > $out/${tag}_phases.txt 2>&1
-P="python bench.py --steps 12 --warmup 3 --ray-reps 3 --wide-steps 2 --no-cpu"
+# launch list of the headline step alone (value + e2e loops), then of the whole bench's first 1500 launches
+P="python bench.py --steps 12 --warmup 3 --no-cpu --headline-only"
 $P > $out/${tag}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches.csv $P > $out/${tag}_ncu1.log 2>&1
 Q="python bench.py --steps 12 --warmup 3 --ray-reps 3 --no-wide --no-cpu"
