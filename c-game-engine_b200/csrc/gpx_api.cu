@@ -256,8 +256,8 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	ok = ok && cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) == cudaSuccess &&
 		 cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
 		 cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
-	ok = ok && dalloc(&w->d_busy, (size_t)cfg->worlds) == GPX_OK && dalloc(&w->d_busy_n, 1) == GPX_OK &&
-		 dalloc(&w->d_busy_flag, (size_t)cfg->worlds) == GPX_OK;
+	ok = ok && dalloc(&w->d_busy, 2 * (size_t)cfg->worlds) == GPX_OK && dalloc(&w->d_busy_n, 2) == GPX_OK &&
+		 dalloc(&w->d_busy_flag, 2 * (size_t)cfg->worlds) == GPX_OK;  // two routing sets, see launch_tick
 	// positions, orientations and the error words share ONE allocation (and so do their host mirrors): what
 	// gpx_sync_transforms reads back every tick is a single contiguous copy
 	{

@@ -121,6 +121,7 @@ struct gpx_world
 	bool hits_pending = false;
 	uint32_t *d_busy = nullptr, *d_busy_n = nullptr;
 	uint8_t *d_busy_flag = nullptr;
+	uint32_t busy_cur = 0;  // which of the two routing sets (list / count / flags) the coming tick reads
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint32_t W = 0, cap = 0, cap_m = 0;
 

@@ -52,6 +52,10 @@ struct TickArgs
 	uint32_t *ev_count;
 	const uint32_t *busy_list, *busy_count;  // worlds routed to the 32-lane launch (that launch only)
 	const uint8_t *busy_flag;                // narrow launch: skip these worlds
+	// the same three for the NEXT tick, written by whichever launch runs a world (nullptr: no split for this world set)
+	uint32_t *next_list, *next_count;
+	uint8_t *next_flag;
+	uint32_t next_above;                     // a world that ends the tick with more manifolds than this is "busy"
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
 };
@@ -152,6 +156,24 @@ __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *m
 		}
 }
 
+// Routing of the next tick, decided where the manifold count is known (the end of this one): next_list[0 .. n) = worlds
+// for the 32-lane launch, next_flag[world] = 1 for exactly those.  The order of the list does not matter.
+__device__ __forceinline__ void route_next(const TickArgs &a, uint32_t world, uint32_t count)
+{
+	if (!a.next_flag) return;
+	uint8_t f = 0;
+	if (count > a.next_above)
+	{
+		const uint32_t k = atomicAdd(a.next_count, 1u);
+		if (k < MAX_BUSY_WORLDS)
+		{
+			a.next_list[k] = world;
+			f = 1;
+		}
+	}
+	a.next_flag[world] = f;
+}
+
 template <int TILE>
 __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 {
@@ -229,7 +251,11 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	// whether or not this shortcut was taken.  (With contact events on, the pass below still has to report the pairs.)
 	if (!a.ev_out && !tile.any(any_active))
 	{
-		if (lane == 0) a.mc.count[world] = 0;
+		if (lane == 0)
+		{
+			a.mc.count[world] = 0;
+			route_next(a, world, 0);
+		}
 		return;
 	}
 	const uint32_t m0 = world * cap_m;
@@ -675,6 +701,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	if (lane == 0)
 	{
 		a.mc.count[world] = hdr[1];
+		route_next(a, world, hdr[1]);
 		if (hdr[3])
 		{
 			a.err[1 + world] |= hdr[3];
@@ -842,25 +869,6 @@ __global__ void k_stats(BodyStore bs, ManifoldCache mc, const uint32_t *err, uin
 	}
 }
 
-// list[0 .. n) = worlds for the 32-lane launch, flag[world] = 1 for exactly those
-__global__ void k_classify(const uint32_t *__restrict__ count, uint32_t worlds, uint32_t above, uint32_t *list, uint32_t *n,
-						   uint8_t *flag)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= worlds) return;
-	uint8_t f = 0;
-	if (count[i] > above)
-	{
-		const uint32_t k = atomicAdd(n, 1u);
-		if (k < MAX_BUSY_WORLDS)
-		{
-			list[k] = i;
-			f = 1;
-		}
-	}
-	flag[i] = f;
-}
-
 template <int TILE>
 static int launch_tick_t(gpx_world *w, const TickArgs &a, cudaStream_t stream, uint32_t grid_worlds)
 {
@@ -919,22 +927,31 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.p.h = dt / (float)substeps;
 	a.busy_list = a.busy_count = nullptr;
 	a.busy_flag = nullptr;
+	a.next_list = a.next_count = nullptr;
+	a.next_flag = nullptr;
+	a.next_above = 0;
 	if (w->cap > 16 || w->W < 64) return launch_tick_t<32>(w, a, w->stream, w->W);
 	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane
-	// launch on a second stream takes the rest; both read the same per-world counts, so each world runs exactly once.
+	// launch on a second stream takes the rest.  Each world wrote its own routing at the end of its previous tick
+	// (route_next; two sets of list / count / flags, used alternately), so each world runs exactly once and no
+	// classification kernel sits in front of the two launches.
 	const uint32_t tile = w->cap <= 8 ? 8u : 16u;
 	int rc;
-	GPX_CUDA(cudaMemsetAsync(w->d_busy_n, 0, sizeof(uint32_t), w->stream));
-	k_classify<<<(w->W + 255) / 256, 256, 0, w->stream>>>(w->mc.count, w->W, tile, w->d_busy, w->d_busy_n, w->d_busy_flag);
-	count_launch();
+	const uint32_t cur = w->busy_cur, nxt = cur ^ 1u;
+	w->busy_cur = nxt;
+	GPX_CUDA(cudaMemsetAsync(w->d_busy_n + nxt, 0, sizeof(uint32_t), w->stream));
+	a.next_list = w->d_busy + (size_t)nxt * w->W;
+	a.next_count = w->d_busy_n + nxt;
+	a.next_flag = w->d_busy_flag + (size_t)nxt * w->W;
+	a.next_above = tile;
 	GPX_CUDA(cudaEventRecord(w->ev_fork, w->stream));
 	GPX_CUDA(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
 	TickArgs b = a;
-	b.busy_list = w->d_busy;
-	b.busy_count = w->d_busy_n;
+	b.busy_list = w->d_busy + (size_t)cur * w->W;
+	b.busy_count = w->d_busy_n + cur;
 	if ((rc = launch_tick_t<32>(w, b, w->stream2, w->W < MAX_BUSY_WORLDS ? w->W : MAX_BUSY_WORLDS)) != GPX_OK) return rc;
 	GPX_CUDA(cudaEventRecord(w->ev_join, w->stream2));
-	a.busy_flag = w->d_busy_flag;
+	a.busy_flag = w->d_busy_flag + (size_t)cur * w->W;
 	rc = tile == 8u ? launch_tick_t<8>(w, a, w->stream, w->W) : launch_tick_t<16>(w, a, w->stream, w->W);
 	GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
 	return rc;
