@@ -947,6 +947,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	GPX_CUDA(cudaEventRecord(w->ev_fork, w->stream));
 	GPX_CUDA(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
 	TickArgs b = a;
+	if (getenv("GPX_PHASE_BUSY_ONLY")) a.phase_cycles = nullptr;  // debugging: phase counters of the 32-lane launch alone
 	b.busy_list = w->d_busy + (size_t)cur * w->W;
 	b.busy_count = w->d_busy_n + cur;
 	if ((rc = launch_tick_t<32>(w, b, w->stream2, w->W < MAX_BUSY_WORLDS ? w->W : MAX_BUSY_WORLDS)) != GPX_OK) return rc;
