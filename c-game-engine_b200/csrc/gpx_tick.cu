@@ -55,6 +55,7 @@ struct TickArgs
 	// the same three for the NEXT tick, written by whichever launch runs a world (nullptr: no split for this world set)
 	uint32_t *next_list, *next_count;
 	uint8_t *next_flag;
+	const uint8_t *cur_flag;                 // this tick's flags as seen by BOTH launches (busy_flag is the narrow launch's)
 	uint32_t next_above;                     // a world that ends the tick with more manifolds than this is "busy"
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
 	TickParams p;
@@ -158,20 +159,25 @@ __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *m
 
 // Routing of the next tick, decided where the manifold count is known (the end of this one): next_list[0 .. n) = worlds
 // for the 32-lane launch, next_flag[world] = 1 for exactly those.  The order of the list does not matter.
+// A world that needed the wide launch stays on it for BUSY_STICKY more ticks: a tipping column hovers around the limit,
+// and every tick it spends on a narrow tile with one manifold too many holds up the whole wave.  The flag byte is the
+// number of ticks left.
+constexpr uint32_t BUSY_STICKY = 30;
 __device__ __forceinline__ void route_next(const TickArgs &a, uint32_t world, uint32_t count)
 {
 	if (!a.next_flag) return;
-	uint8_t f = 0;
-	if (count > a.next_above)
+	const uint32_t left = a.cur_flag[world];
+	uint32_t f = count > a.next_above ? BUSY_STICKY : (left > 1u ? left - 1u : 0u);
+	if (count == 0) f = 0;  // an idle world has no tick to run
+	if (f)
 	{
 		const uint32_t k = atomicAdd(a.next_count, 1u);
 		if (k < MAX_BUSY_WORLDS)
-		{
 			a.next_list[k] = world;
-			f = 1;
-		}
+		else
+			f = 0;
 	}
-	a.next_flag[world] = f;
+	a.next_flag[world] = (uint8_t)f;
 }
 
 template <int TILE>
@@ -929,6 +935,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.busy_flag = nullptr;
 	a.next_list = a.next_count = nullptr;
 	a.next_flag = nullptr;
+	a.cur_flag = nullptr;
 	a.next_above = 0;
 	if (w->cap > 16 || w->W < 64) return launch_tick_t<32>(w, a, w->stream, w->W);
 	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane
@@ -944,6 +951,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.next_count = w->d_busy_n + nxt;
 	a.next_flag = w->d_busy_flag + (size_t)nxt * w->W;
 	a.next_above = tile;
+	a.cur_flag = w->d_busy_flag + (size_t)cur * w->W;
 	GPX_CUDA(cudaEventRecord(w->ev_fork, w->stream));
 	GPX_CUDA(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
 	TickArgs b = a;
