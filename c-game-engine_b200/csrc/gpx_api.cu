@@ -278,7 +278,7 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	ok = ok && dalloc(&w->mc.count, (size_t)w->W) == GPX_OK;
 	if (!wide)
 		ok = ok && dalloc(&w->mc.key, nm) == GPX_OK && dalloc(&w->mc.p1, nm * 4) == GPX_OK && dalloc(&w->mc.p2, nm * 4) == GPX_OK &&
-			 dalloc(&w->mc.lt2, nm) == GPX_OK && dalloc(&w->d_park, nm * 9) == GPX_OK;
+			 dalloc(&w->d_park, nm * 31) == GPX_OK;
 	else
 		ok = ok && wide_create(w) == GPX_OK;
 	ok = ok && cudaMalloc(&w->d_cand, sizeof(uint4) * 8 * nb) == cudaSuccess &&
@@ -319,7 +319,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->bs.pos); /* + quat, d_err: one allocation */ cudaFree(w->bs.lin); cudaFree(w->bs.ang);
 	cudaFree(w->bs.prop0); cudaFree(w->bs.prop1); cudaFree(w->bs.prop2); cudaFree(w->bs.flags);
 	cudaFree(w->bs.sleep_c); cudaFree(w->bs.sleep_t);
-	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.lt2); cudaFree(w->mc.count);
+	cudaFree(w->mc.key); cudaFree(w->mc.p1); cudaFree(w->mc.p2); cudaFree(w->mc.count);
 	cudaFree(w->d_stats); cudaFree(w->d_cmd); if (w->sd.ray_tri != w->sd.tri) cudaFree(w->sd.ray_tri);
 	if (w->sd.ray_nodes != w->sd.nodes) cudaFree(w->sd.ray_nodes);
 	cudaFree(w->sd.tri); cudaFree(w->sd.nodes);

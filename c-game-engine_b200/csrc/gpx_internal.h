@@ -50,8 +50,8 @@ struct ManifoldCache
 {
 	uint4 *key;       // a, b, np, 0
 	float4 *p1;       // 4 per manifold: local point on a, w = normal lambda
-	float4 *p2;       // 4 per manifold: local point on b (static: world), w = tangent-1 lambda
-	float4 *lt2;      // tangent-2 lambdas of the 4 points
+	float4 *p2;       // 4 per manifold: local point on b (static: world); w of the first three = the manifold's friction
+	                  // impulse (tangent 1, tangent 2, twist)
 	uint32_t *count;  // per world
 };
 
@@ -163,7 +163,7 @@ struct gpx_world
 	unsigned long long *d_ch_keys = nullptr;
 	uint32_t *d_ch_nkeys = nullptr;
 	std::vector<gpx::CharDev> h_ch;
-	float4 *d_park = nullptr;  // 9 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
+	float4 *d_park = nullptr;  // 31 float4 per manifold slot (gpx_tick.cu, worlds with more manifolds than lanes)
 	gpx::WideDevice *wide = nullptr;  // non-null: this world runs the wide-world kernels
 	uint4 *d_cand = nullptr;  // static-candidate cache, 8 x uint4 per body (gpx_tick.cu)
 	unsigned long long *d_phase = nullptr;  // 16 counters, allocated by gpx_debug_phase_cycles(enable)

@@ -24,7 +24,7 @@ struct SBody  // 39 words: odd stride, conflict-free when lane = body
 	float inv_mass;  // as stored in the body store
 };
 
-struct SMan  // 49 words (odd stride): what outlives one manifold's register-resident solve
+struct SMan  // 41 words (odd stride): a contact manifold between narrowphase, solver and warm-start cache
 {
 	uint32_t a, b;
 	int np;      // 0 = empty slot (pair that did not touch)
@@ -32,31 +32,62 @@ struct SMan  // 49 words (odd stride): what outlives one manifold's register-res
 	v3 n;
 	float friction, restitution;
 	v3 p1l[4], p2l[4];
-	float ln[4], lt1[4], lt2[4];
-	float bias[4];
+	float ln[4];  // accumulated non-penetration impulse per point
+	float cf[3];  // accumulated friction impulse of the manifold: tangent 1, tangent 2 (through the centroid), twist about n
+	float pad;
 };
 
-// One manifold's constraint rows while its lane iterates (phase 7).  The per-manifold part lives in registers; the
-// per-point part (lever arms, effective masses) in a small per-lane record in shared memory so that the four points
-// run through ONE rolled loop body — fully unrolled, the velocity iteration alone was ~18 KB of SASS and the warps
-// spent a third of their time waiting for instruction fetch.  Accumulated impulses and biases are read and written
-// in place in the manifold record.
+// One constraint row: the velocity it measures is Jv = (axis . va + a1 . wa) - (axis . vb + a2 . wb); an impulse d along it
+// changes va by -lA d, wa by -I1 d, vb by +lB d, wb by +I2 d (lA / lB = axis times the body's inverse mass, kept once per
+// axis in Rows).  em = 1 / (J M^-1 J^T).  Everything an iteration needs is precomputed: a row costs 12 FMAs to measure
+// and 12 to apply.
+struct Row
+{
+	v3 a1, a2;  // r1 x axis, r2 x axis
+	v3 I1, I2;  // world inverse inertia times a1 / a2
+	float em;
+};
+
+// The friction rows of a manifold: two tangent rows through the centroid of the contact points plus a twist row about
+// the normal, limited by friction x (sum of the normal impulses) (x the patch radius for the twist).  52 words = 13
+// float4: with that stride the 16-byte shared-memory loads of a quarter-warp fall on different banks.
+struct __align__(16) FricRows
+{
+	Row t[2];
+	v3 wI1, wI2;  // twist row: inverse inertias times the normal
+	float wem;
+	float rp;     // patch radius: RMS distance of the contact points from their centroid
+	v3 tA[2], tB[2];  // tangent times inverse mass, locked translation axes zeroed
+	float pad[6];
+};
+static_assert(sizeof(FricRows) == 52 * sizeof(float), "FricRows is staged as 13 float4");
+
+// The rows of one manifold, rebuilt every sub-step from the bodies' poses: a non-penetration row per contact point
+// (rows of points the manifold does not have are zero: they measure nothing and apply nothing) and the friction rows.
+// In the ensemble kernel a lane keeps the non-penetration rows in REGISTERS for the whole velocity solve (every index
+// is a compile-time constant after unrolling) and the friction rows, which an iteration visits once, in its slice of
+// shared memory; the wide-world kernels keep everything in their solver records.
+struct __align__(16) Rows
+{
+	Row n[4];
+	float bias[4];
+	float ln[4];  // words 56..59 (float4 14 of the parked record)
+	float cf[3];  // words 60..62 (float4 15)
+	float pad;
+	v3 nA, nB;    // normal times inverse mass, locked translation axes zeroed
+	float pad2[2];
+	FricRows f;
+};
+static_assert(sizeof(Rows) == 124 * sizeof(float), "Rows is parked as 31 float4");
+
+// What a manifold's lane needs besides the rows.
 struct Con
 {
 	uint32_t ia, ib;
 	bool has_b, a_dyn, b_dyn;
-	uint32_t a_dofs, b_dofs;
-	float ima, imb;
-	float MA[6], MB[6];
 	int np;
 	float friction;
 	v3 n, t1, t2;
-};
-
-struct ConPts  // 36 words
-{
-	v3 r1[4], r2[4];
-	float em[4][3];
 };
 
 
@@ -372,32 +403,14 @@ __device__ __forceinline__ float eff_mass(float ima, const float *MA, float imb,
 	return k > 0.0f ? 1.0f / k : 0.0f;
 }
 
+// v - t * s
+__device__ __forceinline__ v3 msub(v3 v, v3 t, float s) { return V(fmaf(-t.x, s, v.x), fmaf(-t.y, s, v.y), fmaf(-t.z, s, v.z)); }
+
 // The two bodies' velocities of one manifold, in registers for the duration of one colour phase.
 struct Vel
 {
 	v3 va, wa, vb, wb;
 };
-
-__device__ __forceinline__ v3 rel_vel(const Con &c, const Vel &u, v3 r1, v3 r2)
-{
-	v3 ua = u.va + cross(u.wa, r1);
-	if (!c.has_b) return ua;
-	return ua - (u.vb + cross(u.wb, r2));
-}
-
-__device__ __forceinline__ void apply_impulse(const Con &c, Vel &u, v3 r1, v3 r2, v3 P)
-{
-	if (c.a_dyn)
-	{
-		u.va = u.va - mask_lin(c.a_dofs, P * c.ima);
-		u.wa = u.wa - sym_mul(c.MA, cross(r1, P));
-	}
-	if (c.has_b && c.b_dyn)
-	{
-		u.vb = u.vb + mask_lin(c.b_dofs, P * c.imb);
-		u.wb = u.wb + sym_mul(c.MB, cross(r2, P));
-	}
-}
 
 __device__ __forceinline__ void load_vel(const Con &c, const SBody *bodies, Vel &u)
 {
@@ -426,8 +439,33 @@ __device__ __forceinline__ void store_vel(const Con &c, SBody *bodies, const Vel
 	}
 }
 
-// Per-manifold part of the constraint set-up (reads body state only)
-__device__ __forceinline__ void con_header(Con &c, const SMan &m, const SBody *bodies)
+__device__ __forceinline__ void row_setup(Row &r, float ima, const float *MA, float imb, const float *MB, v3 r1, v3 r2, v3 axis)
+{
+	r.a1 = cross(r1, axis);
+	r.a2 = cross(r2, axis);
+	r.I1 = sym_mul(MA, r.a1);
+	r.I2 = sym_mul(MB, r.a2);
+	const float k = ((ima + imb) + dot(r.a1, r.I1)) + dot(r.a2, r.I2);
+	r.em = k > 0.0f ? 1.0f / k : 0.0f;
+}
+
+__device__ __forceinline__ float row_jv(const Row &r, v3 axis, const Vel &u)
+{
+	return (dot(axis, u.va) + dot(r.a1, u.wa)) - (dot(axis, u.vb) + dot(r.a2, u.wb));
+}
+
+__device__ __forceinline__ void row_apply(const Row &r, v3 lA, v3 lB, float d, Vel &u)
+{
+	u.va = msub(u.va, lA, d);
+	u.wa = msub(u.wa, r.I1, d);
+	u.vb = madd(u.vb, lB, d);
+	u.wb = madd(u.wb, r.I2, d);
+}
+
+// Set-up of one manifold (reads body state only): header, rows, speculative / restitution bias; the accumulated impulses
+// move from the manifold record into the rows.  Rows of points the manifold does not have are zero: they measure
+// nothing and apply nothing.
+__device__ __forceinline__ void build_rows(Con &c, Rows &R, const SMan &m, const SBody *bodies, float h)
 {
 	const SBody &A = bodies[m.a];
 	c.ia = m.a;
@@ -436,16 +474,123 @@ __device__ __forceinline__ void con_header(Con &c, const SMan &m, const SBody *b
 	const SBody &B = bodies[c.ib];
 	c.a_dyn = is_dynamic(A.flags);
 	c.b_dyn = c.has_b && is_dynamic(B.flags);
-	c.a_dofs = dofs_of(A.flags);
-	c.b_dofs = dofs_of(B.flags);
-	c.ima = A.im;
-	c.imb = c.has_b ? B.im : 0.0f;
+	const uint32_t a_dofs = dofs_of(A.flags), b_dofs = dofs_of(B.flags);
+	const float ima = A.im, imb = c.has_b ? B.im : 0.0f;
+	float MA[6], MB[6];
 #pragma unroll
 	for (int k = 0; k < 6; k++)
 	{
-		c.MA[k] = A.M[k];
-		c.MB[k] = c.has_b ? B.M[k] : 0.0f;
+		MA[k] = A.M[k];
+		MB[k] = c.has_b ? B.M[k] : 0.0f;
 	}
+	c.np = m.np;
+	c.friction = m.friction;
+	c.n = m.n;
+	c.t1 = vperp(c.n);
+	c.t2 = cross(c.n, c.t1);
+	const v3 zero = V(0.0f, 0.0f, 0.0f);
+	R.nA = mask_lin(a_dofs, c.n * ima);
+	R.f.tA[0] = mask_lin(a_dofs, c.t1 * ima);
+	R.f.tA[1] = mask_lin(a_dofs, c.t2 * ima);
+	R.nB = c.has_b ? mask_lin(b_dofs, c.n * imb) : zero;
+	R.f.tB[0] = c.has_b ? mask_lin(b_dofs, c.t1 * imb) : zero;
+	R.f.tB[1] = c.has_b ? mask_lin(b_dofs, c.t2 * imb) : zero;
+	const v3 ax = A.x, bx = B.x;
+	const q4 aq = A.q, bq = B.q;
+	Vel u;
+	load_vel(c, bodies, u);
+	v3 mid[4];
+	v3 csum = zero;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		if (k < c.np)
+		{
+			const v3 p1 = ax + qrot(aq, m.p1l[k]);
+			const v3 p2 = c.has_b ? bx + qrot(bq, m.p2l[k]) : m.p2l[k];
+			mid[k] = (p1 + p2) * 0.5f;
+			csum = csum + mid[k];
+			const v3 r1 = mid[k] - ax;
+			const v3 r2 = c.has_b ? mid[k] - bx : zero;
+			row_setup(R.n[k], ima, MA, imb, MB, r1, r2, c.n);
+			const float pen = dot(p1 - p2, c.n);
+			float bias = fmaxf(0.0f, -pen / h);
+			if (m.restitution > 0.0f)
+			{
+				const float nv = -row_jv(R.n[k], c.n, u);
+				if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
+			}
+			R.bias[k] = bias;
+			R.ln[k] = m.ln[k];
+		}
+		else
+		{
+			mid[k] = zero;
+			R.n[k].a1 = R.n[k].a2 = R.n[k].I1 = R.n[k].I2 = zero;
+			R.n[k].em = 0.0f;
+			R.bias[k] = 0.0f;
+			R.ln[k] = 0.0f;
+		}
+	}
+	R.cf[0] = m.cf[0];
+	R.cf[1] = m.cf[1];
+	R.cf[2] = m.cf[2];
+	R.pad = R.pad2[0] = R.pad2[1] = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 6; k++) R.f.pad[k] = 0.0f;
+	const float inv_np = 1.0f / (float)c.np;
+	const v3 cen = csum * inv_np;
+	float s = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (k < c.np) s = s + len2(mid[k] - cen);
+	R.f.rp = sqrtf(s * inv_np);
+	const v3 rc1 = cen - ax, rc2 = c.has_b ? cen - bx : zero;
+	row_setup(R.f.t[0], ima, MA, imb, MB, rc1, rc2, c.t1);
+	row_setup(R.f.t[1], ima, MA, imb, MB, rc1, rc2, c.t2);
+	R.f.wI1 = sym_mul(MA, c.n);
+	R.f.wI2 = sym_mul(MB, c.n);
+	const float kw = dot(c.n, R.f.wI1) + dot(c.n, R.f.wI2);
+	R.f.wem = kw > 0.0f ? 1.0f / kw : 0.0f;
+}
+
+// accumulated impulses back into the manifold record (warm-start cache, position pass keep using SMan)
+__device__ __forceinline__ void save_impulses(SMan &m, const Rows &R)
+{
+#pragma unroll
+	for (int k = 0; k < 4; k++) m.ln[k] = R.ln[k];
+	m.cf[0] = R.cf[0];
+	m.cf[1] = R.cf[1];
+	m.cf[2] = R.cf[2];
+}
+
+// Rows <-> 31 float4 in global memory (worlds with more manifolds than lanes)
+__device__ __forceinline__ void park_rows(const Rows &R, float4 *g)
+{
+	const float *f = reinterpret_cast<const float *>(&R);
+#pragma unroll
+	for (int i = 0; i < 31; i++) __stcg(&g[i], make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
+}
+
+__device__ __forceinline__ void unpark_rows(Rows &R, const float4 *g)
+{
+	float *f = reinterpret_cast<float *>(&R);
+#pragma unroll
+	for (int i = 0; i < 31; i++)
+	{
+		const float4 v = __ldcg(&g[i]);
+		f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+	}
+}
+
+// the manifold header alone, for a lane that pulls parked rows
+__device__ __forceinline__ void con_header(Con &c, const SMan &m, const SBody *bodies)
+{
+	c.ia = m.a;
+	c.has_b = m.b < STATIC_BODY_BASE;
+	c.ib = c.has_b ? m.b : m.a;
+	c.a_dyn = is_dynamic(bodies[c.ia].flags);
+	c.b_dyn = c.has_b && is_dynamic(bodies[c.ib].flags);
 	c.np = m.np;
 	c.friction = m.friction;
 	c.n = m.n;
@@ -453,113 +598,74 @@ __device__ __forceinline__ void con_header(Con &c, const SMan &m, const SBody *b
 	c.t2 = cross(c.n, c.t1);
 }
 
-// Full set-up of one manifold: header + per-point lever arms / effective masses into `pt`, and the speculative /
-// restitution bias into the manifold record.
-__device__ __forceinline__ void build_con(Con &c, ConPts &pt, SMan &m, const SBody *bodies, float h)
+// re-apply the impulses carried over from the previous sub-step.  `F` are the manifold's friction rows: R.f or a copy.
+__device__ __forceinline__ void warm_start(const Con &c, const Rows &R, const FricRows &F, Vel &u)
 {
-	con_header(c, m, bodies);
-	const SBody &A = bodies[c.ia], &B = bodies[c.ib];
-	const v3 ax = A.x, bx = B.x;
-	const q4 aq = A.q, bq = B.q;
-	Vel u;
-	load_vel(c, bodies, u);
-#pragma unroll 1
-	for (int k = 0; k < c.np; k++)
-	{
-		v3 p1 = ax + qrot(aq, m.p1l[k]);
-		v3 p2 = c.has_b ? bx + qrot(bq, m.p2l[k]) : m.p2l[k];
-		v3 mid = (p1 + p2) * 0.5f;
-		const v3 r1 = mid - ax;
-		const v3 r2 = c.has_b ? mid - bx : V(0.0f, 0.0f, 0.0f);
-		pt.r1[k] = r1;
-		pt.r2[k] = r2;
-		pt.em[k][0] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.n);
-		pt.em[k][1] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.t1);
-		pt.em[k][2] = eff_mass(c.ima, c.MA, c.imb, c.MB, r1, r2, c.t2);
-		float pen = dot(p1 - p2, c.n);
-		float bias = fmaxf(0.0f, -pen / h);
-		if (m.restitution > 0.0f)
-		{
-			float nv = -dot(c.n, rel_vel(c, u, r1, r2));
-			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m.restitution * nv;
-		}
-		m.bias[k] = bias;
-	}
-}
-
-// ConPts <-> 9 float4 in global memory (worlds with more manifolds than lanes; the wide-world kernels)
-__device__ __forceinline__ void park_con(const ConPts &pt, float4 *g)
-{
-	const float *f = reinterpret_cast<const float *>(&pt);
 #pragma unroll
-	for (int i = 0; i < 9; i++) __stcg(&g[i], make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
+	for (int k = 0; k < 4; k++) row_apply(R.n[k], R.nA, R.nB, R.ln[k], u);
+	row_apply(F.t[0], F.tA[0], F.tB[0], R.cf[0], u);
+	row_apply(F.t[1], F.tA[1], F.tB[1], R.cf[1], u);
+	u.wa = msub(u.wa, F.wI1, R.cf[2]);
+	u.wb = madd(u.wb, F.wI2, R.cf[2]);
 }
 
-__device__ __forceinline__ void unpark_con(ConPts &pt, const float4 *g)
+__device__ __forceinline__ void normal_row(const Con &c, Rows &R, int k, Vel &u)
 {
-	float *f = reinterpret_cast<float *>(&pt);
-#pragma unroll
-	for (int i = 0; i < 9; i++)
-	{
-		const float4 v = __ldcg(&g[i]);
-		f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
-	}
+	float lambda = R.n[k].em * (row_jv(R.n[k], c.n, u) - R.bias[k]);
+	const float nt = fmaxf(0.0f, R.ln[k] + lambda);
+	lambda = nt - R.ln[k];
+	R.ln[k] = nt;
+	row_apply(R.n[k], R.nA, R.nB, lambda, u);
 }
 
-// `M` is any record with ln / lt1 / lt2 (and, for solve_velocity, bias) arrays: the manifold itself or a solver record
-template <typename M>
-__device__ __forceinline__ void warm_start(const Con &c, const ConPts &pt, const M &m, Vel &u)
+// One velocity iteration of a manifold: friction first (non-penetration is more important, so it goes last) — the two
+// tangent rows through the centroid share one limit, then the twist row — then the four non-penetration rows, forwards
+// in even iterations and backwards in odd ones (a fixed order leaves the residual on the same point every time, and a
+// tall stack turns that bias into a whirl that never dies).
+__device__ __forceinline__ void solve_velocity(const Con &c, Rows &R, const FricRows &F, Vel &u, uint32_t it)
 {
-#pragma unroll 1
-	for (int k = 0; k < c.np; k++)
+	const float maxf = c.friction * (((R.ln[0] + R.ln[1]) + R.ln[2]) + R.ln[3]);
+	// nothing to hold with and nothing held (speculative points that do not touch): the rows stay at zero
+	if (!(maxf == 0.0f && R.cf[0] == 0.0f && R.cf[1] == 0.0f))
 	{
-		const float ln = m.ln[k], lt1 = m.lt1[k], lt2 = m.lt2[k];
-		if (ln == 0.0f && lt1 == 0.0f && lt2 == 0.0f) continue;
-		v3 P = ((c.n * ln) + (c.t1 * lt1)) + (c.t2 * lt2);
-		apply_impulse(c, u, pt.r1[k], pt.r2[k], P);
-	}
-}
-
-template <typename M>
-__device__ __forceinline__ void solve_velocity(const Con &c, const ConPts &pt, M &m, Vel &u)
-{
-	// friction first: non-penetration is more important, so it goes last
-#pragma unroll 1
-	for (int k = 0; k < c.np; k++)
-	{
-		const float o1 = m.lt1[k], o2 = m.lt2[k];
-		const float maxf = c.friction * m.ln[k];
-		// nothing to hold with and nothing held (a speculative point that does not touch): the row stays at zero
-		if (maxf == 0.0f && o1 == 0.0f && o2 == 0.0f) continue;
-		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
-		v3 rv = rel_vel(c, u, r1, r2);
-		float l1 = o1 + (pt.em[k][1] * dot(c.t1, rv));
-		float l2 = o2 + (pt.em[k][2] * dot(c.t2, rv));
-		float sq = (l1 * l1) + (l2 * l2);
+		float l1 = R.cf[0] + (F.t[0].em * row_jv(F.t[0], c.t1, u));
+		float l2 = R.cf[1] + (F.t[1].em * row_jv(F.t[1], c.t2, u));
+		const float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
-			// no normal impulse yet (a speculative point): 0 / sqrt(sq) is that zero, skip the division and the root
-			float s = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
-			l1 = l1 * s;
-			l2 = l2 * s;
+			// no normal impulse: 0 / sqrt(sq) is that zero, skip the division and the root
+			const float sc = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
+			l1 = l1 * sc;
+			l2 = l2 * sc;
 		}
-		const float d1 = l1 - o1, d2 = l2 - o2;
-		m.lt1[k] = l1;
-		m.lt2[k] = l2;
-		// an impulse is applied only when it is not zero (Jolt's AxisConstraintPart::ApplyVelocityStep)
-		if (d1 != 0.0f || d2 != 0.0f) apply_impulse(c, u, r1, r2, (c.t1 * d1) + (c.t2 * d2));
+		const float d1 = l1 - R.cf[0], d2 = l2 - R.cf[1];
+		R.cf[0] = l1;
+		R.cf[1] = l2;
+		row_apply(F.t[0], F.tA[0], F.tB[0], d1, u);
+		row_apply(F.t[1], F.tA[1], F.tB[1], d2, u);
 	}
-#pragma unroll 1
-	for (int k = 0; k < c.np; k++)
+	if (c.np >= 2)
 	{
-		const v3 r1 = pt.r1[k], r2 = pt.r2[k];
-		const float old = m.ln[k];
-		v3 rv = rel_vel(c, u, r1, r2);
-		float lambda = pt.em[k][0] * (dot(c.n, rv) - m.bias[k]);
-		float nt = fmaxf(0.0f, old + lambda);
-		lambda = nt - old;
-		m.ln[k] = nt;
-		if (lambda != 0.0f) apply_impulse(c, u, r1, r2, c.n * lambda);
+		const float lim = maxf * F.rp;
+		if (!(lim == 0.0f && R.cf[2] == 0.0f))
+		{
+			float l = R.cf[2] + (F.wem * (dot(c.n, u.wa) - dot(c.n, u.wb)));
+			l = fminf(fmaxf(l, -lim), lim);
+			const float d = l - R.cf[2];
+			R.cf[2] = l;
+			u.wa = msub(u.wa, F.wI1, d);
+			u.wb = madd(u.wb, F.wI2, d);
+		}
+	}
+	if (it & 1u)
+	{
+#pragma unroll
+		for (int k = 3; k >= 0; k--) normal_row(c, R, k, u);
+	}
+	else
+	{
+#pragma unroll
+		for (int k = 0; k < 4; k++) normal_row(c, R, k, u);
 	}
 }
 
@@ -622,7 +728,8 @@ __device__ __forceinline__ void store_points(SMan &m, const SBody &A, const SBod
 		m.p1l[i] = mtmul(RA, p1[i] - A.x);
 		m.p2l[i] = B ? mtmul(RB, p2[i] - B->x) : p2[i];
 	}
-	for (int i = 0; i < 4; i++) m.ln[i] = m.lt1[i] = m.lt2[i] = 0.0f;
+	for (int i = 0; i < 4; i++) m.ln[i] = 0.0f;
+	m.cf[0] = m.cf[1] = m.cf[2] = 0.0f;
 }
 
 struct StaticSlot

@@ -41,7 +41,7 @@ struct TickArgs
 	const float4 *tris;
 	uint32_t n_nodes;
 	uint32_t *err;  // [0] OR of all worlds' errors, [1 + world] per world
-	float4 *con_park;  // 9 float4 per manifold slot: parked solver constants of worlds with more manifolds than lanes
+	float4 *con_park;  // 31 float4 per manifold slot: parked solver rows of worlds with more manifolds than lanes
 	uint4 *cand;  // per body 8 x uint4: {count, -, -, -}, {fat lo xyz, -}, {fat hi xyz, -}... see cand_* below
 	// contact events (gpx_events_enable): per world the sorted touching pairs of the previous tick and this tick's events
 	const unsigned long long *ch_keys;  // the player character's contacts (gpx_char.cu), 64 per world, or nullptr
@@ -89,9 +89,10 @@ struct PhaseClock
 __host__ __device__ inline size_t world_scratch_bytes(uint32_t tile, uint32_t cap_m)
 {
 	// also: (cap_m + 64) 8-byte keys for the contact-event pass at the end of the tick
-	size_t a = sizeof(Scratch) * tile, b = sizeof(uint32_t) * 3 * cap_m, c = 8u * ((size_t)cap_m + CHARACTER_MAX_CONTACTS);
+	size_t a = (sizeof(Scratch) > sizeof(FricRows) ? sizeof(Scratch) : sizeof(FricRows)) * tile, b = sizeof(uint32_t) * 3 * cap_m,
+		   c = 8u * ((size_t)cap_m + CHARACTER_MAX_CONTACTS);
 	if (c > b) b = c;
-	return a > b ? a : b;
+	return ((a > b ? a : b) + 15u) & ~(size_t)15u;
 }
 
 __host__ __device__ inline size_t world_smem_bytes(uint32_t tile, uint32_t cap, uint32_t cap_m)
@@ -102,7 +103,7 @@ __host__ __device__ inline size_t world_smem_bytes(uint32_t tile, uint32_t cap, 
 	b += sizeof(SMan) * cap_m;
 	b += sizeof(uint32_t) * 2 * cap_m;      // pair list (a | slot << 16, b)
 	b += sizeof(uint32_t) * cap_m;          // active manifolds in canonical order
-	b += world_scratch_bytes(tile, cap_m);  // narrowphase polygon scratch, later the cached keys + the active list
+	b += world_scratch_bytes(tile, cap_m) + 16;  // narrowphase polygon scratch, later the cached keys, then the friction rows (16-byte aligned)
 	b += sizeof(uint32_t) * 2 * cap;        // per-body counts, bases
 	b += sizeof(uint32_t) * 8;              // header
 	return (b + 15) & ~(size_t)15;
@@ -113,21 +114,23 @@ __device__ __forceinline__ bool sensor_pair(const SMan &m, const SBody *bodies)
 	return m.b < STATIC_BODY_BASE && ((bodies[m.a].flags | bodies[m.b].flags) & BF_SENSOR) != 0;
 }
 
-// Velocity solve with one lane per active manifold: set-up once, warm start, then the iterations; per colour a lane
-// pulls its bodies' velocities from shared memory, runs its rows and pushes them back.
+// Velocity solve with one lane per active manifold: the manifold's rows are built once into REGISTERS, then warm start
+// and the iterations; per colour a lane pulls its bodies' velocities from shared memory, runs its rows and pushes them
+// back.
 template <int TILE, typename Tile>
 __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *man, const uint32_t *act, uint32_t nact,
-												   SBody *bodies, ConPts &pt, int ncol, uint32_t vel_steps, float h,
-												   PhaseClock &pc)
+												   SBody *bodies, FricRows &F, int ncol, uint32_t vel_steps, float h, PhaseClock &pc)
 {
 	const bool mine = (uint32_t)lane < nact;
 	SMan &m = man[mine ? act[lane] : 0];
 	Con c;
+	Rows R;
 	int colour = -1;
-	tile.sync();  // the cached keys that share `pt`'s bytes are dead from here on
+	tile.sync();  // the cached keys that share `F`'s bytes are dead from here on
 	if (mine)
 	{
-		build_con(c, pt, m, bodies, h);
+		build_rows(c, R, m, bodies, h);
+		F = R.f;
 		colour = m.colour;
 	}
 	pc.mark(PH_SETUP);
@@ -137,7 +140,7 @@ __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *m
 		{
 			Vel u;
 			load_vel(c, bodies, u);
-			warm_start(c, pt, m, u);
+			warm_start(c, R, F, u);
 			store_vel(c, bodies, u);
 		}
 		tile.sync();
@@ -150,11 +153,12 @@ __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *m
 			{
 				Vel u;
 				load_vel(c, bodies, u);
-				solve_velocity(c, pt, m, u);
+				solve_velocity(c, R, F, u, it);
 				store_vel(c, bodies, u);
 			}
 			tile.sync();
 		}
+	if (mine) save_impulses(m, R);
 }
 
 // Routing of the next tick, decided where the manifold count is known (the end of this one): next_list[0 .. n) = worlds
@@ -212,10 +216,10 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	uint32_t *pair_b = pair_a + cap_m;
 	uint32_t *act = pair_b + cap_m;
 	// One region, three lives per sub-step: a polygon Scratch per lane while contacts are generated; the cached keys
-	// during the warm-start match; a ConPts per lane during the velocity solve.
-	unsigned char *scratch_raw = reinterpret_cast<unsigned char *>(act + cap_m);
+	// during the warm-start match; the friction rows of the lane's manifold during the velocity solve.
+	unsigned char *scratch_raw = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(act + cap_m) + 15u) & ~(uintptr_t)15u);
 	Scratch &scratch = reinterpret_cast<Scratch *>(scratch_raw)[lane];
-	ConPts &conpts = *reinterpret_cast<ConPts *>(&scratch);
+	FricRows &fric = reinterpret_cast<FricRows *>(scratch_raw)[lane];
 	uint32_t *pkey_a = reinterpret_cast<uint32_t *>(scratch_raw);
 	uint32_t *pkey_b = pkey_a + cap_m;
 	uint32_t *pkey_np = pkey_b + cap_m;
@@ -439,11 +443,10 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				nmatch += hit ? 1 : 0;
 			}
 			// stage 2: every lane with a match pulls its record at once (one overlapped batch of L2 reads per tile)
+			bool got_cf = false;
 			for (int j = j0; j >= 0 && nmatch > 0; )
 			{
 				const uint32_t onp = pkey_np[j];
-				const float4 l2 = __ldcg(&a.mc.lt2[m0 + j]);
-				const float ol2[4] = {l2.x, l2.y, l2.z, l2.w};
 				float4 c1[4], c2[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++)
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 				for (int p = 0; p < 4; p++)
 				{
 					if (p >= m.np) continue;
-					if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
+					if (m.ln[p] != 0.0f) continue;
 					const v3 a1 = m.p1l[p], a2 = m.p2l[p];
 					bool done = false;
 #pragma unroll
@@ -466,8 +469,14 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 						if (ok)
 						{
 							m.ln[p] = c1[k].w;
-							m.lt1[p] = c2[k].w;
-							m.lt2[p] = ol2[k];
+							// the friction impulse of the manifold comes from the first old manifold a point is found in
+							if (!got_cf)
+							{
+								got_cf = true;
+								m.cf[0] = c2[0].w;
+								m.cf[1] = c2[1].w;
+								m.cf[2] = c2[2].w;
+							}
 							done = true;
 						}
 					}
@@ -529,18 +538,18 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 		// ---- 7: set-up, warm start, velocity iterations; within a colour no two manifolds share a dynamic body
 		if (nact <= (uint32_t)TILE)
-			solve_one_per_lane<TILE>(tile, lane, man, act, nact, bodies, conpts, ncol, a.p.vel_steps, h, pc);
+			solve_one_per_lane<TILE>(tile, lane, man, act, nact, bodies, fric, ncol, a.p.vel_steps, h, pc);
 		else
 		{
-			// more manifolds than lanes: a lane revisits several manifolds, so the per-point constants (lever arms,
-			// effective masses) are parked in an L2-resident scratch record and pulled back each visit
-			float4 *park = a.con_park + 9ull * m0;
-			tile.sync();  // the cached keys that share `conpts`' bytes are dead from here on
+			// more manifolds than lanes: a lane revisits several manifolds, so their rows are parked in an L2-resident
+			// scratch record and pulled back each visit
+			float4 *park = a.con_park + 31ull * m0;
 			for (uint32_t k = lane; k < nact; k += TILE)
 			{
 				Con c;
-				build_con(c, conpts, man[act[k]], bodies, h);
-				park_con(conpts, park + 9ull * act[k]);
+				Rows R;
+				build_rows(c, R, man[act[k]], bodies, h);
+				park_rows(R, park + 31ull * act[k]);
 			}
 			__threadfence_block();
 			tile.sync();
@@ -552,15 +561,21 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 						SMan &m = man[act[k]];
 						if (m.colour != col) continue;
 						Con c;
+						Rows R;
 						con_header(c, m, bodies);
-						unpark_con(conpts, park + 9ull * act[k]);
+						unpark_rows(R, park + 31ull * act[k]);
 						Vel u;
 						load_vel(c, bodies, u);
 						if (it == 0)
-							warm_start(c, conpts, m, u);
+							warm_start(c, R, R.f, u);
 						else
-							solve_velocity(c, conpts, m, u);
+							solve_velocity(c, R, R.f, u, it - 1u);
 						store_vel(c, bodies, u);
+						// only the accumulated impulses change: float4 14 (ln) and 15 (cf) of the parked record
+						float4 *g = park + 31ull * act[k];
+						__stcg(&g[14], make_float4(R.ln[0], R.ln[1], R.ln[2], R.ln[3]));
+						__stcg(&g[15], make_float4(R.cf[0], R.cf[1], R.cf[2], 0.0f));
+						if (it == a.p.vel_steps) save_impulses(m, R);
 					}
 					tile.sync();
 				}
@@ -594,12 +609,11 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 		{
 			const SMan &m = man[act[k]];
 			__stcg(&a.mc.key[m0 + k], make_uint4(m.a, m.b, (uint32_t)m.np, 0u));
-			__stcg(&a.mc.lt2[m0 + k], make_float4(m.lt2[0], m.lt2[1], m.lt2[2], m.lt2[3]));
 #pragma unroll
 			for (int p = 0; p < 4; p++)
 			{
 				__stcg(&a.mc.p1[4 * (m0 + k) + p], F4(m.p1l[p], m.ln[p]));
-				__stcg(&a.mc.p2[4 * (m0 + k) + p], F4(m.p2l[p], m.lt1[p]));
+				__stcg(&a.mc.p2[4 * (m0 + k) + p], F4(m.p2l[p], p < 3 ? m.cf[p] : 0.0f));
 			}
 		}
 		if (lane == 0) hdr[1] = nact;
@@ -626,7 +640,6 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 	if (a.ev_out && lane == 0)
 	{
 		unsigned long long *keys = reinterpret_cast<unsigned long long *>(scratch_raw);  // free after the last sub-step
-		static_assert(sizeof(Scratch) >= sizeof(ConPts), "per-lane scratch must hold the solver's per-point record");
 		const uint32_t nman = hdr[0];
 		uint32_t n = 0;
 		for (uint32_t mi = 0; mi < nman; mi++)

@@ -62,9 +62,7 @@ constexpr int SENSOR_COLOUR = -0x40000000;  // a touching pair with a sensor in 
 struct __align__(16) SolveRec
 {
 	Con con;
-	ConPts pts;
-	float bias[4];
-	float ln[4], lt1[4], lt2[4];
+	Rows rows;
 	uint32_t mi;
 };
 static_assert(sizeof(SolveRec) % 16 == 0, "solver records are copied in 16-byte pieces");
@@ -490,6 +488,7 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 		return;
 	}
 	// warm start: previous manifolds of the same body pair, in creation order (ordinal 0, 1, ...)
+	bool got_cf = false;
 	for (uint32_t o = 0; o < (uint32_t)MAX_SLOTS; o++)
 	{
 		const int j = hash_find(a, man_key(m.a, m.b, o));
@@ -497,14 +496,20 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 		const SMan &old = a.prev[j];
 		for (int p = 0; p < m.np; p++)
 		{
-			if (m.ln[p] != 0.0f || m.lt1[p] != 0.0f || m.lt2[p] != 0.0f) continue;
+			if (m.ln[p] != 0.0f) continue;
 			for (int k = 0; k < old.np; k++)
 				if (len2(m.p1l[p] - old.p1l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
 					len2(m.p2l[p] - old.p2l[k]) < PRESERVE_LAMBDA_MAX_DIST_SQ)
 				{
 					m.ln[p] = old.ln[k];
-					m.lt1[p] = old.lt1[k];
-					m.lt2[p] = old.lt2[k];
+					// the friction impulse of the manifold comes from the first old manifold a point is found in
+					if (!got_cf)
+					{
+						got_cf = true;
+						m.cf[0] = old.cf[0];
+						m.cf[1] = old.cf[1];
+						m.cf[2] = old.cf[2];
+					}
 					break;
 				}
 		}
@@ -642,21 +647,11 @@ __global__ void __launch_bounds__(WT) kw_isl_fill(WideArgs a)
 	if (big) a.big_list[base + (uint32_t)__popc(votes & ((1u << lane) - 1u))] = mi;
 }
 
-// per-lane working set of kw_island: lever arms / effective masses, accumulated impulses, bias.  53 words: odd, so the
-// 32 lanes of a warp fall on different banks.
-struct IslLane
-{
-	ConPts pts;
-	float ln[4], lt1[4], lt2[4], bias[4];
-	float pad;
-};
-
 // One warp = one 32-slot window of isl_man = a few whole islands, one manifold per lane.  The sequence per manifold
 // is exactly kw_colour + kw_solve's; only the barriers are warp barriers.  Lanes of different islands never refer to
 // each other (neighbour masks stay inside an island), so they simply share the colour phases.
 __global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
 {
-	__shared__ IslLane lanes[ISLAND_WARPS * 32];
 	__shared__ float vel[ISLAND_WARPS][64][6];
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t win = blockIdx.x * ISLAND_WARPS + (threadIdx.x >> 5);
@@ -664,7 +659,7 @@ __global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
 	const uint32_t mi = a.isl_man[win * 32u + lane];
 	const bool have = mi != 0xFFFFFFFFu;
 	const uint32_t FULL = 0xFFFFFFFFu;
-	IslLane &L = lanes[threadIdx.x];
+	Rows R;  // this lane's manifold: rows in registers for the whole solve
 
 	// --- neighbours (manifolds sharing a dynamic body) as a lane mask
 	if (have) a.pending[mi] = (int)lane;
@@ -743,16 +738,7 @@ __global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
 	Con c;
 	if (have)
 	{
-		SMan &m = a.man[mi];
-		build_con(c, L.pts, m, a.bodies, h);
-#pragma unroll
-		for (int p = 0; p < 4; p++)
-		{
-			L.bias[p] = m.bias[p];
-			L.ln[p] = m.ln[p];
-			L.lt1[p] = m.lt1[p];
-			L.lt2[p] = m.lt2[p];
-		}
+		build_rows(c, R, a.man[mi], a.bodies, h);
 	}
 	// --- velocities of the island's dynamic bodies live in shared memory while the rows run.  A body belongs to the
 	// lane that holds the first manifold of its incidence list (slot 2 * lane + end); the other lanes look the slot up.
@@ -802,9 +788,9 @@ __global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
 					u.wb = V(pb[3], pb[4], pb[5]);
 				}
 				if (it == 0)
-					warm_start(c, L.pts, L, u);
+					warm_start(c, R, R.f, u);
 				else
-					solve_velocity(c, L.pts, L, u);
+					solve_velocity(c, R, R.f, u, it - 1u);
 				if (pa)
 				{
 					pa[0] = u.va.x; pa[1] = u.va.y; pa[2] = u.va.z; pa[3] = u.wa.x; pa[4] = u.wa.y; pa[5] = u.wa.z;
@@ -818,14 +804,7 @@ __global__ void __launch_bounds__(ISLAND_WARPS * 32) kw_island(WideArgs a)
 		}
 	if (have)
 	{
-		SMan &m = a.man[mi];
-#pragma unroll
-		for (int p = 0; p < 4; p++)
-		{
-			m.ln[p] = L.ln[p];
-			m.lt1[p] = L.lt1[p];
-			m.lt2[p] = L.lt2[p];
-		}
+		save_impulses(a.man[mi], R);
 		// --- velocities back, and integrate: every dynamic body of the island once, by the lane that owns it
 		const uint32_t ends[2] = {ma, mb};
 		const bool own[2] = {own_a, own_b};
@@ -991,7 +970,7 @@ __global__ void __launch_bounds__(256) kw_colour(WideArgs a)
 // One colour phase over the solver records [lo, hi): each warp stages its 32 consecutive records in shared memory with
 // coalesced 16-byte copies, solves from there (warm start or one velocity iteration) and writes back only the impulses.
 __device__ __forceinline__ void solve_colour_range(const WideArgs &a, SolveRec *recs, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t stride,
-												   SolveRec *stage, uint32_t lane, bool warm)
+												   SolveRec *stage, uint32_t lane, uint32_t it)
 {
 	for (uint32_t k0 = lo + (tid & ~31u); k0 < hi; k0 += stride)
 	{
@@ -1007,19 +986,16 @@ __device__ __forceinline__ void solve_colour_range(const WideArgs &a, SolveRec *
 			const Con c = r.con;
 			Vel u;
 			load_vel(c, a.bodies, u);
-			if (warm)
-				warm_start(c, r.pts, r, u);
+			if (it == 0)
+				warm_start(c, r.rows, r.rows.f, u);
 			else
-				solve_velocity(c, r.pts, r, u);
+				solve_velocity(c, r.rows, r.rows.f, u, it - 1u);
 			store_vel(c, a.bodies, u);
 			SolveRec &g = recs[k0 + lane];
 #pragma unroll
-			for (int p = 0; p < 4; p++)
-			{
-				g.ln[p] = r.ln[p];
-				g.lt1[p] = r.lt1[p];
-				g.lt2[p] = r.lt2[p];
-			}
+			for (int p = 0; p < 4; p++) g.rows.ln[p] = r.rows.ln[p];
+#pragma unroll
+			for (int p = 0; p < 3; p++) g.rows.cf[p] = r.rows.cf[p];
 		}
 		__syncwarp();
 	}
@@ -1048,17 +1024,9 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 			SMan &m = a.man[mi];
 			SolveRec &r = a.recs[k];
 			Con c;
-			build_con(c, r.pts, m, a.bodies, h);
+			build_rows(c, r.rows, m, a.bodies, h);
 			r.con = c;
 			r.mi = mi;
-#pragma unroll
-			for (int p = 0; p < 4; p++)
-			{
-				r.bias[p] = m.bias[p];
-				r.ln[p] = m.ln[p];
-				r.lt1[p] = m.lt1[p];
-				r.lt2[p] = m.lt2[p];
-			}
 		}
 		bar();
 		// it == 0: warm start; then the velocity iterations.  Colour by colour: no two manifolds of a colour share a
@@ -1067,21 +1035,14 @@ __global__ void __launch_bounds__(256) kw_solve(WideArgs a)
 			for (int col = 0; col < ncol; col++)
 			{
 				const uint32_t lo = a.cnt[WC_COLOFF + col], hi = a.cnt[WC_COLOFF + col + 1];
-				solve_colour_range(a, a.recs, lo, hi, tid, stride, stage, lane, it == 0);
+				solve_colour_range(a, a.recs, lo, hi, tid, stride, stage, lane, it);
 				bar();
 			}
 		// accumulated impulses back into the manifolds (next sub-step's warm start reads them there)
 		for (uint32_t k = tid; k < nact; k += stride)
 		{
 			const SolveRec &r = a.recs[k];
-			SMan &m = a.man[r.mi];
-#pragma unroll
-			for (int p = 0; p < 4; p++)
-			{
-				m.ln[p] = r.ln[p];
-				m.lt1[p] = r.lt1[p];
-				m.lt2[p] = r.lt2[p];
-			}
+			save_impulses(a.man[r.mi], r.rows);
 		}
 	}
 	grid.sync();
@@ -1184,17 +1145,9 @@ __global__ void __launch_bounds__(MEDIUM_T) kw_island_block(WideArgs a)
 		SMan &m = a.man[mi];
 		SolveRec &r = a.recs[base + k];
 		Con c;
-		build_con(c, r.pts, m, a.bodies, h);
+		build_rows(c, r.rows, m, a.bodies, h);
 		r.con = c;
 		r.mi = mi;
-#pragma unroll
-		for (int p = 0; p < 4; p++)
-		{
-			r.bias[p] = m.bias[p];
-			r.ln[p] = m.ln[p];
-			r.lt1[p] = m.lt1[p];
-			r.lt2[p] = m.lt2[p];
-		}
 	}
 	__threadfence_block();
 	__syncthreads();
@@ -1202,7 +1155,7 @@ __global__ void __launch_bounds__(MEDIUM_T) kw_island_block(WideArgs a)
 	for (uint32_t it = 0; it <= a.vel_steps; it++)
 		for (int col = 0; col < ncol; col++)
 		{
-			solve_colour_range(a, a.recs + base, s_coloff[col], s_coloff[col + 1], tid, MEDIUM_T, stage, lane, it == 0);
+			solve_colour_range(a, a.recs + base, s_coloff[col], s_coloff[col + 1], tid, MEDIUM_T, stage, lane, it);
 			__threadfence_block();
 			__syncthreads();
 		}
@@ -1212,13 +1165,7 @@ __global__ void __launch_bounds__(MEDIUM_T) kw_island_block(WideArgs a)
 	{
 		const SolveRec &r = a.recs[base + k];
 		SMan &m = a.man[r.mi];
-#pragma unroll
-		for (int p = 0; p < 4; p++)
-		{
-			m.ln[p] = r.ln[p];
-			m.lt1[p] = r.lt1[p];
-			m.lt2[p] = r.lt2[p];
-		}
+		save_impulses(m, r.rows);
 		const uint32_t ends[2] = {m.a, m.b};
 		for (int e = 0; e < 2; e++)
 		{

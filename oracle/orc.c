@@ -68,6 +68,28 @@ static inline int is_active(const body_t *b)
 		   (b->v.x != 0.0f || b->v.y != 0.0f || b->v.z != 0.0f || b->w.x != 0.0f || b->w.y != 0.0f || b->w.z != 0.0f);
 }
 
+/* One constraint row: the velocity it measures is Jv = (axis.va + a1.wa) - (axis.vb + a2.wb); an impulse d along it
+ * changes va by -lA*d, wa by -I1*d, vb by +lB*d, wb by +I2*d.  em = 1 / (J M^-1 J^T). */
+typedef struct
+{
+	v3 a1, a2; /* r1 x axis, r2 x axis (twist row: the axis itself) */
+	v3 I1, I2; /* world inverse inertia times a1 / a2 */
+	float em;
+} row_t;
+
+/* The rows of one manifold, rebuilt every sub-step from the bodies' poses: a non-penetration row per contact point, and
+ * for the manifold as a whole two friction rows through the centroid of the contact points plus one twist row about the
+ * normal, limited by the friction coefficient times the sum of the normal impulses (times the patch radius for twist). */
+typedef struct
+{
+	row_t n[4];
+	float bias[4];
+	row_t t[2];
+	row_t w;
+	float rp;              /* patch radius: RMS distance of the contact points from their centroid */
+	v3 nA, nB, tA[2], tB[2]; /* axis times inverse mass, locked translation axes zeroed */
+} rows_t;
+
 typedef struct
 {
 	uint32_t a, b; /* a: slot body (dynamic side); b: slot body or ORC_STATIC_BODY_BASE + k */
@@ -75,13 +97,12 @@ typedef struct
 	float depth;   /* deepest penetration seen when merging */
 	int np;
 	v3 p1l[4], p2l[4]; /* contact points in the local frames of a and b (static: world) */
-	float ln[4], lt1[4], lt2[4];
+	float ln[4];       /* accumulated normal impulse per point */
+	float cf[3];       /* accumulated friction impulse of the manifold: tangent 1, tangent 2 (at the centroid), twist about n */
 	/* solver scratch */
 	float friction, restitution;
 	v3 t1, t2;
-	float bias[4];
-	v3 r1[4], r2[4];  /* lever arms from the centres of mass to the contact midpoint */
-	float em[4][3];   /* effective mass along normal, tangent1, tangent2 */
+	rows_t rows;
 	int colour;
 	uint32_t ord;  /* ordinal among the manifolds of the same (a, b): 0 for body pairs, slot index for static bodies */
 	uint32_t prio; /* colouring priority (mode 1) */
@@ -1189,20 +1210,27 @@ static void warm_start_match(orc_world *w)
 	for (uint32_t i = 0; i < w->nman; i++)
 	{
 		manifold_t *m = &w->man[i];
+		int got_cf = 0;
 		for (uint32_t j = 0; j < w->nprev; j++)
 		{
 			const manifold_t *o = &w->prev[j];
 			if (o->a != m->a || o->b != m->b) continue;
 			for (int p = 0; p < m->np; p++)
 			{
-				if (m->ln[p] != 0.0f || m->lt1[p] != 0.0f || m->lt2[p] != 0.0f) continue;
+				if (m->ln[p] != 0.0f) continue;
 				for (int k = 0; k < o->np; k++)
 					if (vlen2(vsub(m->p1l[p], o->p1l[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ &&
 						vlen2(vsub(m->p2l[p], o->p2l[k])) < PRESERVE_LAMBDA_MAX_DIST_SQ)
 					{
 						m->ln[p] = o->ln[k];
-						m->lt1[p] = o->lt1[k];
-						m->lt2[p] = o->lt2[k];
+						/* the friction impulse of the manifold comes from the first old manifold a point is found in */
+						if (!got_cf)
+						{
+							got_cf = 1;
+							m->cf[0] = o->cf[0];
+							m->cf[1] = o->cf[1];
+							m->cf[2] = o->cf[2];
+						}
 						break;
 					}
 			}
@@ -1397,57 +1425,128 @@ static float eff_mass(float ima, const float *MA, float imb, const float *MB, v3
 	return k > 0.0f ? 1.0f / k : 0.0f;
 }
 
-/* velocity of a's contact point relative to b's */
-static v3 rel_vel(const body_t *A, const body_t *B, v3 r1, v3 r2)
+/* v - t * s */
+static inline v3 vmsub(v3 v, v3 t, float s) { return V(fmaf(-t.x, s, v.x), fmaf(-t.y, s, v.y), fmaf(-t.z, s, v.z)); }
+
+/* the two bodies' velocities as the rows see them (b static: zero) */
+typedef struct { v3 va, wa, vb, wb; } vel_t;
+
+static vel_t load_vel(const body_t *A, const body_t *B)
 {
-	v3 ua = vadd(A->v, vcross(A->w, r1));
-	if (!B) return ua;
-	return vsub(ua, vadd(B->v, vcross(B->w, r2)));
+	vel_t u;
+	u.va = A->v;
+	u.wa = A->w;
+	u.vb = B ? B->v : V(0, 0, 0);
+	u.wb = B ? B->w : V(0, 0, 0);
+	return u;
 }
 
-/* impulse P pushes b along +P and a along -P */
-static void apply_impulse(body_t *A, body_t *B, v3 r1, v3 r2, v3 P)
+static void store_vel(body_t *A, body_t *B, const vel_t *u)
 {
 	if (is_dyn(A))
 	{
-		A->v = vsub(A->v, mask_lin(A->dofs, vscale(P, A->im)));
-		A->w = vsub(A->w, sym_mul(A->M, vcross(r1, P)));
+		A->v = u->va;
+		A->w = u->wa;
 	}
 	if (B && is_dyn(B))
 	{
-		B->v = vadd(B->v, mask_lin(B->dofs, vscale(P, B->im)));
-		B->w = vadd(B->w, sym_mul(B->M, vcross(r2, P)));
+		B->v = u->vb;
+		B->w = u->wb;
 	}
 }
 
-/* per sub-step set-up (reads body state only): lever arms, tangents, effective masses, speculative / restitution bias */
+static row_t row_setup(float ima, const float *MA, float imb, const float *MB, v3 r1, v3 r2, v3 axis)
+{
+	row_t r;
+	r.a1 = vcross(r1, axis);
+	r.a2 = vcross(r2, axis);
+	r.I1 = sym_mul(MA, r.a1);
+	r.I2 = sym_mul(MB, r.a2);
+	float k = ((ima + imb) + vdot(r.a1, r.I1)) + vdot(r.a2, r.I2);
+	r.em = k > 0.0f ? 1.0f / k : 0.0f;
+	return r;
+}
+
+static inline float row_jv(const row_t *r, v3 axis, const vel_t *u)
+{
+	return (vdot(axis, u->va) + vdot(r->a1, u->wa)) - (vdot(axis, u->vb) + vdot(r->a2, u->wb));
+}
+
+static inline void row_apply(const row_t *r, v3 lA, v3 lB, float d, vel_t *u)
+{
+	u->va = vmsub(u->va, lA, d);
+	u->wa = vmsub(u->wa, r->I1, d);
+	u->vb = vmadd(u->vb, lB, d);
+	u->wb = vmadd(u->wb, r->I2, d);
+}
+
+/* twist about the normal: angular parts only */
+static inline float twist_jv(v3 n, const vel_t *u) { return vdot(n, u->wa) - vdot(n, u->wb); }
+static inline void twist_apply(const row_t *r, float d, vel_t *u)
+{
+	u->wa = vmsub(u->wa, r->I1, d);
+	u->wb = vmadd(u->wb, r->I2, d);
+}
+
+/* per sub-step set-up (reads body state only): the manifold's rows and the speculative / restitution bias */
 static void setup_manifold(orc_world *w, manifold_t *m, float h)
 {
 	body_t *A = &w->bodies[m->a];
 	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
 	const float imb = B ? B->im : 0.0f;
 	const float *MB = B ? B->M : ZERO_M;
+	rows_t *R = &m->rows;
 	m->t1 = vperp(m->n);
 	m->t2 = vcross(m->n, m->t1);
+	R->nA = mask_lin(A->dofs, vscale(m->n, A->im));
+	R->tA[0] = mask_lin(A->dofs, vscale(m->t1, A->im));
+	R->tA[1] = mask_lin(A->dofs, vscale(m->t2, A->im));
+	R->nB = B ? mask_lin(B->dofs, vscale(m->n, imb)) : V(0, 0, 0);
+	R->tB[0] = B ? mask_lin(B->dofs, vscale(m->t1, imb)) : V(0, 0, 0);
+	R->tB[1] = B ? mask_lin(B->dofs, vscale(m->t2, imb)) : V(0, 0, 0);
+	const vel_t u = load_vel(A, B);
+	v3 mid[4];
+	v3 csum = V(0, 0, 0);
 	for (int k = 0; k < m->np; k++)
 	{
 		v3 p1 = vadd(A->x, qrot(A->q, m->p1l[k]));
 		v3 p2 = B ? vadd(B->x, qrot(B->q, m->p2l[k])) : m->p2l[k];
-		v3 mid = vscale(vadd(p1, p2), 0.5f);
-		m->r1[k] = vsub(mid, A->x);
-		m->r2[k] = B ? vsub(mid, B->x) : V(0, 0, 0);
-		m->em[k][0] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->n);
-		m->em[k][1] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->t1);
-		m->em[k][2] = eff_mass(A->im, A->M, imb, MB, m->r1[k], m->r2[k], m->t2);
+		mid[k] = vscale(vadd(p1, p2), 0.5f);
+		csum = vadd(csum, mid[k]);
+		v3 r1 = vsub(mid[k], A->x);
+		v3 r2 = B ? vsub(mid[k], B->x) : V(0, 0, 0);
+		R->n[k] = row_setup(A->im, A->M, imb, MB, r1, r2, m->n);
 		float pen = vdot(vsub(p1, p2), m->n);
 		float bias = fmaxf(0.0f, -pen / h);
 		if (m->restitution > 0.0f)
 		{
-			float nv = -vdot(m->n, rel_vel(A, B, m->r1[k], m->r2[k])); /* separating speed of b relative to a */
+			float nv = -row_jv(&R->n[k], m->n, &u); /* separating speed of b relative to a */
 			if (nv < -MIN_VELOCITY_FOR_RESTITUTION) bias = m->restitution * nv;
 		}
-		m->bias[k] = bias;
+		R->bias[k] = bias;
 	}
+	/* rows of points the manifold does not have are zero: they measure nothing and apply nothing */
+	for (int k = m->np; k < 4; k++)
+	{
+		memset(&R->n[k], 0, sizeof(R->n[k]));
+		R->bias[k] = 0.0f;
+		m->ln[k] = 0.0f;
+	}
+	if (m->np == 0) return;
+	const float inv_np = 1.0f / (float)m->np;
+	const v3 c = vscale(csum, inv_np);
+	float s = 0.0f;
+	for (int k = 0; k < m->np; k++) s = s + vlen2(vsub(mid[k], c));
+	R->rp = sqrtf(s * inv_np);
+	const v3 rc1 = vsub(c, A->x), rc2 = B ? vsub(c, B->x) : V(0, 0, 0);
+	R->t[0] = row_setup(A->im, A->M, imb, MB, rc1, rc2, m->t1);
+	R->t[1] = row_setup(A->im, A->M, imb, MB, rc1, rc2, m->t2);
+	R->w.a1 = m->n;
+	R->w.a2 = m->n;
+	R->w.I1 = sym_mul(A->M, m->n);
+	R->w.I2 = sym_mul(MB, m->n);
+	float kw = vdot(m->n, R->w.I1) + vdot(m->n, R->w.I2);
+	R->w.em = kw > 0.0f ? 1.0f / kw : 0.0f;
 }
 
 /* re-apply the impulses carried over from the previous sub-step */
@@ -1455,50 +1554,71 @@ static void warm_start(orc_world *w, manifold_t *m)
 {
 	body_t *A = &w->bodies[m->a];
 	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
-	for (int k = 0; k < m->np; k++)
-	{
-		if (m->ln[k] == 0.0f && m->lt1[k] == 0.0f && m->lt2[k] == 0.0f) continue;
-		v3 P = vadd(vadd(vscale(m->n, m->ln[k]), vscale(m->t1, m->lt1[k])), vscale(m->t2, m->lt2[k]));
-		apply_impulse(A, B, m->r1[k], m->r2[k], P);
-	}
+	const rows_t *R = &m->rows;
+	if (m->np == 0) return;
+	vel_t u = load_vel(A, B);
+	for (int k = 0; k < 4; k++) row_apply(&R->n[k], R->nA, R->nB, m->ln[k], &u);
+	row_apply(&R->t[0], R->tA[0], R->tB[0], m->cf[0], &u);
+	row_apply(&R->t[1], R->tA[1], R->tB[1], m->cf[1], &u);
+	twist_apply(&R->w, m->cf[2], &u);
+	store_vel(A, B, &u);
 }
 
-static void solve_velocity(orc_world *w, manifold_t *m)
+/* One velocity iteration of a manifold.  Friction first (non-penetration is more important, so it goes last): the two
+ * tangent rows through the centroid share one limit, friction * (sum of the normal impulses), then the twist row with
+ * that limit times the patch radius.  The non-penetration rows run forwards in even iterations and backwards in odd
+ * ones: with a fixed order the last point of every manifold always ends exact and the first one always carries the
+ * residual, and that bias turns a tall stack's residuals into a slow whirl that never dies (tests/test_oracle.py,
+ * test_kicked_column_comes_to_rest). */
+static void solve_velocity(orc_world *w, manifold_t *m, uint32_t it)
 {
 	body_t *A = &w->bodies[m->a];
 	body_t *B = m->b < ORC_STATIC_BODY_BASE ? &w->bodies[m->b] : NULL;
-	/* friction first (non-penetration is more important, so it goes last) */
-	for (int k = 0; k < m->np; k++)
+	const rows_t *R = &m->rows;
+	if (m->np == 0) return;
+	vel_t u = load_vel(A, B);
+	const float maxf = m->friction * (((m->ln[0] + m->ln[1]) + m->ln[2]) + m->ln[3]);
+	/* nothing to hold with and nothing held (speculative points that do not touch): the rows stay at zero */
+	if (!(maxf == 0.0f && m->cf[0] == 0.0f && m->cf[1] == 0.0f))
 	{
-		float maxf = m->friction * m->ln[k];
-		/* nothing to hold with and nothing held (a speculative point that does not touch): the row stays at zero */
-		if (maxf == 0.0f && m->lt1[k] == 0.0f && m->lt2[k] == 0.0f) continue;
-		v3 u = rel_vel(A, B, m->r1[k], m->r2[k]);
-		float l1 = m->lt1[k] + (m->em[k][1] * vdot(m->t1, u));
-		float l2 = m->lt2[k] + (m->em[k][2] * vdot(m->t2, u));
+		float l1 = m->cf[0] + (R->t[0].em * row_jv(&R->t[0], m->t1, &u));
+		float l2 = m->cf[1] + (R->t[1].em * row_jv(&R->t[1], m->t2, &u));
 		float sq = (l1 * l1) + (l2 * l2);
 		if (sq > (maxf * maxf))
 		{
-			/* no normal impulse yet: 0 / sqrt(sq) is that zero */
-			float s = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
-			l1 = l1 * s;
-			l2 = l2 * s;
+			/* no normal impulse: 0 / sqrt(sq) is that zero */
+			float sc = maxf == 0.0f ? maxf : maxf / sqrtf(sq);
+			l1 = l1 * sc;
+			l2 = l2 * sc;
 		}
-		const float d1 = l1 - m->lt1[k], d2 = l2 - m->lt2[k];
-		m->lt1[k] = l1;
-		m->lt2[k] = l2;
-		/* an impulse is applied only when it is not zero (Jolt: AxisConstraintPart::ApplyVelocityStep) */
-		if (d1 != 0.0f || d2 != 0.0f) apply_impulse(A, B, m->r1[k], m->r2[k], vadd(vscale(m->t1, d1), vscale(m->t2, d2)));
+		const float d1 = l1 - m->cf[0], d2 = l2 - m->cf[1];
+		m->cf[0] = l1;
+		m->cf[1] = l2;
+		row_apply(&R->t[0], R->tA[0], R->tB[0], d1, &u);
+		row_apply(&R->t[1], R->tA[1], R->tB[1], d2, &u);
 	}
-	for (int k = 0; k < m->np; k++)
+	if (m->np >= 2)
 	{
-		v3 u = rel_vel(A, B, m->r1[k], m->r2[k]);
-		float lambda = m->em[k][0] * (vdot(m->n, u) - m->bias[k]);
+		const float lim = maxf * R->rp;
+		if (!(lim == 0.0f && m->cf[2] == 0.0f))
+		{
+			float l = m->cf[2] + (R->w.em * twist_jv(m->n, &u));
+			l = fminf(fmaxf(l, -lim), lim);
+			const float d = l - m->cf[2];
+			m->cf[2] = l;
+			twist_apply(&R->w, d, &u);
+		}
+	}
+	for (int i = 0; i < 4; i++)
+	{
+		const int k = (it & 1u) ? 3 - i : i;
+		float lambda = R->n[k].em * (row_jv(&R->n[k], m->n, &u) - R->bias[k]);
 		float nt = fmaxf(0.0f, m->ln[k] + lambda);
 		lambda = nt - m->ln[k];
 		m->ln[k] = nt;
-		if (lambda != 0.0f) apply_impulse(A, B, m->r1[k], m->r2[k], vscale(m->n, lambda));
+		row_apply(&R->n[k], R->nA, R->nB, lambda, &u);
 	}
+	store_vel(A, B, &u);
 }
 
 static void solve_position(orc_world *w, manifold_t *m)
@@ -1742,7 +1862,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t k = 0; k < w->nman; k++) setup_manifold(w, &w->man[k], h);
 		for (uint32_t k = 0; k < w->nman; k++) warm_start(w, &w->man[w->order[k]]);
 		for (uint32_t it = 0; it < w->vel_steps; it++)
-			for (uint32_t k = 0; k < w->nman; k++) solve_velocity(w, &w->man[w->order[k]]);
+			for (uint32_t k = 0; k < w->nman; k++) solve_velocity(w, &w->man[w->order[k]], it);
 		for (uint32_t i = 0; i < w->max_bodies; i++)
 		{
 			body_t *b = &w->bodies[i];

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_DIR = os.environ.get("ORC_DIR", os.path.join(ROOT, "oracle"))
 STATIC_BASE = 0x400000
 INVALID = 0xFFFFFFFF
 

@@ -30,6 +30,12 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-oracle" not in sys.argv:
+        assets()
+    oracle_vectors()
+
+
+def assets():
     for name in ("test", "stacked", "shapes", "orb"):
         m = gasset.load_gmap(f"{REF}/assets/game/map/{name}.gmap")
         assert m.leftover == 0
@@ -64,7 +70,10 @@ def main():
             models[f"{name}_tris"] = g.tris.astype(np.float32)
     np.savez_compressed(os.path.join(OUT, "models.npz"), **models)
 
-    # ---- oracle regression vectors
+
+
+def oracle_vectors():
+    # ---- oracle regression vectors (re-run with --only-oracle after a deliberate change of the restated solver)
     import orc  # noqa: E402
     scenes = importlib.import_module("c-game-engine_b200.scenes")
 
