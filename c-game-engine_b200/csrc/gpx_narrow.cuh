@@ -88,8 +88,10 @@ __device__ __forceinline__ void box_face(const Box &b, v3 dir, v3 *out4, v3 &nou
 	nout = col(b.R, k) * s;
 }
 
-// Sutherland-Hodgman against one plane; keeps (p - origin).normal >= 0
-__device__ __forceinline__ int clip_plane(const v3 *in, int n, v3 origin, v3 normal, v3 *out)
+// Sutherland-Hodgman against one plane; keeps (p - origin).normal >= 0.  Not inlined: a face test calls it four times,
+// and one copy that stays in the instruction cache beats eight inlined ones (ncu: the inlined clip code was 9 % of the
+// tick's stall samples, 60 % of them "no instruction").
+static __device__ __noinline__ int clip_plane(const v3 *in, int n, v3 origin, v3 normal, v3 *out)
 {
 	int m = 0;
 	if (n == 0) return 0;

@@ -669,7 +669,8 @@ __device__ __forceinline__ void solve_velocity(const Con &c, Rows &R, const Fric
 	}
 }
 
-static __device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
+// returns whether any point of the manifold was outside the slop (i.e. whether anything moved)
+static __device__ __noinline__ bool solve_position(SMan &m, SBody *bodies)
 {
 	SBody &A = bodies[m.a];
 	SBody *B = m.b < STATIC_BODY_BASE ? &bodies[m.b] : nullptr;
@@ -714,6 +715,7 @@ static __device__ __noinline__ void solve_position(SMan &m, SBody *bodies)
 			B->q = qstep(B->q, sym_mul(B->M, cross(r2, P)));
 		}
 	}
+	return ready;
 }
 
 // manifold points: world -> local frames (b static: world)

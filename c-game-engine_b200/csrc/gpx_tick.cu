@@ -596,12 +596,17 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 
 		// ---- 9: position iterations
 		for (uint32_t it = 0; it < a.p.pos_steps; it++)
+		{
+			bool moved = false;
 			for (int c = 0; c < ncol; c++)
 			{
 				for (uint32_t k = lane; k < nact; k += TILE)
-					if (man[act[k]].colour == c) solve_position(man[act[k]], bodies);
+					if (man[act[k]].colour == c) moved = solve_position(man[act[k]], bodies) || moved;
 				tile.sync();
 			}
+			// an iteration that found every point inside the slop changed nothing: the remaining ones would find the same
+			if (!tile.any(moved)) break;
+		}
 
 		pc.mark(PH_POSITION);
 		// ---- this sub-step's manifolds become the warm-start cache (compacted, canonical order kept)

@@ -330,3 +330,96 @@ def test_island_sleeps_together_and_wakes_in_a_cascade(orc, scenes):
     woke = [c for c in counts if c < 8]
     assert woke[0] == 7 and min(counts) == 0 and counts[-1] == 9               # top box first, then everything, then rest
     assert sorted(woke[:woke.index(0) + 1], reverse=True) == woke[:woke.index(0) + 1]   # one way down the column
+
+
+# ------------------------------------------------------------------------------------------------ dissipation / rest
+# Known answers the restated solver has to meet before any trajectory of it is worth comparing (the first
+# restatement left kicked columns whirling at 0.2 m/s for ever): energy leaves a kicked column and does not come back,
+# the column ends at rest at the stacked heights, and sliding friction stops a box where Coulomb's law says.
+
+BOX_MASS, BOX_SIDE = 10.0, 0.4
+
+
+def _kinetic_energy(vel):
+    inertia = BOX_MASS * BOX_SIDE * BOX_SIDE / 6.0
+    return 0.5 * BOX_MASS * float((vel[:, :3].astype(np.float64) ** 2).sum()) + \
+        0.5 * inertia * float((vel[:, 3:].astype(np.float64) ** 2).sum())
+
+
+def _kicked_column(orc, scenes, world, allow_sleeping):
+    """One world of BASELINE config 5: the 8-box column with the bench's Philox kicks of that world index."""
+    o = _stacked_world(orc, scenes)
+    vel = scenes.ensemble_velocities(1, 8, first_world=world)[0]
+    for k, p in enumerate(scenes.stack_positions(8)):
+        o.create(orc.body_desc(position=tuple(p), linear_velocity=tuple(vel[k]), allow_sleeping=allow_sleeping))
+    return o
+
+
+@pytest.mark.parametrize("world", [0, 1, 2, 3])
+def test_kicked_column_loses_its_energy_and_comes_to_rest(orc, scenes, world):
+    """Bodies that may not sleep (the bench's setting): the kinetic energy of the swaying column, taken as the maximum
+    over one-second windows (the sway trades kinetic for potential energy within a window), never grows by more than
+    5 % from one window to the next after the first second, drops at least a hundredfold within ten seconds and is
+    below a millijoule at fifteen; the column still stands."""
+    o = _kicked_column(orc, scenes, world, allow_sleeping=0)
+    ke = []
+    for _ in range(900):
+        assert o.step() == 0
+        ke.append(_kinetic_energy(o.state(8)[1]))
+    win = np.array([max(ke[a:a + 60]) for a in range(0, 900, 60)])
+    assert (win[2:] <= 1.05 * win[1:-1]).all(), f"kinetic energy grows again: {win}"
+    assert win[9] < 0.01 * win[1], f"too little dissipation: {win}"
+    assert win[14] < 1.0e-3, f"still moving after 15 s: {win}"
+    xf, vel = o.state(8)
+    assert np.abs(vel[:, :3]).max() < 0.02 and np.abs(vel[:, 3:]).max() < 0.02
+    assert np.abs(xf[:, 1] - (-1.3 + 0.4 * np.arange(8))).max() < 5e-3
+
+
+@pytest.mark.parametrize("world", [0, 1, 5, 10, 14])
+def test_kicked_column_falls_asleep_at_rest(orc, scenes, world):
+    """With sleeping allowed (Jolt's and therefore the engine's default): every kicked column is asleep within five
+    seconds — exactly at rest, at the stacked heights — and stays that way."""
+    o = _kicked_column(orc, scenes, world, allow_sleeping=1)
+    for _ in range(300):
+        assert o.step() == 0
+    assert o.asleep(8).all()
+    xf, vel = o.state(8)
+    assert (vel == 0).all() and _kinetic_energy(vel) == 0.0
+    assert np.abs(xf[:, 1] - (-1.3 + 0.4 * np.arange(8))).max() < 5e-3
+    for _ in range(300):
+        assert o.step() == 0
+    xf2, vel2 = o.state(8)
+    assert o.asleep(8).all() and (vel2 == 0).all() and np.array_equal(xf, xf2)
+
+
+def test_undisturbed_column_is_at_rest_to_a_millimetre_per_second(orc, scenes):
+    """BASELINE config 2: the column set down without kicks is at rest (|v|, |w| < 1e-3) after 600 ticks."""
+    o = _stacked_world(orc, scenes)
+    for p in scenes.stack_positions(8):
+        o.create(orc.body_desc(position=tuple(p)))
+    for _ in range(600):
+        assert o.step() == 0
+    xf, vel = o.state(8)
+    assert np.abs(vel).max() < 1.0e-3
+    assert np.abs(xf[:, 1] - (-1.3 + 0.4 * np.arange(8))).max() < 5e-3
+
+
+@pytest.mark.parametrize("friction,v0", [(0.2, 1.0), (0.2, 2.0), (0.05, 1.0)])
+def test_sliding_box_stops_at_the_coulomb_distance(orc, scenes, friction, v0):
+    """A box pushed to v0 on the map floor (friction 4.25, combined sqrt(f1 f2)) stops after v0^2 / (2 mu g), less the
+    half step v0 h / 2 the semi-implicit integrator takes off; it does not turn and does not drift sideways."""
+    o = _stacked_world(orc, scenes)
+    o.create(orc.body_desc(position=(0.0, -1.3, -1.5), friction=friction))
+    for _ in range(60):
+        assert o.step() == 0
+    x0 = o.state(1)[0][0, :3].copy()
+    o.set_velocity(0, v=(v0, 0.0, 0.0))
+    for _ in range(240):
+        assert o.step() == 0
+    xf, vel = o.state(1)
+    mu = np.sqrt(friction * 4.25)
+    want = v0 * v0 / (2.0 * mu * 9.81) - 0.5 * v0 / 120.0
+    slid = float(xf[0, 0] - x0[0])
+    assert abs(slid - want) < 0.02 * want + 1.0e-3, (slid, want)
+    assert np.abs(vel).max() < 1.0e-6
+    assert abs(float(xf[0, 2] - x0[2])) < 1.0e-4 and abs(float(xf[0, 4])) < 1.0e-4
