@@ -4,8 +4,10 @@
 Workload (BASELINE.json configs[4], the one `metric` is quoted on): an ensemble of independent worlds, each the
 8-box column over sector 0 of stacked.gmap with Philox-randomised initial velocities.  One STEP is
 one fixed tick (dt = 1/60 s, two collision sub-steps; engine/src/physics/MapPhysics.c:72,105-108) of every world a
-rank owns.  Worlds are independent, so ranks shard the ensemble with no data-path collective: 4096 worlds per GPU
-("weak"); NCCL is used only for the timing reduction and the end-of-run stats gather.
+rank owns.  Worlds are independent, so ranks shard the ensemble with no data-path collective.  The default split is
+the one BASELINE configs[4] / SURVEY §8d C5 name: 4096 worlds IN TOTAL, rank g owning worlds [g*4096/G, (g+1)*4096/G)
+("strong"); `--scaling weak` gives every GPU its own 4096 worlds, and the strong run reports that figure as well
+(`extra.weak`).  NCCL is used only for the timing reduction and the end-of-run stats gather.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA through the C ABI, libgpx.so)
   python bench.py --impl reference ...                            the CPU arm: the oracle restatement on all host
@@ -162,62 +164,86 @@ def tick_rays(gpx, worlds: int, tick: int, out: np.ndarray):
 
 # --------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_tick_rate(orc, scenes, target_s: float, worlds: int, warm_ticks: int):
-    """body-steps/s of the oracle on all host threads over `worlds` sample worlds; ticks scaled to ~target_s."""
+def cpu_sample(orc, scenes, worlds: int, warm_ticks: int, ticks: int):
+    """The CPU arm's one code path: `worlds` sample worlds of the ensemble (world indices 0 .. worlds-1) stepped by ONE
+    orc_step_many call (pthreads over worlds, all host threads) for `ticks` ticks after `warm_ticks` untimed ones.
+    Returns body-steps/s, threads, seconds."""
     ws, arr = make_cpu_ensemble(orc, scenes, worlds)
     L = orc.lib()
     threads = min(L.orc_max_threads(), worlds)
-    L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, warm_ticks)
-    t0 = time.perf_counter()
-    L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 10)
-    per_tick = (time.perf_counter() - t0) / 10
-    ticks = int(max(10, min(600, target_s / max(per_tick, 1e-6))))
+    if warm_ticks:
+        assert L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, warm_ticks) == 0
     t0 = time.perf_counter()
     err = L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, ticks)
     dt = time.perf_counter() - t0
     assert err == 0
-    return worlds * BOXES * ticks / dt, threads, ticks
+    return worlds * BOXES * ticks / dt, threads, dt
+
+
+def cpu_tick_rate(orc, scenes, target_s: float, worlds: int, warm_ticks: int):
+    """cpu_baseline leg of our arm: the same sample, its tick count scaled to ~target_s of CPU work."""
+    _, _, dt = cpu_sample(orc, scenes, worlds, warm_ticks, 10)
+    ticks = int(max(10, min(600, target_s / max(dt / 10, 1e-6))))
+    v, threads, _ = cpu_sample(orc, scenes, worlds, warm_ticks, ticks)
+    return v, threads, ticks
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the same tick on all host threads, same metric/config."""
+    """--impl reference: the CPU restatement of the same tick on all host threads, same metric/config.  Each of the K
+    steps is one tick of a bounded sample of the workload (--ref-worlds of its worlds)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import orc
     scenes = importlib.import_module("c-game-engine_b200.scenes")
-    L = orc.lib()
     worlds = args.ref_worlds
-    ws, arr = make_cpu_ensemble(orc, scenes, worlds)
-    threads = min(L.orc_max_threads(), worlds)
-    for _ in range(args.warmup):
-        L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        err = L.orc_step_many(arr, worlds, 1.0 / 60.0, 2, 1)
-        assert err == 0
-    dt = time.perf_counter() - t0
-    value = worlds * BOXES * args.steps / dt
-    sample = f"{worlds} of the {args.worlds} worlds per step (first {worlds} world indices), {args.steps} ticks"
+    value, threads, dt = cpu_sample(orc, scenes, worlds, args.warmup, args.steps)
+    total = args.worlds if args.scaling == "strong" else args.worlds * args.gpus
+    sample = (f"{worlds} of the {total} worlds (world indices 0..{worlds - 1}), {args.steps} ticks after {args.warmup} "
+              f"warm-up ticks, one orc_step_many call on {threads} host threads")
     line = {
         "impl": "reference", "metric": "body_steps_per_s", "value": value, "unit": "body-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "CPU restatement (oracle/orc.c); Jolt/joltc is not vendored and cannot be built here"},
+                         "note": "CPU restatement (oracle/orc.c): brute-force triangle loop, all-pairs broadphase; "
+                                 "Jolt/joltc is not vendored and cannot be built here"},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     return line
 
 
+def worlds_of_rank(args, rank: int, world_size: int):
+    """(first world index, worlds) of a rank: strong = BASELINE configs[4]'s split of args.worlds in total."""
+    if args.scaling == "strong":
+        first = args.worlds * rank // world_size
+        return first, args.worlds * (rank + 1) // world_size - first
+    return rank * args.worlds, args.worlds
+
+
 def workload_config(args):
-    return {"workload": f"C5 ensemble: {args.worlds} independent stacked.gmap worlds per GPU x {BOXES}-box column, "
-                        "Philox initial velocities (key 0x5EED0005), dt=1/60, 2 sub-steps, 10 velocity + 2 position iterations",
-            "worlds_per_gpu": args.worlds, "bodies_per_world": BOXES, "static_triangles": 396,
+    total = args.worlds if args.scaling == "strong" else args.worlds * args.gpus
+    return {"workload": f"C5 ensemble: {total} independent stacked.gmap worlds x {BOXES}-box column over {args.gpus} GPU(s) "
+                        f"({args.scaling} scaling), Philox initial velocities (key 0x5EED0005), dt=1/60, 2 sub-steps, "
+                        "10 velocity + 2 position iterations, bodies may not sleep",
+            "worlds_total": total, "worlds_per_gpu": total // max(args.gpus, 1), "bodies_per_world": BOXES, "static_triangles": 396,
             "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
             "parallelism": f"worlds sharded, {args.gpus} rank(s), no data-path collective"}
+
+
+def timed_ticks(g, steps, flush, torch):
+    """`steps` ticks of the ensemble, CUDA events around each gpx_step on the library's stream, L2 flushed before each."""
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        g.timer_begin()
+        rc = g.step()
+        ms += g.timer_end()
+        assert rc == 0, f"gpx_step error {rc}"
+    return ms
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -253,8 +279,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    W = args.worlds
-    first = rank * W
+    first, W = worlds_of_rank(args, rank, world_size)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     # ---------------- value: ticks with state resident in HBM
@@ -267,15 +292,8 @@ def run_gpu(args):
     if rank == 0:
         clocks.start()
     launches0 = L.gpx_launch_count()
-    dev_ms = 0.0
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        g.timer_begin()
-        rc = g.step()
-        dev_ms += g.timer_end()
-        assert rc == 0, f"gpx_step error {rc}"
+    dev_ms = timed_ticks(g, args.steps, flush, torch)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     launches = L.gpx_launch_count() - launches0
@@ -284,8 +302,10 @@ def run_gpu(args):
     dev_ms = max_over_ranks(dev_ms)
     ms_per_step = dev_ms / args.steps
     bodies_per_rank = W * BOXES
-    value = world_size * bodies_per_rank / (ms_per_step * 1e-3)
+    total_worlds = args.worlds if args.scaling == "strong" else args.worlds * world_size
+    value = total_worlds * BOXES / (ms_per_step * 1e-3)
     achieved = bodies_per_rank * BYTES_PER_BODY_STEP / (ms_per_step * 1e-3) / 1e9
+    ticks_done = args.warmup + args.steps
 
     # ---------------- e2e: the engine-facing per-tick sequence with host buffers
     n_rays = W * RAYS_PER_WORLD_TICK
@@ -296,6 +316,7 @@ def run_gpu(args):
         g.raycast_into_async(h_rays, h_hits)
         g.step()
         g.sync()
+    ticks_done += 3
     check_hits = np.array(h_hits[:2048], copy=True)
     g.raycast_into(h_rays, h_hits)
     # (the state moved on by one tick between the two batches, so only static hits are comparable)
@@ -310,42 +331,83 @@ def run_gpu(args):
         assert rc == 0
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world_size * bodies_per_rank * e2e_steps / e2e_s
+    ticks_done += e2e_steps
+    e2e_value = total_worlds * BOXES * e2e_steps / e2e_s
     h2d = n_rays * 32
     d2h = n_rays * 16 + 2 * 16 * bodies_per_rank + 4
     stats = g.stats()
     assert (stats["error"] == 0).all()
 
-    # ---------------- secondary metric: 2^20 hitscan rays against shapes.gmap (C3)
+    # the state the sample check below compares with the oracle (rank 0's first worlds, after `ticks_done` ticks)
+    n_check = min(16, W)
+    xf_check = g.transforms()[:n_check].copy() if rank == 0 else None
+
     only = args.headline_only  # profiling runs: the launch list then holds the headline step's kernels and nothing else
+    # ---------------- the other split of the same ensemble (N > 1): 4096 worlds per GPU when the headline is the strong
+    # split, so both curves come from one run
+    weak_res = None
+    if world_size > 1 and args.scaling == "strong" and not only:
+        g2 = make_gpu_ensemble(gpx, scenes, args.worlds, rank * args.worlds, local_rank)
+        for _ in range(args.warmup):
+            assert g2.step() == 0
+        assert g2.sync() == 0
+        barrier()
+        k = min(args.steps, 200)
+        ms2 = max_over_ranks(timed_ticks(g2, k, flush, torch)) / k
+        weak_res = {"scaling": "weak", "worlds_per_gpu": args.worlds, "steps": k, "ms_per_step": ms2,
+                    "value": world_size * args.worlds * BOXES / (ms2 * 1e-3), "unit": "body-steps/s"}
+        del g2
+
+    # ---------------- secondary metric: 2^20 hitscan rays against shapes.gmap (C3)
     rays_res = None if only else bench_rays(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
     # ---------------- C4: one wide world of 100k boxes (replicated per rank)
-    single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if rank == 0 and not only else None
-    test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if rank == 0 and not only else None
     wide_res = None if args.no_wide or only else bench_wide(gpx, scenes, args, local_rank, rank, world_size, barrier, max_over_ranks, flush, hbm_peak)
 
-    # ---------------- end-of-run stats gather over NCCL (the only collective)
+    # ---------------- end-of-run stats gather over NCCL (the only collective).  Everything after it runs on
+    # rank 0 alone, with the process group gone, so the other GPUs are released instead of spinning in a barrier.
     gathered_worlds = W
     if dist is not None:
         t = torch.from_numpy(stats.view(np.uint8).reshape(-1).copy()).cuda()
+        if args.scaling == "strong" and total_worlds % world_size:
+            raise SystemExit("bench.py: --worlds must be a multiple of --gpus for the gather")
         out = [torch.empty_like(t) for _ in range(world_size)]
         dist.all_gather(out, t)
         gathered_worlds = sum(o.numel() for o in out) // 32
+        dist.barrier()
+        dist.destroy_process_group()
 
     line = None
     if rank == 0:
+        # ---------------- latency lines (C2, C1) and the saturation sweep: one GPU
+        single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if not only else None
+        test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if not only else None
+        sweep = bench_saturation(gpx, scenes, args, local_rank, flush, torch) if not only else None
         cpu = None
+        sample_ok = None
         if not args.no_cpu:
             import orc
             v, threads, ticks = cpu_tick_rate(orc, scenes, args.cpu_seconds, args.ref_worlds, 5)
             cpu = {"value": v, "unit": "body-steps/s", "cores": threads, "kind": "port",
-                   "sample": f"{args.ref_worlds} worlds of the same ensemble x {ticks} ticks on {threads} host threads "
-                             "(oracle/orc.c via orc_step_many; Jolt unavailable in this environment)"}
+                   "sample": f"{args.ref_worlds} worlds of the same ensemble (world indices 0..{args.ref_worlds - 1}) x {ticks} ticks, one "
+                             f"orc_step_many call on {threads} host threads (oracle/orc.c: brute-force triangle loop, all-pairs "
+                             "broadphase; Jolt unavailable in this environment)"}
+            # the timed ensemble against the oracle: the first worlds of rank 0, every tick this run made, bit for bit
+            ws, arr = make_cpu_ensemble(orc, scenes, n_check, first_world=first)
+            assert orc.lib().orc_step_many(arr, n_check, 1.0 / 60.0, 2, ticks_done) == 0
+            xo = np.stack([o.state(BOXES)[0] for o in ws])
+            sample_ok = bool(np.array_equal(xo.view(np.uint32), xf_check.view(np.uint32)))
+            if rays_res is not None:
+                cpu_rays_leg(orc, scenes, args, rays_res)
+            if wide_res is not None:
+                cpu_wide_leg(orc, scenes, args, wide_res)
+        if rays_res is not None:
+            rays_res.pop("_check", None)
+        issue = measured_traffic("k_tick_inst_executed")
         line = {
             "metric": "body_steps_per_s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -354,19 +416,41 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "k_tick", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": args.traffic if args.traffic is not None else measured_traffic("k_tick"), "peak_source": peak_src,
                          "bytes_per_unit": BYTES_PER_BODY_STEP, "units_per_launch": bodies_per_rank},
+            # what actually bounds k_tick: warp instructions issued.  inst = smsp__inst_executed.sum per launch from the
+            # committed ncu capture (profiles/traffic.json, 4096 worlds); peak = 148 SMs x 4 schedulers x 1 instruction / cycle
+            "roofline_issue": None if issue is None or W != 4096 else {
+                "bound": "fp32_issue", "kernel": "k_tick", "achieved": issue / (ms_per_step * 1e-3) / 1e9,
+                "peak": 148 * 4 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clk else 148 * 4 * 1.965, "unit": "G warp-inst/s",
+                "frac": issue / (ms_per_step * 1e-3) / (148 * 4 * ((clk["sm_mhz"] if clk and clk["sm_mhz"] else 1965.0) * 1e6)),
+                "inst_per_launch": issue},
             "cpu_baseline": cpu,
+            "sample_matches_oracle": sample_ok,
+            "sample_check": f"transforms of worlds {first}..{first + n_check - 1} after all {ticks_done} ticks of this run vs independent oracle worlds, bit for bit",
             "rays": rays_res,
             "wide": wide_res,
             "single_world": single_res,
             "test_map": test_map_res,
+            "extra": {"weak": weak_res, "saturation": sweep},
             "wall_ms_timed_region": wall_ms,
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
         }
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
     return line
+
+
+def bench_saturation(gpx, scenes, args, device, flush, torch):
+    """One GPU, the same columns, 512 ... 32768 worlds: where the tick stops being one wave of latency-bound warps."""
+    out = []
+    for W in (512, 1024, 2048, 4096, 8192, 16384, 32768):
+        g = make_gpu_ensemble(gpx, scenes, W, 0, device)
+        for _ in range(20):
+            assert g.step() == 0
+        assert g.sync() == 0
+        k = 60
+        ms = timed_ticks(g, k, flush, torch) / k
+        out.append({"worlds": W, "ms_per_tick": ms, "body_steps_per_s": W * BOXES / (ms * 1e-3)})
+        del g
+    return out
 
 
 def make_wide_world(gpx, scenes, pos, device):
@@ -503,8 +587,11 @@ def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
            "roofline": {"bound": "hbm", "kernel": "wide tick (all kw_* kernels)", "achieved": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
            "min_y": float(y.min())}
-    if rank == 0 and not args.no_cpu:
-        import orc
+    return res
+
+
+def cpu_wide_leg(orc, scenes, args, res):
+    if True:
         sp = scenes.lattice_positions(16, 10, 16)
         o = orc.World(len(sp))
         for p, t in scenes.box_map():
@@ -522,7 +609,6 @@ def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
         res["cpu_baseline"] = {"value": len(sp) * k / dt, "unit": "body-steps/s", "cores": 1, "kind": "port",
                                "sample": f"16 x 10 x 16 = {len(sp)} boxes of the same lattice, {k} ticks, single thread "
                                          "(oracle/orc.c wide mode; its broadphase is all-pairs, so larger samples are not representative)"}
-    return res
 
 
 def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ranks, flush, hbm_peak):
@@ -572,8 +658,16 @@ def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / hbm_peak,
                         "traffic": args.ray_traffic if args.ray_traffic is not None else measured_traffic("k_raycast")},
            "hit_fraction": hit_frac}
-    if rank == 0 and world_size == 1 and not args.no_cpu:
-        import orc
+    if rank == 0:
+        res["_check"] = (rays, np.array(h_hits[:min(n, args.cpu_rays)], copy=True))
+    return res
+
+
+def cpu_rays_leg(orc, scenes, args, res):
+    rays, h_hits = res.pop("_check")
+    n = len(rays)
+    if True:
+        meshes = scenes.load_static("shapes")
         o = orc.World(8)
         for pos, tris in meshes:
             o.add_mesh(pos, tris)
@@ -584,7 +678,6 @@ def bench_rays(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
         res["cpu_baseline"] = {"value": m / dt, "unit": "rays/s", "cores": orc.lib().orc_max_threads(), "kind": "port",
                                "sample": f"first {m} rays of the batch, brute force over 512 triangles (oracle/orc.c)"}
         res["sample_matches_oracle"] = bool(np.array_equal(ho.view(np.uint8), np.asarray(h_hits[:m]).view(np.uint8)))
-    return res
 
 
 def main():
@@ -593,7 +686,9 @@ def main():
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds in total (--scaling strong) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: BASELINE configs[4], --worlds in total split over the GPUs; weak: --worlds per GPU")
     ap.add_argument("--rays", type=int, default=1 << 20, help="rays per GPU for the secondary metric")
     ap.add_argument("--ray-reps", type=int, default=20)
     ap.add_argument("--ref-worlds", type=int, default=256, help="worlds per step in the CPU sample")

@@ -161,6 +161,7 @@ struct Cursor
 	const uint8_t *d;
 	uint64_t n, o = 0;
 	bool bad = false;
+	int depth = 0;  // nesting of arrays / key-value lists while skipping a parameter (hostile files recurse for ever)
 	template <typename T>
 	T get()
 	{
@@ -185,6 +186,13 @@ struct Cursor
 };
 void Cursor::skip_param()
 {
+	if (++depth > 32)
+	{
+		bad = true;
+		depth--;
+		return;
+	}
+	struct Leave { int &d; ~Leave() { d--; } } leave{depth};
 	uint8_t t = get<uint8_t>();
 	switch (t)
 	{
@@ -412,9 +420,18 @@ int gpx_static_info(const gpx_world *w, uint32_t *n_tris, uint32_t *n_nodes, uin
  * then numCollisionMeshes x { pos, subShapeCount x { numTris x 9 f32 } }; each mesh becomes one static body with
  * friction 4.25 (MapLoader.c:263). */
 
+static int load_gmap_body(gpx_world *w, const uint8_t *body, uint64_t size);
+
 int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size)
 {
 	if (!w || !body) return -GPX_ERR_INVALID_ARG;
+	// nothing may unwind through the C ABI: allocation failures on a corrupt file become an error code
+	try { return load_gmap_body(w, body, size); }
+	catch (...) { return -GPX_ERR_INVALID_ARG; }
+}
+
+static int load_gmap_body(gpx_world *w, const uint8_t *body, uint64_t size)
+{
 	Cursor c{body, size};
 	if (c.get<uint8_t>()) c.skip_string();
 	c.skip_string();
@@ -457,7 +474,7 @@ int gpx_static_load_gmap(gpx_world *w, const uint8_t *body, uint64_t size)
 		for (uint64_t j = 0; j < n_sub && !c.bad; j++)
 		{
 			const uint64_t nt = c.get<uint64_t>();
-			if (c.bad || c.o + nt * 36u > c.n) { c.bad = true; break; }
+			if (c.bad || nt > (c.n - c.o) / 36u) { c.bad = true; break; }  // (no nt * 36: it wraps for a hostile count)
 			const size_t at = tris.size();
 			tris.resize(at + nt * 9u);
 			memcpy(tris.data() + at, c.d + c.o, nt * 36u);
@@ -486,8 +503,10 @@ int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t s
 	memcpy(&raw_size, blob + 7, 8);
 	memcpy(&gz_size, blob + 15, 8);
 	if (magic != 0x454D4147u || blob[4] != 2u) return -GPX_ERR_INVALID_ARG;
-	if (size - HEADER != gz_size || raw_size > (1ull << 32)) return -GPX_ERR_INVALID_ARG;
-	std::vector<uint8_t> body((size_t)raw_size);
+	if (size - HEADER != gz_size || raw_size >= (1ull << 32)) return -GPX_ERR_INVALID_ARG;  // avail_out is 32 bits wide
+	std::vector<uint8_t> body;
+	try { body.resize((size_t)raw_size); }
+	catch (...) { return -GPX_ERR_INVALID_ARG; }
 	z_stream zs;
 	memset(&zs, 0, sizeof(zs));
 	if (inflateInit2(&zs, MAX_WBITS | 16) != Z_OK) return -GPX_ERR_INVALID_ARG;
@@ -890,6 +909,9 @@ int gpx_sync_transforms(gpx_world *w)
 	// positions | orientations | error word: one allocation on each side, one copy
 	GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, 2 * sizeof(float4) * nb + sizeof(uint32_t), cudaMemcpyDeviceToHost,
 							 w->stream));
+	// the error word has been read: the ticks after this synchronisation report their own errors (Jolt's Update returns
+	// each update's result); the per-world words d_err[1 + world] stay sticky for gpx_read_stats
+	GPX_CUDA(cudaMemsetAsync(w->d_err, 0, sizeof(uint32_t), w->stream));
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	w->m_err[0] = *reinterpret_cast<const uint32_t *>(w->mb_pos[back] + 2 * nb);
 	w->mirror_gen.store(gen + 1u, std::memory_order_release);  // the tick just read back becomes the front
@@ -946,10 +968,9 @@ int gpx_read_stats(gpx_world *w, gpx_world_stats *out)
 
 /* ---- rays */
 
-int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
+// callers hold w->mu
+static int raycast_device_locked(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 {
-	if (!w || (n && (!d_rays || !d_hits))) return GPX_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	int rc;
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
@@ -957,10 +978,20 @@ int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void 
 	return launch_raycast(w, d_rays, n, d_hits);
 }
 
+int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
+{
+	if (!w || (n && (!d_rays || !d_hits))) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	return raycast_device_locked(w, d_rays, n, d_hits);
+}
+
+// One batch through the world's staging buffers.  The world's mutex is held from staging the rays to the last use of
+// the shared buffers (two threads casting on one world would otherwise overwrite each other's rays or hits, or free
+// buffers the other is about to launch with); the synchronous variant therefore also waits inside.
 static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async)
 {
+	std::lock_guard<std::mutex> lk(w->mu);
 	{
-		std::lock_guard<std::mutex> lk(w->mu);
 		cudaSetDevice(w->device);
 		int jr = join_hits(w);  // the previous batch's hits leave d_hits before this one's kernel writes it
 		if (jr != GPX_OK) return jr;
@@ -977,16 +1008,16 @@ static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hi
 		}
 		GPX_CUDA(cudaMemcpyAsync(w->d_rays, rays, sizeof(gpx_ray) * n, cudaMemcpyHostToDevice, w->stream));
 	}
-	int rc = gpx_raycast_batch_device(w, w->d_rays, n, w->d_hits);
+	int rc = raycast_device_locked(w, w->d_rays, n, w->d_hits);
 	if (rc != GPX_OK) return rc;
 	if (!async)
 	{
 		GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream));
+		GPX_CUDA(cudaStreamSynchronize(w->stream));
 		return GPX_OK;
 	}
 	// async: the copy back overlaps whatever the caller enqueues next (the tick); the world's stream picks it up again
 	// at the next gpx_sync_transforms / gpx_device_sync / ray batch
-	std::lock_guard<std::mutex> lk(w->mu);
 	GPX_CUDA(cudaEventRecord(w->ev_rays_done, w->stream));
 	GPX_CUDA(cudaStreamWaitEvent(w->stream_copy, w->ev_rays_done, 0));
 	GPX_CUDA(cudaMemcpyAsync(hits, w->d_hits, sizeof(gpx_hit) * n, cudaMemcpyDeviceToHost, w->stream_copy));
@@ -999,10 +1030,7 @@ int gpx_raycast_batch(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hi
 {
 	if (!w || (n && (!rays || !hits))) return GPX_ERR_INVALID_ARG;
 	if (n == 0) return GPX_OK;
-	int rc = raycast_enqueue(w, rays, n, hits, false);
-	if (rc != GPX_OK) return rc;
-	GPX_CUDA(cudaStreamSynchronize(w->stream));
-	return GPX_OK;
+	return raycast_enqueue(w, rays, n, hits, false);
 }
 
 int gpx_raycast_batch_async(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits)

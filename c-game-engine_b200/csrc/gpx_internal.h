@@ -15,6 +15,7 @@ constexpr uint32_t STATIC_BODY_BASE = 0x400000u;  // ids >= this name static col
 constexpr float RAY_MISS_FRACTION = 2.0f;
 constexpr uint32_t CHARACTER_BODY_ID = 0x3FFFFFu;  // pseudo body id of a world's player character in contact events
 constexpr uint32_t CHARACTER_MAX_CONTACTS = 64;
+constexpr int GPX_MAX_DEVICES = 64;  // per-device bookkeeping of function attributes
 constexpr float BVH_PAD = 1.0e-3f;  // node boxes are padded; leaves are re-tested exactly
 
 // body flag word

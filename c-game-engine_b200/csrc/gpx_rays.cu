@@ -7,6 +7,7 @@
 // Kernel shape: persistent CTAs, one per SM slot; each CTA copies the whole tree (nodes + triangle records) into
 // shared memory once with a bulk async copy, then its warps pull batches of 32 rays.  A ray is 32 B in, 16 B out;
 // everything else stays on chip.
+#include <atomic>
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
 
@@ -302,12 +303,15 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 	unsigned long long want = (n + RAY_THREADS - 1) / RAY_THREADS;
 	if (smem)
 	{
-		static bool attr_set = false;
-		if (!attr_set)
+		// function attributes are per device, and one process may hold worlds on several: remember per device
+		static std::atomic<bool> attr_set[GPX_MAX_DEVICES];
+		if (dev >= 0 && dev < GPX_MAX_DEVICES && !attr_set[dev].load(std::memory_order_acquire))
 		{
 			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			attr_set = true;
+			attr_set[dev].store(true, std::memory_order_release);
 		}
+		else if (dev < 0 || dev >= GPX_MAX_DEVICES)
+			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		int per_sm = (int)((227u * 1024u) / (tree_bytes + 1024u));
 		if (per_sm < 1) per_sm = 1;
 		if (per_sm > 4) per_sm = 4;

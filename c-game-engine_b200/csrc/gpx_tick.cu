@@ -23,6 +23,7 @@
 // and identical for any TILE width.
 #include <cooperative_groups.h>
 
+#include <atomic>
 #include <cstdlib>
 
 #include "gpx_solver.cuh"
@@ -904,14 +905,19 @@ static int launch_tick_t(gpx_world *w, const TickArgs &a, cudaStream_t stream, u
 	while (wpb > 1 && per_world * wpb > budget) wpb >>= 1;
 	const uint32_t threads = wpb * TILE;
 	const size_t smem = per_world * wpb;
-	static size_t configured = 0;  // per instantiation
-	if (smem > configured)
+	// per instantiation AND per device (function attributes are per device; one process may hold worlds on several, each
+	// stepping on its own thread)
+	static std::atomic<size_t> configured[GPX_MAX_DEVICES];
+	const int device = w->device;
+	const int dev = device >= 0 && device < GPX_MAX_DEVICES ? device : 0;
+	if (device != dev || smem > configured[dev].load(std::memory_order_acquire))
 	{
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		int carve = 100;
 		if (const char *e = getenv("GPX_CARVEOUT")) carve = atoi(e);  // tuning knob for profiling runs
 		GPX_CUDA(cudaFuncSetAttribute(k_tick<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-		configured = smem;
+		size_t old = configured[dev].load(std::memory_order_relaxed);
+		while (old < smem && !configured[dev].compare_exchange_weak(old, smem, std::memory_order_release)) {}
 	}
 	const uint32_t grid = (grid_worlds + wpb - 1) / wpb;
 	k_tick<TILE><<<grid, threads, smem, stream>>>(a);

@@ -1533,11 +1533,15 @@ int wide_counters(gpx_world *w, uint32_t *out8)
 	return GPX_OK;
 }
 
+__global__ void kw_or_word(uint32_t *dst, const uint32_t *src) { *dst |= *src; }
+
 int launch_wide_tick(gpx_world *w, float dt, int substeps)
 {
 	WideDevice *d = w->wide;
 	cudaStream_t st = w->stream;
 	if (substeps < 1) substeps = 1;
+	// every tick reports its own errors (Jolt's Update returns that update's result): the error word starts clean
+	GPX_CUDA(cudaMemsetAsync(d->counters + WC_ERR, 0, sizeof(uint32_t), st));
 	WideArgs a;
 	a.bs = w->bs;
 	a.bodies = d->bodies;
@@ -1644,9 +1648,10 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		int rc = wide_events(w, d->man[d->cur ^ 1]);
 		if (rc != GPX_OK) return rc;
 	}
-	// merge the error word into the world's error slot (d_err[0], d_err[1])
+	// this tick's error word into the world's error slot (d_err[0]); d_err[1] keeps every error the world ever had (stats)
 	GPX_CUDA(cudaMemcpyAsync(w->d_err, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-	GPX_CUDA(cudaMemcpyAsync(w->d_err + 1, d->counters + WC_ERR, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+	kw_or_word<<<1, 1, 0, st>>>(w->d_err + 1, d->counters + WC_ERR);
+	count_launch();
 	GPX_CUDA(cudaGetLastError());
 	return GPX_OK;
 }

@@ -331,7 +331,9 @@ JPH_PhysicsSystem *JPH_PhysicsSystem_Create(const JPH_PhysicsSystemSettings *s)
 	}
 	auto *sys = new JPH_PhysicsSystem;
 	const char *env = getenv("GPX_MAX_BODIES");
-	sys->max_bodies = env ? (uint32_t)atoi(env) : (s->maxBodies ? s->maxBodies : 64u);
+	// joltc's default when the engine leaves maxBodies at 0 (Physics.c:91-97 does): 10240 bodies, served by the wide-world
+	// kernels; a map known to stay within 64 bodies can ask for the single fused kernel with maxBodies / GPX_MAX_BODIES <= 64
+	sys->max_bodies = env ? (uint32_t)atoi(env) : (s->maxBodies ? s->maxBodies : 10240u);
 	// The engine's MAX_CONTACT_CONSTRAINTS (16384) is a pool bound, not a need: the default sizing (3 per body) applies
 	// unless the limit is smaller.
 	sys->max_manifolds = 0;
@@ -424,7 +426,10 @@ JPH_PhysicsUpdateError JPH_PhysicsSystem_Update(JPH_PhysicsSystem *sys, float dt
 	if (rc != GPX_OK)
 	{
 		fprintf(stderr, "joltc_gpx: tick failed with %d (%s)\n", rc, gpx_last_error());
-		return (JPH_PhysicsUpdateError)((rc & 7) ? (rc & 7) : JPH_PhysicsUpdateError_ContactConstraintsFull);
+		// tick errors are Jolt's own bits (1, 2, 4); library errors (CUDA, capacity, arguments) have no Jolt counterpart and
+		// are reported as "contact constraints full", the engine treats any non-zero value as fatal (MapPhysics.c:109-113)
+		const bool tick_error = rc > 0 && rc < 8;
+		return (JPH_PhysicsUpdateError)(tick_error ? rc : JPH_PhysicsUpdateError_ContactConstraintsFull);
 	}
 	deliver_character_events(sys);
 	return JPH_PhysicsUpdateError_None;
@@ -661,7 +666,11 @@ JPH_BodyID make_body(JPH_PhysicsSystem *sys, const JPH_BodyCreationSettings *st)
 		d.ray_flags = st->user_data == 0 ? GPX_BODY_BLOCKS_LASERS : 0u;  // refined by the body filter before filtered casts
 		d.user_data = st->user_data;
 		id = gpx_body_create(sys->w, 0, &d);
-		if (id == GPX_INVALID_BODY) return JPH_BodyId_InvalidBodyID;
+		if (id == GPX_INVALID_BODY)
+		{
+			complain("CreateAndAddBody: no free body slot (JPH_PhysicsSystemSettings.maxBodies / GPX_MAX_BODIES too small)");
+			return JPH_BodyId_InvalidBodyID;
+		}
 		rec.center = lo.center;
 	}
 	if (st->shape)
