@@ -343,6 +343,9 @@ void gpx_world_destroy(gpx_world *w)
 	if (w->ev_rays_done) cudaEventDestroy(w->ev_rays_done);
 	if (w->ev_hits_done) cudaEventDestroy(w->ev_hits_done);
 	if (w->stream_copy) cudaStreamDestroy(w->stream_copy);
+	if (w->stream_h2d) cudaStreamDestroy(w->stream_h2d);
+	for (cudaEvent_t e : w->ev_pipe)
+		if (e) cudaEventDestroy(e);
 	cudaFree(w->d_busy); cudaFree(w->d_busy_n); cudaFree(w->d_busy_flag);
 	if (w->stream) cudaStreamDestroy(w->stream);
 	delete w;
@@ -985,6 +988,39 @@ int gpx_raycast_batch_device(gpx_world *w, const void *d_rays, uint64_t n, void 
 	return raycast_device_locked(w, d_rays, n, d_hits);
 }
 
+// callers hold w->mu; the staging buffers hold n rays
+static int raycast_pipelined(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, uint64_t chunks)
+{
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	if (!w->stream_h2d) GPX_CUDA(cudaStreamCreateWithFlags(&w->stream_h2d, cudaStreamNonBlocking));
+	for (uint64_t k = 0; k < 2 * chunks + 1; k++)
+		if (!w->ev_pipe[k]) GPX_CUDA(cudaEventCreateWithFlags(&w->ev_pipe[k], cudaEventDisableTiming));
+	// the copy stream starts after whatever the world's stream still does with the staging buffers
+	GPX_CUDA(cudaEventRecord(w->ev_pipe[2 * chunks], w->stream));
+	GPX_CUDA(cudaStreamWaitEvent(w->stream_h2d, w->ev_pipe[2 * chunks], 0));
+	const uint64_t per = ((n + chunks - 1) / chunks + 1023u) & ~1023ull;
+	gpx_ray *d_rays = static_cast<gpx_ray *>(w->d_rays);
+	gpx_hit *d_hits = static_cast<gpx_hit *>(w->d_hits);
+	uint64_t c = 0;
+	for (uint64_t off = 0; off < n; off += per, c++)
+	{
+		const uint64_t cnt = n - off < per ? n - off : per;
+		GPX_CUDA(cudaMemcpyAsync(d_rays + off, rays + off, sizeof(gpx_ray) * cnt, cudaMemcpyHostToDevice, w->stream_h2d));
+		GPX_CUDA(cudaEventRecord(w->ev_pipe[2 * c], w->stream_h2d));
+		GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_pipe[2 * c], 0));
+		if ((rc = launch_raycast(w, d_rays + off, cnt, d_hits + off)) != GPX_OK) return rc;
+		GPX_CUDA(cudaEventRecord(w->ev_pipe[2 * c + 1], w->stream));
+		GPX_CUDA(cudaStreamWaitEvent(w->stream_copy, w->ev_pipe[2 * c + 1], 0));
+		GPX_CUDA(cudaMemcpyAsync(hits + off, d_hits + off, sizeof(gpx_hit) * cnt, cudaMemcpyDeviceToHost, w->stream_copy));
+	}
+	GPX_CUDA(cudaEventRecord(w->ev_hits_done, w->stream_copy));
+	GPX_CUDA(cudaStreamWaitEvent(w->stream, w->ev_hits_done, 0));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+
 // One batch through the world's staging buffers.  The world's mutex is held from staging the rays to the last use of
 // the shared buffers (two threads casting on one world would otherwise overwrite each other's rays or hits, or free
 // buffers the other is about to launch with); the synchronous variant therefore also waits inside.
@@ -1006,8 +1042,12 @@ static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hi
 			GPX_CUDA(cudaMalloc(&w->d_hits, sizeof(gpx_hit) * n));
 			w->ray_cap = n;
 		}
-		GPX_CUDA(cudaMemcpyAsync(w->d_rays, rays, sizeof(gpx_ray) * n, cudaMemcpyHostToDevice, w->stream));
 	}
+	// A large synchronous batch is PCIe-bound (48 bytes per ray cross the bus): cut it into chunks so that chunk c's
+	// kernel and chunk c-1's hits copy run under chunk c+1's rays copy.
+	constexpr uint64_t PIPE_MIN = 1ull << 18, PIPE_CHUNKS = 8;
+	if (!async && n >= PIPE_MIN) return raycast_pipelined(w, rays, n, hits, PIPE_CHUNKS);
+	GPX_CUDA(cudaMemcpyAsync(w->d_rays, rays, sizeof(gpx_ray) * n, cudaMemcpyHostToDevice, w->stream));
 	int rc = raycast_device_locked(w, w->d_rays, n, w->d_hits);
 	if (rc != GPX_OK) return rc;
 	if (!async)

@@ -832,6 +832,11 @@ int build_static(gpx_world *w)
 		lo[a] = v < lo[a] ? v : lo[a];
 		hi[a] = v > hi[a] ? v : hi[a];
 	}
+	for (int k = 0; k < 3; k++)
+	{
+		sd.lo[k] = lo[k];
+		sd.hi[k] = hi[k];
+	}
 	float3 flo = make_float3(lo[0], lo[1], lo[2]);
 	float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.0f,
 							 hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.0f);
@@ -862,6 +867,7 @@ int build_static(gpx_world *w)
 	sd.ray_tri = sd.tri;
 	sd.n_ray_leaves = n;
 	sd.n_ray_nodes = sd.n_nodes;
+	sd.ray_depth = 64;
 	// the rays' tree: split references, as many as still let the whole tree sit in one SM's shared memory, under a SAH
 	// topology built on the host (maps too large for shared memory keep one leaf per triangle but still get the SAH)
 	uint32_t budget = RAY_TREE_MAX_LEAVES;
@@ -885,6 +891,7 @@ int build_static(gpx_world *w)
 						topo.depth <= 56 ? &topo : nullptr);
 		sd.n_ray_leaves = nr;
 		sd.n_ray_nodes = nr - 1;
+		sd.ray_depth = topo.depth <= 56 ? (uint32_t)topo.depth : 64u;
 	}
 	cudaFree(d_tris); cudaFree(d_body); cudaFree(d_fr); cudaFree(d_rf); cudaFree(d_refb); cudaFree(d_ref_orig);
 	return rc;

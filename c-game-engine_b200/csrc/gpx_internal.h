@@ -64,6 +64,8 @@ struct StaticDevice
 	// the rays' tree: same record formats over split references (large triangles cut into several leaves that all
 	// point at the original triangle); aliases the tree above when nothing was split
 	uint32_t n_ray_leaves = 0, n_ray_nodes = 0;
+	float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounds of the static geometry (rays: coherence bins)
+	uint32_t ray_depth = 64;  // deepest leaf of the rays' tree (64: unknown, a radix tree's bound)
 	float4 *ray_tri = nullptr, *ray_nodes = nullptr;
 };
 constexpr uint32_t RAY_TREE_MAX_HOST_BUILD = 1u << 18;  // triangles up to which the rays' tree gets its SAH topology on the host
@@ -120,6 +122,9 @@ struct gpx_world
 	cudaStream_t stream_copy = nullptr;
 	cudaEvent_t ev_rays_done = nullptr, ev_hits_done = nullptr;
 	bool hits_pending = false;
+	// gpx_raycast_batch on large batches: chunks pipelined over three streams (H2D | kernel | D2H), one event pair per chunk
+	cudaStream_t stream_h2d = nullptr;
+	cudaEvent_t ev_pipe[32] = {};
 	uint32_t *d_busy = nullptr, *d_busy_n = nullptr;
 	uint8_t *d_busy_flag = nullptr;
 	uint32_t busy_cur = 0;  // which of the two routing sets (list / count / flags) the coming tick reads

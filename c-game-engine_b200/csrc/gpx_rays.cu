@@ -8,6 +8,7 @@
 // shared memory once with a bulk async copy, then its warps pull batches of 32 rays.  A ray is 32 B in, 16 B out;
 // everything else stays on chip.
 #include <atomic>
+#include <cstdlib>
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
 
@@ -16,6 +17,7 @@ namespace gpx {
 constexpr int RAY_THREADS = 256;       // CTA size when several CTAs share an SM
 constexpr int RAY_THREADS_MAX = 1024;  // one CTA per SM (a large tree in shared memory): as many warps as registers allow
 constexpr int STACK_DEPTH = 64;  // a radix tree over 64-bit keys is at most 64 levels deep
+constexpr int SSTACK_DEPTH = 32;  // levels of the shared-memory traversal stack (16-bit entries, one column per thread)
 
 struct RayArgs
 {
@@ -100,10 +102,14 @@ __device__ __forceinline__ bool ray_sphere(v3 o, v3 d, float tmax, v3 x, float r
 	return true;
 }
 
-// One ray through the tree.  NODES/TRIS point at shared or global memory.
+// One ray through the tree.  NODES/TRIS point at shared or global memory.  SSTACK: the traversal stack is this thread's
+// column of a shared-memory array of 16-bit node codes (entry k at sstack[k * stride]: a warp's accesses fall on
+// consecutive half-words) — the per-lane array it replaces lived in local memory and cost 2.7 M local loads and stores
+// per 2^20 rays; used when the tree is known to be shallow enough and its node codes fit 16 bits.
+template <bool SSTACK>
 __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, const float4 *__restrict__ TRIS,
 											 uint32_t n_nodes, v3 o, v3 d, float tmax, bool need_flag, float &best,
-											 uint32_t &bbody, uint32_t &bface)
+											 uint32_t &bbody, uint32_t &bface, short *sstack, uint32_t stride)
 {
 	if (n_nodes == 0) return;
 	// reciprocal direction with zeros nudged so that slabs never produce 0 * inf
@@ -114,7 +120,7 @@ __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, c
 	// the slab arithmetic only decides which nodes are visited (boxes are padded by BVH_PAD, far more than its rounding),
 	// so it may use fused multiply-adds; the triangle test below is the exact one
 	const float ox = -(o.x * idx), oy = -(o.y * idy), oz = -(o.z * idz);
-	int stack[STACK_DEPTH];
+	int stack[SSTACK ? 1 : STACK_DEPTH];
 	int sp = 0;
 	int node = 0;
 	float limit = fminf(best, tmax);
@@ -140,7 +146,10 @@ __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, c
 			if (h0 && h1)
 			{
 				bool swap = tn1 < tn0;
-				stack[sp++] = swap ? c0 : c1;
+				if (SSTACK)
+					sstack[(uint32_t)(sp++) * stride] = (short)(swap ? c0 : c1);
+				else
+					stack[sp++] = swap ? c0 : c1;
 				node = swap ? c1 : c0;
 				continue;
 			}
@@ -168,7 +177,7 @@ __device__ __forceinline__ void trace_static(const float4 *__restrict__ NODES, c
 			}
 		}
 		if (sp == 0) break;
-		node = stack[--sp];
+		node = SSTACK ? (int)sstack[(uint32_t)(--sp) * stride] : stack[--sp];
 	}
 }
 
@@ -212,12 +221,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 }
 
 // SMEM = tree staged in shared memory (TMA bulk copy); otherwise read through L1/L2.
-template <bool SMEM>
+template <bool SMEM, bool SSTACK>
 __global__ void __launch_bounds__(RAY_THREADS_MAX) k_raycast(RayArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const float4 *NODES = a.nodes;
 	const float4 *TRIS = a.tris;
+	short *sstack = nullptr;
+	if (SSTACK) sstack = reinterpret_cast<short *>(smem_raw + (size_t)a.n_nodes * 64u + (size_t)a.n_tris * 64u) + threadIdx.x;
 	if (SMEM)
 	{
 		float4 *s_nodes = reinterpret_cast<float4 *>(smem_raw);
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(RAY_THREADS_MAX) k_raycast(RayArgs a)
 		const uint32_t world = mask >> 16;
 		float best = 3.0e38f;
 		uint32_t bbody = GPX_INVALID_BODY, bface = GPX_INVALID_FACE;
-		if (layers & 1u) trace_static(NODES, TRIS, a.n_nodes, o, d, tmax, need_flag, best, bbody, bface);
+		if (layers & 1u) trace_static<SSTACK>(NODES, TRIS, a.n_nodes, o, d, tmax, need_flag, best, bbody, bface, sstack, blockDim.x);
 		if (layers & ~1u) trace_bodies(a, world, layers, need_flag, o, d, tmax, best, bbody, bface);
 		float4 h;
 		h.x = bbody == GPX_INVALID_BODY ? RAY_MISS_FRACTION : best / tmax;
@@ -283,6 +294,7 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 {
 	if (n == 0) return GPX_OK;
 	RayArgs a;
+
 	a.nodes = w->sd.ray_nodes;
 	a.tris = w->sd.ray_tri;
 	a.n_nodes = w->sd.n_ray_nodes;
@@ -305,28 +317,39 @@ int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)
 	{
 		// function attributes are per device, and one process may hold worlds on several: remember per device
 		static std::atomic<bool> attr_set[GPX_MAX_DEVICES];
-		if (dev >= 0 && dev < GPX_MAX_DEVICES && !attr_set[dev].load(std::memory_order_acquire))
+		if (dev < 0 || dev >= GPX_MAX_DEVICES || !attr_set[dev].load(std::memory_order_acquire))
 		{
-			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			attr_set[dev].store(true, std::memory_order_release);
+			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+			if (dev >= 0 && dev < GPX_MAX_DEVICES) attr_set[dev].store(true, std::memory_order_release);
 		}
-		else if (dev < 0 || dev >= GPX_MAX_DEVICES)
-			GPX_CUDA(cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		int per_sm = (int)((227u * 1024u) / (tree_bytes + 1024u));
-		if (per_sm < 1) per_sm = 1;
-		if (per_sm > 4) per_sm = 4;
+		// the traversal stack joins the tree in shared memory when the tree is shallow enough (the SAH build knows its depth)
+		// and its node codes fit 16 bits: 64 bytes per thread
+		const bool sstack = w->sd.ray_depth < (uint32_t)SSTACK_DEPTH && a.n_nodes < 32768u && a.n_tris < 32768u;
+		const size_t per_thread = sstack ? sizeof(short) * SSTACK_DEPTH : 0;
+		int per_sm = 4, threads = 256;
 		// about 1024 threads per SM whatever the number of tree copies that fit
-		const int threads = per_sm >= 4 ? 256 : (per_sm == 3 ? 320 : (per_sm == 2 ? 512 : RAY_THREADS_MAX));
+		for (;; per_sm--)
+		{
+			threads = per_sm >= 4 ? 256 : (per_sm == 3 ? 320 : (per_sm == 2 ? 512 : RAY_THREADS_MAX));
+			if (per_sm == 1 || (tree_bytes + per_thread * threads + 1024u) * per_sm <= 227u * 1024u) break;
+		}
+		size_t smem_bytes = tree_bytes + per_thread * threads;
+		const bool use_sstack = sstack && smem_bytes <= 226u * 1024u;
+		if (!use_sstack) smem_bytes = tree_bytes;
 		want = (n + threads - 1) / threads;
 		unsigned long long grid = (unsigned long long)sms * per_sm;
 		if (grid > want) grid = want;
-		k_raycast<true><<<(unsigned)grid, threads, tree_bytes, w->stream>>>(a);
+		if (use_sstack)
+			k_raycast<true, true><<<(unsigned)grid, threads, smem_bytes, w->stream>>>(a);
+		else
+			k_raycast<true, false><<<(unsigned)grid, threads, smem_bytes, w->stream>>>(a);
 	}
 	else
 	{
 		unsigned long long grid = (unsigned long long)sms * 8;
 		if (grid > want) grid = want;
-		k_raycast<false><<<(unsigned)grid, RAY_THREADS, 0, w->stream>>>(a);
+		k_raycast<false, false><<<(unsigned)grid, RAY_THREADS, 0, w->stream>>>(a);
 	}
 	count_launch();
 	GPX_CUDA(cudaGetLastError());
