@@ -225,6 +225,7 @@ def lib() -> C.CDLL:
         "gpx_character_set_position": (i32, [vp, u32, C.POINTER(f32)]),
         "gpx_character_update": (i32, [vp, f32]),
         "gpx_character_get": (i32, [vp, u32, C.POINTER(CharacterState)]),
+        "gpx_character_contacts": (i32, [vp, u32, vp, u32, C.POINTER(C.c_uint32)]),
         "gpx_events_enable": (i32, [vp, i32]),
         "gpx_poll_events": (i32, [vp, vp, u64, C.POINTER(u64)]),
     }
@@ -477,6 +478,13 @@ class World:
         _check(self.L.gpx_character_get(self.h, world, C.byref(s)), "gpx_character_get")
         return (np.array(list(s.position), np.float32), np.array(list(s.linear_velocity), np.float32), s.ground_state,
                 s.ground_body)
+
+    def character_contacts(self, world=0) -> np.ndarray:
+        """Ids the character touches after the last character_update (bodies, then static meshes)."""
+        out = np.zeros(64, np.uint32)
+        n = C.c_uint32()
+        _check(self.L.gpx_character_contacts(self.h, world, out.ctypes.data, 64, C.byref(n)), "gpx_character_contacts")
+        return out[:n.value].copy()
 
     def enable_events(self, on=True):
         _check(self.L.gpx_events_enable(self.h, 1 if on else 0), "gpx_events_enable")

@@ -1,5 +1,6 @@
 // gpx_api.cu — the C ABI of include/gpx.h: world/body management, host mirror, command queue.
 // Host logic only; every compute entry point ends in a kernel launch from the other translation units.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -1259,6 +1260,29 @@ int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out)
 	out->ground_state = c.ground;
 	out->ground_body = c.ground_body;
 	return c.alive ? GPX_OK : GPX_ERR_INVALID_ARG;
+}
+
+int gpx_character_contacts(gpx_world *w, uint32_t world, uint32_t *others, uint32_t capacity, uint32_t *count)
+{
+	if (!w || world >= w->W || !w->d_ch || !count || (capacity && !others)) return GPX_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	unsigned long long keys[CHARACTER_MAX_CONTACTS];
+	uint32_t n = 0;
+	GPX_CUDA(cudaMemcpyAsync(&n, w->d_ch_nkeys + world, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaMemcpyAsync(keys, w->d_ch_keys + (size_t)world * CHARACTER_MAX_CONTACTS, sizeof(keys), cudaMemcpyDeviceToHost,
+							 w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	if (n > CHARACTER_MAX_CONTACTS) n = CHARACTER_MAX_CONTACTS;
+	std::sort(keys, keys + n);
+	n = (uint32_t)(std::unique(keys, keys + n) - keys);
+	for (uint32_t i = 0; i < n && i < capacity; i++)
+	{
+		const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+		others[i] = a == CHARACTER_BODY_ID ? b : a;
+	}
+	*count = n;
+	return GPX_OK;
 }
 
 int gpx_events_enable(gpx_world *w, int enable)

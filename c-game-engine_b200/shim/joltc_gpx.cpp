@@ -4,6 +4,7 @@
 // engine's layer callbacks into bit masks, the character listener dispatch, and the host quaternion helpers.  All
 // simulation and ray work happens in libgpx.so on the device; when no device is usable JPH_Init returns false and
 // JPH_PhysicsSystem_Create returns NULL — there is no CPU path behind these entry points.
+#include <algorithm>
 #include "../../include/joltc_gpx.h"
 #include "../../include/gpx.h"
 
@@ -124,6 +125,7 @@ struct JPH_CharacterVirtual
 	JPH_Quat rotation{0, 0, 0, 1};
 	bool stale = true;  // cached state older than the last update / set
 	gpx_character_state state{};
+	std::vector<uint32_t> touching;  // device ids the character touched after the previous ExtendedUpdate (listener diff)
 };
 
 struct JPH_PhysicsSystem
@@ -389,7 +391,25 @@ static void deliver_character_events(JPH_PhysicsSystem *sys)
 		sys->events.resize(n);
 		gpx_poll_events(sys->w, sys->events.data(), sys->events.size(), &n);
 	}
+	// The character listener's callbacks already ran inside JPH_CharacterVirtual_ExtendedUpdate (character_callbacks
+	// below), where Jolt runs them; the tick's event list, which repeats the character's contacts next to the bodies',
+	// is only drained here.  (The engine registers no body-body ContactListener.)
 	ch->stale = true;
+}
+
+// CharacterContactListener callbacks of one ExtendedUpdate (PlayerPhysics.c:89-152), on the caller's thread and with no
+// lock held — handlers create and destroy bodies (Coin.c:85), and a body destroyed here is gone before the
+// JPH_PhysicsSystem_Update of the same MapFixedUpdate, as with Jolt.  Order: contacts that exist now (added or
+// persisted) by id, bodies before map meshes, then the ones that ended.
+static void character_callbacks(JPH_CharacterVirtual *ch)
+{
+	JPH_PhysicsSystem *sys = ch->sys;
+	uint32_t now[64], n = 0;
+	if (gpx_character_contacts(sys->w, 0, now, 64, &n) != GPX_OK) return;
+	if (n > 64) n = 64;
+	std::vector<uint32_t> before;
+	before.swap(ch->touching);
+	ch->touching.assign(now, now + n);
 	if (!ch->listener) return;
 	const JPH_CharacterContactListener_Impl &cb = ch->listener->impl;
 	gpx_character_state cs;
@@ -397,25 +417,19 @@ static void deliver_character_events(JPH_PhysicsSystem *sys)
 	gpx_character_get(sys->w, 0, &cs);
 	const JPH_RVec3 pos = {cs.position[0], cs.position[1], cs.position[2]};
 	const Vector3 nrm = {cs.ground_normal[0], cs.ground_normal[1], cs.ground_normal[2]};
-	// No lock is held here: handlers create and destroy bodies (Coin.c:85).
-	for (uint64_t i = 0; i < n; i++)
+	auto rank = [](uint32_t id) { return id >= GPX_STATIC_BODY_BASE ? (1ull << 32) | id : (uint64_t)id; };
+	for (uint32_t i = 0; i < n; i++)
 	{
-		const gpx_contact_event &e = sys->events[i];
-		JPH_BodyID other;
-		if (e.body_a == GPX_CHARACTER_BODY) other = e.body_b;
-		else if (e.body_b == GPX_CHARACTER_BODY) other = e.body_a;
-		else continue;
-		other = sys->to_public(other);
-		if (e.kind == GPX_EVENT_REMOVED)
-		{
-			if (cb.OnContactRemoved) cb.OnContactRemoved(ch, other, 0);
-			continue;
-		}
+		const bool was = std::find(before.begin(), before.end(), now[i]) != before.end();
+		const JPH_BodyID other = sys->to_public(now[i]);
 		if (cb.OnContactValidate && !cb.OnContactValidate(ch, other, 0)) continue;
 		JPH_CharacterContactSettings io = {true, true};
-		if (e.kind == GPX_EVENT_ADDED && cb.OnContactAdded) cb.OnContactAdded(ch, other, 0, &pos, &nrm, &io);
-		if (e.kind == GPX_EVENT_PERSISTED && cb.OnContactPersisted) cb.OnContactPersisted(ch, other, 0, &pos, &nrm, &io);
+		if (!was && cb.OnContactAdded) cb.OnContactAdded(ch, other, 0, &pos, &nrm, &io);
+		if (was && cb.OnContactPersisted) cb.OnContactPersisted(ch, other, 0, &pos, &nrm, &io);
 	}
+	std::sort(before.begin(), before.end(), [&](uint32_t a, uint32_t b) { return rank(a) < rank(b); });
+	for (uint32_t id : before)
+		if (std::find(now, now + n, id) == now + n && cb.OnContactRemoved) cb.OnContactRemoved(ch, sys->to_public(id), 0);
 }
 
 JPH_PhysicsUpdateError JPH_PhysicsSystem_Update(JPH_PhysicsSystem *sys, float dt, int collisionSteps, JPH_JobSystem *)
@@ -1137,6 +1151,7 @@ void JPH_CharacterVirtual_ExtendedUpdate(JPH_CharacterVirtual *ch, float dt, con
 	if (!ch || !ch->sys) return;
 	if (gpx_character_update(ch->sys->w, dt) != GPX_OK) fprintf(stderr, "joltc_gpx: character update failed: %s\n", gpx_last_error());
 	ch->stale = true;
+	character_callbacks(ch);
 }
 JPH_CharacterContactListener *JPH_CharacterContactListener_Create(const JPH_CharacterContactListener_Impl *impl)
 {

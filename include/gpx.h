@@ -290,6 +290,8 @@ uint64_t gpx_thread_last_tick_ns(void); /* what TickGraphUpdate is fed (PhysicsT
  * body of the world; one per world instance.  Its contacts are reported by gpx_poll_events with the pseudo body id
  * GPX_CHARACTER_BODY (the CharacterContactListener callbacks, PlayerPhysics.c:89-152). */
 #define GPX_CHARACTER_BODY 0x3FFFFFu
+/* ids at or above this name the static collision meshes, in the order they were added */
+#define GPX_STATIC_BODY_BASE 0x400000u
 enum gpx_ground_state /* JPH_GroundState */
 {
 	GPX_GROUND_ON_GROUND = 0,
@@ -326,6 +328,12 @@ int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3]);
 int gpx_character_update(gpx_world *w, float dt);
 /* Waits for the stream and reads the character back. */
 int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out);
+/* What the character touches after the last gpx_character_update: body ids first (ascending), then static meshes
+ * (GPX_STATIC_BODY_BASE + k, ascending), sensors included — the order in which the tick's contact events list them.
+ * Waits for the stream.  This is what lets a host deliver the CharacterContactListener callbacks of
+ * PlayerPhysics.c:89-152 from inside its ExtendedUpdate, as Jolt does, instead of after the next gpx_step.  *count gets
+ * the number of contacts even when it exceeds `capacity`. */
+int gpx_character_contacts(gpx_world *w, uint32_t world, uint32_t *others, uint32_t capacity, uint32_t *count);
 
 /* ---- contact events ------------------------------------------------------------------------------------------------ */
 

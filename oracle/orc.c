@@ -2106,6 +2106,23 @@ void orc_character_create(orc_world *w, const float pos[3], float half_height, f
 	w->ch_nkeys = 0;
 }
 void orc_character_destroy(orc_world *w) { w->ch_alive = 0; w->ch_nkeys = 0; }
+
+uint32_t orc_character_contacts(const orc_world *w, uint32_t *others, uint32_t cap)
+{
+	uint64_t keys[64];
+	uint32_t n = w->ch_nkeys;
+	memcpy(keys, w->ch_keys, sizeof(uint64_t) * n);
+	qsort(keys, n, sizeof(uint64_t), cmp_u64);
+	uint32_t m = 0;
+	for (uint32_t i = 0; i < n; i++)
+		if (i == 0 || keys[i] != keys[i - 1])
+		{
+			const uint32_t a = (uint32_t)(keys[i] >> 32), b = (uint32_t)(keys[i] & 0xFFFFFFFFu);
+			if (m < cap) others[m] = a == CH_ID ? b : a;
+			m++;
+		}
+	return m;
+}
 void orc_character_set_velocity(orc_world *w, const float v[3]) { w->ch_v = V(v[0], v[1], v[2]); }
 void orc_character_set_position(orc_world *w, const float p[3]) { w->ch_x = V(p[0], p[1], p[2]); }
 void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body)

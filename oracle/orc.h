@@ -100,6 +100,8 @@ void orc_character_update(orc_world *w, float dt);
 float orc_overlap_capsule(const orc_world *w, const float center[3], float half_height, float radius, float normal[3],
 						  uint32_t *body);
 void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body);
+/* ids the character touches after the last orc_character_update: bodies ascending, then static meshes ascending */
+uint32_t orc_character_contacts(const orc_world *w, uint32_t *others, uint32_t cap);
 /* closest-hit rays, brute force over every static triangle and every body */
 void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);
 uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_body, uint32_t cap);

@@ -124,6 +124,8 @@ def lib():
     L.orc_character_set_position.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.orc_character_update.argtypes = [C.c_void_p, C.c_float]
     L.orc_character_get.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.orc_character_contacts.restype = C.c_uint32
+    L.orc_character_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.orc_events.restype = C.c_uint32
     L.orc_events.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.orc_manifold_count.restype = C.c_uint32
@@ -233,6 +235,11 @@ class World:
         g, gb = C.c_uint32(), C.c_uint32()
         self.L.orc_character_get(self.h, p, v, C.byref(g), C.byref(gb))
         return np.array(list(p), np.float32), np.array(list(v), np.float32), g.value, gb.value
+
+    def character_contacts(self) -> np.ndarray:
+        out = np.zeros(64, np.uint32)
+        n = self.L.orc_character_contacts(self.h, out.ctypes.data, 64)
+        return out[:n].copy()
 
     def events(self) -> np.ndarray:
         """(n, 3) triples a, b, kind of the last tick."""

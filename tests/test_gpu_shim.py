@@ -67,6 +67,7 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
     names = {b: "prop_physbox" for b in box_ids}
     names.update({coin: "prop_coin", door: "prop_door", lasers[0]: "laser", lasers[1]: "laser3"})
     coin_alive = True
+    touching = []
     g_step = np.float32(np.float64(np.float32(-9.81)) * (1.0 / 60.0))
 
     def ray(origin, direction, tmax, mask):
@@ -95,6 +96,21 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
                        f"{int(h['face']) if hit else 0:08x}")
         o.character_update()
         pos = o.character_get()[0]
+        # the listener's callbacks run inside ExtendedUpdate: contacts that exist now (added / persisted) by id, bodies
+        # before map meshes, then the ones that ended; the coin's handler removes it before this tick's Update
+        now = [int(x) for x in o.character_contacts()]
+        for other in now:
+            if other in touching:
+                out.append(f"E {tick} persisted {other:08x}")
+            else:
+                out.append(f"E {tick} added {other:08x} {names.get(other, '-')}")
+                if other == coin and coin_alive:
+                    o.destroy(coin)
+                    coin_alive = False
+        for other in sorted(touching, key=lambda i: (i >= 0x400000, i)):
+            if other not in now:
+                out.append(f"E {tick} removed {other:08x}")
+        touching = now
         if tick == 60:
             o.set_velocity(door, (0.0, 0.0, 1.0))
         if tick == 120:
@@ -110,19 +126,6 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
                 out.append(f"R {tick} {'laser' if i == 0 else 'laser3'} {hit} {int(h['body']) if hit else 0:08x} "
                            f"{bits(h['fraction']) if hit else bits(0.0)} {int(h['face']) if hit else 0:08x} {bits(off) if hit else bits(0.0)}")
         assert o.step() == 0
-        for a, b, kind in o.events():
-            if a != CHAR and b != CHAR:
-                continue
-            other = int(b if a == CHAR else a)
-            if kind == 3:
-                out.append(f"E {tick} removed {other:08x}")
-            elif kind == 1:
-                out.append(f"E {tick} added {other:08x} {names.get(other, '-')}")
-                if other == coin and coin_alive:
-                    o.destroy(coin)
-                    coin_alive = False
-            else:
-                out.append(f"E {tick} persisted {other:08x}")
         if tick % 20 == 0 or tick == ticks:
             for b in box_ids + [door]:
                 xf, _ = o.get(b)
