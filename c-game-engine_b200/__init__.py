@@ -224,6 +224,7 @@ def lib() -> C.CDLL:
         "gpx_character_set_linear_velocity": (i32, [vp, u32, C.POINTER(f32)]),
         "gpx_character_set_position": (i32, [vp, u32, C.POINTER(f32)]),
         "gpx_character_update": (i32, [vp, f32]),
+        "gpx_character_update_ex": (i32, [vp, f32, C.POINTER(C.c_float * 5)]),
         "gpx_character_get": (i32, [vp, u32, C.POINTER(CharacterState)]),
         "gpx_character_contacts": (i32, [vp, u32, vp, u32, C.POINTER(C.c_uint32)]),
         "gpx_events_enable": (i32, [vp, i32]),
@@ -470,8 +471,13 @@ class World:
     def character_set_position(self, p, world=0):
         _check(self.L.gpx_character_set_position(self.h, world, (C.c_float * 3)(*p)), "gpx_character_set_position")
 
-    def character_update(self, dt=1.0 / 60.0):
-        _check(self.L.gpx_character_update(self.h, dt), "gpx_character_update")
+    def character_update(self, dt=1.0 / 60.0, settings=None):
+        """settings: JPH_ExtendedUpdateSettings as (stick_to_floor_step_down, walk_stairs_step_up, min_step_forward,
+        step_forward_test, cos_angle_forward_contact); None = plain update."""
+        if settings is None:
+            _check(self.L.gpx_character_update(self.h, dt), "gpx_character_update")
+        else:
+            _check(self.L.gpx_character_update_ex(self.h, dt, C.byref((C.c_float * 5)(*settings))), "gpx_character_update_ex")
 
     def character_get(self, world=0):
         s = CharacterState()

@@ -1235,7 +1235,9 @@ int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3])
 	return char_upload(w, world);
 }
 
-int gpx_character_update(gpx_world *w, float dt)
+int gpx_character_update(gpx_world *w, float dt) { return gpx_character_update_ex(w, dt, nullptr); }
+
+int gpx_character_update_ex(gpx_world *w, float dt, const gpx_character_update_settings *settings)
 {
 	if (!w || !w->d_ch || !(dt > 0.0f)) return GPX_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(w->mu);
@@ -1243,7 +1245,7 @@ int gpx_character_update(gpx_world *w, float dt)
 	int rc;
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
-	return launch_character(w, dt);
+	return launch_character(w, dt, settings);
 }
 
 int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out)

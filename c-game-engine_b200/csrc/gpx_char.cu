@@ -8,6 +8,7 @@
 // segment-vs-shape closest points, and a shuffle reduction picks the deepest penetration (ties: lowest id) — up to
 // eight push-outs per update, then the ground probe / stick-to-floor step and the contact list that the tick's event
 // pass merges with the body contacts.
+#include <cstring>
 #include "gpx_solver.cuh"
 
 namespace gpx {
@@ -196,6 +197,7 @@ struct CharArgs
 	uint32_t worlds, cap;
 	uint32_t *err;
 	float dt;
+	gpx_character_update_settings cfg;  // JPH_ExtendedUpdateSettings; all zero = plain update
 };
 
 struct Deepest
@@ -357,6 +359,76 @@ __device__ __forceinline__ void ch_push_body(const CharArgs &a, uint32_t g, v3 n
 	}
 }
 
+// One collide-and-slide pass (warp-cooperative; every lane carries the same state): up to CH_MAX_ITERS times find the
+// deepest penetration, push the capsule out along that normal and remove the velocity component into it; ground state from
+// the contact normals.  `push`: dynamic bodies in the way get the character's contact impulse.  `blocked`: some contact
+// too steep to walk on faces the motion direction `dir` within the angle whose cosine is cos_fwd.
+struct Slide
+{
+	v3 x, v, ground_n;
+	uint32_t ground, ground_body;
+	bool blocked;
+};
+
+__device__ __forceinline__ Slide ch_slide(const CharArgs &a, uint32_t world, const CharDev &ch, v3 x, v3 v, bool push, v3 dir, float cos_fwd,
+										  int *cand_orig, int *cand_leaf, int *s_nc, uint32_t &err, int lane)
+{
+	Slide s;
+	s.ground = 3u;
+	s.ground_body = GPX_INVALID_BODY;
+	s.ground_n = V(0.0f, 1.0f, 0.0f);
+	s.blocked = false;
+	for (int it = 0; it < CH_MAX_ITERS; it++)
+	{
+		const Deepest d = ch_deepest(a, world, x, ch.hh, ch.r, cand_orig, cand_leaf, s_nc, err);
+		if (!(d.pen > 0.0f)) break;
+		if (push && d.body < STATIC_BODY_BASE)
+		{
+			ch_push_body(a, world * a.cap + d.body, d.n, d.pen, d.cp, v, a.dt, lane);
+			__syncwarp();  // the next round reads the body's new velocity
+		}
+		x = x + (d.n * d.pen);
+		const float vn = dot(v, d.n);
+		if (vn < 0.0f) v = v - (d.n * vn);
+		if (d.n.y >= ch.cos_slope)
+		{
+			s.ground = 0u;
+			s.ground_body = d.body;
+			s.ground_n = d.n;
+		}
+		else
+		{
+			if (d.n.y > 0.0f && s.ground != 0u)
+			{
+				s.ground = 1u;
+				s.ground_body = d.body;
+				s.ground_n = d.n;
+			}
+			// too steep to walk on: does it face the motion?
+			const float hl = sqrtf((d.n.x * d.n.x) + (d.n.z * d.n.z));
+			if (hl > 1.0e-6f && (-((d.n.x * dir.x) + (d.n.z * dir.z))) >= (cos_fwd * hl)) s.blocked = true;
+		}
+	}
+	s.x = x;
+	s.v = v;
+	return s;
+}
+
+// Floor below x within `reach`, by probes 5 cm apart: the first probe depth at which the capsule touches something that
+// faces up (0: nothing); `d` = what was found there.
+__device__ __forceinline__ float ch_probe_down(const CharArgs &a, uint32_t world, const CharDev &ch, v3 x, float reach, Deepest &d,
+											   int *cand_orig, int *cand_leaf, int *s_nc, uint32_t &err)
+{
+	for (float s = CH_GROUND_PROBE; s <= reach + 1.0e-6f; s += CH_GROUND_PROBE)
+	{
+		d = ch_deepest(a, world, V(x.x, x.y - s, x.z), ch.hh, ch.r, cand_orig, cand_leaf, s_nc, err);
+		if (d.pen > 0.0f && d.n.y > 0.0f) return s;
+	}
+	return 0.0f;
+}
+
+// JPH_CharacterVirtual_ExtendedUpdate as the engine calls it (PlayerPhysics.c:439-453), restated on the discrete
+// collide-and-slide: the move, then stick-to-floor, then walk-stairs.
 __global__ void __launch_bounds__(128) k_character(CharArgs a)
 {
 	__shared__ int s_orig[4][MAX_TRI_CANDIDATES], s_leaf[4][MAX_TRI_CANDIDATES], s_nc[4];
@@ -368,45 +440,79 @@ __global__ void __launch_bounds__(128) k_character(CharArgs a)
 	if (!ch.alive) return;
 	uint32_t err = 0;
 	const float hh = ch.hh, r = ch.r;
-	v3 v = V(ch.vx, ch.vy, ch.vz);
-	v3 x = V(ch.px, ch.py, ch.pz) + (v * a.dt);
-	uint32_t ground = 3u, ground_body = GPX_INVALID_BODY;
-	v3 ground_n = V(0.0f, 1.0f, 0.0f);
-	for (int it = 0; it < CH_MAX_ITERS; it++)
-	{
-		const Deepest d = ch_deepest(a, world, x, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
-		if (!(d.pen > 0.0f)) break;
-		if (d.body < STATIC_BODY_BASE)
-		{
-			ch_push_body(a, world * a.cap + d.body, d.n, d.pen, d.cp, v, a.dt, lane);
-			__syncwarp();  // the next round reads the body's new velocity
-		}
-		x = x + (d.n * d.pen);
-		const float vn = dot(v, d.n);
-		if (vn < 0.0f) v = v - (d.n * vn);
-		if (d.n.y >= ch.cos_slope)
-		{
-			ground = 0u;
-			ground_body = d.body;
-			ground_n = d.n;
-		}
-		else if (d.n.y > 0.0f && ground != 0u)
-		{
-			ground = 1u;
-			ground_body = d.body;
-			ground_n = d.n;
-		}
-	}
+	const gpx_character_update_settings &cfg = a.cfg;
+	const v3 x_old = V(ch.px, ch.py, ch.pz), v_in = V(ch.vx, ch.vy, ch.vz);
+	const bool was_on_ground = ch.ground == 0u || ch.ground == 1u;  // Jolt's IsSupported(): on ground or on steep ground
+	// what the host asked for, horizontally
+	const v3 want = V(v_in.x * a.dt, 0.0f, v_in.z * a.dt);
+	const float want_len = sqrtf((want.x * want.x) + (want.z * want.z));
+	const v3 dir = want_len > 0.0f ? V(want.x / want_len, 0.0f, want.z / want_len) : V(0.0f, 0.0f, 0.0f);
+	const Slide m = ch_slide(a, world, ch, x_old + (v_in * a.dt), v_in, true, dir, cfg.walk_stairs_cos_angle_forward_contact, s_orig[wib],
+							 s_leaf[wib], &s_nc[wib], err, lane);
+	v3 x = m.x, v = m.v;
+	uint32_t ground = m.ground, ground_body = m.ground_body;
+	v3 ground_n = m.ground_n;
 	if (ground == 3u)
 	{
-		const Deepest d = ch_deepest(a, world, V(x.x, x.y - CH_GROUND_PROBE, x.z), hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
-		if (d.pen > 0.0f && d.n.y > 0.0f)
+		// ground within 5 cm counts as ground; beyond that only stick-to-floor reaches, and only from a standing start
+		const float reach = (was_on_ground && v.y <= 0.0f && cfg.stick_to_floor_step_down > CH_GROUND_PROBE) ? cfg.stick_to_floor_step_down
+																										   : CH_GROUND_PROBE;
+		Deepest d;
+		const float s = ch_probe_down(a, world, ch, x, reach, d, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+		if (s > 0.0f)
 		{
 			ground = d.n.y >= ch.cos_slope ? 0u : 1u;
 			ground_body = d.body;
 			ground_n = d.n;
 			// stick to the floor: close the gap over walkable ground when not moving up
-			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, CH_GROUND_PROBE - d.pen);
+			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, s - d.pen);
+		}
+	}
+	if (cfg.walk_stairs_step_up > 0.0f && want_len > 0.0f && (ground == 0u || ground == 1u || was_on_ground) && m.blocked)
+	{
+		const v3 got = x - x_old;
+		const float got_len = fmaxf(0.0f, (got.x * dir.x) + (got.z * dir.z));
+		if ((got_len + 1.0e-4f) < want_len)
+		{
+			const float fwd = fmaxf(cfg.walk_stairs_min_step_forward, want_len - got_len);
+			const v3 up = V(x.x, x.y + cfg.walk_stairs_step_up, x.z);
+			const Deepest head = ch_deepest(a, world, up, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+			if (!(head.pen > 0.0f))  // head room
+			{
+				const Slide f = ch_slide(a, world, ch, V(up.x + (dir.x * fwd), up.y, up.z + (dir.z * fwd)), v, false, dir, 2.0f, s_orig[wib],
+										 s_leaf[wib], &s_nc[wib], err, lane);
+				const v3 adv = f.x - up;
+				// headway, and on the level: a push-out that lifted the capsule means the step is higher than step_up
+				if (((adv.x * dir.x) + (adv.z * dir.z)) > 1.0e-4f && fabsf(adv.y) <= 1.0e-3f)
+				{
+					Deepest d;
+					const float s = ch_probe_down(a, world, ch, f.x, cfg.walk_stairs_step_up + CH_GROUND_PROBE, d, s_orig[wib], s_leaf[wib],
+												  &s_nc[wib], err);
+					bool ok = s > 0.0f && d.n.y >= ch.cos_slope;
+					if (s > 0.0f && !ok && cfg.walk_stairs_step_forward_test > 0.0f)
+					{
+						// landed on the edge of the step: is there walkable floor a little further on?
+						const float t = cfg.walk_stairs_step_forward_test;
+						const v3 ahead = V(up.x + (dir.x * t), up.y, up.z + (dir.z * t));
+						// (the lifted capsule must fit there: a step higher than step_up is in the way)
+						const Deepest fit = ch_deepest(a, world, ahead, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
+						if (!(fit.pen > 0.0f))
+						{
+							Deepest d2;
+							const float s2 = ch_probe_down(a, world, ch, ahead, cfg.walk_stairs_step_up + CH_GROUND_PROBE, d2, s_orig[wib],
+														   s_leaf[wib], &s_nc[wib], err);
+							ok = s2 > 0.0f && d2.n.y >= ch.cos_slope;
+						}
+					}
+					if (ok)
+					{
+						x = V(f.x.x, f.x.y - fmaxf(0.0f, s - d.pen), f.x.z);
+						ground = d.n.y >= ch.cos_slope ? 0u : 1u;
+						ground_body = d.body;
+						ground_n = d.n;
+					}
+				}
+			}
 		}
 	}
 	// ---- contacts for the callbacks: bodies (sensors included) and static meshes within the contact margin
@@ -531,15 +637,18 @@ int launch_overlap_capsules(gpx_world *w, const void *d_queries, uint64_t n, voi
 	a.cap = w->cap;
 	a.err = w->d_err;
 	a.dt = 0.0f;
+	memset(&a.cfg, 0, sizeof(a.cfg));
 	k_overlap_capsules<<<(unsigned)((n + 3) / 4), 128, 0, w->stream>>>(a, (const float4 *)d_queries, n, (float4 *)d_out);
 	count_launch();
 	GPX_CUDA(cudaGetLastError());
 	return GPX_OK;
 }
 
-int launch_character(gpx_world *w, float dt)
+int launch_character(gpx_world *w, float dt, const gpx_character_update_settings *cfg)
 {
 	CharArgs a;
+	memset(&a.cfg, 0, sizeof(a.cfg));
+	if (cfg) a.cfg = *cfg;
 	a.ch = w->d_ch;
 	a.keys = w->d_ch_keys;
 	a.nkeys = w->d_ch_nkeys;

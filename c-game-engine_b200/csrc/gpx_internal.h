@@ -202,7 +202,7 @@ int wide_counters(gpx_world *w, uint32_t *out8);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 // gpx_char.cu
-int launch_character(gpx_world *w, float dt);
+int launch_character(gpx_world *w, float dt, const gpx_character_update_settings *cfg);
 int launch_overlap_capsules(gpx_world *w, const void *d_queries, uint64_t n, void *d_out);
 // gpx_tick.cu
 int launch_tick(gpx_world *w, float dt, int substeps);

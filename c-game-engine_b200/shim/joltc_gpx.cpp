@@ -1145,11 +1145,22 @@ JPH_GroundState JPH_CharacterBase_GetGroundState(const JPH_CharacterBase *ch)
 	const gpx_character_state *s = character_state(ch);
 	return s ? (JPH_GroundState)s->ground_state : JPH_GroundState_InAir;
 }
-void JPH_CharacterVirtual_ExtendedUpdate(JPH_CharacterVirtual *ch, float dt, const JPH_ExtendedUpdateSettings *, JPH_ObjectLayer,
+void JPH_CharacterVirtual_ExtendedUpdate(JPH_CharacterVirtual *ch, float dt, const JPH_ExtendedUpdateSettings *es, JPH_ObjectLayer,
 										 const JPH_PhysicsSystem *, const JPH_BodyFilter *, const JPH_ShapeFilter *)
 {
 	if (!ch || !ch->sys) return;
-	if (gpx_character_update(ch->sys->w, dt) != GPX_OK) fprintf(stderr, "joltc_gpx: character update failed: %s\n", gpx_last_error());
+	// the step vectors are vertical in the engine (PlayerPhysics.c:440-441): down is -y, up is +y
+	gpx_character_update_settings cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	if (es)
+	{
+		cfg.stick_to_floor_step_down = es->stickToFloorStepDown.y < 0.0f ? -es->stickToFloorStepDown.y : 0.0f;
+		cfg.walk_stairs_step_up = es->walkStairsStepUp.y > 0.0f ? es->walkStairsStepUp.y : 0.0f;
+		cfg.walk_stairs_min_step_forward = es->walkStairsMinStepForward;
+		cfg.walk_stairs_step_forward_test = es->walkStairsStepForwardTest;
+		cfg.walk_stairs_cos_angle_forward_contact = es->walkStairsCosAngleForwardContact;
+	}
+	if (gpx_character_update_ex(ch->sys->w, dt, &cfg) != GPX_OK) fprintf(stderr, "joltc_gpx: character update failed: %s\n", gpx_last_error());
 	ch->stale = true;
 	character_callbacks(ch);
 }

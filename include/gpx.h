@@ -326,6 +326,22 @@ int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3]);
  * floor.  Call before gpx_step, as
  * MapFixedUpdate does (MapPhysics.c:74 then :105).  Asynchronous on the world's stream. */
 int gpx_character_update(gpx_world *w, float dt);
+/* The same with JPH_ExtendedUpdateSettings as the engine fills it (PlayerPhysics.c:439-446): after the move, a character
+ * that stood on walkable ground and is now in the air without moving up is set down on a floor found within
+ * stick_to_floor_step_down; a character on the ground whose horizontal move was cut short by something too steep that
+ * faces the motion (within the angle of walk_stairs_cos_angle_forward_contact) tries the rest of the move lifted by
+ * walk_stairs_step_up — at least walk_stairs_min_step_forward — and stands on walkable floor found within the step height
+ * below; if it lands on the edge of the step, walkable floor walk_stairs_step_forward_test further on decides.  All zero
+ * = gpx_character_update. */
+typedef struct gpx_character_update_settings
+{
+	float stick_to_floor_step_down;              /* 0.25 */
+	float walk_stairs_step_up;                   /* 0.25 */
+	float walk_stairs_min_step_forward;          /* 0.02 */
+	float walk_stairs_step_forward_test;         /* 0.15 */
+	float walk_stairs_cos_angle_forward_contact; /* cos 75 deg */
+} gpx_character_update_settings;
+int gpx_character_update_ex(gpx_world *w, float dt, const gpx_character_update_settings *settings);
 /* Waits for the stream and reads the character back. */
 int gpx_character_get(gpx_world *w, uint32_t world, gpx_character_state *out);
 /* What the character touches after the last gpx_character_update: body ids first (ascending), then static meshes

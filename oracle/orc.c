@@ -2254,49 +2254,161 @@ float orc_overlap_capsule(const orc_world *w, const float center[3], float half_
 	return pen;
 }
 
-void orc_character_update(orc_world *w, float dt)
+/* One collide-and-slide pass: up to CH_MAX_ITERS times find the deepest penetration, push the capsule out along that
+ * normal and remove the velocity component into it; ground state from the contact normals.  `push`: dynamic bodies in
+ * the way get the character's contact impulse.  `blocked` reports a contact too steep to walk on that faces the motion
+ * direction `dir` (unit, horizontal) within the angle whose cosine is cos_fwd — what lets ExtendedUpdate try a stair
+ * step. */
+typedef struct { v3 x, v, ground_n; uint32_t ground, ground_body; int blocked; } slide_t;
+
+static slide_t ch_slide(orc_world *w, v3 x, v3 v, float dt, int push, v3 dir, float cos_fwd)
 {
-	if (!w->ch_alive) return;
-	v3 x = vadd(w->ch_x, vscale(w->ch_v, dt));
-	v3 v = w->ch_v;
-	uint32_t ground = 3, ground_body = ORC_INVALID;
-	v3 ground_n = V(0, 1, 0);
+	slide_t s;
+	s.ground = 3;
+	s.ground_body = ORC_INVALID;
+	s.ground_n = V(0, 1, 0);
+	s.blocked = 0;
 	for (int it = 0; it < CH_MAX_ITERS; it++)
 	{
 		v3 n, cp;
 		uint32_t hb;
 		float pen = capsule_deepest(w, x, w->ch_hh, w->ch_r, &n, &hb, &cp);
 		if (!(pen > 0.0f)) break;
-		if (hb < ORC_STATIC_BODY_BASE) ch_push_body(&w->bodies[hb], n, pen, cp, v, dt);
+		if (push && hb < ORC_STATIC_BODY_BASE) ch_push_body(&w->bodies[hb], n, pen, cp, v, dt);
 		x = vadd(x, vscale(n, pen));
 		float vn = vdot(v, n);
 		if (vn < 0.0f) v = vsub(v, vscale(n, vn));
 		if (n.y >= w->ch_cos_slope)
 		{
-			ground = 0;
-			ground_body = hb;
-			ground_n = n;
+			s.ground = 0;
+			s.ground_body = hb;
+			s.ground_n = n;
 		}
-		else if (n.y > 0.0f && ground != 0)
+		else
 		{
-			ground = 1;
-			ground_body = hb;
-			ground_n = n;
+			if (n.y > 0.0f && s.ground != 0)
+			{
+				s.ground = 1;
+				s.ground_body = hb;
+				s.ground_n = n;
+			}
+			/* too steep to walk on: does it face the motion? */
+			const float hl = sqrtf((n.x * n.x) + (n.z * n.z));
+			if (hl > 1.0e-6f && (-((n.x * dir.x) + (n.z * dir.z))) >= (cos_fwd * hl)) s.blocked = 1;
 		}
 	}
-	if (ground == 3)
+	s.x = x;
+	s.v = v;
+	return s;
+}
+
+/* Floor below x within `reach`, by probes 5 cm apart: the first probe depth at which the capsule touches something that
+ * faces up.  Returns that depth (0: nothing), the penetration found there, its normal and body. */
+static float ch_probe_down(const orc_world *w, v3 x, float reach, float *pen_out, v3 *n_out, uint32_t *hb_out)
+{
+	for (float s = CH_GROUND_PROBE; s <= reach + 1.0e-6f; s += CH_GROUND_PROBE)
 	{
 		v3 n;
 		uint32_t hb;
-		float pen = ch_deepest(w, V(x.x, x.y - CH_GROUND_PROBE, x.z), &n, &hb);
+		float pen = ch_deepest(w, V(x.x, x.y - s, x.z), &n, &hb);
 		if (pen > 0.0f && n.y > 0.0f)
+		{
+			*pen_out = pen;
+			*n_out = n;
+			*hb_out = hb;
+			return s;
+		}
+	}
+	return 0.0f;
+}
+
+void orc_character_update(orc_world *w, float dt)
+{
+	const orc_character_settings none = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+	orc_character_update_ex(w, dt, &none);
+}
+
+/* JPH_CharacterVirtual_ExtendedUpdate as the engine calls it (PlayerPhysics.c:439-453), restated on the discrete
+ * collide-and-slide: the move, then stick-to-floor (a character that stood on walkable ground and is now in the air without
+ * moving up is set down on a floor found within stick_to_floor_step_down), then walk-stairs (a character on the ground
+ * whose horizontal move was cut short by something too steep tries the same move lifted by walk_stairs_step_up and, if
+ * that makes headway and there is walkable floor within the step height below, stands there). */
+void orc_character_update_ex(orc_world *w, float dt, const orc_character_settings *cfg)
+{
+	if (!w->ch_alive) return;
+	const v3 x_old = w->ch_x;
+	const int was_on_ground = w->ch_ground == 0 || w->ch_ground == 1; /* Jolt's IsSupported(): on ground or on steep ground */
+	/* what the host asked for, horizontally */
+	const v3 want = V(w->ch_v.x * dt, 0.0f, w->ch_v.z * dt);
+	const float want_len = sqrtf((want.x * want.x) + (want.z * want.z));
+	const v3 dir = want_len > 0.0f ? V(want.x / want_len, 0.0f, want.z / want_len) : V(0, 0, 0);
+	slide_t m = ch_slide(w, vadd(w->ch_x, vscale(w->ch_v, dt)), w->ch_v, dt, 1, dir, cfg->walk_stairs_cos_angle_forward_contact);
+	v3 x = m.x, v = m.v;
+	uint32_t ground = m.ground, ground_body = m.ground_body;
+	v3 ground_n = m.ground_n;
+	if (ground == 3)
+	{
+		/* ground within 5 cm counts as ground; beyond that only stick-to-floor reaches, and only from a standing start */
+		const float reach = (was_on_ground && v.y <= 0.0f && cfg->stick_to_floor_step_down > CH_GROUND_PROBE)
+								? cfg->stick_to_floor_step_down : CH_GROUND_PROBE;
+		v3 n;
+		uint32_t hb;
+		float pen;
+		const float s = ch_probe_down(w, x, reach, &pen, &n, &hb);
+		if (s > 0.0f)
 		{
 			ground = n.y >= w->ch_cos_slope ? 0u : 1u;
 			ground_body = hb;
 			ground_n = n;
 			/* stick to the floor (the stickToFloorStepDown of ExtendedUpdate, PlayerPhysics.c:439-446): close the gap
 			 * when standing on walkable ground and not moving up */
-			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, CH_GROUND_PROBE - pen);
+			if (ground == 0u && v.y <= 0.0f) x.y = x.y - fmaxf(0.0f, s - pen);
+		}
+	}
+	if (cfg->walk_stairs_step_up > 0.0f && want_len > 0.0f && (ground == 0u || ground == 1u || was_on_ground) && m.blocked)
+	{
+		const v3 got = vsub(x, x_old);
+		const float got_len = fmaxf(0.0f, (got.x * dir.x) + (got.z * dir.z));
+		if ((got_len + 1.0e-4f) < want_len)
+		{
+			const float fwd = fmaxf(cfg->walk_stairs_min_step_forward, want_len - got_len);
+			const v3 up = V(x.x, x.y + cfg->walk_stairs_step_up, x.z);
+			v3 n;
+			uint32_t hb;
+			if (!(ch_deepest(w, up, &n, &hb) > 0.0f)) /* head room */
+			{
+				const slide_t f = ch_slide(w, V(up.x + (dir.x * fwd), up.y, up.z + (dir.z * fwd)), v, dt, 0, dir, 2.0f);
+				const v3 adv = vsub(f.x, up);
+				/* headway, and on the level: a push-out that lifted the capsule means the step is higher than step_up */
+				if (((adv.x * dir.x) + (adv.z * dir.z)) > 1.0e-4f && fabsf(adv.y) <= 1.0e-3f)
+				{
+					float pen;
+					const float s = ch_probe_down(w, f.x, cfg->walk_stairs_step_up + CH_GROUND_PROBE, &pen, &n, &hb);
+					int ok = s > 0.0f && n.y >= w->ch_cos_slope;
+					if (s > 0.0f && !ok && cfg->walk_stairs_step_forward_test > 0.0f)
+					{
+						/* landed on the edge of the step: is there walkable floor a little further on? */
+						const float t = cfg->walk_stairs_step_forward_test;
+						v3 n2;
+						uint32_t hb2;
+						float pen2;
+						const v3 ahead = V(up.x + (dir.x * t), up.y, up.z + (dir.z * t));
+						/* (the lifted capsule must fit there: a step higher than step_up is in the way) */
+						if (!(ch_deepest(w, ahead, &n2, &hb2) > 0.0f))
+						{
+							const float s2 = ch_probe_down(w, ahead, cfg->walk_stairs_step_up + CH_GROUND_PROBE, &pen2, &n2, &hb2);
+							ok = s2 > 0.0f && n2.y >= w->ch_cos_slope;
+						}
+					}
+					if (ok)
+					{
+						x = V(f.x.x, f.x.y - fmaxf(0.0f, s - pen), f.x.z);
+						ground = n.y >= w->ch_cos_slope ? 0u : 1u;
+						ground_body = hb;
+						ground_n = n;
+					}
+				}
+			}
 		}
 	}
 	w->ch_x = x;

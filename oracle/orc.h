@@ -97,6 +97,16 @@ void orc_character_destroy(orc_world *w);
 void orc_character_set_velocity(orc_world *w, const float v[3]);
 void orc_character_set_position(orc_world *w, const float p[3]);
 void orc_character_update(orc_world *w, float dt);
+/* JPH_ExtendedUpdateSettings as the engine fills it (PlayerPhysics.c:439-446); all zero = plain update */
+typedef struct
+{
+	float stick_to_floor_step_down;  /* 0.25 */
+	float walk_stairs_step_up;       /* 0.25 */
+	float walk_stairs_min_step_forward;            /* 0.02 */
+	float walk_stairs_step_forward_test;           /* 0.15 */
+	float walk_stairs_cos_angle_forward_contact;   /* cos 75 deg */
+} orc_character_settings;
+void orc_character_update_ex(orc_world *w, float dt, const orc_character_settings *cfg);
 float orc_overlap_capsule(const orc_world *w, const float center[3], float half_height, float radius, float normal[3],
 						  uint32_t *body);
 void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body);

@@ -123,6 +123,7 @@ def lib():
     L.orc_character_set_velocity.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.orc_character_set_position.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.orc_character_update.argtypes = [C.c_void_p, C.c_float]
+    L.orc_character_update_ex.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_float * 5)]
     L.orc_character_get.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_character_contacts.restype = C.c_uint32
     L.orc_character_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
@@ -227,8 +228,12 @@ class World:
     def character_set_position(self, p):
         self.L.orc_character_set_position(self.h, (C.c_float * 3)(*p))
 
-    def character_update(self, dt=1.0 / 60.0):
-        self.L.orc_character_update(self.h, dt)
+    def character_update(self, dt=1.0 / 60.0, settings=None):
+        """settings: (stick_to_floor_step_down, walk_stairs_step_up, min_step_forward, step_forward_test, cos_angle_forward_contact)"""
+        if settings is None:
+            self.L.orc_character_update(self.h, dt)
+        else:
+            self.L.orc_character_update_ex(self.h, dt, C.byref((C.c_float * 5)(*settings)))
 
     def character_get(self):
         p, v = (C.c_float * 3)(), (C.c_float * 3)()

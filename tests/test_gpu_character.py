@@ -177,3 +177,29 @@ def test_character_wakes_and_pushes_a_sleeping_box(gpx, orc, scenes):
         x_box.append(float(g.get_transform(0)[0]) if tick % 10 == 0 else (x_box[-1] if x_box else 1.0))
     assert x_box[5] == 1.0                       # untouched while the character stands still
     assert max(x_box) > 1.5                      # shoved more than half a metre along +x
+
+
+@pytest.mark.parametrize("height,start,vx", [(0.24, (0.0, 0.5, 0.0), 1.5), (0.30, (0.0, 0.5, 0.0), 1.5),
+                                             (0.20, (2.0, 0.66, 0.0), -1.5), (0.12, (0.0, 0.5, 0.3), 2.5)])
+def test_extended_update_stairs_and_stick_to_floor_match_the_oracle(gpx, orc, height, start, vx):
+    """JPH_CharacterVirtual_ExtendedUpdate with the engine's settings (PlayerPhysics.c:439-446) on a floor with one step:
+    up a 0.24 m step, stopped by a 0.30 m one, set down when walking off a 0.20 m one — bit for bit like the oracle,
+    every tick; the contact lists agree too."""
+    from test_oracle import ENGINE_EXTENDED_UPDATE, stair_scene
+    g = gpx.World(worlds=1, max_bodies=8)
+    o = orc.World(8)
+    for side in (g, o):
+        side.add_mesh((0, 0, 0), stair_scene(height))
+        side.commit()
+        side.character_create(start)
+    for tick in range(1, 121):
+        for side in (g, o):
+            _move(side, (vx if tick > 20 else 0.0, 0.0, 0.0))
+            side.character_update(settings=ENGINE_EXTENDED_UPDATE)
+        _same(g, o, f"step {height} tick {tick}")
+        assert list(g.character_contacts()) == list(o.character_contacts())
+    p = o.character_get()[0]
+    if height == 0.24:
+        assert p[0] > 1.5 and abs(p[1] - (height + 0.45)) < 1e-3
+    if height == 0.30:
+        assert abs(p[0] - 0.75) < 1e-3

@@ -68,6 +68,12 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
     names.update({coin: "prop_coin", door: "prop_door", lasers[0]: "laser", lasers[1]: "laser3"})
     coin_alive = True
     touching = []
+    # JPH_ExtendedUpdateSettings as the driver fills it (PlayerPhysics.c:439-446), cos 75 deg by the C library's cosf
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.cosf.restype = ctypes.c_float
+    libm.cosf.argtypes = [ctypes.c_float]
+    ext = (0.25, 0.25, 0.02, 0.15, libm.cosf(np.float32(np.float32(75.0) * np.float32(3.14159265358979323846)) / np.float32(180.0)))
     g_step = np.float32(np.float64(np.float32(-9.81)) * (1.0 / 60.0))
 
     def ray(origin, direction, tmax, mask):
@@ -94,7 +100,7 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
             hit = int(h["body"] != 0xFFFFFFFF)
             out.append(f"R {tick} camera {hit} {int(h['body']) if hit else 0:08x} {bits(h['fraction']) if hit else bits(0.0)} "
                        f"{int(h['face']) if hit else 0:08x}")
-        o.character_update()
+        o.character_update(settings=ext)
         pos = o.character_get()[0]
         # the listener's callbacks run inside ExtendedUpdate: contacts that exist now (added / persisted) by id, bodies
         # before map meshes, then the ones that ended; the coin's handler removes it before this tick's Update

@@ -423,3 +423,68 @@ def test_sliding_box_stops_at_the_coulomb_distance(orc, scenes, friction, v0):
     assert abs(slid - want) < 0.02 * want + 1.0e-3, (slid, want)
     assert np.abs(vel).max() < 1.0e-6
     assert abs(float(xf[0, 2] - x0[2])) < 1.0e-4 and abs(float(xf[0, 4])) < 1.0e-4
+
+
+# ------------------------------------------------------------------------------------------------ stairs (ExtendedUpdate)
+
+ENGINE_EXTENDED_UPDATE = (0.25, 0.25, 0.02, 0.15, float(np.cos(np.radians(75.0))))  # PlayerPhysics.c:439-446
+
+
+def stair_scene(h):
+    """A floor (y = 0, x in [-4, 4]) with a step of height h from x = 1 on; normals face up / towards -x."""
+    def quad(a, b, c, d):
+        return [[a, b, c], [c, d, a]]
+    tris = quad((4, 0, 2), (4, 0, -2), (-4, 0, -2), (-4, 0, 2))
+    tris += quad((4, h, 2), (4, h, -2), (1, h, -2), (1, h, 2))
+    tris += quad((1, 0, -2), (1, h, -2), (1, h, 2), (1, 0, 2))
+    return np.array(tris, np.float32)
+
+
+def walk(world, ticks, vx, settings, record=None):
+    """The engine's MovePlayer + UpdatePlayer loop (PlayerPhysics.c:203-295): horizontal speed vx, gravity while in the air."""
+    g = np.float32(-9.81 / 60.0)
+    for _ in range(ticks):
+        _, v, ground, _ = world.character_get()
+        mv = np.zeros(3, np.float32)
+        mv[0] = vx
+        if ground != 0:
+            mv[1] = np.float32(v[1] + g)
+        world.character_set_velocity([float(x) for x in mv])
+        world.character_update(settings=settings)
+        if record is not None:
+            record.append(world.character_get())
+
+
+@pytest.mark.parametrize("height,settings,climbs", [(0.24, None, False), (0.24, ENGINE_EXTENDED_UPDATE, True),
+                                                    (0.30, ENGINE_EXTENDED_UPDATE, False)])
+def test_character_walks_up_steps_no_higher_than_the_step_height(orc, height, settings, climbs):
+    """walkStairsStepUp = 0.25 (PlayerPhysics.c:441): a 0.24 m step stops the plain update, ExtendedUpdate's walk-stairs
+    takes it, and a 0.30 m step stays a wall."""
+    o = orc.World(8)
+    o.add_mesh((0, 0, 0), stair_scene(height))
+    o.commit()
+    o.character_create((0.0, 0.5, 0.0))
+    walk(o, 90, 1.5, settings)
+    p, _, ground, _ = o.character_get()
+    if climbs:
+        assert p[0] > 1.5 and abs(p[1] - (height + 0.45)) < 1e-3 and ground == 0
+    else:
+        assert abs(p[0] - 0.75) < 1e-3 and abs(p[1] - 0.45) < 1e-3 and ground == 0
+
+
+def test_character_sticks_to_the_floor_when_walking_down_a_step(orc):
+    """stickToFloorStepDown = 0.25 (PlayerPhysics.c:440): walking off a 0.2 m step the character is set down at once and
+    never reports being in the air; without it there are airborne ticks."""
+    airborne = {}
+    for name, settings in (("plain", None), ("extended", ENGINE_EXTENDED_UPDATE)):
+        o = orc.World(8)
+        o.add_mesh((0, 0, 0), stair_scene(0.2))
+        o.commit()
+        o.character_create((2.0, 0.2 + 0.45 + 0.01, 0.0))
+        rec = []
+        walk(o, 20, 0.0, settings)
+        walk(o, 80, -1.5, settings, rec)
+        p = rec[-1][0]
+        assert abs(p[1] - 0.45) < 1e-3 and p[0] < 0.5
+        airborne[name] = sum(1 for _, _, ground, _ in rec if ground == 3)
+    assert airborne["extended"] == 0 and airborne["plain"] > 0
