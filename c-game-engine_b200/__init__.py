@@ -76,8 +76,18 @@ class BodyDesc(C.Structure):
     ]
 
 
+class ModelCollision(C.Structure):
+    """gpx_model_collision (include/gpx.h)."""
+    pass
+
+
 class HullShape(C.Structure):
     _fields_ = [("shape", C.c_uint32), ("half_extents", C.c_float * 3), ("center", C.c_float * 3), ("exact", C.c_uint32)]
+
+
+ModelCollision._fields_ = [("collision_type", C.c_uint32), ("bb_origin", C.c_float * 3), ("bb_extents", C.c_float * 3),
+                           ("n_hulls", C.c_uint32), ("n_triangles", C.c_uint64), ("hull_points", C.c_uint64 * 8),
+                           ("hull", HullShape * 8), ("exact", C.c_uint32)]
 
 
 class CharacterDesc(C.Structure):
@@ -182,6 +192,9 @@ def lib() -> C.CDLL:
         "gpx_static_load_gmap_file": (i32, [vp, C.c_char_p]),
         "gpx_static_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "gpx_shape_from_hull": (i32, [vp, u64, f32, C.POINTER(HullShape)]),
+        "gpx_model_load_gmdl": (i32, [vp, u64, f32, C.POINTER(ModelCollision)]),
+        "gpx_model_load_gmdl_container": (i32, [vp, u64, f32, C.POINTER(ModelCollision)]),
+        "gpx_static_add_gmdl": (i32, [vp, C.POINTER(Transform), vp, u64, f32, u32]),
         "gpx_body_create": (u32, [vp, u32, C.POINTER(BodyDesc)]),
         "gpx_body_create_all": (i32, [vp, C.POINTER(BodyDesc), u32, vp, vp, vp]),
         "gpx_body_destroy": (i32, [vp, u32, u32]),
@@ -294,6 +307,17 @@ class World:
         _check(self.L.gpx_static_add_mesh(self.h, C.byref(x), t.ctypes.data, len(t), friction, user_data,
                                           C.byref(out)), "gpx_static_add_mesh")
         return out.value
+
+    def add_gmdl(self, pos, body: bytes, friction=4.25, rot=(0, 0, 0, 1), ray_flags=1) -> int:
+        """gpx_static_add_gmdl: a static model's triangle mesh (decompressed .gmdl) as one static body."""
+        x = Transform()
+        x.position[:] = [float(v) for v in pos]
+        x.rotation[:] = rot
+        buf = np.frombuffer(body, dtype=np.uint8)
+        rc = self.L.gpx_static_add_gmdl(self.h, C.byref(x), buf.ctypes.data, len(buf), friction, ray_flags)
+        if rc < 0:
+            raise GpxError(f"gpx_static_add_gmdl failed with {-rc}")
+        return STATIC_BODY_BASE + rc
 
     def load_gmap(self, body: bytes) -> int:
         buf = np.frombuffer(body, dtype=np.uint8)
@@ -548,6 +572,15 @@ def pinned_array(n: int, dtype) -> np.ndarray:
 
 
 _PINNED: list = []
+
+
+def model_collision(data: bytes, container=False, tolerance=0.03) -> ModelCollision:
+    """gpx_model_load_gmdl(_container): the collision section of a .gmdl.  Host-side, needs no device."""
+    out = ModelCollision()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    fn = lib().gpx_model_load_gmdl_container if container else lib().gpx_model_load_gmdl
+    _check(fn(C.addressof(buf), len(data), tolerance, C.byref(out)), "gpx_model_load_gmdl")
+    return out
 
 
 def shape_from_hull(points, tolerance=0.03):

@@ -496,24 +496,23 @@ static int load_gmap_body(gpx_world *w, const uint8_t *body, uint64_t size)
 /* The asset container around a map (engine/src/assets/AssetReader.c:150-257, AssetReader.h:15-17): 23-byte header
  * <u32 magic "GAME"><u8 version = 2><u8 type><u8 typeVersion><u64 rawSize><u64 gzSize>, then one gzip member.  The
  * same size checks as DecompressAsset; the decompressed body goes to gpx_static_load_gmap. */
-int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t size)
+// The asset container (AssetReader.c:150-257): header checks as DecompressAsset, then the one gzip member.
+static int inflate_container(const uint8_t *blob, uint64_t size, uint8_t want_type, std::vector<uint8_t> &body)
 {
-	if (!w || !blob) return -GPX_ERR_INVALID_ARG;
 	const uint64_t HEADER = 23;
-	if (size < HEADER) return -GPX_ERR_INVALID_ARG;
+	if (!blob || size < HEADER) return GPX_ERR_INVALID_ARG;
 	uint32_t magic;
-	uint64_t raw_size, gz_size;
 	memcpy(&magic, blob, 4);
+	if (magic != 0x454D4147u || blob[4] != 2 || (want_type != 0xFF && blob[5] != want_type)) return GPX_ERR_INVALID_ARG;
+	uint64_t raw_size, gz_size;
 	memcpy(&raw_size, blob + 7, 8);
 	memcpy(&gz_size, blob + 15, 8);
-	if (magic != 0x454D4147u || blob[4] != 2u) return -GPX_ERR_INVALID_ARG;
-	if (size - HEADER != gz_size || raw_size >= (1ull << 32)) return -GPX_ERR_INVALID_ARG;  // avail_out is 32 bits wide
-	std::vector<uint8_t> body;
+	if (size - HEADER != gz_size || raw_size >= (1ull << 32)) return GPX_ERR_INVALID_ARG;
 	try { body.resize((size_t)raw_size); }
-	catch (...) { return -GPX_ERR_INVALID_ARG; }
+	catch (...) { return GPX_ERR_INVALID_ARG; }
 	z_stream zs;
 	memset(&zs, 0, sizeof(zs));
-	if (inflateInit2(&zs, MAX_WBITS | 16) != Z_OK) return -GPX_ERR_INVALID_ARG;
+	if (inflateInit2(&zs, MAX_WBITS | 16) != Z_OK) return GPX_ERR_INVALID_ARG;
 	zs.next_in = const_cast<Bytef *>(blob + HEADER);
 	zs.avail_in = (uInt)gz_size;
 	zs.next_out = body.data();
@@ -521,8 +520,120 @@ int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t s
 	const int zrc = inflate(&zs, Z_FINISH);
 	const uint64_t got = zs.total_out;
 	inflateEnd(&zs);
-	if (zrc != Z_STREAM_END || got != raw_size) return -GPX_ERR_INVALID_ARG;
-	return gpx_static_load_gmap(w, body.data(), raw_size);
+	return zrc == Z_STREAM_END && got == raw_size ? GPX_OK : GPX_ERR_INVALID_ARG;
+}
+
+int gpx_static_load_gmap_container(gpx_world *w, const uint8_t *blob, uint64_t size)
+{
+	if (!w || !blob) return -GPX_ERR_INVALID_ARG;
+	std::vector<uint8_t> body;
+	if (inflate_container(blob, size, 0xFF, body) != GPX_OK) return -GPX_ERR_INVALID_ARG;
+	return gpx_static_load_gmap(w, body.data(), body.size());
+}
+
+// Walks a decompressed .gmdl up to its collision section (ModelLoader.c:66-151); the cursor is left on the hull /
+// triangle counts.
+static bool gmdl_seek_collision(Cursor &c, gpx_model_collision &m)
+{
+	const uint32_t n_mat = c.get<uint32_t>(), n_slot = c.get<uint32_t>(), n_skin = c.get<uint32_t>(), n_lod = c.get<uint32_t>();
+	m.collision_type = c.get<uint8_t>();
+	for (uint32_t i = 0; i < n_mat && !c.bad; i++)
+	{
+		c.skip_string();
+		c.skip(16 + 4);  // colour, shader
+	}
+	c.skip(4ull * n_slot * n_skin);
+	for (uint32_t i = 0; i < n_lod && !c.bad; i++)
+	{
+		c.skip(8);  // lod distance, squared distance
+		const uint64_t nv = c.get<uint64_t>();
+		if (c.bad || nv > (c.n - c.o) / 48u) { c.bad = true; break; }
+		c.skip(nv * 48u);  // ModelVertex
+		c.skip(4);         // total index count
+		std::vector<uint32_t> counts;
+		for (uint32_t j = 0; j < n_slot && !c.bad; j++) counts.push_back(c.get<uint32_t>());
+		for (uint32_t cnt : counts) c.skip(4ull * cnt);
+	}
+	for (int k = 0; k < 3; k++) m.bb_origin[k] = c.get<float>();
+	for (int k = 0; k < 3; k++) m.bb_extents[k] = c.get<float>();
+	return !c.bad && m.collision_type <= 2;
+}
+
+int gpx_model_load_gmdl(const uint8_t *body, uint64_t size, float tolerance, gpx_model_collision *out)
+{
+	if (!body || !out) return GPX_ERR_INVALID_ARG;
+	try
+	{
+		gpx_model_collision m;
+		memset(&m, 0, sizeof(m));
+		Cursor c{body, size};
+		if (!gmdl_seek_collision(c, m)) return GPX_ERR_INVALID_ARG;
+		m.exact = 1;
+		if (m.collision_type == 2)
+		{
+			const uint64_t nh = c.get<uint64_t>();
+			if (c.bad || nh > (c.n - c.o) / 20u) return GPX_ERR_INVALID_ARG;
+			m.n_hulls = (uint32_t)nh;
+			for (uint64_t h = 0; h < nh; h++)
+			{
+				const uint64_t np = c.get<uint64_t>();
+				float off[3];
+				for (int k = 0; k < 3; k++) off[k] = c.get<float>();
+				if (c.bad || np > (c.n - c.o) / 12u) return GPX_ERR_INVALID_ARG;
+				if (h < GPX_MODEL_MAX_HULLS)
+				{
+					std::vector<float> pts(3 * (size_t)np);
+					memcpy(pts.data(), c.d + c.o, 12 * (size_t)np);
+					m.hull_points[h] = np;
+					if (np < 3 || gpx_shape_from_hull(pts.data(), np, tolerance, &m.hull[h]) != GPX_OK) return GPX_ERR_INVALID_ARG;
+					for (int k = 0; k < 3; k++) m.hull[h].center[k] += off[k];  // AddShape2(settings, &offset, ...), ModelLoader.c:336
+					if (!m.hull[h].exact) m.exact = 0;
+				}
+				else
+					m.exact = 0;
+				c.skip(12 * np);
+			}
+		}
+		else if (m.collision_type == 1)
+		{
+			m.n_triangles = c.get<uint64_t>();
+			if (c.bad || m.n_triangles > (c.n - c.o) / 36u) return GPX_ERR_INVALID_ARG;
+		}
+		if (c.bad) return GPX_ERR_INVALID_ARG;
+		*out = m;
+		return GPX_OK;
+	}
+	catch (...) { return GPX_ERR_INVALID_ARG; }
+}
+
+int gpx_model_load_gmdl_container(const uint8_t *blob, uint64_t size, float tolerance, gpx_model_collision *out)
+{
+	std::vector<uint8_t> body;
+	const int rc = inflate_container(blob, size, 0xFF, body);
+	if (rc != GPX_OK) return rc;
+	return gpx_model_load_gmdl(body.data(), body.size(), tolerance, out);
+}
+
+int gpx_static_add_gmdl(gpx_world *w, const gpx_transform *xfm, const uint8_t *body, uint64_t size, float friction, uint32_t ray_flags)
+{
+	if (!w || !xfm || !body) return -GPX_ERR_INVALID_ARG;
+	try
+	{
+		gpx_model_collision m;
+		memset(&m, 0, sizeof(m));
+		Cursor c{body, size};
+		if (!gmdl_seek_collision(c, m) || m.collision_type != 1) return -GPX_ERR_INVALID_ARG;
+		const uint64_t nt = c.get<uint64_t>();
+		if (c.bad || nt == 0 || nt > (c.n - c.o) / 36u) return -GPX_ERR_INVALID_ARG;
+		std::vector<float> tris(9 * (size_t)nt);
+		memcpy(tris.data(), c.d + c.o, 36 * (size_t)nt);
+		uint32_t sbody = 0;
+		const int rc = gpx_static_add_mesh(w, xfm, tris.data(), nt, friction, 0, &sbody);
+		if (rc != GPX_OK) return -rc;
+		if (ray_flags != GPX_BODY_BLOCKS_LASERS) gpx_body_set_ray_flags(w, 0, sbody, ray_flags);
+		return (int)(sbody - STATIC_BODY_BASE);
+	}
+	catch (...) { return -GPX_ERR_INVALID_ARG; }
 }
 
 int gpx_static_load_gmap_file(gpx_world *w, const char *path)

@@ -207,6 +207,32 @@ typedef struct gpx_hull_shape
 } gpx_hull_shape;
 int gpx_shape_from_hull(const float *points, uint64_t n, float tolerance, gpx_hull_shape *out);
 
+/* The collision section of a decompressed .gmdl (engine/src/assets/ModelLoader.c:54-211: materials, skins and LODs are
+ * skipped, then the bounding box, then either `numHulls x { numPoints, offset, points }` for dynamic models or
+ * `numTriangles x 9 f32` for static ones).  Dynamic hulls are classified like gpx_shape_from_hull (with the hull's offset
+ * added to `center`); a static model's triangles can be added to a world with gpx_static_add_gmdl.  Host-side; needs no
+ * device.  Returns GPX_OK or GPX_ERR_INVALID_ARG for a malformed file. */
+#define GPX_MODEL_MAX_HULLS 8
+typedef struct gpx_model_collision
+{
+	uint32_t collision_type;   /* 0 none, 1 static (triangle mesh), 2 dynamic (convex hulls) */
+	float bb_origin[3], bb_extents[3]; /* ModelDefinition::boundingBoxOrigin / Extents: the shape `collision = 1` actors use */
+	uint32_t n_hulls;          /* hulls in the file (only the first GPX_MODEL_MAX_HULLS are described below) */
+	uint64_t n_triangles;      /* static models */
+	uint64_t hull_points[GPX_MODEL_MAX_HULLS];
+	gpx_hull_shape hull[GPX_MODEL_MAX_HULLS];
+	uint32_t exact;            /* 1 when every hull is exactly a box or a sphere */
+} gpx_model_collision;
+int gpx_model_load_gmdl(const uint8_t *body, uint64_t size, float tolerance, gpx_model_collision *out);
+/* the same from the asset container (23-byte header + gzip member, AssetReader.c:150-257) */
+int gpx_model_load_gmdl_container(const uint8_t *blob, uint64_t size, float tolerance, gpx_model_collision *out);
+
+/* A static model's triangle mesh (CreateStaticModelShape, ModelLoader.c:345-351: JPH_MeshShapeSettings_Create over the
+ * file's triangles) as one static body at `xfm`, e.g. the laser emitters of test.gmap.  Returns the static body index or
+ * a negative error; gpx_static_commit afterwards. */
+int gpx_static_add_gmdl(gpx_world *w, const gpx_transform *xfm, const uint8_t *body, uint64_t size, float friction,
+						uint32_t ray_flags);
+
 /* ---- bodies --------------------------------------------------------------------------------------------------- */
 
 /* JPH_BodyInterface_CreateAndAddBody (17 call sites).  Returns body id or GPX_INVALID_BODY. */

@@ -180,3 +180,29 @@ def test_async_batches_back_to_back_and_device_sync(gpx, orc, scenes):
             assert g.sync() == 0
         _assert_hits_equal(np.asarray(oa), ref_a)
         _assert_hits_equal(np.asarray(ob), ref_b)
+
+
+def test_static_model_mesh_from_a_gmdl_is_hit_like_the_same_triangles(gpx, orc, scenes):
+    """gpx_static_add_gmdl: laseremitter.gmdl's 310-triangle collision mesh placed like the map's emitters
+    (CreateStaticModelShape, ModelLoader.c:345-351) answers rays exactly like the oracle given the same triangles."""
+    import gasset
+    m = np.load(scenes.GOLDEN + "/models.npz")
+    body = gasset.build_gmdl_body(1, m["laseremitter_bb"][:3], m["laseremitter_bb"][3:], tris=m["laseremitter_tris"])
+    rot = (0.0, float(np.sin(0.4)), 0.0, float(np.cos(0.4)))
+    g = gpx.World(worlds=1, max_bodies=8)
+    o = orc.World(8)
+    sb = g.add_gmdl((1.0, 0.5, -2.0), body, friction=4.25, rot=rot)
+    assert sb == o.add_mesh((1.0, 0.5, -2.0), m["laseremitter_tris"], friction=4.25, rot=rot)
+    g.commit()
+    o.commit()
+    rng = np.random.default_rng(11)
+    n = 4096
+    rays = np.zeros(n, gpx.RAY_DTYPE)
+    rays["origin"] = np.float32([1.0, 0.5, -2.0]) + rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    d = np.float32([1.0, 0.5, -2.0]) + rng.uniform(-0.3, 0.3, (n, 3)).astype(np.float32) - rays["origin"]
+    rays["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmax"] = 10.0
+    rays["mask"] = gpx.RAYMASK_STATIC
+    hg, ho = g.raycast(rays), o.raycast(rays)
+    assert (hg["body"] != gpx.INVALID_BODY).mean() > 0.5
+    assert np.array_equal(hg.view(np.uint8), ho.view(np.uint8))

@@ -201,3 +201,48 @@ def test_hull_classifier_on_the_shipped_models(gpx, scenes):
     assert shape == gpx.SHAPE_BOX and not exact and np.allclose(he, (0.25, 0.5, 0.25), atol=1e-6)
     with pytest.raises(gpx.GpxError):
         gpx.shape_from_hull(cyl[:3])
+
+
+def test_gmdl_collision_section_is_parsed_by_the_library(gpx, scenes):
+    """gpx_model_load_gmdl(_container) (host-side, no device): the collision section of a .gmdl as ModelLoader.c:145-211
+    reads it.  The files are rebuilt from the hulls / triangles decoded from the shipped models (tools/make_golden.py),
+    with render data that the parser has to skip (two materials, one skin, one LOD with vertices and indices)."""
+    import struct
+    import gasset
+    m = np.load(scenes.GOLDEN + "/models.npz")
+
+    def with_render_data(collision):
+        # 2 materials, 2 slots, 1 skin, 1 lod; then what build_gmdl_body appends after its empty header
+        b = struct.pack("<4IB", 2, 2, 1, 1, collision[16])
+        for name in (b"texture/a\0", b"texture/bb\0"):
+            b += struct.pack("<Q", len(name)) + name + struct.pack("<4fI", 1, 1, 1, 1, 0)
+        b += struct.pack("<2I", 0, 1)                                 # the skin's material per slot
+        b += struct.pack("<2fQ", 10.0, 100.0, 3) + bytes(3 * 48)      # lod distances, 3 vertices
+        b += struct.pack("<I2I", 6, 3, 3) + bytes(4 * 3) + bytes(4 * 3)
+        return b + collision[17:]
+
+    cube = gasset.build_gmdl_body(2, m["cube_bb"][:3], m["cube_bb"][3:], hulls=[((0, 0, 0), m["cube_hull_points"])])
+    mc = gpx.model_collision(with_render_data(cube))
+    assert mc.collision_type == 2 and mc.n_hulls == 1 and mc.hull_points[0] == 120 and mc.exact == 1
+    assert mc.hull[0].shape == gpx.SHAPE_BOX and np.allclose(list(mc.hull[0].half_extents), 0.2, atol=1e-6)
+    assert np.allclose(list(mc.bb_extents), 0.2)
+    # leafy: two hulls with offsets (none of them a primitive); the offsets land in `center`
+    n0, n1 = (int(x) for x in m["leafy_hull_counts"])
+    pts = m["leafy_hull_points"]
+    leafy = gasset.build_gmdl_body(2, m["leafy_bb"][:3], m["leafy_bb"][3:],
+                                   hulls=[((0, 0.5, 0), pts[:n0] - np.float32([0, 0.5, 0])), ((0, 0, 0), pts[n0:])])
+    mc = gpx.model_collision(gasset.write_container(gasset.MODEL_ASSET_TYPE if hasattr(gasset, "MODEL_ASSET_TYPE") else 2, 1, with_render_data(leafy)),
+                             container=True)
+    assert mc.n_hulls == 2 and mc.exact == 0 and (mc.hull_points[0], mc.hull_points[1]) == (n0, n1)
+    lo, hi = pts[:n0].min(0), pts[:n0].max(0)
+    assert np.allclose(list(mc.hull[0].center), (lo + hi) / 2, atol=1e-5) and np.allclose(list(mc.hull[0].half_extents), (hi - lo) / 2, atol=1e-5)
+    # a static model: its triangle count; hostile counts are refused, not allocated
+    emitter = gasset.build_gmdl_body(1, m["laseremitter_bb"][:3], m["laseremitter_bb"][3:], tris=m["laseremitter_tris"])
+    mc = gpx.model_collision(with_render_data(emitter))
+    assert mc.collision_type == 1 and mc.n_triangles == 310
+    bad = bytearray(emitter)
+    bad[-310 * 36 - 8:-310 * 36] = struct.pack("<Q", 1 << 62)
+    with pytest.raises(gpx.GpxError):
+        gpx.model_collision(bytes(bad))
+    with pytest.raises(gpx.GpxError):
+        gpx.model_collision(cube[:40])
