@@ -29,6 +29,8 @@ RAYMASK_STATIC_DYNAMIC = 3
 RAYMASK_REQUIRE_BLOCKS_LASERS = 1 << 8
 ERR_CUDA = 32
 
+CAST_DTYPE = np.dtype([("origin", "<f4", 3), ("tmax", "<f4"), ("dir", "<f4", 3), ("mask", "<u4"), ("radius", "<f4"), ("pad", "<f4", 3)])
+CAST_HIT_DTYPE = np.dtype([("fraction", "<f4"), ("body", "<u4"), ("face", "<u4"), ("world", "<u4"), ("normal", "<f4", 3), ("pad", "<f4")])
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmax", "<f4"), ("dir", "<f4", 3), ("mask", "<u4")])
 HIT_DTYPE = np.dtype([("fraction", "<f4"), ("body", "<u4"), ("face", "<u4"), ("world", "<u4")])
 TRANSFORM_DTYPE = np.dtype([("position", "<f4", 3), ("rotation", "<f4", 4)])
@@ -201,6 +203,7 @@ def lib() -> C.CDLL:
         "gpx_body_set_ray_flags": (i32, [vp, u32, u32, u32]),
         "gpx_body_wake": (i32, [vp, u32, u32]),
         "gpx_overlap_capsule_batch": (i32, [vp, vp, u64, vp]),
+        "gpx_spherecast_batch": (i32, [vp, vp, u64, vp]),
         "gpx_read_sleeping": (i32, [vp, vp, u64]),
         "gpx_body_set_linear_velocity": (i32, [vp, u32, u32, C.POINTER(f32)]),
         "gpx_body_set_linear_and_angular_velocity": (i32, [vp, u32, u32, C.POINTER(f32), C.POINTER(f32)]),
@@ -447,6 +450,13 @@ class World:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.zeros(len(rays), HIT_DTYPE)
         _check(self.L.gpx_raycast_batch(self.h, rays.ctypes.data, len(rays), hits.ctypes.data), "gpx_raycast_batch")
+        return hits
+
+    def spherecast(self, casts: np.ndarray) -> np.ndarray:
+        """gpx_spherecast_batch: first contact of each swept sphere with the map and the bodies its mask admits."""
+        casts = np.ascontiguousarray(casts, dtype=CAST_DTYPE)
+        hits = np.zeros(len(casts), CAST_HIT_DTYPE)
+        _check(self.L.gpx_spherecast_batch(self.h, casts.ctypes.data, len(casts), hits.ctypes.data), "gpx_spherecast_batch")
         return hits
 
     def raycast_into(self, rays: np.ndarray, hits: np.ndarray) -> None:

@@ -1207,6 +1207,35 @@ int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *ori
 	return gpx_raycast_batch(w, &r, 1, out);
 }
 
+int gpx_spherecast_batch(gpx_world *w, const gpx_sphere_cast *casts, uint64_t n, gpx_cast_hit *hits)
+{
+	if (!w || (n && (!casts || !hits))) return GPX_ERR_INVALID_ARG;
+	if (n == 0) return GPX_OK;
+	static_assert(sizeof(gpx_sphere_cast) == 48 && sizeof(gpx_cast_hit) == 32, "three / two float4 per record");
+	std::lock_guard<std::mutex> lk(w->mu);
+	cudaSetDevice(w->device);
+	int rc;
+	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
+	if ((rc = flush_commands(w)) != GPX_OK) return rc;
+	// staging shared with the capsule queries: 48 B in, 32 B out per cast
+	if (2 * n > w->capq_cap)
+	{
+		GPX_CUDA(cudaStreamSynchronize(w->stream));
+		cudaFree(w->d_capq);
+		cudaFree(w->d_capo);
+		w->d_capq = w->d_capo = nullptr;
+		w->capq_cap = 0;
+		GPX_CUDA(cudaMalloc(&w->d_capq, 64ull * n));
+		GPX_CUDA(cudaMalloc(&w->d_capo, 64ull * n));
+		w->capq_cap = 2 * n;
+	}
+	GPX_CUDA(cudaMemcpyAsync(w->d_capq, casts, 48ull * n, cudaMemcpyHostToDevice, w->stream));
+	if ((rc = launch_spherecast(w, w->d_capq, n, w->d_capo)) != GPX_OK) return rc;
+	GPX_CUDA(cudaMemcpyAsync(hits, w->d_capo, 32ull * n, cudaMemcpyDeviceToHost, w->stream));
+	GPX_CUDA(cudaStreamSynchronize(w->stream));
+	return GPX_OK;
+}
+
 int gpx_overlap_capsule_batch(gpx_world *w, const gpx_capsule_query *queries, uint64_t n, gpx_overlap *out)
 {
 	if (!w || (n && (!queries || !out))) return GPX_ERR_INVALID_ARG;

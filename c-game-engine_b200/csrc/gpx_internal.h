@@ -201,6 +201,7 @@ uint32_t wide_event_capacity(const gpx_world *w);
 int wide_counters(gpx_world *w, uint32_t *out8);
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
+int launch_spherecast(gpx_world *w, const void *d_casts, uint64_t n, void *d_hits);
 // gpx_char.cu
 int launch_character(gpx_world *w, float dt, const gpx_character_update_settings *cfg);
 int launch_overlap_capsules(gpx_world *w, const void *d_queries, uint64_t n, void *d_out);

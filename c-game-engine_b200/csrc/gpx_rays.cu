@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
+#include "gpx_narrow.cuh"
 
 namespace gpx {
 
@@ -288,6 +289,334 @@ __global__ void __launch_bounds__(RAY_THREADS_MAX) k_raycast(RayArgs a)
 		h.w = __uint_as_float(world);
 		a.hits[i] = h;
 	}
+}
+
+// ---------------------------------------------------------------------------------------------------- sphere casts
+// First contact of a sphere swept along a ray with a triangle = the earliest of: the sphere's lowest point reaching the
+// triangle's plane inside the triangle; the centre's ray entering a cylinder of the sphere's radius around an edge; the
+// centre's ray entering a sphere of that radius around a vertex.  Boxes: six faces, twelve edges, eight corners in the
+// box's frame.  Same formulas, same order as the CPU restatement.
+
+// the centre's ray (o, unit d) against the cylinder of radius r around the segment p0 -> p1
+__device__ __forceinline__ bool sweep_edge(v3 o, v3 d, float tmax, float r, v3 p0, v3 p1, float &best, v3 &n)
+{
+	const v3 ed = p1 - p0, m = o - p0;
+	const float ee = dot(ed, ed), md = dot(m, ed), dd = dot(d, ed);
+	const float a = ee - (dd * dd);
+	if (!(a > 1.0e-12f)) return false;
+	const float k = dot(m, m) - (r * r);
+	const float c = (ee * k) - (md * md);
+	const float b = (ee * dot(m, d)) - (dd * md);
+	const float disc = (b * b) - (a * c);
+	if (disc < 0.0f) return false;
+	const float t = (-b - sqrtf(disc)) / a;
+	if (!(t >= 0.0f && t <= tmax && t < best)) return false;
+	const float s = md + (t * dd);
+	if (s < 0.0f || s > ee) return false;
+	const v3 q = madd(o, d, t) - madd(p0, ed, s / ee);
+	best = t;
+	n = q * (1.0f / r);
+	return true;
+}
+
+__device__ __forceinline__ bool sweep_vertex(v3 o, v3 d, float tmax, float r, v3 p, float &best, v3 &n)
+{
+	const v3 m = o - p;
+	const float b = dot(m, d), c = dot(m, m) - (r * r);
+	const float disc = (b * b) - c;
+	if (disc < 0.0f) return false;
+	const float t = -b - sqrtf(disc);
+	if (!(t >= 0.0f && t <= tmax && t < best)) return false;
+	best = t;
+	n = (madd(o, d, t) - p) * (1.0f / r);
+	return true;
+}
+
+static __device__ __noinline__ bool sweep_sphere_tri(v3 o, v3 d, float tmax, float r, v3 a, v3 b, v3 c, float &tout, v3 &nout)
+{
+	// overlapping at the start
+	const v3 cp = closest_on_tri(o, a, b, c);
+	const v3 dv = o - cp;
+	const float d2 = len2(dv);
+	if (d2 <= (r * r))
+	{
+		tout = 0.0f;
+		nout = d2 > 1.0e-12f ? dv * (1.0f / sqrtf(d2)) : -d;
+		return true;
+	}
+	const v3 e1 = b - a, e2 = c - a;
+	const v3 nn = cross(e1, e2);
+	const float l2 = len2(nn);
+	float best = 3.0e38f;
+	v3 bn = V(0.0f, 0.0f, 0.0f);
+	if (l2 > 1.0e-20f)
+	{
+		v3 n = nn * (1.0f / sqrtf(l2));
+		float s0 = dot(n, o - a), nd = dot(n, d);
+		if (s0 < 0.0f)
+		{
+			n = -n;
+			s0 = -s0;
+			nd = -nd;
+		}
+		if (nd < 0.0f && s0 > r)
+		{
+			const float t = (r - s0) / nd;
+			if (t <= tmax)
+			{
+				// where the sphere touches the plane; inside the triangle?
+				const v3 p = madd(o, d, t) - (n * r);
+				const v3 ca = cross(b - a, p - a), cb = cross(c - b, p - b), cc = cross(a - c, p - c);
+				const float sa = dot(ca, nn), sb = dot(cb, nn), sc = dot(cc, nn);
+				if (sa >= 0.0f && sb >= 0.0f && sc >= 0.0f)
+				{
+					tout = t;
+					nout = n;
+					return true;
+				}
+			}
+		}
+	}
+	if (!(r > 0.0f)) return false;  // a ray only meets the face
+	bool hit = false;
+	hit |= sweep_edge(o, d, tmax, r, a, b, best, bn);
+	hit |= sweep_edge(o, d, tmax, r, b, c, best, bn);
+	hit |= sweep_edge(o, d, tmax, r, c, a, best, bn);
+	hit |= sweep_vertex(o, d, tmax, r, a, best, bn);
+	hit |= sweep_vertex(o, d, tmax, r, b, best, bn);
+	hit |= sweep_vertex(o, d, tmax, r, c, best, bn);
+	if (!hit) return false;
+	tout = best;
+	nout = bn;
+	return true;
+}
+
+__device__ __forceinline__ bool sweep_sphere_sphere(v3 o, v3 d, float tmax, float r, v3 x, float R, float &tout, v3 &nout)
+{
+	const float rr = r + R;
+	const v3 m = o - x;
+	const float mm = dot(m, m);
+	if (mm <= (rr * rr))
+	{
+		tout = 0.0f;
+		nout = mm > 1.0e-12f ? m * (1.0f / sqrtf(mm)) : -d;
+		return true;
+	}
+	float best = 3.0e38f;
+	v3 n;
+	if (!sweep_vertex(o, d, tmax, rr, x, best, n)) return false;
+	tout = best;
+	nout = n;
+	return true;
+}
+
+// in the box's frame; the normal goes back to the world; face = the box face the normal leans to (2k: -axis, 2k+1: +axis)
+static __device__ __noinline__ bool sweep_sphere_box(v3 o, v3 d, float tmax, float r, v3 x, q4 q, v3 he, float &tout, v3 &nout,
+													 uint32_t &face)
+{
+	const m33 R = qmat(q);
+	const v3 lo = mtmul(R, o - x), ld = mtmul(R, d);
+	float best = 3.0e38f;
+	v3 bn = V(0.0f, 0.0f, 0.0f);
+	bool hit = false;
+	const v3 cl = V(fminf(fmaxf(lo.x, -he.x), he.x), fminf(fmaxf(lo.y, -he.y), he.y), fminf(fmaxf(lo.z, -he.z), he.z));
+	const v3 dv = lo - cl;
+	const float d2 = len2(dv);
+	if (d2 <= (r * r))
+	{
+		best = 0.0f;
+		bn = d2 > 1.0e-12f ? dv * (1.0f / sqrtf(d2)) : -ld;
+		hit = true;
+	}
+	else
+	{
+		// faces: the plane he_k + r on the side the centre comes from, hit inside the face's rectangle
+		for (int k = 0; k < 3; k++)
+		{
+			const float ok = get(lo, k), dk = get(ld, k), hk = get(he, k);
+			const float side = ok >= 0.0f ? 1.0f : -1.0f;
+			if ((dk * side) >= 0.0f || (ok * side) <= (hk + r)) continue;  // moving away, or not outside this slab
+			const float t = (((hk + r) * side) - ok) / dk;
+			if (!(t >= 0.0f && t <= tmax && t < best)) continue;
+			const v3 p = madd(lo, ld, t);
+			const int u = (k + 1) % 3, v = (k + 2) % 3;
+			if (fabsf(get(p, u)) <= get(he, u) && fabsf(get(p, v)) <= get(he, v))
+			{
+				best = t;
+				bn = V(k == 0 ? side : 0.0f, k == 1 ? side : 0.0f, k == 2 ? side : 0.0f);
+				hit = true;
+			}
+		}
+		// twelve edges (four along each axis), eight corners (a ray, radius 0, only meets the faces)
+		for (int k = 0; k < 3 && r > 0.0f; k++)
+			for (int su = -1; su <= 1; su += 2)
+				for (int sv = -1; sv <= 1; sv += 2)
+				{
+					const int u = (k + 1) % 3, v = (k + 2) % 3;
+					float p0[3], p1[3];
+					p0[k] = -get(he, k); p1[k] = get(he, k);
+					p0[u] = p1[u] = (float)su * get(he, u);
+					p0[v] = p1[v] = (float)sv * get(he, v);
+					hit |= sweep_edge(lo, ld, tmax, r, V(p0[0], p0[1], p0[2]), V(p1[0], p1[1], p1[2]), best, bn);
+				}
+		for (int sx = -1; sx <= 1 && r > 0.0f; sx += 2)
+			for (int sy = -1; sy <= 1; sy += 2)
+				for (int sz = -1; sz <= 1; sz += 2)
+					hit |= sweep_vertex(lo, ld, tmax, r, V((float)sx * he.x, (float)sy * he.y, (float)sz * he.z), best, bn);
+	}
+	if (!hit) return false;
+	const float ax = fabsf(bn.x), ay = fabsf(bn.y), az = fabsf(bn.z);
+	int k = 0;
+	if (ay > ax) k = 1;
+	if (az > (k == 0 ? ax : ay)) k = 2;
+	face = (uint32_t)(2 * k + (get(bn, k) > 0.0f ? 1 : 0));
+	tout = best;
+	nout = mmul(R, bn);
+	return true;
+}
+
+struct CastArgs
+{
+	const float4 *nodes;
+	const float4 *tris;
+	uint32_t n_nodes;
+	const float4 *casts;  // 3 per cast: origin|tmax, dir|mask, radius|-
+	float4 *hits;         // 2 per cast: fraction body face world | normal -
+	unsigned long long n;
+	const float4 *pos, *quat, *prop1;
+	const uint32_t *flags;
+	uint32_t worlds, cap;
+};
+
+// One thread per cast: the rays' tree with every box grown by the radius, the exact sweep at the leaves (a triangle cut
+// into several leaves is simply tested again), then the world's bodies.
+__global__ void __launch_bounds__(128) k_spherecast(CastArgs a)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const float4 c0 = __ldg(&a.casts[3 * i]), c1 = __ldg(&a.casts[3 * i + 1]), c2 = __ldg(&a.casts[3 * i + 2]);
+	const v3 o = V(c0), d = V(c1);
+	const float tmax = c0.w, r = c2.x;
+	const uint32_t mask = __float_as_uint(c1.w), layers = mask & 0xFu, world = mask >> 16;
+	const bool need_flag = (mask & GPX_RAYMASK_REQUIRE_BLOCKS_LASERS) != 0;
+	float best = 3.0e38f;
+	uint32_t bbody = GPX_INVALID_BODY, bface = GPX_INVALID_FACE;
+	v3 bn = V(0.0f, 0.0f, 0.0f);
+	if ((layers & 1u) && a.n_nodes > 0)
+	{
+		const float tiny = 1.0e-20f;
+		const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+		const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+		const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+		const float pad = r + 1.0e-3f;  // the swept sphere reaches `r` beyond the centre's ray
+		int stack[STACK_DEPTH];
+		int sp = 0, node = 0;
+		while (true)
+		{
+			if (node >= 0)
+			{
+				const float4 n0 = __ldg(&a.nodes[4 * node + 0]), n1 = __ldg(&a.nodes[4 * node + 1]), n2 = __ldg(&a.nodes[4 * node + 2]),
+							 n3 = __ldg(&a.nodes[4 * node + 3]);
+				const float limit = fminf(best, tmax);
+				bool h[2];
+#pragma unroll
+				for (int ch = 0; ch < 2; ch++)
+				{
+					const float4 bx = ch ? n1 : n0;
+					const float zl = ch ? n2.z : n2.x, zh = ch ? n2.w : n2.y;
+					const float ax0 = ((bx.x - pad) - o.x) * idx, ax1 = ((bx.y + pad) - o.x) * idx;
+					const float ay0 = ((bx.z - pad) - o.y) * idy, ay1 = ((bx.w + pad) - o.y) * idy;
+					const float az0 = ((zl - pad) - o.z) * idz, az1 = ((zh + pad) - o.z) * idz;
+					const float tn = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+					const float tf = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), limit));
+					h[ch] = tn <= tf;
+				}
+				const int k0 = __float_as_int(n3.x), k1 = __float_as_int(n3.y);
+				if (h[0] && h[1])
+				{
+					stack[sp++] = k1;
+					node = k0;
+					continue;
+				}
+				if (h[0]) { node = k0; continue; }
+				if (h[1]) { node = k1; continue; }
+			}
+			else
+			{
+				const int leaf = ~node;
+				const float4 A = __ldg(&a.tris[4 * leaf + 0]), B = __ldg(&a.tris[4 * leaf + 1]), C = __ldg(&a.tris[4 * leaf + 2]);
+				bool ok = true;
+				if (need_flag) ok = (__float_as_uint(__ldg(&a.tris[4 * leaf + 3]).w) & 1u) != 0;
+				float t;
+				v3 n;
+				if (ok && sweep_sphere_tri(o, d, tmax, r, V(A), V(B), V(C), t, n))
+				{
+					const uint32_t orig = __float_as_uint(A.w);
+					// first contact; equal times resolve to the lower triangle index, independent of traversal order
+					if (t < best || (t == best && orig < bface))
+					{
+						best = t;
+						bn = n;
+						bface = orig;
+						bbody = STATIC_BODY_BASE + __float_as_uint(B.w);
+					}
+				}
+			}
+			if (sp == 0) break;
+			node = stack[--sp];
+		}
+	}
+	if ((layers & ~1u) && world < a.worlds)
+	{
+		const uint32_t base = world * a.cap;
+		for (uint32_t b = 0; b < a.cap; b++)
+		{
+			const uint32_t f = a.flags[base + b];
+			if (!(f & BF_ALIVE)) continue;
+			const uint32_t shape = (f >> BF_SHAPE_SHIFT) & 7u;
+			if (shape == GPX_SHAPE_EMPTY) continue;
+			if (!((layers >> ((f >> BF_LAYER_SHIFT) & 3u)) & 1u)) continue;
+			if (need_flag && !((f >> BF_RAYFLAG_SHIFT) & 1u)) continue;
+			const float4 p = a.pos[base + b], p1 = a.prop1[base + b];
+			float t;
+			v3 n;
+			uint32_t face = 0;
+			const bool hit = shape == GPX_SHAPE_BOX ? sweep_sphere_box(o, d, tmax, r, V(p), Q(a.quat[base + b]), V(p1), t, n, face)
+													: sweep_sphere_sphere(o, d, tmax, r, V(p), p1.x, t, n);
+			if (hit && t < best)
+			{
+				best = t;
+				bn = n;
+				bbody = b;
+				bface = face;
+			}
+		}
+	}
+	const bool miss = bbody == GPX_INVALID_BODY;
+	a.hits[2 * i] = make_float4(miss ? RAY_MISS_FRACTION : best / tmax, __uint_as_float(bbody), __uint_as_float(bface), __uint_as_float(world));
+	a.hits[2 * i + 1] = miss ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(bn.x, bn.y, bn.z, 0.0f);
+}
+
+int launch_spherecast(gpx_world *w, const void *d_casts, uint64_t n, void *d_hits)
+{
+	if (n == 0) return GPX_OK;
+	CastArgs a;
+	a.nodes = w->sd.ray_nodes;
+	a.tris = w->sd.ray_tri;
+	a.n_nodes = w->sd.n_ray_nodes;
+	a.casts = (const float4 *)d_casts;
+	a.hits = (float4 *)d_hits;
+	a.n = n;
+	a.pos = w->bs.pos;
+	a.quat = w->bs.quat;
+	a.prop1 = w->bs.prop1;
+	a.flags = w->bs.flags;
+	a.worlds = w->W;
+	a.cap = w->cap;
+	k_spherecast<<<(unsigned)((n + 127) / 128), 128, 0, w->stream>>>(a);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
 }
 
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits)

@@ -415,6 +415,31 @@ int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *ori
 
 /* ---- shape queries ------------------------------------------------------------------------------------------------------ */
 
+/* Batched sphere casts (shape casts): a sphere of `radius` moved from `origin` along the unit `dir` for up to `tmax`, first
+ * contact with the static map and the bodies the layer mask admits (same mask bits, body filter and world index as
+ * gpx_ray).  fraction = t / tmax, 0 when the sphere overlaps something at the start, 2.0 on a miss; normal = unit vector
+ * from the contact point to the sphere's centre at that moment; face as in gpx_hit (box: the face the normal leans to).
+ * Host buffers; copies and the wait are part of the call. */
+typedef struct gpx_sphere_cast /* 48 B */
+{
+	float origin[3];
+	float tmax;
+	float dir[3];
+	uint32_t mask;
+	float radius;
+	float pad[3];
+} gpx_sphere_cast;
+typedef struct gpx_cast_hit /* 32 B */
+{
+	float fraction;
+	uint32_t body;
+	uint32_t face;
+	uint32_t world;
+	float normal[3];
+	float pad;
+} gpx_cast_hit;
+int gpx_spherecast_batch(gpx_world *w, const gpx_sphere_cast *casts, uint64_t n, gpx_cast_hit *hits);
+
 /* Batched capsule overlap: the collide-shape query JPH_CharacterVirtual_ExtendedUpdate is built from
  * (engine/src/physics/PlayerPhysics.c:447), for callers that bring their own upright capsules.  Each query reports the
  * deepest penetration against the static map and the solid bodies (layers STATIC and DYNAMIC, no sensors) of its world:

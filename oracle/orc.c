@@ -514,6 +514,258 @@ typedef struct
 	int64_t lo, hi;
 } job_t;
 
+/* ------------------------------------------------------------------------------------------ sphere casts
+ * First contact of a sphere swept along a ray with a triangle = the earliest of: the sphere's lowest point reaching the
+ * triangle's plane inside the triangle; the centre's ray entering a cylinder of the sphere's radius around an edge; the
+ * centre's ray entering a sphere of that radius around a vertex.  Boxes are the same with six faces, twelve edges and
+ * eight corners in the box's frame. */
+
+static v3 closest_on_tri(v3 p, v3 a, v3 b, v3 c);
+
+/* the centre's ray (o, unit d) against the cylinder of radius r around the segment p0 -> p1 */
+static int sweep_edge(v3 o, v3 d, float tmax, float r, v3 p0, v3 p1, float *best, v3 *n)
+{
+	const v3 ed = vsub(p1, p0), m = vsub(o, p0);
+	const float ee = vdot(ed, ed), md = vdot(m, ed), dd = vdot(d, ed);
+	const float a = ee - (dd * dd);
+	if (!(a > 1.0e-12f)) return 0;
+	const float k = vdot(m, m) - (r * r);
+	const float c = (ee * k) - (md * md);
+	const float b = (ee * vdot(m, d)) - (dd * md);
+	const float disc = (b * b) - (a * c);
+	if (disc < 0.0f) return 0;
+	const float t = (-b - sqrtf(disc)) / a;
+	if (!(t >= 0.0f && t <= tmax && t < *best)) return 0;
+	const float s = md + (t * dd);
+	if (s < 0.0f || s > ee) return 0;
+	const v3 q = vsub(vmadd(o, d, t), vmadd(p0, ed, s / ee));
+	*best = t;
+	*n = vscale(q, 1.0f / r);
+	return 1;
+}
+
+static int sweep_vertex(v3 o, v3 d, float tmax, float r, v3 p, float *best, v3 *n)
+{
+	const v3 m = vsub(o, p);
+	const float b = vdot(m, d), c = vdot(m, m) - (r * r);
+	const float disc = (b * b) - c;
+	if (disc < 0.0f) return 0;
+	const float t = -b - sqrtf(disc);
+	if (!(t >= 0.0f && t <= tmax && t < *best)) return 0;
+	*best = t;
+	*n = vscale(vsub(vmadd(o, d, t), p), 1.0f / r);
+	return 1;
+}
+
+static int sweep_sphere_tri(v3 o, v3 d, float tmax, float r, v3 a, v3 b, v3 c, float *tout, v3 *nout)
+{
+	/* overlapping at the start */
+	const v3 cp = closest_on_tri(o, a, b, c);
+	const v3 dv = vsub(o, cp);
+	const float d2 = vlen2(dv);
+	if (d2 <= (r * r))
+	{
+		*tout = 0.0f;
+		*nout = d2 > 1.0e-12f ? vscale(dv, 1.0f / sqrtf(d2)) : vneg(d);
+		return 1;
+	}
+	const v3 e1 = vsub(b, a), e2 = vsub(c, a);
+	const v3 nn = vcross(e1, e2);
+	const float l2 = vlen2(nn);
+	float best = 3.0e38f;
+	v3 bn = V(0, 0, 0);
+	if (l2 > 1.0e-20f)
+	{
+		v3 n = vscale(nn, 1.0f / sqrtf(l2));
+		float s0 = vdot(n, vsub(o, a)), nd = vdot(n, d);
+		if (s0 < 0.0f)
+		{
+			n = vneg(n);
+			s0 = -s0;
+			nd = -nd;
+		}
+		if (nd < 0.0f && s0 > r)
+		{
+			const float t = (r - s0) / nd;
+			if (t <= tmax)
+			{
+				/* where the sphere touches the plane; inside the triangle? */
+				const v3 p = vsub(vmadd(o, d, t), vscale(n, r));
+				const v3 ca = vcross(vsub(b, a), vsub(p, a)), cb = vcross(vsub(c, b), vsub(p, b)), cc = vcross(vsub(a, c), vsub(p, c));
+				const float sa = vdot(ca, nn), sb = vdot(cb, nn), sc = vdot(cc, nn);
+				if (sa >= 0.0f && sb >= 0.0f && sc >= 0.0f)
+				{
+					*tout = t;
+					*nout = n;
+					return 1;
+				}
+			}
+		}
+	}
+	if (!(r > 0.0f)) return 0; /* a ray only meets the face */
+	int hit = 0;
+	hit |= sweep_edge(o, d, tmax, r, a, b, &best, &bn);
+	hit |= sweep_edge(o, d, tmax, r, b, c, &best, &bn);
+	hit |= sweep_edge(o, d, tmax, r, c, a, &best, &bn);
+	hit |= sweep_vertex(o, d, tmax, r, a, &best, &bn);
+	hit |= sweep_vertex(o, d, tmax, r, b, &best, &bn);
+	hit |= sweep_vertex(o, d, tmax, r, c, &best, &bn);
+	if (!hit) return 0;
+	*tout = best;
+	*nout = bn;
+	return 1;
+}
+
+static int sweep_sphere_sphere(v3 o, v3 d, float tmax, float r, v3 x, float R, float *tout, v3 *nout)
+{
+	const float rr = r + R;
+	const v3 m = vsub(o, x);
+	const float mm = vdot(m, m);
+	if (mm <= (rr * rr))
+	{
+		*tout = 0.0f;
+		*nout = mm > 1.0e-12f ? vscale(m, 1.0f / sqrtf(mm)) : vneg(d);
+		return 1;
+	}
+	float best = 3.0e38f;
+	v3 n;
+	if (!sweep_vertex(o, d, tmax, rr, x, &best, &n)) return 0;
+	*tout = best;
+	*nout = n;
+	return 1;
+}
+
+/* in the box's frame; the normal goes back to the world; face = the box face the normal leans to (2k: -axis, 2k+1: +axis) */
+static int sweep_sphere_box(v3 o, v3 d, float tmax, float r, const body_t *B, float *tout, v3 *nout, uint32_t *face)
+{
+	const m33 R = qmat(B->q);
+	const v3 lo = mtmul(&R, vsub(o, B->x)), ld = mtmul(&R, d), he = B->he;
+	float best = 3.0e38f;
+	v3 bn = V(0, 0, 0);
+	int hit = 0;
+	const v3 cl = V(fminf(fmaxf(lo.x, -he.x), he.x), fminf(fmaxf(lo.y, -he.y), he.y), fminf(fmaxf(lo.z, -he.z), he.z));
+	const v3 dv = vsub(lo, cl);
+	const float d2 = vlen2(dv);
+	if (d2 <= (r * r))
+	{
+		best = 0.0f;
+		bn = d2 > 1.0e-12f ? vscale(dv, 1.0f / sqrtf(d2)) : vneg(ld);
+		hit = 1;
+	}
+	else
+	{
+		/* faces: the plane he_k + r on the side the centre comes from, hit inside the face's rectangle */
+		for (int k = 0; k < 3; k++)
+		{
+			const float ok = vget(lo, k), dk = vget(ld, k), hk = vget(he, k);
+			const float side = ok >= 0.0f ? 1.0f : -1.0f;
+			if ((dk * side) >= 0.0f || (ok * side) <= (hk + r)) continue; /* moving away, or not outside this slab */
+			const float t = (((hk + r) * side) - ok) / dk;
+			if (!(t >= 0.0f && t <= tmax && t < best)) continue;
+			const v3 q = vmadd(lo, ld, t);
+			const int u = (k + 1) % 3, v = (k + 2) % 3;
+			if (fabsf(vget(q, u)) <= vget(he, u) && fabsf(vget(q, v)) <= vget(he, v))
+			{
+				best = t;
+				bn = V(k == 0 ? side : 0.0f, k == 1 ? side : 0.0f, k == 2 ? side : 0.0f);
+				hit = 1;
+			}
+		}
+		/* twelve edges (four along each axis), eight corners (a ray, radius 0, only meets the faces) */
+		for (int k = 0; k < 3 && r > 0.0f; k++)
+			for (int su = -1; su <= 1; su += 2)
+				for (int sv = -1; sv <= 1; sv += 2)
+				{
+					const int u = (k + 1) % 3, v = (k + 2) % 3;
+					float p0[3], p1[3];
+					p0[k] = -vget(he, k); p1[k] = vget(he, k);
+					p0[u] = p1[u] = (float)su * vget(he, u);
+					p0[v] = p1[v] = (float)sv * vget(he, v);
+					hit |= sweep_edge(lo, ld, tmax, r, V(p0[0], p0[1], p0[2]), V(p1[0], p1[1], p1[2]), &best, &bn);
+				}
+		for (int sx = -1; sx <= 1 && r > 0.0f; sx += 2)
+			for (int sy = -1; sy <= 1; sy += 2)
+				for (int sz = -1; sz <= 1; sz += 2)
+					hit |= sweep_vertex(lo, ld, tmax, r, V((float)sx * he.x, (float)sy * he.y, (float)sz * he.z), &best, &bn);
+	}
+	if (!hit) return 0;
+	const float ax = fabsf(bn.x), ay = fabsf(bn.y), az = fabsf(bn.z);
+	int k = 0;
+	if (ay > ax) k = 1;
+	if (az > (k == 0 ? ax : ay)) k = 2;
+	*face = (uint32_t)(2 * k + (vget(bn, k) > 0.0f ? 1 : 0));
+	*tout = best;
+	*nout = mmul(&R, bn);
+	return 1;
+}
+
+static void spherecast_one(const orc_world *w, const orc_sphere_cast *q, orc_cast_hit *h)
+{
+	const v3 o = V(q->origin[0], q->origin[1], q->origin[2]);
+	const v3 d = V(q->dir[0], q->dir[1], q->dir[2]);
+	const uint32_t layers = q->mask & 0xFu;
+	const int need_flag = (q->mask & (1u << 8)) != 0;
+	float best = 3.0e38f;
+	uint32_t bbody = ORC_INVALID, bface = ORC_INVALID;
+	v3 bn = V(0, 0, 0);
+	if (layers & 1u)
+		for (uint32_t i = 0; i < w->ntris; i++)
+		{
+			const tri_t *T = &w->tris[i];
+			if (need_flag && !(w->sbodies[T->body].ray_flags & 1u)) continue;
+			float t;
+			v3 n;
+			if (sweep_sphere_tri(o, d, q->tmax, q->radius, T->v0, T->vb, T->vc, &t, &n) && t < best)
+			{
+				best = t;
+				bn = n;
+				bbody = ORC_STATIC_BODY_BASE + T->body;
+				bface = i;
+			}
+		}
+	for (uint32_t i = 0; i < w->max_bodies; i++)
+	{
+		const body_t *b = &w->bodies[i];
+		if (!b->alive || b->shape == ORC_SHAPE_EMPTY) continue;
+		if (!((layers >> b->layer) & 1u)) continue;
+		if (need_flag && !(b->ray_flags & 1u)) continue;
+		float t;
+		v3 n;
+		uint32_t f = 0;
+		int hit = b->shape == ORC_SHAPE_BOX ? sweep_sphere_box(o, d, q->tmax, q->radius, b, &t, &n, &f)
+											: sweep_sphere_sphere(o, d, q->tmax, q->radius, b->x, b->he.x, &t, &n);
+		if (hit && t < best)
+		{
+			best = t;
+			bn = n;
+			bbody = i;
+			bface = f;
+		}
+	}
+	memset(h, 0, sizeof(*h));
+	h->world = q->mask >> 16;
+	if (bbody == ORC_INVALID)
+	{
+		h->fraction = RAY_MISS_FRACTION;
+		h->body = ORC_INVALID;
+		h->face = ORC_INVALID;
+	}
+	else
+	{
+		h->fraction = best / q->tmax;
+		h->body = bbody;
+		h->face = bface;
+		h->normal[0] = bn.x;
+		h->normal[1] = bn.y;
+		h->normal[2] = bn.z;
+	}
+}
+
+void orc_spherecast(const orc_world *w, const orc_sphere_cast *casts, uint64_t n, orc_cast_hit *hits)
+{
+	for (uint64_t i = 0; i < n; i++) spherecast_one(w, &casts[i], &hits[i]);
+}
+
 static void *job_main(void *arg)
 {
 	job_t *j = (job_t *)arg;

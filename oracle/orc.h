@@ -112,6 +112,12 @@ float orc_overlap_capsule(const orc_world *w, const float center[3], float half_
 void orc_character_get(const orc_world *w, float pos[3], float vel[3], uint32_t *ground, uint32_t *ground_body);
 /* ids the character touches after the last orc_character_update: bodies ascending, then static meshes ascending */
 uint32_t orc_character_contacts(const orc_world *w, uint32_t *others, uint32_t cap);
+/* Sphere casts (shape casts): a sphere of `radius` moved from `origin` along the unit `dir` for up to `tmax`; the first
+ * contact with the static triangles and the bodies the layer mask admits.  fraction = t / tmax (0 when the sphere
+ * already overlaps something at the start), normal = from the contact point to the sphere's centre at that moment. */
+typedef struct orc_sphere_cast { float origin[3]; float tmax; float dir[3]; uint32_t mask; float radius; float pad[3]; } orc_sphere_cast;
+typedef struct orc_cast_hit { float fraction; uint32_t body; uint32_t face; uint32_t world; float normal[3]; float pad; } orc_cast_hit;
+void orc_spherecast(const orc_world *w, const orc_sphere_cast *casts, uint64_t n, orc_cast_hit *hits);
 /* closest-hit rays, brute force over every static triangle and every body */
 void orc_raycast(const orc_world *w, const orc_ray *rays, uint64_t n, orc_hit *hits);
 uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_body, uint32_t cap);

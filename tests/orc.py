@@ -46,6 +46,8 @@ class BodyDesc(C.Structure):
     ]
 
 
+CAST_DTYPE = np.dtype([("origin", "<f4", 3), ("tmax", "<f4"), ("dir", "<f4", 3), ("mask", "<u4"), ("radius", "<f4"), ("pad", "<f4", 3)])
+CAST_HIT_DTYPE = np.dtype([("fraction", "<f4"), ("body", "<u4"), ("face", "<u4"), ("world", "<u4"), ("normal", "<f4", 3), ("pad", "<f4")])
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmax", "<f4"), ("dir", "<f4", 3), ("mask", "<u4")])
 HIT_DTYPE = np.dtype([("fraction", "<f4"), ("body", "<u4"), ("face", "<u4"), ("world", "<u4")])
 
@@ -132,6 +134,7 @@ def lib():
     L.orc_manifold_count.restype = C.c_uint32
     L.orc_manifold_count.argtypes = [C.c_void_p]
     L.orc_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_spherecast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.orc_raycast_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.orc_max_threads.restype = C.c_int
     L.orc_step_many.restype = C.c_int
@@ -255,6 +258,12 @@ class World:
 
     def manifolds(self) -> int:
         return self.L.orc_manifold_count(self.h)
+
+    def spherecast(self, casts: np.ndarray) -> np.ndarray:
+        casts = np.ascontiguousarray(casts, dtype=CAST_DTYPE)
+        hits = np.zeros(len(casts), CAST_HIT_DTYPE)
+        self.L.orc_spherecast(self.h, casts.ctypes.data, len(casts), hits.ctypes.data)
+        return hits
 
     def raycast(self, rays: np.ndarray, mt=False) -> np.ndarray:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -206,3 +206,41 @@ def test_static_model_mesh_from_a_gmdl_is_hit_like_the_same_triangles(gpx, orc, 
     hg, ho = g.raycast(rays), o.raycast(rays)
     assert (hg["body"] != gpx.INVALID_BODY).mean() > 0.5
     assert np.array_equal(hg.view(np.uint8), ho.view(np.uint8))
+
+
+def test_sphere_casts_match_the_oracle_on_the_shapes_map_and_on_bodies(gpx, orc, scenes):
+    """gpx_spherecast_batch (north_star: "ray and shape queries"): 16384 random sphere casts through shapes.gmap with boxes
+    and spheres in the way — hit / miss, ids, fractions and normals bit-identical to the oracle's brute force."""
+    meshes = scenes.load_static("shapes")
+    g = gpx.World(worlds=1, max_bodies=8)
+    o = orc.World(8)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    centre = np.mean([p for p, _ in meshes], axis=0)
+    rng = np.random.default_rng(5)
+    for k in range(6):
+        d = dict(position=tuple(float(x) for x in centre + rng.uniform(-3, 3, 3)), motion_type=0, layer=1,
+                 rotation=tuple(float(x) for x in (lambda q: q / np.linalg.norm(q))(rng.normal(size=4))))
+        if k % 2:
+            d.update(shape=2, half_extents=(0.5, 0, 0))
+        else:
+            d.update(half_extents=(0.4, 0.7, 0.3))
+        assert g.create(gpx.body_desc(**d)) == o.create(orc.body_desc(**d))
+    assert g.step() == 0   # the creates reach the device
+    o.step()
+    n = 16384
+    rays = scenes.shapes_rays(n, np.array([p for p, _ in meshes]))
+    c = np.zeros(n, gpx.CAST_DTYPE)
+    c["origin"] = rays["origin"]
+    c["origin"][::3] = (centre + rng.uniform(-4, 4, (len(c[::3]), 3))).astype(np.float32)
+    c["dir"] = rays["dir"]
+    c["tmax"] = 25.0
+    c["mask"] = gpx.RAYMASK_STATIC_DYNAMIC
+    c["mask"][::5] = gpx.RAYMASK_STATIC
+    c["radius"] = rng.choice(np.float32([0.0, 0.05, 0.25, 0.6]), n)
+    hg, ho = g.spherecast(c), o.spherecast(c)
+    assert (hg["body"] != gpx.INVALID_BODY).mean() > 0.9 and (hg["body"] < 8).mean() > 0.01 and (hg["fraction"] == 0).mean() > 0.001
+    bad = np.nonzero(hg.view(np.uint8).reshape(n, 32) != ho.view(np.uint8).reshape(n, 32))[0]
+    assert len(bad) == 0, (bad[:5], hg[bad[:3]], ho[bad[:3]])

@@ -488,3 +488,41 @@ def test_character_sticks_to_the_floor_when_walking_down_a_step(orc):
         assert abs(p[1] - 0.45) < 1e-3 and p[0] < 0.5
         airborne[name] = sum(1 for _, _, ground, _ in rec if ground == 3)
     assert airborne["extended"] == 0 and airborne["plain"] > 0
+
+
+# ------------------------------------------------------------------------------------------------ sphere casts
+
+def test_sphere_cast_known_answers(orc):
+    """A sphere of radius 0.25 cast down -z at a triangle in the plane z = -5, a 1 m box and a 0.4 m sphere: face hits stop
+    a radius early, edge / vertex / corner hits at sqrt(r^2 - offset^2) from the feature, an overlapping start reports 0."""
+    o = orc.World(8)
+    o.add_mesh((0, 0, 0), np.array([[[-1, -1, -5], [1, -1, -5], [0, 1, -5]]], np.float32))
+    o.create(orc.body_desc(position=(3, 0, -5), half_extents=(0.5, 0.5, 0.5), motion_type=0, layer=1))
+    o.create(orc.body_desc(shape=2, half_extents=(0.4, 0, 0), position=(6, 0, -5), motion_type=0, layer=1))
+    c = np.zeros(9, orc.CAST_DTYPE)
+    c["dir"] = (0, 0, -1)
+    c["tmax"] = 10
+    c["mask"] = orc.RAYMASK_STATIC_DYNAMIC
+    c["radius"] = 0.25
+    c["origin"] = [(0, 0, 0), (1.1, -1, 0), (3, 0, 0), (3.6, 0, 0), (6, 0, 0), (0, 0, -4.9), (10, 0, 0), (3.6, 0.6, 0), (3, 0, 0)]
+    c["mask"][8] = orc.RAYMASK_STATIC           # the box is filtered out by the layer mask
+    h = o.spherecast(c)
+    t = h["fraction"] * 10
+    edge = 0.25 ** 2 - 0.1 ** 2
+    assert abs(t[0] - 4.75) < 1e-5 and h["body"][0] == orc.STATIC_BASE and np.allclose(h["normal"][0], (0, 0, 1))
+    assert abs(t[1] - (5 - np.sqrt(edge))) < 1e-5 and abs(np.linalg.norm(h["normal"][1]) - 1) < 1e-5
+    assert abs(t[2] - 4.25) < 1e-5 and h["body"][2] == 0 and h["face"][2] == 5
+    assert abs(t[3] - (4.5 - np.sqrt(edge))) < 1e-5 and h["body"][3] == 0
+    assert abs(t[4] - (5 - 0.65)) < 1e-5 and h["body"][4] == 1
+    assert t[5] == 0 and h["body"][5] == orc.STATIC_BASE
+    assert h["body"][6] == orc.INVALID and h["fraction"][6] == 2.0
+    assert abs(t[7] - (4.5 - np.sqrt(0.25 ** 2 - 0.02))) < 1e-5
+    assert h["body"][8] == orc.INVALID
+    # a cast with radius 0 is a ray
+    c["radius"] = 0.0
+    r = np.zeros(9, orc.RAY_DTYPE)
+    for k in ("origin", "dir", "tmax", "mask"):
+        r[k] = c[k]
+    hr, hc = o.raycast(r), o.spherecast(c)
+    hit = hr["body"] != orc.INVALID
+    assert np.array_equal(hr["body"], hc["body"]) and np.allclose(hr["fraction"][hit], hc["fraction"][hit], atol=1e-6)

@@ -13,10 +13,21 @@ for _ in range(WARM):
     g.step()
 g.phase_cycles(True)
 N = 50
-g.timer_begin()
-for _ in range(N):
-    g.step()
-ms = g.timer_end()
+if os.environ.get("FLUSH"):  # FLUSH=1: cold L2 for every tick, as bench.py times them
+    import torch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ms = 0.0
+    for _ in range(N):
+        flush.zero_()
+        torch.cuda.synchronize()
+        g.timer_begin()
+        g.step()
+        ms += g.timer_end()
+else:
+    g.timer_begin()
+    for _ in range(N):
+        g.step()
+    ms = g.timer_end()
 ph = g.phase_cycles(False)
 tot = sum(ph.values())
 st = g.stats()

@@ -12,11 +12,24 @@ W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 TICKS = int(sys.argv[2]) if len(sys.argv) > 2 else 600
 BLOCK = int(sys.argv[3]) if len(sys.argv) > 3 else 50
 g = bench.make_gpu_ensemble(gpx, scenes, W, 0, 0)
+FLUSH = os.environ.get("FLUSH")  # FLUSH=1: write 256 MiB between ticks, as bench.py does (cold L2 for every tick)
+if FLUSH:
+    import torch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for t0 in range(0, TICKS, BLOCK):
-    g.timer_begin()
-    for _ in range(BLOCK):
-        g.step()
-    ms = g.timer_end()
+    if FLUSH:
+        ms = 0.0
+        for _ in range(BLOCK):
+            flush.zero_()
+            torch.cuda.synchronize()
+            g.timer_begin()
+            g.step()
+            ms += g.timer_end()
+    else:
+        g.timer_begin()
+        for _ in range(BLOCK):
+            g.step()
+        ms = g.timer_end()
     st = g.stats()
     m = st["manifolds"]
     print(f"ticks {t0:4d}..{t0 + BLOCK - 1:4d}: {ms / BLOCK * 1e3:7.1f} us/tick  manifolds mean {m.mean():5.2f} max {m.max():3d} "
