@@ -961,12 +961,21 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.next_flag = nullptr;
 	a.cur_flag = nullptr;
 	a.next_above = 0;
-	if (w->cap > 16 || w->W < 64) return launch_tick_t<32>(w, a, w->stream, w->W);
+	// The widest tile that still puts every world on the machine at once: the tick is a chain of dependent instructions
+	// per world, and a world that has a warp to itself (no other world's branches in its instruction stream) runs that
+	// chain fastest.  148 SMs x 7 resident one-warp blocks: up to 1036 worlds get 32 lanes each (one launch, no routing),
+	// up to 2072 get 16, more get 8 (four worlds per warp).
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+	const uint32_t one_wave = (uint32_t)sms * 7u;
+	static const char *force_tile = getenv("GPX_TILE");  // experiments: 8 / 16 / 32
+	const uint32_t forced = force_tile ? (uint32_t)atoi(force_tile) : 0u;
+	if (w->cap > 16 || forced == 32u || (!forced && w->W <= one_wave)) return launch_tick_t<32>(w, a, w->stream, w->W);
 	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane
 	// launch on a second stream takes the rest.  Each world wrote its own routing at the end of its previous tick
 	// (route_next; two sets of list / count / flags, used alternately), so each world runs exactly once and no
 	// classification kernel sits in front of the two launches.
-	const uint32_t tile = w->cap <= 8 ? 8u : 16u;
+	const uint32_t tile = forced == 8u || forced == 16u ? (w->cap <= 8 ? forced : 16u) : ((w->cap <= 8 && w->W > 2u * one_wave) ? 8u : 16u);
 	int rc;
 	const uint32_t cur = w->busy_cur, nxt = cur ^ 1u;
 	w->busy_cur = nxt;

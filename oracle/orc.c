@@ -6,7 +6,7 @@
  *   2 find contacts: all-pairs AABB + brute-force triangle loop, SAT + supporting-face clipping, <=4 points
  *   3 carry impulses from the previous sub-step's manifolds (warm start)
  *   4 colour manifolds greedily in canonical order; solve in (colour, index) order
- *   5 velocity_steps x (friction, then non-penetration)    sequential impulses
+ *   5 velocity_steps x (manifold friction rows, then the points' non-penetration rows in alternating order)
  *   6 integrate positions / rotations
  *   7 position_steps x Baumgarte position correction
  */

@@ -15,8 +15,16 @@
  *   static map upload, friction 4.25 ......... engine/src/assets/MapLoader.c:200-273
  *   body parameters .......................... game/src/actor/prop/Physbox.c:19-38, engine/src/actor/Trigger.c:33-50 ...
  *   rays and their filters ................... engine/src/physics/PlayerPhysics.c:55-86,297-315, game/src/actor/prop/Laser.c:40-158
- * It is pinned instead by analytic known answers (tests/test_oracle_*.py): free fall with damping, resting
- * contact height, Moller-Trumbore known hits, momentum/energy properties.
+ * It is pinned instead by analytic known answers (tests/test_oracle.py): free fall with damping, resting contact height,
+ * Moller-Trumbore and swept-sphere known hits, momentum conservation, Coulomb stopping distances, and the dissipation a
+ * contact solver owes its user — a kicked 8-box column loses its kinetic energy monotonically (one-second windows), comes
+ * to rest at the stacked heights and, with sleeping allowed, is asleep within five seconds.
+ *
+ * Two deliberate departures from Jolt's solver, both needed for that last property with 10 velocity iterations (DESIGN.md
+ * section 3 has the measurements): friction is solved per MANIFOLD (two tangent rows through the centroid of the contact
+ * points plus one twist row about the normal, limited by friction x the manifold's total normal impulse) instead of per
+ * contact point, and the non-penetration rows of a manifold are swept forwards in even iterations and backwards in odd
+ * ones instead of always in the same order.
  *
  * Plain C, single precision, compiled with -ffp-contract=off so that every expression rounds exactly like the
  * CUDA build (-fmad=false).  Algorithms here are deliberately the naive ones (all-pairs broadphase, brute-force
