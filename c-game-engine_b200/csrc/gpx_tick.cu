@@ -185,11 +185,30 @@ __device__ __forceinline__ void route_next(const TickArgs &a, uint32_t world, ui
 	a.next_flag[world] = (uint8_t)f;
 }
 
+// A world's lanes: a tile of a warp (8 / 16 / 32 lanes, barriers are warp barriers) or, for worlds of a few dozen bodies and
+// a hundred-odd manifolds, a whole block (TILE = 256: one manifold per thread still holds — with 32 lanes such a world
+// revisited five manifolds per lane and colour phase and parked their rows in L2).
+struct BlockTile
+{
+	__device__ __forceinline__ int thread_rank() const { return (int)threadIdx.x; }
+	__device__ __forceinline__ void sync() const { __syncthreads(); }
+	__device__ __forceinline__ bool any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
+};
+
 template <int TILE>
-__global__ void __launch_bounds__(128) k_tick(TickArgs a)
+__device__ __forceinline__ auto make_tile()
+{
+	if constexpr (TILE <= 32)
+		return cg::tiled_partition<TILE>(cg::this_thread_block());
+	else
+		return BlockTile{};
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	auto tile = cg::tiled_partition<TILE>(cg::this_thread_block());
+	auto tile = make_tile<TILE>();
 	const int lane = tile.thread_rank();
 	const uint32_t tiles_per_block = blockDim.x / TILE;
 	const uint32_t slot = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
@@ -348,8 +367,48 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			}
 			if (err) atomicOr(&hdr[3], err);
 			tile.sync();
-			// slots for this chunk of bodies: serial prefix on lane 0 (a handful of bodies)
-			if (lane == 0)
+			// slots for this chunk of bodies.  A block-wide tile holds all bodies in one chunk: every body lane sums the counts
+			// of the bodies before it (at most 63) and writes its own pairs — the same slots and the same order as the serial
+			// prefix below, which is what a tile of a warp uses for its handful of bodies.
+			if constexpr (TILE > 32)
+			{
+				if (lane == 0) hdr[4] = 0;
+				tile.sync();
+				if (i < cap)
+				{
+					uint32_t n = 0, np = 0;
+					for (uint32_t k = 0; k < i; k++)
+					{
+						const uint32_t pk = (uint32_t)__popcll(pmask[k]);
+						n += cnt_static[k] + pk;
+						np += pk;
+					}
+					slot_base[i] = n;
+					n += cnt_static[i];
+					uint32_t stored = 0;
+					unsigned long long pm = pmask[i];
+					while (pm)
+					{
+						const int j = __ffsll((long long)pm) - 1;
+						pm &= pm - 1;
+						if (n < cap_m && np < cap_m)
+						{
+							pair_a[np] = i | (n << 16);
+							pair_b[np] = (uint32_t)j;
+							stored++;
+						}
+						np++;
+						n++;
+					}
+					if (stored) atomicAdd(&hdr[4], stored);
+					if (i == cap - 1)
+					{
+						if (n > cap_m) atomicOr(&hdr[3], (uint32_t)GPX_ERR_CONTACT_CONSTRAINTS_FULL);
+						hdr[0] = min(n, cap_m);
+					}
+				}
+			}
+			else if (lane == 0)
 			{
 				uint32_t n = i0 == 0 ? 0 : hdr[0];
 				uint32_t np = i0 == 0 ? 0 : hdr[4];
@@ -496,41 +555,53 @@ __global__ void __launch_bounds__(128) k_tick(TickArgs a)
 			}
 		}
 		pc.mark(PH_MATCH);
-		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour); active list
-		if (lane == 0)
+		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour); active list.  The lanes
+		// classify the manifolds into one word each (solved or not, the slots of its dynamic bodies); lane 0 then walks
+		// those words, so its chain per manifold is one load, two colour sets, a first-fit and the stores — it used to
+		// chase manifold -> bodies -> flags through shared memory for every one of them.
 		{
-			unsigned long long *used = pmask;  // reuse: per-body colour sets
-			for (uint32_t k = 0; k < cap; k++) used[k] = 0ull;
-			int ncol = 0;
-			uint32_t nact = 0;
-			for (uint32_t mi = 0; mi < nman; mi++)
+			uint32_t *desc = pkey_a;  // the cached keys are dead from here on
+			for (uint32_t mi = lane; mi < nman; mi += TILE)
 			{
 				SMan &m = man[mi];
+				uint32_t d = 0;
 				if (m.np == 0)
-				{
 					m.colour = -1;
-					continue;
-				}
-				if (sensor_pair(m, bodies))
-				{
+				else if (sensor_pair(m, bodies))
 					m.colour = -3;  // touching, reported as a contact event, never solved
-					continue;
+				else
+				{
+					const bool a_dyn = is_dynamic(bodies[m.a].flags);
+					const bool b_dyn = m.b < STATIC_BODY_BASE && is_dynamic(bodies[m.b].flags);
+					d = 0x80000000u | (a_dyn ? m.a : 0xFFu) | ((b_dyn ? m.b : 0xFFu) << 8);
 				}
-				const bool a_dyn = is_dynamic(bodies[m.a].flags);
-				const bool b_dyn = m.b < STATIC_BODY_BASE && is_dynamic(bodies[m.b].flags);
-				unsigned long long u = 0ull;
-				if (a_dyn) u |= used[m.a];
-				if (b_dyn) u |= used[m.b];
-				int c = 0;
-				while (c < 63 && ((u >> c) & 1ull)) c++;
-				m.colour = c;
-				if (a_dyn) used[m.a] |= 1ull << c;
-				if (b_dyn) used[m.b] |= 1ull << c;
-				if (c + 1 > ncol) ncol = c + 1;
-				act[nact++] = mi;
+				desc[mi] = d;
 			}
-			hdr[2] = (uint32_t)ncol;
-			hdr[5] = nact;
+			tile.sync();
+			if (lane == 0)
+			{
+				unsigned long long *used = pmask;  // reuse: per-body colour sets
+				for (uint32_t k = 0; k < cap; k++) used[k] = 0ull;
+				int ncol = 0;
+				uint32_t nact = 0;
+				for (uint32_t mi = 0; mi < nman; mi++)
+				{
+					const uint32_t d = desc[mi];
+					if (!d) continue;
+					const uint32_t ia = d & 0xFFu, ib = (d >> 8) & 0xFFu;
+					unsigned long long u = 0ull;
+					if (ia != 0xFFu) u |= used[ia];
+					if (ib != 0xFFu) u |= used[ib];
+					const int c = ~u ? min(63, __ffsll((long long)~u) - 1) : 63;  // first colour neither body has yet
+					man[mi].colour = c;
+					if (ia != 0xFFu) used[ia] |= 1ull << c;
+					if (ib != 0xFFu) used[ib] |= 1ull << c;
+					if (c + 1 > ncol) ncol = c + 1;
+					act[nact++] = mi;
+				}
+				hdr[2] = (uint32_t)ncol;
+				hdr[5] = nact;
+			}
 		}
 		tile.sync();
 		const int ncol = (int)hdr[2];
@@ -901,7 +972,7 @@ static int launch_tick_t(gpx_world *w, const TickArgs &a, cudaStream_t stream, u
 	const size_t per_world = world_smem_bytes(TILE, w->cap, w->cap_m);
 	const size_t budget = 200u * 1024u;
 	if (per_world > budget) return GPX_ERR_CAPACITY;
-	uint32_t wpb = 32 / TILE;
+	uint32_t wpb = TILE <= 32 ? 32 / TILE : 1;
 	while (wpb > 1 && per_world * wpb > budget) wpb >>= 1;
 	const uint32_t threads = wpb * TILE;
 	const size_t smem = per_world * wpb;
@@ -970,6 +1041,9 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	const uint32_t one_wave = (uint32_t)sms * 7u;
 	static const char *force_tile = getenv("GPX_TILE");  // experiments: 8 / 16 / 32
 	const uint32_t forced = force_tile ? (uint32_t)atoi(force_tile) : 0u;
+	// worlds of more than 32 bodies: a block per world (one manifold per thread up to 256 manifolds)
+	static const bool no_block = getenv("GPX_NO_BLOCK_TILE") != nullptr;
+	if (w->cap > 32 && !no_block && world_smem_bytes(256, w->cap, w->cap_m) <= 200u * 1024u) return launch_tick_t<256>(w, a, w->stream, w->W);
 	if (w->cap > 16 || forced == 32u || (!forced && w->W <= one_wave)) return launch_tick_t<32>(w, a, w->stream, w->W);
 	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane
 	// launch on a second stream takes the rest.  Each world wrote its own routing at the end of its previous tick
