@@ -383,6 +383,7 @@ def run_gpu(args):
         single_res = bench_single_world(gpx, scenes, args, local_rank, rank) if not only else None
         test_map_res = bench_test_map(gpx, scenes, args, local_rank, rank) if not only else None
         sweep = bench_saturation(gpx, scenes, args, local_rank, flush, torch) if not only else None
+        block = bench_block_variant(gpx, scenes, args, local_rank, flush, torch) if not only else None
         cpu = None
         sample_ok = None
         if not args.no_cpu:
@@ -430,12 +431,33 @@ def run_gpu(args):
             "wide": wide_res,
             "single_world": single_res,
             "test_map": test_map_res,
-            "extra": {"weak": weak_res, "saturation": sweep},
+            "extra": {"weak": weak_res, "saturation": sweep, "block_variant": block},
             "wall_ms_timed_region": wall_ms,
             "stats_gathered_worlds": gathered_worlds,
             "kinetic_energy_mean": float(stats["kinetic_energy"].mean()),
         }
     return line
+
+
+def bench_block_variant(gpx, scenes, args, device, flush, torch):
+    """SURVEY §8d C5's optional variant: 512 worlds x the 4 x 4 x 4 block of 64 boxes (about 150 manifolds per world; a block
+    of 256 threads per world)."""
+    W = 512
+    pos = scenes.block_positions()
+    g = gpx.World(worlds=W, max_bodies=64, max_manifolds=256, device=device)
+    for p, t in scenes.load_static("stacked"):
+        g.add_mesh(p, t)
+    g.commit()
+    g.create_all([gpx.body_desc(position=tuple(p)) for p in pos], linvel=scenes.ensemble_velocities(W, 64))
+    for _ in range(30):
+        assert g.step() == 0
+    assert g.sync() == 0
+    k = 60
+    ms = timed_ticks(g, k, flush, torch) / k
+    st = g.stats()
+    assert (st["error"] == 0).all()
+    return {"workload": "C5 block variant: 512 worlds x 64 boxes (4 x 4 x 4, pitch 0.45) on stacked.gmap, same kicks, ticks 30..89",
+            "ms_per_tick": ms, "body_steps_per_s": W * 64 / (ms * 1e-3), "manifolds_per_world": float(st["manifolds"].mean())}
 
 
 def bench_saturation(gpx, scenes, args, device, flush, torch):
@@ -585,7 +607,7 @@ def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
            "workload": "C4: 100 x 10 x 100 lattice of 0.4 m boxes (pitch 0.5, xz jitter +-0.02, Philox key 0x5EED0004) in the "
                        "12-triangle 1024 m room of mapSources/max_box.json, one world per GPU, after 30 settling ticks",
            "roofline": {"bound": "hbm", "kernel": "wide tick (all kw_* kernels)", "achieved": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+                        "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": measured_traffic("wide_tick")},
            "min_y": float(y.min())}
     return res
 
