@@ -1076,6 +1076,7 @@ int gpx_read_stats(gpx_world *w, gpx_world_stats *out)
 	int rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	if ((rc = launch_stats(w)) != GPX_OK) return rc;
+	if (w->wide && (rc = wide_stats(w)) != GPX_OK) return rc;
 	GPX_CUDA(cudaMemcpyAsync(out, w->d_stats, sizeof(gpx_world_stats) * w->W, cudaMemcpyDeviceToHost, w->stream));
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	return GPX_OK;

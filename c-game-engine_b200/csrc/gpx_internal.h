@@ -199,6 +199,7 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps);
 int wide_events_enable(gpx_world *w, bool enable);
 uint32_t wide_event_capacity(const gpx_world *w);
 int wide_counters(gpx_world *w, uint32_t *out8);
+int wide_stats(gpx_world *w);  // after launch_stats: adds the wide world's manifold counts to d_stats
 // gpx_rays.cu
 int launch_raycast(gpx_world *w, const void *d_rays, uint64_t n, void *d_hits);
 int launch_spherecast(gpx_world *w, const void *d_casts, uint64_t n, void *d_hits);

@@ -1535,6 +1535,23 @@ int wide_counters(gpx_world *w, uint32_t *out8)
 
 __global__ void kw_or_word(uint32_t *dst, const uint32_t *src) { *dst |= *src; }
 
+// gpx_read_stats: the manifolds of the last sub-step that hold contact points, counted into their world's entry
+__global__ void kw_count_manifolds(const SMan *man, const uint32_t *cnt, uint32_t cap_m, uint32_t cap, gpx_world_stats *stats)
+{
+	const uint32_t n = min(cnt[WC_NMAN], cap_m);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		if (man[i].np > 0) atomicAdd(&stats[man[i].a / cap].manifolds, 1u);
+}
+
+int wide_stats(gpx_world *w)
+{
+	const WideDevice *d = w->wide;
+	kw_count_manifolds<<<296, 256, 0, w->stream>>>(d->man[d->cur ^ 1], d->counters, d->cap_m, w->cap, w->d_stats);
+	count_launch();
+	GPX_CUDA(cudaGetLastError());
+	return GPX_OK;
+}
+
 int launch_wide_tick(gpx_world *w, float dt, int substeps)
 {
 	WideDevice *d = w->wide;

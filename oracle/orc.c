@@ -1323,7 +1323,72 @@ static void store_points(manifold_t *m, const body_t *A, const body_t *B, int np
 	}
 }
 
-static void find_contacts(orc_world *w, int *err)
+/* Candidate partners for large worlds.  The pair loop of find_contacts visits (i, j > i) in ascending order and applies
+ * every filter itself; for more than SWEEP_MIN_BODIES slots the j's it visits come from this sort-and-sweep over the
+ * x axis instead of from i+1..max_bodies.  The list is a superset of the overlapping pairs in the same (i, j) order, so
+ * the contacts found — and their order — are those of the all-pairs loop. */
+#define SWEEP_MIN_BODIES 256
+typedef struct { float lo; uint32_t id; } sweep_key_t;
+static int sweep_key_cmp(const void *a, const void *b)
+{
+	const sweep_key_t *x = (const sweep_key_t *)a, *y = (const sweep_key_t *)b;
+	return x->lo < y->lo ? -1 : x->lo > y->lo ? 1 : x->id < y->id ? -1 : x->id > y->id;
+}
+static int u64_cmp(const void *a, const void *b)
+{
+	const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+	return x < y ? -1 : x > y;
+}
+/* returns the sorted candidate pairs (i << 32 | j), *first[i] = index of body i's first pair, first[max_bodies] = count */
+static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out)
+{
+	const uint32_t nb = w->max_bodies;
+	const float m = 2.0f * SPECULATIVE_DISTANCE + 1e-3f;
+	v3 *lo = (v3 *)malloc(sizeof(v3) * nb), *hi = (v3 *)malloc(sizeof(v3) * nb);
+	sweep_key_t *keys = (sweep_key_t *)malloc(sizeof(sweep_key_t) * nb);
+	uint32_t n = 0;
+	for (uint32_t i = 0; i < nb; i++)
+	{
+		const body_t *B = &w->bodies[i];
+		if (!B->alive || B->shape == ORC_SHAPE_EMPTY) continue;
+		body_aabb(B, &lo[i], &hi[i]);
+		keys[n].lo = lo[i].x;
+		keys[n++].id = i;
+	}
+	qsort(keys, n, sizeof(sweep_key_t), sweep_key_cmp);
+	size_t cap = 4 * (size_t)n + 64, cnt = 0;
+	uint64_t *pairs = (uint64_t *)malloc(sizeof(uint64_t) * cap);
+	for (uint32_t p = 0; p < n; p++)
+	{
+		const uint32_t a = keys[p].id;
+		for (uint32_t q = p + 1; q < n && keys[q].lo <= hi[a].x + m; q++)
+		{
+			const uint32_t b = keys[q].id;
+			if (lo[a].y - m > hi[b].y || lo[b].y - m > hi[a].y || lo[a].z - m > hi[b].z || lo[b].z - m > hi[a].z) continue;
+			if (cnt == cap)
+			{
+				cap *= 2;
+				pairs = (uint64_t *)realloc(pairs, sizeof(uint64_t) * cap);
+			}
+			pairs[cnt++] = a < b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a;
+		}
+	}
+	qsort(pairs, cnt, sizeof(uint64_t), u64_cmp);
+	uint32_t *first = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)nb + 1));
+	size_t k = 0;
+	for (uint32_t i = 0; i <= nb; i++)
+	{
+		while (k < cnt && (uint32_t)(pairs[k] >> 32) < i) k++;
+		first[i] = (uint32_t)k;
+	}
+	free(lo);
+	free(hi);
+	free(keys);
+	*first_out = first;
+	return pairs;
+}
+
+static void find_contacts_among(orc_world *w, int *err, const uint64_t *cand, const uint32_t *cand_first)
 {
 	w->nman = 0;
 	w->nsens = 0;
@@ -1397,8 +1462,10 @@ static void find_contacts(orc_world *w, int *err)
 			}
 		}
 		/* (b) against higher-numbered slot bodies */
-		for (uint32_t j = i + 1; j < w->max_bodies; j++)
+		const uint32_t npartners = cand ? cand_first[i + 1] - cand_first[i] : w->max_bodies - (i + 1);
+		for (uint32_t q = 0; q < npartners; q++)
 		{
+			const uint32_t j = cand ? (uint32_t)cand[cand_first[i] + q] : i + 1 + q;
 			body_t *B = &w->bodies[j];
 			if (!B->alive || B->shape == ORC_SHAPE_EMPTY) continue;
 			/* at least one awake dynamic body — or a moving kinematic body reaching a sleeper, which only wakes it */
@@ -1455,18 +1522,34 @@ static void find_contacts(orc_world *w, int *err)
 	}
 }
 
+static void find_contacts(orc_world *w, int *err)
+{
+	uint32_t *cand_first = NULL;
+	uint64_t *cand = w->max_bodies > SWEEP_MIN_BODIES ? sweep_candidates(w, &cand_first) : NULL;
+	find_contacts_among(w, err, cand, cand_first);
+	free(cand);
+	free(cand_first);
+}
+
 /* ------------------------------------------------------------------------------------------ solver */
 
 static void warm_start_match(orc_world *w)
 {
+	/* both lists are in canonical order (body a ascending), so the old manifolds of body a are one contiguous run */
+	uint32_t *run = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)w->max_bodies + 1));
+	for (uint32_t a = 0, j = 0; a <= w->max_bodies; a++)
+	{
+		while (j < w->nprev && w->prev[j].a < a) j++;
+		run[a] = j;
+	}
 	for (uint32_t i = 0; i < w->nman; i++)
 	{
 		manifold_t *m = &w->man[i];
 		int got_cf = 0;
-		for (uint32_t j = 0; j < w->nprev; j++)
+		for (uint32_t j = run[m->a]; j < run[m->a + 1]; j++)
 		{
 			const manifold_t *o = &w->prev[j];
-			if (o->a != m->a || o->b != m->b) continue;
+			if (o->b != m->b) continue;
 			for (int p = 0; p < m->np; p++)
 			{
 				if (m->ln[p] != 0.0f) continue;
@@ -1488,6 +1571,7 @@ static void warm_start_match(orc_world *w)
 			}
 		}
 	}
+	free(run);
 }
 
 static int colour_manifolds(orc_world *w)

@@ -27,8 +27,9 @@
  * ones instead of always in the same order.
  *
  * Plain C, single precision, compiled with -ffp-contract=off so that every expression rounds exactly like the
- * CUDA build (-fmad=false).  Algorithms here are deliberately the naive ones (all-pairs broadphase, brute-force
- * triangle loops, sequential constraint order) — the GPU path must reproduce their results, not their structure.
+ * CUDA build (-fmad=false).  Algorithms here are deliberately the naive ones (all-pairs broadphase — above 256 bodies
+ * its candidates come from a sort-and-sweep that yields the same pairs in the same order —, brute-force triangle loops,
+ * sequential constraint order): the GPU path must reproduce their results, not their structure.
  */
 #ifndef ORC_H
 #define ORC_H

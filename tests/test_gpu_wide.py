@@ -1,9 +1,11 @@
 """GPU parity: the wide-world kernels (one large world, state in global memory: sort-and-sweep broadphase, one thread
 per pair, hashed-priority colouring, cooperative coloured solver) through the C ABI vs the CPU oracle in its wide mode.
 
-BASELINE config 4 is 100 000 boxes in the 1024 m room of mapSources/max_box.json; the oracle's all-pairs broadphase
-finishes in seconds only up to a few thousand bodies, so bit-exact parity is asserted at those sizes and the full
-size is covered by size-independent properties (no errors, nothing falls through the floor, bit-reproducible runs).
+BASELINE config 4 is 100 000 boxes in the 1024 m room of mapSources/max_box.json.  Above 256 bodies the oracle takes
+its candidate pairs from a sort-and-sweep (same pairs, same order as its all-pairs loop), which lets it follow the full
+100 000-box world at a few seconds per tick: bit-exact parity is asserted there for the ticks in which the lattice
+lands and its 100 000 contacts form, at 20 250 boxes for longer, and the rest of the full-size run is covered by
+size-independent properties (no errors, nothing falls through the floor, bit-reproducible runs).
 """
 import numpy as np
 import pytest
@@ -129,6 +131,33 @@ def test_two_thousand_boxes_match_oracle(gpx, orc, scenes):
         if tick in (1, 6, 12):
             assert g.sync() == 0
             _assert_same(g, o, n, f"lattice 20x5x20 tick {tick}")
+
+
+def _lattice_parity(gpx, orc, scenes, dims, ticks, checks):
+    pos = scenes.lattice_positions(*dims)
+    n = len(pos)
+    g, o = _pair(gpx, orc, scenes.box_map(), n)
+    g.create_all([gpx.body_desc(position=tuple(p)) for p in pos])
+    for p in pos:
+        o.create(orc.body_desc(position=tuple(p)))
+    for tick in range(1, ticks + 1):
+        assert g.step() == 0 and o.step() == 0
+        if tick in checks:
+            assert g.sync() == 0
+            _assert_same(g, o, n, f"lattice {dims} tick {tick}")
+    return g, o
+
+
+def test_twenty_thousand_boxes_match_oracle(gpx, orc, scenes):
+    """45 x 10 x 45 lattice through landing and into rest: 2025 columns of ten boxes, 20 250 manifolds."""
+    g, o = _lattice_parity(gpx, orc, scenes, (45, 10, 45), 45, (5, 15, 30, 45))
+    assert o.L.orc_manifold_count(o.h) == 20250 == int(g.stats()["manifolds"][0])
+
+
+def test_the_benchmarked_100k_lattice_matches_oracle(gpx, orc, scenes):
+    """BASELINE configs[3] itself: 100 x 10 x 100 boxes, the 30 settling ticks bench.py runs before it times anything."""
+    g, o = _lattice_parity(gpx, orc, scenes, (100, 10, 100), 30, (10, 20, 30))
+    assert o.L.orc_manifold_count(o.h) == 100000 == int(g.stats()["manifolds"][0])
 
 
 def test_create_destroy_and_setters_in_a_wide_world(gpx, orc, scenes):

@@ -526,3 +526,32 @@ def test_sphere_cast_known_answers(orc):
     hr, hc = o.raycast(r), o.spherecast(c)
     hit = hr["body"] != orc.INVALID
     assert np.array_equal(hr["body"], hc["body"]) and np.allclose(hr["fraction"][hit], hc["fraction"][hit], atol=1e-6)
+
+
+def test_sweep_candidates_reproduce_the_all_pairs_loop(orc, scenes):
+    """Above 256 body slots the oracle takes candidate pairs from a sort-and-sweep; the same 200 bodies in a world of
+    200 slots (all-pairs) and one of 300 slots (sweep) must evolve bit-identically."""
+    rng = np.random.default_rng(7)
+    n = 200
+    pos = np.stack([rng.uniform(-1.5, 1.5, n), -512.0 + 0.3 + 0.45 * np.arange(n) / 8, rng.uniform(-1.5, 1.5, n)], axis=1)
+    spin = rng.uniform(-3, 3, (n, 3))
+    worlds = []
+    for slots in (n, 300):
+        o = orc.World(slots, wide=True)
+        for p, t in scenes.box_map():
+            o.add_mesh(p, t)
+        for i in range(n):
+            kind = orc.SHAPE_SPHERE if i % 5 == 0 else orc.SHAPE_BOX
+            o.create(orc.body_desc(shape=kind, position=tuple(pos[i]), linear_velocity=(0.0, -2.0, 0.0),
+                                   angular_velocity=tuple(spin[i])))
+        worlds.append(o)
+    seen = 0
+    for tick in range(60):
+        for o in worlds:
+            assert o.step() == 0
+        seen = max(seen, worlds[0].L.orc_manifold_count(worlds[0].h))
+        xa, va = worlds[0].state(n)
+        xb, vb = worlds[1].state(n)
+        assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)), f"tick {tick}"
+        assert np.array_equal(va.view(np.uint32), vb.view(np.uint32)), f"tick {tick}"
+    assert seen > 150            # the pile really is in contact
