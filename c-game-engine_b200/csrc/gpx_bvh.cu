@@ -5,6 +5,7 @@
 // linked into a binary radix tree (Karras 2012) and refitted bottom-up.  Output is two flat float4 arrays laid out
 // for the traversal kernels: 64-byte nodes that carry BOTH children's boxes, and 64-byte triangle records in leaf
 // order.  The whole tree of a shipped map (<= 2k triangles) is <= 250 KB and is read through shared memory / L2.
+#include <cooperative_groups.h>
 #include <cfloat>
 
 #include <algorithm>
@@ -14,6 +15,8 @@
 
 #include "gpx_internal.h"
 #include "gpx_math.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace gpx {
 
@@ -163,8 +166,8 @@ constexpr uint32_t RADIX_BLOCK = 256, RADIX_ITEMS = 4, RADIX_TILE = RADIX_BLOCK 
 
 // `fused` (a few hundred blocks at most): counters are stored block-major and every scatter block sums the table itself —
 // 256 threads read it coalesced out of L2 in a microsecond, where the one-block scan kernel in between cost ten.
-__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long long *__restrict__ keys, uint32_t shift,
-															uint32_t *__restrict__ ghist, bool fused)
+__device__ __forceinline__ void radix_hist_block(const unsigned long long *__restrict__ keys, uint32_t shift,
+												 uint32_t *__restrict__ ghist, bool fused)
 {
 	__shared__ uint32_t hist[256];
 	hist[threadIdx.x] = 0;
@@ -179,13 +182,21 @@ __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long 
 	else
 		ghist[threadIdx.x * gridDim.x + blockIdx.x] = hist[threadIdx.x];  // digit-major: the scan order of the scatter
 }
+__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_hist(const unsigned long long *__restrict__ keys, uint32_t shift,
+															uint32_t *__restrict__ ghist, bool fused,
+															const uint32_t *__restrict__ only_if)
+{
+	if (only_if && *only_if == 0u) return;  // the caller found the array sorted already
+	radix_hist_block(keys, shift, ghist, fused);
+}
 
 // exclusive scan of `n` counters by one block (n = 256 digits x blocks, a few 10^4): each warp owns a contiguous
 // chunk and walks it 32 entries at a time (coalesced); the loads of the first pass are independent, the second pass
 // re-reads from cache
-__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ ghist, uint32_t n)
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ ghist, uint32_t n, const uint32_t *__restrict__ only_if)
 {
 	__shared__ uint32_t warp_sum[32];
+	if (only_if && *only_if == 0u) return;
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	const uint32_t chunk = (((n + 31u) / 32u) + 31u) & ~31u;
 	const uint32_t lo = wid * chunk, hi = min(lo + chunk, n);
@@ -223,9 +234,9 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ ghis
 	}
 }
 
-__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned long long *__restrict__ keys,
-															   unsigned long long *__restrict__ out, uint32_t shift,
-															   const uint32_t *__restrict__ ghist, bool fused)
+__device__ __forceinline__ void radix_scatter_block(const unsigned long long *__restrict__ keys,
+													unsigned long long *__restrict__ out, uint32_t shift,
+													const uint32_t *__restrict__ ghist, bool fused)
 {
 	__shared__ uint32_t wcnt[RADIX_BLOCK / 32][256];
 	__shared__ uint32_t wtot[RADIX_BLOCK / 32];
@@ -292,21 +303,63 @@ __global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned lo
 #pragma unroll
 	for (uint32_t i = 0; i < RADIX_ITEMS; i++) out[wcnt[w][(uint32_t)(key[i] >> shift) & 255u] + local[i]] = key[i];
 }
+__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_scatter(const unsigned long long *__restrict__ keys,
+															   unsigned long long *__restrict__ out, uint32_t shift,
+															   const uint32_t *__restrict__ ghist, bool fused,
+															   const uint32_t *__restrict__ only_if)
+{
+	if (only_if && *only_if == 0u) return;
+	radix_scatter_block(keys, out, shift, ghist, fused);
+}
+
+// The whole sort in ONE cooperative launch (at most 256 blocks, all resident): used where the sort is a rarely needed
+// fall-back behind `only_if`, so that not needing it costs one empty launch instead of two per pass.
+__global__ void __launch_bounds__(RADIX_BLOCK) k_radix_sort_coop(unsigned long long *keys, unsigned long long *tmp,
+																 uint32_t *ghist, uint32_t first_bit, const uint32_t *only_if)
+{
+	if (only_if && *only_if == 0u) return;  // the same answer in every block
+	cg::grid_group grid = cg::this_grid();
+	unsigned long long *src = keys, *dst = tmp;
+	int passes = 0;
+	for (uint32_t sh = first_bit; sh < 64u; sh += 8u) passes++;
+	for (int p = 0; p < passes + (passes & 1); p++)
+	{
+		const uint32_t sh = min(first_bit + 8u * (uint32_t)p, 56u);
+		radix_hist_block(src, sh, ghist, true);
+		grid.sync();
+		radix_scatter_block(src, dst, sh, ghist, true);
+		grid.sync();
+		unsigned long long *t = src;
+		src = dst;
+		dst = t;
+	}
+}
 
 // In-place exclusive prefix sum of `n` counters (one block; the radix sort's scan).
 void exclusive_scan_u32(uint32_t *d, uint32_t n, cudaStream_t st)
 {
-	k_radix_scan<<<1, 1024, 0, st>>>(d, n);
+	k_radix_scan<<<1, 1024, 0, st>>>(d, n, nullptr);
 	count_launch();
 }
 
 // Ascending stable sort of bits [first_bit, 64) of `n` keys (n a multiple of 1024); bits below first_bit keep their
 // input order.  `tmp` holds n keys, `ghist` 256 * n / 1024 counters.  The result ends in `d_keys`.
+// `only_if` (optional): a device word; the passes do nothing when it is zero at the time they run.
 void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_t *ghist, uint32_t n, uint32_t first_bit,
-					cudaStream_t st)
+					cudaStream_t st, const uint32_t *only_if)
 {
 	const uint32_t blocks = n / RADIX_TILE;
-	uint32_t shifts[8];
+	if (only_if && blocks <= 256u)
+	{
+		void *params[] = {&d_keys, &tmp, &ghist, &first_bit, &only_if};
+		if (cudaLaunchCooperativeKernel((const void *)k_radix_sort_coop, dim3(blocks), dim3(RADIX_BLOCK), params, 0, st) == cudaSuccess)
+		{
+			count_launch();
+			return;
+		}
+		cudaGetLastError();  // not resident on this device: the per-pass launches below
+	}
+	uint32_t shifts[9];
 	int passes = 0;
 	for (uint32_t sh = first_bit; sh < 64u; sh += 8u) shifts[passes++] = sh > 56u ? 56u : sh;
 	if (passes & 1) shifts[passes++] = 56u;  // an even number of passes leaves the result in d_keys (a repeat is harmless)
@@ -314,9 +367,9 @@ void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_
 	const bool fused = blocks <= 256u;
 	for (int p = 0; p < passes; p++)
 	{
-		k_radix_hist<<<blocks, RADIX_BLOCK, 0, st>>>(src, shifts[p], ghist, fused);
-		if (!fused) k_radix_scan<<<1, 1024, 0, st>>>(ghist, 256u * blocks);
-		k_radix_scatter<<<blocks, RADIX_BLOCK, 0, st>>>(src, dst, shifts[p], ghist, fused);
+		k_radix_hist<<<blocks, RADIX_BLOCK, 0, st>>>(src, shifts[p], ghist, fused, only_if);
+		if (!fused) k_radix_scan<<<1, 1024, 0, st>>>(ghist, 256u * blocks, only_if);
+		k_radix_scatter<<<blocks, RADIX_BLOCK, 0, st>>>(src, dst, shifts[p], ghist, fused, only_if);
 		count_launch(fused ? 2 : 3);
 		unsigned long long *t = src;
 		src = dst;

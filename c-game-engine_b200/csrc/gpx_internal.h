@@ -189,7 +189,7 @@ int build_static(gpx_world *w);
 void bitonic_sort_u64(unsigned long long *d_keys, uint32_t n_pad, cudaStream_t st);
 void exclusive_scan_u32(uint32_t *d, uint32_t n, cudaStream_t st);
 void radix_sort_u64(unsigned long long *d_keys, unsigned long long *tmp, uint32_t *ghist, uint32_t n, uint32_t first_bit,
-					cudaStream_t st);
+					cudaStream_t st, const uint32_t *only_if = nullptr);
 uint32_t next_pow2(uint32_t v);
 // gpx_wide.cu: the tick of ONE large world (more than 64 bodies), state in global memory
 struct WideDevice;

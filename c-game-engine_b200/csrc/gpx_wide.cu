@@ -47,7 +47,7 @@ constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase ker
 
 enum WideCounter { WC_NMAN = 0, WC_NPREV, WC_NCOL, WC_ERR, WC_UNCOLOURED, WC_NACTIVE, WC_MAXEXT_X, WC_MAXEXT_Z, WC_COLCNT = 8,
 				   WC_COLOFF = WC_COLCNT + WIDE_MAXCOL, WC_COLCUR = WC_COLOFF + WIDE_MAXCOL + 1, WC_NISL = WC_COLCUR + WIDE_MAXCOL,
-				   WC_ISLCUR, WC_NBIG, WC_NMED, WC_MEDCUR, WC_COUNT };
+				   WC_ISLCUR, WC_NBIG, WC_NMED, WC_MEDCUR, WC_UNSORTED, WC_COUNT };
 constexpr uint32_t MEDIUM_MAX = 1024;    // manifolds of an island solved by one block (kw_island_block); more: the cooperative kernels
 constexpr uint32_t MEDIUM_T = 128;       // threads of that block
 constexpr uint32_t SINGLE_BLOCK_MAX = 4096;  // manifolds of large islands up to which ONE block colours and solves them
@@ -72,6 +72,11 @@ struct WideDevice
 	uint32_t nb = 0, n_pad = 0, cap_m = 0, hsize = 0, isl_slots = 0;
 	SBody *bodies = nullptr;
 	unsigned long long *keys = nullptr, *keys_tmp = nullptr;  // keys_tmp / sort_hist: radix sort scratch
+	// the order of the last sort (body per sorted position) and this sub-step's keys by body: bodies move little between
+	// sub-steps, so the keys laid out in the last order are sorted by two passes of tile sorts almost every time, and the
+	// radix sort behind them returns at once
+	uint32_t *order = nullptr, *sort_fallbacks = nullptr;
+	unsigned long long *bkeys = nullptr;
 	uint32_t *sort_hist = nullptr;
 	float4 *boxlo = nullptr, *boxhi = nullptr;
 	SMan *man[2] = {nullptr, nullptr};
@@ -96,6 +101,13 @@ struct WideDevice
 	unsigned long long *ev_keys = nullptr, *ev_tmp = nullptr, *ev_cur = nullptr;
 	uint32_t *ev_hist = nullptr, *ev_flag = nullptr, *ev_pos = nullptr, *ev_ncur = nullptr;
 	int coop_grid_colour = 0, coop_grid_solve = 0;
+	// the tick as a CUDA graph: the launch sequence depends on nothing the host sees during a tick, so it is captured
+	// once per signature (arguments, sub-steps, buffer parity, sleep / event passes) and replayed
+	cudaGraphExec_t graph = nullptr;
+	unsigned char graph_sig[1024];
+	size_t graph_sig_n = 0;
+	uint64_t graph_launches = 0;
+	bool graph_off = false;
 };
 
 struct WideArgs
@@ -106,6 +118,8 @@ struct WideArgs
 	float4 *boxlo, *boxhi;
 	SMan *man, *prev;
 	uint32_t *ord, *prev_ord;
+	uint32_t *order, *sort_fallbacks;
+	unsigned long long *bkeys;  // this sub-step's keys in body order; `keys` is the sorted array
 	SolveRec *recs;
 	uint32_t *cnt;
 	unsigned long long *hkeys;
@@ -161,12 +175,17 @@ __device__ __forceinline__ uint32_t man_prio(uint32_t a, uint32_t b, uint32_t or
 
 // ---------------------------------------------------------------------------------------------------- per body
 
+// Sort keys of slots without a box (dead, empty shape, padding): above every live key, and still carrying the slot, so
+// that the sorted array stays a permutation of the slots.
+__device__ __forceinline__ unsigned long long dead_key(uint32_t i) { return (~0ull << 20) | (unsigned long long)i; }
+__device__ __forceinline__ bool is_dead_key(unsigned long long k) { return (k >> 20) == (~0ull >> 20); }
+
 // one body of kw_begin; `ex` / `ez` return the extents of its box along x and z (0 when it has none)
 __device__ __forceinline__ void begin_body(const WideArgs &a, uint32_t i, float &ex, float &ez)
 {
 	if (i >= a.nb)
 	{
-		a.keys[i] = ~0ull;
+		a.bkeys[i] = dead_key(i);
 		return;
 	}
 	SBody &b = a.bodies[i];
@@ -199,7 +218,7 @@ __device__ __forceinline__ void begin_body(const WideArgs &a, uint32_t i, float 
 	const uint32_t f = b.flags;
 	if (!(f & BF_ALIVE))
 	{
-		a.keys[i] = ~0ull;
+		a.bkeys[i] = dead_key(i);
 		return;
 	}
 	const float h = a.h;
@@ -221,10 +240,10 @@ __device__ __forceinline__ void begin_body(const WideArgs &a, uint32_t i, float 
 	body_aabb(b);
 	if (shape_of(f) == GPX_SHAPE_EMPTY)
 	{
-		a.keys[i] = ~0ull;
+		a.bkeys[i] = dead_key(i);
 		return;
 	}
-	a.keys[i] = 0ull;  // filled by kw_keys once the largest extents are known
+	a.bkeys[i] = 0ull;  // filled by kw_keys once the largest extents are known
 	ex = fmaxf(b.hi.x - b.lo.x, 0.0f);
 	ez = fmaxf(b.hi.z - b.lo.z, 0.0f);
 }
@@ -270,9 +289,52 @@ __device__ __forceinline__ unsigned long long sweep_key(uint32_t row, float lo_x
 __global__ void __launch_bounds__(WT) kw_keys(WideArgs a)
 {
 	const uint32_t i = blockIdx.x * WT + threadIdx.x;
-	if (i >= a.nb || a.keys[i] == ~0ull) return;
+	if (i >= a.nb || is_dead_key(a.bkeys[i])) return;
 	const SBody &b = a.bodies[i];
-	a.keys[i] = sweep_key(row_of(b.lo.z, row_thickness(a), i / a.cap, a.rows_per_world), b.lo.x, i);
+	a.bkeys[i] = sweep_key(row_of(b.lo.z, row_thickness(a), i / a.cap, a.rows_per_world), b.lo.x, i);
+}
+
+// ---- the sort, given the order of the last one
+// Bitonic sort of one tile of SORT_TILE keys in shared memory; tile t covers [offset + t * SORT_TILE, ...).  The first pass
+// (`order` given) reads this sub-step's keys in the order the last sort left the bodies in.  Run over the aligned tiles and
+// then over the tiles shifted by half a tile, this sorts any array whose keys are less than half a tile from their place;
+// kw_sorted_check says whether that was enough.
+constexpr uint32_t SORT_TILE = 2048;
+__global__ void __launch_bounds__(SORT_TILE / 2) kw_tile_sort(unsigned long long *keys, const unsigned long long *bkeys,
+															  const uint32_t *order, uint32_t n, uint32_t offset)
+{
+	__shared__ unsigned long long s[SORT_TILE];
+	const uint32_t base = offset + blockIdx.x * SORT_TILE, t = threadIdx.x;
+	for (uint32_t k = t; k < SORT_TILE; k += SORT_TILE / 2)
+		s[k] = base + k < n ? (order ? bkeys[order[base + k]] : keys[base + k]) : ~0ull;
+	__syncthreads();
+	for (uint32_t k = 2; k <= SORT_TILE; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+			const unsigned long long x = s[i], y = s[i | j];
+			if ((x > y) == ((i & k) == 0u))
+			{
+				s[i] = y;
+				s[i | j] = x;
+			}
+			__syncthreads();
+		}
+	for (uint32_t k = t; k < SORT_TILE; k += SORT_TILE / 2)
+		if (base + k < n) keys[base + k] = s[k];
+}
+
+__global__ void __launch_bounds__(WT) kw_sorted_check(WideArgs a)
+{
+	const uint32_t p = blockIdx.x * WT + threadIdx.x;
+	if (p + 1 < a.n_pad && a.keys[p] > a.keys[p + 1])
+		if (atomicExch(&a.cnt[WC_UNSORTED], 1u) == 0u) a.sort_fallbacks[0]++;
+}
+
+__global__ void kw_iota(uint32_t *v, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) v[i] = i;
 }
 
 __global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
@@ -280,12 +342,13 @@ __global__ void __launch_bounds__(WT) kw_gather(WideArgs a)
 	const uint32_t p = blockIdx.x * WT + threadIdx.x;
 	if (p >= a.n_pad) return;
 	const unsigned long long k = a.keys[p];
-	if (k == ~0ull)
+	const uint32_t i = (uint32_t)(k & 0xFFFFFull);
+	a.order[p] = i;
+	if (is_dead_key(k))
 	{
 		a.boxlo[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
 		return;
 	}
-	const uint32_t i = (uint32_t)(k & 0xFFFFFull);
 	const SBody &b = a.bodies[i];
 	a.boxlo[p] = F4(b.lo, __uint_as_float(i));
 	a.boxhi[p] = F4(b.hi, __uint_as_float(b.flags));
@@ -334,7 +397,7 @@ __global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
 	const uint32_t p = blockIdx.x * WT + threadIdx.x;
 	if (p >= a.n_pad) return;
 	const unsigned long long key_p = a.keys[p];
-	if (key_p == ~0ull) return;
+	if (is_dead_key(key_p)) return;
 	const float4 lo_p = a.boxlo[p], hi_p = a.boxhi[p];
 	const uint32_t ip = __float_as_uint(lo_p.w), fp = __float_as_uint(hi_p.w);
 	const uint32_t row = (uint32_t)(key_p >> 52);
@@ -343,7 +406,7 @@ __global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
 	for (uint32_t q = p + 1; q < a.n_pad; q++)
 	{
 		const unsigned long long kq = a.keys[q];
-		if (kq == ~0ull || (uint32_t)(kq >> 52) != row) break;
+		if (is_dead_key(kq) || (uint32_t)(kq >> 52) != row) break;
 		if (a.boxlo[q].x > reach) break;
 		sweep_test(a, lo_p, hi_p, ip, fp, q);
 	}
@@ -351,7 +414,7 @@ __global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
 	if (row + 1 >= (uint32_t)WIDE_ROWS) return;
 	const float back = (lo_p.x - __uint_as_float(a.cnt[WC_MAXEXT_X])) - (4.0f * SPECULATIVE_DISTANCE);
 	const unsigned long long want = sweep_key(row + 1, back, 0u);
-	uint32_t lo = p + 1, hi = a.n_pad;  // first q with keys[q] >= want (padding keys are ~0, so the array is sorted)
+	uint32_t lo = p + 1, hi = a.n_pad;  // first q with keys[q] >= want (dead keys sort last, so the array is sorted)
 	while (lo < hi)
 	{
 		const uint32_t mid = (lo + hi) >> 1;
@@ -361,7 +424,7 @@ __global__ void __launch_bounds__(WT) kw_sweep(WideArgs a)
 	for (uint32_t q = lo; q < a.n_pad; q++)
 	{
 		const unsigned long long kq = a.keys[q];
-		if (kq == ~0ull || (uint32_t)(kq >> 52) != row + 1) break;
+		if (is_dead_key(kq) || (uint32_t)(kq >> 52) != row + 1) break;
 		if (a.boxlo[q].x > reach) break;
 		sweep_test(a, lo_p, hi_p, ip, fp, q);
 	}
@@ -1416,7 +1479,9 @@ int wide_create(gpx_world *w)
 			  walloc(&d->isl_man, (size_t)d->isl_slots) && walloc(&d->big_list, d->cap_m) && walloc(&d->med_list, (size_t)d->med_slots) &&
 			  walloc(&d->med_coloff, (size_t)d->med_slots * (WIDE_MAXCOL + 1)) &&
 			  walloc(&d->keys_tmp, d->n_pad) && walloc(&d->sort_hist, (size_t)256 * (d->n_pad / 1024u + 1u)) &&
-			  walloc(&d->can_sleep, d->nb);
+			  walloc(&d->can_sleep, d->nb) && walloc(&d->order, d->n_pad) && walloc(&d->bkeys, d->n_pad) &&
+			  walloc(&d->sort_fallbacks, 1);
+	if (ok) kw_iota<<<(d->n_pad + 255u) / 256u, 256>>>(d->order, d->n_pad);
 	if (!ok)
 	{
 		set_error("wide_create", cudaGetLastError());
@@ -1438,6 +1503,8 @@ void wide_destroy(gpx_world *w)
 	WideDevice *d = w->wide;
 	if (!d) return;
 	cudaFree(d->bodies); cudaFree(d->keys); cudaFree(d->boxlo); cudaFree(d->boxhi); cudaFree(d->man[0]); cudaFree(d->man[1]);
+	if (d->graph) cudaGraphExecDestroy(d->graph);
+	cudaFree(d->order); cudaFree(d->bkeys); cudaFree(d->sort_fallbacks);
 	cudaFree(d->ord[0]); cudaFree(d->ord[1]); cudaFree(d->recs); cudaFree(d->counters); cudaFree(d->hkeys); cudaFree(d->hvals);
 	cudaFree(d->adj); cudaFree(d->adj_n); cudaFree(d->prio); cudaFree(d->pending); cudaFree(d->col_list);
 	cudaFree(d->parent); cudaFree(d->root_of); cudaFree(d->isl_cnt); cudaFree(d->isl_off); cudaFree(d->isl_cur);
@@ -1530,6 +1597,7 @@ int wide_counters(gpx_world *w, uint32_t *out8)
 	GPX_CUDA(cudaMemcpy(out8, w->wide->counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	GPX_CUDA(cudaMemcpy(out8 + WC_NPREV, w->wide->counters + WC_NISL, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	GPX_CUDA(cudaMemcpy(out8 + WC_UNCOLOURED, w->wide->counters + WC_NMED, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	GPX_CUDA(cudaMemcpy(out8 + WC_MAXEXT_X, w->wide->sort_fallbacks, sizeof(uint32_t), cudaMemcpyDeviceToHost));  // sub-steps that needed the radix passes
 	return GPX_OK;
 }
 
@@ -1552,17 +1620,21 @@ int wide_stats(gpx_world *w)
 	return GPX_OK;
 }
 
+static int record_wide_tick(gpx_world *w, WideArgs &a, float dt, int substeps);
+
 int launch_wide_tick(gpx_world *w, float dt, int substeps)
 {
 	WideDevice *d = w->wide;
 	cudaStream_t st = w->stream;
 	if (substeps < 1) substeps = 1;
-	// every tick reports its own errors (Jolt's Update returns that update's result): the error word starts clean
-	GPX_CUDA(cudaMemsetAsync(d->counters + WC_ERR, 0, sizeof(uint32_t), st));
 	WideArgs a;
+	memset(&a, 0, sizeof(a));
 	a.bs = w->bs;
 	a.bodies = d->bodies;
 	a.keys = d->keys;
+	a.order = d->order;
+	a.sort_fallbacks = d->sort_fallbacks;
+	a.bkeys = d->bkeys;
 	a.boxlo = d->boxlo;
 	a.boxhi = d->boxhi;
 	a.recs = d->recs;
@@ -1602,6 +1674,63 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 	a.gy = w->cfg.gravity[1];
 	a.gz = w->cfg.gravity[2];
 	a.h = dt / (float)substeps;
+	static const bool no_graph = getenv("GPX_WIDE_NO_GRAPH") != nullptr;
+	if (no_graph || d->graph_off) return record_wide_tick(w, a, dt, substeps);
+	// signature of the launch sequence: every kernel argument and everything that selects launches
+	struct { int substeps, cur; float dt; bool sleep; const void *ev, *ch_keys, *ch_nkeys, *ev_prev, *ev_nprev, *ev_count; } extra;
+	memset(&extra, 0, sizeof(extra));
+	extra.substeps = substeps;
+	extra.cur = d->cur;
+	extra.dt = dt;
+	extra.sleep = w->sleep_enabled;
+	extra.ev = w->d_ev_out;
+	extra.ch_keys = w->d_ch_keys;
+	extra.ch_nkeys = w->d_ch_nkeys;
+	extra.ev_prev = w->d_ev_prev;
+	extra.ev_nprev = w->d_ev_nprev;
+	extra.ev_count = w->d_ev_count;
+	unsigned char sig[sizeof(a) + sizeof(extra)];
+	static_assert(sizeof(sig) <= sizeof(d->graph_sig), "graph signature buffer");
+	memcpy(sig, &a, sizeof(a));
+	memcpy(sig + sizeof(a), &extra, sizeof(extra));
+	if (!d->graph || d->graph_sig_n != sizeof(sig) || memcmp(sig, d->graph_sig, sizeof(sig)) != 0)
+	{
+		if (d->graph) cudaGraphExecDestroy(d->graph);
+		d->graph = nullptr;
+		const int cur0 = d->cur;
+		const uint64_t l0 = gpx_launch_count();
+		cudaGraph_t g = nullptr;
+		bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+		const int rc = ok ? record_wide_tick(w, a, dt, substeps) : GPX_ERR_CUDA;
+		if (ok) ok = cudaStreamEndCapture(st, &g) == cudaSuccess && rc == GPX_OK && g;
+		if (ok) ok = cudaGraphInstantiate(&d->graph, g, 0) == cudaSuccess;
+		if (g) cudaGraphDestroy(g);
+		d->graph_launches = gpx_launch_count() - l0;
+		d->cur = cur0;
+		if (!ok)
+		{
+			// no graphs for this world from here on: plain launches
+			cudaGetLastError();
+			d->graph = nullptr;
+			d->graph_off = true;
+			return record_wide_tick(w, a, dt, substeps);
+		}
+		memcpy(d->graph_sig, sig, sizeof(sig));
+		d->graph_sig_n = sizeof(sig);
+	}
+	else
+		count_launch(d->graph_launches);
+	GPX_CUDA(cudaGraphLaunch(d->graph, st));
+	d->cur ^= substeps & 1;
+	return GPX_OK;
+}
+
+static int record_wide_tick(gpx_world *w, WideArgs &a, float dt, int substeps)
+{
+	WideDevice *d = w->wide;
+	cudaStream_t st = w->stream;
+	// every tick reports its own errors (Jolt's Update returns that update's result): the error word starts clean
+	GPX_CUDA(cudaMemsetAsync(d->counters + WC_ERR, 0, sizeof(uint32_t), st));
 	const uint32_t gb = (d->n_pad + WT - 1) / WT, gm = (d->cap_m + WT - 1) / WT;
 	for (int sub = 0; sub < substeps; sub++)
 	{
@@ -1617,10 +1746,32 @@ int launch_wide_tick(gpx_world *w, float dt, int substeps)
 		kw_begin<<<gb, WT, 0, st>>>(a);
 		kw_keys<<<gb, WT, 0, st>>>(a);
 		count_launch(2);
-		// keys arrive in body order with the body index in the low 20 bits: a stable sort of the bits above it is the
-		// full sort
-		if (d->n_pad >= 4096u) radix_sort_u64(d->keys, d->keys_tmp, d->sort_hist, d->n_pad, 20u, st);
-		else bitonic_sort_u64(d->keys, d->n_pad, st);
+		if (d->n_pad >= 4096u)
+		{
+			static const bool no_coherence = getenv("GPX_WIDE_NO_COHERENT_SORT") != nullptr;
+			if (!no_coherence)
+			{
+				// the keys in the last order, two passes of tile sorts; the radix sort (all 64 bits: the input is in no
+				// particular order below bit 20) runs only if that was not enough
+				kw_tile_sort<<<d->n_pad / SORT_TILE, SORT_TILE / 2, 0, st>>>(d->keys, d->bkeys, d->order, d->n_pad, 0u);
+				kw_tile_sort<<<d->n_pad / SORT_TILE - 1u, SORT_TILE / 2, 0, st>>>(d->keys, nullptr, nullptr, d->n_pad, SORT_TILE / 2);
+				kw_sorted_check<<<gb, WT, 0, st>>>(a);
+				count_launch(3);
+				radix_sort_u64(d->keys, d->keys_tmp, d->sort_hist, d->n_pad, 0u, st, d->counters + WC_UNSORTED);
+			}
+			else
+			{
+				// keys arrive in body order with the body index in the low 20 bits: a stable sort of the bits above it is
+				// the full sort
+				GPX_CUDA(cudaMemcpyAsync(d->keys, d->bkeys, sizeof(unsigned long long) * d->n_pad, cudaMemcpyDeviceToDevice, st));
+				radix_sort_u64(d->keys, d->keys_tmp, d->sort_hist, d->n_pad, 20u, st);
+			}
+		}
+		else
+		{
+			GPX_CUDA(cudaMemcpyAsync(d->keys, d->bkeys, sizeof(unsigned long long) * d->n_pad, cudaMemcpyDeviceToDevice, st));
+			bitonic_sort_u64(d->keys, d->n_pad, st);
+		}
 		kw_gather<<<gb, WT, 0, st>>>(a);
 		kw_sweep<<<gb, WT, 0, st>>>(a);
 		kw_pairs<<<(d->cap_m + NARROW_T - 1) / NARROW_T, NARROW_T, 0, st>>>(a);

@@ -40,5 +40,5 @@ launches = (g.L.gpx_launch_count() - l0) / ticks
 assert g.sync() == 0
 c = np.zeros(8, np.uint32)
 g.L.gpx_debug_wide_counters(g.h, c.ctypes.data)
-print("manifold slots", c[0], "small islands", c[1], "medium islands", c[4], "large-island manifolds", c[5], "colours", c[2], "error", c[3])
+print("manifold slots", c[0], "small islands", c[1], "medium islands", c[4], "large-island manifolds", c[5], "colours", c[2], "error", c[3], "sub-steps that needed the radix passes", c[6])
 print(f"{len(pos)} boxes: {ms:.3f} ms/tick, {len(pos) / ms * 1e3 / 1e6:.1f} M body-steps/s, {launches:.0f} launches/tick")
