@@ -295,11 +295,22 @@ __global__ void __launch_bounds__(WT) kw_keys(WideArgs a)
 }
 
 // ---- the sort, given the order of the last one
-// Bitonic sort of one tile of SORT_TILE keys in shared memory; tile t covers [offset + t * SORT_TILE, ...).  The first pass
-// (`order` given) reads this sub-step's keys in the order the last sort left the bodies in.  Run over the aligned tiles and
-// then over the tiles shifted by half a tile, this sorts any array whose keys are less than half a tile from their place;
-// kw_sorted_check says whether that was enough.
+// Sort of one tile of SORT_TILE keys in shared memory; tile t covers [offset + t * SORT_TILE, ...).  The first pass (`order`
+// given) reads this sub-step's keys in the order the last sort left the bodies in and sorts each aligned tile — most are
+// sorted as they come, which one comparison per key finds out; the rest take a bitonic sort.  The second pass runs over the
+// tiles shifted by half a tile: both halves of such a window are sorted by then, so it only has to merge them, and only
+// where the two keys in the middle are out of order.  Together they sort any array whose keys are less than half a tile
+// from their place; kw_sorted_check says whether that was enough.
 constexpr uint32_t SORT_TILE = 2048;
+__device__ __forceinline__ void tile_exchange(unsigned long long *s, uint32_t i, uint32_t l, bool ascending)
+{
+	const unsigned long long x = s[i], y = s[l];
+	if ((x > y) == ascending)
+	{
+		s[i] = y;
+		s[l] = x;
+	}
+}
 __global__ void __launch_bounds__(SORT_TILE / 2) kw_tile_sort(unsigned long long *keys, const unsigned long long *bkeys,
 															  const uint32_t *order, uint32_t n, uint32_t offset)
 {
@@ -308,18 +319,37 @@ __global__ void __launch_bounds__(SORT_TILE / 2) kw_tile_sort(unsigned long long
 	for (uint32_t k = t; k < SORT_TILE; k += SORT_TILE / 2)
 		s[k] = base + k < n ? (order ? bkeys[order[base + k]] : keys[base + k]) : ~0ull;
 	__syncthreads();
-	for (uint32_t k = 2; k <= SORT_TILE; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+	const bool merge_only = order == nullptr;
+	bool unsorted;
+	if (merge_only)
+		unsorted = s[SORT_TILE / 2 - 1] > s[SORT_TILE / 2];  // the same answer in every thread
+	else
+		unsorted = __syncthreads_or((s[2 * t] > s[2 * t + 1]) || (2 * t + 2 < SORT_TILE && s[2 * t + 1] > s[2 * t + 2]));
+	if (unsorted)
+	{
+		if (merge_only)
 		{
-			const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
-			const unsigned long long x = s[i], y = s[i | j];
-			if ((x > y) == ((i & k) == 0u))
-			{
-				s[i] = y;
-				s[i | j] = x;
-			}
+			// bitonic merge of two ascending halves: mirror step, then the half-cleaners
+			tile_exchange(s, t, SORT_TILE - 1u - t, true);
 			__syncthreads();
+			for (uint32_t j = SORT_TILE >> 2; j > 0; j >>= 1)
+			{
+				const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+				tile_exchange(s, i, i | j, true);
+				__syncthreads();
+			}
 		}
+		else
+			for (uint32_t k = 2; k <= SORT_TILE; k <<= 1)
+				for (uint32_t j = k >> 1; j > 0; j >>= 1)
+				{
+					const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+					tile_exchange(s, i, i | j, (i & k) == 0u);
+					__syncthreads();
+				}
+	}
+	else if (merge_only)
+		return;  // in place already
 	for (uint32_t k = t; k < SORT_TILE; k += SORT_TILE / 2)
 		if (base + k < n) keys[base + k] = s[k];
 }
