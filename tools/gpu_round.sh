@@ -18,4 +18,8 @@ $Q > $out/${tag}_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_tick -s 20 -c 2 -o $out/${tag}_tick $Q > $out/${tag}_ncu2.log 2>&1
 $Q > $out/${tag}_plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_raycast -s 20 -c 1 -o $out/${tag}_rays $Q > $out/${tag}_ncu3.log 2>&1
+# launch list of the wide tick (plain launches instead of the graph, so every kernel is listed; the last ticks are settled)
+python tools/wide_profile.py 100 10 100 60 > $out/${tag}_wide.txt 2>&1 && \
+GPX_WIDE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_wide_launches_all.csv python tools/wide_profile.py 100 10 100 30 > $out/${tag}_ncu4.log 2>&1
+tail -n 90 $out/${tag}_wide_launches_all.csv > $out/${tag}_wide_launches.csv; rm -f $out/${tag}_wide_launches_all.csv
 tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench.json | cut -c1-600; tail -2 $out/${tag}_bench.err
