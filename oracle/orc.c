@@ -126,6 +126,7 @@ typedef struct
 
 struct orc_world
 {
+	uint32_t free_hint;  /* body slots below it are all alive */
 	uint32_t max_bodies, max_manifolds, vel_steps, pos_steps;
 	v3 gravity;
 	body_t *bodies;
@@ -253,14 +254,16 @@ uint32_t orc_static_triangles(const orc_world *w, float *out9, uint32_t *out_bod
 
 uint32_t orc_body_create(orc_world *w, const orc_body_desc *d)
 {
+	/* the lowest free slot; every slot below free_hint is known to be taken */
 	uint32_t id = ORC_INVALID;
-	for (uint32_t i = 0; i < w->max_bodies; i++)
+	for (uint32_t i = w->free_hint; i < w->max_bodies; i++)
 		if (!w->bodies[i].alive)
 		{
 			id = i;
 			break;
 		}
 	if (id == ORC_INVALID) return id;
+	w->free_hint = id + 1;
 	body_t *b = &w->bodies[id];
 	memset(b, 0, sizeof(*b));
 	b->alive = 1;
@@ -313,7 +316,9 @@ uint32_t orc_body_create(orc_world *w, const orc_body_desc *d)
 
 void orc_body_destroy(orc_world *w, uint32_t id)
 {
-	if (id < w->max_bodies) w->bodies[id].alive = 0;
+	if (id >= w->max_bodies) return;
+	w->bodies[id].alive = 0;
+	if (id < w->free_hint) w->free_hint = id;
 }
 
 static void wake_body(body_t *b)
@@ -1339,11 +1344,53 @@ static int u64_cmp(const void *a, const void *b)
 	const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
 	return x < y ? -1 : x > y;
 }
-/* returns the sorted candidate pairs (i << 32 | j), *first[i] = index of body i's first pair, first[max_bodies] = count */
-static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out)
+/* the sweep proper over sorted positions [lo, hi) of slice k: pairs (min << 32 | max) into the slice's own list */
+typedef struct
+{
+	uint32_t n, nslices;
+	float m;
+	const sweep_key_t *keys;
+	const v3 *slo, *shi;
+	uint64_t **pairs;
+	size_t *cnt;
+} sweep_t;
+static void sweep_slices(void *ctx, int64_t k0, int64_t k1)
+{
+	sweep_t *S = (sweep_t *)ctx;
+	const float m = S->m;
+	for (int64_t k = k0; k < k1; k++)
+	{
+		const uint32_t p0 = (uint32_t)((uint64_t)S->n * k / S->nslices), p1 = (uint32_t)((uint64_t)S->n * (k + 1) / S->nslices);
+		size_t cap = 4 * (size_t)(p1 - p0) + 64, cnt = 0;
+		uint64_t *pairs = (uint64_t *)malloc(sizeof(uint64_t) * cap);
+		for (uint32_t p = p0; p < p1; p++)
+		{
+			const uint32_t a = S->keys[p].id;
+			const v3 alo = S->slo[p], ahi = S->shi[p];
+			const float reach = ahi.x + m;
+			for (uint32_t q = p + 1; q < S->n && S->slo[q].x <= reach; q++)
+			{
+				if (alo.z - m > S->shi[q].z || S->slo[q].z - m > ahi.z || alo.y - m > S->shi[q].y || S->slo[q].y - m > ahi.y) continue;
+				const uint32_t b = S->keys[q].id;
+				if (cnt == cap)
+				{
+					cap *= 2;
+					pairs = (uint64_t *)realloc(pairs, sizeof(uint64_t) * cap);
+				}
+				pairs[cnt++] = a < b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a;
+			}
+		}
+		S->pairs[k] = pairs;
+		S->cnt[k] = cnt;
+	}
+}
+static void pool_for(int64_t n, void (*fn)(void *, int64_t, int64_t), void *ctx, int64_t grain);
+
+/* returns the sorted candidate pairs (i << 32 | j), *first[i] = index of body i's first pair, first[max_bodies] = count;
+ * threaded: the sweep runs in slices over the host threads (orc_step_mt) */
+static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out, int threaded)
 {
 	const uint32_t nb = w->max_bodies;
-	const float m = 2.0f * SPECULATIVE_DISTANCE + 1e-3f;
 	v3 *lo = (v3 *)malloc(sizeof(v3) * nb), *hi = (v3 *)malloc(sizeof(v3) * nb);
 	sweep_key_t *keys = (sweep_key_t *)malloc(sizeof(sweep_key_t) * nb);
 	uint32_t n = 0;
@@ -1356,22 +1403,28 @@ static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out)
 		keys[n++].id = i;
 	}
 	qsort(keys, n, sizeof(sweep_key_t), sweep_key_cmp);
-	size_t cap = 4 * (size_t)n + 64, cnt = 0;
-	uint64_t *pairs = (uint64_t *)malloc(sizeof(uint64_t) * cap);
+	/* the boxes once more in sorted order: the sweep walks them front to back */
+	v3 *slo = (v3 *)malloc(sizeof(v3) * (n + 1)), *shi = (v3 *)malloc(sizeof(v3) * (n + 1));
 	for (uint32_t p = 0; p < n; p++)
 	{
-		const uint32_t a = keys[p].id;
-		for (uint32_t q = p + 1; q < n && keys[q].lo <= hi[a].x + m; q++)
-		{
-			const uint32_t b = keys[q].id;
-			if (lo[a].y - m > hi[b].y || lo[b].y - m > hi[a].y || lo[a].z - m > hi[b].z || lo[b].z - m > hi[a].z) continue;
-			if (cnt == cap)
-			{
-				cap *= 2;
-				pairs = (uint64_t *)realloc(pairs, sizeof(uint64_t) * cap);
-			}
-			pairs[cnt++] = a < b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a;
-		}
+		slo[p] = lo[keys[p].id];
+		shi[p] = hi[keys[p].id];
+	}
+	enum { MAX_SLICES = 256 };
+	uint64_t *slice_pairs[MAX_SLICES];
+	size_t slice_cnt[MAX_SLICES];
+	sweep_t S = {n, threaded ? MAX_SLICES : 1, 2.0f * SPECULATIVE_DISTANCE + 1e-3f, keys, slo, shi, slice_pairs, slice_cnt};
+	if (threaded) pool_for(S.nslices, sweep_slices, &S, 2);
+	else sweep_slices(&S, 0, 1);
+	size_t cnt = 0;
+	for (uint32_t k = 0; k < S.nslices; k++) cnt += slice_cnt[k];
+	uint64_t *pairs = (uint64_t *)malloc(sizeof(uint64_t) * (cnt + 1));
+	cnt = 0;
+	for (uint32_t k = 0; k < S.nslices; k++)
+	{
+		memcpy(pairs + cnt, slice_pairs[k], sizeof(uint64_t) * slice_cnt[k]);
+		cnt += slice_cnt[k];
+		free(slice_pairs[k]);
 	}
 	qsort(pairs, cnt, sizeof(uint64_t), u64_cmp);
 	uint32_t *first = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)nb + 1));
@@ -1381,6 +1434,8 @@ static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out)
 		while (k < cnt && (uint32_t)(pairs[k] >> 32) < i) k++;
 		first[i] = (uint32_t)k;
 	}
+	free(slo);
+	free(shi);
 	free(lo);
 	free(hi);
 	free(keys);
@@ -1388,11 +1443,10 @@ static uint64_t *sweep_candidates(const orc_world *w, uint32_t **first_out)
 	return pairs;
 }
 
-static void find_contacts_among(orc_world *w, int *err, const uint64_t *cand, const uint32_t *cand_first)
+/* contacts whose first body lies in [i0, i1), appended to w->man / w->sens */
+static void find_contacts_among(orc_world *w, int *err, const uint64_t *cand, const uint32_t *cand_first, uint32_t i0, uint32_t i1)
 {
-	w->nman = 0;
-	w->nsens = 0;
-	for (uint32_t i = 0; i < w->max_bodies; i++)
+	for (uint32_t i = i0; i < i1; i++)
 	{
 		body_t *A = &w->bodies[i];
 		if (!A->alive || A->shape == ORC_SHAPE_EMPTY) continue;
@@ -1525,14 +1579,17 @@ static void find_contacts_among(orc_world *w, int *err, const uint64_t *cand, co
 static void find_contacts(orc_world *w, int *err)
 {
 	uint32_t *cand_first = NULL;
-	uint64_t *cand = w->max_bodies > SWEEP_MIN_BODIES ? sweep_candidates(w, &cand_first) : NULL;
-	find_contacts_among(w, err, cand, cand_first);
+	uint64_t *cand = w->max_bodies > SWEEP_MIN_BODIES ? sweep_candidates(w, &cand_first, 0) : NULL;
+	w->nman = 0;
+	w->nsens = 0;
+	find_contacts_among(w, err, cand, cand_first, 0, w->max_bodies);
 	free(cand);
 	free(cand_first);
 }
 
 /* ------------------------------------------------------------------------------------------ solver */
 
+static void warm_start_match_range(orc_world *w, const uint32_t *run, uint32_t lo, uint32_t hi);
 static void warm_start_match(orc_world *w)
 {
 	/* both lists are in canonical order (body a ascending), so the old manifolds of body a are one contiguous run */
@@ -1542,7 +1599,13 @@ static void warm_start_match(orc_world *w)
 		while (j < w->nprev && w->prev[j].a < a) j++;
 		run[a] = j;
 	}
-	for (uint32_t i = 0; i < w->nman; i++)
+	warm_start_match_range(w, run, 0, w->nman);
+	free(run);
+}
+
+static void warm_start_match_range(orc_world *w, const uint32_t *run, uint32_t lo, uint32_t hi)
+{
+	for (uint32_t i = lo; i < hi; i++)
 	{
 		manifold_t *m = &w->man[i];
 		int got_cf = 0;
@@ -1571,7 +1634,6 @@ static void warm_start_match(orc_world *w)
 			}
 		}
 	}
-	free(run);
 }
 
 static int colour_manifolds(orc_world *w)
@@ -2166,6 +2228,40 @@ static void sleep_pass(orc_world *w, float dt)
 	free(can);
 }
 
+/* gravity, damping, velocity clamps and the world-space inverse inertia of bodies [lo, hi) */
+static void apply_forces(orc_world *w, float h, uint32_t lo, uint32_t hi)
+{
+	for (uint32_t i = lo; i < hi; i++)
+	{
+		body_t *b = &w->bodies[i];
+		if (!b->alive) continue;
+		if (is_dyn(b))
+		{
+			b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
+			b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
+			b->w = vscale(b->w, fmaxf(0.0f, 1.0f - (b->ang_damp * h)));
+			b->v = clamp_len(mask_lin(b->dofs, b->v), MAX_LINEAR_VELOCITY);
+			v3 ww = b->w;
+			if (!(b->dofs & 8u)) ww.x = 0.0f;
+			if (!(b->dofs & 16u)) ww.y = 0.0f;
+			if (!(b->dofs & 32u)) ww.z = 0.0f;
+			b->w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
+		}
+		body_world_inertia(b);
+	}
+}
+
+static void integrate_positions(orc_world *w, float h, uint32_t lo, uint32_t hi)
+{
+	for (uint32_t i = lo; i < hi; i++)
+	{
+		body_t *b = &w->bodies[i];
+		if (!b->alive || b->motion == ORC_MOTION_STATIC || b->asleep) continue;
+		b->x = vadd(b->x, vscale(b->v, h));
+		b->q = qstep(b->q, vscale(b->w, h));
+	}
+}
+
 int orc_step(orc_world *w, float dt, int collision_steps)
 {
 	int err = 0;
@@ -2173,24 +2269,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 	const float h = dt / (float)collision_steps;
 	for (int s = 0; s < collision_steps; s++)
 	{
-		for (uint32_t i = 0; i < w->max_bodies; i++)
-		{
-			body_t *b = &w->bodies[i];
-			if (!b->alive) continue;
-			if (is_dyn(b))
-			{
-				b->v = vadd(b->v, vscale(w->gravity, h * b->grav_factor));
-				b->v = vscale(b->v, fmaxf(0.0f, 1.0f - (b->lin_damp * h)));
-				b->w = vscale(b->w, fmaxf(0.0f, 1.0f - (b->ang_damp * h)));
-				b->v = clamp_len(mask_lin(b->dofs, b->v), MAX_LINEAR_VELOCITY);
-				v3 ww = b->w;
-				if (!(b->dofs & 8u)) ww.x = 0.0f;
-				if (!(b->dofs & 16u)) ww.y = 0.0f;
-				if (!(b->dofs & 32u)) ww.z = 0.0f;
-				b->w = clamp_len(ww, MAX_ANGULAR_VELOCITY);
-			}
-			body_world_inertia(b);
-		}
+		apply_forces(w, h, 0, w->max_bodies);
 		find_contacts(w, &err);
 		warm_start_match(w);
 		if (w->mode == 1) colour_manifolds_jp(w);
@@ -2199,13 +2278,7 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t k = 0; k < w->nman; k++) warm_start(w, &w->man[w->order[k]]);
 		for (uint32_t it = 0; it < w->vel_steps; it++)
 			for (uint32_t k = 0; k < w->nman; k++) solve_velocity(w, &w->man[w->order[k]], it);
-		for (uint32_t i = 0; i < w->max_bodies; i++)
-		{
-			body_t *b = &w->bodies[i];
-			if (!b->alive || b->motion == ORC_MOTION_STATIC || b->asleep) continue;
-			b->x = vadd(b->x, vscale(b->v, h));
-			b->q = qstep(b->q, vscale(b->w, h));
-		}
+		integrate_positions(w, h, 0, w->max_bodies);
 		for (uint32_t it = 0; it < w->pos_steps; it++)
 			for (uint32_t k = 0; k < w->nman; k++) solve_position(w, &w->man[w->order[k]]);
 		manifold_t *t = w->prev;
@@ -2216,6 +2289,250 @@ int orc_step(orc_world *w, float dt, int collision_steps)
 		for (uint32_t i = 0; i < w->max_bodies; i++)
 			if (w->bodies[i].alive && w->bodies[i].wake_mark) wake_body(&w->bodies[i]);
 	}
+	sleep_pass(w, dt);
+	make_events(w);
+	return err;
+}
+
+/* ---- orc_step over host threads: the CPU baseline bench.py quotes for ONE large world (mode 1).  Same stages, same
+ * arithmetic; what runs side by side is what cannot interact: bodies, the contacts of disjoint ranges of first bodies
+ * (gathered in range order, so the manifold list is the one orc_step builds), manifolds of one colour (they share no
+ * dynamic body).  tests/test_oracle.py holds it to orc_step's bits. */
+typedef struct
+{
+	orc_world *w;
+	float h;
+	uint32_t it;
+	int stage;
+	uint32_t lo, hi;            /* slice of `order` for the colour stages */
+	const uint64_t *cand;
+	const uint32_t *cand_first;
+	orc_world *shadow;          /* per slot: a copy of the world header with its own manifold / sensor buffers */
+	int *slot_err;
+	int nslots;
+	const uint32_t *run;        /* warm-start match: first old manifold per body */
+} mtjob_t;
+enum { ST_FORCES, ST_CONTACTS, ST_MATCH, ST_SETUP, ST_WARM, ST_VEL, ST_INTEGRATE, ST_POS };
+
+static void mt_range(void *ctx, int64_t lo, int64_t hi)
+{
+	mtjob_t *j = (mtjob_t *)ctx;
+	orc_world *w = j->w;
+	switch (j->stage)
+	{
+	case ST_FORCES: apply_forces(w, j->h, (uint32_t)lo, (uint32_t)hi); break;
+	case ST_INTEGRATE: integrate_positions(w, j->h, (uint32_t)lo, (uint32_t)hi); break;
+	case ST_CONTACTS:
+		/* [lo, hi) are slots: slot k owns the bodies [k, k + 1) * max_bodies / nslots */
+		for (int64_t k = lo; k < hi; k++)
+		{
+			orc_world *t = &j->shadow[k];
+			t->nman = 0;
+			t->nsens = 0;
+			j->slot_err[k] = 0;
+			find_contacts_among(t, &j->slot_err[k], j->cand, j->cand_first, (uint32_t)((uint64_t)w->max_bodies * k / j->nslots),
+								(uint32_t)((uint64_t)w->max_bodies * (k + 1) / j->nslots));
+		}
+		break;
+	case ST_MATCH: warm_start_match_range(w, j->run, (uint32_t)lo, (uint32_t)hi); break;
+	case ST_SETUP:
+		for (int64_t k = lo; k < hi; k++) setup_manifold(w, &w->man[k], j->h);
+		break;
+	case ST_WARM:
+		for (int64_t k = lo; k < hi; k++) warm_start(w, &w->man[w->order[j->lo + k]]);
+		break;
+	case ST_VEL:
+		for (int64_t k = lo; k < hi; k++) solve_velocity(w, &w->man[w->order[j->lo + k]], j->it);
+		break;
+	case ST_POS:
+		for (int64_t k = lo; k < hi; k++) solve_position(w, &w->man[w->order[j->lo + k]]);
+		break;
+	}
+}
+
+/* a persistent pool: parallel_for's thread-per-call start-up would dominate the hundred colour phases of a tick */
+typedef struct
+{
+	pthread_t th[256];
+	int nt, started;
+	pthread_mutex_t mu;
+	pthread_cond_t go, done;
+	uint64_t gen;
+	int pending;
+	void (*fn)(void *, int64_t, int64_t);
+	void *ctx;
+	int64_t n;
+} pool_t;
+static pool_t g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .go = PTHREAD_COND_INITIALIZER, .done = PTHREAD_COND_INITIALIZER};
+
+static void *pool_main(void *arg)
+{
+	const int t = (int)(intptr_t)arg;
+	uint64_t seen = 0;
+	for (;;)
+	{
+		pthread_mutex_lock(&g_pool.mu);
+		while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+		seen = g_pool.gen;
+		void (*fn)(void *, int64_t, int64_t) = g_pool.fn;
+		void *ctx = g_pool.ctx;
+		const int64_t n = g_pool.n;
+		pthread_mutex_unlock(&g_pool.mu);
+		const int64_t lo = n * t / g_pool.nt, hi = n * (t + 1) / g_pool.nt;
+		if (hi > lo) fn(ctx, lo, hi);
+		pthread_mutex_lock(&g_pool.mu);
+		if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.done);
+		pthread_mutex_unlock(&g_pool.mu);
+	}
+	return NULL;
+}
+
+/* fn over [0, n) in one slice per thread; fewer than `grain` items are not worth a wake-up */
+static void pool_for(int64_t n, void (*fn)(void *, int64_t, int64_t), void *ctx, int64_t grain)
+{
+	if (!g_pool.started)
+	{
+		g_pool.nt = orc_max_threads();
+		if (g_pool.nt > 256) g_pool.nt = 256;
+		for (int t = 1; t < g_pool.nt; t++) pthread_create(&g_pool.th[t], NULL, pool_main, (void *)(intptr_t)t);
+		g_pool.started = 1;
+	}
+	if (n < grain || g_pool.nt == 1)
+	{
+		if (n > 0) fn(ctx, 0, n);
+		return;
+	}
+	pthread_mutex_lock(&g_pool.mu);
+	g_pool.fn = fn;
+	g_pool.ctx = ctx;
+	g_pool.n = n;
+	g_pool.pending = g_pool.nt - 1;
+	g_pool.gen++;
+	pthread_cond_broadcast(&g_pool.go);
+	pthread_mutex_unlock(&g_pool.mu);
+	const int64_t hi = n / g_pool.nt;  /* slice 0 is the caller's */
+	if (hi > 0) fn(ctx, 0, hi);
+	pthread_mutex_lock(&g_pool.mu);
+	while (g_pool.pending) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+	pthread_mutex_unlock(&g_pool.mu);
+}
+
+int orc_step_mt(orc_world *w, float dt, int collision_steps)
+{
+	if (w->mode != 1) return orc_step(w, dt, collision_steps);
+	int err = 0;
+	if (collision_steps < 1) collision_steps = 1;
+	const float h = dt / (float)collision_steps;
+	const int nslots = 4 * orc_max_threads() < 1024 ? 4 * orc_max_threads() : 1024;
+	orc_world *shadow = (orc_world *)malloc(sizeof(orc_world) * nslots);
+	const uint32_t slot_cap = 4u * (w->max_manifolds / (uint32_t)nslots) + 1024u;
+	int *slot_err = (int *)calloc((size_t)nslots, sizeof(int));
+	for (int k = 0; k < nslots; k++)
+	{
+		shadow[k] = *w;
+		shadow[k].max_manifolds = slot_cap;
+		shadow[k].man = (manifold_t *)malloc(sizeof(manifold_t) * slot_cap);
+		shadow[k].sens = (uint64_t *)malloc(sizeof(uint64_t) * slot_cap);
+	}
+	mtjob_t j;
+	memset(&j, 0, sizeof(j));
+	j.w = w;
+	j.h = h;
+	j.shadow = shadow;
+	j.slot_err = slot_err;
+	j.nslots = nslots;
+	for (int s = 0; s < collision_steps; s++)
+	{
+		j.stage = ST_FORCES;
+		pool_for(w->max_bodies, mt_range, &j, 2048);
+		/* contacts: the candidate sweep in slices of sorted positions, the narrowphase per slot of first bodies */
+		uint32_t *cand_first = NULL;
+		uint64_t *cand = w->max_bodies > SWEEP_MIN_BODIES ? sweep_candidates(w, &cand_first, 1) : NULL;
+		for (int k = 0; k < nslots; k++)
+		{
+			shadow[k].bodies = w->bodies;
+			shadow[k].prev = w->prev;
+			shadow[k].nprev = w->nprev;
+		}
+		j.cand = cand;
+		j.cand_first = cand_first;
+		j.stage = ST_CONTACTS;
+		pool_for(nslots, mt_range, &j, 2);
+		free(cand);
+		free(cand_first);
+		w->nman = 0;
+		w->nsens = 0;
+		int crowded = 0;
+		for (int k = 0; k < nslots; k++) crowded |= slot_err[k] != 0;
+		for (int k = 0; k < nslots && !crowded; k++)
+		{
+			if (w->nman + shadow[k].nman > w->max_manifolds)
+			{
+				err = 4;
+				break;
+			}
+			memcpy(&w->man[w->nman], shadow[k].man, sizeof(manifold_t) * shadow[k].nman);
+			w->nman += shadow[k].nman;
+			for (uint32_t q = 0; q < shadow[k].nsens && w->nsens < w->max_manifolds; q++) w->sens[w->nsens++] = shadow[k].sens[q];
+		}
+		if (crowded) find_contacts(w, &err);  /* a slot's share of the manifold buffer was too small: the serial search */
+		/* warm-start match over manifolds */
+		uint32_t *run = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)w->max_bodies + 1));
+		for (uint32_t a = 0, q = 0; a <= w->max_bodies; a++)
+		{
+			while (q < w->nprev && w->prev[q].a < a) q++;
+			run[a] = q;
+		}
+		j.run = run;
+		j.stage = ST_MATCH;
+		pool_for(w->nman, mt_range, &j, 2048);
+		free(run);
+		colour_manifolds_jp(w);
+		j.stage = ST_SETUP;
+		pool_for(w->nman, mt_range, &j, 2048);
+		/* colour ranges of `order` (colour-major); the last colour may hold manifolds that share a body: serial */
+		uint32_t start[66];
+		int ncol = 0;
+		for (uint32_t k = 0; k < w->nman; k++)
+		{
+			const int c = w->man[w->order[k]].colour;
+			while (ncol <= c) start[ncol++] = k;
+		}
+		start[ncol] = w->nman;
+		for (int pass = 0; pass < 2 + (int)w->vel_steps + (int)w->pos_steps; pass++)
+		{
+			if (pass == 1 + (int)w->vel_steps)
+			{
+				j.stage = ST_INTEGRATE;
+				pool_for(w->max_bodies, mt_range, &j, 2048);
+				continue;
+			}
+			j.stage = pass == 0 ? ST_WARM : (pass <= (int)w->vel_steps ? ST_VEL : ST_POS);
+			j.it = pass >= 1 && pass <= (int)w->vel_steps ? (uint32_t)(pass - 1) : 0u;
+			for (int c = 0; c < ncol; c++)
+			{
+				j.lo = start[c];
+				j.hi = start[c + 1];
+				if (c == 63)
+					mt_range(&j, 0, (int64_t)(j.hi - j.lo));
+				else
+					pool_for((int64_t)(j.hi - j.lo), mt_range, &j, 1024);
+			}
+		}
+		manifold_t *t = w->prev;
+		w->prev = w->man;
+		w->man = t;
+		w->nprev = w->nman;
+		for (uint32_t i = 0; i < w->max_bodies; i++)
+			if (w->bodies[i].alive && w->bodies[i].wake_mark) wake_body(&w->bodies[i]);
+	}
+	for (int k = 0; k < nslots; k++)
+	{
+		free(shadow[k].man);
+		free(shadow[k].sens);
+	}
+	free(shadow);
+	free(slot_err);
 	sleep_pass(w, dt);
 	make_events(w);
 	return err;

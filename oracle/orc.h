@@ -92,6 +92,8 @@ uint32_t orc_body_asleep(const orc_world *w, uint32_t id);
 void orc_body_set_ray_flags(orc_world *w, uint32_t id, uint32_t ray_flags);
 /* one tick = collision_steps sub-steps of dt/collision_steps; returns 0 or an error code (4 = contact constraints full) */
 int orc_step(orc_world *w, float dt, int collision_steps);
+/* the same tick over host threads (wide mode only; any other world takes orc_step): bit-identical to orc_step */
+int orc_step_mt(orc_world *w, float dt, int collision_steps);
 /* state access: out = 7 floats pos+quat, 6 floats lin+ang */
 void orc_body_get(const orc_world *w, uint32_t id, float *xf7, float *vel6);
 uint32_t orc_body_active(const orc_world *w, uint32_t id);

@@ -119,6 +119,8 @@ def lib():
     L.orc_body_asleep.restype = C.c_uint32
     L.orc_step.restype = C.c_int
     L.orc_step.argtypes = [C.c_void_p, C.c_float, C.c_int]
+    L.orc_step_mt.restype = C.c_int
+    L.orc_step_mt.argtypes = [C.c_void_p, C.c_float, C.c_int]
     L.orc_body_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.orc_character_create.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float]
     L.orc_character_destroy.argtypes = [C.c_void_p]
@@ -207,6 +209,10 @@ class World:
 
     def step(self, dt=1.0 / 60.0, collision_steps=2) -> int:
         return self.L.orc_step(self.h, dt, collision_steps)
+
+    def step_mt(self, dt=1.0 / 60.0, collision_steps=2) -> int:
+        """The same tick over host threads (wide mode); bit-identical to step()."""
+        return self.L.orc_step_mt(self.h, dt, collision_steps)
 
     def get(self, bid: int):
         xf = np.zeros(7, np.float32)

@@ -555,3 +555,39 @@ def test_sweep_candidates_reproduce_the_all_pairs_loop(orc, scenes):
         assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)), f"tick {tick}"
         assert np.array_equal(va.view(np.uint32), vb.view(np.uint32)), f"tick {tick}"
     assert seen > 150            # the pile really is in contact
+
+
+def test_threaded_step_reproduces_the_serial_step(orc, scenes):
+    """orc_step_mt (bench.py's CPU baseline for the one large world) against orc_step: a gas of 6000 spheres and boxes
+    that collide all over the place, and a lattice that lands in columns — the same bits, tick after tick."""
+    rng = np.random.default_rng(11)
+    n = 6000
+    pos = rng.uniform(-12.0, 12.0, (n, 3)).astype(np.float32)
+    pos[:, 1] -= 490.0
+    vel = rng.uniform(-6.0, 6.0, (n, 3)).astype(np.float32)
+    lat = scenes.lattice_positions(24, 6, 24)
+    for kind in ("gas", "lattice"):
+        worlds = []
+        for _ in range(2):
+            count = n if kind == "gas" else len(lat)
+            o = orc.World(count, gravity=(0.0, 0.0, 0.0) if kind == "gas" else (0.0, -9.81, 0.0))
+            for p, t in scenes.box_map():
+                o.add_mesh(p, t)
+            for i in range(count):
+                if kind == "gas":
+                    o.create(orc.body_desc(position=tuple(pos[i]), linear_velocity=tuple(vel[i]), shape=2 if i % 3 == 0 else 1,
+                                           half_extents=(0.15, 0.15, 0.15), linear_damping=0.0, allow_sleeping=1))
+                else:
+                    o.create(orc.body_desc(position=tuple(lat[i]), allow_sleeping=1))
+            worlds.append((o, count))
+        (a, count), (b, _) = worlds
+        contacts = 0
+        for tick in range(30):
+            assert a.step() == 0 and b.step_mt() == 0
+            contacts = max(contacts, a.L.orc_manifold_count(a.h))
+            assert a.L.orc_manifold_count(a.h) == b.L.orc_manifold_count(b.h)
+            xa, va = a.state(count)
+            xb, vb = b.state(count)
+            assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)), f"{kind} tick {tick}"
+            assert np.array_equal(va.view(np.uint32), vb.view(np.uint32)), f"{kind} tick {tick}"
+        assert contacts > 100
