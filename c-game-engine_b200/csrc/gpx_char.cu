@@ -363,6 +363,7 @@ __device__ __forceinline__ void ch_push_body(const CharArgs &a, uint32_t g, v3 n
 // deepest penetration, push the capsule out along that normal and remove the velocity component into it; ground state from
 // the contact normals.  `push`: dynamic bodies in the way get the character's contact impulse.  `blocked`: some contact
 // too steep to walk on faces the motion direction `dir` within the angle whose cosine is cos_fwd.
+constexpr int CH_MAX_PIECES = 16;  // pieces of one tick's move: 2 m per tick, 120 m/s
 struct Slide
 {
 	v3 x, v, ground_n;
@@ -370,7 +371,7 @@ struct Slide
 	bool blocked;
 };
 
-__device__ __forceinline__ Slide ch_slide(const CharArgs &a, uint32_t world, const CharDev &ch, v3 x, v3 v, bool push, v3 dir, float cos_fwd,
+__device__ __forceinline__ Slide ch_slide(const CharArgs &a, uint32_t world, const CharDev &ch, v3 x, v3 v, float dt, bool push, v3 dir, float cos_fwd,
 										  int *cand_orig, int *cand_leaf, int *s_nc, uint32_t &err, int lane)
 {
 	Slide s;
@@ -384,7 +385,7 @@ __device__ __forceinline__ Slide ch_slide(const CharArgs &a, uint32_t world, con
 		if (!(d.pen > 0.0f)) break;
 		if (push && d.body < STATIC_BODY_BASE)
 		{
-			ch_push_body(a, world * a.cap + d.body, d.n, d.pen, d.cp, v, a.dt, lane);
+			ch_push_body(a, world * a.cap + d.body, d.n, d.pen, d.cp, v, dt, lane);
 			__syncwarp();  // the next round reads the body's new velocity
 		}
 		x = x + (d.n * d.pen);
@@ -447,8 +448,21 @@ __global__ void __launch_bounds__(128) k_character(CharArgs a)
 	const v3 want = V(v_in.x * a.dt, 0.0f, v_in.z * a.dt);
 	const float want_len = sqrtf((want.x * want.x) + (want.z * want.z));
 	const v3 dir = want_len > 0.0f ? V(want.x / want_len, 0.0f, want.z / want_len) : V(0.0f, 0.0f, 0.0f);
-	const Slide m = ch_slide(a, world, ch, x_old + (v_in * a.dt), v_in, true, dir, cfg.walk_stairs_cos_angle_forward_contact, s_orig[wib],
-							 s_leaf[wib], &s_nc[wib], err, lane);
+	// swept motion, restated on the discrete test: the move in pieces no longer than half the capsule's radius, each
+	// collided and slid before the next, so that no floor or wall is stepped over (one piece up to 7.5 m/s)
+	const float travel = len(v_in * a.dt);
+	int pieces = (int)ceilf(travel / (0.5f * r));
+	pieces = pieces < 1 ? 1 : (pieces > CH_MAX_PIECES ? CH_MAX_PIECES : pieces);
+	const float pdt = a.dt / (float)pieces;
+	Slide m = ch_slide(a, world, ch, x_old + (v_in * pdt), v_in, pdt, true, dir, cfg.walk_stairs_cos_angle_forward_contact, s_orig[wib],
+					   s_leaf[wib], &s_nc[wib], err, lane);
+	for (int k = 1; k < pieces; k++)
+	{
+		const bool blocked = m.blocked;
+		m = ch_slide(a, world, ch, m.x + (m.v * pdt), m.v, pdt, true, dir, cfg.walk_stairs_cos_angle_forward_contact, s_orig[wib],
+					 s_leaf[wib], &s_nc[wib], err, lane);
+		m.blocked |= blocked;
+	}
 	v3 x = m.x, v = m.v;
 	uint32_t ground = m.ground, ground_body = m.ground_body;
 	v3 ground_n = m.ground_n;
@@ -479,8 +493,15 @@ __global__ void __launch_bounds__(128) k_character(CharArgs a)
 			const Deepest head = ch_deepest(a, world, up, hh, r, s_orig[wib], s_leaf[wib], &s_nc[wib], err);
 			if (!(head.pen > 0.0f))  // head room
 			{
-				const Slide f = ch_slide(a, world, ch, V(up.x + (dir.x * fwd), up.y, up.z + (dir.z * fwd)), v, false, dir, 2.0f, s_orig[wib],
-										 s_leaf[wib], &s_nc[wib], err, lane);
+				// the lifted move forward, swept like the move itself
+				int fp = (int)ceilf(fwd / (0.5f * r));
+				fp = fp < 1 ? 1 : (fp > CH_MAX_PIECES ? CH_MAX_PIECES : fp);
+				const float step = fwd / (float)fp;
+				Slide f = ch_slide(a, world, ch, V(up.x + (dir.x * step), up.y, up.z + (dir.z * step)), v, a.dt, false, dir, 2.0f, s_orig[wib],
+								   s_leaf[wib], &s_nc[wib], err, lane);
+				for (int k = 1; k < fp; k++)
+					f = ch_slide(a, world, ch, V(f.x.x + (dir.x * step), f.x.y, f.x.z + (dir.z * step)), f.v, a.dt, false, dir, 2.0f,
+								 s_orig[wib], s_leaf[wib], &s_nc[wib], err, lane);
 				const v3 adv = f.x - up;
 				// headway, and on the level: a push-out that lifted the capsule means the step is higher than step_up
 				if (((adv.x * dir.x) + (adv.z * dir.z)) > 1.0e-4f && fabsf(adv.y) <= 1.0e-3f)

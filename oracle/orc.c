@@ -2913,6 +2913,7 @@ float orc_overlap_capsule(const orc_world *w, const float center[3], float half_
  * direction `dir` (unit, horizontal) within the angle whose cosine is cos_fwd — what lets ExtendedUpdate try a stair
  * step. */
 typedef struct { v3 x, v, ground_n; uint32_t ground, ground_body; int blocked; } slide_t;
+#define CH_MAX_PIECES 16 /* pieces of one tick's move: 2 m per tick, 120 m/s */
 
 static slide_t ch_slide(orc_world *w, v3 x, v3 v, float dt, int push, v3 dir, float cos_fwd)
 {
@@ -2995,7 +2996,19 @@ void orc_character_update_ex(orc_world *w, float dt, const orc_character_setting
 	const v3 want = V(w->ch_v.x * dt, 0.0f, w->ch_v.z * dt);
 	const float want_len = sqrtf((want.x * want.x) + (want.z * want.z));
 	const v3 dir = want_len > 0.0f ? V(want.x / want_len, 0.0f, want.z / want_len) : V(0, 0, 0);
-	slide_t m = ch_slide(w, vadd(w->ch_x, vscale(w->ch_v, dt)), w->ch_v, dt, 1, dir, cfg->walk_stairs_cos_angle_forward_contact);
+	/* swept motion, restated on the discrete test: the move in pieces no longer than half the capsule's radius, each
+	 * collided and slid before the next, so that no floor or wall is stepped over (one piece up to 7.5 m/s) */
+	const float travel = vlen(vscale(w->ch_v, dt));
+	int pieces = (int)ceilf(travel / (0.5f * w->ch_r));
+	pieces = pieces < 1 ? 1 : (pieces > CH_MAX_PIECES ? CH_MAX_PIECES : pieces);
+	const float pdt = dt / (float)pieces;
+	slide_t m = ch_slide(w, vadd(w->ch_x, vscale(w->ch_v, pdt)), w->ch_v, pdt, 1, dir, cfg->walk_stairs_cos_angle_forward_contact);
+	for (int k = 1; k < pieces; k++)
+	{
+		const int blocked = m.blocked;
+		m = ch_slide(w, vadd(m.x, vscale(m.v, pdt)), m.v, pdt, 1, dir, cfg->walk_stairs_cos_angle_forward_contact);
+		m.blocked |= blocked;
+	}
 	v3 x = m.x, v = m.v;
 	uint32_t ground = m.ground, ground_body = m.ground_body;
 	v3 ground_n = m.ground_n;
@@ -3030,7 +3043,13 @@ void orc_character_update_ex(orc_world *w, float dt, const orc_character_setting
 			uint32_t hb;
 			if (!(ch_deepest(w, up, &n, &hb) > 0.0f)) /* head room */
 			{
-				const slide_t f = ch_slide(w, V(up.x + (dir.x * fwd), up.y, up.z + (dir.z * fwd)), v, dt, 0, dir, 2.0f);
+				/* the lifted move forward, swept like the move itself */
+				int fp = (int)ceilf(fwd / (0.5f * w->ch_r));
+				fp = fp < 1 ? 1 : (fp > CH_MAX_PIECES ? CH_MAX_PIECES : fp);
+				const float step = fwd / (float)fp;
+				slide_t f = ch_slide(w, V(up.x + (dir.x * step), up.y, up.z + (dir.z * step)), v, dt, 0, dir, 2.0f);
+				for (int k = 1; k < fp; k++)
+					f = ch_slide(w, V(f.x.x + (dir.x * step), f.x.y, f.x.z + (dir.z * step)), f.v, dt, 0, dir, 2.0f);
 				const v3 adv = vsub(f.x, up);
 				/* headway, and on the level: a push-out that lifted the capsule means the step is higher than step_up */
 				if (((adv.x * dir.x) + (adv.z * dir.z)) > 1.0e-4f && fabsf(adv.y) <= 1.0e-3f)

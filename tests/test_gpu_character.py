@@ -203,3 +203,27 @@ def test_extended_update_stairs_and_stick_to_floor_match_the_oracle(gpx, orc, he
         assert p[0] > 1.5 and abs(p[1] - (height + 0.45)) < 1e-3
     if height == 0.30:
         assert abs(p[0] - 0.75) < 1e-3
+
+
+def test_fast_moves_are_swept_like_the_oracles(gpx, orc):
+    """A tick's move longer than half the capsule radius is taken in pieces (swept motion): a fall at 40 m/s ends on the
+    floor, a run at 40 m/s ends at the wall, and every tick is the oracle's, bit for bit."""
+    from test_oracle import ENGINE_EXTENDED_UPDATE, stair_scene
+    g = gpx.World(worlds=1, max_bodies=8)
+    o = orc.World(8)
+    for side in (g, o):
+        side.add_mesh((0, 0, 0), stair_scene(3.0))
+        side.commit()
+        side.character_create((-2.0, 10.3, 0.0))
+    for tick in range(1, 31):
+        for side in (g, o):
+            side.character_set_velocity([0.0, -40.0, 0.0])
+            side.character_update(settings=ENGINE_EXTENDED_UPDATE)
+        _same(g, o, f"fall tick {tick}")
+    assert abs(o.character_get()[0][1] - 0.45) < 1e-3
+    for tick in range(1, 41):
+        for side in (g, o):
+            side.character_set_velocity([40.0, 0.0, 1.0])
+            side.character_update(settings=ENGINE_EXTENDED_UPDATE)
+        _same(g, o, f"run tick {tick}")
+    assert abs(o.character_get()[0][0] - 0.75) < 1e-3

@@ -490,6 +490,29 @@ def test_character_sticks_to_the_floor_when_walking_down_a_step(orc):
     assert airborne["extended"] == 0 and airborne["plain"] > 0
 
 
+def test_a_fast_character_does_not_pass_through_a_floor_or_a_wall(orc):
+    """Swept motion: at 40 m/s a tick's move (0.67 m) is longer than the capsule's radius; taken in one piece the centre
+    would land beyond a zero-thickness floor or wall and be pushed out on the far side.  The move is taken in pieces of
+    at most half a radius: the character lands on the floor (centre at half height + radius) and stops at the wall."""
+    o = orc.World(8)
+    o.add_mesh((0, 0, 0), stair_scene(3.0))           # floor y = 0, a 3 m wall at x = 1 facing -x
+    o.commit()
+    # falling: starts 10.3 m up so that, at 40 m/s, whole ticks would carry the centre from above the floor to below it
+    o.character_create((-2.0, 10.3, 0.0))
+    for _ in range(30):
+        o.character_set_velocity([0.0, -40.0, 0.0])
+        o.character_update()
+    p, _, ground, _ = o.character_get()
+    assert abs(p[1] - 0.45) < 1e-3 and ground == 0
+    # running at the wall
+    o.character_set_position([-3.05, 0.45, 0.0])
+    for _ in range(30):
+        o.character_set_velocity([40.0, 0.0, 0.0])
+        o.character_update()
+    p, _, ground, _ = o.character_get()
+    assert abs(p[0] - 0.75) < 1e-3 and abs(p[1] - 0.45) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ sphere casts
 
 def test_sphere_cast_known_answers(orc):
