@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 				j = jn;
 			}
 		}
+		tile.sync();  // the cached keys are overwritten below; a lane of another warp may still be matching against them
 		pc.mark(PH_MATCH);
 		// ---- 6: greedy colouring in canonical order (only dynamic bodies constrain a colour); active list.  The lanes
 		// classify the manifolds into one word each (solved or not, the slots of its dynamic bodies); lane 0 then walks
@@ -1042,7 +1043,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	static const char *force_tile = getenv("GPX_TILE");  // experiments: 8 / 16 / 32
 	const uint32_t forced = force_tile ? (uint32_t)atoi(force_tile) : 0u;
 	// worlds of more than 32 bodies: a block per world (one manifold per thread up to 256 manifolds)
-	static const bool no_block = getenv("GPX_NO_BLOCK_TILE") != nullptr;
+	const bool no_block = getenv("GPX_NO_BLOCK_TILE") != nullptr;  // read per launch: tests switch it
 	if (w->cap > 32 && !no_block && world_smem_bytes(256, w->cap, w->cap_m) <= 200u * 1024u) return launch_tick_t<256>(w, a, w->stream, w->W);
 	if (w->cap > 16 || forced == 32u || (!forced && w->W <= one_wave)) return launch_tick_t<32>(w, a, w->stream, w->W);
 	// Ensembles of small worlds: the narrow launch takes every world whose previous tick fitted its lanes, a 32-lane

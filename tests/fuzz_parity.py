@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Differential fuzzing of the CUDA tick against the CPU oracle: random scenes on a shipped map (boxes and spheres of
+random size, mass, friction, restitution and spin, kinematic movers, sensors, bodies that may or may not sleep), random
+host edits between ticks (create, destroy, set velocity / position, wake), both kernel families (worlds of up to 64
+bodies -> k_tick; more -> the wide kernels).  Every tick's transforms, velocities, sleep flags and contact events must be
+bit-identical.  Usage: python tests/fuzz_parity.py [first_seed] [seeds] [ticks]   (needs a GPU; test infrastructure)"""
+import importlib, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+gpx = importlib.import_module("c-game-engine_b200")
+scenes = importlib.import_module("c-game-engine_b200.scenes")
+import orc
+
+OFF = set(filter(None, os.environ.get("FUZZ_NO", "").split(",")))   # dofs, rest, spheres, kin, sensor, sleep, edits, spin
+ticks = 240
+
+
+def random_desc(rng, area):
+    kind = rng.integers(0, 10)
+    pos = (float(rng.uniform(-area, area)), float(rng.uniform(-1.0, 2.5)), float(rng.uniform(-area, area) - 1.5))
+    d = dict(position=pos, friction=float(rng.uniform(0.0, 1.0)), restitution=float(rng.choice([0.0, 0.0, 0.3, 0.8])),
+             mass=float(rng.uniform(0.5, 30.0)), allow_sleeping=int(rng.integers(0, 2)),
+             linear_velocity=tuple(float(v) for v in rng.uniform(-2, 2, 3)),
+             angular_velocity=tuple(float(v) for v in rng.uniform(-4, 4, 3)))
+    if "spheres" in OFF and 6 <= kind < 8:
+        kind = 0
+    if "kin" in OFF and kind == 8:
+        kind = 0
+    if "sensor" in OFF and kind == 9:
+        kind = 0
+    if "rest" in OFF:
+        d["restitution"] = 0.0
+    if "sleep" in OFF:
+        d["allow_sleeping"] = 0
+    if "spin" in OFF:
+        d["angular_velocity"] = (0.0, 0.0, 0.0)
+    if kind < 6:
+        d.update(shape=1, half_extents=tuple(float(v) for v in rng.uniform(0.08, 0.4, 3)))
+        a = rng.normal(size=4)
+        d.update(rotation=tuple(float(v) for v in (a / np.linalg.norm(a)).astype(np.float32)))
+    elif kind < 8:
+        d.update(shape=2, half_extents=(float(rng.uniform(0.08, 0.35)), 0.0, 0.0))
+    elif kind == 8:
+        d.update(shape=1, half_extents=(0.5, 0.05, 0.5), motion_type=1, angular_velocity=(0.0, 0.0, 0.0),
+                 linear_velocity=(float(rng.uniform(-0.4, 0.4)), 0.0, float(rng.uniform(-0.4, 0.4))))
+    else:
+        d.update(shape=1, half_extents=(0.4, 0.3, 0.4), layer=3, motion_type=0, is_sensor=1, linear_velocity=(0, 0, 0),
+                 angular_velocity=(0, 0, 0))
+    if rng.integers(0, 6) == 0 and "dofs" not in OFF:
+        d["allowed_dofs"] = int(rng.choice([0b010111, 0b111000 | 0b111, 0b000111]))
+    return d
+
+
+def compare(g, o, cap, live, what):
+    """state of the bodies that exist (a destroyed slot reads as zeros on one side and as its last state on the other)"""
+    assert g.sync() == 0
+    live = np.array(sorted(live), np.int64)
+    xg, vg = g.transforms()[0][live], g.velocities()[0][live]
+    xo, vo = o.state(cap)
+    xo, vo = xo[live], vo[live]
+    if not np.array_equal(xg.view(np.uint32), xo.view(np.uint32)):
+        bad = np.nonzero(np.any(xg.view(np.uint32) != xo.view(np.uint32), axis=1))[0]
+        raise AssertionError(f"{what}: transforms differ at bodies {live[bad[:8]]}: {xg[bad[0]]} vs {xo[bad[0]]}")
+    if not np.array_equal(vg.view(np.uint32), vo.view(np.uint32)):
+        bad = np.nonzero(np.any(vg.view(np.uint32) != vo.view(np.uint32), axis=1))[0]
+        sg, so = g.sleeping()[0][live], o.asleep(cap)[live]
+        raise AssertionError(f"{what}: velocities differ at bodies {live[bad[:8]]}: {vg[bad[0]]} vs {vo[bad[0]]}; asleep {sg[bad[0]]} vs {so[bad[0]]}; "
+                             f"transform {xg[bad[0]]}")
+    sg, so = g.sleeping()[0][live], o.asleep(cap)[live]
+    if not np.array_equal(sg, so):
+        raise AssertionError(f"{what}: sleep flags differ at {np.nonzero(sg != so)[0][:8]}")
+
+
+def run(seed):
+    rng = np.random.default_rng(seed)
+    wide = bool(seed & 1) if "FUZZ_CAP" not in os.environ else int(os.environ["FUZZ_CAP"]) > 64
+    cap = int(rng.integers(80, 200)) if wide else int(rng.integers(6, 65))
+    cap = int(os.environ.get("FUZZ_CAP", cap))
+    n0 = int(cap * rng.uniform(0.4, 0.9))
+    meshes = scenes.load_static("stacked")
+    g = gpx.World(worlds=1, max_bodies=cap)
+    o = orc.World(cap)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    area = 2.5 if wide else 1.5
+    live = []
+    for _ in range(n0):
+        d = random_desc(rng, area)
+        a, b = g.create(gpx.body_desc(**d)), o.create(orc.body_desc(**d))
+        assert a == b, (a, b)
+        live.append(a)
+    errors = 0
+    log = []
+    for tick in range(1, ticks + 1):
+        # host edits
+        for _ in range(int(rng.integers(0, 3)) if "edits" not in OFF else 0):
+            op = rng.integers(0, 5)
+            if op == 0 and len(live) < cap:
+                d = random_desc(rng, area)
+                a, b = g.create(gpx.body_desc(**d)), o.create(orc.body_desc(**d))
+                assert a == b, (a, b)
+                live.append(a)
+                log.append((tick, 'create', a, d))
+            elif op == 1 and len(live) > 2:
+                b = live.pop(int(rng.integers(0, len(live))))
+                g.destroy(b)
+                o.destroy(b)
+                log.append((tick, 'destroy', b))
+            elif op == 2 and live:
+                b = live[int(rng.integers(0, len(live)))]
+                v = tuple(float(x) for x in rng.uniform(-3, 3, 3))
+                w = tuple(float(x) for x in rng.uniform(-3, 3, 3))
+                g.set_velocity(b, v, w)
+                o.set_velocity(b, v, w)
+                log.append((tick, 'velocity', b, v, w))
+            elif op == 3 and live:
+                b = live[int(rng.integers(0, len(live)))]
+                p = (float(rng.uniform(-area, area)), float(rng.uniform(0.0, 2.5)), float(rng.uniform(-area, area) - 1.5))
+                g.set_position(b, p)      # JPH_Activation_Activate
+                o.set_position(b, p)
+                o.wake(b)
+                log.append((tick, 'position', b, p))
+        rg, ro = g.step(), o.step()
+        if rg != ro:
+            raise AssertionError(f"seed {seed} tick {tick}: step returned {rg} (gpu) vs {ro} (oracle)")
+        errors += rg != 0
+        eg, eo = g.poll_events(), o.events()
+        got = np.stack([eg["body_a"], eg["body_b"], eg["kind"]], axis=1) if len(eg) else np.zeros((0, 3), np.uint32)
+        if rg == 0 and not np.array_equal(got, eo):
+            raise AssertionError(f"seed {seed} tick {tick}: events differ\n{got}\n{eo}")
+        if tick % 4 == 0 or tick < 8 or os.environ.get("FUZZ_EVERY_TICK"):
+            try:
+                compare(g, o, cap, live, f"seed {seed} ({'wide' if wide else 'ensemble'}, cap {cap}) tick {tick}")
+            except AssertionError:
+                if os.environ.get("FUZZ_LOG"):
+                    for e in log[-12:]:
+                        print("edit", e)
+                raise
+    return wide, cap, len(live), errors
+
+
+if __name__ == "__main__":
+    first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    seeds = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    ticks = int(sys.argv[3]) if len(sys.argv) > 3 else 240
+    failed = 0
+    for seed in range(first, first + seeds):
+        try:
+            wide, cap, n, errors = run(seed)
+        except AssertionError as e:
+            failed += 1
+            print("FAILED", str(e)[:400], flush=True)
+            continue
+        print(f"seed {seed}: {'wide' if wide else 'ensemble'} cap {cap}, {n} bodies at the end, {ticks} ticks, "
+              f"{errors} ticks with a reported error code (same on both sides): identical", flush=True)
+    print(f"{seeds - failed} of {seeds} seeds identical")
+    sys.exit(1 if failed else 0)

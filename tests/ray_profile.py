@@ -1,3 +1,5 @@
+"""Timing of the ray batch on one GPU, device-resident and host-to-host, with a parity check against the oracle (test
+infrastructure: it lives under tests/ because it loads the oracle)."""
 import importlib, os, sys, numpy as np
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 gpx=importlib.import_module('c-game-engine_b200'); scenes=importlib.import_module('c-game-engine_b200.scenes')

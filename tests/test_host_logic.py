@@ -180,7 +180,7 @@ def test_two_rank_sharding_and_stats_gather_over_gloo(tmp_path):
 
 def test_hull_classifier_on_the_shipped_models(gpx, scenes):
     """gpx_shape_from_hull (host-side, no device): what CreateDynamicModelShape's convex hulls become in the body store
-    (engine/src/assets/ModelLoader.c:324-341).  Hull points decoded from assets/game/model/*.gmdl by tools/make_golden.py."""
+    (engine/src/assets/ModelLoader.c:324-341).  Hull points decoded from assets/game/model/*.gmdl by tests/golden/make_golden.py."""
     m = np.load(scenes.GOLDEN + "/models.npz")
     shape, he, c, exact = gpx.shape_from_hull(m["cube_hull_points"])
     assert shape == gpx.SHAPE_BOX and exact and np.allclose(he, 0.2, atol=1e-6) and np.allclose(c, 0, atol=1e-6)
@@ -205,7 +205,7 @@ def test_hull_classifier_on_the_shipped_models(gpx, scenes):
 
 def test_gmdl_collision_section_is_parsed_by_the_library(gpx, scenes):
     """gpx_model_load_gmdl(_container) (host-side, no device): the collision section of a .gmdl as ModelLoader.c:145-211
-    reads it.  The files are rebuilt from the hulls / triangles decoded from the shipped models (tools/make_golden.py),
+    reads it.  The files are rebuilt from the hulls / triangles decoded from the shipped models (tests/golden/make_golden.py),
     with render data that the parser has to skip (two materials, one skin, one LOD with vertices and indices)."""
     import struct
     import gasset

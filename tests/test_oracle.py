@@ -2,7 +2,7 @@
 
 The reference has no tests or golden files for this path and its Jolt dependency is not buildable here
 (PARITY UNPINNED, see oracle/orc.h and DESIGN.md), so the oracle is pinned by physics that has a closed form and by
-regression vectors generated with tools/make_golden.py.
+regression vectors generated with tests/golden/make_golden.py.
 """
 import numpy as np
 import pytest
