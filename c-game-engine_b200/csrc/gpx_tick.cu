@@ -1040,7 +1040,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
 	const uint32_t one_wave = (uint32_t)sms * 7u;
-	static const char *force_tile = getenv("GPX_TILE");  // experiments: 8 / 16 / 32
+	const char *force_tile = getenv("GPX_TILE");  // experiments and tests: 8 / 16 / 32 (read per launch)
 	const uint32_t forced = force_tile ? (uint32_t)atoi(force_tile) : 0u;
 	// worlds of more than 32 bodies: a block per world (one manifold per thread up to 256 manifolds)
 	const bool no_block = getenv("GPX_NO_BLOCK_TILE") != nullptr;  // read per launch: tests switch it

@@ -144,12 +144,91 @@ def run(seed):
     return wide, cap, len(live), errors
 
 
+def run_ensemble(seed, worlds, cap):
+    """Many small worlds in one gpx world (the benchmarked shape: narrow tiles, toppled worlds routed to the 32-lane
+    launch) against one oracle world each; random scenes per world, random edits in random worlds; state of every world
+    compared after every tick, contact events too."""
+    rng = np.random.default_rng(seed)
+    meshes = scenes.load_static("stacked")
+    g = gpx.World(worlds=worlds, max_bodies=cap)
+    os_ = [orc.World(cap) for _ in range(worlds)]
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        for o in os_:
+            o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    live = [[] for _ in range(worlds)]
+    for wi in range(worlds):
+        for _ in range(int(rng.integers(1, cap + 1))):
+            d = random_desc(rng, 1.2)
+            a, b = g.create(gpx.body_desc(**d), world=wi), os_[wi].create(orc.body_desc(**d))
+            assert a == b, (a, b)
+            live[wi].append(a)
+    for tick in range(1, ticks + 1):
+        for _ in range(int(rng.integers(0, 4)) if "edits" not in OFF else 0):
+            wi = int(rng.integers(0, worlds))
+            o = os_[wi]
+            op = rng.integers(0, 4)
+            if op == 0 and len(live[wi]) < cap:
+                d = random_desc(rng, 1.2)
+                a, b = g.create(gpx.body_desc(**d), world=wi), o.create(orc.body_desc(**d))
+                assert a == b, (a, b)
+                live[wi].append(a)
+            elif op == 1 and len(live[wi]) > 1:
+                b = live[wi].pop(int(rng.integers(0, len(live[wi]))))
+                g.destroy(b, world=wi)
+                o.destroy(b)
+            elif op == 2 and live[wi]:
+                b = live[wi][int(rng.integers(0, len(live[wi])))]
+                v = tuple(float(x) for x in rng.uniform(-3, 3, 3))
+                w = tuple(float(x) for x in rng.uniform(-3, 3, 3))
+                g.set_velocity(b, v, w, world=wi)
+                o.set_velocity(b, v, w)
+            elif op == 3 and live[wi]:
+                b = live[wi][int(rng.integers(0, len(live[wi])))]
+                p = (float(rng.uniform(-1.2, 1.2)), float(rng.uniform(0.0, 2.5)), float(rng.uniform(-1.2, 1.2) - 1.5))
+                g.set_position(b, p, world=wi)
+                o.set_position(b, p)
+                o.wake(b)
+        rg = g.step()
+        ro = 0
+        for o in os_:
+            ro |= o.step()
+        assert rg == ro, f"seed {seed} tick {tick}: step returned {rg} (gpu) vs {ro} (oracles)"
+        assert g.sync() == 0
+        xg, vg, sg = g.transforms(), g.velocities(), g.sleeping()
+        eg = g.poll_events()
+        for wi, o in enumerate(os_):
+            if not live[wi]:
+                continue
+            idx = np.array(sorted(live[wi]), np.int64)
+            xo, vo = o.state(cap)
+            what = f"seed {seed} ({worlds} worlds x {cap}) tick {tick} world {wi}"
+            assert np.array_equal(xg[wi][idx].view(np.uint32), xo[idx].view(np.uint32)), f"{what}: transforms differ"
+            assert np.array_equal(vg[wi][idx].view(np.uint32), vo[idx].view(np.uint32)), f"{what}: velocities differ"
+            assert np.array_equal(sg[wi][idx], o.asleep(cap)[idx]), f"{what}: sleep flags differ"
+            if rg == 0:
+                e = eg[eg["world"] == wi]
+                got = np.stack([e["body_a"], e["body_b"], e["kind"]], axis=1) if len(e) else np.zeros((0, 3), np.uint32)
+                assert np.array_equal(got, o.events()), f"{what}: events differ"
+    return sum(len(l) for l in live)
+
+
 if __name__ == "__main__":
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     seeds = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     ticks = int(sys.argv[3]) if len(sys.argv) > 3 else 240
     failed = 0
     for seed in range(first, first + seeds):
+        if os.environ.get("FUZZ_WORLDS"):
+            try:
+                n = run_ensemble(seed, int(os.environ["FUZZ_WORLDS"]), int(os.environ.get("FUZZ_CAP", 8)))
+                print(f"seed {seed}: {os.environ['FUZZ_WORLDS']} worlds, {n} bodies at the end, {ticks} ticks: identical", flush=True)
+            except AssertionError as e:
+                failed += 1
+                print("FAILED", str(e)[:400], flush=True)
+            continue
         try:
             wide, cap, n, errors = run(seed)
         except AssertionError as e:

@@ -33,3 +33,15 @@ def test_random_scenes_with_host_edits_match_the_oracle_every_tick(monkeypatch, 
     fz.ticks = 240
     for seed in seeds:
         fz.run(seed)
+
+
+@pytest.mark.parametrize("worlds,cap,tile", [(48, 8, "8"), (48, 8, "16"), (32, 16, "16"), (24, 8, "32")])
+def test_random_ensembles_match_one_oracle_world_each(monkeypatch, worlds, cap, tile):
+    """The benchmarked launch shape with random content: narrow tiles (four or two worlds per warp), worlds that outgrow
+    their lanes routed to the 32-lane launch, edits in random worlds; every world, every tick, events included."""
+    monkeypatch.setenv("GPX_TILE", tile)
+    monkeypatch.delenv("GPX_NO_BLOCK_TILE", raising=False)
+    fz = _fuzz()
+    fz.ticks = 160
+    for seed in (500, 501):
+        fz.run_ensemble(seed, worlds, cap)
