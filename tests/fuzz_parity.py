@@ -226,12 +226,127 @@ def run_ensemble(seed, worlds, cap):
     return sum(len(l) for l in live)
 
 
+def run_queries(seed):
+    """Rays and sphere casts against a random scene (a shipped map plus random bodies, some of which block lasers): random
+    origins inside the scene's bounds, random directions (a share of them axis-aligned), random lengths and layer masks;
+    ids, faces, fractions and cast normals must be the oracle's, bit for bit."""
+    rng = np.random.default_rng(seed)
+    name = ("stacked", "shapes", "test")[seed % 3]
+    meshes = scenes.load_static(name)
+    cap = 48
+    g = gpx.World(worlds=1, max_bodies=cap)
+    o = orc.World(cap)
+    lo, hi = np.full(3, 1e9), np.full(3, -1e9)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+        w = np.asarray(tris, np.float64).reshape(-1, 3) + np.asarray(pos, np.float64)
+        lo, hi = np.minimum(lo, w.min(axis=0)), np.maximum(hi, w.max(axis=0))
+    g.commit()
+    for _ in range(int(rng.integers(4, cap))):
+        d = random_desc(rng, 1.0)
+        d["position"] = tuple(float(v) for v in rng.uniform(lo, hi))
+        d["ray_flags"] = int(rng.integers(0, 2))
+        a, b = g.create(gpx.body_desc(**d)), o.create(orc.body_desc(**d))
+        assert a == b
+    for _ in range(int(rng.integers(0, 4))):     # let things move a little so that bodies are not where they were created
+        assert g.step() == 0 and o.step() == 0
+    n = 20000
+    rays = np.zeros(n, gpx.RAY_DTYPE)
+    rays["origin"] = rng.uniform(lo - 1.0, hi + 1.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    axis = rng.integers(0, 8, n) == 0
+    d[axis] = np.eye(3)[rng.integers(0, 3, axis.sum())] * rng.choice([-1.0, 1.0], (axis.sum(), 1))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["dir"] = d.astype(np.float32)
+    rays["tmax"] = rng.choice([0.5, 3.0, 20.0, 200.0], n).astype(np.float32)
+    rays["mask"] = rng.choice([1, 2, 3, 0xB, 0xF, 3 | (1 << 8), 0xF | (1 << 8)], n).astype(np.uint32)
+    hg, ho = g.raycast(rays), o.raycast(rays, mt=True)
+    for f in ("body", "face"):
+        assert np.array_equal(hg[f], ho[f]), f"seed {seed} ({name}): ray {f} differs at {np.nonzero(hg[f] != ho[f])[0][:5]}"
+    assert np.array_equal(hg["fraction"].view(np.uint32), ho["fraction"].view(np.uint32)), f"seed {seed} ({name}): ray fractions differ"
+    m = 4000
+    casts = np.zeros(m, gpx.CAST_DTYPE)
+    for f in ("origin", "dir", "tmax", "mask"):
+        casts[f] = rays[f][:m]
+    casts["mask"] &= 0xF
+    casts["radius"] = rng.choice([0.0, 0.05, 0.25, 0.6], m).astype(np.float32)
+    cg, co = g.spherecast(casts), o.spherecast(casts)
+    for f in ("body", "face"):
+        assert np.array_equal(cg[f], co[f]), f"seed {seed} ({name}): cast {f} differs at {np.nonzero(cg[f] != co[f])[0][:5]}"
+    assert np.array_equal(cg["fraction"].view(np.uint32), co["fraction"].view(np.uint32)), f"seed {seed} ({name}): cast fractions differ"
+    assert np.array_equal(cg["normal"].view(np.uint32), co["normal"].view(np.uint32)), f"seed {seed} ({name}): cast normals differ"
+    return name, int((hg["body"] != 0xFFFFFFFF).sum()), int((cg["body"] != 0xFFFFFFFF).sum())
+
+
+def run_character(seed):
+    """The player capsule on a shipped map among random bodies: a random walk (speed changes, jumps, the engine's
+    ExtendedUpdate settings or the plain update), the physics tick after every move as in the engine; position, velocity,
+    ground state, contact list and the bodies it pushes must be the oracle's after every tick."""
+    rng = np.random.default_rng(seed)
+    name = ("stacked", "test")[seed % 2]
+    meshes = scenes.load_static(name)
+    cap = 24
+    g = gpx.World(worlds=1, max_bodies=cap)
+    o = orc.World(cap)
+    for pos, tris in meshes:
+        g.add_mesh(pos, tris)
+        o.add_mesh(pos, tris)
+    g.commit()
+    start = (0.0, 0.5, -1.5) if name == "stacked" else (0.0, 1.0, 0.0)
+    for _ in range(int(rng.integers(2, cap))):
+        d = random_desc(rng, 1.5)
+        d["position"] = (start[0] + float(rng.uniform(-2, 2)), start[1] + float(rng.uniform(-0.5, 1.5)), start[2] + float(rng.uniform(-2, 2)))
+        a, b = g.create(gpx.body_desc(**d)), o.create(orc.body_desc(**d))
+        assert a == b
+    settings = (0.25, 0.25, 0.02, 0.15, float(np.cos(np.radians(75.0)))) if seed % 3 else None
+    for side in (g, o):
+        side.character_create(start)
+    vx = vz = 0.0
+    for tick in range(1, ticks + 1):
+        if rng.integers(0, 12) == 0:
+            speed = float(rng.choice([0.0, 1.5, 4.0, 9.0]))
+            ang = float(rng.uniform(0, 2 * np.pi))
+            vx, vz = speed * float(np.cos(ang)), speed * float(np.sin(ang))
+        jump = rng.integers(0, 40) == 0
+        for side in (g, o):
+            p, v, ground, _ = side.character_get()
+            vy = 0.0
+            if ground != 0:
+                vy = float(np.float32(v[1]) + np.float32(-9.81 / 60.0))
+            elif jump:
+                vy = 4.5
+            side.character_set_velocity((vx, vy, vz))
+            side.character_update(settings=settings)
+        assert g.step() == 0 and o.step() == 0
+        pg, vg, gg, bg = g.character_get()
+        po, vo, go, bo = o.character_get()
+        what = f"seed {seed} ({name}) tick {tick}"
+        assert np.array_equal(pg.view(np.uint32), po.view(np.uint32)), f"{what}: character position {pg} vs {po}"
+        assert np.array_equal(vg.view(np.uint32), vo.view(np.uint32)), f"{what}: character velocity {vg} vs {vo}"
+        assert (gg, bg) == (go, bo), f"{what}: ground {gg}/{bg:#x} vs {go}/{bo:#x}"
+        assert list(g.character_contacts()) == list(o.character_contacts()), f"{what}: contact lists differ"
+        assert g.sync() == 0
+        xo, vo_ = o.state(cap)
+        assert np.array_equal(g.transforms()[0].view(np.uint32), xo.view(np.uint32)), f"{what}: bodies differ"
+        assert np.array_equal(g.velocities()[0].view(np.uint32), vo_.view(np.uint32)), f"{what}: body velocities differ"
+    return name
+
+
 if __name__ == "__main__":
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     seeds = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     ticks = int(sys.argv[3]) if len(sys.argv) > 3 else 240
     failed = 0
     for seed in range(first, first + seeds):
+        if os.environ.get("FUZZ_MODE") in ("queries", "character"):
+            try:
+                r = run_queries(seed) if os.environ["FUZZ_MODE"] == "queries" else run_character(seed)
+                print(f"seed {seed}: {os.environ['FUZZ_MODE']} {r}: identical", flush=True)
+            except AssertionError as e:
+                failed += 1
+                print("FAILED", str(e)[:400], flush=True)
+            continue
         if os.environ.get("FUZZ_WORLDS"):
             try:
                 n = run_ensemble(seed, int(os.environ["FUZZ_WORLDS"]), int(os.environ.get("FUZZ_CAP", 8)))

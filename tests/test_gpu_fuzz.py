@@ -45,3 +45,21 @@ def test_random_ensembles_match_one_oracle_world_each(monkeypatch, worlds, cap, 
     fz.ticks = 160
     for seed in (500, 501):
         fz.run_ensemble(seed, worlds, cap)
+
+
+def test_random_rays_and_sphere_casts_match_the_oracle():
+    """20 000 random rays and 4000 sphere casts per scene (random origins, a share of axis-aligned directions, random
+    lengths, layer masks and radii) against a shipped map with random bodies: ids, faces, fractions, normals."""
+    fz = _fuzz()
+    for seed in (0, 1, 2):
+        fz.run_queries(seed)
+
+
+def test_random_character_walks_match_the_oracle(monkeypatch):
+    """The player capsule among random bodies on two shipped maps: random walk with speed changes and jumps, the tick after
+    every move; the character, its contact list and the bodies it pushes, every tick."""
+    monkeypatch.delenv("GPX_TILE", raising=False)
+    fz = _fuzz()
+    fz.ticks = 240
+    for seed in (1, 2, 4):
+        fz.run_character(seed)
