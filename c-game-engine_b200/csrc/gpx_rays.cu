@@ -297,38 +297,49 @@ __global__ void __launch_bounds__(RAY_THREADS_MAX) k_raycast(RayArgs a)
 // centre's ray entering a sphere of that radius around a vertex.  Boxes: six faces, twelve edges, eight corners in the
 // box's frame.  Same formulas, same order as the CPU restatement.
 
-// the centre's ray (o, unit d) against the cylinder of radius r around the segment p0 -> p1
+// the centre's ray (o, unit d) against the cylinder of radius r around the segment p0 -> p1 / the sphere around a vertex.
+// Both quadratics are solved from an origin advanced to just outside the feature's bounding sphere: with the cast's own
+// origin, tens of metres away, the terms that cancel are a million times the radius squared and fp32 leaves nothing of the
+// answer.  A solution whose contact point is not at the radius is refused.
+constexpr float SWEEP_RADIUS_TOL = 0.02f;
 __device__ __forceinline__ bool sweep_edge(v3 o, v3 d, float tmax, float r, v3 p0, v3 p1, float &best, v3 &n)
 {
-	const v3 ed = p1 - p0, m = o - p0;
-	const float ee = dot(ed, ed), md = dot(m, ed), dd = dot(d, ed);
+	const v3 ed = p1 - p0;
+	const float ee = dot(ed, ed);
+	const float t0 = fmaxf(0.0f, dot(madd(p0, ed, 0.5f) - o, d) - ((0.5f * sqrtf(ee)) + r));
+	const v3 o2 = madd(o, d, t0), m = o2 - p0;
+	const float md = dot(m, ed), dd = dot(d, ed);
 	const float a = ee - (dd * dd);
-	if (!(a > 1.0e-12f)) return false;
+	if (!(a > (1.0e-5f * ee))) return false;  // along the edge: the spheres around its ends cover it
 	const float k = dot(m, m) - (r * r);
 	const float c = (ee * k) - (md * md);
 	const float b = (ee * dot(m, d)) - (dd * md);
 	const float disc = (b * b) - (a * c);
 	if (disc < 0.0f) return false;
-	const float t = (-b - sqrtf(disc)) / a;
-	if (!(t >= 0.0f && t <= tmax && t < best)) return false;
+	const float t = (-b - sqrtf(disc)) / a, tt = t0 + t;
+	if (!(t >= 0.0f && tt <= tmax && tt < best)) return false;
 	const float s = md + (t * dd);
 	if (s < 0.0f || s > ee) return false;
-	const v3 q = madd(o, d, t) - madd(p0, ed, s / ee);
-	best = t;
+	const v3 q = madd(o2, d, t) - madd(p0, ed, s / ee);
+	if (fabsf(len2(q) - (r * r)) > (SWEEP_RADIUS_TOL * (r * r))) return false;
+	best = tt;
 	n = q * (1.0f / r);
 	return true;
 }
 
 __device__ __forceinline__ bool sweep_vertex(v3 o, v3 d, float tmax, float r, v3 p, float &best, v3 &n)
 {
-	const v3 m = o - p;
+	const float t0 = fmaxf(0.0f, dot(p - o, d) - r);
+	const v3 o2 = madd(o, d, t0), m = o2 - p;
 	const float b = dot(m, d), c = dot(m, m) - (r * r);
 	const float disc = (b * b) - c;
 	if (disc < 0.0f) return false;
-	const float t = -b - sqrtf(disc);
-	if (!(t >= 0.0f && t <= tmax && t < best)) return false;
-	best = t;
-	n = (madd(o, d, t) - p) * (1.0f / r);
+	const float t = -b - sqrtf(disc), tt = t0 + t;
+	if (!(t >= 0.0f && tt <= tmax && tt < best)) return false;
+	const v3 q = madd(o2, d, t) - p;
+	if (fabsf(len2(q) - (r * r)) > (SWEEP_RADIUS_TOL * (r * r))) return false;
+	best = tt;
+	n = q * (1.0f / r);
 	return true;
 }
 

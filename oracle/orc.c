@@ -528,37 +528,48 @@ typedef struct
 static v3 closest_on_tri(v3 p, v3 a, v3 b, v3 c);
 
 /* the centre's ray (o, unit d) against the cylinder of radius r around the segment p0 -> p1 */
+/* Both quadratics are solved from an origin advanced to just outside the feature's bounding sphere: with the cast's own
+ * origin, tens of metres away, the terms that cancel are a million times the radius squared and fp32 leaves nothing of the
+ * answer (false hits with "normals" of length 1.2).  A solution whose contact point is not at the radius is refused. */
+#define SWEEP_RADIUS_TOL 0.02f
 static int sweep_edge(v3 o, v3 d, float tmax, float r, v3 p0, v3 p1, float *best, v3 *n)
 {
-	const v3 ed = vsub(p1, p0), m = vsub(o, p0);
-	const float ee = vdot(ed, ed), md = vdot(m, ed), dd = vdot(d, ed);
+	const v3 ed = vsub(p1, p0);
+	const float ee = vdot(ed, ed);
+	const float t0 = fmaxf(0.0f, vdot(vsub(vmadd(p0, ed, 0.5f), o), d) - ((0.5f * sqrtf(ee)) + r));
+	const v3 o2 = vmadd(o, d, t0), m = vsub(o2, p0);
+	const float md = vdot(m, ed), dd = vdot(d, ed);
 	const float a = ee - (dd * dd);
-	if (!(a > 1.0e-12f)) return 0;
+	if (!(a > (1.0e-5f * ee))) return 0; /* along the edge: the spheres around its ends cover it */
 	const float k = vdot(m, m) - (r * r);
 	const float c = (ee * k) - (md * md);
 	const float b = (ee * vdot(m, d)) - (dd * md);
 	const float disc = (b * b) - (a * c);
 	if (disc < 0.0f) return 0;
-	const float t = (-b - sqrtf(disc)) / a;
-	if (!(t >= 0.0f && t <= tmax && t < *best)) return 0;
+	const float t = (-b - sqrtf(disc)) / a, tt = t0 + t;
+	if (!(t >= 0.0f && tt <= tmax && tt < *best)) return 0;
 	const float s = md + (t * dd);
 	if (s < 0.0f || s > ee) return 0;
-	const v3 q = vsub(vmadd(o, d, t), vmadd(p0, ed, s / ee));
-	*best = t;
+	const v3 q = vsub(vmadd(o2, d, t), vmadd(p0, ed, s / ee));
+	if (fabsf(vlen2(q) - (r * r)) > (SWEEP_RADIUS_TOL * (r * r))) return 0;
+	*best = tt;
 	*n = vscale(q, 1.0f / r);
 	return 1;
 }
 
 static int sweep_vertex(v3 o, v3 d, float tmax, float r, v3 p, float *best, v3 *n)
 {
-	const v3 m = vsub(o, p);
+	const float t0 = fmaxf(0.0f, vdot(vsub(p, o), d) - r);
+	const v3 o2 = vmadd(o, d, t0), m = vsub(o2, p);
 	const float b = vdot(m, d), c = vdot(m, m) - (r * r);
 	const float disc = (b * b) - c;
 	if (disc < 0.0f) return 0;
-	const float t = -b - sqrtf(disc);
-	if (!(t >= 0.0f && t <= tmax && t < *best)) return 0;
-	*best = t;
-	*n = vscale(vsub(vmadd(o, d, t), p), 1.0f / r);
+	const float t = -b - sqrtf(disc), tt = t0 + t;
+	if (!(t >= 0.0f && tt <= tmax && tt < *best)) return 0;
+	const v3 q = vsub(vmadd(o2, d, t), p);
+	if (fabsf(vlen2(q) - (r * r)) > (SWEEP_RADIUS_TOL * (r * r))) return 0;
+	*best = tt;
+	*n = vscale(q, 1.0f / r);
 	return 1;
 }
 
