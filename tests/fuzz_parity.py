@@ -169,7 +169,11 @@ def run_ensemble(seed, worlds, cap):
         for o in os_:
             o.add_mesh(pos, tris)
     g.commit()
-    g.enable_events()
+    events = True
+    try:
+        g.enable_events()
+    except gpx.GpxError:
+        events = False          # an ensemble of worlds of more than 64 bodies each reports no events
     live = [[] for _ in range(worlds)]
     for wi in range(worlds):
         for _ in range(int(rng.integers(1, cap + 1))):
@@ -210,7 +214,7 @@ def run_ensemble(seed, worlds, cap):
         assert rg == ro, f"seed {seed} tick {tick}: step returned {rg} (gpu) vs {ro} (oracles)"
         assert g.sync() == 0
         xg, vg, sg = g.transforms(), g.velocities(), g.sleeping()
-        eg = g.poll_events()
+        eg = g.poll_events() if events else None
         for wi, o in enumerate(os_):
             if not live[wi]:
                 continue
@@ -220,7 +224,7 @@ def run_ensemble(seed, worlds, cap):
             assert np.array_equal(xg[wi][idx].view(np.uint32), xo[idx].view(np.uint32)), f"{what}: transforms differ"
             assert np.array_equal(vg[wi][idx].view(np.uint32), vo[idx].view(np.uint32)), f"{what}: velocities differ"
             assert np.array_equal(sg[wi][idx], o.asleep(cap)[idx]), f"{what}: sleep flags differ"
-            if rg == 0:
+            if rg == 0 and events:
                 e = eg[eg["world"] == wi]
                 got = np.stack([e["body_a"], e["body_b"], e["kind"]], axis=1) if len(e) else np.zeros((0, 3), np.uint32)
                 assert np.array_equal(got, o.events()), f"{what}: events differ"

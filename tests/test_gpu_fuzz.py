@@ -6,6 +6,7 @@ bodies), a block per world (33..64 bodies — where this test found a missing ba
 colouring), the same worlds forced onto the warp tile with parked rows, and the wide-world kernels."""
 import importlib.util
 import os
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -63,3 +64,46 @@ def test_random_character_walks_match_the_oracle(monkeypatch):
     fz.ticks = 240
     for seed in (1, 2, 4):
         fz.run_character(seed)
+
+
+def test_gmap_loaders_survive_corrupted_input(gpx, scenes):
+    """Mutation fuzzing of the .gmap readers (decoded body and gzip container): flipped bytes, overwritten counts,
+    truncations, insertions.  A map is loaded or refused — and a world that refused a map still loads the intact one and
+    answers rays."""
+    import ctypes as C
+    import gasset
+    rng = np.random.default_rng(5)
+    blob = open(f"{scenes.GOLDEN}/stacked_min.gmap", "rb").read()
+    _, _, body = gasset.read_container(blob)
+    loaded = refused = 0
+    for data, container in ((body, False), (blob, True)):
+        for _ in range(120):
+            b = bytearray(data)
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif kind == 1:
+                at = int(rng.integers(0, max(1, len(b) - 8)))
+                b[at:at + 8] = (0, 1, 0xFFFFFFFF, 1 << 40, (1 << 64) - 1)[int(rng.integers(0, 5))].to_bytes(8, "little")
+            elif kind == 2:
+                b = b[:int(rng.integers(0, len(b)))]
+            else:
+                at = int(rng.integers(0, len(b)))
+                b[at:at] = bytes(int(rng.integers(1, 64)))
+            g = gpx.World(worlds=1, max_bodies=8)
+            buf = (C.c_uint8 * max(1, len(b))).from_buffer_copy(bytes(b) or b"\0")
+            fn = g.L.gpx_static_load_gmap_container if container else g.L.gpx_static_load_gmap
+            rc = fn(g.h, C.addressof(buf), len(b))
+            if rc >= 0:
+                loaded += 1
+                g.commit()
+            else:
+                refused += 1
+                assert g.load_gmap(body) == 10        # the intact map still loads into the same world
+                g.commit()
+                rays = np.zeros(1, gpx.RAY_DTYPE)
+                rays["origin"], rays["dir"], rays["tmax"], rays["mask"] = (0.0, 0.5, -1.5), (0.0, -1.0, 0.0), 10.0, 1
+                assert g.raycast(rays)["body"][0] != 0xFFFFFFFF
+            g.close()
+    assert loaded + refused == 240 and refused > 60

@@ -246,3 +246,41 @@ def test_gmdl_collision_section_is_parsed_by_the_library(gpx, scenes):
         gpx.model_collision(bytes(bad))
     with pytest.raises(gpx.GpxError):
         gpx.model_collision(cube[:40])
+
+
+def test_gmdl_parser_survives_corrupted_input(gpx, scenes):
+    """Mutation fuzzing of the host-side .gmdl reader (plain body and gzip container): flipped bytes, overwritten counts,
+    truncations.  Every outcome is either a parsed model or GPX_ERR_INVALID_ARG — never a crash, a hang or an allocation
+    sized by the file's say-so."""
+    import gasset
+    m = np.load(scenes.GOLDEN + "/models.npz")
+    n0 = int(m["leafy_hull_counts"][0])
+    pts = m["leafy_hull_points"]
+    bodies = [gasset.build_gmdl_body(2, m["cube_bb"][:3], m["cube_bb"][3:], hulls=[((0, 0, 0), m["cube_hull_points"])]),
+              gasset.build_gmdl_body(2, m["leafy_bb"][:3], m["leafy_bb"][3:], hulls=[((0, 0.5, 0), pts[:n0]), ((0, 0, 0), pts[n0:])]),
+              gasset.build_gmdl_body(1, m["laseremitter_bb"][:3], m["laseremitter_bb"][3:], tris=m["laseremitter_tris"])]
+    rng = np.random.default_rng(3)
+    parsed = refused = 0
+    for body in bodies:
+        blobs = [(body, False), (gasset.write_container(2, 1, body), True)]
+        for blob, container in blobs:
+            for _ in range(150):
+                b = bytearray(blob)
+                kind = rng.integers(0, 4)
+                if kind == 0:
+                    for _ in range(int(rng.integers(1, 6))):
+                        b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+                elif kind == 1:
+                    at = int(rng.integers(0, max(1, len(b) - 8)))
+                    b[at:at + 8] = (0, 1, 0xFFFFFFFF, 1 << 40, (1 << 64) - 1)[int(rng.integers(0, 5))].to_bytes(8, "little")
+                elif kind == 2:
+                    b = b[:int(rng.integers(0, len(b)))]
+                else:
+                    at = int(rng.integers(0, len(b)))
+                    b[at:at] = bytes(int(rng.integers(1, 64)))
+                try:
+                    gpx.model_collision(bytes(b), container=container)
+                    parsed += 1
+                except gpx.GpxError:
+                    refused += 1
+    assert parsed + refused == 900 and refused > 300
