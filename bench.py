@@ -404,6 +404,8 @@ def run_gpu(args):
                 cpu_wide_leg(orc, scenes, args, wide_res)
         if rays_res is not None:
             rays_res.pop("_check", None)
+        if wide_res is not None:
+            wide_res.pop("_x30", None)
         issue = measured_traffic("k_tick_inst_executed")
         line = {
             "metric": "body_steps_per_s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
@@ -587,6 +589,7 @@ def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
     for _ in range(30):           # let the lattice drop the 5-10 cm onto the floor / each other: contacts everywhere
         assert g.step() == 0
     assert g.sync() == 0
+    x30 = g.transforms()[0].copy() if rank == 0 else None   # checked against the CPU port's state after its 30 ticks
     L = gpx.lib()
     barrier()
     l0 = L.gpx_launch_count()
@@ -609,6 +612,8 @@ def bench_wide(gpx, scenes, args, device, rank, world_size, barrier, max_over_ra
            "roofline": {"bound": "hbm", "kernel": "wide tick (all kw_* kernels)", "achieved": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * BYTES_PER_BODY_STEP / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": measured_traffic("wide_tick")},
            "min_y": float(y.min())}
+    if x30 is not None:
+        res["_x30"] = x30
     return res
 
 
@@ -628,6 +633,10 @@ def cpu_wide_leg(orc, scenes, args, res):
         o.create(desc)
     for _ in range(30):
         o.step_mt()
+    x30 = res.pop("_x30", None)
+    if x30 is not None and len(x30) == len(sp):
+        res["sample_matches_oracle"] = bool(np.array_equal(o.state(len(sp))[0].view(np.uint32), x30.view(np.uint32)))
+        res["sample_check"] = "transforms of all 100 000 boxes after the 30 settling ticks vs the CPU port's, bit for bit"
     t0 = time.perf_counter()
     k = 0
     while (time.perf_counter() - t0 < args.cpu_seconds / 2 and k < 60) or k < 3:
