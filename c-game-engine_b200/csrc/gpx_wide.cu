@@ -40,7 +40,7 @@ namespace cg = cooperative_groups;
 
 namespace gpx {
 
-constexpr int WIDE_MAXADJ = 16;      // manifolds incident to one dynamic body
+constexpr int WIDE_MAXADJ = 32;      // manifolds incident to one dynamic body (a 128-byte row of the incidence table)
 constexpr int WIDE_MAXCOL = 64;
 constexpr uint32_t WT = 128;         // threads per block of the per-item kernels
 constexpr uint32_t NARROW_T = 64;    // threads per block of the narrowphase kernels (shared polygon scratch)

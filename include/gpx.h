@@ -29,7 +29,7 @@ enum gpx_error
 	GPX_ERR_MANIFOLD_CACHE_FULL = 1,
 	GPX_ERR_BODY_PAIR_CACHE_FULL = 2,
 	GPX_ERR_CONTACT_CONSTRAINTS_FULL = 4, /* more manifolds than max_manifolds_per_world — or, in a world of more than 64
-	                                       * bodies, more than 16 manifolds on one dynamic body; the tick goes on without
+	                                       * bodies, more than 32 manifolds on one dynamic body; the tick goes on without
 	                                       * the contacts that did not fit */
 	GPX_ERR_INVALID_ARG = 16,
 	GPX_ERR_CAPACITY = 17,

@@ -61,7 +61,7 @@ def compare(g, o, cap, live, what):
     """state of the bodies that exist (a destroyed slot reads as zeros on one side and as its last state on the other)"""
     rc = g.sync()
     if rc != 0:
-        raise CapacityError(f"{what}: the tick reported error code {rc} (a capacity of the device path, e.g. more than 16 "
+        raise CapacityError(f"{what}: the tick reported error code {rc} (a capacity of the device path, e.g. more than 32 "
                             "manifolds on one body of a wide world); nothing to compare from here on")
     live = np.array(sorted(live), np.int64)
     xg, vg = g.transforms()[0][live], g.velocities()[0][live]
