@@ -23,10 +23,10 @@ def _f(hexbits: str) -> np.float32:
     return np.array([int(hexbits, 16)], np.uint32).view(np.float32)[0]
 
 
-def _scene_file(path, scenes):
+def _scene_file(path, scenes, boxes=None):
     meshes = scenes.load_static("stacked")
     pts = np.load(os.path.join(scenes.GOLDEN, "models.npz"))["cube_hull_points"].astype(np.float32)
-    boxes = scenes.stack_positions(8).astype(np.float32)
+    boxes = scenes.stack_positions(8).astype(np.float32) if boxes is None else np.asarray(boxes, np.float32)
     with open(path, "wb") as f:
         f.write(struct.pack("<I", len(meshes)))
         for pos, tris in meshes:
@@ -173,6 +173,26 @@ def test_engine_call_sequence_through_the_shim_matches_the_oracle(orc, scenes, t
     door = {int(l.split()[1]): l.split() for l in got if l.startswith("X") and l.split()[2] == "door"}
     assert abs(_f(door[100][6]) - (-1.5 + 41 / 60)) < 1e-4                   # kinematic: 41 ticks at 1 m/s after tick 60
     assert _f(door[140][6]) == np.float32(-0.5)                            # snapped open by SetPosition at tick 120
+
+
+@pytest.mark.parametrize("seed,max_bodies", [(1, 64), (2, 64), (3, 128)])
+def test_shim_with_a_loose_pile_of_physboxes_matches_the_oracle(orc, scenes, tmp_path, seed, max_bodies):
+    """The same engine-style driver with the physboxes thrown in as a loose, overlapping pile next to the player instead of
+    the tidy column (boxes shove each other, the player, the door and the laser beams): every printed observation —
+    transforms, rays, character state, listener callbacks — line by line."""
+    import shim_build
+    driver = shim_build.build_driver()
+    rng = np.random.default_rng(seed)
+    boxes = np.stack([rng.uniform(-1.2, 1.2, 14), rng.uniform(-1.0, 1.5, 14), rng.uniform(-2.4, -0.4, 14)], axis=1)
+    meshes, boxes = _scene_file(tmp_path / "scene.bin", scenes, boxes)
+    env = dict(os.environ, GPX_MAX_BODIES=str(max_bodies))
+    r = subprocess.run([driver, str(tmp_path / "scene.bin"), str(TICKS)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, f"driver exit {r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    got = r.stdout.strip().splitlines()
+    want, _ = _oracle_run(orc, scenes, meshes, boxes, TICKS, max_bodies)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, f"line {i}: shim printed\n  {g}\noracle says\n  {w}"
+    assert len(got) == len(want)
 
 
 def test_shim_rejects_foreign_layer_tables_and_reports_inexact_shapes(tmp_path):
