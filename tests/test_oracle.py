@@ -425,6 +425,98 @@ def test_sliding_box_stops_at_the_coulomb_distance(orc, scenes, friction, v0):
     assert abs(float(xf[0, 2] - x0[2])) < 1.0e-4 and abs(float(xf[0, 4])) < 1.0e-4
 
 
+@pytest.mark.parametrize("mu_box,slides", [(0.01, True), (0.2, False)])
+def test_box_on_an_incline_slides_with_g_sin_minus_mu_g_cos_or_stays(orc, mu_box, slides):
+    """A 20 degree ramp (mesh friction 4.25, combined sqrt(f1 f2)): with mu = 0.206 < tan 20 the box accelerates down the
+    slope at g (sin - mu cos) (less the 0.05 linear damping), without tumbling; with mu = 0.92 it stays where it was put."""
+    th = np.radians(20.0)
+    c, s_ = float(np.cos(th)), float(np.sin(th))
+    # ramp: a 12 m x 4 m quad through the origin, descending along +x
+    a, b = np.array([-6 * c, 6 * s_, -2.0]), np.array([6 * c, -6 * s_, -2.0])
+    quad = np.array([[a, b, b + [0, 0, 4.0]], [b + [0, 0, 4.0], a + [0, 0, 4.0], a]], np.float32)
+    o = orc.World(8)
+    o.add_mesh((0, 0, 0), quad)
+    o.commit()
+    n = np.array([s_, c, 0.0])                      # the ramp's normal
+    half = np.sqrt(0.5 * (1 - c))                   # rotation about z by -20 degrees
+    start = (-4.0 * np.array([c, -s_, 0.0])) + n * 0.2
+    o.create(orc.body_desc(position=tuple(float(v) for v in start), rotation=(0.0, 0.0, -float(np.sin(th / 2)), float(np.cos(th / 2))),
+                           friction=mu_box, linear_velocity=(0.0, 0.0, 0.0)))
+    x0 = o.state(1)[0][0, :3].astype(np.float64)
+    for _ in range(60):
+        assert o.step() == 0
+    xf, vel = o.state(1)
+    along = np.array([c, -s_, 0.0])
+    moved = float((xf[0, :3] - x0) @ along)
+    mu = float(np.sqrt(mu_box * 4.25))
+    if slides:
+        acc = 9.81 * (s_ - mu * c)
+        # v' = acc - 0.05 v  =>  x(1) = acc / k (1 - (1 - exp(-k)) / k)
+        k = 0.05
+        want = acc / k * (1.0 - (1.0 - np.exp(-k)) / k)
+        assert abs(moved - want) < 0.03 * want, (moved, want)
+        assert abs(float(vel[0, :3] @ along) - acc / k * (1 - np.exp(-k))) < 0.03 * acc
+        assert np.abs(vel[0, 3:]).max() < 0.05                      # slides, does not tumble
+        assert abs(float((xf[0, :3] - x0) @ n)) < 2e-3              # stays on the ramp
+    else:
+        assert abs(moved) < 2e-3 and np.abs(vel).max() < 1e-3
+
+
+def test_restitution_returns_e_squared_of_the_drop_height(orc, scenes):
+    """A sphere with restitution 0.8 dropped 1 m onto the map floor (restitution is the larger of the two, 0.8) leaves it
+    with 0.8 of its impact speed and climbs back to 0.64 of the drop height, damping and the discrete contact apart."""
+    o = _stacked_world(orc, scenes)
+    floor_y = -1.5
+    o.create(orc.body_desc(shape=orc.SHAPE_SPHERE, half_extents=(0.2, 0, 0), position=(0.0, floor_y + 0.2 + 1.0, -1.5), restitution=0.8,
+                           linear_damping=0.0, angular_damping=0.0))
+    ys, vys = [], []
+    for _ in range(150):
+        assert o.step() == 0
+        x, v = o.state(1)
+        ys.append(float(x[0, 1]) - (floor_y + 0.2))
+        vys.append(float(v[0, 1]))
+    hit = int(np.argmax(np.array(vys) > 0))                     # first tick moving up again
+    v_in, v_out = -min(vys[:hit]), vys[hit]
+    assert abs(v_in - np.sqrt(2 * 9.81 * 1.0)) < 0.05 * v_in
+    assert abs(v_out / v_in - 0.8) < 0.03
+    apex = max(ys[hit:])
+    assert abs(apex - 0.64) < 0.05
+
+
+def test_free_spin_keeps_its_angular_velocity_as_jolt_does_without_gyroscopic_forces(orc):
+    """No gravity, no contacts, no damping: a spinning box keeps its world-frame angular velocity for ten seconds, about a
+    principal axis and about a skew one alike — Jolt's default (mApplyGyroscopicForce = false) integrates w without the
+    gyroscopic term, so for the skew spin it is w that is constant, not the angular momentum I w; the orientation stays a
+    unit quaternion."""
+    o = orc.World(8, gravity=(0.0, 0.0, 0.0))
+    he = (0.1, 0.2, 0.4)
+    o.create(orc.body_desc(position=(0, 0, 0), half_extents=he, angular_velocity=(0.0, 3.0, 0.0), linear_damping=0.0, angular_damping=0.0))
+    o.create(orc.body_desc(position=(5, 0, 0), half_extents=he, angular_velocity=(1.0, 2.0, 0.5), linear_damping=0.0, angular_damping=0.0))
+    m = 10.0
+    inertia = np.array([m / 3 * (he[1] ** 2 + he[2] ** 2), m / 3 * (he[0] ** 2 + he[2] ** 2), m / 3 * (he[0] ** 2 + he[1] ** 2)])
+
+    def momentum(xf, w):
+        q = xf[3:].astype(np.float64)
+        x, y, z, s = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * s), 2 * (x * z + y * s)],
+                      [2 * (x * y + z * s), 1 - 2 * (x * x + z * z), 2 * (y * z - x * s)],
+                      [2 * (x * z - y * s), 2 * (y * z + x * s), 1 - 2 * (x * x + y * y)]])
+        return R @ (inertia * (R.T @ w.astype(np.float64)))
+    xf, vel = o.state(2)
+    l0 = momentum(xf[1], vel[1, 3:])
+    w_first = vel[1, 3:].copy()
+    for _ in range(600):
+        assert o.step() == 0
+    xf, vel = o.state(2)
+    assert np.allclose(vel[0, 3:], (0.0, 3.0, 0.0), atol=1e-6)
+    l1 = momentum(xf[1], vel[1, 3:])
+    # Jolt (and this restatement) integrates w without the gyroscopic term: w stays constant in the world frame, so
+    # |L| is NOT conserved for a skew spin — what is pinned here is that documented behaviour
+    assert np.allclose(vel[1, 3:], w_first, atol=1e-6)
+    assert abs(np.linalg.norm(xf[1, 3:]) - 1.0) < 1e-5
+    assert np.linalg.norm(l1 - l0) > 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ stairs (ExtendedUpdate)
 
 ENGINE_EXTENDED_UPDATE = (0.25, 0.25, 0.02, 0.15, float(np.cos(np.radians(75.0))))  # PlayerPhysics.c:439-446
