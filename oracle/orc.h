@@ -16,7 +16,8 @@
  *   body parameters .......................... game/src/actor/prop/Physbox.c:19-38, engine/src/actor/Trigger.c:33-50 ...
  *   rays and their filters ................... engine/src/physics/PlayerPhysics.c:55-86,297-315, game/src/actor/prop/Laser.c:40-158
  * It is pinned instead by analytic known answers (tests/test_oracle.py): free fall with damping, resting contact height,
- * Moller-Trumbore and swept-sphere known hits, momentum conservation, Coulomb stopping distances, and the dissipation a
+ * Moller-Trumbore and swept-sphere known hits, momentum conservation, Coulomb stopping distances, the incline law,
+ * restitution, and the dissipation a
  * contact solver owes its user — a kicked 8-box column loses its kinetic energy monotonically (one-second windows), comes
  * to rest at the stacked heights and, with sleeping allowed, is asleep within five seconds.
  *
