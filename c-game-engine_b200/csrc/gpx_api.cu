@@ -140,6 +140,7 @@ static int flush_commands(gpx_world *w)
 	}
 	GPX_CUDA(cudaMemcpyAsync(w->d_cmd, w->pending.data(), sizeof(BodyCommand) * n, cudaMemcpyHostToDevice, w->stream));
 	int rc = launch_apply_commands(w, w->d_cmd, (uint32_t)n);
+	w->mirror_direct = false;  // the device state has moved on from what the last tick wrote into the mirror
 	// the staging vector is pageable: wait so it can be reused
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	w->pending.clear();
@@ -308,6 +309,12 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 	{
 		memset(w->mb_pos[k], 0, sizeof(float4) * (2 * nb + 1));
 		w->mb_quat[k] = w->mb_pos[k] + nb;  // the error word follows at [2 * nb]
+		if (k == 0 && !w->d_mirror_fresh && cudaMalloc(&w->d_mirror_fresh, w->W) == cudaSuccess) cudaMemset(w->d_mirror_fresh, 0, w->W);
+		void *dev = nullptr;
+		if (!getenv("GPX_NO_DIRECT_MIRROR") && w->d_mirror_fresh && cudaHostGetDevicePointer(&dev, w->mb_pos[k], 0) == cudaSuccess)
+			w->mb_dev[k] = reinterpret_cast<float4 *>(dev);
+		else
+			cudaGetLastError();
 	}
 	memset(w->m_lin, 0, sizeof(float4) * nb);
 	memset(w->m_ang, 0, sizeof(float4) * nb);
@@ -335,6 +342,7 @@ void gpx_world_destroy(gpx_world *w)
 	cudaFree(w->d_rays); cudaFree(w->d_hits); cudaFree(w->d_capq); cudaFree(w->d_capo); cudaFree(w->d_phase); cudaFree(w->d_cand); cudaFree(w->d_park);
 	cudaFree(w->d_ev_prev); cudaFree(w->d_ev_nprev); cudaFree(w->d_ev_count); cudaFree(w->d_ev_out);
 	cudaFree(w->d_ch); cudaFree(w->d_ch_keys); cudaFree(w->d_ch_nkeys);
+	cudaFree(w->d_mirror_fresh);
 	cudaFreeHost(w->mb_pos[0]); cudaFreeHost(w->mb_pos[1]); cudaFreeHost(w->m_lin); cudaFreeHost(w->m_ang); cudaFreeHost(w->m_err);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
@@ -993,6 +1001,8 @@ int gpx_step(gpx_world *w, float dt, int collision_steps)
 	if (w->static_dirty && (rc = build_static(w)) != GPX_OK) return rc;
 	if ((rc = flush_commands(w)) != GPX_OK) return rc;
 	if ((rc = (w->wide ? launch_wide_tick(w, dt, collision_steps) : launch_tick(w, dt, collision_steps))) != GPX_OK) return rc;
+	w->mirror_direct = !w->wide && w->mb_dev[0] && w->mb_dev[1] && w->synced_since_step;  // what launch_tick decided
+	w->synced_since_step = false;
 	// the sleep test runs once per tick, and only in worlds that hold a body allowed to sleep (wide worlds run theirs
 	// at the end of launch_wide_tick)
 	if (w->sleep_enabled && !w->wide && (rc = launch_sleep_test(w, dt)) != GPX_OK) return rc;
@@ -1021,15 +1031,21 @@ int gpx_sync_transforms(gpx_world *w)
 	if ((rc = join_hits(w)) != GPX_OK) return rc;
 	const size_t nb = (size_t)w->W * w->cap;
 	const uint32_t gen = w->mirror_gen.load(std::memory_order_relaxed), back = (gen + 1u) & 1u;
-	// positions | orientations | error word: one allocation on each side, one copy
-	GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, 2 * sizeof(float4) * nb + sizeof(uint32_t), cudaMemcpyDeviceToHost,
-							 w->stream));
+	if (w->mirror_direct)
+		// the tick wrote positions and orientations into the back buffer itself: only the error word is left
+		GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back] + 2 * nb, w->bs.pos + 2 * nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+	else
+		// positions | orientations | error word: one allocation on each side, one copy
+		GPX_CUDA(cudaMemcpyAsync(w->mb_pos[back], w->bs.pos, 2 * sizeof(float4) * nb + sizeof(uint32_t), cudaMemcpyDeviceToHost,
+								 w->stream));
 	// the error word has been read: the ticks after this synchronisation report their own errors (Jolt's Update returns
 	// each update's result); the per-world words d_err[1 + world] stay sticky for gpx_read_stats
 	GPX_CUDA(cudaMemsetAsync(w->d_err, 0, sizeof(uint32_t), w->stream));
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
 	w->m_err[0] = *reinterpret_cast<const uint32_t *>(w->mb_pos[back] + 2 * nb);
 	w->mirror_gen.store(gen + 1u, std::memory_order_release);  // the tick just read back becomes the front
+	w->mirror_direct = false;                                  // the next tick writes the other buffer
+	w->synced_since_step = true;
 	return (int)w->m_err[0];
 }
 

@@ -153,6 +153,15 @@ struct gpx_world
 	// transforms are double-buffered: a readback fills the back pair, then mirror_gen is bumped (front = mirror_gen & 1), so
 	// getters on other threads (render, LOD) never see a half-written tick
 	float4 *mb_pos[2] = {nullptr, nullptr}, *mb_quat[2] = {nullptr, nullptr};
+	// the same two buffers as the device sees them (nullptr: not mapped).  The ensemble tick writes each world's final
+	// positions and orientations straight into the back buffer as the world finishes, so gpx_sync_transforms has only the
+	// error word left to fetch; mirror_direct says the back buffer holds the state of the last thing enqueued.
+	float4 *mb_dev[2] = {nullptr, nullptr};
+	bool mirror_direct = false;
+	// direct writes cost the tick a few microseconds of bus traffic, so they are only asked for when the caller has been
+	// reading every tick back (the last step was followed by a synchronisation)
+	bool synced_since_step = false;
+	uint8_t *d_mirror_fresh = nullptr;  // per world: bit b = mirror buffer b holds the world's current state (kernel-written)
 	std::atomic<uint32_t> mirror_gen{0};
 	float4 *m_lin = nullptr, *m_ang = nullptr;
 	uint32_t *d_err = nullptr;  // [0] = OR of per-world tick errors

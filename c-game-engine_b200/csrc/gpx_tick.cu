@@ -59,6 +59,9 @@ struct TickArgs
 	const uint8_t *cur_flag;                 // this tick's flags as seen by BOTH launches (busy_flag is the narrow launch's)
 	uint32_t next_above;                     // a world that ends the tick with more manifolds than this is "busy"
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
+	float4 *host_pos, *host_quat;      // the host's back mirror buffer (mapped pinned memory), or nullptr
+	uint8_t *mirror_fresh;             // per world: which of the host's two mirror buffers hold its current state
+	uint32_t mirror_back;              // the buffer host_pos points into (0 / 1)
 	TickParams p;
 };
 
@@ -285,6 +288,17 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 		{
 			a.mc.count[world] = 0;
 			route_next(a, world, 0);
+		}
+		// the mirror's two buffers alternate: this one may be a tick older than the world's last change — once
+		if (a.host_pos && !((a.mirror_fresh[world] >> a.mirror_back) & 1u))
+		{
+			for (uint32_t i = lane; i < cap; i += TILE)
+			{
+				a.host_pos[g0 + i] = a.bs.pos[g0 + i];
+				a.host_quat[g0 + i] = a.bs.quat[g0 + i];
+			}
+			tile.sync();
+			if (lane == 0) a.mirror_fresh[world] |= (uint8_t)(1u << a.mirror_back);
 		}
 		return;
 	}
@@ -794,9 +808,17 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 		a.bs.quat[g0 + i] = make_float4(b.q.x, b.q.y, b.q.z, b.q.w);
 		a.bs.lin[g0 + i] = F4(b.v, 0.0f);
 		a.bs.ang[g0 + i] = F4(b.w, 0.0f);
+		if (a.host_pos)
+		{
+			// straight into the host's mirror: worlds finish at different times, so by the end of the launch most of
+			// this has already crossed the bus and the read-back copy is not needed
+			a.host_pos[g0 + i] = F4(b.x, 0.0f);
+			a.host_quat[g0 + i] = make_float4(b.q.x, b.q.y, b.q.z, b.q.w);
+		}
 	}
 	if (lane == 0)
 	{
+		if (a.mirror_fresh) a.mirror_fresh[world] = a.host_pos ? (uint8_t)(1u << a.mirror_back) : (uint8_t)0;
 		a.mc.count[world] = hdr[1];
 		route_next(a, world, hdr[1]);
 		if (hdr[3])
@@ -1016,6 +1038,14 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.ev_out = w->d_ev_out;
 	a.ev_count = w->d_ev_count;
 	a.con_park = w->d_park;
+	{
+		// the host's back mirror buffer (the one gpx_sync_transforms will publish next)
+		const uint32_t back = (w->mirror_gen.load(std::memory_order_relaxed) + 1u) & 1u;
+		a.host_pos = w->mb_dev[0] && w->mb_dev[1] && w->synced_since_step ? w->mb_dev[back] : nullptr;
+		a.host_quat = a.host_pos ? a.host_pos + (size_t)w->W * w->cap : nullptr;
+		a.mirror_fresh = w->d_mirror_fresh;
+		a.mirror_back = back;
+	}
 	a.p.worlds = w->W;
 	a.p.cap = w->cap;
 	a.p.cap_m = w->cap_m;
