@@ -1153,11 +1153,34 @@ static int raycast_pipelined(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_
 // One batch through the world's staging buffers.  The world's mutex is held from staging the rays to the last use of
 // the shared buffers (two threads casting on one world would otherwise overwrite each other's rays or hits, or free
 // buffers the other is about to launch with); the synchronous variant therefore also waits inside.
+// the device's view of a host buffer that is pinned and mapped (cudaMallocHost / cudaHostRegister), or nullptr
+static void *mapped_alias(const void *host)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, host) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async)
 {
 	std::lock_guard<std::mutex> lk(w->mu);
 	{
 		cudaSetDevice(w->device);
+		// Pinned, mapped host buffers: the kernel reads the rays and writes the hits across the bus itself — no staging
+		// copies, one launch; the bus carries both directions at once while the kernel traces.
+		static const bool no_zero_copy = getenv("GPX_NO_ZERO_COPY_RAYS") != nullptr;
+		void *zr = no_zero_copy ? nullptr : mapped_alias(rays), *zh = zr ? mapped_alias(hits) : nullptr;
+		if (zr && zh)
+		{
+			int rc = raycast_device_locked(w, zr, n, zh);
+			if (rc != GPX_OK || async) return rc;  // async: valid once the world's stream has passed this point
+			GPX_CUDA(cudaStreamSynchronize(w->stream));
+			return GPX_OK;
+		}
 		int jr = join_hits(w);  // the previous batch's hits leave d_hits before this one's kernel writes it
 		if (jr != GPX_OK) return jr;
 		if (n > w->ray_cap)
