@@ -298,7 +298,7 @@ gpx_world *gpx_world_create(const gpx_world_config *cfg)
 		 cudaMallocHost(&w->mb_pos[1], sizeof(float4) * (2 * nb + 1)) == cudaSuccess &&
 		 cudaMallocHost(&w->m_lin, sizeof(float4) * nb) == cudaSuccess &&
 		 cudaMallocHost(&w->m_ang, sizeof(float4) * nb) == cudaSuccess &&
-		 cudaMallocHost(&w->m_err, sizeof(uint32_t) * 4) == cudaSuccess;
+		 cudaMallocHost(&w->m_err, sizeof(uint32_t) * 4 + sizeof(gpx_ray) + sizeof(gpx_hit)) == cudaSuccess;  // + one ray, one hit
 	if (!ok)
 	{
 		set_error("gpx_world_create", cudaGetLastError());
@@ -1165,9 +1165,15 @@ static void *mapped_alias(const void *host)
 	return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+static int raycast_enqueue_locked(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async);
 static int raycast_enqueue(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async)
 {
 	std::lock_guard<std::mutex> lk(w->mu);
+	return raycast_enqueue_locked(w, rays, n, hits, async);
+}
+
+static int raycast_enqueue_locked(gpx_world *w, const gpx_ray *rays, uint64_t n, gpx_hit *hits, bool async)
+{
 	{
 		cudaSetDevice(w->device);
 		// Pinned, mapped host buffers: the kernel reads the rays and writes the hits across the bus itself — no staging
@@ -1244,7 +1250,16 @@ int gpx_raycast_transform(gpx_world *w, uint32_t world, const gpx_transform *ori
 	r.tmax = max_distance;
 	r.dir[0] = d.x; r.dir[1] = d.y; r.dir[2] = d.z;
 	r.mask = (mask & 0xFFFFu) | (world << 16);
-	return gpx_raycast_batch(w, &r, 1, out);
+	// the engine's one ray per call (crosshair, a laser): through the world's pinned scratch record, so that it takes the
+	// copy-free path — one launch and one synchronisation
+	std::lock_guard<std::mutex> lk(w->mu);
+	if (!w->m_err) return GPX_ERR_INVALID_ARG;
+	gpx_ray *pr = reinterpret_cast<gpx_ray *>(w->m_err + 4);
+	gpx_hit *ph = reinterpret_cast<gpx_hit *>(w->m_err + 4 + sizeof(gpx_ray) / sizeof(uint32_t));
+	*pr = r;
+	const int rc = raycast_enqueue_locked(w, pr, 1, ph, false);
+	if (rc == GPX_OK) *out = *ph;
+	return rc;
 }
 
 int gpx_spherecast_batch(gpx_world *w, const gpx_sphere_cast *casts, uint64_t n, gpx_cast_hit *hits)
