@@ -1413,10 +1413,9 @@ int gpx_character_set_linear_velocity(gpx_world *w, uint32_t world, const float 
 	if (!w || world >= w->W || !w->d_ch || !v) return GPX_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
-	int rc = char_fetch(w, world);
-	if (rc != GPX_OK) return rc;
-	w->h_ch[world].vx = v[0]; w->h_ch[world].vy = v[1]; w->h_ch[world].vz = v[2];
-	return char_upload(w, world);
+	// three floats into the record, in stream order; no read-back (the source is pageable: staged before the call returns)
+	GPX_CUDA(cudaMemcpyAsync(&w->d_ch[world].vx, v, 3 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+	return GPX_OK;
 }
 
 int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3])
@@ -1424,10 +1423,8 @@ int gpx_character_set_position(gpx_world *w, uint32_t world, const float p[3])
 	if (!w || world >= w->W || !w->d_ch || !p) return GPX_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
-	int rc = char_fetch(w, world);
-	if (rc != GPX_OK) return rc;
-	w->h_ch[world].px = p[0]; w->h_ch[world].py = p[1]; w->h_ch[world].pz = p[2];
-	return char_upload(w, world);
+	GPX_CUDA(cudaMemcpyAsync(&w->d_ch[world].px, p, 3 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+	return GPX_OK;
 }
 
 int gpx_character_update(gpx_world *w, float dt) { return gpx_character_update_ex(w, dt, nullptr); }
