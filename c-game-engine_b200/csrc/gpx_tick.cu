@@ -137,6 +137,9 @@ __device__ __forceinline__ void solve_one_per_lane(Tile &tile, int lane, SMan *m
 		F = R.f;
 		colour = m.colour;
 	}
+	// every lane has read the velocities its rows' restitution bias is made of before any lane's warm start changes them
+	// (the set-up of ALL manifolds precedes the first impulse)
+	tile.sync();
 	pc.mark(PH_SETUP);
 	for (int col = 0; col < ncol; col++)
 	{
@@ -1088,7 +1091,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.next_list = w->d_busy + (size_t)nxt * w->W;
 	a.next_count = w->d_busy_n + nxt;
 	a.next_flag = w->d_busy_flag + (size_t)nxt * w->W;
-	a.next_above = tile;
+	a.next_above = getenv("GPX_DEBUG_NO_ROUTE") ? 0x7FFFFFFFu : tile;  // debugging: nobody is ever handed to the 32-lane launch
 	a.cur_flag = w->d_busy_flag + (size_t)cur * w->W;
 	GPX_CUDA(cudaEventRecord(w->ev_fork, w->stream));
 	GPX_CUDA(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));

@@ -169,9 +169,10 @@ def run_ensemble(seed, worlds, cap):
         for o in os_:
             o.add_mesh(pos, tris)
     g.commit()
-    events = True
+    events = "events" not in OFF
     try:
-        g.enable_events()
+        if events:
+            g.enable_events()
     except gpx.GpxError:
         events = False          # an ensemble of worlds of more than 64 bodies each reports no events
     live = [[] for _ in range(worlds)]
@@ -221,7 +222,10 @@ def run_ensemble(seed, worlds, cap):
             idx = np.array(sorted(live[wi]), np.int64)
             xo, vo = o.state(cap)
             what = f"seed {seed} ({worlds} worlds x {cap}) tick {tick} world {wi}"
-            assert np.array_equal(xg[wi][idx].view(np.uint32), xo[idx].view(np.uint32)), f"{what}: transforms differ"
+            if not np.array_equal(xg[wi][idx].view(np.uint32), xo[idx].view(np.uint32)):
+                bad = idx[np.nonzero(np.any(xg[wi][idx].view(np.uint32) != xo[idx].view(np.uint32), axis=1))[0]]
+                raise AssertionError(f"{what}: transforms differ at bodies {bad[:6]} of {len(idx)}: {xg[wi][bad[0]]} vs {xo[bad[0]]}; "
+                                     f"manifolds {o.manifolds()}, stats {g.stats()[wi]}")
             assert np.array_equal(vg[wi][idx].view(np.uint32), vo[idx].view(np.uint32)), f"{what}: velocities differ"
             assert np.array_equal(sg[wi][idx], o.asleep(cap)[idx]), f"{what}: sleep flags differ"
             if rg == 0 and events:

@@ -48,6 +48,17 @@ def test_random_ensembles_match_one_oracle_world_each(monkeypatch, worlds, cap, 
         fz.run_ensemble(seed, worlds, cap)
 
 
+def test_restitution_bias_is_taken_before_any_warm_start(monkeypatch):
+    """Seed 6028, 64 worlds x 8 slots on 8-lane tiles: in world 27 a bouncy body's manifold read the velocity of a body
+    another lane had already warm-started (the row set-up of all manifolds precedes the first impulse; a barrier was
+    missing) — visible only when all four worlds of that warp were busy, at tick 107."""
+    monkeypatch.setenv("GPX_TILE", "8")
+    monkeypatch.delenv("GPX_NO_BLOCK_TILE", raising=False)
+    fz = _fuzz()
+    fz.ticks = 120
+    fz.run_ensemble(6028, 64, 8)
+
+
 def test_random_rays_and_sphere_casts_match_the_oracle():
     """20 000 random rays and 4000 sphere casts per scene (random origins, a share of axis-aligned directions, random
     lengths, layer masks and radii) against a shipped map with random bodies: ids, faces, fractions, normals."""
