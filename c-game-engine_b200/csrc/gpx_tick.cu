@@ -59,6 +59,7 @@ struct TickArgs
 	const uint8_t *cur_flag;                 // this tick's flags as seen by BOTH launches (busy_flag is the narrow launch's)
 	uint32_t next_above;                     // a world that ends the tick with more manifolds than this is "busy"
 	unsigned long long *phase_cycles;  // optional (gpx_debug_phase_cycles): SM cycles per phase summed over tiles' lane 0
+	uint32_t jitter;                   // debugging (GPX_DEBUG_JITTER): lanes leave every barrier after a random delay
 	float4 *host_pos, *host_quat;      // the host's back mirror buffer (mapped pinned memory), or nullptr
 	uint8_t *mirror_fresh;             // per world: which of the host's two mirror buffers hold its current state
 	uint32_t mirror_back;              // the buffer host_pos points into (0 / 1)
@@ -201,6 +202,38 @@ struct BlockTile
 	__device__ __forceinline__ bool any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
 };
 
+// (Builds with -DGPX_JITTER only.)  A world's lanes with a debugging switch on their barriers: with `jitter` set, every lane leaves every barrier after its
+// own pseudo-random delay (up to a microsecond), so lanes enter each phase staggered.  Code that needs a barrier it does
+// not have then fails under tests/fuzz_parity.py instead of once in fifty seeds; results must not change.
+template <typename Tile>
+struct JitterTile
+{
+	Tile t;
+	uint32_t jitter;
+	__device__ __forceinline__ int thread_rank() const { return (int)t.thread_rank(); }
+	__device__ __forceinline__ void delay() const
+	{
+		if (!jitter) return;
+		uint32_t h = (threadIdx.x * 2654435761u) ^ (uint32_t)clock64() ^ jitter;
+		h ^= h >> 13;
+		h *= 0x5BD1E995u;
+		h ^= h >> 15;
+		const long long until = clock64() + (long long)(h & 2047u);
+		while (clock64() < until) {}
+	}
+	__device__ __forceinline__ void sync() const
+	{
+		t.sync();
+		delay();
+	}
+	__device__ __forceinline__ bool any(bool p) const
+	{
+		const bool r = t.any(p);
+		delay();
+		return r;
+	}
+};
+
 template <int TILE>
 __device__ __forceinline__ auto make_tile()
 {
@@ -214,7 +247,12 @@ template <int TILE>
 __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+#ifdef GPX_JITTER  // make -C csrc clean && make -C csrc NVFLAGS_EXTRA=-DGPX_JITTER, then run with GPX_DEBUG_JITTER=1
+	auto raw_tile = make_tile<TILE>();
+	JitterTile<decltype(raw_tile)> tile{raw_tile, a.jitter};
+#else
 	auto tile = make_tile<TILE>();
+#endif
 	const int lane = tile.thread_rank();
 	const uint32_t tiles_per_block = blockDim.x / TILE;
 	const uint32_t slot = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
@@ -1041,6 +1079,7 @@ int launch_tick(gpx_world *w, float dt, int substeps)
 	a.ev_out = w->d_ev_out;
 	a.ev_count = w->d_ev_count;
 	a.con_park = w->d_park;
+	a.jitter = getenv("GPX_DEBUG_JITTER") ? 0x9E3779B9u + w->ticks : 0u;
 	{
 		// the host's back mirror buffer (the one gpx_sync_transforms will publish next)
 		const uint32_t back = (w->mirror_gen.load(std::memory_order_relaxed) + 1u) & 1u;
