@@ -1485,7 +1485,6 @@ int gpx_events_enable(gpx_world *w, int enable)
 	std::lock_guard<std::mutex> lk(w->mu);
 	cudaSetDevice(w->device);
 	GPX_CUDA(cudaStreamSynchronize(w->stream));
-	if (w->wide && w->W != 1) return GPX_ERR_INVALID_ARG;  // a wide ENSEMBLE keeps no per-world event lists
 	if (w->wide) return wide_events_enable(w, enable != 0);
 	if (enable && !w->d_ev_out)
 	{
@@ -1523,12 +1522,22 @@ int gpx_poll_events(gpx_world *w, gpx_contact_event *out, uint64_t capacity, uin
 		w->h_ev_out.resize(n);
 		if (n) GPX_CUDA(cudaMemcpyAsync(w->h_ev_out.data(), w->d_ev_out, sizeof(uint4) * n, cudaMemcpyDeviceToHost, w->stream));
 		GPX_CUDA(cudaStreamSynchronize(w->stream));
-		for (uint32_t k = 0; k < n && k < capacity; k++)
+		// the device lists all added / persisted pairs, then all removed ones, each sorted by global body index; the host's
+		// format is world after world, each with its added / persisted and then its removed pairs: a stable bucketing
+		std::vector<uint32_t> at((size_t)w->W + 1, 0u);
+		for (uint32_t k = 0; k < n; k++)
+			if (w->h_ev_out[k].w < w->W) at[w->h_ev_out[k].w + 1]++;
+		for (uint32_t wi = 0; wi < w->W; wi++) at[wi + 1] += at[wi];
+		for (uint32_t k = 0; k < n; k++)
 		{
-			out[k].world = 0;
-			out[k].body_a = w->h_ev_out[k].x;
-			out[k].body_b = w->h_ev_out[k].y;
-			out[k].kind = w->h_ev_out[k].z;
+			const uint4 ev = w->h_ev_out[k];
+			if (ev.w >= w->W) continue;
+			const uint32_t dst = at[ev.w]++;
+			if (dst >= capacity) continue;
+			out[dst].world = ev.w;
+			out[dst].body_a = ev.x;
+			out[dst].body_b = ev.y;
+			out[dst].kind = ev.z;
 		}
 		*count = n;
 		return n > capacity ? GPX_ERR_CAPACITY : GPX_OK;

@@ -1384,11 +1384,13 @@ __global__ void __launch_bounds__(WT) kw_sleep_apply(WideArgs a, const unsigned 
 // of the last sub-step — solver manifolds, sensor overlaps, the character's contacts — are sorted and made unique, then
 // compared with the previous tick's list by binary search.  Output order as in the ensemble kernel: added and
 // persisted pairs sorted by key, then the removed ones sorted by key.
+constexpr uint32_t EV_CHARACTER = 0x200000u;  // + world: the character's id inside the event keys (bodies < 2^20 < this < static ids)
 struct EvArgs
 {
 	const SMan *man;
 	const uint32_t *cnt;
 	uint32_t cap_m, n_ev;
+	uint32_t worlds, cap;  // an ensemble of wide worlds: body indices are world * cap + local
 	const unsigned long long *ch_keys;
 	const uint32_t *ch_nkeys;
 	unsigned long long *keys, *cur, *prev;
@@ -1405,9 +1407,43 @@ __global__ void __launch_bounds__(WT) kw_ev_keys(EvArgs e)
 	{
 		if (i < min(e.cnt[WC_NMAN], e.cap_m) && e.man[i].np > 0) key = ((unsigned long long)e.man[i].a << 32) | e.man[i].b;
 	}
-	else if (e.ch_keys && i - e.cap_m < min(e.ch_nkeys[0], (uint32_t)CHARACTER_MAX_CONTACTS))
-		key = e.ch_keys[i - e.cap_m];
+	else if (e.ch_keys)
+	{
+		// the characters' contacts, one block of 64 per world: (other << 32 | character).  With the body index made global
+		// and the character's pseudo id replaced by EV_CHARACTER + world — still between the bodies' ids and the static
+		// ones, so the order within a world is the one a single world has — the keys of different worlds stay apart.
+		const uint32_t j = i - e.cap_m, wi = j / CHARACTER_MAX_CONTACTS, slot = j % CHARACTER_MAX_CONTACTS;
+		if (wi < e.worlds && slot < min(e.ch_nkeys[wi], (uint32_t)CHARACTER_MAX_CONTACTS))
+		{
+			const unsigned long long k = e.ch_keys[(size_t)wi * CHARACTER_MAX_CONTACTS + slot];
+			// (body, character) for bodies, (character, static id) for the map's meshes
+			const uint32_t ka = (uint32_t)(k >> 32), kb = (uint32_t)(k & 0xFFFFFFFFull);
+			if (ka == CHARACTER_BODY_ID)
+				key = ((unsigned long long)(EV_CHARACTER + wi) << 32) | kb;
+			else
+				key = ((unsigned long long)(ka + wi * e.cap) << 32) | (EV_CHARACTER + wi);
+		}
+	}
 	e.keys[i] = key;
+}
+
+// a key of the lists above as the record the host reads: ids local to the world, the world in .w
+__device__ __forceinline__ uint4 ev_record(const EvArgs &e, unsigned long long k, uint32_t kind)
+{
+	uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)(k & 0xFFFFFFFFull), world = 0;
+	if (a >= EV_CHARACTER && a < STATIC_BODY_BASE)
+	{
+		world = a - EV_CHARACTER;  // (character, static id)
+		a = CHARACTER_BODY_ID;
+	}
+	else
+	{
+		world = a / e.cap;
+		a %= e.cap;
+		if (b >= EV_CHARACTER && b < STATIC_BODY_BASE) b = CHARACTER_BODY_ID;  // (body, character)
+		else if (b < STATIC_BODY_BASE) b %= e.cap;
+	}
+	return make_uint4(a, b, kind, world);
 }
 
 __global__ void __launch_bounds__(WT) kw_ev_unique(EvArgs e)
@@ -1449,7 +1485,7 @@ __global__ void __launch_bounds__(WT) kw_ev_diff(EvArgs e)
 	if (i < ncur)
 	{
 		const unsigned long long k = e.cur[i];
-		e.out[i] = make_uint4((uint32_t)(k >> 32), (uint32_t)(k & 0xFFFFFFFFull), ev_contains(e.prev, nprev, k) ? 2u : 1u, 0u);
+		e.out[i] = ev_record(e, k, ev_contains(e.prev, nprev, k) ? 2u : 1u);
 	}
 	const uint32_t gone = (i < nprev && !ev_contains(e.cur, ncur, e.prev[i])) ? 1u : 0u;
 	e.flag[i] = gone;
@@ -1464,7 +1500,7 @@ __global__ void __launch_bounds__(WT) kw_ev_removed(EvArgs e)
 	if (e.flag[i])
 	{
 		const unsigned long long k = e.prev[i];
-		e.out[ncur + e.pos[i]] = make_uint4((uint32_t)(k >> 32), (uint32_t)(k & 0xFFFFFFFFull), 3u, 0u);
+		e.out[ncur + e.pos[i]] = ev_record(e, k, 3u);
 	}
 	if (i == e.n_ev - 1) e.count[0] = ncur + e.pos[i] + e.flag[i];
 }
@@ -1552,7 +1588,7 @@ int wide_events_enable(gpx_world *w, bool enable)
 	WideDevice *d = w->wide;
 	if (enable && !d->ev_keys)
 	{
-		d->n_ev = ((d->cap_m + CHARACTER_MAX_CONTACTS + 1023u) / 1024u) * 1024u;
+		d->n_ev = ((d->cap_m + w->W * CHARACTER_MAX_CONTACTS + 1023u) / 1024u) * 1024u;
 		const bool ok = walloc(&d->ev_keys, d->n_ev) && walloc(&d->ev_tmp, d->n_ev) && walloc(&d->ev_cur, d->n_ev) &&
 						walloc(&d->ev_hist, (size_t)256 * (d->n_ev / 1024u + 1u)) && walloc(&d->ev_flag, d->n_ev) &&
 						walloc(&d->ev_pos, d->n_ev) && walloc(&d->ev_ncur, 1) && walloc(&w->d_ev_prev, d->n_ev) &&
@@ -1586,6 +1622,8 @@ static int wide_events(gpx_world *w, const SMan *man)
 	e.cnt = d->counters;
 	e.cap_m = d->cap_m;
 	e.n_ev = d->n_ev;
+	e.worlds = w->W;
+	e.cap = w->cap;
 	e.ch_keys = w->d_ch_keys;
 	e.ch_nkeys = w->d_ch_nkeys;
 	e.keys = d->ev_keys;

@@ -124,3 +124,55 @@ def test_wide_world_events_sensors_and_character_contacts(gpx, orc, scenes):
     assert np.array_equal(g.transforms()[0, :63].view(np.uint32), o.state(63)[0].view(np.uint32))
     pg, po = g.character_get(), o.character_get()
     assert np.array_equal(pg[0].view(np.uint32), po[0].view(np.uint32)) and pg[2:] == po[2:]
+
+
+def test_events_of_an_ensemble_of_wide_worlds(gpx, orc, scenes):
+    """Three worlds of 80 slots each (the wide kernels, bodies of all worlds in one array): every world has its own pile, a
+    sensor, a coin and a walking character; the event stream of each world, tick by tick, is its own oracle's."""
+    n, W = 80, 3
+    g = gpx.World(worlds=W, max_bodies=n)
+    os_ = [orc.World(n) for _ in range(W)]
+    for pos, tris in scenes.load_static("stacked"):
+        g.add_mesh(pos, tris)
+        for o in os_:
+            o.add_mesh(pos, tris)
+    g.commit()
+    g.enable_events()
+    for wi, o in enumerate(os_):
+        descs = []
+        for ix in range(3 + wi):
+            for k in range(3):
+                descs.append(dict(position=(-1.2 + 0.8 * ix, -1.25 + 0.43 * k, -2.6 + 0.3 * wi)))
+        descs.append(dict(position=(0.3, 0.6, 0.8)))
+        descs.append(dict(half_extents=(0.5, 0.15, 0.5), position=(0.3, -0.2, 0.8), layer=3, motion_type=0, is_sensor=1))
+        descs.append(dict(half_extents=(0.25, 0.25, 0.25), position=(0.0, -1.25, 1.6 - 0.2 * wi), layer=3, motion_type=0, is_sensor=1))
+        for d in descs:
+            assert g.create(gpx.body_desc(**d), world=wi) == o.create(orc.body_desc(**d))
+        g.character_create((0.0, -0.9, 2.6), world=wi)
+        o.character_create((0.0, -0.9, 2.6))
+    kinds = [set() for _ in range(W)]
+    for tick in range(1, 121):
+        for wi, o in enumerate(os_):
+            p, vel, ground, _ = o.character_get()
+            vy = 0.0 if ground == 0 else float(vel[1]) + (-9.81 / 60.0)
+            v = (0.0, vy, (-1.5 - 0.3 * wi) if tick > 20 else 0.0)
+            o.character_set_velocity(v)
+            g.character_set_velocity(v, world=wi)
+            o.character_update()
+        g.character_update()
+        assert g.step() == 0
+        for o in os_:
+            assert o.step() == 0
+        eg = g.poll_events()
+        for wi, o in enumerate(os_):
+            e = eg[eg["world"] == wi]
+            got = np.stack([e["body_a"], e["body_b"], e["kind"]], axis=1) if len(e) else np.zeros((0, 3), np.uint32)
+            eo = o.events()
+            assert np.array_equal(got, eo), f"tick {tick} world {wi}: {len(got)} vs {len(eo)} events\n{got[:6]}\n{eo[:6]}"
+            kinds[wi] |= {int(k) for k in got[:, 2]}
+            pg, vg, gg, bg = g.character_get(world=wi)
+            po, vo, go, bo = o.character_get()
+            assert np.array_equal(pg.view(np.uint32), po.view(np.uint32)) and (gg, bg) == (go, bo)
+        # the worlds' records come world after world
+        assert np.all(np.diff(eg["world"].astype(np.int64)) >= 0)
+    assert all(k == {1, 2, 3} for k in kinds)
