@@ -144,7 +144,7 @@ def _oracle_run(orc, scenes, meshes, boxes, ticks, max_bodies=64):
     return out, dict(coin=coin, door=door, boxes=box_ids, first_map=first_map)
 
 
-@pytest.mark.parametrize("max_bodies", [64, 128], ids=["ensemble-kernel world", "wide-world kernels"])
+@pytest.mark.parametrize("max_bodies", [64, 128, 10240], ids=["ensemble-kernel world", "wide-world kernels", "joltc default capacity"])
 def test_engine_call_sequence_through_the_shim_matches_the_oracle(orc, scenes, tmp_path, max_bodies):
     """The same engine-style run twice: in the default 64-slot world (the fused ensemble kernel) and, with
     GPX_MAX_BODIES=128, in a wide world (sort-and-sweep, islands, per-tick event kernels) against the oracle's wide mode."""
@@ -152,6 +152,8 @@ def test_engine_call_sequence_through_the_shim_matches_the_oracle(orc, scenes, t
     driver = shim_build.build_driver()
     meshes, boxes = _scene_file(tmp_path / "scene.bin", scenes)
     env = dict(os.environ, GPX_MAX_BODIES=str(max_bodies))
+    if max_bodies == 10240:
+        env.pop("GPX_MAX_BODIES")       # what the shim does when nobody says anything: joltc's default of 10240 bodies
     r = subprocess.run([driver, str(tmp_path / "scene.bin"), str(TICKS)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, f"driver exit {r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     got = r.stdout.strip().splitlines()
