@@ -1,9 +1,25 @@
 #!/usr/bin/env python
-"""Differential fuzzing of the CUDA tick against the CPU oracle: random scenes on a shipped map (boxes and spheres of
-random size, mass, friction, restitution and spin, kinematic movers, sensors, bodies that may or may not sleep), random
-host edits between ticks (create, destroy, set velocity / position, wake), both kernel families (worlds of up to 64
-bodies -> k_tick; more -> the wide kernels).  Every tick's transforms, velocities, sleep flags and contact events must be
-bit-identical.  Usage: python tests/fuzz_parity.py [first_seed] [seeds] [ticks]   (needs a GPU; test infrastructure)"""
+"""Differential fuzzing of the CUDA path against the CPU oracle (needs a GPU; test infrastructure).
+
+  python tests/fuzz_parity.py [first_seed] [seeds] [ticks]
+
+Modes (environment):
+  default              one world per seed: random boxes and spheres (size, mass, friction, restitution, orientation, spin),
+                       kinematic movers, sensors, restricted degrees of freedom, bodies that may or may not sleep, and random
+                       host edits between ticks (create, destroy, set velocity, set position).  Even seeds: up to 64 body
+                       slots (k_tick); odd seeds: 80..200 (the wide kernels).  FUZZ_CAP=<n> fixes the slot count.
+  FUZZ_WORLDS=<w>      an ensemble of w such worlds in one gpx world against one oracle world each (FUZZ_CAP slots, default 8);
+                       with GPX_TILE=8|16|32 the narrow tiles and their routing of toppled worlds are forced.
+  FUZZ_MODE=queries    20 000 rays and 4000 sphere casts against a shipped map with random bodies.
+  FUZZ_MODE=character  the player capsule on a random walk (speed changes, jumps, ExtendedUpdate settings) among random bodies.
+  FUZZ_NO=a,b,...      switch features off: dofs, rest, spheres, kin, sensor, sleep, edits, spin, events.
+  FUZZ_EVERY_TICK=1    compare after every tick (default: every fourth).   FUZZ_LOG=1  print the last edits on a mismatch.
+
+Transforms, velocities, sleep flags and contact events (ids, faces, fractions, normals for the queries; position, velocity,
+ground state and contact list for the character) must be bit-identical.  A scene that overflows a capacity of the device
+path (reported through the tick's error code) ends its seed: the oracle has no such limits.
+tests/test_gpu_fuzz.py runs a slice of every mode; GPX_NO_BLOCK_TILE, GPX_TILE and a -DGPX_JITTER build of the library
+(README) widen what a run exercises."""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
