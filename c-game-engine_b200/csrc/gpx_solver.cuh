@@ -34,7 +34,7 @@ struct SMan  // 41 words (odd stride): a contact manifold between narrowphase, s
 	v3 p1l[4], p2l[4];
 	float ln[4];  // accumulated non-penetration impulse per point
 	float cf[3];  // accumulated friction impulse of the manifold: tangent 1, tangent 2 (through the centroid), twist about n
-	float pad;
+	uint32_t tri;  // against a static body: the triangle that opened this manifold's slot (part of the warm-start key); else 0
 };
 
 // One constraint row: the velocity it measures is Jv = (axis . va + a1 . wa) - (axis . vb + a2 . wb); an impulse d along it
@@ -739,6 +739,7 @@ struct StaticSlot
 	v3 n;
 	float depth, friction;
 	uint32_t sbody;
+	uint32_t tri;  // the triangle that opened the slot
 	int np;
 	v3 p1[8], p2[8];
 };
@@ -800,6 +801,7 @@ __device__ __forceinline__ int body_static_contacts(const StaticView &sv, uint4 
 			slots[s].depth = hit.depth;
 			slots[s].friction = sqrtf(A.friction * TC.w);
 			slots[s].sbody = sbody;
+			slots[s].tri = (uint32_t)cand_orig[c];
 			slots[s].np = 0;
 		}
 		else if (hit.depth > slots[s].depth)

@@ -94,7 +94,7 @@ struct PhaseClock
 __host__ __device__ inline size_t world_scratch_bytes(uint32_t tile, uint32_t cap_m)
 {
 	// also: (cap_m + 64) 8-byte keys for the contact-event pass at the end of the tick
-	size_t a = (sizeof(Scratch) > sizeof(FricRows) ? sizeof(Scratch) : sizeof(FricRows)) * tile, b = sizeof(uint32_t) * 3 * cap_m,
+	size_t a = (sizeof(Scratch) > sizeof(FricRows) ? sizeof(Scratch) : sizeof(FricRows)) * tile, b = sizeof(uint32_t) * 4 * cap_m,
 		   c = 8u * ((size_t)cap_m + CHARACTER_MAX_CONTACTS);
 	if (c > b) b = c;
 	return ((a > b ? a : b) + 15u) & ~(size_t)15u;
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 	uint32_t *pkey_a = reinterpret_cast<uint32_t *>(scratch_raw);
 	uint32_t *pkey_b = pkey_a + cap_m;
 	uint32_t *pkey_np = pkey_b + cap_m;
+	uint32_t *pkey_tri = pkey_np + cap_m;
 	uint32_t *cnt_static = reinterpret_cast<uint32_t *>(scratch_raw + world_scratch_bytes(TILE, cap_m));
 	uint32_t *slot_base = cnt_static + cap;
 	uint32_t *hdr = slot_base + cap;  // 0 nman, 1 nprev, 2 ncol, 3 err, 4 npairs, 5 nact
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 					SMan &m = man[slot];
 					m.a = i;
 					m.b = STATIC_BODY_BASE + slots[s].sbody;
+					m.tri = slots[s].tri;
 					m.n = slots[s].n;
 					m.friction = slots[s].friction;
 					m.restitution = A.restitution;
@@ -521,6 +523,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 			m.a = ia;
 			m.b = ib;
 			m.np = 0;
+			m.tri = 0;
 			pair_contact(A, B, scratch, m);
 			const uint32_t fa = A.flags, fb = B.flags;
 			if (((fa | fb) & BF_ASLEEP) && m.np > 0 && !((fa | fb) & BF_SENSOR))
@@ -542,6 +545,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 			pkey_a[i] = k.x;
 			pkey_b[i] = k.y;
 			pkey_np[i] = k.z;
+			pkey_tri[i] = k.w;
 		}
 		tile.sync();
 		for (uint32_t mi0 = 0; mi0 < nman; mi0 += TILE)
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 			int j0 = -1, nmatch = 0;
 			for (uint32_t j = 0; j < nprev; j++)
 			{
-				const bool hit = live && pkey_a[j] == m.a && pkey_b[j] == m.b;
+				const bool hit = live && pkey_a[j] == m.a && pkey_b[j] == m.b && pkey_tri[j] == m.tri;
 				if (hit && j0 < 0) j0 = (int)j;
 				nmatch += hit ? 1 : 0;
 			}
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 				int jn = -1;
 				if (nmatch > 0)
 					for (uint32_t jj = (uint32_t)j + 1; jj < nprev; jj++)
-						if (pkey_a[jj] == m.a && pkey_b[jj] == m.b)
+						if (pkey_a[jj] == m.a && pkey_b[jj] == m.b && pkey_tri[jj] == m.tri)
 						{
 							jn = (int)jj;
 							break;
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(TILE > 128 ? TILE : 128) k_tick(TickArgs a)
 		for (uint32_t k = lane; k < nact; k += TILE)
 		{
 			const SMan &m = man[act[k]];
-			__stcg(&a.mc.key[m0 + k], make_uint4(m.a, m.b, (uint32_t)m.np, 0u));
+			__stcg(&a.mc.key[m0 + k], make_uint4(m.a, m.b, (uint32_t)m.np, m.tri));
 #pragma unroll
 			for (int p = 0; p < 4; p++)
 			{

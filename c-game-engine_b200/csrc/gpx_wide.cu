@@ -418,6 +418,7 @@ __device__ __forceinline__ void sweep_test(WideArgs &a, float4 lo_p, float4 hi_p
 	m.a = p_first ? ip : iq;
 	m.b = p_first ? iq : ip;
 	m.np = 0;
+	m.tri = 0;
 	m.colour = -2;
 	a.ord[k] = 0;
 }
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(NARROW_T) kw_static(WideArgs a)
 		SMan &m = a.man[k];
 		m.a = i;
 		m.b = STATIC_BODY_BASE + slots[s].sbody;
+		m.tri = slots[s].tri;
 		m.colour = -2;
 		m.n = slots[s].n;
 		m.friction = slots[s].friction;
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(WT) kw_link(WideArgs a)
 		const int j = hash_find(a, man_key(m.a, m.b, o));
 		if (j < 0) break;
 		const SMan &old = a.prev[j];
+		if (old.tri != m.tri) continue;  // another slot of the same static body (the wall next to the floor)
 		for (int p = 0; p < m.np; p++)
 		{
 			if (m.ln[p] != 0.0f) continue;

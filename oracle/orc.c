@@ -105,6 +105,8 @@ typedef struct
 	rows_t rows;
 	int colour;
 	uint32_t ord;  /* ordinal among the manifolds of the same (a, b): 0 for body pairs, slot index for static bodies */
+	uint32_t tri;  /* static bodies: the triangle that opened this manifold's slot — what keeps the warm start of a box's
+	                * floor manifold and of its wall manifold (same body pair, contact points a hair apart) from feeding each other */
 	uint32_t prio; /* colouring priority (mode 1) */
 } manifold_t;
 
@@ -1511,6 +1513,7 @@ static void find_contacts_among(orc_world *w, int *err, const uint64_t *cand, co
 					slots[s] = m;
 					snp[s] = 0;
 					m->ord = (uint32_t)s;
+					m->tri = t;
 				}
 				else if (h.depth > slots[s]->depth)
 				{
@@ -1623,7 +1626,7 @@ static void warm_start_match_range(orc_world *w, const uint32_t *run, uint32_t l
 		for (uint32_t j = run[m->a]; j < run[m->a + 1]; j++)
 		{
 			const manifold_t *o = &w->prev[j];
-			if (o->b != m->b) continue;
+			if (o->b != m->b || o->tri != m->tri) continue;
 			for (int p = 0; p < m->np; p++)
 			{
 				if (m->ln[p] != 0.0f) continue;

@@ -25,7 +25,8 @@
  * section 3 has the measurements): friction is solved per MANIFOLD (two tangent rows through the centroid of the contact
  * points plus one twist row about the normal, limited by friction x the manifold's total normal impulse) instead of per
  * contact point, and the non-penetration rows of a manifold are swept forwards in even iterations and backwards in odd
- * ones instead of always in the same order.
+ * ones instead of always in the same order.  Manifolds against a static mesh are cached per (body, mesh, triangle that
+ * opened the manifold's slot), the nearest equivalent here of Jolt's sub-shape-pair key.
  *
  * Plain C, single precision, compiled with -ffp-contract=off so that every expression rounds exactly like the
  * CUDA build (-fmad=false).  Algorithms here are deliberately the naive ones (all-pairs broadphase — above 256 bodies

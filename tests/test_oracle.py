@@ -706,3 +706,44 @@ def test_threaded_step_reproduces_the_serial_step(orc, scenes):
             assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32)), f"{kind} tick {tick}"
             assert np.array_equal(va.view(np.uint32), vb.view(np.uint32)), f"{kind} tick {tick}"
         assert contacts > 100
+
+
+def test_floor_and_wall_manifolds_of_one_body_do_not_feed_each_other(orc, scenes):
+    """Fuzz seed 40275 on the CPU: a thin plate knocked into the corner between the floor and a sloping wall of
+    stacked.gmap has two manifolds against the SAME static body whose contact points lie a hair apart.  Matching the
+    warm start by body pair and point distance alone let each manifold pick up the other's impulses, sub-step after
+    sub-step (2.4e6, 2.7e6, 3.4e6 ...), until the plate left at 38 km/s with a NaN orientation — on the GPU and here
+    alike.  The slot's opening triangle is part of the key now (Jolt keys its cache by sub-shape pair)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(__file__), "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(40275)
+    cap = int(rng.integers(80, 200))
+    n0 = int(cap * rng.uniform(0.4, 0.9))
+    o = orc.World(cap)
+    for pos, tris in scenes.load_static("stacked"):
+        o.add_mesh(pos, tris)
+    area = 2.5 * max(1.0, (cap / 150.0) ** 0.5)
+    live = []
+    for _ in range(n0):
+        live.append(o.create(orc.body_desc(**fz.random_desc(rng, area))))
+    for tick in range(1, 221):
+        for _ in range(int(rng.integers(0, 3))):
+            op = rng.integers(0, 5)
+            if op == 0 and len(live) < cap:
+                live.append(o.create(orc.body_desc(**fz.random_desc(rng, area))))
+            elif op == 1 and len(live) > 2:
+                o.destroy(live.pop(int(rng.integers(0, len(live)))))
+            elif op == 2 and live:
+                b = live[int(rng.integers(0, len(live)))]
+                o.set_velocity(b, tuple(float(x) for x in rng.uniform(-3, 3, 3)), tuple(float(x) for x in rng.uniform(-3, 3, 3)))
+            elif op == 3 and live:
+                b = live[int(rng.integers(0, len(live)))]
+                o.set_position(b, (float(rng.uniform(-area, area)), float(rng.uniform(0.0, 2.5)), float(rng.uniform(-area, area) - 1.5)))
+                o.wake(b)
+        assert o.step() == 0
+        x, v = o.state(cap)
+        assert np.isfinite(x[live]).all() and np.isfinite(v[live]).all(), f"tick {tick}"
+        assert np.abs(v[live][:, :3]).max() < 60.0, f"tick {tick}: {np.abs(v[live][:, :3]).max()} m/s"
