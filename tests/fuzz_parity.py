@@ -276,6 +276,9 @@ def run_queries(seed):
         assert a == b
     for _ in range(int(rng.integers(0, 4))):     # let things move a little so that bodies are not where they were created
         assert g.step() == 0 and o.step() == 0
+    rc = g.sync()
+    if rc != 0:
+        raise CapacityError(f"seed {seed} ({name}): a tick reported error code {rc} (bodies spawned inside each other)")
     m = 4000
     n = 20000
     rays = np.zeros(n, gpx.RAY_DTYPE)
