@@ -118,3 +118,15 @@ def test_gmap_loaders_survive_corrupted_input(gpx, scenes):
                 assert g.raycast(rays)["body"][0] != 0xFFFFFFFF
             g.close()
     assert loaded + refused == 240 and refused > 60
+
+
+def test_plate_wedged_between_floor_and_wall_stays_identical_and_finite(monkeypatch):
+    """Fuzz seed 40275 (a wide world of 161 slots): the scene in which a box's floor and wall manifolds used to feed each
+    other's warm start until the box left with a NaN orientation — bit-identical to the oracle through that tick, and the
+    oracle's own test (tests/test_oracle.py) says it stays finite."""
+    monkeypatch.delenv("FUZZ_CAP", raising=False)
+    monkeypatch.delenv("GPX_TILE", raising=False)
+    monkeypatch.setenv("FUZZ_EVERY_TICK", "1")
+    fz = _fuzz()
+    fz.ticks = 220
+    fz.run(40275)
